@@ -1,0 +1,101 @@
+"""ctypes binding of libctl_b200.so (the C ABI declared in include/ctl_b200.h).
+
+The library is built in-tree by ``csrc/build.sh`` (``__graft_entry__.build()``); it is NOT
+optional: there is no CPU or PyTorch fallback behind any compute entry point, and a missing
+library or a non-sm_100 device raises here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libctl_b200.so")
+
+CTL_DIST_EUCLIDEAN = 0
+CTL_DIST_COSINE = 1
+CTL_FLAG_NORMALIZE = 2
+
+_ERRORS = {
+    -1: ValueError,   # CTL_ERR_INVALID_ARGUMENT
+    -2: RuntimeError,  # CTL_ERR_WORKSPACE
+    -3: NotImplementedError,  # CTL_ERR_UNSUPPORTED
+    -4: OverflowError,  # CTL_ERR_CAPACITY
+    -5: RuntimeError,  # CTL_ERR_NO_DEVICE
+}
+
+_p = C.c_void_p
+_i64 = C.c_int64
+_i32 = C.c_int32
+_sz = C.c_size_t
+
+# name -> (restype, argtypes); kept in one table so tests can check it against the header
+SIGNATURES = {
+    "ctl_last_error": (C.c_char_p, []),
+    "ctl_abi_version": (C.c_int, []),
+    "ctl_device_check": (C.c_int, []),
+    "ctl_planes_bytes": (_sz, [_i64, _i32]),
+    "ctl_planes_build": (C.c_int, [_p, _i64, _i32, _i32, _p, _p]),
+    "ctl_dist_matrix": (C.c_int, [_p, _i64, _p, _i64, _i32, _i32, _p, _i64, _p]),
+    "ctl_topk_workspace_bytes": (_sz, [_i64, _i64, _i32]),
+    "ctl_l2_topk": (C.c_int, [_p, _i64, _p, _i64, _i32, _i32, _i32, _i64, _p, _p, _p, _p, _sz, _p]),
+    "ctl_eval_collect": (C.c_int, [_p, _i64, _p, _i64, _i32, _i32, _p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p]),
+    "ctl_sort_key_rows": (C.c_int, [_p, _p, _i64, _i32, _p]),
+    "ctl_eval_count": (C.c_int, [_p, _i64, _p, _i64, _i32, _i32, _p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p]),
+    "ctl_eval_finalize": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p]),
+    "ctl_key_encode": (C.c_uint64, [C.c_float, C.c_uint32]),
+    "ctl_key_decode": (None, [C.c_uint64, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
+    "ctl_segment_mean": (C.c_int, [_p, _i64, _i32, _p, _p, _i64, _p, _p]),
+}
+
+_lib = None
+
+
+def lib():
+    """Loads the shared library once; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(centroids-reid_b200 has no CPU / PyTorch fallback)"
+            )
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name, None)
+            if fn is None:
+                continue  # symbol checks live in tests/test_abi.py
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int):
+    if rc == 0:
+        return
+    msg = lib().ctl_last_error().decode("utf-8", "replace")
+    if rc < 0:
+        raise _ERRORS.get(rc, RuntimeError)(f"ctl_b200 error {rc}: {msg}")
+    raise RuntimeError(f"ctl_b200 CUDA error {rc}: {msg}")
+
+
+def require_cuda(*tensors: torch.Tensor):
+    """North-star contract: non-CUDA tensors raise, nothing silently runs on the host."""
+    for t in tensors:
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise RuntimeError(
+                "centroids-reid_b200 computes on a B200 only: expected CUDA tensors "
+                f"(got {type(t).__name__}{'' if not isinstance(t, torch.Tensor) else ' on ' + str(t.device)})"
+            )
+    check(lib().ctl_device_check())
+
+
+def ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream

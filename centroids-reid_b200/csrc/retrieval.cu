@@ -1,0 +1,796 @@
+// Query x gallery distances on 5th-gen tensor cores with streamed top-k / CMC / mAP epilogues.
+//
+// Replaces utils/reid_metric.py:25-33,51-59,112-136, utils/eval_reid.py:25-92 and
+// inference/get_similar.py:104-128 of the reference (see include/ctl_b200.h).
+//
+// Arithmetic.  The reference computes q.g in fp32.  Here every fp32 row x is split exactly as
+//     x * s = hi + 2^-11 * lo        (s: per-row power of two, hi/lo: fp16)
+// and q.g = (hi_q.hi_g + 2^-11 (hi_q.lo_g + lo_q.hi_g)) / (s_q s_g): three fp16 tcgen05.mma
+// passes with fp32 accumulation into TWO TMEM accumulators (the 2^-11 terms never get swamped
+// by the leading term).  Dropped: 2^-22 lo.lo -- i.e. >= 22 significant bits per product,
+// fp32-equivalent, and EXACT whenever the operands have <= 11 significant bits (the
+// dyadic-grid fixtures on which rank parity is asserted bit-exact).
+//
+// One persistent CTA per SM, 6 warps: TMA producer / MMA issuer / 4 epilogue warps; 3-stage
+// smem ring of {q_hi, q_lo, g_hi, g_lo} 128x64 fp16 tiles (SWIZZLE_128B), double-buffered TMEM
+// accumulators (2 x (128 + 128) columns) so the epilogue of tile i overlaps the MMAs of i+1.
+#include <math_constants.h>
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.h"
+#include "umma.cuh"
+
+namespace ctl {
+
+static constexpr int BM = 128;      // queries per tile (TMEM lanes)
+static constexpr int BN = 128;      // gallery rows per tile (TMEM columns per accumulator)
+static constexpr int BK = 64;       // fp16 elements per k-block = one 128-byte swizzle row
+static constexpr int STAGES = 3;
+static constexpr int TILE_BYTES = BM * BK * 2;          // 16 KiB
+static constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // q_hi, q_lo, g_hi, g_lo
+static constexpr int GEMM_THREADS = 192;
+static constexpr int GROUP_W = 16;                      // columns per group-min
+static constexpr size_t GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+// ---------------------------------------------------------------------------------------
+// (distance, index) keys: ascending uint64 order == ascending (distance, index)
+// ---------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t float_orderable(float f) {
+#ifdef __CUDA_ARCH__
+  uint32_t b = __float_as_uint(f);
+#else
+  uint32_t b;
+  memcpy(&b, &f, 4);
+#endif
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float orderable_float(uint32_t u) {
+  uint32_t b = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(b);
+#else
+  float f;
+  memcpy(&f, &b, 4);
+  return f;
+#endif
+}
+__host__ __device__ __forceinline__ uint64_t make_key(float d, uint32_t idx) {
+  return (static_cast<uint64_t>(float_orderable(d)) << 32) | idx;
+}
+
+// ---------------------------------------------------------------------------------------
+// planes layout
+// ---------------------------------------------------------------------------------------
+struct PlanesView {
+  const __half* hi;
+  const __half* lo;
+  const float* sq;
+  const float* inv_scale;
+};
+static size_t planes_off_lo(int64_t n, int32_t d) { return ((size_t)n * d * 2 + 255) & ~size_t(255); }
+static size_t planes_off_sq(int64_t n, int32_t d) { return 2 * planes_off_lo(n, d); }
+static size_t planes_off_is(int64_t n, int32_t d) { return planes_off_sq(n, d) + (((size_t)n * 4 + 255) & ~size_t(255)); }
+static size_t planes_total(int64_t n, int32_t d) { return planes_off_is(n, d) + (((size_t)n * 4 + 255) & ~size_t(255)); }
+static PlanesView planes_view(const void* p, int64_t n, int32_t d) {
+  const char* c = static_cast<const char*>(p);
+  PlanesView v;
+  v.hi = reinterpret_cast<const __half*>(c);
+  v.lo = reinterpret_cast<const __half*>(c + planes_off_lo(n, d));
+  v.sq = reinterpret_cast<const float*>(c + planes_off_sq(n, d));
+  v.inv_scale = reinterpret_cast<const float*>(c + planes_off_is(n, d));
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// One warp per row.  n_norm sequential L2 normalisations x <- x / max(|x|, 1e-12)
+// (F.normalize, reid_metric.py:113-115; cosine_similarity, reid_metric.py:43-46), then the
+// exact hi/lo split and the fp32 squared norm of the (normalised) row.
+__global__ void __launch_bounds__(128) planes_build_kernel(const float* __restrict__ x, int64_t n, int d, int n_norm,
+                                                           __half* __restrict__ hi, __half* __restrict__ lo,
+                                                           float* __restrict__ sq, float* __restrict__ inv_scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float* xr = x + row * d;
+  float denom[2] = {1.f, 1.f};
+  for (int t = 0; t < n_norm; ++t) {
+    float ss = 0.f;
+    for (int i = lane; i < d; i += 32) {
+      float v = xr[i];
+      if (t > 0) v = __fdiv_rn(v, denom[0]);
+      ss = __fmaf_rn(v, v, ss);
+    }
+    ss = warp_sum(ss);
+    denom[t] = fmaxf(__fsqrt_rn(ss), 1e-12f);
+  }
+  float ss = 0.f, mx = 0.f;
+  for (int i = lane; i < d; i += 32) {
+    float v = xr[i];
+    if (n_norm > 0) v = __fdiv_rn(v, denom[0]);
+    if (n_norm > 1) v = __fdiv_rn(v, denom[1]);
+    ss = __fmaf_rn(v, v, ss);
+    mx = fmaxf(mx, fabsf(v));
+  }
+  ss = warp_sum(ss);
+  mx = warp_max(mx);
+  int sexp = 0;
+  if (mx > 0.f && mx < CUDART_INF_F) {
+    int e;
+    frexpf(mx, &e);            // mx = m * 2^e, m in [0.5, 1)
+    sexp = min(14 - e, 120);   // mx * 2^sexp in [2^13, 2^14)
+  }
+  const float scale = scalbnf(1.f, sexp);
+  for (int i = lane; i < d; i += 32) {
+    float v = xr[i];
+    if (n_norm > 0) v = __fdiv_rn(v, denom[0]);
+    if (n_norm > 1) v = __fdiv_rn(v, denom[1]);
+    const float vs = v * scale;  // exact (power of two)
+    const __half h = __float2half_rn(vs);
+    const float r = vs - __half2float(h);  // exact remainder
+    hi[row * d + i] = h;
+    lo[row * d + i] = __float2half_rn(r * 2048.f);
+  }
+  if (lane == 0) {
+    sq[row] = ss;
+    inv_scale[row] = scalbnf(1.f, -sexp);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// the GEMM pass
+// ---------------------------------------------------------------------------------------
+struct GemmPass {
+  int nq, ng, d;
+  int m_tiles, n_tiles;
+  int cosine;
+  long long g_off;
+  const float* q_sq;
+  const float* q_is;
+  const float* g_sq;
+  const float* g_is;
+  // full matrix
+  float* dist_out;
+  long long ld_out;
+  // group minima (pass A of top-k)
+  float* gmin;
+  int n_groups;
+  // candidates <= tau (pass B of top-k)
+  const float* tau;
+  unsigned long long* cand_keys;
+  int* cand_count;
+  int cand_cap;
+  // identities (eval)
+  const int* q_pid;
+  const int* q_cam;
+  const int* g_pid;
+  const unsigned long long* g_mask;
+  unsigned long long* pos_keys;  // collect
+  int* pos_count;
+  int max_pos;
+  const unsigned long long* thr_keys;  // count
+  const int* thr_count;
+  int* buckets;
+  int* overflow;
+};
+
+struct GemmMaps {
+  CUtensorMap q_hi, q_lo, g_hi, g_lo;
+};
+
+// The ONE place a distance is formed from the accumulators: every pass must produce
+// bit-identical values for the same (query, gallery) pair.
+__device__ __forceinline__ float dist_from_acc(float acc0, float acc1, float q_is, float g_is, float qq, float gg,
+                                               int cosine) {
+  float dot = __fmaf_rn(acc1, 4.8828125e-4f /* 2^-11 */, acc0);
+  dot = __fmul_rn(__fmul_rn(dot, q_is), g_is);
+  if (cosine) return fmaxf(fabsf(__fsub_rn(1.f, dot)), 1e-12f);
+  return __fmaf_rn(-2.f, dot, __fadd_rn(qq, gg));
+}
+
+__device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, int& mt, int& nt) {
+  // bands of 16 gallery tiles, query tiles fastest inside a band-row: the CTAs that run
+  // concurrently touch a compact (m x n) block, so each operand tile is fetched from HBM ~once
+  const int band_w = 16;
+  const int band = tile / (band_w * m_tiles);
+  const int rem = tile - band * band_w * m_tiles;
+  const int w = min(band_w, n_tiles - band * band_w);
+  mt = rem / w;
+  nt = band * band_w + rem % w;
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    dist_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmPass p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int k_blocks = (p.d + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.q_hi);
+    tma_prefetch_desc(&maps.q_lo);
+    tma_prefetch_desc(&maps.g_hi);
+    tma_prefetch_desc(&maps.g_lo);
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int mt, nt;
+        tile_coords(tile, p.m_tiles, p.n_tiles, mt, nt);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t dst = smem_base + stage * STAGE_BYTES;
+          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+          tma_load_2d(dst + 0 * TILE_BYTES, &maps.q_hi, full_bar(stage), kb * BK, mt * BM);
+          tma_load_2d(dst + 1 * TILE_BYTES, &maps.q_lo, full_bar(stage), kb * BK, mt * BM);
+          tma_load_2d(dst + 2 * TILE_BYTES, &maps.g_hi, full_bar(stage), kb * BK, nt * BN);
+          tma_load_2d(dst + 3 * TILE_BYTES, &maps.g_lo, full_bar(stage), kb * BK, nt * BN);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + as * 256;
+        const uint32_t acc1 = acc0 + 128;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t base = smem_base + stage * STAGE_BYTES;
+          const uint64_t d_qh = make_sw128_kmajor_desc(base + 0 * TILE_BYTES);
+          const uint64_t d_ql = make_sw128_kmajor_desc(base + 1 * TILE_BYTES);
+          const uint64_t d_gh = make_sw128_kmajor_desc(base + 2 * TILE_BYTES);
+          const uint64_t d_gl = make_sw128_kmajor_desc(base + 3 * TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+            umma_f16(acc0, desc_advance_k(d_qh, k), desc_advance_k(d_gh, k), idesc, acc);
+            umma_f16(acc1, desc_advance_k(d_qh, k), desc_advance_k(d_gl, k), idesc, acc);
+            umma_f16(acc1, desc_advance_k(d_ql, k), desc_advance_k(d_gh, k), idesc, 1u);
+          }
+          umma_commit(empty_bar(stage));  // smem slot free once these MMAs have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(tfull_bar(as));  // accumulators complete
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: 4 warps, warp%4 selects the 32-lane TMEM quarter ========
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int mt, nt;
+      tile_coords(tile, p.m_tiles, p.n_tiles, mt, nt);
+      const int row = mt * BM + row_in_tile;
+      const bool row_ok = row < p.nq;
+      float qq = 0.f, qis = 0.f, tau = -CUDART_INF_F;
+      int qpid = -1, qcam = 0, npos = 0;
+      unsigned long long maxkey = 0ull;
+      if (row_ok) {
+        qq = p.q_sq[row];
+        qis = p.q_is[row];
+        if (p.tau) tau = p.tau[row];
+        if (p.q_pid) {
+          qpid = p.q_pid[row];
+          qcam = p.q_cam[row];
+        }
+        if (p.buckets) {
+          npos = p.thr_count[row];
+          if (npos > 0) maxkey = p.thr_keys[(size_t)row * p.max_pos + npos - 1];
+        }
+      }
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const uint32_t t0 = tmem_base + as * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
+      for (int c = 0; c < BN / 16; ++c) {
+        uint32_t r0[16], r1[16];
+        tmem_ld16(t0 + c * 16, r0);
+        tmem_ld16(t0 + 128 + c * 16, r1);
+        tmem_ld_wait();
+        const int col0 = nt * BN + c * 16;
+        float gmin = CUDART_INF_F;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int col = col0 + j;
+          if (col < p.ng && row_ok) {  // col bound is warp-uniform
+            const float dist = dist_from_acc(__uint_as_float(r0[j]), __uint_as_float(r1[j]), qis, __ldg(p.g_is + col),
+                                             qq, __ldg(p.g_sq + col), p.cosine);
+            const unsigned int gidx = static_cast<unsigned int>(col + p.g_off);
+            if (p.dist_out) p.dist_out[(size_t)row * p.ld_out + col] = dist;
+            gmin = fminf(gmin, dist);
+            if (p.cand_keys && dist <= tau) {
+              const int slot = atomicAdd(p.cand_count + row, 1);
+              if (slot < p.cand_cap)
+                p.cand_keys[(size_t)row * p.cand_cap + slot] = make_key(dist, gidx);
+              else
+                *p.overflow = 1;
+            }
+            if (p.q_pid) {
+              const bool same = __ldg(p.g_pid + col) == qpid;
+              const bool junk = same && ((__ldg(p.g_mask + col) >> qcam) & 1ull);
+              if (p.pos_keys && same && !junk) {
+                const int slot = atomicAdd(p.pos_count + row, 1);
+                if (slot < p.max_pos)
+                  p.pos_keys[(size_t)row * p.max_pos + slot] = make_key(dist, gidx);
+                else
+                  *p.overflow = 1;
+              }
+              if (p.buckets && !junk && npos > 0) {
+                const unsigned long long key = make_key(dist, gidx);
+                if (key < maxkey) {
+                  // first positive that sorts strictly after this row
+                  const unsigned long long* thr = p.thr_keys + (size_t)row * p.max_pos;
+                  int lo_i = 0, hi_i = npos - 1;  // thr[hi_i] = maxkey > key
+                  while (lo_i < hi_i) {
+                    const int mid = (lo_i + hi_i) >> 1;
+                    if (thr[mid] > key) hi_i = mid; else lo_i = mid + 1;
+                  }
+                  atomicAdd(p.buckets + (size_t)row * (p.max_pos + 1) + lo_i, 1);
+                }
+              }
+            }
+          }
+        }
+        if (p.gmin && row_ok && col0 < p.ng) p.gmin[(size_t)row * p.n_groups + (col0 >> 4)] = gmin;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1u;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// small kernels: k-th smallest group minimum, key-row sort, top-k emit, AP finalize
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void bitonic_sort_smem(T* s, int n_pow2) {
+  for (int k = 2; k <= n_pow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const T a = s[i], b = s[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) {
+            s[i] = b;
+            s[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// tau[q] = k-th smallest of the (merged) group minima: an upper bound of the k-th smallest
+// distance, with at most merge*GROUP_W*(k-1) rows strictly below it.
+__global__ void select_tau_kernel(const float* __restrict__ gmin, int n_groups, int merge, int k, int n_pow2,
+                                  float* __restrict__ tau) {
+  extern __shared__ uint32_t skeys[];
+  const float* g = gmin + (size_t)blockIdx.x * n_groups;
+  const int n_merged = (n_groups + merge - 1) / merge;
+  for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+    float m = CUDART_INF_F;
+    if (i < n_merged)
+      for (int t = 0; t < merge; ++t) {
+        const int gi = i * merge + t;
+        if (gi < n_groups) m = fminf(m, g[gi]);
+      }
+    skeys[i] = (i < n_merged) ? float_orderable(m) : 0xFFFFFFFFu;
+  }
+  __syncthreads();
+  bitonic_sort_smem(skeys, n_pow2);
+  if (threadIdx.x == 0) tau[blockIdx.x] = orderable_float(skeys[k - 1]);
+}
+
+__global__ void sort_key_rows_kernel(unsigned long long* __restrict__ keys, const int* __restrict__ counts,
+                                     int row_stride, int n_pow2) {
+  extern __shared__ unsigned long long lkeys[];
+  unsigned long long* row = keys + (size_t)blockIdx.x * row_stride;
+  const int cnt = min(counts[blockIdx.x], row_stride);
+  if (cnt <= 1) return;
+  int np2 = 2;
+  while (np2 < cnt) np2 <<= 1;  // block-uniform
+  for (int i = threadIdx.x; i < np2; i += blockDim.x) lkeys[i] = (i < cnt) ? row[i] : ~0ull;
+  __syncthreads();
+  bitonic_sort_smem(lkeys, np2);
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) row[i] = lkeys[i];
+}
+
+__global__ void topk_emit_kernel(const unsigned long long* __restrict__ keys, const int* __restrict__ counts, int cap,
+                                 int k, int64_t nq, long long* __restrict__ out_idx, float* __restrict__ out_dist,
+                                 int* __restrict__ overflow) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq * k) return;
+  const int64_t q = i / k;
+  const int j = (int)(i - q * k);
+  if (j >= counts[q]) {  // cannot happen (count(<= tau) >= k by construction)
+    *overflow = 2;
+    out_idx[i] = -1;
+    out_dist[i] = CUDART_INF_F;
+    return;
+  }
+  const unsigned long long key = keys[(size_t)q * cap + j];
+  out_idx[i] = (long long)(key & 0xFFFFFFFFull);
+  out_dist[i] = orderable_float((uint32_t)(key >> 32));
+}
+
+__global__ void eval_finalize_kernel(const int* __restrict__ buckets, const int* __restrict__ pos_count, int64_t nq,
+                                     int max_pos, int* __restrict__ ranks, double* __restrict__ ap) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const int n = min(pos_count[q], max_pos);
+  const int* b = buckets + (size_t)q * (max_pos + 1);
+  int* r = ranks + (size_t)q * max_pos;
+  long long before = 0;
+  double acc = 0.0;
+  for (int j = 0; j < n; ++j) {
+    before += b[j];
+    const int rank = (int)before + 1;  // kept rows strictly before positive j, plus itself
+    r[j] = rank;
+    acc += (double)(j + 1) / (double)rank;  // utils/eval_reid.py:75-79
+  }
+  for (int j = n; j < max_pos; ++j) r[j] = -1;
+  ap[q] = n > 0 ? acc / (double)n : CUDART_NAN;
+}
+
+// ---------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------
+static int make_plane_maps(GemmMaps* m, const PlanesView& q, int64_t nq, const PlanesView& g, int64_t ng, int32_t d) {
+  const uint64_t qd[2] = {(uint64_t)d, (uint64_t)nq};
+  const uint64_t gd[2] = {(uint64_t)d, (uint64_t)ng};
+  const uint64_t st[2] = {2, (uint64_t)d * 2};
+  const uint32_t box[2] = {BK, BM};
+  int rc;
+  if ((rc = encode_tensor_map(&m->q_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 2, q.hi, qd, st, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = encode_tensor_map(&m->q_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 2, q.lo, qd, st, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = encode_tensor_map(&m->g_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 2, g.hi, gd, st, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = encode_tensor_map(&m->g_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 2, g.lo, gd, st, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  return 0;
+}
+
+static int launch_gemm_pass(const void* q_planes, int64_t nq, const void* g_planes, int64_t ng, int32_t d, int32_t flags,
+                            GemmPass p, cudaStream_t stream) {
+  CTL_CHECK_ARG(q_planes && g_planes, "null planes");
+  CTL_CHECK_ARG(nq > 0 && ng > 0 && nq < (1ll << 31) && ng < (1ll << 31), "nq/ng out of range (%lld, %lld)", (long long)nq, (long long)ng);
+  CTL_CHECK_ARG(d > 0 && d % 8 == 0, "feature dim %d must be a positive multiple of 8", d);
+  int rc = ctl_device_check();
+  if (rc) return rc;
+  const PlanesView q = planes_view(q_planes, nq, d), g = planes_view(g_planes, ng, d);
+  GemmMaps maps;
+  if ((rc = make_plane_maps(&maps, q, nq, g, ng, d))) return rc;
+  p.nq = (int)nq;
+  p.ng = (int)ng;
+  p.d = d;
+  p.m_tiles = (int)((nq + BM - 1) / BM);
+  p.n_tiles = (int)((ng + BN - 1) / BN);
+  p.cosine = (flags & CTL_DIST_COSINE) ? 1 : 0;
+  p.q_sq = q.sq;
+  p.q_is = q.inv_scale;
+  p.g_sq = g.sq;
+  p.g_is = g.inv_scale;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CTL_CUDA(cudaFuncSetAttribute(dist_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    attr_set = true;
+  }
+  const long long tiles = (long long)p.m_tiles * p.n_tiles;
+  const int grid = (int)std::min<long long>(tiles, sm_count());
+  dist_gemm_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(maps, p);
+  CTL_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void fill_f32_kernel(float* p, int64_t n, float v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+static constexpr int SORT_MAX = 16384;  // keys per row the smem bitonic sort accepts
+
+static int sort_rows(unsigned long long* keys, const int* counts, int64_t rows, int row_stride, cudaStream_t stream) {
+  if (row_stride > SORT_MAX) {
+    set_error("key rows of %d entries exceed the sort capacity %d", row_stride, SORT_MAX);
+    return CTL_ERR_UNSUPPORTED;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    CTL_CUDA(cudaFuncSetAttribute(sort_key_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_MAX * 8));
+    attr_set = true;
+  }
+  int np2 = 2;
+  while (np2 < row_stride) np2 <<= 1;
+  const int threads = np2 >= 2048 ? 1024 : (np2 >= 512 ? 256 : 64);
+  sort_key_rows_kernel<<<(unsigned)rows, threads, (size_t)np2 * 8, stream>>>(keys, counts, row_stride, np2);
+  CTL_LAUNCH_CHECK();
+  return 0;
+}
+
+static int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+struct TopkPlan {
+  bool emit_all;
+  int n_groups;   // GROUP_W-wide groups
+  int merge;      // groups merged per selection slot
+  int n_merged_pow2;
+  int cap;        // candidate capacity per query
+};
+static constexpr int EMIT_ALL_MAX = 4096;
+static constexpr int SELECT_MAX = 8192;
+static constexpr int CAP_MAX = SORT_MAX;
+
+static int plan_topk(int64_t ng, int k, TopkPlan* pl) {
+  pl->n_groups = (int)((ng + GROUP_W - 1) / GROUP_W);
+  if (ng <= EMIT_ALL_MAX) {
+    pl->emit_all = true;
+    pl->merge = 1;
+    pl->n_merged_pow2 = 0;
+    pl->cap = next_pow2((int)ng);
+    return 0;
+  }
+  pl->emit_all = false;
+  pl->merge = (pl->n_groups + SELECT_MAX - 1) / SELECT_MAX;
+  const int n_merged = (pl->n_groups + pl->merge - 1) / pl->merge;
+  if (n_merged < k) {
+    set_error("k=%d needs at least k column groups (have %d); use ctl_dist_matrix for k this large", k, n_merged);
+    return CTL_ERR_UNSUPPORTED;
+  }
+  pl->n_merged_pow2 = next_pow2(n_merged);
+  long long cap = (long long)pl->merge * GROUP_W * (k - 1) + 512;  // strict bound + room for ties at tau
+  cap = next_pow2((int)std::min<long long>(cap, (long long)ng));
+  if (cap > CAP_MAX) {
+    set_error("top-k candidate capacity %lld exceeds %d (k=%d, ng=%lld)", cap, CAP_MAX, k, (long long)ng);
+    return CTL_ERR_UNSUPPORTED;
+  }
+  pl->cap = (int)cap;
+  return 0;
+}
+
+}  // namespace ctl
+
+using namespace ctl;
+
+extern "C" {
+
+size_t ctl_planes_bytes(int64_t n, int32_t d) { return planes_total(n, d); }
+
+int ctl_planes_build(const float* x, int64_t n, int32_t d, int32_t flags, void* planes, ctl_stream_t stream) {
+  CTL_CHECK_ARG(x && planes, "null pointer");
+  CTL_CHECK_ARG(n > 0 && d > 0 && d % 8 == 0, "bad shape n=%lld d=%d (d must be a multiple of 8)", (long long)n, d);
+  int rc = ctl_device_check();
+  if (rc) return rc;
+  char* c = static_cast<char*>(planes);
+  const int n_norm = ((flags & CTL_FLAG_NORMALIZE) ? 1 : 0) + ((flags & CTL_DIST_COSINE) ? 1 : 0);
+  planes_build_kernel<<<(unsigned)((n + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
+      x, n, d, n_norm, reinterpret_cast<__half*>(c), reinterpret_cast<__half*>(c + planes_off_lo(n, d)),
+      reinterpret_cast<float*>(c + planes_off_sq(n, d)), reinterpret_cast<float*>(c + planes_off_is(n, d)));
+  CTL_LAUNCH_CHECK();
+  return 0;
+}
+
+int ctl_dist_matrix(const void* q_planes, int64_t nq, const void* g_planes, int64_t ng, int32_t d, int32_t flags,
+                    float* out, int64_t ld_out, ctl_stream_t stream) {
+  CTL_CHECK_ARG(out && ld_out >= ng, "bad output (ld_out=%lld, ng=%lld)", (long long)ld_out, (long long)ng);
+  GemmPass p = {};
+  p.dist_out = out;
+  p.ld_out = ld_out;
+  return launch_gemm_pass(q_planes, nq, g_planes, ng, d, flags, p, (cudaStream_t)stream);
+}
+
+size_t ctl_topk_workspace_bytes(int64_t nq, int64_t ng, int32_t k) {
+  TopkPlan pl;
+  if (plan_topk(ng, k, &pl)) return 0;
+  Workspace ws(nullptr, 0);
+  ws.take<float>((size_t)nq * pl.n_groups);
+  ws.take<float>((size_t)nq);
+  ws.take<unsigned long long>((size_t)nq * pl.cap);
+  ws.take<int>((size_t)nq);
+  return ws.off;
+}
+
+int ctl_l2_topk(const void* q_planes, int64_t nq, const void* g_planes, int64_t ng, int32_t d, int32_t flags, int32_t k,
+                int64_t g_index_offset, int64_t* out_idx, float* out_dist, int32_t* overflow, void* workspace,
+                size_t workspace_bytes, ctl_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CTL_CHECK_ARG(out_idx && out_dist && workspace && overflow, "null pointer");
+  CTL_CHECK_ARG(k >= 1 && k <= ng, "k=%d must be in [1, ng=%lld]", k, (long long)ng);
+  CTL_CHECK_ARG(g_index_offset >= 0 && g_index_offset + ng < (1ll << 32), "gallery index out of uint32 range");
+  TopkPlan pl;
+  int rc = plan_topk(ng, k, &pl);
+  if (rc) return rc;
+  Workspace ws(workspace, workspace_bytes);
+  float* gmin = ws.take<float>((size_t)nq * pl.n_groups);
+  float* tau = ws.take<float>((size_t)nq);
+  unsigned long long* cand = ws.take<unsigned long long>((size_t)nq * pl.cap);
+  int* cand_count = ws.take<int>((size_t)nq);
+  if (!gmin || !tau || !cand || !cand_count) {
+    set_error("workspace too small: need %zu bytes, have %zu", ws.off, workspace_bytes);
+    return CTL_ERR_WORKSPACE;
+  }
+  CTL_CUDA(cudaMemsetAsync(cand_count, 0, (size_t)nq * sizeof(int), stream));
+  CTL_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int), stream));
+  if (pl.emit_all) {
+    // small gallery: every row is a candidate (tau = +inf), one GEMM pass
+    fill_f32_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, stream>>>(tau, nq, INFINITY);
+    CTL_LAUNCH_CHECK();
+  } else {
+    // pass A: minima of 16-column groups -> tau = k-th smallest group minimum
+    GemmPass a = {};
+    a.gmin = gmin;
+    a.n_groups = pl.n_groups;
+    if ((rc = launch_gemm_pass(q_planes, nq, g_planes, ng, d, flags, a, stream))) return rc;
+    select_tau_kernel<<<(unsigned)nq, 256, pl.n_merged_pow2 * sizeof(uint32_t), stream>>>(gmin, pl.n_groups, pl.merge, k,
+                                                                                         pl.n_merged_pow2, tau);
+    CTL_LAUNCH_CHECK();
+  }
+  // pass B: rows with distance <= tau become (distance, index) keys
+  GemmPass b = {};
+  b.tau = tau;
+  b.cand_keys = cand;
+  b.cand_count = cand_count;
+  b.cand_cap = pl.cap;
+  b.g_off = g_index_offset;
+  b.overflow = overflow;
+  if ((rc = launch_gemm_pass(q_planes, nq, g_planes, ng, d, flags, b, stream))) return rc;
+  if ((rc = sort_rows(cand, cand_count, nq, pl.cap, stream))) return rc;
+  const int64_t total = nq * k;
+  topk_emit_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(cand, cand_count, pl.cap, k, nq,
+                                                                     (long long*)out_idx, out_dist, overflow);
+  CTL_LAUNCH_CHECK();
+  return 0;
+}
+
+int ctl_sort_key_rows(uint64_t* keys, const int32_t* counts, int64_t rows, int32_t row_stride, ctl_stream_t stream) {
+  CTL_CHECK_ARG(keys && counts && rows > 0 && row_stride > 0, "bad arguments");
+  int rc = ctl_device_check();
+  if (rc) return rc;
+  return sort_rows(reinterpret_cast<unsigned long long*>(keys), counts, rows, row_stride, (cudaStream_t)stream);
+}
+
+static int check_ids(const int32_t* q_pid, const int32_t* q_cam, const int32_t* g_pid, const uint64_t* g_cammask,
+                     int64_t ng, int64_t g_index_offset, int32_t max_pos) {
+  CTL_CHECK_ARG(q_pid && q_cam && g_pid && g_cammask, "null identity arrays");
+  CTL_CHECK_ARG(max_pos >= 1, "max_pos must be >= 1");
+  CTL_CHECK_ARG(g_index_offset >= 0 && g_index_offset + ng < (1ll << 32), "gallery index out of uint32 range");
+  return 0;
+}
+
+int ctl_eval_collect(const void* q_planes, int64_t nq, const void* g_planes, int64_t ng, int32_t d, int32_t flags,
+                     const int32_t* q_pid, const int32_t* q_cam, const int32_t* g_pid, const uint64_t* g_cammask,
+                     int64_t g_index_offset, int32_t max_pos, uint64_t* pos_keys, int32_t* pos_count,
+                     int32_t* overflow, ctl_stream_t stream) {
+  int rc = check_ids(q_pid, q_cam, g_pid, g_cammask, ng, g_index_offset, max_pos);
+  if (rc) return rc;
+  CTL_CHECK_ARG(pos_keys && pos_count && overflow, "null output");
+  GemmPass p = {};
+  p.q_pid = q_pid;
+  p.q_cam = q_cam;
+  p.g_pid = g_pid;
+  p.g_mask = reinterpret_cast<const unsigned long long*>(g_cammask);
+  p.pos_keys = reinterpret_cast<unsigned long long*>(pos_keys);
+  p.pos_count = pos_count;
+  p.max_pos = max_pos;
+  p.g_off = g_index_offset;
+  p.overflow = overflow;
+  return launch_gemm_pass(q_planes, nq, g_planes, ng, d, flags, p, (cudaStream_t)stream);
+}
+
+int ctl_eval_count(const void* q_planes, int64_t nq, const void* g_planes, int64_t ng, int32_t d, int32_t flags,
+                   const int32_t* q_pid, const int32_t* q_cam, const int32_t* g_pid, const uint64_t* g_cammask,
+                   int64_t g_index_offset, int32_t max_pos, const uint64_t* pos_keys_sorted, const int32_t* pos_count,
+                   int32_t* buckets, ctl_stream_t stream) {
+  int rc = check_ids(q_pid, q_cam, g_pid, g_cammask, ng, g_index_offset, max_pos);
+  if (rc) return rc;
+  CTL_CHECK_ARG(pos_keys_sorted && pos_count && buckets, "null pointer");
+  GemmPass p = {};
+  p.q_pid = q_pid;
+  p.q_cam = q_cam;
+  p.g_pid = g_pid;
+  p.g_mask = reinterpret_cast<const unsigned long long*>(g_cammask);
+  p.thr_keys = reinterpret_cast<const unsigned long long*>(pos_keys_sorted);
+  p.thr_count = pos_count;
+  p.buckets = buckets;
+  p.max_pos = max_pos;
+  p.g_off = g_index_offset;
+  return launch_gemm_pass(q_planes, nq, g_planes, ng, d, flags, p, (cudaStream_t)stream);
+}
+
+int ctl_eval_finalize(const int32_t* buckets, const int32_t* pos_count, int64_t nq, int32_t max_pos, int32_t* ranks,
+                      double* ap, ctl_stream_t stream) {
+  CTL_CHECK_ARG(buckets && pos_count && ranks && ap && nq > 0 && max_pos >= 1, "bad arguments");
+  int rc = ctl_device_check();
+  if (rc) return rc;
+  eval_finalize_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, (cudaStream_t)stream>>>(buckets, pos_count, nq, max_pos,
+                                                                                       ranks, ap);
+  CTL_LAUNCH_CHECK();
+  return 0;
+}
+
+uint64_t ctl_key_encode(float dist, uint32_t index) { return make_key(dist, index); }
+void ctl_key_decode(uint64_t key, float* dist, uint32_t* index) {
+  if (dist) *dist = orderable_float((uint32_t)(key >> 32));
+  if (index) *index = (uint32_t)(key & 0xFFFFFFFFull);
+}
+
+}  // extern "C"

@@ -1,0 +1,297 @@
+"""Query x gallery retrieval engine: distance planes, full matrices, streamed top-k and
+streamed CMC / mAP, single GPU or gallery-sharded over ranks.
+
+Host-side mirror of the reference's retrieval path (utils/reid_metric.py:112-136,
+utils/eval_reid.py:25-92, inference/get_similar.py:104-128) on top of the C ABI in
+include/ctl_b200.h.  torch is used for device memory, streams and torch.distributed only.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+K_LIST = (1, 5, 10, 20, 50)  # utils/eval_reid.py:15
+
+
+@dataclass
+class Planes:
+    """Opaque operand buffer of the distance kernel (see ctl_planes_build)."""
+
+    buf: torch.Tensor
+    n: int
+    d: int
+    flags: int
+
+    @property
+    def ptr(self):
+        return self.buf.data_ptr()
+
+
+def _flags(dist: str, normalize: bool) -> int:
+    if dist not in ("euclidean", "cosine"):
+        raise KeyError(dist)
+    f = N.CTL_DIST_COSINE if dist == "cosine" else N.CTL_DIST_EUCLIDEAN
+    if normalize:
+        f |= N.CTL_FLAG_NORMALIZE
+    return f
+
+
+def build_planes(x: torch.Tensor, dist: str = "euclidean", normalize: bool = False) -> Planes:
+    N.require_cuda(x)
+    if x.dim() != 2:
+        raise ValueError(f"expected [n, d] features, got {tuple(x.shape)}")
+    x = x.detach().float().contiguous()
+    n, d = x.shape
+    flags = _flags(dist, normalize)
+    L = N.lib()
+    buf = torch.empty(L.ctl_planes_bytes(n, d), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        N.check(L.ctl_planes_build(x.data_ptr(), n, d, flags, buf.data_ptr(), N.stream_ptr()))
+    return Planes(buf, n, d, flags)
+
+
+def dist_matrix(x: torch.Tensor, y: torch.Tensor, dist: str = "euclidean", normalize: bool = False) -> torch.Tensor:
+    """get_euclidean / get_cosine (utils/reid_metric.py:25-59): the full [m, n] matrix."""
+    qp, gp = build_planes(x, dist, normalize), build_planes(y, dist, normalize)
+    if qp.d != gp.d:
+        raise ValueError("feature dims differ")
+    out = torch.empty(qp.n, gp.n, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        N.check(N.lib().ctl_dist_matrix(qp.ptr, qp.n, gp.ptr, gp.n, qp.d, qp.flags, out.data_ptr(), gp.n, N.stream_ptr()))
+    return out
+
+
+def topk(qp: Planes, gp: Planes, k: int, g_index_offset: int = 0):
+    """k nearest gallery rows per query in ascending (distance, index) order.
+    Returns (idx int64 [nq, k], dist float32 [nq, k]) on the device."""
+    L = N.lib()
+    k = int(min(k, gp.n))
+    dev = qp.buf.device
+    idx = torch.empty(qp.n, k, dtype=torch.int64, device=dev)
+    dst = torch.empty(qp.n, k, dtype=torch.float32, device=dev)
+    ovf = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws_bytes = L.ctl_topk_workspace_bytes(qp.n, gp.n, k)
+    if ws_bytes == 0:
+        N.check(-3)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        N.check(L.ctl_l2_topk(qp.ptr, qp.n, gp.ptr, gp.n, qp.d, qp.flags, k, g_index_offset, idx.data_ptr(),
+                              dst.data_ptr(), ovf.data_ptr(), ws.data_ptr(), ws_bytes, N.stream_ptr()))
+    return idx, dst, ovf
+
+
+def topk_similar(q: torch.Tensor, g: torch.Tensor, k: int = 100, dist: str = "euclidean", normalize: bool = False):
+    """inference/get_similar.py:104-128 without the distance matrix: (indices, distances)."""
+    qp, gp = build_planes(q, dist, normalize), build_planes(g, dist, normalize)
+    idx, dst, ovf = topk(qp, gp, k)
+    if int(ovf.item()) != 0:
+        raise OverflowError("top-k candidate capacity exceeded (too many exact ties at the k-th distance)")
+    return idx, dst
+
+
+# ----------------------------------------------------------------------------------------
+# identities -> dense int32 pids / camera indices / camera bit masks
+# ----------------------------------------------------------------------------------------
+
+
+def encode_identities(q_pids, g_pids, q_camids, g_camids, respect_camids: bool):
+    """Host-side re-labelling for the eval kernels (utils/eval_reid.py:52-59): pids -> dense
+    int32; cameras -> dense index < 64; gallery cameras -> bit mask (one bit, or -- with
+    respect_camids -- the set of cameras a centroid was built from)."""
+    q_pids = np.asarray(q_pids)
+    g_pids = np.asarray(g_pids)
+    uniq, inv = np.unique(np.concatenate([q_pids, g_pids]), return_inverse=True)
+    qp = inv[: len(q_pids)].astype(np.int32)
+    gp = inv[len(q_pids):].astype(np.int32)
+    n_g = len(g_pids)
+    if respect_camids:
+        q_cam_vals = [c[0] if isinstance(c, (list, tuple, np.ndarray)) else c for c in q_camids]
+        g_sets = [list(np.atleast_1d(c)) for c in list(g_camids)[:n_g]]
+        cams = sorted(set(q_cam_vals) | {c for s in g_sets for c in s})
+    else:
+        q_cam_vals = list(np.asarray(q_camids).tolist())
+        g_flat = np.asarray(g_camids)[:n_g]  # may be over-long (bases.py:255-260 quirk)
+        g_sets = [[c] for c in g_flat.tolist()]
+        cams = sorted(set(q_cam_vals) | set(g_flat.tolist()))
+    if len(cams) > 64:
+        raise NotImplementedError(f"{len(cams)} distinct cameras; the junk filter packs camera sets into 64 bits")
+    cam_index = {c: i for i, c in enumerate(cams)}
+    qc = np.asarray([cam_index[c] for c in q_cam_vals], dtype=np.int32)
+    gm = np.zeros(n_g, dtype=np.uint64)
+    for i, s in enumerate(g_sets):
+        m = 0
+        for c in s:
+            m |= 1 << cam_index[c]
+        gm[i] = m
+    # upper bound of positives per query: the largest pid group in the gallery
+    max_pos = int(np.bincount(gp).max()) if n_g else 1
+    return qp, qc, gp, gm, max(1, max_pos)
+
+
+@dataclass
+class EvalResult:
+    cmc: np.ndarray          # float32 [max_rank]
+    mAP: float
+    all_topk: np.ndarray     # float64 [5]
+    single_performance: np.ndarray  # [n_valid, 3] (q_idx, q_pid, AP)
+    ranks: np.ndarray        # int32 [nq, max_pos] 1-based kept ranks of the positives (-1 pad)
+
+
+def _aggregate(ranks: np.ndarray, ap: np.ndarray, n_pos: np.ndarray, q_pids, num_g: int, max_rank: int) -> EvalResult:
+    """The reductions at the end of eval_func (utils/eval_reid.py:86-92) from per-query ranks."""
+    max_rank = min(max_rank, num_g)
+    valid = n_pos > 0
+    if not valid.any():
+        raise RuntimeError("no valid query: no query identity appears in the gallery")
+    first = ranks[valid, 0].astype(np.int64)  # sorted ascending -> first hit
+    thresholds = np.arange(1, max_rank + 1)
+    cmc_rows = (first[:, None] <= thresholds[None, :]).astype(np.float32)
+    num_valid = float(valid.sum())
+    cmc = cmc_rows.sum(0) / num_valid  # float32 / python float, as the reference
+    topk = np.stack([(first <= k).astype(np.int64) for k in K_LIST], 1)
+    q_idx = np.nonzero(valid)[0]
+    aps = ap[valid]
+    single = np.array([[int(i), q_pids[i], a] for i, a in zip(q_idx, aps)])
+    return EvalResult(cmc.astype(np.float32), float(np.mean(aps)), np.mean(topk, 0), single, ranks)
+
+
+def evaluate_streamed(
+    qp: Planes,
+    gp: Planes,
+    q_pids,
+    g_pids,
+    q_camids,
+    g_camids,
+    max_rank: int = 50,
+    respect_camids: bool = False,
+    g_index_offset: int = 0,
+    group=None,
+    total_gallery: Optional[int] = None,
+) -> EvalResult:
+    """eval_func semantics (utils/eval_reid.py:25-92) straight from the features: two tensor-
+    core passes (collect the positives' distances; count kept rows before each positive),
+    no distance matrix, no argsort.  With `group` (torch.distributed), `gp` is this rank's
+    gallery shard and g_* its identities; keys are all-gathered, buckets all-reduced."""
+    import torch.distributed as dist
+
+    L = N.lib()
+    dev = qp.buf.device
+    nq, ng = qp.n, gp.n
+    world = dist.get_world_size(group) if group is not None else 1
+    q_pid, q_cam, g_pid, g_mask, max_pos_local = encode_identities(q_pids, g_pids, q_camids, g_camids, respect_camids)
+    if world > 1:
+        # dense re-labelling must agree across ranks: callers pass globally consistent int
+        # pids / cams, so re-label with the identity map instead of np.unique
+        if not np.issubdtype(np.asarray(q_pids).dtype, np.integer):
+            raise ValueError("sharded evaluation needs integer pids")
+        q_pid, q_cam, g_pid, g_mask, max_pos_local = _encode_identities_global(q_pids, g_pids, q_camids, g_camids)
+    def to_dev(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
+
+    d_qpid, d_qcam, d_gpid = to_dev(q_pid), to_dev(q_cam), to_dev(g_pid)
+    d_gmask = to_dev(g_mask.view(np.int64))
+    max_pos = max_pos_local
+    if world > 1:
+        mp = torch.tensor([max_pos_local], device=dev, dtype=torch.int64)
+        dist.all_reduce(mp, op=dist.ReduceOp.SUM, group=group)  # positives of a pid may spread over shards
+        max_pos = int(mp.item())
+    pos_keys = torch.zeros(nq, max_pos, dtype=torch.int64, device=dev)
+    pos_count = torch.zeros(nq, dtype=torch.int32, device=dev)
+    ovf = torch.zeros(1, dtype=torch.int32, device=dev)
+    s = N.stream_ptr
+    with torch.cuda.device(dev):
+        N.check(L.ctl_eval_collect(qp.ptr, nq, gp.ptr, ng, qp.d, qp.flags, d_qpid.data_ptr(), d_qcam.data_ptr(),
+                                   d_gpid.data_ptr(), d_gmask.data_ptr(), g_index_offset, max_pos,
+                                   pos_keys.data_ptr(), pos_count.data_ptr(), ovf.data_ptr(), s()))
+        if world > 1:
+            pos_keys, pos_count = _allgather_keys(pos_keys, pos_count, max_pos, group)
+        N.check(L.ctl_sort_key_rows(pos_keys.data_ptr(), pos_count.data_ptr(), nq, max_pos, s()))
+        buckets = torch.zeros(nq, max_pos + 1, dtype=torch.int32, device=dev)
+        N.check(L.ctl_eval_count(qp.ptr, nq, gp.ptr, ng, qp.d, qp.flags, d_qpid.data_ptr(), d_qcam.data_ptr(),
+                                 d_gpid.data_ptr(), d_gmask.data_ptr(), g_index_offset, max_pos,
+                                 pos_keys.data_ptr(), pos_count.data_ptr(), buckets.data_ptr(), s()))
+        if world > 1:
+            dist.all_reduce(buckets, op=dist.ReduceOp.SUM, group=group)
+        ranks = torch.empty(nq, max_pos, dtype=torch.int32, device=dev)
+        ap = torch.empty(nq, dtype=torch.float64, device=dev)
+        N.check(L.ctl_eval_finalize(buckets.data_ptr(), pos_count.data_ptr(), nq, max_pos, ranks.data_ptr(),
+                                    ap.data_ptr(), s()))
+    # one read-back for everything the host reduction needs
+    ranks_h, ap_h, cnt_h, ovf_h = ranks.cpu().numpy(), ap.cpu().numpy(), pos_count.cpu().numpy(), int(ovf.item())
+    if ovf_h:
+        raise OverflowError("positives list overflowed (max_pos too small)")
+    num_g = total_gallery if total_gallery is not None else ng
+    return _aggregate(ranks_h, ap_h, cnt_h, np.asarray(q_pids), num_g, max_rank)
+
+
+def _encode_identities_global(q_pids, g_pids, q_camids, g_camids):
+    q_pid = np.asarray(q_pids).astype(np.int32)
+    g_pid = np.asarray(g_pids).astype(np.int32)
+    q_cam = np.asarray(q_camids).astype(np.int32)
+    g_cam = np.asarray(g_camids).astype(np.int64)[: len(g_pid)]
+    if q_cam.max(initial=0) >= 64 or g_cam.max(initial=0) >= 64 or min(q_cam.min(initial=0), g_cam.min(initial=0)) < 0:
+        raise NotImplementedError("sharded evaluation expects camera ids in [0, 64)")
+    g_mask = (np.uint64(1) << g_cam.astype(np.uint64)).astype(np.uint64)
+    max_pos = int(np.bincount(g_pid - g_pid.min()).max()) if len(g_pid) else 1
+    return q_pid, q_cam, g_pid, g_mask, max(1, max_pos)
+
+
+def _allgather_keys(pos_keys, pos_count, max_pos, group):
+    """Concatenates every rank's positives per query (ragged, packed to the left)."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    keys_all = [torch.empty_like(pos_keys) for _ in range(world)]
+    cnt_all = [torch.empty_like(pos_count) for _ in range(world)]
+    dist.all_gather(keys_all, pos_keys, group=group)
+    dist.all_gather(cnt_all, pos_count, group=group)
+    nq = pos_keys.shape[0]
+    out = torch.zeros_like(pos_keys)
+    total = torch.zeros_like(pos_count)
+    col = torch.arange(max_pos, device=pos_keys.device)[None, :]
+    for kr, cr in zip(keys_all, cnt_all):
+        valid = col < cr[:, None]
+        dest = (total[:, None] + col).clamp(max=max_pos - 1)
+        rows = torch.arange(nq, device=pos_keys.device)[:, None].expand_as(dest)
+        out[rows[valid], dest[valid].long()] = kr[valid]
+        total = total + cr
+    return out, total
+
+
+def merge_topk(idx_list: Sequence[torch.Tensor], dist_list: Sequence[torch.Tensor], k: int):
+    """k-way merge of per-shard (ascending) top-k lists under the canonical (distance, index)
+    order -- deterministic regardless of world size."""
+    idx = torch.cat(list(idx_list), 1)
+    dst = torch.cat(list(dist_list), 1)
+    # sort by index first (stable), then by distance (stable): lexicographic (distance, index)
+    o1 = torch.argsort(idx, dim=1, stable=True)
+    idx, dst = idx.gather(1, o1), dst.gather(1, o1)
+    o2 = torch.argsort(dst, dim=1, stable=True)
+    return idx.gather(1, o2)[:, :k], dst.gather(1, o2)[:, :k]
+
+
+def topk_sharded(q_local: torch.Tensor, g_local: torch.Tensor, k: int, g_index_offset: int, group,
+                 dist: str = "euclidean", normalize: bool = False):
+    """BASELINE config 5: queries sharded by rank are all-gathered once (NCCL), the gallery
+    stays sharded; every rank returns the merged global top-k of ALL queries."""
+    import torch.distributed as tdist
+
+    world = tdist.get_world_size(group)
+    q_all = [torch.empty_like(q_local) for _ in range(world)]
+    tdist.all_gather(q_all, q_local.contiguous(), group=group)
+    q = torch.cat(q_all, 0)
+    qp, gp = build_planes(q, dist, normalize), build_planes(g_local, dist, normalize)
+    idx, dst, ovf = topk(qp, gp, k, g_index_offset)
+    idx_all = [torch.empty_like(idx) for _ in range(world)]
+    dst_all = [torch.empty_like(dst) for _ in range(world)]
+    tdist.all_gather(idx_all, idx, group=group)
+    tdist.all_gather(dst_all, dst, group=group)
+    tdist.all_reduce(ovf, group=group)
+    if int(ovf.item()) != 0:
+        raise OverflowError("top-k candidate capacity exceeded on some rank")
+    return merge_topk(idx_all, dst_all, k)

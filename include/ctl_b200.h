@@ -1,0 +1,117 @@
+/* libctl_b200.so -- C ABI of the B200-native centroid-triplet re-ID hot path.
+ *
+ * The reference (mikwieczorek/centroids-reid @ a1825b7) is pure Python: the path it exposes
+ * is a Python module/class API called by PyTorch-Lightning hooks, there is no FFI of its
+ * own.  This header is the boundary a maintainer binds instead of the torch/numpy calls at
+ * the cited reference lines (see INTEGRATION.md for the ctypes stub); the Python package
+ * `centroids-reid_b200` is that binding plus drop-in classes with the reference's names.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless marked host;
+ *     buffers are caller-owned (the Python shim allocates them with torch's caching
+ *     allocator) and must be contiguous and 16-byte aligned;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing
+ *     synchronises unless stated;
+ *   - return value: 0 = ok, negative = CTL_ERR_* (argument / capacity error),
+ *     positive = cudaError_t; ctl_last_error() returns a thread-local description;
+ *   - there is NO CPU fallback: without an sm_100 device every compute entry point fails.
+ */
+#ifndef CTL_B200_H_
+#define CTL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTL_ABI_VERSION 1
+
+#define CTL_OK 0
+#define CTL_ERR_INVALID_ARGUMENT (-1)
+#define CTL_ERR_WORKSPACE (-2)   /* workspace too small; ctl_last_error() names the size */
+#define CTL_ERR_UNSUPPORTED (-3)
+#define CTL_ERR_CAPACITY (-4)    /* a device-side list overflowed (see the entry point) */
+#define CTL_ERR_NO_DEVICE (-5)
+
+typedef void* ctl_stream_t; /* cudaStream_t */
+
+const char* ctl_last_error(void);
+int ctl_abi_version(void);
+/* 0 when the current device is sm_100 (B200); CTL_ERR_NO_DEVICE otherwise. */
+int ctl_device_check(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Query x gallery distances, top-k and streamed CMC / mAP ranks
+ * replaces: utils/reid_metric.py:25-33 (get_euclidean), :51-59 (get_cosine), :112-136
+ * (R1_mAP.compute: normalize, distmat, np.argsort), utils/eval_reid.py:25-92 (eval_func),
+ * inference/get_similar.py:104-128 (dist + argsort + [:, :topk]).
+ * ---------------------------------------------------------------------------------------- */
+#define CTL_DIST_EUCLIDEAN 0 /* squared L2, unclamped: |q|^2 + |g|^2 - 2 q.g */
+#define CTL_DIST_COSINE 1    /* clamp(|1 - cos|, 1e-12) */
+#define CTL_FLAG_NORMALIZE 2 /* torch.nn.functional.normalize(x, dim=1, p=2) first */
+
+/* Row planes: the fp32 rows split into two fp16 planes (hi + 2^-11 lo, per-row power-of-two
+ * scale) plus fp32 squared norms, the operand format of the tensor-core distance kernel.
+ * Opaque to the caller; ctl_planes_bytes() gives the buffer size. */
+size_t ctl_planes_bytes(int64_t n, int32_t d);
+int ctl_planes_build(const float* x, int64_t n, int32_t d, int32_t flags, void* planes, ctl_stream_t stream);
+
+/* out[nq, ld_out] = dist(q, g): the full matrix (get_euclidean / get_cosine drop-in). */
+int ctl_dist_matrix(const void* q_planes, int64_t nq, const void* g_planes, int64_t ng, int32_t d, int32_t flags,
+                    float* out, int64_t ld_out, ctl_stream_t stream);
+
+/* Per-query k smallest distances in ascending (distance, gallery index) order, without
+ * materialising the matrix.  out_idx = local gallery row + g_index_offset.  Requires
+ * k <= ng.  *overflow (device int, written asynchronously) becomes non-zero if more rows
+ * than the candidate capacity tie exactly at the selection threshold; the results are then
+ * invalid and the shim raises CTL_ERR_CAPACITY after its result read-back. */
+size_t ctl_topk_workspace_bytes(int64_t nq, int64_t ng, int32_t k);
+int ctl_l2_topk(const void* q_planes, int64_t nq, const void* g_planes, int64_t ng, int32_t d, int32_t flags,
+                int32_t k, int64_t g_index_offset, int64_t* out_idx, float* out_dist, int32_t* overflow,
+                void* workspace, size_t workspace_bytes, ctl_stream_t stream);
+
+/* Streamed evaluation (eval_func semantics).  Identity / camera arrays: q_pid, g_pid int32;
+ * q_cam = dense camera index in [0,64); g_cammask = bit set of the cameras a gallery row
+ * (or centroid, utils/eval_reid.py:52-56 respect_camids) was built from.  A gallery row is
+ * junk for a query iff same pid and bit q_cam of its mask is set; it is a positive iff
+ * same pid and not junk.
+ *   collect : pos_keys[nq, max_pos] <- (distance, gallery index) keys of each query's
+ *             positives (unordered), pos_count[nq] (zeroed by the caller);
+ *   sort    : ascending sort of every row of a key matrix (counts[i] valid entries);
+ *   count   : buckets[nq, max_pos + 1] (zeroed by the caller) += for every kept gallery row,
+ *             the index of the first positive that sorts after it;
+ *   finalize: ranks[nq, max_pos] (1-based rank of each positive among kept rows),
+ *             ap[nq] (float64, eval_reid.py:75-79), -1 / NaN for queries without positives.
+ * With a gallery sharded over ranks: collect per shard, all-gather + sort the keys, count
+ * per shard, all-reduce(sum) the buckets, finalize. */
+int ctl_eval_collect(const void* q_planes, int64_t nq, const void* g_planes, int64_t ng, int32_t d, int32_t flags,
+                     const int32_t* q_pid, const int32_t* q_cam, const int32_t* g_pid, const uint64_t* g_cammask,
+                     int64_t g_index_offset, int32_t max_pos, uint64_t* pos_keys, int32_t* pos_count,
+                     int32_t* overflow, ctl_stream_t stream);
+int ctl_sort_key_rows(uint64_t* keys, const int32_t* counts, int64_t rows, int32_t row_stride, ctl_stream_t stream);
+int ctl_eval_count(const void* q_planes, int64_t nq, const void* g_planes, int64_t ng, int32_t d, int32_t flags,
+                   const int32_t* q_pid, const int32_t* q_cam, const int32_t* g_pid, const uint64_t* g_cammask,
+                   int64_t g_index_offset, int32_t max_pos, const uint64_t* pos_keys_sorted,
+                   const int32_t* pos_count, int32_t* buckets, ctl_stream_t stream);
+int ctl_eval_finalize(const int32_t* buckets, const int32_t* pos_count, int64_t nq, int32_t max_pos, int32_t* ranks,
+                      double* ap, ctl_stream_t stream);
+/* key <-> (distance, index) helpers for host-side merges of per-shard results */
+uint64_t ctl_key_encode(float dist, uint32_t index);
+void ctl_key_decode(uint64_t key, float* dist, uint32_t* index);
+
+/* ------------------------------------------------------------------------------------------
+ * Per-identity centroid mean (segmented reduction)
+ * replaces: modelling/bases.py:92-95 (_calculate_centroids), the tensor part of
+ * :179-262 (validation_create_centroids), inference/inference_utils.py:147-159.
+ * out[s, :] = sum_{j in [indptr[s], indptr[s+1])} x[indices[j], :] / count  (CSR groups;
+ * indices == NULL means contiguous rows j).
+ * ---------------------------------------------------------------------------------------- */
+int ctl_segment_mean(const float* x, int64_t n, int32_t d, const int64_t* indptr, const int64_t* indices,
+                     int64_t n_seg, float* out, ctl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTL_B200_H_ */

@@ -1,0 +1,86 @@
+"""CPU: host-side logic of the package (no GPU compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import ctl_b200
+from conftest import ROOT, load_golden
+from ctl_b200 import _native as N
+from ctl_b200 import retrieval as R
+from ctl_b200.utils.eval_reid import eval_func
+from oracle import ctl_oracle as O
+
+
+def test_abi_exports_every_declared_symbol():
+    """The shared library loads and exports exactly what include/ctl_b200.h declares."""
+    header = open(os.path.join(ROOT, "include", "ctl_b200.h")).read()
+    declared = set(re.findall(r"\b(ctl_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(N.LIB_PATH)
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, f"declared in the header but not exported: {missing}"
+    assert declared == set(N.SIGNATURES), declared ^ set(N.SIGNATURES)
+    assert N.lib().ctl_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        R.build_planes(torch.zeros(4, 64))
+    assert N.lib().ctl_device_check() != 0
+    assert b"CUDA" in N.lib().ctl_last_error() or b"device" in N.lib().ctl_last_error()
+
+
+def test_key_encoding_orders_like_distance_then_index():
+    L = N.lib()
+    vals = [-3.5, -0.0, 0.0, 1e-30, 1.0, 1.0000001, 7.25, float("inf")]
+    keys = [L.ctl_key_encode(v, 5) for v in vals]
+    assert keys == sorted(keys)
+    assert L.ctl_key_encode(1.0, 3) < L.ctl_key_encode(1.0, 4) < L.ctl_key_encode(1.0000001, 0)
+    d, i = ctypes.c_float(), ctypes.c_uint32()
+    L.ctl_key_decode(L.ctl_key_encode(-2.75, 123456), ctypes.byref(d), ctypes.byref(i))
+    assert d.value == -2.75 and i.value == 123456
+
+
+@pytest.mark.parametrize("name", ["small", "ties"])
+def test_eval_func_matches_reference_golden(name):
+    g = load_golden(f"retrieval_{name}.npz")
+    nq, ng = int(g["num_q"]), int(g["num_g"])
+    _, pids, cams = O.synth_retrieval(nq, ng, int(g["num_ids"]), 2048, float(g["sigma"]), int(g["seed"]),
+                                      dyadic=bool(g["dyadic"]))
+    idx = O.rank_indices(g["dist"])
+    cmc, mAP, topk, single = eval_func(idx, pids[:nq], pids[nq:], cams[:nq], cams[nq:], 50)
+    assert np.array_equal(cmc, g["cmc"])
+    np.testing.assert_allclose(mAP, float(g["mAP"]), rtol=1e-12)
+    np.testing.assert_allclose(topk, g["all_topk"], rtol=1e-12)
+    np.testing.assert_allclose(single[:, 2].astype(np.float64), g["ap"], rtol=1e-12)
+
+
+def test_eval_func_respect_camids_matches_oracle():
+    g = load_golden("centroids.npz")
+    nq = int(g["num_q"])
+    feats, pids, cams = O.synth_retrieval(nq, int(g["num_g"]), int(g["num_ids"]), 2048, 3.0, 11, num_cams=4)
+    emb, lab, cam = O.validation_create_centroids(feats, pids, cams, nq, True)
+    import torch
+
+    f = torch.nn.functional.normalize(emb.float(), dim=1)
+    idx = O.rank_indices(O.get_euclidean(f[:nq], f[nq:]).numpy())
+    cmc, mAP, topk, single = eval_func(idx, lab[:nq], lab[nq:], cam[:nq], cam[nq:], 50, True)
+    assert np.array_equal(cmc, g["cam_cmc"])
+    np.testing.assert_allclose(mAP, float(g["cam_mAP"]), rtol=1e-12)
+    np.testing.assert_allclose(single[:, 2].astype(np.float64), g["cam_ap"], rtol=1e-12)
+
+
+def test_encode_identities_masks():
+    qp, qc, gp, gm, max_pos = R.encode_identities([5, 9], [9, 9, 5, 7], [0, 3], [[0, 3], [1], [3], [0]], True)
+    assert qp.tolist() == [0, 2] and gp.tolist() == [2, 2, 0, 1]
+    assert max_pos == 2
+    cams = {0: 0, 1: 1, 3: 2}
+    assert gm.tolist() == [(1 << cams[0]) | (1 << cams[3]), 1 << cams[1], 1 << cams[3], 1 << cams[0]]
+    assert qc.tolist() == [cams[0], cams[3]]
