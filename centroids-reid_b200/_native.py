@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libctl_b200.so")
 CTL_DIST_EUCLIDEAN = 0
 CTL_DIST_COSINE = 1
 CTL_FLAG_NORMALIZE = 2
+CTL_DIST_SQRT = 4
 
 _ERRORS = {
     -1: ValueError,   # CTL_ERR_INVALID_ARGUMENT
@@ -30,6 +31,19 @@ _p = C.c_void_p
 _i64 = C.c_int64
 _i32 = C.c_int32
 _sz = C.c_size_t
+
+_f = C.c_float
+
+
+class LossConfig(C.Structure):
+    """struct ctl_loss_config (include/ctl_b200.h)."""
+
+    _fields_ = [("B", _i32), ("D", _i32), ("P", _i32), ("K", _i32), ("C", _i32), ("margin", _f),
+                ("center_weight", _f), ("xent_weight", _f), ("triplet_weight", _f), ("ctl_weight", _f),
+                ("bn_eps", _f), ("bn_momentum", _f), ("label_smooth", _f)]
+
+
+_cfgp = C.POINTER(LossConfig)
 
 # name -> (restype, argtypes); kept in one table so tests can check it against the header
 SIGNATURES = {
@@ -48,6 +62,12 @@ SIGNATURES = {
     "ctl_key_encode": (C.c_uint64, [C.c_float, C.c_uint32]),
     "ctl_key_decode": (None, [C.c_uint64, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
     "ctl_segment_mean": (C.c_int, [_p, _i64, _i32, _p, _p, _i64, _p, _p]),
+    "ctl_loss_workspace_bytes": (_sz, [_cfgp]),
+    "ctl_loss_step": (C.c_int, [_cfgp] + [_p] * 14 + [_p, _sz, _p]),
+    "ctl_triplet_workspace_bytes": (_sz, [_i32, _i32]),
+    "ctl_triplet_step": (C.c_int, [_p, _i32, _i32, _p, _p, _f, _p, _p, _p, _p, _p, _sz, _p]),
+    "ctl_center_loss_step": (C.c_int, [_p, _i32, _i32, _p, _p, _i32, _p, _p, _p, _p, _sz, _p]),
+    "ctl_xent_smooth_step": (C.c_int, [_p, _i32, _i32, _p, _f, _p, _p, _p, _sz, _p]),
 }
 
 _lib = None

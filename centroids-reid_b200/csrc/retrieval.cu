@@ -196,8 +196,10 @@ __device__ __forceinline__ float dist_from_acc(float acc0, float acc1, float q_i
                                                int cosine) {
   float dot = __fmaf_rn(acc1, 4.8828125e-4f /* 2^-11 */, acc0);
   dot = __fmul_rn(__fmul_rn(dot, q_is), g_is);
-  if (cosine) return fmaxf(fabsf(__fsub_rn(1.f, dot)), 1e-12f);
-  return __fmaf_rn(-2.f, dot, __fadd_rn(qq, gg));
+  if (cosine & 1) return fmaxf(fabsf(__fsub_rn(1.f, dot)), 1e-12f);
+  const float sqd = __fmaf_rn(-2.f, dot, __fadd_rn(qq, gg));
+  // CTL_DIST_SQRT: losses/triplet_loss.py:40  dist.clamp(min=1e-12).sqrt()
+  return (cosine & 4) ? __fsqrt_rn(fmaxf(sqd, 1e-12f)) : sqd;
 }
 
 __device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, int& mt, int& nt) {
@@ -541,7 +543,7 @@ static int launch_gemm_pass(const void* q_planes, int64_t nq, const void* g_plan
   p.d = d;
   p.m_tiles = (int)((nq + BM - 1) / BM);
   p.n_tiles = (int)((ng + BN - 1) / BN);
-  p.cosine = (flags & CTL_DIST_COSINE) ? 1 : 0;
+  p.cosine = flags & (CTL_DIST_COSINE | CTL_DIST_SQRT);
   p.q_sq = q.sq;
   p.q_is = q.inv_scale;
   p.g_sq = g.sq;

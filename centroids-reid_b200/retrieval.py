@@ -33,9 +33,11 @@ class Planes:
 
 
 def _flags(dist: str, normalize: bool) -> int:
-    if dist not in ("euclidean", "cosine"):
+    if dist not in ("euclidean", "cosine", "euclidean_sqrt"):
         raise KeyError(dist)
     f = N.CTL_DIST_COSINE if dist == "cosine" else N.CTL_DIST_EUCLIDEAN
+    if dist == "euclidean_sqrt":
+        f |= N.CTL_DIST_SQRT
     if normalize:
         f |= N.CTL_FLAG_NORMALIZE
     return f

@@ -51,6 +51,7 @@ int ctl_device_check(void);
 #define CTL_DIST_EUCLIDEAN 0 /* squared L2, unclamped: |q|^2 + |g|^2 - 2 q.g */
 #define CTL_DIST_COSINE 1    /* clamp(|1 - cos|, 1e-12) */
 #define CTL_FLAG_NORMALIZE 2 /* torch.nn.functional.normalize(x, dim=1, p=2) first */
+#define CTL_DIST_SQRT 4      /* euclidean only: sqrt(clamp(d, 1e-12)) -- losses/triplet_loss.py:27-41 */
 
 /* Row planes: the fp32 rows split into two fp16 planes (hi + 2^-11 lo, per-row power-of-two
  * scale) plus fp32 squared norms, the operand format of the tensor-core distance kernel.
@@ -110,6 +111,54 @@ void ctl_key_decode(uint64_t key, float* dist, uint32_t* index);
  * ---------------------------------------------------------------------------------------- */
 int ctl_segment_mean(const float* x, int64_t n, int32_t d, const int64_t* indptr, const int64_t* indices,
                      int64_t n_seg, float* out, ctl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * CTL training-step losses, forward + backward in one enqueue
+ * replaces: train_ctl_model.py:54-152 (everything between the trunk and manual_backward) and
+ * the gradients autograd derives from it; modelling/bases.py:359-384 (create_masks_train);
+ * losses/triplet_loss.py:27-41,68-173,194-205; losses/center_loss.py:26-45.
+ * Batch contract (datasets/bases.py:346-406): B = P*K rows, pid-major blocks of K, padded rows
+ * (is_real = 0) at the end of a block, every pid keeps >= 2 real rows.  labels[B] = class
+ * index in [0, C).  All matrices fp32 row-major.
+ * out_losses[8] = total, xent, triplet, center, ctl, dist_ap, dist_an, l2_mean_centroid (each
+ * already multiplied by its SOLVER weight, like the reference's logged values).
+ * Gradients are those of `total`: d_feats[B,D], d_centers[C,D] (dense, NOT yet rescaled by
+ * 1/center_weight -- train_ctl_model.py:157-158 does that in the step), d_bn_weight[D],
+ * d_fc_weight[C,D].  bn_running_mean/var are updated in place (momentum, unbiased var).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct ctl_loss_config {
+  int32_t B, D, P, K, C;
+  float margin;         /* SOLVER.MARGIN (MarginRankingLoss) */
+  float center_weight;  /* SOLVER.CENTER_LOSS_WEIGHT */
+  float xent_weight;    /* SOLVER.QUERY_XENT_WEIGHT */
+  float triplet_weight; /* SOLVER.QUERY_CONTRASTIVE_WEIGHT */
+  float ctl_weight;     /* SOLVER.CENTROID_CONTRASTIVE_WEIGHT */
+  float bn_eps;         /* 1e-5 */
+  float bn_momentum;    /* 0.1 */
+  float label_smooth;   /* 0.1 */
+} ctl_loss_config;
+
+size_t ctl_loss_workspace_bytes(const ctl_loss_config* cfg);
+int ctl_loss_step(const ctl_loss_config* cfg, const float* feats, const int32_t* labels, const uint8_t* is_real,
+                  const float* centers, const float* bn_weight, const float* bn_bias, float* bn_running_mean,
+                  float* bn_running_var, const float* fc_weight, float* out_losses, float* d_feats, float* d_centers,
+                  float* d_bn_weight, float* d_fc_weight, void* workspace, size_t workspace_bytes,
+                  ctl_stream_t stream);
+
+/* Stand-alone drop-ins (forward value + gradient of that value in one call):
+ *   TripletLoss.__call__ (losses/triplet_loss.py:139-173; euclidean, margin ranking, optional
+ *   anchor mask; any label multiset), CenterLoss.forward (losses/center_loss.py:26-45),
+ *   CrossEntropyLabelSmooth.forward (losses/triplet_loss.py:194-205). */
+size_t ctl_triplet_workspace_bytes(int32_t n, int32_t d);
+int ctl_triplet_step(const float* feats, int32_t n, int32_t d, const int32_t* labels, const uint8_t* anchor_mask,
+                     float margin, float* out_loss, float* out_dist_ap, float* out_dist_an, float* d_feats,
+                     void* workspace, size_t workspace_bytes, ctl_stream_t stream);
+int ctl_center_loss_step(const float* x, int32_t b, int32_t d, const int32_t* labels, const float* centers, int32_t c,
+                         float* out_loss, float* d_x, float* d_centers, void* workspace, size_t workspace_bytes,
+                         ctl_stream_t stream);
+int ctl_xent_smooth_step(const float* logits, int32_t b, int32_t c, const int32_t* targets, float epsilon,
+                         float* out_loss, float* d_logits, void* workspace, size_t workspace_bytes,
+                         ctl_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,141 @@
+"""GPU parity tests of the loss path (through the C ABI) against the golden vectors produced
+by the UNMODIFIED reference's CTLModel.training_step, and against the oracle restatement.
+Tolerance: north_star's 1e-4 relative on fp32 losses / gradients (written per assertion)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import ctl_oracle as O
+from oracle.make_golden import DIM, LOSS_CASES, NUM_CLASSES, checksum, head_state
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+def _close(a, b, rtol=RTOL, atol=0.0):
+    np.testing.assert_allclose(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64), rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("name", list(LOSS_CASES))
+def test_ctl_step_matches_reference_training_step(name):
+    from ctl_b200 import _native as N
+    from ctl_b200.losses._fn import CTLStepFn
+
+    g = load_golden(f"loss_{name}.npz")
+    P, K, pad, seed, scale = LOSS_CASES[name]
+    feats, labels, is_real = O.synth_batch(P, K, DIM, NUM_CLASSES, seed, pad, scale)
+    _close(checksum(feats), g["in_checksum"], 1e-12)
+    hs = head_state(seed)
+    f = feats.cuda().requires_grad_(True)
+    centers = hs["centers"].cuda().requires_grad_(True)
+    bn_w = hs["bn_weight"].cuda().requires_grad_(True)
+    fc_w = hs["fc_weight"].cuda().requires_grad_(True)
+    run_mean, run_var = torch.zeros(DIM).cuda(), torch.ones(DIM).cuda()
+    cfg = N.LossConfig(P * K, DIM, P, K, NUM_CLASSES, 0.5, 5e-4, 1.0, 1.0, 1.0, 1e-5, 0.1, 0.1)
+    total, parts = CTLStepFn.apply(f, centers, bn_w, fc_w, hs["bn_bias"].cuda(), run_mean, run_var, labels.cuda(),
+                                   is_real.cuda(), cfg)
+    total.backward()
+    parts = parts.cpu().numpy()
+    for i, key in enumerate(("total", "xent", "triplet", "center", "ctl", "dist_ap", "dist_an", "l2_centroid")):
+        _close(parts[i], float(g[key]), RTOL)
+    gscale = np.abs(g["grad_feats"]).max()
+    _close(f.grad.cpu().numpy(), g["grad_feats"], RTOL, 1e-4 * gscale)
+    rows = torch.from_numpy(g["grad_centers_rows_idx"])
+    gc = centers.grad.cpu()
+    # the reference multiplies centers.grad by 1/CENTER_LOSS_WEIGHT afterwards (train_ctl_model.py:157-158)
+    _close(gc[rows].numpy() / 5e-4, g["grad_centers_rows"], RTOL, 1e-5 * np.abs(g["grad_centers_rows"]).max())
+    _close(float(gc.abs().sum()) / 5e-4, float(g["grad_centers_abs_sum"]), RTOL)
+    _close(bn_w.grad.cpu().numpy(), g["grad_bn_weight"], 1e-3, 1e-4 * np.abs(g["grad_bn_weight"]).max())
+    _close(fc_w.grad.cpu()[rows].numpy(), g["grad_fc_rows"], 1e-3, 1e-4 * np.abs(g["grad_fc_rows"]).max())
+    _close(checksum(fc_w.grad.cpu()), g["grad_fc_checksum"], 1e-3, 1e-6)
+    _close(run_mean.cpu().numpy(), g["bn_running_mean"], RTOL, 1e-6)
+    _close(run_var.cpu().numpy(), g["bn_running_var"], RTOL, 1e-6)
+
+
+def test_standalone_losses_match_oracle():
+    from ctl_b200.losses.center_loss import CenterLoss
+    from ctl_b200.losses.triplet_loss import (CrossEntropyLabelSmooth, TripletLoss, cosine_dist, euclidean_dist,
+                                              hard_example_mining)
+
+    feats, labels, is_real = O.synth_batch(12, 4, 512, 100, seed=9, pad_fraction=0.3)
+    # TripletLoss with an anchor mask, vs autograd through the oracle restatement
+    fo = feats.clone().requires_grad_(True)
+    lo, apo, ano = O.triplet_loss(fo, labels, 0.5, mask=is_real)
+    lo.backward()
+    fg = feats.cuda().requires_grad_(True)
+    lg, apg, ang = TripletLoss(0.5)(fg, labels.cuda(), mask=is_real.cuda())
+    lg.backward()
+    _close(lg.item(), lo.item())
+    _close(apg.cpu().numpy(), apo.detach().numpy())
+    _close(ang.cpu().numpy(), ano.detach().numpy())
+    _close(fg.grad.cpu().numpy(), fo.grad.numpy(), RTOL, 1e-4 * float(fo.grad.abs().max()))
+    # ragged label multiset (the reference's view() cannot do this; the masked form can)
+    lab2 = torch.tensor([0, 0, 0, 1, 1, 2, 2, 2, 2, 3, 3, 4, 4, 4, 5, 5])
+    f2 = torch.randn(16, 256, generator=torch.Generator().manual_seed(1))
+    l2o, _, _ = O.triplet_loss(f2, lab2, 0.3)
+    l2g, _, _ = TripletLoss(0.3)(f2.cuda(), lab2.cuda())
+    _close(l2g.item(), l2o.item())
+    # distances
+    d = euclidean_dist(feats.cuda(), feats[:7].cuda()).cpu()
+    assert float((d - O.euclidean_dist(feats, feats[:7])).abs().max()) < 1e-3  # sqrt amplifies near 0 (self pairs)
+    off = ~torch.eye(48, 7, dtype=torch.bool)
+    _close(d[off].numpy(), O.euclidean_dist(feats, feats[:7])[off].numpy(), 1e-5)
+    _close(cosine_dist(feats.cuda(), feats[:7].cuda()).cpu().numpy(), O.cosine_dist(feats, feats[:7]).numpy(), 0, 2e-6)
+    dm = O.euclidean_dist(feats, feats)
+    ap, an, pi, ni = hard_example_mining(dm.cuda(), labels.cuda(), return_inds=True)
+    apo2, ano2 = O.hard_example_mining(dm, labels)
+    assert torch.equal(ap.cpu(), apo2) and torch.equal(an.cpu(), ano2)
+    # CenterLoss
+    cl = CenterLoss(100, 512).cuda()
+    xo = feats.clone().requires_grad_(True)
+    co = cl.centers.detach().cpu().clone().requires_grad_(True)
+    O.center_loss(xo, labels, co).backward()
+    xg = feats.cuda().requires_grad_(True)
+    loss_g = cl(xg, labels.cuda())
+    loss_g.backward()
+    _close(loss_g.item(), O.center_loss(feats, labels, co.detach()).item())
+    _close(xg.grad.cpu().numpy(), xo.grad.numpy(), RTOL, 1e-6)
+    _close(cl.centers.grad.cpu().numpy(), co.grad.numpy(), RTOL, 1e-6)
+    # CrossEntropyLabelSmooth
+    z = torch.randn(48, 100, generator=torch.Generator().manual_seed(2)) * 3
+    zo = z.clone().requires_grad_(True)
+    O.cross_entropy_label_smooth(zo, labels, 100).backward()
+    zg = z.cuda().requires_grad_(True)
+    lx = CrossEntropyLabelSmooth(100)(zg, labels.cuda())
+    lx.backward()
+    _close(lx.item(), O.cross_entropy_label_smooth(z, labels, 100).item())
+    _close(zg.grad.cpu().numpy(), zo.grad.numpy(), RTOL, 1e-7)
+
+
+def test_centroids_match_reference_golden():
+    from ctl_b200 import reduce as RD
+    from ctl_b200 import retrieval as R
+
+    g = load_golden("centroids.npz")
+    nq, ng = int(g["num_q"]), int(g["num_g"])
+    feats, pids, cams = O.synth_retrieval(nq, ng, int(g["num_ids"]), DIM, 3.0, 11, num_cams=4)
+    for respect, tag in ((False, "nocam"), (True, "cam")):
+        emb, lab, cam = RD.validation_create_centroids(feats.cuda(), pids, cams, nq, respect)
+        _close(emb.cpu().numpy(), g[f"{tag}_emb"], 1e-5, 1e-7)
+        assert np.array_equal(lab, g[f"{tag}_lab"])
+        if respect:
+            assert [len(c) for c in cam] == g[f"{tag}_cam_len"].tolist()
+        else:
+            assert np.array_equal(cam, g[f"{tag}_cam"])
+        qp = R.build_planes(emb[:nq], normalize=True)
+        gp = R.build_planes(emb[nq:], normalize=True)
+        res = R.evaluate_streamed(qp, gp, lab[:nq], lab[nq:], cam[:nq], cam[nq:], 50, respect)
+        assert np.array_equal(res.cmc, g[f"{tag}_cmc"])
+        _close(res.mAP, float(g[f"{tag}_mAP"]), 1e-9)
+        _close(res.single_performance[:, 2].astype(np.float64), g[f"{tag}_ap"], 1e-9)
+    pid_index = {}
+    for i, p in enumerate(pids[nq:].tolist()):
+        pid_index.setdefault(p, []).append(i)
+    cents, cp = RD.calculate_centroids(feats[nq:].numpy(), pid_index)
+    _close(cents, g["inf_centroids"], 1e-5, 1e-7)
+    assert np.array_equal(cp, g["inf_pids"])
+    v = torch.randn(6, 5, 64).cuda()
+    _close(RD._calculate_centroids(v, 1).cpu().numpy(), (v.sum(1) / 5).cpu().numpy(), 1e-6, 1e-7)
