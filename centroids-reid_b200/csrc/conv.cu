@@ -1,0 +1,599 @@
+// Trunk (ResNet50 / ResNet50-IBN-A) inference forward: fused conv + folded-BN (+ residual)
+// (+ ReLU) as implicit GEMM on tcgen05 tensor cores, fed by TMA.
+//
+// Replaces modelling/backbones/resnet.py:51-133, resnet_ibn_a.py:18-141,
+// modelling/baseline.py:91-96 and the eval embedding path modelling/bases.py:169-177 /
+// inference/inference_utils.py:104-113.
+//
+// Layout.  Activations NHWC fp16; weights [Cout][kh][kw][Cin] fp16 with the eval-mode
+// BatchNorm scale folded in, bias fp32.  GEMM view: D[M = N*Ho*Wo, Cout] = A[M, K] W^T with
+// K = kh*kw*Cin.  There is no im2col buffer: an M-tile is a TH x TW block of output pixels
+// of one image (TH*TW = 128) and, for every filter tap (r, s) and 64-channel slab, ONE 4-D TMA
+// box {64 ch, TW, TH, 1} at (c0, w0 + s - pad, h0 + r - pad, n) lands in shared memory as a
+// 128-row x 128-byte K-major operand tile (SWIZZLE_128B); out-of-bounds coordinates are
+// zero-filled by the TMA unit, which IS the convolution's zero padding.  Stride-2 convolutions
+// read four parity views {h%2, w%2} of the input (strided tensor maps), so every box is still a
+// dense stride-1 box.  Accumulators live in TMEM (double-buffered), the epilogue applies
+// bias / residual / ReLU and writes fp16 NHWC.
+//
+// Roofline: tensor pipe for the 3x3 and wide 1x1 convolutions, HBM for the narrow 1x1s
+// (arithmetic intensity 2*Cin*Cout/(2*(Cin+Cout)) flop/B < 221); algorithmic bytes per conv =
+// 2*(M*Cin [if read once] + M*Cout [+ M*Cout residual]) + 2*K*Cout.
+#include <algorithm>
+
+#include "common.h"
+#include "umma.cuh"
+
+namespace ctl {
+
+static constexpr int CBM = 128;  // output pixels per tile
+static constexpr int CBK = 64;   // channels per k-block (128 bytes)
+static constexpr int CONV_THREADS = 192;
+static constexpr int A_TILE_BYTES = CBM * CBK * 2;
+
+struct ConvTap {
+  int map;   // which A tensor map (parity view)
+  int dh, dw;
+  int koff;  // offset of this tap's channel slab inside the weight K dimension
+};
+
+struct ConvKernelParams {
+  CUtensorMap a_map[4];
+  CUtensorMap b_map;
+  ConvTap taps[9];
+  int n_taps;
+  int cin_blocks;  // Cin / 64
+  int n_img, Ho, Wo, Cout;
+  int TW, TH, tiles_w, tiles_h;
+  int m_tiles, n_tiles;
+  const float* bias;        // [Cout]
+  const __half* residual;   // NHWC [n, Ho, Wo, Cout] or null
+  __half* out;              // NHWC
+  int relu;                 // apply ReLU to channels >= relu_from
+  int relu_from;
+};
+
+template <int BN>
+struct ConvCfg {
+  static constexpr int B_TILE_BYTES = BN * CBK * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int STAGES = BN == 64 ? 8 : (BN == 128 ? 6 : 4);
+  static constexpr int TMEM_COLS = BN == 64 ? 128 : (BN == 128 ? 256 : 512);  // 2 accumulator stages
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
+  using Cfg = ConvCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int k_blocks = p.n_taps * p.cin_blocks;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.a_map[i]);
+    tma_prefetch_desc(&p.b_map);
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;  // n fastest: neighbours share the A tile in L2
+        const int img = mt / tiles_per_img, tr = mt - img * tiles_per_img;
+        const int h0 = (tr / p.tiles_w) * p.TH, w0 = (tr % p.tiles_w) * p.TW;
+        for (int t = 0; t < p.n_taps; ++t) {
+          const ConvTap tap = p.taps[t];
+          for (int cb = 0; cb < p.cin_blocks; ++cb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t dst = smem_base + stage * Cfg::STAGE_BYTES;
+            mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+            tma_load_4d(dst, &p.a_map[tap.map], full_bar(stage), cb * CBK, w0 + tap.dw, h0 + tap.dh, img);
+            tma_load_2d(dst + A_TILE_BYTES, &p.b_map, full_bar(stage), tap.koff + cb * CBK, nt * BN);
+            if (++stage == Cfg::STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(CBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + as * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t base = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint64_t da = make_sw128_kmajor_desc(base);
+          const uint64_t db = make_sw128_kmajor_desc(base + A_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < CBK / 16; ++k)
+            umma_f16(acc, desc_advance_k(da, k), desc_advance_k(db, k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(empty_bar(stage));
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(tfull_bar(as));
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1u;
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int pix = quarter * 32 + lane;  // pixel inside the tile == TMEM lane
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      const int img = mt / tiles_per_img, tr = mt - img * tiles_per_img;
+      const int h = (tr / p.tiles_w) * p.TH + pix / p.TW, w = (tr % p.tiles_w) * p.TW + pix % p.TW;
+      const bool ok = h < p.Ho && w < p.Wo;
+      const size_t off = (((size_t)img * p.Ho + h) * p.Wo + w) * p.Cout + (size_t)nt * BN;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const uint32_t t0 = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 16; ++c) {
+        uint32_t r[16];
+        tmem_ld16(t0 + c * 16, r);
+        tmem_ld_wait();
+        if (ok) {
+          const int ch0 = nt * BN + c * 16;
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + __ldg(p.bias + ch0 + j);
+          if (p.residual) {
+            const uint4 ra = *reinterpret_cast<const uint4*>(p.residual + off + c * 16);
+            const uint4 rb = *reinterpret_cast<const uint4*>(p.residual + off + c * 16 + 8);
+            const __half2* ha = reinterpret_cast<const __half2*>(&ra);
+            const __half2* hb = reinterpret_cast<const __half2*>(&rb);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 fa = __half22float2(ha[j]), fb = __half22float2(hb[j]);
+              v[2 * j] += fa.x;
+              v[2 * j + 1] += fa.y;
+              v[8 + 2 * j] += fb.x;
+              v[8 + 2 * j + 1] += fb.y;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (ch0 + j >= p.relu_from) v[j] = fmaxf(v[j], 0.f);
+          }
+          uint4 oa, ob;
+          __half2* pa = reinterpret_cast<__half2*>(&oa);
+          __half2* pb = reinterpret_cast<__half2*>(&ob);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            pa[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+            pb[j] = __floats2half2_rn(v[8 + 2 * j], v[8 + 2 * j + 1]);
+          }
+          *reinterpret_cast<uint4*>(p.out + off + c * 16) = oa;
+          *reinterpret_cast<uint4*>(p.out + off + c * 16 + 8) = ob;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1u;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// stem: conv 7x7 / 2, pad 3, 3 -> 64 (+ folded BN, optional ReLU) from NCHW fp32 to NHWC fp16
+// (modelling/backbones/resnet.py:93-97,122-125 -- NO ReLU; resnet_ibn_a.py:84-86,126-129 -- ReLU)
+// Direct convolution on the CUDA cores: K = 147 with Cin = 3 does not map on TMA channel slabs.
+// Block: 8 x 32 output pixels x 64 channels, 256 threads, each 8 pixels (along w) x 8 channels.
+// ---------------------------------------------------------------------------------------
+static constexpr int ST_TH = 8, ST_TW = 32;
+static constexpr int ST_PH = 2 * ST_TH + 5, ST_PW = 2 * ST_TW + 5;  // 21 x 69 input patch
+static constexpr size_t STEM_SMEM = (size_t)(147 * 64 + 3 * ST_PH * (ST_PW + 1)) * sizeof(float);
+
+__global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ x, int H, int W,
+                                                        const float* __restrict__ wt /*[147][64], k=(c*7+r)*7+s*/,
+                                                        const float* __restrict__ bias, int relu,
+                                                        __half* __restrict__ out, int Ho, int Wo) {
+  extern __shared__ float ssm[];
+  float* sw = ssm;                 // [147][64]
+  float* sp = ssm + 147 * 64;      // [3][ST_PH][ST_PW + 1]
+  const int n = blockIdx.z, oh0 = blockIdx.y * ST_TH, ow0 = blockIdx.x * ST_TW;
+  for (int i = threadIdx.x; i < 147 * 64; i += 256) sw[i] = wt[i];
+  const int ih0 = 2 * oh0 - 3, iw0 = 2 * ow0 - 3;
+  for (int i = threadIdx.x; i < 3 * ST_PH * ST_PW; i += 256) {
+    const int c = i / (ST_PH * ST_PW), rem = i % (ST_PH * ST_PW), ph = rem / ST_PW, pw = rem % ST_PW;
+    const int ih = ih0 + ph, iw = iw0 + pw;
+    float v = 0.f;
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = x[(((size_t)n * 3 + c) * H + ih) * W + iw];
+    sp[(c * ST_PH + ph) * (ST_PW + 1) + pw] = v;
+  }
+  __syncthreads();
+  const int cg = threadIdx.x & 7;    // 8 channels
+  const int pg = threadIdx.x >> 3;   // 32 pixel groups: row = pg / 4, 8 consecutive columns
+  const int orow = pg >> 2, ocol0 = (pg & 3) * 8;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (int c = 0; c < 3; ++c)
+    for (int r = 0; r < 7; ++r) {
+      const float* prow = sp + (c * ST_PH + 2 * orow + r) * (ST_PW + 1) + 2 * ocol0;
+#pragma unroll
+      for (int s = 0; s < 7; ++s) {
+        const float4 w0 = *reinterpret_cast<const float4*>(sw + ((c * 7 + r) * 7 + s) * 64 + cg * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(sw + ((c * 7 + r) * 7 + s) * 64 + cg * 8 + 4);
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xv = prow[2 * i + s];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = __fmaf_rn(xv, wv[j], acc[i][j]);
+        }
+      }
+    }
+  const int oh = oh0 + orow;
+  if (oh >= Ho) return;
+  float b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) b[j] = bias[cg * 8 + j];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int ow = ow0 + ocol0 + i;
+    if (ow >= Wo) continue;
+    uint4 o;
+    __half2* ph2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a0 = acc[i][2 * j] + b[2 * j], a1 = acc[i][2 * j + 1] + b[2 * j + 1];
+      if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+      ph2[j] = __floats2half2_rn(a0, a1);
+    }
+    *reinterpret_cast<uint4*>(out + (((size_t)n * Ho + oh) * Wo + ow) * 64 + cg * 8) = o;
+  }
+}
+
+// maxpool 3x3 / 2, pad 1, NHWC fp16; one thread = 8 channels of one output pixel
+__global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __half* __restrict__ x, int N, int H, int W, int C,
+                                                           __half* __restrict__ out, int Ho, int Wo) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cv = C / 8;
+  const size_t total = (size_t)N * Ho * Wo * cv;
+  if (i >= total) return;
+  const int c8 = (int)(i % cv);
+  size_t t = i / cv;
+  const int ow = (int)(t % Wo);
+  t /= Wo;
+  const int oh = (int)(t % Ho);
+  const int n = (int)(t / Ho);
+  __half2 m[4];
+  const __half2 neg = __float2half2_rn(-65504.f);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) m[j] = neg;
+  for (int r = 0; r < 3; ++r) {
+    const int ih = 2 * oh - 1 + r;
+    if (ih < 0 || ih >= H) continue;
+    for (int s = 0; s < 3; ++s) {
+      const int iw = 2 * ow - 1 + s;
+      if (iw < 0 || iw >= W) continue;
+      const uint4 v = *reinterpret_cast<const uint4*>(x + (((size_t)n * H + ih) * W + iw) * C + c8 * 8);
+      const __half2* hv = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) m[j] = __hmax2(m[j], hv[j]);
+    }
+  }
+  uint4 o;
+  __half2* po = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) po[j] = m[j];
+  *reinterpret_cast<uint4*>(out + (((size_t)n * Ho + oh) * Wo + ow) * C + c8 * 8) = o;
+}
+
+// global average pool over H*W (fp32 accumulate, pixel order) + optional eval BatchNorm1d
+// (modelling/baseline.py:93-94, modelling/bases.py:175): one thread = 2 channels of one image
+__global__ void __launch_bounds__(256) gap_bn_kernel(const __half* __restrict__ x, int HW, int C,
+                                                     const float* __restrict__ bn_scale /*gamma/sqrt(var+eps)*/,
+                                                     const float* __restrict__ bn_shift, float* __restrict__ feat,
+                                                     float* __restrict__ emb) {
+  const int n = blockIdx.y;
+  const int c2 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c2 * 2 >= C) return;
+  const __half2* base = reinterpret_cast<const __half2*>(x + (size_t)n * HW * C) + c2;
+  float s0 = 0.f, s1 = 0.f;
+  for (int p = 0; p < HW; ++p) {
+    const float2 v = __half22float2(base[(size_t)p * (C / 2)]);
+    s0 += v.x;
+    s1 += v.y;
+  }
+  const float inv = 1.f / (float)HW;
+  const float f0 = s0 * inv, f1 = s1 * inv;
+  if (feat) {
+    feat[(size_t)n * C + 2 * c2] = f0;
+    feat[(size_t)n * C + 2 * c2 + 1] = f1;
+  }
+  if (emb) {
+    emb[(size_t)n * C + 2 * c2] = __fmaf_rn(f0, bn_scale[2 * c2], bn_shift[2 * c2]);
+    emb[(size_t)n * C + 2 * c2 + 1] = __fmaf_rn(f1, bn_scale[2 * c2 + 1], bn_shift[2 * c2 + 1]);
+  }
+}
+
+// InstanceNorm2d(affine, instance statistics) + ReLU in place on channels [0, half) of an NHWC
+// fp16 tensor (IBN, resnet_ibn_a.py:18-32): one block per (image, 8-channel group).
+__global__ void __launch_bounds__(256) instnorm_relu_kernel(__half* __restrict__ x, int HW, int C, int half,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float eps) {
+  __shared__ float s_sum[8][8], s_sq[8][8];
+  __shared__ float s_mean[8], s_istd[8];
+  const int n = blockIdx.y, c0 = blockIdx.x * 8;
+  if (c0 >= half) return;
+  __half* base = x + (size_t)n * HW * C + c0;
+  float s[8] = {}, q[8] = {};
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+    const uint4 v = *reinterpret_cast<const uint4*>(base + (size_t)p * C);
+    const __half2* hv = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(hv[j]);
+      s[2 * j] += f.x; q[2 * j] = __fmaf_rn(f.x, f.x, q[2 * j]);
+      s[2 * j + 1] += f.y; q[2 * j + 1] = __fmaf_rn(f.y, f.y, q[2 * j + 1]);
+    }
+  }
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+      q[j] += __shfl_xor_sync(0xffffffffu, q[j], o);
+    }
+    if (lane == 0) { s_sum[wp][j] = s[j]; s_sq[wp][j] = q[j]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float ts = 0.f, tq = 0.f;
+    for (int w = 0; w < 8; ++w) { ts += s_sum[w][threadIdx.x]; tq += s_sq[w][threadIdx.x]; }
+    const float mean = ts / (float)HW;
+    const float var = fmaxf(tq / (float)HW - mean * mean, 0.f);  // biased, like F.instance_norm
+    s_mean[threadIdx.x] = mean;
+    s_istd[threadIdx.x] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = gamma[c0 + j] * s_istd[j];
+    sh[j] = beta[c0 + j] - s_mean[j] * sc[j];
+  }
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+    uint4 v = *reinterpret_cast<const uint4*>(base + (size_t)p * C);
+    __half2* hv = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(hv[j]);
+      hv[j] = __floats2half2_rn(fmaxf(__fmaf_rn(f.x, sc[2 * j], sh[2 * j]), 0.f),
+                                fmaxf(__fmaf_rn(f.y, sc[2 * j + 1], sh[2 * j + 1]), 0.f));
+    }
+    *reinterpret_cast<uint4*>(base + (size_t)p * C) = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------
+static void pick_tile(int Ho, int Wo, int* TH, int* TW) {
+  // TH*TW = 128, minimise the over-covered area; prefer wide tiles (longer contiguous runs)
+  int best = -1, bth = 1, btw = 128;
+  for (int tw = 128; tw >= 1; tw >>= 1) {
+    const int th = 128 / tw;
+    const long long cover = (long long)((Ho + th - 1) / th) * th * ((Wo + tw - 1) / tw) * tw;
+    if (best < 0 || cover < best) {
+      best = (int)cover;
+      bth = th;
+      btw = tw;
+    }
+  }
+  *TH = bth;
+  *TW = btw;
+}
+
+template <int BN>
+static int launch_conv(const ConvKernelParams& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CTL_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)ConvCfg<BN>::SMEM));
+    attr_set = true;
+  }
+  const long long tiles = (long long)p.m_tiles * p.n_tiles;
+  const int grid = (int)std::min<long long>(tiles, sm_count());
+  conv_gemm_kernel<BN><<<grid, CONV_THREADS, ConvCfg<BN>::SMEM, st>>>(p);
+  CTL_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace ctl
+
+using namespace ctl;
+
+extern "C" {
+
+int ctl_conv2d_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, int32_t cin, const void* weight,
+                        const float* bias, const void* residual, void* out, int32_t cout, int32_t ksize,
+                        int32_t stride, int32_t relu, int32_t relu_from, ctl_stream_t stream) {
+  CTL_CHECK_ARG(x && weight && bias && out, "null pointer");
+  CTL_CHECK_ARG(n >= 1 && h >= 1 && w >= 1, "bad activation shape");
+  CTL_CHECK_ARG(cin % 64 == 0 && cout % 64 == 0, "Cin=%d and Cout=%d must be multiples of 64", cin, cout);
+  CTL_CHECK_ARG((ksize == 1 || ksize == 3) && (stride == 1 || stride == 2), "only 1x1 / 3x3, stride 1 / 2");
+  CTL_CHECK_ARG(stride == 1 || (h % 2 == 0 && w % 2 == 0), "stride 2 needs even H, W (got %dx%d)", h, w);
+  int rc = ctl_device_check();
+  if (rc) return rc;
+  const int pad = ksize == 3 ? 1 : 0;
+  const int Ho = (h + 2 * pad - ksize) / stride + 1, Wo = (w + 2 * pad - ksize) / stride + 1;
+  ConvKernelParams p = {};
+  pick_tile(Ho, Wo, &p.TH, &p.TW);
+  p.tiles_h = (Ho + p.TH - 1) / p.TH;
+  p.tiles_w = (Wo + p.TW - 1) / p.TW;
+  p.n_img = n;
+  p.Ho = Ho;
+  p.Wo = Wo;
+  p.Cout = cout;
+  p.cin_blocks = cin / 64;
+  p.bias = bias;
+  p.residual = static_cast<const __half*>(residual);
+  p.out = static_cast<__half*>(out);
+  p.relu = relu;
+  p.relu_from = relu_from;
+  p.m_tiles = n * p.tiles_h * p.tiles_w;
+  const int BN = cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64);
+  p.n_tiles = cout / BN;
+  const __half* xb = static_cast<const __half*>(x);
+  const uint32_t abox[4] = {CBK, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+  if (stride == 1) {
+    const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+    const uint64_t strd[4] = {2, (uint64_t)cin * 2, (uint64_t)w * cin * 2, (uint64_t)h * w * cin * 2};
+    for (int i = 0; i < 4; ++i)
+      if ((rc = encode_tensor_map(&p.a_map[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, xb, dims, strd, abox,
+                                  CU_TENSOR_MAP_SWIZZLE_128B)))
+        return rc;
+    p.n_taps = ksize * ksize;
+    for (int r = 0; r < ksize; ++r)
+      for (int s = 0; s < ksize; ++s) p.taps[r * ksize + s] = ConvTap{0, r - pad, s - pad, (r * ksize + s) * cin};
+  } else {
+    // parity views: view (ph, pw) holds input pixels (2i + ph, 2j + pw)
+    const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)(w / 2), (uint64_t)(h / 2), (uint64_t)n};
+    const uint64_t strd[4] = {2, (uint64_t)cin * 4, (uint64_t)w * cin * 4, (uint64_t)h * w * cin * 2};
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw)
+        if ((rc = encode_tensor_map(&p.a_map[ph * 2 + pw], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4,
+                                    xb + ((size_t)ph * w + pw) * cin, dims, strd, abox, CU_TENSOR_MAP_SWIZZLE_128B)))
+          return rc;
+    p.n_taps = ksize * ksize;
+    for (int r = 0; r < ksize; ++r)
+      for (int s = 0; s < ksize; ++s) {
+        // input row 2*ho + r - pad = 2*(ho + dh) + ph
+        const int ar = r - pad, as = s - pad;
+        const int ph = ((ar % 2) + 2) % 2, pw = ((as % 2) + 2) % 2;
+        const int dh = (ar - ph) / 2, dw = (as - pw) / 2;
+        p.taps[r * ksize + s] = ConvTap{ph * 2 + pw, dh, dw, (r * ksize + s) * cin};
+      }
+  }
+  const uint64_t bdims[2] = {(uint64_t)ksize * ksize * cin, (uint64_t)cout};
+  const uint64_t bstr[2] = {2, (uint64_t)ksize * ksize * cin * 2};
+  const uint32_t bbox[2] = {CBK, (uint32_t)BN};
+  if ((rc = encode_tensor_map(&p.b_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 2, weight, bdims, bstr, bbox,
+                              CU_TENSOR_MAP_SWIZZLE_128B)))
+    return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (BN == 256) return launch_conv<256>(p, st);
+  if (BN == 128) return launch_conv<128>(p, st);
+  return launch_conv<64>(p, st);
+}
+
+int ctl_stem_conv7x7(const float* x_nchw, int32_t n, int32_t h, int32_t w, const float* weight_k64, const float* bias,
+                     int32_t relu, void* out_nhwc_f16, ctl_stream_t stream) {
+  CTL_CHECK_ARG(x_nchw && weight_k64 && bias && out_nhwc_f16, "null pointer");
+  CTL_CHECK_ARG(n >= 1 && h >= 7 && w >= 7, "bad input shape");
+  int rc = ctl_device_check();
+  if (rc) return rc;
+  const int Ho = (h + 6 - 7) / 2 + 1, Wo = (w + 6 - 7) / 2 + 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CTL_CUDA(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEM_SMEM));
+    attr_set = true;
+  }
+  dim3 grid((Wo + ST_TW - 1) / ST_TW, (Ho + ST_TH - 1) / ST_TH, n);
+  stem_conv_kernel<<<grid, 256, STEM_SMEM, (cudaStream_t)stream>>>(x_nchw, h, w, weight_k64, bias, relu,
+                                                                  static_cast<__half*>(out_nhwc_f16), Ho, Wo);
+  CTL_LAUNCH_CHECK();
+  return 0;
+}
+
+int ctl_maxpool3x3s2_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, void* out,
+                              ctl_stream_t stream) {
+  CTL_CHECK_ARG(x && out && c % 8 == 0, "bad arguments");
+  int rc = ctl_device_check();
+  if (rc) return rc;
+  const int Ho = (h + 2 - 3) / 2 + 1, Wo = (w + 2 - 3) / 2 + 1;
+  const size_t total = (size_t)n * Ho * Wo * (c / 8);
+  maxpool3x3s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      static_cast<const __half*>(x), n, h, w, c, static_cast<__half*>(out), Ho, Wo);
+  CTL_LAUNCH_CHECK();
+  return 0;
+}
+
+int ctl_gap_bn_nhwc_f16(const void* x, int32_t n, int32_t hw, int32_t c, const float* bn_scale, const float* bn_shift,
+                        float* feat, float* emb, ctl_stream_t stream) {
+  CTL_CHECK_ARG(x && (feat || emb) && c % 2 == 0, "bad arguments");
+  CTL_CHECK_ARG(emb == nullptr || (bn_scale && bn_shift), "emb needs the folded BatchNorm1d scale/shift");
+  int rc = ctl_device_check();
+  if (rc) return rc;
+  dim3 grid((c / 2 + 255) / 256, n);
+  gap_bn_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const __half*>(x), hw, c, bn_scale, bn_shift, feat,
+                                                       emb);
+  CTL_LAUNCH_CHECK();
+  return 0;
+}
+
+int ctl_instnorm_relu_nhwc_f16(void* x, int32_t n, int32_t hw, int32_t c, int32_t half, const float* gamma,
+                               const float* beta, float eps, ctl_stream_t stream) {
+  CTL_CHECK_ARG(x && gamma && beta && half % 8 == 0 && half <= c && c % 8 == 0, "bad arguments");
+  int rc = ctl_device_check();
+  if (rc) return rc;
+  dim3 grid(half / 8, n);
+  instnorm_relu_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<__half*>(x), hw, c, half, gamma, beta, eps);
+  CTL_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,138 @@
+"""B200 inference engine of the ResNet50(-IBN-A) trunk.
+
+Packs a reference-layout state_dict (keys of modelling/backbones/resnet.py:90-120 /
+resnet_ibn_a.py:77-124) into kernel operands -- NHWC / [Cout][kh][kw][Cin] fp16 weights with the
+eval-mode BatchNorm folded in, fp32 biases -- and runs the forward as a sequence of fused
+conv+BN(+residual)(+ReLU) tcgen05 launches (csrc/conv.cu) through the C ABI.
+
+Forward semantics follow ResNet.forward (resnet.py:122-133: NO ReLU after the stem) and
+ResNet_IBN.forward (resnet_ibn_a.py:126-141: ReLU after the stem; IBN as bn1 of layer1-3),
+Baseline.forward (baseline.py:91-96: global average pool) and the eval embedding
+bn(backbone(x)) of modelling/bases.py:169-177.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from ... import _native as N
+
+R50_LAYERS = (3, 4, 6, 3)
+BN_EPS = 1e-5
+
+
+def _fold(w: torch.Tensor, bn: Dict[str, torch.Tensor], eps: float = BN_EPS):
+    scale = bn["weight"].float() / torch.sqrt(bn["running_var"].float() + eps)
+    bias = bn["bias"].float() - bn["running_mean"].float() * scale
+    return w.float() * scale[:, None, None, None], bias
+
+
+def _bn(sd, prefix):
+    return {k: sd[f"{prefix}.{k}"] for k in ("weight", "bias", "running_mean", "running_var")}
+
+
+class _Conv:
+    __slots__ = ("w", "b", "cin", "cout", "k", "stride", "relu", "relu_from")
+
+    def __init__(self, w_folded, bias, stride, relu, relu_from=0):
+        cout, cin, k, _ = w_folded.shape
+        self.w = w_folded.permute(0, 2, 3, 1).contiguous().half()  # [Cout][kh][kw][Cin]
+        self.b = bias.float().contiguous()
+        self.cin, self.cout, self.k, self.stride, self.relu, self.relu_from = cin, cout, k, stride, relu, relu_from
+
+
+class TrunkEngine:
+    """Packed weights + forward.  `state` is the `base.*`-stripped trunk state_dict on any
+    device; `bn_head` optionally the BatchNorm1d(2048) of ModelBase (bases.py:83) for `embed`."""
+
+    def __init__(self, state: Dict[str, torch.Tensor], device, ibn: bool = False, last_stride: int = 1,
+                 layers=R50_LAYERS, bn_head: Optional[Dict[str, torch.Tensor]] = None):
+        self.device = torch.device(device)
+        self.ibn = ibn
+        sd = {k: v.detach().to(self.device) for k, v in state.items() if v.is_floating_point()}
+        w, b = _fold(sd["conv1.weight"], _bn(sd, "bn1"))
+        # stem weights as [147][64], k = (c*7 + r)*7 + s
+        self.stem_w = w.permute(1, 2, 3, 0).reshape(147, 64).contiguous()
+        self.stem_b = b.contiguous()
+        self.blocks = []
+        for li, (planes, nblk) in enumerate(zip((64, 128, 256, 512), layers), start=1):
+            stride0 = 1 if li == 1 else (last_stride if li == 4 else 2)
+            for bi in range(nblk):
+                p = f"layer{li}.{bi}"
+                stride = stride0 if bi == 0 else 1
+                blk = {}
+                if ibn and planes != 512:  # resnet_ibn_a.py:116-119
+                    half = planes // 2
+                    wbn, bbn = _fold(sd[p + ".conv1.weight"][half:], _bn(sd, p + ".bn1.BN"))
+                    w1 = torch.cat((sd[p + ".conv1.weight"][:half].float(), wbn), 0)
+                    b1 = torch.cat((torch.zeros(half, device=self.device), bbn), 0)
+                    blk["conv1"] = _Conv(w1, b1, 1, True, relu_from=half)
+                    blk["in"] = (half, sd[p + ".bn1.IN.weight"].float().contiguous(),
+                                 sd[p + ".bn1.IN.bias"].float().contiguous())
+                else:
+                    blk["conv1"] = _Conv(*_fold(sd[p + ".conv1.weight"], _bn(sd, p + ".bn1")), 1, True)
+                blk["conv2"] = _Conv(*_fold(sd[p + ".conv2.weight"], _bn(sd, p + ".bn2")), stride, True)
+                blk["conv3"] = _Conv(*_fold(sd[p + ".conv3.weight"], _bn(sd, p + ".bn3")), 1, True)
+                if bi == 0:
+                    blk["down"] = _Conv(*_fold(sd[p + ".downsample.0.weight"], _bn(sd, p + ".downsample.1")),
+                                        stride, False)
+                self.blocks.append(blk)
+        self.out_channels = self.blocks[-1]["conv3"].cout
+        self.head = None
+        if bn_head is not None:
+            scale = bn_head["weight"].float() / torch.sqrt(bn_head["running_var"].float() + BN_EPS)
+            shift = bn_head["bias"].float() - bn_head["running_mean"].float() * scale
+            self.head = (scale.to(self.device).contiguous(), shift.to(self.device).contiguous())
+
+    # -- single ops --------------------------------------------------------------------------
+    def _conv(self, x, n, h, w, c: _Conv, residual=None):
+        pad = 1 if c.k == 3 else 0
+        ho, wo = (h + 2 * pad - c.k) // c.stride + 1, (w + 2 * pad - c.k) // c.stride + 1
+        out = torch.empty(n, ho, wo, c.cout, dtype=torch.float16, device=self.device)
+        N.check(N.lib().ctl_conv2d_nhwc_f16(x.data_ptr(), n, h, w, c.cin, c.w.data_ptr(), c.b.data_ptr(),
+                                            N.ptr(residual), out.data_ptr(), c.cout, c.k, c.stride, int(c.relu),
+                                            c.relu_from, N.stream_ptr()))
+        return out, ho, wo
+
+    def forward(self, x: torch.Tensor, want_base: bool = False, want_emb: bool = False):
+        """x: [B, 3, H, W] fp32 NCHW on the device -> dict(global_feat [B, C] fp32,
+        base_out NHWC fp16 (if want_base), emb (if want_emb and a head was given))."""
+        N.require_cuda(x)
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError(f"expected [B, 3, H, W], got {tuple(x.shape)}")
+        x = x.float().contiguous()
+        n, _, H, W = x.shape
+        L = N.lib()
+        with torch.cuda.device(self.device):
+            h, w = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+            s = torch.empty(n, h, w, 64, dtype=torch.float16, device=self.device)
+            N.check(L.ctl_stem_conv7x7(x.data_ptr(), n, H, W, self.stem_w.data_ptr(), self.stem_b.data_ptr(),
+                                       int(self.ibn), s.data_ptr(), N.stream_ptr()))
+            hp, wp = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+            a = torch.empty(n, hp, wp, 64, dtype=torch.float16, device=self.device)
+            N.check(L.ctl_maxpool3x3s2_nhwc_f16(s.data_ptr(), n, h, w, 64, a.data_ptr(), N.stream_ptr()))
+            h, w = hp, wp
+            for blk in self.blocks:
+                o1, h1, w1 = self._conv(a, n, h, w, blk["conv1"])
+                if "in" in blk:
+                    half, g, b = blk["in"]
+                    N.check(L.ctl_instnorm_relu_nhwc_f16(o1.data_ptr(), n, h1 * w1, blk["conv1"].cout, half,
+                                                         g.data_ptr(), b.data_ptr(), BN_EPS, N.stream_ptr()))
+                o2, h2, w2 = self._conv(o1, n, h1, w1, blk["conv2"])
+                res = a
+                if "down" in blk:
+                    res, _, _ = self._conv(a, n, h, w, blk["down"])
+                a, h, w = self._conv(o2, n, h2, w2, blk["conv3"], residual=res)
+            c = self.out_channels
+            feat = torch.empty(n, c, dtype=torch.float32, device=self.device)
+            emb = torch.empty(n, c, dtype=torch.float32, device=self.device) if (want_emb and self.head) else None
+            sc, sh = self.head if self.head else (None, None)
+            N.check(L.ctl_gap_bn_nhwc_f16(a.data_ptr(), n, h * w, c, N.ptr(sc), N.ptr(sh), feat.data_ptr(),
+                                          N.ptr(emb), N.stream_ptr()))
+        out = {"global_feat": feat}
+        if want_base:
+            out["base_out_nhwc"] = a
+        if emb is not None:
+            out["emb"] = emb
+        return out

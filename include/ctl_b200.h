@@ -160,6 +160,32 @@ int ctl_xent_smooth_step(const float* logits, int32_t b, int32_t c, const int32_
                          float* out_loss, float* d_logits, void* workspace, size_t workspace_bytes,
                          ctl_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Trunk inference forward (ResNet50 / ResNet50-IBN-A), NHWC fp16 activations
+ * replaces: modelling/backbones/resnet.py:51-133, resnet_ibn_a.py:18-141,
+ * modelling/baseline.py:91-96, modelling/bases.py:169-177, inference/inference_utils.py:104-113.
+ *   conv2d   : out = [relu]( conv(x, weight) + bias [+ residual] ), weight [Cout][k][k][Cin] fp16
+ *              (eval BatchNorm folded in), 1x1 or 3x3 (pad k/2), stride 1 or 2, Cin/Cout % 64 == 0;
+ *              ReLU (if relu != 0) is applied to output channels >= relu_from only (IBN: the
+ *              InstanceNorm half of bn1 is left raw for ctl_instnorm_relu);
+ *   stem     : conv 7x7/2 pad 3 (3 -> 64) + folded BN [+ ReLU] from NCHW fp32 to NHWC fp16;
+ *              weight_k64 = [147][64] fp32 with k = (c*7 + r)*7 + s;
+ *   maxpool  : 3x3 / 2, pad 1;
+ *   gap_bn   : feat = mean over H*W (fp32), emb = feat * bn_scale + bn_shift (eval BatchNorm1d);
+ *   instnorm : per-(image, channel) InstanceNorm(affine) + ReLU in place on channels [0, half).
+ * ---------------------------------------------------------------------------------------- */
+int ctl_conv2d_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, int32_t cin, const void* weight,
+                        const float* bias, const void* residual, void* out, int32_t cout, int32_t ksize,
+                        int32_t stride, int32_t relu, int32_t relu_from, ctl_stream_t stream);
+int ctl_stem_conv7x7(const float* x_nchw, int32_t n, int32_t h, int32_t w, const float* weight_k64, const float* bias,
+                     int32_t relu, void* out_nhwc_f16, ctl_stream_t stream);
+int ctl_maxpool3x3s2_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, void* out,
+                              ctl_stream_t stream);
+int ctl_gap_bn_nhwc_f16(const void* x, int32_t n, int32_t hw, int32_t c, const float* bn_scale, const float* bn_shift,
+                        float* feat, float* emb, ctl_stream_t stream);
+int ctl_instnorm_relu_nhwc_f16(void* x, int32_t n, int32_t hw, int32_t c, int32_t half, const float* gamma,
+                               const float* beta, float eps, ctl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

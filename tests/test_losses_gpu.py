@@ -50,7 +50,9 @@ def test_ctl_step_matches_reference_training_step(name):
     _close(float(gc.abs().sum()) / 5e-4, float(g["grad_centers_abs_sum"]), RTOL)
     _close(bn_w.grad.cpu().numpy(), g["grad_bn_weight"], 1e-3, 1e-4 * np.abs(g["grad_bn_weight"]).max())
     _close(fc_w.grad.cpu()[rows].numpy(), g["grad_fc_rows"], 1e-3, 1e-4 * np.abs(g["grad_fc_rows"]).max())
-    _close(checksum(fc_w.grad.cpu()), g["grad_fc_checksum"], 1e-3, 1e-6)
+    cs = checksum(fc_w.grad.cpu())
+    assert abs(cs[0] - g["grad_fc_checksum"][0]) < 1e-3  # a sum of ~1.5M signed terms: absolute tolerance
+    _close(cs[1], g["grad_fc_checksum"][1], 1e-3)
     _close(run_mean.cpu().numpy(), g["bn_running_mean"], RTOL, 1e-6)
     _close(run_var.cpu().numpy(), g["bn_running_var"], RTOL, 1e-6)
 
@@ -61,8 +63,10 @@ def test_standalone_losses_match_oracle():
                                               hard_example_mining)
 
     feats, labels, is_real = O.synth_batch(12, 4, 512, 100, seed=9, pad_fraction=0.3)
-    # TripletLoss with an anchor mask, vs autograd through the oracle restatement
-    fo = feats.clone().requires_grad_(True)
+    # The checker runs the oracle restatement in float64: small fp32 matmuls on the GPU box's
+    # host CPU were observed to be ~2e-4 off (reduced-precision oneDNN path), which would mask
+    # real 1e-4 errors.  TripletLoss with an anchor mask, vs autograd through the oracle.
+    fo = feats.double().requires_grad_(True)
     lo, apo, ano = O.triplet_loss(fo, labels, 0.5, mask=is_real)
     lo.backward()
     fg = feats.cuda().requires_grad_(True)
@@ -75,38 +79,40 @@ def test_standalone_losses_match_oracle():
     # ragged label multiset (the reference's view() cannot do this; the masked form can)
     lab2 = torch.tensor([0, 0, 0, 1, 1, 2, 2, 2, 2, 3, 3, 4, 4, 4, 5, 5])
     f2 = torch.randn(16, 256, generator=torch.Generator().manual_seed(1))
-    l2o, _, _ = O.triplet_loss(f2, lab2, 0.3)
+    l2o, _, _ = O.triplet_loss(f2.double(), lab2, 0.3)
     l2g, _, _ = TripletLoss(0.3)(f2.cuda(), lab2.cuda())
     _close(l2g.item(), l2o.item())
     # distances
     d = euclidean_dist(feats.cuda(), feats[:7].cuda()).cpu()
-    assert float((d - O.euclidean_dist(feats, feats[:7])).abs().max()) < 1e-3  # sqrt amplifies near 0 (self pairs)
+    d_or = O.euclidean_dist(feats.double(), feats[:7].double())
+    assert float((d - d_or).abs().max()) < 2e-2  # sqrt amplifies fp32 cancellation noise on self pairs
     off = ~torch.eye(48, 7, dtype=torch.bool)
-    _close(d[off].numpy(), O.euclidean_dist(feats, feats[:7])[off].numpy(), 1e-5)
-    _close(cosine_dist(feats.cuda(), feats[:7].cuda()).cpu().numpy(), O.cosine_dist(feats, feats[:7]).numpy(), 0, 2e-6)
+    _close(d[off].numpy(), d_or[off].numpy(), 1e-5)
+    _close(cosine_dist(feats.cuda(), feats[:7].cuda()).cpu().numpy(),
+           O.cosine_dist(feats.double(), feats[:7].double()).numpy(), 0, 2e-6)
     dm = O.euclidean_dist(feats, feats)
     ap, an, pi, ni = hard_example_mining(dm.cuda(), labels.cuda(), return_inds=True)
     apo2, ano2 = O.hard_example_mining(dm, labels)
     assert torch.equal(ap.cpu(), apo2) and torch.equal(an.cpu(), ano2)
     # CenterLoss
     cl = CenterLoss(100, 512).cuda()
-    xo = feats.clone().requires_grad_(True)
-    co = cl.centers.detach().cpu().clone().requires_grad_(True)
+    xo = feats.double().requires_grad_(True)
+    co = cl.centers.detach().cpu().double().requires_grad_(True)
     O.center_loss(xo, labels, co).backward()
     xg = feats.cuda().requires_grad_(True)
     loss_g = cl(xg, labels.cuda())
     loss_g.backward()
-    _close(loss_g.item(), O.center_loss(feats, labels, co.detach()).item())
+    _close(loss_g.item(), O.center_loss(feats.double(), labels, co.detach()).item())
     _close(xg.grad.cpu().numpy(), xo.grad.numpy(), RTOL, 1e-6)
     _close(cl.centers.grad.cpu().numpy(), co.grad.numpy(), RTOL, 1e-6)
     # CrossEntropyLabelSmooth
     z = torch.randn(48, 100, generator=torch.Generator().manual_seed(2)) * 3
-    zo = z.clone().requires_grad_(True)
+    zo = z.double().requires_grad_(True)
     O.cross_entropy_label_smooth(zo, labels, 100).backward()
     zg = z.cuda().requires_grad_(True)
     lx = CrossEntropyLabelSmooth(100)(zg, labels.cuda())
     lx.backward()
-    _close(lx.item(), O.cross_entropy_label_smooth(z, labels, 100).item())
+    _close(lx.item(), O.cross_entropy_label_smooth(z.double(), labels, 100).item())
     _close(zg.grad.cpu().numpy(), zo.grad.numpy(), RTOL, 1e-7)
 
 

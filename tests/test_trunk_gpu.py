@@ -1,0 +1,148 @@
+"""GPU parity tests of the trunk inference forward (csrc/conv.cu) through the C ABI.
+
+Checker for single ops: float64 torch-CPU convolution of the SAME fp16-rounded operands (so
+only the fp32 accumulation order and the final fp16 rounding differ): tolerance 1 fp16 ulp of
+the output magnitude (2^-10 relative) + 1e-3 absolute.
+Checker for the whole trunk: oracle.trunk_forward_fp16sim (same rounding points), tolerance
+3e-3 of the feature scale; and the fp32 reference's golden features within 1e-2 (an fp16
+trunk cannot meet 1e-4 against fp32 -- SURVEY section 7; DESIGN.md 'Parity')."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden
+from oracle import ctl_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _conv_case(n, h, w, cin, cout, k, stride, relu, residual, relu_from=0, seed=0):
+    from ctl_b200 import _native as N
+
+    g = torch.Generator().manual_seed(seed)
+    x = (torch.randn(n, h, w, cin, generator=g) * 0.5).half()
+    wt = (torch.randn(cout, k, k, cin, generator=g) / (k * (cin ** 0.5))).half()
+    bias = torch.randn(cout, generator=g) * 0.1
+    pad = 1 if k == 3 else 0
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    res = (torch.randn(n, ho, wo, cout, generator=g) * 0.5).half() if residual else None
+    ref = F.conv2d(x.double().permute(0, 3, 1, 2), wt.double().permute(0, 3, 1, 2), bias.double(), stride, pad)
+    ref = ref.permute(0, 2, 3, 1)
+    if res is not None:
+        ref = ref + res.double()
+    if relu:
+        ref[..., relu_from:] = ref[..., relu_from:].clamp(min=0)
+    xd, wd, bd = x.cuda(), wt.cuda(), bias.cuda()
+    rd = res.cuda() if res is not None else None
+    out = torch.full((n, ho, wo, cout), float("nan"), dtype=torch.float16, device="cuda")
+    N.check(N.lib().ctl_conv2d_nhwc_f16(xd.data_ptr(), n, h, w, cin, wd.data_ptr(), bd.data_ptr(), N.ptr(rd),
+                                        out.data_ptr(), cout, k, stride, int(relu), relu_from, N.stream_ptr()))
+    torch.cuda.synchronize()
+    got = out.cpu().double()
+    assert torch.isfinite(got).all(), "unwritten or non-finite outputs"
+    err = (got - ref).abs()
+    tol = ref.abs() * 2.0 ** -10 + 1e-3
+    bad = err > tol
+    assert not bad.any(), (f"{int(bad.sum())} / {bad.numel()} outputs off; max err {float(err.max()):.4e}; first bad "
+                           f"index {bad.nonzero()[0].tolist()}")
+
+
+@pytest.mark.parametrize("case", [
+    # n, h, w, cin, cout, k, stride, relu, residual
+    (2, 64, 32, 64, 64, 1, 1, True, False),
+    (2, 64, 32, 64, 256, 1, 1, True, True),
+    (2, 64, 32, 256, 64, 1, 1, True, False),
+    (2, 64, 32, 64, 64, 3, 1, True, False),
+    (3, 32, 16, 128, 128, 3, 1, True, False),
+    (3, 16, 8, 512, 512, 3, 1, True, False),
+    (2, 64, 32, 128, 128, 3, 2, True, False),
+    (3, 32, 16, 256, 256, 3, 2, True, False),
+    (2, 64, 32, 256, 512, 1, 2, False, False),
+    (3, 16, 8, 1024, 2048, 1, 1, False, False),
+    (3, 16, 8, 2048, 512, 1, 1, True, False),
+    (5, 16, 8, 512, 2048, 1, 1, True, True),
+    (2, 20, 20, 256, 256, 3, 1, True, False),     # 320x320 geometry: partial tiles
+    (1, 80, 80, 64, 64, 3, 1, True, False),
+    (2, 40, 40, 128, 128, 3, 2, True, False),
+    (1, 7, 5, 64, 128, 3, 1, False, True),        # tiny, heavily over-covered tile
+])
+def test_conv_shapes(case):
+    _conv_case(*case)
+
+
+def test_conv_relu_from_channel():
+    _conv_case(2, 32, 16, 256, 128, 1, 1, True, False, relu_from=64, seed=3)
+
+
+def test_stem_maxpool_gap_instnorm():
+    from ctl_b200 import _native as N
+
+    L = N.lib()
+    g = torch.Generator().manual_seed(5)
+    n, H, W = 3, 64, 48
+    x = torch.randn(n, 3, H, W, generator=g)
+    w = torch.randn(64, 3, 7, 7, generator=g) * 0.1
+    b = torch.randn(64, generator=g) * 0.1
+    for relu in (0, 1):
+        ref = F.conv2d(x.double(), w.double(), b.double(), 2, 3)
+        if relu:
+            ref = ref.clamp(min=0)
+        ho, wo = ref.shape[2:]
+        out = torch.empty(n, ho, wo, 64, dtype=torch.float16, device="cuda")
+        wk = w.permute(1, 2, 3, 0).reshape(147, 64).contiguous().cuda()
+        N.check(L.ctl_stem_conv7x7(x.cuda().data_ptr(), n, H, W, wk.data_ptr(), b.cuda().data_ptr(), relu,
+                                   out.data_ptr(), N.stream_ptr()))
+        got = out.cpu().double().permute(0, 3, 1, 2)
+        assert float((got - ref).abs().max()) <= float(ref.abs().max()) * 2.0 ** -10 + 1e-4
+    s = out  # relu'd stem output, NHWC fp16
+    hp, wp = (ho + 2 - 3) // 2 + 1, (wo + 2 - 3) // 2 + 1
+    pooled = torch.empty(n, hp, wp, 64, dtype=torch.float16, device="cuda")
+    N.check(L.ctl_maxpool3x3s2_nhwc_f16(s.data_ptr(), n, ho, wo, 64, pooled.data_ptr(), N.stream_ptr()))
+    refp = F.max_pool2d(s.cpu().float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    assert torch.equal(pooled.cpu().float(), refp)
+    # global average pool + eval BatchNorm1d
+    act = (torch.randn(4, 16, 8, 2048, generator=g)).half().cuda()
+    sc, sh = (torch.rand(2048, generator=g) + 0.5).cuda(), torch.randn(2048, generator=g).cuda()
+    feat, emb = torch.empty(4, 2048, device="cuda"), torch.empty(4, 2048, device="cuda")
+    N.check(L.ctl_gap_bn_nhwc_f16(act.data_ptr(), 4, 128, 2048, sc.data_ptr(), sh.data_ptr(), feat.data_ptr(),
+                                  emb.data_ptr(), N.stream_ptr()))
+    rf = act.cpu().double().mean(dim=(1, 2))
+    np.testing.assert_allclose(feat.cpu().numpy(), rf.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(emb.cpu().numpy(), (rf * sc.cpu().double() + sh.cpu().double()).numpy(), rtol=1e-5,
+                               atol=1e-5)
+    # InstanceNorm + ReLU on the first half of the channels, second half untouched
+    t = (torch.randn(2, 20, 12, 128, generator=g) * 2 + 0.3).half()
+    gam, bet = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.2
+    td = t.clone().cuda()
+    N.check(L.ctl_instnorm_relu_nhwc_f16(td.data_ptr(), 2, 240, 128, 64, gam.cuda().data_ptr(), bet.cuda().data_ptr(),
+                                         1e-5, N.stream_ptr()))
+    ref_in = F.relu(F.instance_norm(t[..., :64].double().permute(0, 3, 1, 2), None, None, gam.double(), bet.double(),
+                                    True, 0.1, 1e-5)).permute(0, 2, 3, 1)
+    got = td.cpu()
+    assert torch.equal(got[..., 64:], t[..., 64:])
+    assert float((got[..., :64].double() - ref_in).abs().max()) <= float(ref_in.abs().max()) * 2.0 ** -10 + 2e-3
+
+
+@pytest.mark.parametrize("tag,ibn,hw", [("r50", False, (256, 128)), ("ibn", True, (128, 64))])
+def test_full_trunk_matches_checker_and_reference_golden(tag, ibn, hw):
+    from ctl_b200.modelling.backbones.engine import TrunkEngine
+
+    g = load_golden("trunk.npz")
+    sd = O.make_trunk_state(seed=7, ibn=ibn)
+    x = torch.randn(2, 3, *hw, generator=torch.Generator().manual_seed(21))
+    head = dict(weight=torch.rand(2048) + 0.5, bias=torch.randn(2048) * 0.1, running_mean=torch.randn(2048) * 0.1,
+                running_var=torch.rand(2048) + 0.5)
+    eng = TrunkEngine(sd, "cuda", ibn=ibn, bn_head=head)
+    out = eng.forward(x.cuda(), want_emb=True)
+    feat = out["global_feat"].cpu()
+    with torch.no_grad():
+        _, sim = O.trunk_forward_fp16sim(x, sd, ibn=ibn)
+    scale = float(sim.abs().max())
+    err_sim = float((feat - sim).abs().max())
+    err_ref = float((feat - torch.from_numpy(g[f"{tag}_eval_feat"])).abs().max())
+    print(f"{tag}: |feat|max {scale:.4f}  err vs fp16-sim {err_sim:.3e}  err vs fp32 reference {err_ref:.3e}")
+    assert err_sim <= 3e-3 * scale
+    assert err_ref <= 1e-2 * scale
+    emb_ref = F.batch_norm(feat, head["running_mean"], head["running_var"], head["weight"], head["bias"], False, 0.1, 1e-5)
+    np.testing.assert_allclose(out["emb"].cpu().numpy(), emb_ref.numpy(), rtol=1e-5, atol=1e-5)
