@@ -45,6 +45,15 @@ class LossConfig(C.Structure):
 
 _cfgp = C.POINTER(LossConfig)
 
+
+class PassDesc(C.Structure):
+    """struct ctl_pass_desc (include/ctl_b200.h)."""
+
+    _fields_ = [("dist_out", _p), ("ld_out", _i64), ("gmin", _p), ("tau", _p), ("cand_keys", _p),
+                ("cand_count", _p), ("cand_cap", _i32), ("q_pid", _p), ("q_cam", _p), ("g_pid", _p),
+                ("g_cammask", _p), ("pos_keys", _p), ("pos_count", _p), ("max_pos", _i32), ("thr_keys", _p),
+                ("thr_count", _p), ("buckets", _p), ("overflow", _p), ("g_index_offset", _i64)]
+
 # name -> (restype, argtypes); kept in one table so tests can check it against the header
 SIGNATURES = {
     "ctl_last_error": (C.c_char_p, []),
@@ -59,6 +68,11 @@ SIGNATURES = {
     "ctl_sort_key_rows": (C.c_int, [_p, _p, _i64, _i32, _p]),
     "ctl_eval_count": (C.c_int, [_p, _i64, _p, _i64, _i32, _i32, _p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p]),
     "ctl_eval_finalize": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p]),
+    "ctl_dist_pass": (C.c_int, [_p, _i64, _p, _i64, _i32, _i32, C.POINTER(PassDesc), _p]),
+    "ctl_topk_plan": (C.c_int, [_i64, _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
+    "ctl_select_tau": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p]),
+    "ctl_fill_f32": (C.c_int, [_p, _i64, C.c_float, _p]),
+    "ctl_topk_emit": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p, _p, _p]),
     "ctl_key_encode": (C.c_uint64, [C.c_float, C.c_uint32]),
     "ctl_key_decode": (None, [C.c_uint64, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
     "ctl_segment_mean": (C.c_int, [_p, _i64, _i32, _p, _p, _i64, _p, _p]),

@@ -789,6 +789,89 @@ int ctl_eval_finalize(const int32_t* buckets, const int32_t* pos_count, int64_t 
   return 0;
 }
 
+int ctl_dist_pass(const void* q_planes, int64_t nq, const void* g_planes, int64_t ng, int32_t d, int32_t flags,
+                  const ctl_pass_desc* desc, ctl_stream_t stream) {
+  CTL_CHECK_ARG(desc != nullptr, "null pass descriptor");
+  const ctl_pass_desc& e = *desc;
+  GemmPass p = {};
+  p.dist_out = e.dist_out;
+  p.ld_out = e.ld_out;
+  CTL_CHECK_ARG(!e.dist_out || e.ld_out >= ng, "ld_out too small");
+  p.gmin = e.gmin;
+  p.n_groups = (int)((ng + GROUP_W - 1) / GROUP_W);
+  p.tau = e.tau;
+  p.cand_keys = reinterpret_cast<unsigned long long*>(e.cand_keys);
+  p.cand_count = e.cand_count;
+  p.cand_cap = e.cand_cap;
+  CTL_CHECK_ARG(!e.cand_keys || (e.tau && e.cand_count && e.cand_cap > 0 && e.overflow), "candidate output needs tau, counts, capacity, overflow");
+  p.q_pid = e.q_pid;
+  p.q_cam = e.q_cam;
+  p.g_pid = e.g_pid;
+  p.g_mask = reinterpret_cast<const unsigned long long*>(e.g_cammask);
+  CTL_CHECK_ARG(!(e.pos_keys || e.buckets) || (e.q_pid && e.q_cam && e.g_pid && e.g_cammask && e.max_pos >= 1),
+                "evaluation epilogues need the identity arrays and max_pos");
+  p.pos_keys = reinterpret_cast<unsigned long long*>(e.pos_keys);
+  p.pos_count = e.pos_count;
+  CTL_CHECK_ARG(!e.pos_keys || (e.pos_count && e.overflow), "collect needs pos_count and overflow");
+  p.max_pos = e.max_pos;
+  p.thr_keys = reinterpret_cast<const unsigned long long*>(e.thr_keys);
+  p.thr_count = e.thr_count;
+  p.buckets = e.buckets;
+  CTL_CHECK_ARG(!e.buckets || (e.thr_keys && e.thr_count), "count needs the sorted positives");
+  p.overflow = e.overflow;
+  p.g_off = e.g_index_offset;
+  CTL_CHECK_ARG(e.g_index_offset >= 0 && e.g_index_offset + ng < (1ll << 32), "gallery index out of uint32 range");
+  if (!p.pos_keys && !p.buckets) p.q_pid = nullptr;  // identities unused
+  return launch_gemm_pass(q_planes, nq, g_planes, ng, d, flags, p, (cudaStream_t)stream);
+}
+
+int ctl_topk_plan(int64_t ng, int32_t k, int32_t* emit_all, int32_t* n_groups, int32_t* merge, int32_t* cand_cap) {
+  CTL_CHECK_ARG(emit_all && n_groups && merge && cand_cap && k >= 1 && k <= ng, "bad arguments (k=%d ng=%lld)", k, (long long)ng);
+  TopkPlan pl;
+  int rc = plan_topk(ng, k, &pl);
+  if (rc) return rc;
+  *emit_all = pl.emit_all ? 1 : 0;
+  *n_groups = pl.n_groups;
+  *merge = pl.merge;
+  *cand_cap = pl.cap;
+  return 0;
+}
+
+int ctl_select_tau(const float* gmin, int64_t nq, int32_t n_groups, int32_t merge, int32_t k, float* tau,
+                   ctl_stream_t stream) {
+  CTL_CHECK_ARG(gmin && tau && nq > 0 && n_groups > 0 && merge >= 1 && k >= 1, "bad arguments");
+  const int n_merged = (n_groups + merge - 1) / merge;
+  CTL_CHECK_ARG(n_merged >= k && n_merged <= SELECT_MAX, "need k <= merged groups <= %d (have %d)", SELECT_MAX, n_merged);
+  int rc = ctl_device_check();
+  if (rc) return rc;
+  const int np2 = next_pow2(n_merged);
+  select_tau_kernel<<<(unsigned)nq, 256, np2 * sizeof(uint32_t), (cudaStream_t)stream>>>(gmin, n_groups, merge, k, np2, tau);
+  CTL_LAUNCH_CHECK();
+  return 0;
+}
+
+int ctl_fill_f32(float* p, int64_t n, float value, ctl_stream_t stream) {
+  CTL_CHECK_ARG(p && n > 0, "bad arguments");
+  int rc = ctl_device_check();
+  if (rc) return rc;
+  fill_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, n, value);
+  CTL_LAUNCH_CHECK();
+  return 0;
+}
+
+int ctl_topk_emit(const uint64_t* cand_keys_sorted, const int32_t* cand_count, int64_t nq, int32_t cand_cap, int32_t k,
+                  int64_t* out_idx, float* out_dist, int32_t* overflow, ctl_stream_t stream) {
+  CTL_CHECK_ARG(cand_keys_sorted && cand_count && out_idx && out_dist && overflow && nq > 0 && k >= 1 && k <= cand_cap, "bad arguments");
+  int rc = ctl_device_check();
+  if (rc) return rc;
+  const int64_t total = nq * k;
+  topk_emit_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const unsigned long long*>(cand_keys_sorted), cand_count, cand_cap, k, nq, (long long*)out_idx,
+      out_dist, overflow);
+  CTL_LAUNCH_CHECK();
+  return 0;
+}
+
 uint64_t ctl_key_encode(float dist, uint32_t index) { return make_key(dist, index); }
 void ctl_key_decode(uint64_t key, float* dist, uint32_t* index) {
   if (dist) *dist = orderable_float((uint32_t)(key >> 32));

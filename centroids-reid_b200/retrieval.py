@@ -297,3 +297,63 @@ def topk_sharded(q_local: torch.Tensor, g_local: torch.Tensor, k: int, g_index_o
     if int(ovf.item()) != 0:
         raise OverflowError("top-k candidate capacity exceeded on some rank")
     return merge_topk(idx_all, dst_all, k)
+
+
+def topk_and_eval(qp: Planes, gp: Planes, k: int, q_pids, g_pids, q_camids, g_camids, max_rank: int = 50,
+                  respect_camids: bool = False):
+    """BASELINE config 3 in TWO tensor-core passes: per-query top-k (ascending (distance, index))
+    AND eval_func's CMC / mAP, neither materialising the distance matrix.
+      pass 1: 16-column group minima (-> tau) + the positives' distances
+      pass 2: candidates <= tau + kept rows before each positive
+    Returns (idx [nq,k] int64, dist [nq,k] float32 on the device, EvalResult)."""
+    import ctypes as C
+
+    L = N.lib()
+    dev = qp.buf.device
+    nq, ng = qp.n, gp.n
+    k = int(min(k, ng))
+    emit_all, n_groups, merge, cap = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+    N.check(L.ctl_topk_plan(ng, k, C.byref(emit_all), C.byref(n_groups), C.byref(merge), C.byref(cap)))
+    q_pid, q_cam, g_pid, g_mask, max_pos = encode_identities(q_pids, g_pids, q_camids, g_camids, respect_camids)
+
+    def to_dev(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
+
+    d_qpid, d_qcam, d_gpid, d_gmask = to_dev(q_pid), to_dev(q_cam), to_dev(g_pid), to_dev(g_mask.view(np.int64))
+    gmin = torch.empty(nq, n_groups.value, dtype=torch.float32, device=dev)
+    tau = torch.empty(nq, dtype=torch.float32, device=dev)
+    cand = torch.empty(nq, cap.value, dtype=torch.int64, device=dev)
+    zeros = torch.zeros(2 * nq + 1, dtype=torch.int32, device=dev)
+    cand_count, pos_count, ovf = zeros[:nq], zeros[nq: 2 * nq], zeros[2 * nq:]
+    pos_keys = torch.empty(nq, max_pos, dtype=torch.int64, device=dev)
+    buckets = torch.zeros(nq, max_pos + 1, dtype=torch.int32, device=dev)
+    idx = torch.empty(nq, k, dtype=torch.int64, device=dev)
+    dst = torch.empty(nq, k, dtype=torch.float32, device=dev)
+    ranks = torch.empty(nq, max_pos, dtype=torch.int32, device=dev)
+    ap = torch.empty(nq, dtype=torch.float64, device=dev)
+    s = N.stream_ptr
+    ids = dict(q_pid=d_qpid.data_ptr(), q_cam=d_qcam.data_ptr(), g_pid=d_gpid.data_ptr(),
+               g_cammask=d_gmask.data_ptr(), max_pos=max_pos, overflow=ovf.data_ptr())
+    with torch.cuda.device(dev):
+        p1 = N.PassDesc(pos_keys=pos_keys.data_ptr(), pos_count=pos_count.data_ptr(), **ids)
+        if not emit_all.value:
+            p1.gmin = gmin.data_ptr()
+        N.check(L.ctl_dist_pass(qp.ptr, nq, gp.ptr, ng, qp.d, qp.flags, C.byref(p1), s()))
+        if emit_all.value:
+            N.check(L.ctl_fill_f32(tau.data_ptr(), nq, float("inf"), s()))
+        else:
+            N.check(L.ctl_select_tau(gmin.data_ptr(), nq, n_groups.value, merge.value, k, tau.data_ptr(), s()))
+        N.check(L.ctl_sort_key_rows(pos_keys.data_ptr(), pos_count.data_ptr(), nq, max_pos, s()))
+        p2 = N.PassDesc(tau=tau.data_ptr(), cand_keys=cand.data_ptr(), cand_count=cand_count.data_ptr(),
+                        cand_cap=cap.value, thr_keys=pos_keys.data_ptr(), thr_count=pos_count.data_ptr(),
+                        buckets=buckets.data_ptr(), **ids)
+        N.check(L.ctl_dist_pass(qp.ptr, nq, gp.ptr, ng, qp.d, qp.flags, C.byref(p2), s()))
+        N.check(L.ctl_sort_key_rows(cand.data_ptr(), cand_count.data_ptr(), nq, cap.value, s()))
+        N.check(L.ctl_topk_emit(cand.data_ptr(), cand_count.data_ptr(), nq, cap.value, k, idx.data_ptr(),
+                                dst.data_ptr(), ovf.data_ptr(), s()))
+        N.check(L.ctl_eval_finalize(buckets.data_ptr(), pos_count.data_ptr(), nq, max_pos, ranks.data_ptr(),
+                                    ap.data_ptr(), s()))
+    ranks_h, ap_h, cnt_h, ovf_h = ranks.cpu().numpy(), ap.cpu().numpy(), pos_count.cpu().numpy(), int(ovf.item())
+    if ovf_h:
+        raise OverflowError("a device-side list overflowed (exact ties at the k-th distance, or max_pos)")
+    return idx, dst, _aggregate(ranks_h, ap_h, cnt_h, np.asarray(q_pids), ng, max_rank)

@@ -98,6 +98,42 @@ int ctl_eval_count(const void* q_planes, int64_t nq, const void* g_planes, int64
                    const int32_t* pos_count, int32_t* buckets, ctl_stream_t stream);
 int ctl_eval_finalize(const int32_t* buckets, const int32_t* pos_count, int64_t nq, int32_t max_pos, int32_t* ranks,
                       double* ap, ctl_stream_t stream);
+/* One generic pass of the distance GEMM with any combination of the streamed epilogues (the
+ * entry points above are compositions of this one).  NULL pointers disable a feature.
+ * With both top-k and evaluation wanted, TWO passes serve both:
+ *   pass 1: gmin (+ pos_keys/pos_count)            -> ctl_select_tau, ctl_sort_key_rows
+ *   pass 2: tau + cand_keys (+ thr_keys + buckets) -> ctl_sort_key_rows, ctl_topk_emit,
+ *                                                     ctl_eval_finalize */
+typedef struct ctl_pass_desc {
+  float* dist_out;            /* [nq, ld_out] full matrix */
+  int64_t ld_out;
+  float* gmin;                /* [nq, n_groups] minima of 16-column groups, n_groups = ceil(ng/16) */
+  const float* tau;           /* [nq] candidate threshold */
+  uint64_t* cand_keys;        /* [nq, cand_cap] rows with dist <= tau */
+  int32_t* cand_count;        /* [nq], zeroed by the caller */
+  int32_t cand_cap;
+  const int32_t* q_pid;       /* identities: see ctl_eval_collect */
+  const int32_t* q_cam;
+  const int32_t* g_pid;
+  const uint64_t* g_cammask;
+  uint64_t* pos_keys;         /* [nq, max_pos] (collect) */
+  int32_t* pos_count;         /* [nq], zeroed by the caller */
+  int32_t max_pos;
+  const uint64_t* thr_keys;   /* [nq, max_pos] sorted positives (count) */
+  const int32_t* thr_count;
+  int32_t* buckets;           /* [nq, max_pos + 1], zeroed by the caller */
+  int32_t* overflow;          /* device int, set non-zero when a list overflows */
+  int64_t g_index_offset;
+} ctl_pass_desc;
+int ctl_dist_pass(const void* q_planes, int64_t nq, const void* g_planes, int64_t ng, int32_t d, int32_t flags,
+                  const ctl_pass_desc* desc, ctl_stream_t stream);
+/* top-k plan for (ng, k): emit_all != 0 means "skip pass 1, tau = +inf". */
+int ctl_topk_plan(int64_t ng, int32_t k, int32_t* emit_all, int32_t* n_groups, int32_t* merge, int32_t* cand_cap);
+int ctl_select_tau(const float* gmin, int64_t nq, int32_t n_groups, int32_t merge, int32_t k, float* tau,
+                   ctl_stream_t stream);
+int ctl_fill_f32(float* p, int64_t n, float value, ctl_stream_t stream);
+int ctl_topk_emit(const uint64_t* cand_keys_sorted, const int32_t* cand_count, int64_t nq, int32_t cand_cap, int32_t k,
+                  int64_t* out_idx, float* out_dist, int32_t* overflow, ctl_stream_t stream);
 /* key <-> (distance, index) helpers for host-side merges of per-shard results */
 uint64_t ctl_key_encode(float dist, uint32_t index);
 void ctl_key_decode(uint64_t key, float* dist, uint32_t* index);

@@ -85,7 +85,9 @@ def test_standalone_losses_match_oracle():
     # distances
     d = euclidean_dist(feats.cuda(), feats[:7].cuda()).cpu()
     d_or = O.euclidean_dist(feats.double(), feats[:7].double())
-    assert float((d - d_or).abs().max()) < 2e-2  # sqrt amplifies fp32 cancellation noise on self pairs
+    # self pairs: sqrt of the fp32 cancellation noise of |x|^2+|x|^2-2x.x (~1e-3 at |x|^2~520), the same
+    # quirk as the reference's own d(a,a); everything else to 1e-5 below
+    assert float((d - d_or).abs().max()) < 0.1
     off = ~torch.eye(48, 7, dtype=torch.bool)
     _close(d[off].numpy(), d_or[off].numpy(), 1e-5)
     _close(cosine_dist(feats.cuda(), feats[:7].cuda()).cpu().numpy(),

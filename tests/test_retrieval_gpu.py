@@ -169,3 +169,17 @@ def test_errors(R):
     qp = R.build_planes(q)
     idx, dst, ovf = R.topk(qp, qp, 100)                 # k clamps to ng like indices[:, :topk]
     assert idx.shape == (8, 8)
+
+
+def test_fused_two_pass_topk_and_eval(R):
+    """The two-pass composition (what bench.py times) == the separate entry points."""
+    for nq, ng, nid, dim in ((300, 5000, 200, 512), (64, 600, 30, 2048)):
+        feats, pids, cams = O.synth_retrieval(nq, ng, nid, dim, 2.0, 13, num_cams=3)
+        q, gal = feats[:nq].cuda(), feats[nq:].cuda()
+        qp, gp = R.build_planes(q), R.build_planes(gal)
+        idx, dst, res = R.topk_and_eval(qp, gp, 100, pids[:nq], pids[nq:], cams[:nq], cams[nq:])
+        idx2, dst2, _ = R.topk(qp, gp, 100)
+        res2 = R.evaluate_streamed(qp, gp, pids[:nq], pids[nq:], cams[:nq], cams[nq:])
+        assert torch.equal(idx, idx2) and torch.equal(dst, dst2)
+        assert np.array_equal(res.cmc, res2.cmc) and res.mAP == res2.mAP
+        assert np.array_equal(res.ranks, res2.ranks)

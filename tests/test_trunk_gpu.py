@@ -91,8 +91,10 @@ def test_stem_maxpool_gap_instnorm():
         ho, wo = ref.shape[2:]
         out = torch.empty(n, ho, wo, 64, dtype=torch.float16, device="cuda")
         wk = w.permute(1, 2, 3, 0).reshape(147, 64).contiguous().cuda()
-        N.check(L.ctl_stem_conv7x7(x.cuda().data_ptr(), n, H, W, wk.data_ptr(), b.cuda().data_ptr(), relu,
+        xd, bd = x.cuda(), b.cuda()  # keep the device buffers alive across the call
+        N.check(L.ctl_stem_conv7x7(xd.data_ptr(), n, H, W, wk.data_ptr(), bd.data_ptr(), relu,
                                    out.data_ptr(), N.stream_ptr()))
+        torch.cuda.synchronize()
         got = out.cpu().double().permute(0, 3, 1, 2)
         assert float((got - ref).abs().max()) <= float(ref.abs().max()) * 2.0 ** -10 + 1e-4
     s = out  # relu'd stem output, NHWC fp16
@@ -114,9 +116,10 @@ def test_stem_maxpool_gap_instnorm():
     # InstanceNorm + ReLU on the first half of the channels, second half untouched
     t = (torch.randn(2, 20, 12, 128, generator=g) * 2 + 0.3).half()
     gam, bet = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.2
-    td = t.clone().cuda()
-    N.check(L.ctl_instnorm_relu_nhwc_f16(td.data_ptr(), 2, 240, 128, 64, gam.cuda().data_ptr(), bet.cuda().data_ptr(),
+    td, gd, btd = t.clone().cuda(), gam.cuda(), bet.cuda()
+    N.check(L.ctl_instnorm_relu_nhwc_f16(td.data_ptr(), 2, 240, 128, 64, gd.data_ptr(), btd.data_ptr(),
                                          1e-5, N.stream_ptr()))
+    torch.cuda.synchronize()
     ref_in = F.relu(F.instance_norm(t[..., :64].double().permute(0, 3, 1, 2), None, None, gam.double(), bet.double(),
                                     True, 0.1, 1e-5)).permute(0, 2, 3, 1)
     got = td.cpu()
