@@ -79,6 +79,8 @@ class TrunkEngine:
                                         stride, False)
                 self.blocks.append(blk)
         self.out_channels = self.blocks[-1]["conv3"].cout
+        self.profile = None  # set to a list to record (kernel, flops, bytes, start_evt, end_evt) per launch
+        self.launches_per_forward = 0
         self.head = None
         if bn_head is not None:
             scale = bn_head["weight"].float() / torch.sqrt(bn_head["running_var"].float() + BN_EPS)
@@ -90,10 +92,20 @@ class TrunkEngine:
         pad = 1 if c.k == 3 else 0
         ho, wo = (h + 2 * pad - c.k) // c.stride + 1, (w + 2 * pad - c.k) // c.stride + 1
         out = torch.empty(n, ho, wo, c.cout, dtype=torch.float16, device=self.device)
-        N.check(N.lib().ctl_conv2d_nhwc_f16(x.data_ptr(), n, h, w, c.cin, c.w.data_ptr(), c.b.data_ptr(),
-                                            N.ptr(residual), out.data_ptr(), c.cout, c.k, c.stride, int(c.relu),
-                                            c.relu_from, N.stream_ptr()))
+        m = n * ho * wo
+        flops = 2.0 * m * c.cout * c.cin * c.k * c.k
+        # algorithmic bytes: input read once (a strided 1x1 only touches its sampled pixels), output
+        # written once, residual read once, weights once -- fp16
+        in_px = m if (c.k == 1) else n * h * w
+        nbytes = 2.0 * (in_px * c.cin + m * c.cout * (2 if residual is not None else 1) + c.cout * c.cin * c.k * c.k)
+        with self._timed("conv_gemm", flops, nbytes):
+            N.check(N.lib().ctl_conv2d_nhwc_f16(x.data_ptr(), n, h, w, c.cin, c.w.data_ptr(), c.b.data_ptr(),
+                                                N.ptr(residual), out.data_ptr(), c.cout, c.k, c.stride, int(c.relu),
+                                                c.relu_from, N.stream_ptr()))
         return out, ho, wo
+
+    def _timed(self, name, flops=0.0, nbytes=0.0):
+        return _Timed(self, name, flops, nbytes)
 
     def forward(self, x: torch.Tensor, want_base: bool = False, want_emb: bool = False):
         """x: [B, 3, H, W] fp32 NCHW on the device -> dict(global_feat [B, C] fp32,
@@ -104,21 +116,25 @@ class TrunkEngine:
         x = x.float().contiguous()
         n, _, H, W = x.shape
         L = N.lib()
+        self.launches_per_forward = 0
         with torch.cuda.device(self.device):
             h, w = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
             s = torch.empty(n, h, w, 64, dtype=torch.float16, device=self.device)
-            N.check(L.ctl_stem_conv7x7(x.data_ptr(), n, H, W, self.stem_w.data_ptr(), self.stem_b.data_ptr(),
-                                       int(self.ibn), s.data_ptr(), N.stream_ptr()))
+            with self._timed("stem_conv", 2.0 * n * h * w * 64 * 147, n * (3.0 * H * W * 4 + h * w * 64 * 2)):
+                N.check(L.ctl_stem_conv7x7(x.data_ptr(), n, H, W, self.stem_w.data_ptr(), self.stem_b.data_ptr(),
+                                           int(self.ibn), s.data_ptr(), N.stream_ptr()))
             hp, wp = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
             a = torch.empty(n, hp, wp, 64, dtype=torch.float16, device=self.device)
-            N.check(L.ctl_maxpool3x3s2_nhwc_f16(s.data_ptr(), n, h, w, 64, a.data_ptr(), N.stream_ptr()))
+            with self._timed("maxpool", 0.0, n * 64 * 2.0 * (h * w + hp * wp)):
+                N.check(L.ctl_maxpool3x3s2_nhwc_f16(s.data_ptr(), n, h, w, 64, a.data_ptr(), N.stream_ptr()))
             h, w = hp, wp
             for blk in self.blocks:
                 o1, h1, w1 = self._conv(a, n, h, w, blk["conv1"])
                 if "in" in blk:
                     half, g, b = blk["in"]
-                    N.check(L.ctl_instnorm_relu_nhwc_f16(o1.data_ptr(), n, h1 * w1, blk["conv1"].cout, half,
-                                                         g.data_ptr(), b.data_ptr(), BN_EPS, N.stream_ptr()))
+                    with self._timed("instnorm_relu", 0.0, 2.0 * 2 * n * h1 * w1 * half):
+                        N.check(L.ctl_instnorm_relu_nhwc_f16(o1.data_ptr(), n, h1 * w1, blk["conv1"].cout, half,
+                                                             g.data_ptr(), b.data_ptr(), BN_EPS, N.stream_ptr()))
                 o2, h2, w2 = self._conv(o1, n, h1, w1, blk["conv2"])
                 res = a
                 if "down" in blk:
@@ -128,11 +144,34 @@ class TrunkEngine:
             feat = torch.empty(n, c, dtype=torch.float32, device=self.device)
             emb = torch.empty(n, c, dtype=torch.float32, device=self.device) if (want_emb and self.head) else None
             sc, sh = self.head if self.head else (None, None)
-            N.check(L.ctl_gap_bn_nhwc_f16(a.data_ptr(), n, h * w, c, N.ptr(sc), N.ptr(sh), feat.data_ptr(),
-                                          N.ptr(emb), N.stream_ptr()))
+            with self._timed("gap_bn", 0.0, n * c * (2.0 * h * w + 8)):
+                N.check(L.ctl_gap_bn_nhwc_f16(a.data_ptr(), n, h * w, c, N.ptr(sc), N.ptr(sh), feat.data_ptr(),
+                                              N.ptr(emb), N.stream_ptr()))
         out = {"global_feat": feat}
         if want_base:
             out["base_out_nhwc"] = a
         if emb is not None:
             out["emb"] = emb
         return out
+
+
+class _Timed:
+    """Counts launches; in profile mode brackets the launch with CUDA events on the current
+    stream (the stream the kernel is enqueued on)."""
+
+    def __init__(self, eng, name, flops, nbytes):
+        self.eng, self.name, self.flops, self.nbytes = eng, name, flops, nbytes
+
+    def __enter__(self):
+        self.eng.launches_per_forward += 1
+        if self.eng.profile is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.eng.profile is not None:
+            self.e1.record()
+            self.eng.profile.append((self.name, self.flops, self.nbytes, self.e0, self.e1))
+        return False
