@@ -330,10 +330,15 @@ def run_retrieval(args, world, rank, local, steps=None, warmup=None):
 # CPU baseline / reference arm: the oracle restatement of the reference, on the host cores
 # ----------------------------------------------------------------------------------------------
 
+def _host_threads():
+    """All the host threads torch can use productively: its own default is one per physical core;
+    hyper-thread oversubscription (os.cpu_count()) was measured 19x SLOWER on the 128-thread box."""
+    return torch.get_num_threads()
+
+
 def cpu_embed(n_images, reps):
     from oracle import ctl_oracle as O  # the one place the bench executes the oracle
 
-    torch.set_num_threads(os.cpu_count())
     sd = O.make_trunk_state(seed=0)
     g = torch.Generator().manual_seed(10_000)
     bn = dict(weight=0.5 + torch.rand(2048, generator=g), bias=torch.zeros(2048),
@@ -351,7 +356,6 @@ def cpu_embed(n_images, reps):
 def cpu_retrieval(nq):
     from oracle import ctl_oracle as O
 
-    torch.set_num_threads(os.cpu_count())
     feats, pids, cams = O.synth_retrieval(RET_Q, RET_G, RET_IDS, RET_D, 3.0, 0)
     q, g = feats[:nq], feats[RET_Q:]
     t0 = time.perf_counter()
@@ -389,7 +393,7 @@ def main():
         line.update({"impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                      "ms_per_step": dt * 1e3 / max(1, min(args.steps, 6)), "higher_is_better": True, "scaling": "weak",
                      "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name},
-                     "cpu_baseline": {"value": v, "unit": line["unit"], "cores": os.cpu_count(), "kind": "port",
+                     "cpu_baseline": {"value": v, "unit": line["unit"], "cores": _host_threads(), "kind": "port",
                                       "sample": line["sample"]},
                      "e2e": {"value": v, "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         print(json.dumps(line))
@@ -418,10 +422,10 @@ def main():
             if rank == 0 and not args.no_secondary and world == 1:
                 line["retrieval"] = run_retrieval(args, world, rank, local, steps=5, warmup=3)
                 v, dt = cpu_embed(64, 2)
-                line["cpu_baseline"] = {"value": v, "unit": "embeddings/s", "cores": os.cpu_count(), "kind": "port",
+                line["cpu_baseline"] = {"value": v, "unit": "embeddings/s", "cores": _host_threads(), "kind": "port",
                                         "sample": f"128 crops (2 x 64) through oracle.embed_forward, torch-CPU fp32, {dt:.1f} s"}
                 rv, rdt = cpu_retrieval(128)
-                line["retrieval"]["cpu_baseline"] = {"value": rv, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
+                line["retrieval"]["cpu_baseline"] = {"value": rv, "unit": "pairs/s", "cores": _host_threads(), "kind": "port",
                                                      "sample": f"128 of {RET_Q} queries x {RET_G} gallery through oracle.r1_map_compute, {rdt:.1f} s"}
         else:
             with ClockSampler(local) as clk:
@@ -434,7 +438,7 @@ def main():
                     "clocks": clk.summary(), "mAP": r["mAP"]}
             if rank == 0 and not args.no_secondary:
                 rv, rdt = cpu_retrieval(128)
-                line["cpu_baseline"] = {"value": rv, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
+                line["cpu_baseline"] = {"value": rv, "unit": "pairs/s", "cores": _host_threads(), "kind": "port",
                                         "sample": f"128 of {RET_Q} queries x {RET_G} gallery, {rdt:.1f} s"}
         if rank == 0:
             print(json.dumps(line))

@@ -115,21 +115,24 @@ def encode_identities(q_pids, g_pids, q_camids, g_camids, respect_camids: bool):
         q_cam_vals = [c[0] if isinstance(c, (list, tuple, np.ndarray)) else c for c in q_camids]
         g_sets = [list(np.atleast_1d(c)) for c in list(g_camids)[:n_g]]
         cams = sorted(set(q_cam_vals) | {c for s in g_sets for c in s})
+        if len(cams) > 64:
+            raise NotImplementedError(f"{len(cams)} distinct cameras; the junk filter packs camera sets into 64 bits")
+        cam_index = {c: i for i, c in enumerate(cams)}
+        qc = np.asarray([cam_index[c] for c in q_cam_vals], dtype=np.int32)
+        gm = np.zeros(n_g, dtype=np.uint64)
+        for i, s in enumerate(g_sets):
+            m = 0
+            for c in s:
+                m |= 1 << cam_index[c]
+            gm[i] = m
     else:
-        q_cam_vals = list(np.asarray(q_camids).tolist())
-        g_flat = np.asarray(g_camids)[:n_g]  # may be over-long (bases.py:255-260 quirk)
-        g_sets = [[c] for c in g_flat.tolist()]
-        cams = sorted(set(q_cam_vals) | set(g_flat.tolist()))
-    if len(cams) > 64:
-        raise NotImplementedError(f"{len(cams)} distinct cameras; the junk filter packs camera sets into 64 bits")
-    cam_index = {c: i for i, c in enumerate(cams)}
-    qc = np.asarray([cam_index[c] for c in q_cam_vals], dtype=np.int32)
-    gm = np.zeros(n_g, dtype=np.uint64)
-    for i, s in enumerate(g_sets):
-        m = 0
-        for c in s:
-            m |= 1 << cam_index[c]
-        gm[i] = m
+        q_cam = np.asarray(q_camids)
+        g_cam = np.asarray(g_camids)[:n_g]  # may be over-long (bases.py:255-260 quirk)
+        cams, inv_c = np.unique(np.concatenate([q_cam, g_cam]), return_inverse=True)
+        if len(cams) > 64:
+            raise NotImplementedError(f"{len(cams)} distinct cameras; the junk filter packs camera sets into 64 bits")
+        qc = inv_c[: len(q_cam)].astype(np.int32)
+        gm = np.uint64(1) << inv_c[len(q_cam):].astype(np.uint64)
     # upper bound of positives per query: the largest pid group in the gallery
     max_pos = int(np.bincount(gp).max()) if n_g else 1
     return qp, qc, gp, gm, max(1, max_pos)
