@@ -40,6 +40,8 @@ struct ConvTap {
 struct ConvKernelParams {
   CUtensorMap a_map[4];
   CUtensorMap b_map;
+  CUtensorMap out_map;  // NHWC output, box {64 ch, TW, TH, 1}
+  CUtensorMap res_map;  // residual, same geometry
   ConvTap taps[9];
   int n_taps;
   int cin_blocks;  // Cin / 64
@@ -47,8 +49,7 @@ struct ConvKernelParams {
   int TW, TH, tiles_w, tiles_h;
   int m_tiles, n_tiles;
   const float* bias;        // [Cout]
-  const __half* residual;   // NHWC [n, Ho, Wo, Cout] or null
-  __half* out;              // NHWC
+  int has_residual;
   int relu;                 // apply ReLU to channels >= relu_from
   int relu_from;
 };
@@ -57,9 +58,10 @@ template <int BN>
 struct ConvCfg {
   static constexpr int B_TILE_BYTES = BN * CBK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int STAGES = BN == 64 ? 8 : (BN == 128 ? 6 : 4);
+  static constexpr int STAGES = BN == 64 ? 5 : (BN == 128 ? 4 : 3);
   static constexpr int TMEM_COLS = BN == 64 ? 128 : (BN == 128 ? 256 : 512);  // 2 accumulator stages
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+  // + 2 output and 2 residual staging slabs of [128 px][64 ch] fp16 (16 KiB each)
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 4 * A_TILE_BYTES + 1024 + 256;
 };
 
 template <int BN>
@@ -67,12 +69,15 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
   using Cfg = ConvCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  const uint32_t out_stage = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;  // 2 x 16 KiB
+  const uint32_t res_stage = out_stage + 2 * A_TILE_BYTES;                // 2 x 16 KiB
+  const uint32_t bar_base = res_stage + 2 * A_TILE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
+  auto res_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 4 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.m_tiles * p.n_tiles;
@@ -87,12 +92,15 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), 4);
+      mbar_init(res_bar(s), 1);
     }
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.a_map[i]);
     tma_prefetch_desc(&p.b_map);
+    tma_prefetch_desc(&p.out_map);
+    tma_prefetch_desc(&p.res_map);
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   tc_fence_before();
@@ -159,68 +167,123 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       }
     }
   } else {
+    // ===== epilogue: 4 warps.  The accumulator is drained in 64-channel sub-tiles: TMEM ->
+    // registers -> (+bias, +residual from shared memory, ReLU) -> fp16 -> swizzled staging slab ->
+    // one TMA store per sub-tile.  Residual sub-tiles arrive by TMA two sub-tiles ahead, so no
+    // global-memory latency is ever exposed to these warps and every HBM access is a full line.
+    constexpr int NSUB = BN / 64;
     const int quarter = warp & 3;
-    const int pix = quarter * 32 + lane;  // pixel inside the tile == TMEM lane
+    const int pix = quarter * 32 + lane;  // pixel inside the tile == TMEM lane == staging row
+    const bool leader = (warp == 2 && lane == 0);
+    const uint32_t row_off = pix * 128;
+    const uint32_t sw = pix & 7;
+    uint8_t* gsm = smem_raw + (out_stage - smem_u32(smem_raw));  // generic pointer to the staging area
+    const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const long long total_sub = (long long)my_tiles * NSUB;
+    auto sub_coords = [&](long long gg, int& ch0, int& w0, int& h0, int& img) {
+      const int it = (int)(gg / NSUB), j = (int)(gg - (long long)it * NSUB);
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      img = mt / tiles_per_img;
+      const int tr = mt - img * tiles_per_img;
+      h0 = (tr / p.tiles_w) * p.TH;
+      w0 = (tr % p.tiles_w) * p.TW;
+      ch0 = nt * BN + j * 64;
+    };
+    auto issue_res = [&](long long gg) {  // leader only
+      int ch0, w0, h0, img;
+      sub_coords(gg, ch0, w0, h0, img);
+      const int b = (int)(gg & 1);
+      mbar_arrive_expect_tx(res_bar(b), A_TILE_BYTES);
+      tma_load_4d(res_stage + b * A_TILE_BYTES, &p.res_map, res_bar(b), ch0, w0, h0, img);
+    };
+    if (p.has_residual && leader) {
+      if (total_sub > 0) issue_res(0);
+      if (total_sub > 1) issue_res(1);
+    }
     int as = 0;
     uint32_t aphase = 0;
+    long long g = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
-      const int img = mt / tiles_per_img, tr = mt - img * tiles_per_img;
-      const int h = (tr / p.tiles_w) * p.TH + pix / p.TW, w = (tr % p.tiles_w) * p.TW + pix % p.TW;
-      const bool ok = h < p.Ho && w < p.Wo;
-      const size_t off = (((size_t)img * p.Ho + h) * p.Wo + w) * p.Cout + (size_t)nt * BN;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t t0 = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < BN / 16; ++c) {
-        uint32_t r[16];
-        tmem_ld16(t0 + c * 16, r);
-        tmem_ld_wait();
-        if (ok) {
-          const int ch0 = nt * BN + c * 16;
-          float v[16];
+      for (int j = 0; j < NSUB; ++j, ++g) {
+        const int b = (int)(g & 1);
+        int ch0, w0, h0, img;
+        sub_coords(g, ch0, w0, h0, img);
+        // staging slab b was handed to the TMA store two sub-tiles ago: wait until it has been read
+        if (leader) tma_store_wait_read<1>();
+        named_bar_sync(1, 128);
+        if (p.has_residual) mbar_wait(res_bar(b), (uint32_t)((g >> 1) & 1));
+        uint8_t* oslab = gsm + b * A_TILE_BYTES + row_off;
+        const uint8_t* rslab = gsm + (2 + b) * A_TILE_BYTES + row_off;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + __ldg(p.bias + ch0 + j);
-          if (p.residual) {
-            const uint4 ra = *reinterpret_cast<const uint4*>(p.residual + off + c * 16);
-            const uint4 rb = *reinterpret_cast<const uint4*>(p.residual + off + c * 16 + 8);
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[16];
+          tmem_ld16(t0 + j * 64 + c * 16, r);
+          tmem_ld_wait();
+          float v[16];
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + ch0 + c * 16);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 bb = __ldg(bp + q4);
+            v[4 * q4 + 0] = __uint_as_float(r[4 * q4 + 0]) + bb.x;
+            v[4 * q4 + 1] = __uint_as_float(r[4 * q4 + 1]) + bb.y;
+            v[4 * q4 + 2] = __uint_as_float(r[4 * q4 + 2]) + bb.z;
+            v[4 * q4 + 3] = __uint_as_float(r[4 * q4 + 3]) + bb.w;
+          }
+          const uint32_t o0 = ((2 * c) ^ sw) << 4, o1 = ((2 * c + 1) ^ sw) << 4;  // swizzled 16-byte chunks
+          if (p.has_residual) {
+            const uint4 ra = *reinterpret_cast<const uint4*>(rslab + o0);
+            const uint4 rb = *reinterpret_cast<const uint4*>(rslab + o1);
             const __half2* ha = reinterpret_cast<const __half2*>(&ra);
             const __half2* hb = reinterpret_cast<const __half2*>(&rb);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 fa = __half22float2(ha[j]), fb = __half22float2(hb[j]);
-              v[2 * j] += fa.x;
-              v[2 * j + 1] += fa.y;
-              v[8 + 2 * j] += fb.x;
-              v[8 + 2 * j + 1] += fb.y;
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const float2 fa = __half22float2(ha[q4]), fb = __half22float2(hb[q4]);
+              v[2 * q4] += fa.x;
+              v[2 * q4 + 1] += fa.y;
+              v[8 + 2 * q4] += fb.x;
+              v[8 + 2 * q4 + 1] += fb.y;
             }
           }
           if (p.relu) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (ch0 + j >= p.relu_from) v[j] = fmaxf(v[j], 0.f);
+            for (int q = 0; q < 16; ++q)
+              if (ch0 + c * 16 + q >= p.relu_from) v[q] = fmaxf(v[q], 0.f);
           }
           uint4 oa, ob;
           __half2* pa = reinterpret_cast<__half2*>(&oa);
           __half2* pb = reinterpret_cast<__half2*>(&ob);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            pa[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-            pb[j] = __floats2half2_rn(v[8 + 2 * j], v[8 + 2 * j + 1]);
+          for (int q4 = 0; q4 < 4; ++q4) {
+            pa[q4] = __floats2half2_rn(v[2 * q4], v[2 * q4 + 1]);
+            pb[q4] = __floats2half2_rn(v[8 + 2 * q4], v[8 + 2 * q4 + 1]);
           }
-          *reinterpret_cast<uint4*>(p.out + off + c * 16) = oa;
-          *reinterpret_cast<uint4*>(p.out + off + c * 16 + 8) = ob;
+          *reinterpret_cast<uint4*>(oslab + o0) = oa;
+          *reinterpret_cast<uint4*>(oslab + o1) = ob;
+        }
+        if (j == NSUB - 1) {  // last TMEM read of this accumulator stage: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(as));
+        }
+        fence_proxy_async();     // staging writes (generic proxy) -> visible to the TMA store (async proxy)
+        named_bar_sync(1, 128);  // slab complete; residual slab b fully consumed
+        if (leader) {
+          tma_store_4d(&p.out_map, out_stage + b * A_TILE_BYTES, ch0, w0, h0, img);
+          tma_store_commit();
+          if (p.has_residual && g + 2 < total_sub) issue_res(g + 2);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
       if (++as == 2) {
         as = 0;
         aphase ^= 1u;
       }
     }
+    if (leader) tma_store_wait<0>();  // shared memory must outlive the last stores
   }
   tc_fence_before();
   __syncthreads();
@@ -301,6 +364,147 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
       ph2[j] = __floats2half2_rn(a0, a1);
     }
     *reinterpret_cast<uint4*>(out + (((size_t)n * Ho + oh) * Wo + ow) * 64 + cg * 8) = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// stem on the tensor cores: the 7x7/2 convolution as a GEMM with K = 21 (c, r) groups x 8
+// (s = 0..6 plus one zero column) = 168, padded to 192 = three 64-wide K slabs.
+// Per tile of 4 x 32 output pixels: the fp32 NCHW input patch (13 x 72 x 3) is converted to
+// fp16 in shared memory, every thread then assembles 16-byte K-chunks -- the 8 taps of one
+// (c, r) group are 8 CONSECUTIVE patch columns -- straight into the SWIZZLE_128B operand
+// layout (generic-proxy stores + fence.proxy.async), one thread issues 12 tcgen05.mma
+// (M=128, N=64), and the epilogue adds the folded-BN bias (+ReLU for IBN) and writes one full
+// 128-byte NHWC line per pixel.  Weights [64][192] fp16 stay resident in shared memory.
+// ---------------------------------------------------------------------------------------
+static constexpr int SK = 192;                    // padded K
+static constexpr int S_TH = 4, S_TW = 32;         // output tile
+static constexpr int S_PH = 2 * S_TH + 5;         // 13 input rows
+static constexpr int S_PW = 72;                   // 2*32 + 5 = 69 input columns, padded to 72
+static constexpr int STEM_TC_THREADS = 256;
+static constexpr int S_A_BYTES = 3 * A_TILE_BYTES;          // 48 KiB: three [128][64] fp16 slabs
+static constexpr int S_B_BYTES = 3 * 64 * 128;              // 24 KiB: three [64][64] fp16 slabs
+static constexpr int S_PATCH_BYTES = 3 * S_PH * S_PW * 2;   // 5.6 KiB
+static constexpr size_t STEM_TC_SMEM = S_A_BYTES + S_B_BYTES + S_PATCH_BYTES + 1024 + 64;
+
+struct StemParams {
+  CUtensorMap w_map;  // [64][192] fp16, box {64, 64}
+  const float* x;     // NCHW fp32
+  const float* bias;
+  __half* out;        // NHWC fp16 [n, Ho, Wo, 64]
+  int n_img, H, W, Ho, Wo, tiles_h, tiles_w, relu;
+};
+
+__global__ void __launch_bounds__(STEM_TC_THREADS, 2) stem_tc_kernel(const __grid_constant__ StemParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sA = base, sB = base + S_A_BYTES;
+  __half* patch = reinterpret_cast<__half*>(gbase + S_A_BYTES + S_B_BYTES);
+  const uint32_t bar_w = base + S_A_BYTES + S_B_BYTES + S_PATCH_BYTES;  // weights landed
+  const uint32_t bar_mma = bar_w + 8;                                   // accumulator ready
+  const uint32_t tmem_slot = bar_w + 16;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&p.w_map);
+  }
+  if (warp == 0) tmem_alloc<64>(tmem_slot);
+  // the three zero chunks (k = 168..191) of every pixel never change: chunks 5,6,7 of slab 2
+  for (int q = tid; q < 128 * 3; q += STEM_TC_THREADS) {
+    const int px = q & 127, ch = 5 + (q >> 7);
+    *reinterpret_cast<uint4*>(gbase + 2 * A_TILE_BYTES + px * 128 + ((ch ^ (px & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_w, S_B_BYTES);
+    for (int kb = 0; kb < 3; ++kb) tma_load_2d(sB + kb * 64 * 128, &p.w_map, bar_w, kb * 64, 0);
+  }
+  const int tiles_per_img = p.tiles_h * p.tiles_w;
+  const int num_tiles = p.n_img * tiles_per_img;
+  uint32_t mma_phase = 0;
+  bool w_ready = false;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int img = tile / tiles_per_img, tr = tile - img * tiles_per_img;
+    const int oh0 = (tr / p.tiles_w) * S_TH, ow0 = (tr % p.tiles_w) * S_TW;
+    const int ih0 = 2 * oh0 - 3, iw0 = 2 * ow0 - 3;
+    // ---- input patch: fp32 NCHW -> fp16 [3][13][72], zero outside the image ----
+    for (int e = tid; e < 3 * S_PH * S_PW; e += STEM_TC_THREADS) {
+      const int c = e / (S_PH * S_PW), rem = e - c * (S_PH * S_PW), ph = rem / S_PW, pw = rem - ph * S_PW;
+      const int ih = ih0 + ph, iw = iw0 + pw;
+      float v = 0.f;
+      if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) v = __ldg(p.x + (((size_t)img * 3 + c) * p.H + ih) * p.W + iw);
+      patch[e] = __float2half_rn(v);
+    }
+    __syncthreads();
+    // ---- operand tile: chunk (pixel px, group cr) = patch[c][2*(px/32) + r][2*(px%32) .. +7] ----
+    for (int q = tid; q < 128 * 21; q += STEM_TC_THREADS) {
+      const int px = q & 127, cr = q >> 7;
+      const int c = cr / 7, r = cr - c * 7;
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(patch + (c * S_PH + 2 * (px >> 5) + r) * S_PW + 2 * (px & 31));
+      const uint4 v = make_uint4(src[0], src[1], src[2], src[3]);
+      const int slab = cr >> 3, ch = cr & 7;
+      *reinterpret_cast<uint4*>(gbase + slab * A_TILE_BYTES + px * 128 + ((ch ^ (px & 7)) << 4)) = v;
+    }
+    fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    __syncthreads();
+    if (tid == 0) {
+      if (!w_ready) mbar_wait(bar_w, 0);
+      tc_fence_after();
+      constexpr uint32_t idesc = make_idesc_f16(128, 64);
+#pragma unroll
+      for (int kb = 0; kb < 3; ++kb) {
+        const uint64_t da = make_sw128_kmajor_desc(sA + kb * A_TILE_BYTES);
+        const uint64_t db = make_sw128_kmajor_desc(sB + kb * 64 * 128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tmem_base, desc_advance_k(da, k), desc_advance_k(db, k), idesc, (kb | k) ? 1u : 0u);
+      }
+      umma_commit(bar_mma);
+    }
+    w_ready = true;
+    mbar_wait(bar_mma, mma_phase);
+    mma_phase ^= 1u;
+    tc_fence_after();
+    if (warp < 4) {
+      const int px = warp * 32 + lane;
+      const int oh = oh0 + (px >> 5), ow = ow0 + (px & 31);
+      const bool ok = oh < p.Ho && ow < p.Wo;
+      __half* dst = p.out + (((size_t)img * p.Ho + oh) * p.Wo + ow) * 64;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c * 16, r);
+        tmem_ld_wait();
+        if (ok) {
+          uint4 oa, ob;
+          __half2* pa = reinterpret_cast<__half2*>(&oa);
+          __half2* pb = reinterpret_cast<__half2*>(&ob);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float a0 = __uint_as_float(r[2 * j]) + __ldg(p.bias + c * 16 + 2 * j);
+            float a1 = __uint_as_float(r[2 * j + 1]) + __ldg(p.bias + c * 16 + 2 * j + 1);
+            if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+            if (j < 4) pa[j] = __floats2half2_rn(a0, a1); else pb[j - 4] = __floats2half2_rn(a0, a1);
+          }
+          *reinterpret_cast<uint4*>(dst + c * 16) = oa;
+          *reinterpret_cast<uint4*>(dst + c * 16 + 8) = ob;
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // accumulator drained, patch and operand tile free for the next tile
+    tc_fence_after();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_dealloc<64>(tmem_base);
   }
 }
 
@@ -490,8 +694,7 @@ int ctl_conv2d_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, int32_t 
   p.Cout = cout;
   p.cin_blocks = cin / 64;
   p.bias = bias;
-  p.residual = static_cast<const __half*>(residual);
-  p.out = static_cast<__half*>(out);
+  p.has_residual = residual != nullptr;
   p.relu = relu;
   p.relu_from = relu_from;
   p.m_tiles = n * p.tiles_h * p.tiles_w;
@@ -528,6 +731,17 @@ int ctl_conv2d_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, int32_t 
         p.taps[r * ksize + s] = ConvTap{ph * 2 + pw, dh, dw, (r * ksize + s) * cin};
       }
   }
+  {
+    const uint64_t odims[4] = {(uint64_t)cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)n};
+    const uint64_t ostr[4] = {2, (uint64_t)cout * 2, (uint64_t)Wo * cout * 2, (uint64_t)Ho * Wo * cout * 2};
+    const uint32_t obox[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+    if ((rc = encode_tensor_map(&p.out_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, out, odims, ostr, obox,
+                                CU_TENSOR_MAP_SWIZZLE_128B)))
+      return rc;
+    if ((rc = encode_tensor_map(&p.res_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, residual ? residual : out, odims,
+                                ostr, obox, CU_TENSOR_MAP_SWIZZLE_128B)))
+      return rc;
+  }
   const uint64_t bdims[2] = {(uint64_t)ksize * ksize * cin, (uint64_t)cout};
   const uint64_t bstr[2] = {2, (uint64_t)ksize * ksize * cin * 2};
   const uint32_t bbox[2] = {CBK, (uint32_t)BN};
@@ -555,6 +769,42 @@ int ctl_stem_conv7x7(const float* x_nchw, int32_t n, int32_t h, int32_t w, const
   dim3 grid((Wo + ST_TW - 1) / ST_TW, (Ho + ST_TH - 1) / ST_TH, n);
   stem_conv_kernel<<<grid, 256, STEM_SMEM, (cudaStream_t)stream>>>(x_nchw, h, w, weight_k64, bias, relu,
                                                                   static_cast<__half*>(out_nhwc_f16), Ho, Wo);
+  CTL_LAUNCH_CHECK();
+  return 0;
+}
+
+int ctl_stem_conv7x7_tc(const float* x_nchw, int32_t n, int32_t h, int32_t w, const void* weight_k192_f16,
+                        const float* bias, int32_t relu, void* out_nhwc_f16, ctl_stream_t stream) {
+  CTL_CHECK_ARG(x_nchw && weight_k192_f16 && bias && out_nhwc_f16, "null pointer");
+  CTL_CHECK_ARG(n >= 1 && h >= 7 && w >= 7, "bad input shape");
+  int rc = ctl_device_check();
+  if (rc) return rc;
+  StemParams p = {};
+  p.x = x_nchw;
+  p.bias = bias;
+  p.out = static_cast<__half*>(out_nhwc_f16);
+  p.n_img = n;
+  p.H = h;
+  p.W = w;
+  p.Ho = (h + 6 - 7) / 2 + 1;
+  p.Wo = (w + 6 - 7) / 2 + 1;
+  p.tiles_h = (p.Ho + S_TH - 1) / S_TH;
+  p.tiles_w = (p.Wo + S_TW - 1) / S_TW;
+  p.relu = relu;
+  const uint64_t dims[2] = {SK, 64};
+  const uint64_t strd[2] = {2, SK * 2};
+  const uint32_t box[2] = {64, 64};
+  if ((rc = encode_tensor_map(&p.w_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 2, weight_k192_f16, dims, strd, box,
+                              CU_TENSOR_MAP_SWIZZLE_128B)))
+    return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CTL_CUDA(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEM_TC_SMEM));
+    attr_set = true;
+  }
+  const long long tiles = (long long)n * p.tiles_h * p.tiles_w;
+  const int grid = (int)std::min<long long>(tiles, 2LL * sm_count());
+  stem_tc_kernel<<<grid, STEM_TC_THREADS, STEM_TC_SMEM, (cudaStream_t)stream>>>(p);
   CTL_LAUNCH_CHECK();
   return 0;
 }

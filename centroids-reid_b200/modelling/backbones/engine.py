@@ -52,8 +52,10 @@ class TrunkEngine:
         self.ibn = ibn
         sd = {k: v.detach().to(self.device) for k, v in state.items() if v.is_floating_point()}
         w, b = _fold(sd["conv1.weight"], _bn(sd, "bn1"))
-        # stem weights as [147][64], k = (c*7 + r)*7 + s
-        self.stem_w = w.permute(1, 2, 3, 0).reshape(147, 64).contiguous()
+        # stem weights for the tensor-core stem: [64][192] fp16, k = (c*7 + r)*8 + s; s = 7 and k >= 168 zero
+        wk = torch.zeros(64, 21, 8, device=self.device)
+        wk[:, :, :7] = w.reshape(64, 21, 7)
+        self.stem_w = torch.cat((wk.reshape(64, 168), torch.zeros(64, 24, device=self.device)), 1).half().contiguous()
         self.stem_b = b.contiguous()
         self.blocks = []
         for li, (planes, nblk) in enumerate(zip((64, 128, 256, 512), layers), start=1):
@@ -121,8 +123,8 @@ class TrunkEngine:
             h, w = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
             s = torch.empty(n, h, w, 64, dtype=torch.float16, device=self.device)
             with self._timed("stem_conv", 2.0 * n * h * w * 64 * 147, n * (3.0 * H * W * 4 + h * w * 64 * 2)):
-                N.check(L.ctl_stem_conv7x7(x.data_ptr(), n, H, W, self.stem_w.data_ptr(), self.stem_b.data_ptr(),
-                                           int(self.ibn), s.data_ptr(), N.stream_ptr()))
+                N.check(L.ctl_stem_conv7x7_tc(x.data_ptr(), n, H, W, self.stem_w.data_ptr(), self.stem_b.data_ptr(),
+                                              int(self.ibn), s.data_ptr(), N.stream_ptr()))
             hp, wp = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
             a = torch.empty(n, hp, wp, 64, dtype=torch.float16, device=self.device)
             with self._timed("maxpool", 0.0, n * 64 * 2.0 * (h * w + hp * wp)):

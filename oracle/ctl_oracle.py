@@ -538,7 +538,7 @@ def trunk_forward_fp16sim(x, sd, last_stride=1, ibn=False, layers=R50_LAYERS):
         return t.half().float()
 
     w, b = fold("conv1.weight", "bn1")
-    x = F.conv2d(x, w, b, 2, 3)  # the stem runs on fp32 operands
+    x = F.conv2d(q(x), q(w), b, 2, 3)  # tensor-core stem: fp16 input crop and weights, fp32 accumulate
     if ibn:
         x = F.relu(x)
     x = F.max_pool2d(q(x), 3, 2, 1)

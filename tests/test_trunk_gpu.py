@@ -97,6 +97,20 @@ def test_stem_maxpool_gap_instnorm():
         torch.cuda.synchronize()
         got = out.cpu().double().permute(0, 3, 1, 2)
         assert float((got - ref).abs().max()) <= float(ref.abs().max()) * 2.0 ** -10 + 1e-4
+        # tensor-core stem: fp16 operands ([64][192] weights, k = (c*7 + r)*8 + s), fp32 accumulate
+        wk192 = torch.zeros(64, 21, 8)
+        wk192[:, :, :7] = w.reshape(64, 21, 7)
+        wk192 = torch.cat((wk192.reshape(64, 168), torch.zeros(64, 24)), 1).half().cuda()
+        out_tc = torch.full((n, ho, wo, 64), float("nan"), dtype=torch.float16, device="cuda")
+        N.check(L.ctl_stem_conv7x7_tc(xd.data_ptr(), n, H, W, wk192.data_ptr(), bd.data_ptr(), relu,
+                                      out_tc.data_ptr(), N.stream_ptr()))
+        torch.cuda.synchronize()
+        ref16 = F.conv2d(x.half().double(), w.half().double(), b.double(), 2, 3)
+        if relu:
+            ref16 = ref16.clamp(min=0)
+        got_tc = out_tc.cpu().double().permute(0, 3, 1, 2)
+        assert torch.isfinite(got_tc).all()
+        assert float((got_tc - ref16).abs().max()) <= float(ref16.abs().max()) * 2.0 ** -10 + 1e-4
     s = out  # relu'd stem output, NHWC fp16
     hp, wp = (ho + 2 - 3) // 2 + 1, (wo + 2 - 3) // 2 + 1
     pooled = torch.empty(n, hp, wp, 64, dtype=torch.float16, device="cuda")
