@@ -28,7 +28,7 @@ namespace ctl {
 
 static constexpr int CBM = 128;  // output pixels per tile
 static constexpr int CBK = 64;   // channels per k-block (128 bytes)
-static constexpr int CONV_THREADS = 192;
+static constexpr int CONV_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 static constexpr int A_TILE_BYTES = CBM * CBK * 2;
 
 struct ConvTap {
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);
+      mbar_init(tempty_bar(s), 8);
       mbar_init(res_bar(s), 1);
     }
     fence_barrier_init();
@@ -167,35 +167,37 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       }
     }
   } else {
-    // ===== epilogue: 4 warps.  The accumulator is drained in 64-channel sub-tiles: TMEM ->
-    // registers -> (+bias, +residual from shared memory, ReLU) -> fp16 -> swizzled staging slab ->
-    // one TMA store per sub-tile.  Residual sub-tiles arrive by TMA two sub-tiles ahead, so no
-    // global-memory latency is ever exposed to these warps and every HBM access is a full line.
+    // ===== epilogue: 8 warps (two per 32-lane TMEM quarter, splitting the columns).  The
+    // accumulator is drained in 64-channel sub-tiles: TMEM -> registers -> (+bias, +residual from
+    // shared memory, ReLU) -> fp16 -> swizzled staging slab -> one TMA store per sub-tile.
+    // Residual sub-tiles arrive by TMA two sub-tiles ahead, so no global-memory latency is ever
+    // exposed to these warps and every HBM access is a full 128-byte line.
     constexpr int NSUB = BN / 64;
-    const int quarter = warp & 3;
+    const int ew = warp - 2;              // 0..7
+    const int quarter = warp & 3;         // TMEM lane quarter this warp may read
+    const int chalf = ew >> 2;            // which 32-channel half of every 64-channel sub-tile
     const int pix = quarter * 32 + lane;  // pixel inside the tile == TMEM lane == staging row
-    const bool leader = (warp == 2 && lane == 0);
+    const bool leader = (ew == 0 && lane == 0);
     const uint32_t row_off = pix * 128;
     const uint32_t sw = pix & 7;
     uint8_t* gsm = smem_raw + (out_stage - smem_u32(smem_raw));  // generic pointer to the staging area
     const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const long long total_sub = (long long)my_tiles * NSUB;
-    auto sub_coords = [&](long long gg, int& ch0, int& w0, int& h0, int& img) {
-      const int it = (int)(gg / NSUB), j = (int)(gg - (long long)it * NSUB);
-      const int tile = blockIdx.x + it * gridDim.x;
-      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+    auto tile_coords = [&](int tile, int& nt, int& w0, int& h0, int& img) {
+      const int mt = tile / p.n_tiles;
+      nt = tile - mt * p.n_tiles;
       img = mt / tiles_per_img;
       const int tr = mt - img * tiles_per_img;
       h0 = (tr / p.tiles_w) * p.TH;
       w0 = (tr % p.tiles_w) * p.TW;
-      ch0 = nt * BN + j * 64;
     };
     auto issue_res = [&](long long gg) {  // leader only
-      int ch0, w0, h0, img;
-      sub_coords(gg, ch0, w0, h0, img);
+      const int it = (int)(gg / NSUB), j = (int)(gg - (long long)it * NSUB);
+      int nt, w0, h0, img;
+      tile_coords(blockIdx.x + it * gridDim.x, nt, w0, h0, img);
       const int b = (int)(gg & 1);
       mbar_arrive_expect_tx(res_bar(b), A_TILE_BYTES);
-      tma_load_4d(res_stage + b * A_TILE_BYTES, &p.res_map, res_bar(b), ch0, w0, h0, img);
+      tma_load_4d(res_stage + b * A_TILE_BYTES, &p.res_map, res_bar(b), nt * BN + j * 64, w0, h0, img);
     };
     if (p.has_residual && leader) {
       if (total_sub > 0) issue_res(0);
@@ -205,75 +207,69 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     uint32_t aphase = 0;
     long long g = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int nt, w0, h0, img;
+      tile_coords(tile, nt, w0, h0, img);
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-      const uint32_t t0 = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+      const uint32_t t0 = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16) + chalf * 32;
 #pragma unroll 1
       for (int j = 0; j < NSUB; ++j, ++g) {
         const int b = (int)(g & 1);
-        int ch0, w0, h0, img;
-        sub_coords(g, ch0, w0, h0, img);
+        const int ch0 = nt * BN + j * 64 + chalf * 32;  // first of this thread's 32 channels
+        uint32_t r[32];
+        tmem_ld16(t0 + j * 64, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+        tmem_ld16(t0 + j * 64 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
         // staging slab b was handed to the TMA store two sub-tiles ago: wait until it has been read
         if (leader) tma_store_wait_read<1>();
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 256);
         if (p.has_residual) mbar_wait(res_bar(b), (uint32_t)((g >> 1) & 1));
-        uint8_t* oslab = gsm + b * A_TILE_BYTES + row_off;
-        const uint8_t* rslab = gsm + (2 + b) * A_TILE_BYTES + row_off;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[16];
-          tmem_ld16(t0 + j * 64 + c * 16, r);
-          tmem_ld_wait();
-          float v[16];
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + ch0 + c * 16);
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const float4 bb = __ldg(bp + q4);
-            v[4 * q4 + 0] = __uint_as_float(r[4 * q4 + 0]) + bb.x;
-            v[4 * q4 + 1] = __uint_as_float(r[4 * q4 + 1]) + bb.y;
-            v[4 * q4 + 2] = __uint_as_float(r[4 * q4 + 2]) + bb.z;
-            v[4 * q4 + 3] = __uint_as_float(r[4 * q4 + 3]) + bb.w;
-          }
-          const uint32_t o0 = ((2 * c) ^ sw) << 4, o1 = ((2 * c + 1) ^ sw) << 4;  // swizzled 16-byte chunks
-          if (p.has_residual) {
-            const uint4 ra = *reinterpret_cast<const uint4*>(rslab + o0);
-            const uint4 rb = *reinterpret_cast<const uint4*>(rslab + o1);
-            const __half2* ha = reinterpret_cast<const __half2*>(&ra);
-            const __half2* hb = reinterpret_cast<const __half2*>(&rb);
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              const float2 fa = __half22float2(ha[q4]), fb = __half22float2(hb[q4]);
-              v[2 * q4] += fa.x;
-              v[2 * q4 + 1] += fa.y;
-              v[8 + 2 * q4] += fb.x;
-              v[8 + 2 * q4 + 1] += fb.y;
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int q = 0; q < 16; ++q)
-              if (ch0 + c * 16 + q >= p.relu_from) v[q] = fmaxf(v[q], 0.f);
-          }
-          uint4 oa, ob;
-          __half2* pa = reinterpret_cast<__half2*>(&oa);
-          __half2* pb = reinterpret_cast<__half2*>(&ob);
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            pa[q4] = __floats2half2_rn(v[2 * q4], v[2 * q4 + 1]);
-            pb[q4] = __floats2half2_rn(v[8 + 2 * q4], v[8 + 2 * q4 + 1]);
-          }
-          *reinterpret_cast<uint4*>(oslab + o0) = oa;
-          *reinterpret_cast<uint4*>(oslab + o1) = ob;
-        }
+        tmem_ld_wait();
         if (j == NSUB - 1) {  // last TMEM read of this accumulator stage: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(as));
         }
+        uint8_t* oslab = gsm + b * A_TILE_BYTES + row_off;
+        const uint8_t* rslab = gsm + (2 + b) * A_TILE_BYTES + row_off;
+        const bool do_relu = p.relu && ch0 >= p.relu_from;  // relu_from is a multiple of 32
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {  // four 16-byte chunks = 32 channels
+          const uint32_t off = ((uint32_t)(chalf * 4 + c) ^ sw) << 4;
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + c * 8));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + c * 8 + 4));
+          float v[8];
+          v[0] = __uint_as_float(r[c * 8 + 0]) + b0.x;
+          v[1] = __uint_as_float(r[c * 8 + 1]) + b0.y;
+          v[2] = __uint_as_float(r[c * 8 + 2]) + b0.z;
+          v[3] = __uint_as_float(r[c * 8 + 3]) + b0.w;
+          v[4] = __uint_as_float(r[c * 8 + 4]) + b1.x;
+          v[5] = __uint_as_float(r[c * 8 + 5]) + b1.y;
+          v[6] = __uint_as_float(r[c * 8 + 6]) + b1.z;
+          v[7] = __uint_as_float(r[c * 8 + 7]) + b1.w;
+          if (p.has_residual) {
+            const uint4 rr = *reinterpret_cast<const uint4*>(rslab + off);
+            const __half2* hr = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 f = __half22float2(hr[q]);
+              v[2 * q] += f.x;
+              v[2 * q + 1] += f.y;
+            }
+          }
+          if (do_relu) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
+          }
+          uint4 o;
+          __half2* po = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) po[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+          *reinterpret_cast<uint4*>(oslab + off) = o;
+        }
         fence_proxy_async();     // staging writes (generic proxy) -> visible to the TMA store (async proxy)
-        named_bar_sync(1, 128);  // slab complete; residual slab b fully consumed
+        named_bar_sync(1, 256);  // slab complete; residual slab b fully consumed
         if (leader) {
-          tma_store_4d(&p.out_map, out_stage + b * A_TILE_BYTES, ch0, w0, h0, img);
+          tma_store_4d(&p.out_map, out_stage + b * A_TILE_BYTES, nt * BN + j * 64, w0, h0, img);
           tma_store_commit();
           if (p.has_residual && g + 2 < total_sub) issue_res(g + 2);
         }
@@ -430,19 +426,35 @@ __global__ void __launch_bounds__(STEM_TC_THREADS, 2) stem_tc_kernel(const __gri
   const int num_tiles = p.n_img * tiles_per_img;
   uint32_t mma_phase = 0;
   bool w_ready = false;
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+  constexpr int NPRE = (3 * S_PH * S_PW + STEM_TC_THREADS - 1) / STEM_TC_THREADS;  // 11 loads in flight / thread
+  float pre[NPRE];
+  auto load_patch = [&](int tile) {  // fp32 NCHW -> registers, zero outside the image
     const int img = tile / tiles_per_img, tr = tile - img * tiles_per_img;
-    const int oh0 = (tr / p.tiles_w) * S_TH, ow0 = (tr % p.tiles_w) * S_TW;
-    const int ih0 = 2 * oh0 - 3, iw0 = 2 * ow0 - 3;
-    // ---- input patch: fp32 NCHW -> fp16 [3][13][72], zero outside the image ----
-    for (int e = tid; e < 3 * S_PH * S_PW; e += STEM_TC_THREADS) {
+    const int ih0 = 2 * ((tr / p.tiles_w) * S_TH) - 3, iw0 = 2 * ((tr % p.tiles_w) * S_TW) - 3;
+#pragma unroll
+    for (int j = 0; j < NPRE; ++j) {
+      const int e = tid + j * STEM_TC_THREADS;
       const int c = e / (S_PH * S_PW), rem = e - c * (S_PH * S_PW), ph = rem / S_PW, pw = rem - ph * S_PW;
       const int ih = ih0 + ph, iw = iw0 + pw;
       float v = 0.f;
-      if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) v = __ldg(p.x + (((size_t)img * 3 + c) * p.H + ih) * p.W + iw);
-      patch[e] = __float2half_rn(v);
+      if (e < 3 * S_PH * S_PW && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W)
+        v = __ldg(p.x + (((size_t)img * 3 + c) * p.H + ih) * p.W + iw);
+      pre[j] = v;
+    }
+  };
+  if ((int)blockIdx.x < num_tiles) load_patch(blockIdx.x);
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int img = tile / tiles_per_img, tr = tile - img * tiles_per_img;
+    const int oh0 = (tr / p.tiles_w) * S_TH, ow0 = (tr % p.tiles_w) * S_TW;
+    // ---- input patch: registers -> fp16 [3][13][72] in shared memory ----
+#pragma unroll
+    for (int j = 0; j < NPRE; ++j) {
+      const int e = tid + j * STEM_TC_THREADS;
+      if (e < 3 * S_PH * S_PW) patch[e] = __float2half_rn(pre[j]);
     }
     __syncthreads();
+    // the next tile's patch travels from HBM while this tile is assembled, multiplied and stored
+    if (tile + (int)gridDim.x < num_tiles) load_patch(tile + gridDim.x);
     // ---- operand tile: chunk (pixel px, group cr) = patch[c][2*(px/32) + r][2*(px%32) .. +7] ----
     for (int q = tid; q < 128 * 21; q += STEM_TC_THREADS) {
       const int px = q & 127, cr = q >> 7;
@@ -679,6 +691,7 @@ int ctl_conv2d_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, int32_t 
   CTL_CHECK_ARG(n >= 1 && h >= 1 && w >= 1, "bad activation shape");
   CTL_CHECK_ARG(cin % 64 == 0 && cout % 64 == 0, "Cin=%d and Cout=%d must be multiples of 64", cin, cout);
   CTL_CHECK_ARG((ksize == 1 || ksize == 3) && (stride == 1 || stride == 2), "only 1x1 / 3x3, stride 1 / 2");
+  CTL_CHECK_ARG(relu_from % 32 == 0, "relu_from=%d must be a multiple of 32", relu_from);
   CTL_CHECK_ARG(stride == 1 || (h % 2 == 0 && w % 2 == 0), "stride 2 needs even H, W (got %dx%d)", h, w);
   int rc = ctl_device_check();
   if (rc) return rc;
