@@ -52,6 +52,7 @@ struct ConvKernelParams {
   int has_residual;
   int relu;                 // apply ReLU to channels >= relu_from
   int relu_from;
+  long long* prof;          // optional [gridDim.x][8] cycle counters (tools/prof_conv.py), else null
 };
 
 template <int BN>
@@ -60,29 +61,65 @@ struct ConvCfg {
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int STAGES = BN == 64 ? 5 : (BN == 128 ? 4 : 3);
   static constexpr int TMEM_COLS = BN == 64 ? 128 : (BN == 128 ? 256 : 512);  // 2 accumulator stages
-  // + 2 output and 2 residual staging slabs of [128 px][64 ch] fp16 (16 KiB each)
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 4 * A_TILE_BYTES + 1024 + 256;
+  static constexpr int OUT_SLABS = 4;                  // [128 px][64 ch] fp16 staging slabs for the TMA stores
+  static constexpr int IDENT_BYTES = 64 * CBK * 2;     // 64x64 identity operand (residual add on the tensor core)
+  static constexpr int BIAS_BYTES = 2 * BN * 4;        // double-buffered bias slice
+  static constexpr size_t SMEM =
+      (size_t)STAGES * STAGE_BYTES + OUT_SLABS * A_TILE_BYTES + IDENT_BYTES + BIAS_BYTES + 1024 + 256;
+};
+
+// Tile order: n fastest, then pixel tiles row-major inside an image, then images.  Each CTA owns a
+// CONTIGUOUS range of tiles so that coordinates advance by carries (no integer division in the loop)
+// and consecutive tiles of a CTA reuse the same activation tile from L2.
+struct TileIter {
+  int nt, tw, th, img;
+  __device__ __forceinline__ void init(int tile, const ConvKernelParams& p) {
+    const int mt = tile / p.n_tiles;
+    nt = tile - mt * p.n_tiles;
+    const int per_img = p.tiles_w * p.tiles_h;
+    img = mt / per_img;
+    const int tr = mt - img * per_img;
+    th = tr / p.tiles_w;
+    tw = tr - th * p.tiles_w;
+  }
+  __device__ __forceinline__ void next(const ConvKernelParams& p) {
+    if (++nt == p.n_tiles) {
+      nt = 0;
+      if (++tw == p.tiles_w) {
+        tw = 0;
+        if (++th == p.tiles_h) {
+          th = 0;
+          ++img;
+        }
+      }
+    }
+  }
 };
 
 template <int BN>
 __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
   using Cfg = ConvCfg<BN>;
+  constexpr int NSUB = BN / 64;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t out_stage = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;  // 2 x 16 KiB
-  const uint32_t res_stage = out_stage + 2 * A_TILE_BYTES;                // 2 x 16 KiB
-  const uint32_t bar_base = res_stage + 2 * A_TILE_BYTES;
+  const uint32_t out_stage = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  const uint32_t ident = out_stage + Cfg::OUT_SLABS * A_TILE_BYTES;
+  const uint32_t bias_sm = ident + Cfg::IDENT_BYTES;
+  const uint32_t bar_base = bias_sm + Cfg::BIAS_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + s); };
-  auto res_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 4 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 6);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
+  uint8_t* gsm = smem_raw + (smem_base - smem_u32(smem_raw));  // generic view of the aligned arena
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.m_tiles * p.n_tiles;
-  const int k_blocks = p.n_taps * p.cin_blocks;
-  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  const int conv_kblocks = p.n_taps * p.cin_blocks;
+  // contiguous, balanced tile range of this CTA
+  const int per = num_tiles / (int)gridDim.x, rem = num_tiles - per * (int)gridDim.x;
+  const int t_begin = (int)blockIdx.x * per + min((int)blockIdx.x, rem);
+  const int t_end = t_begin + per + ((int)blockIdx.x < rem ? 1 : 0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -92,7 +129,6 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), 8);
-      mbar_init(res_bar(s), 1);
     }
     fence_barrier_init();
   }
@@ -103,6 +139,16 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     tma_prefetch_desc(&p.res_map);
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  {  // 64x64 fp16 identity, K-major, SWIZZLE_128B: row r holds a single 1.0 at k = r
+    uint8_t* id = gsm + (ident - smem_base);
+    for (int i = threadIdx.x; i < Cfg::IDENT_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(id)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      const int r = threadIdx.x;
+      *reinterpret_cast<__half*>(id + r * 128 + (((r >> 3) ^ (r & 7)) << 4) + (r & 7) * 2) = __float2half(1.f);
+    }
+    fence_proxy_async();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -110,21 +156,36 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    if (lane == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0 && t_begin < t_end) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;  // n fastest: neighbours share the A tile in L2
-        const int img = mt / tiles_per_img, tr = mt - img * tiles_per_img;
-        const int h0 = (tr / p.tiles_w) * p.TH, w0 = (tr % p.tiles_w) * p.TW;
+      TileIter it;
+      it.init(t_begin, p);
+      for (int tile = t_begin; tile < t_end; ++tile, it.next(p)) {
+        const int h0 = it.th * p.TH, w0 = it.tw * p.TW;
         for (int t = 0; t < p.n_taps; ++t) {
           const ConvTap tap = p.taps[t];
           for (int cb = 0; cb < p.cin_blocks; ++cb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t dst = smem_base + stage * Cfg::STAGE_BYTES;
             mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-            tma_load_4d(dst, &p.a_map[tap.map], full_bar(stage), cb * CBK, w0 + tap.dw, h0 + tap.dh, img);
-            tma_load_2d(dst + A_TILE_BYTES, &p.b_map, full_bar(stage), tap.koff + cb * CBK, nt * BN);
+            tma_load_4d(dst, &p.a_map[tap.map], full_bar(stage), cb * CBK, w0 + tap.dw, h0 + tap.dh, it.img);
+            tma_load_2d(dst + A_TILE_BYTES, &p.b_map, full_bar(stage), tap.koff + cb * CBK, it.nt * BN);
+            if (++stage == Cfg::STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+        if (p.has_residual) {
+          // the residual rides the same ring: one [128 px][64 ch] slab per 64 output channels,
+          // added to the accumulator by an identity MMA (exact: fp16 x 1.0 into fp32)
+          for (int j = 0; j < NSUB; ++j) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_arrive_expect_tx(full_bar(stage), A_TILE_BYTES);
+            tma_load_4d(smem_base + stage * Cfg::STAGE_BYTES, &p.res_map, full_bar(stage), it.nt * BN + j * 64, w0, h0,
+                        it.img);
             if (++stage == Cfg::STAGES) {
               stage = 0;
               phase ^= 1u;
@@ -134,17 +195,20 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       }
     }
   } else if (warp == 1) {
+    // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(CBM, BN);
+      constexpr uint32_t idesc64 = make_idesc_f16(CBM, 64);
+      const uint64_t d_ident = make_sw128_kmajor_desc(ident);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = t_begin; tile < t_end; ++tile) {
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
         const uint32_t acc = tmem_base + as * BN;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        for (int kb = 0; kb < conv_kblocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t base = smem_base + stage * Cfg::STAGE_BYTES;
@@ -159,6 +223,21 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
             phase ^= 1u;
           }
         }
+        if (p.has_residual) {
+          for (int j = 0; j < NSUB; ++j) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint64_t da = make_sw128_kmajor_desc(smem_base + stage * Cfg::STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < CBK / 16; ++k)
+              umma_f16(acc + j * 64, desc_advance_k(da, k), desc_advance_k(d_ident, k), idesc64, 1u);
+            umma_commit(empty_bar(stage));
+            if (++stage == Cfg::STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
         umma_commit(tfull_bar(as));
         if (++as == 2) {
           as = 0;
@@ -168,75 +247,67 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     }
   } else {
     // ===== epilogue: 8 warps (two per 32-lane TMEM quarter, splitting the columns).  The
-    // accumulator is drained in 64-channel sub-tiles: TMEM -> registers -> (+bias, +residual from
-    // shared memory, ReLU) -> fp16 -> swizzled staging slab -> one TMA store per sub-tile.
-    // Residual sub-tiles arrive by TMA two sub-tiles ahead, so no global-memory latency is ever
-    // exposed to these warps and every HBM access is a full 128-byte line.
-    constexpr int NSUB = BN / 64;
+    // accumulator (conv + residual) is drained in 64-channel sub-tiles: TMEM -> registers ->
+    // (+bias, ReLU) -> fp16 -> swizzled staging slab -> one TMA store per sub-tile; four slabs
+    // keep up to three stores in flight.  No global memory access is issued by these warps
+    // except the per-tile bias slice.
     const int ew = warp - 2;              // 0..7
+    const int et = threadIdx.x - 64;      // 0..255
     const int quarter = warp & 3;         // TMEM lane quarter this warp may read
     const int chalf = ew >> 2;            // which 32-channel half of every 64-channel sub-tile
     const int pix = quarter * 32 + lane;  // pixel inside the tile == TMEM lane == staging row
     const bool leader = (ew == 0 && lane == 0);
     const uint32_t row_off = pix * 128;
     const uint32_t sw = pix & 7;
-    uint8_t* gsm = smem_raw + (out_stage - smem_u32(smem_raw));  // generic pointer to the staging area
-    const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const long long total_sub = (long long)my_tiles * NSUB;
-    auto tile_coords = [&](int tile, int& nt, int& w0, int& h0, int& img) {
-      const int mt = tile / p.n_tiles;
-      nt = tile - mt * p.n_tiles;
-      img = mt / tiles_per_img;
-      const int tr = mt - img * tiles_per_img;
-      h0 = (tr / p.tiles_w) * p.TH;
-      w0 = (tr % p.tiles_w) * p.TW;
-    };
-    auto issue_res = [&](long long gg) {  // leader only
-      const int it = (int)(gg / NSUB), j = (int)(gg - (long long)it * NSUB);
-      int nt, w0, h0, img;
-      tile_coords(blockIdx.x + it * gridDim.x, nt, w0, h0, img);
-      const int b = (int)(gg & 1);
-      mbar_arrive_expect_tx(res_bar(b), A_TILE_BYTES);
-      tma_load_4d(res_stage + b * A_TILE_BYTES, &p.res_map, res_bar(b), nt * BN + j * 64, w0, h0, img);
-    };
-    if (p.has_residual && leader) {
-      if (total_sub > 0) issue_res(0);
-      if (total_sub > 1) issue_res(1);
-    }
+    uint8_t* oslabs = gsm + (out_stage - smem_base);
+    float* bias_s = reinterpret_cast<float*>(gsm + (bias_sm - smem_base));
     int as = 0;
     uint32_t aphase = 0;
-    long long g = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      int nt, w0, h0, img;
-      tile_coords(tile, nt, w0, h0, img);
+    uint32_t g = 0;  // running sub-tile counter -> staging slab
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = clock64();
+#define CTL_STAMP(i)                         \
+  if (p.prof) {                              \
+    const long long _t = clock64();          \
+    pc[i] += _t - tprev;                     \
+    tprev = _t;                              \
+  }
+    TileIter it;
+    if (t_begin < t_end) it.init(t_begin, p);
+    for (int tile = t_begin; tile < t_end; ++tile, it.next(p)) {
+      const int h0 = it.th * p.TH, w0 = it.tw * p.TW;
+      float* bias_t = bias_s + ((tile - t_begin) & 1) * BN;  // double-buffered: the previous tile may still read its slice
+      if (et < BN) bias_t[et] = __ldg(p.bias + it.nt * BN + et);
+      CTL_STAMP(7)
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
+      CTL_STAMP(0)
       const uint32_t t0 = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16) + chalf * 32;
 #pragma unroll 1
       for (int j = 0; j < NSUB; ++j, ++g) {
-        const int b = (int)(g & 1);
-        const int ch0 = nt * BN + j * 64 + chalf * 32;  // first of this thread's 32 channels
+        const uint32_t b = g & (Cfg::OUT_SLABS - 1);
+        const int ch0 = j * 64 + chalf * 32;  // first of this thread's 32 channels inside the n-tile
         uint32_t r[32];
         tmem_ld16(t0 + j * 64, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
         tmem_ld16(t0 + j * 64 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
-        // staging slab b was handed to the TMA store two sub-tiles ago: wait until it has been read
-        if (leader) tma_store_wait_read<1>();
-        named_bar_sync(1, 256);
-        if (p.has_residual) mbar_wait(res_bar(b), (uint32_t)((g >> 1) & 1));
+        // slab b was handed to a TMA store OUT_SLABS sub-tiles ago: wait until that store has read it
+        if (leader) tma_store_wait_read<Cfg::OUT_SLABS - 1>();
+        CTL_STAMP(1)
+        named_bar_sync(1, 256);  // also publishes this tile's bias slice
+        CTL_STAMP(2)
         tmem_ld_wait();
+        CTL_STAMP(4)
         if (j == NSUB - 1) {  // last TMEM read of this accumulator stage: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(as));
         }
-        uint8_t* oslab = gsm + b * A_TILE_BYTES + row_off;
-        const uint8_t* rslab = gsm + (2 + b) * A_TILE_BYTES + row_off;
-        const bool do_relu = p.relu && ch0 >= p.relu_from;  // relu_from is a multiple of 32
+        uint8_t* oslab = oslabs + b * A_TILE_BYTES + row_off;
+        const bool do_relu = p.relu && (it.nt * BN + ch0) >= p.relu_from;  // relu_from is a multiple of 32
 #pragma unroll
         for (int c = 0; c < 4; ++c) {  // four 16-byte chunks = 32 channels
-          const uint32_t off = ((uint32_t)(chalf * 4 + c) ^ sw) << 4;
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + c * 8));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + c * 8 + 4));
+          const float4 b0 = *reinterpret_cast<const float4*>(bias_t + ch0 + c * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(bias_t + ch0 + c * 8 + 4);
           float v[8];
           v[0] = __uint_as_float(r[c * 8 + 0]) + b0.x;
           v[1] = __uint_as_float(r[c * 8 + 1]) + b0.y;
@@ -246,16 +317,6 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
           v[5] = __uint_as_float(r[c * 8 + 5]) + b1.y;
           v[6] = __uint_as_float(r[c * 8 + 6]) + b1.z;
           v[7] = __uint_as_float(r[c * 8 + 7]) + b1.w;
-          if (p.has_residual) {
-            const uint4 rr = *reinterpret_cast<const uint4*>(rslab + off);
-            const __half2* hr = reinterpret_cast<const __half2*>(&rr);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float2 f = __half22float2(hr[q]);
-              v[2 * q] += f.x;
-              v[2 * q + 1] += f.y;
-            }
-          }
           if (do_relu) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
@@ -264,15 +325,16 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
           __half2* po = reinterpret_cast<__half2*>(&o);
 #pragma unroll
           for (int q = 0; q < 4; ++q) po[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
-          *reinterpret_cast<uint4*>(oslab + off) = o;
+          *reinterpret_cast<uint4*>(oslab + (((uint32_t)(chalf * 4 + c) ^ sw) << 4)) = o;
         }
+        CTL_STAMP(5)
         fence_proxy_async();     // staging writes (generic proxy) -> visible to the TMA store (async proxy)
-        named_bar_sync(1, 256);  // slab complete; residual slab b fully consumed
+        named_bar_sync(1, 256);  // slab complete
         if (leader) {
-          tma_store_4d(&p.out_map, out_stage + b * A_TILE_BYTES, nt * BN + j * 64, w0, h0, img);
+          tma_store_4d(&p.out_map, out_stage + b * A_TILE_BYTES, it.nt * BN + j * 64, w0, h0, it.img);
           tma_store_commit();
-          if (p.has_residual && g + 2 < total_sub) issue_res(g + 2);
         }
+        CTL_STAMP(6)
       }
       if (++as == 2) {
         as = 0;
@@ -280,6 +342,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       }
     }
     if (leader) tma_store_wait<0>();  // shared memory must outlive the last stores
+    if (p.prof && (leader || (ew == 5 && lane == 7))) {
+      long long* dst = p.prof + ((size_t)blockIdx.x * 2 + (leader ? 0 : 1)) * 8;
+      for (int i = 0; i < 8; ++i) dst[i] = pc[i];
+    }
+#undef CTL_STAMP
   }
   tc_fence_before();
   __syncthreads();
@@ -663,6 +730,8 @@ static void pick_tile(int Ho, int Wo, int* TH, int* TW) {
   *TW = btw;
 }
 
+static long long* g_conv_prof = nullptr;
+
 template <int BN>
 static int launch_conv(const ConvKernelParams& p, cudaStream_t st) {
   static bool attr_set = false;
@@ -710,6 +779,7 @@ int ctl_conv2d_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, int32_t 
   p.has_residual = residual != nullptr;
   p.relu = relu;
   p.relu_from = relu_from;
+  p.prof = g_conv_prof;
   p.m_tiles = n * p.tiles_h * p.tiles_w;
   const int BN = cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64);
   p.n_tiles = cout / BN;
@@ -766,6 +836,9 @@ int ctl_conv2d_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, int32_t 
   if (BN == 128) return launch_conv<128>(p, st);
   return launch_conv<64>(p, st);
 }
+
+/* debug: per-CTA epilogue cycle counters [sm_count][2][8] written by the next conv launches */
+void ctl_debug_set_conv_profile(long long* device_buffer) { g_conv_prof = device_buffer; }
 
 int ctl_stem_conv7x7(const float* x_nchw, int32_t n, int32_t h, int32_t w, const float* weight_k64, const float* bias,
                      int32_t relu, void* out_nhwc_f16, ctl_stream_t stream) {

@@ -213,6 +213,9 @@ int ctl_xent_smooth_step(const float* logits, int32_t b, int32_t c, const int32_
 int ctl_conv2d_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, int32_t cin, const void* weight,
                         const float* bias, const void* residual, void* out, int32_t cout, int32_t ksize,
                         int32_t stride, int32_t relu, int32_t relu_from, ctl_stream_t stream);
+/* debug aid (not part of the drop-in surface): when non-NULL, the epilogue of the following
+ * ctl_conv2d_nhwc_f16 launches adds its per-phase clock64() cycles into [grid][2][8] int64 slots. */
+void ctl_debug_set_conv_profile(long long* device_buffer);
 int ctl_stem_conv7x7(const float* x_nchw, int32_t n, int32_t h, int32_t w, const float* weight_k64, const float* bias,
                      int32_t relu, void* out_nhwc_f16, ctl_stream_t stream);
 /* tensor-core stem: weight_k192_f16 = [64][192] fp16, k = (c*7 + r)*8 + s (s = 7 and k >= 168 zero) */
