@@ -444,11 +444,12 @@ static constexpr int SK = 192;                    // padded K
 static constexpr int S_TH = 4, S_TW = 32;         // output tile
 static constexpr int S_PH = 2 * S_TH + 5;         // 13 input rows
 static constexpr int S_PW = 72;                   // 2*32 + 5 = 69 input columns, padded to 72
-static constexpr int STEM_TC_THREADS = 256;
+static constexpr int STEM_BUILDERS = 256;                   // warps 0-7 assemble operand tiles
+static constexpr int STEM_TC_THREADS = STEM_BUILDERS + 32 + 128;  // + MMA warp (8) + 4 epilogue warps (9-12)
 static constexpr int S_A_BYTES = 3 * A_TILE_BYTES;          // 48 KiB: three [128][64] fp16 slabs
 static constexpr int S_B_BYTES = 3 * 64 * 128;              // 24 KiB: three [64][64] fp16 slabs
 static constexpr int S_PATCH_BYTES = 3 * S_PH * S_PW * 2;   // 5.6 KiB
-static constexpr size_t STEM_TC_SMEM = S_A_BYTES + S_B_BYTES + S_PATCH_BYTES + 1024 + 64;
+static constexpr size_t STEM_TC_SMEM = 2 * S_A_BYTES + S_B_BYTES + 2 * S_PATCH_BYTES + 1024 + 128 + 256;
 
 struct StemParams {
   CUtensorMap w_map;  // [64][192] fp16, box {64, 64}
@@ -458,132 +459,194 @@ struct StemParams {
   int n_img, H, W, Ho, Wo, tiles_h, tiles_w, relu;
 };
 
-__global__ void __launch_bounds__(STEM_TC_THREADS, 2) stem_tc_kernel(const __grid_constant__ StemParams p) {
+// Persistent, one CTA per SM, three roles connected by mbarriers:
+//   builders (8 warps): prefetched fp32 patch -> fp16 patch in smem -> swizzled operand tile A[buf]
+//   MMA warp          : 12 tcgen05.mma (M=128, N=64) per tile into TMEM stage `as`
+//   epilogue (4 warps): TMEM -> +bias (+ReLU) -> fp16 -> one 128-byte NHWC line per pixel
+// A, the patch and the accumulator are double-buffered, so all three roles overlap.
+__global__ void __launch_bounds__(STEM_TC_THREADS, 1) stem_tc_kernel(const __grid_constant__ StemParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t sA = base, sB = base + S_A_BYTES;
-  __half* patch = reinterpret_cast<__half*>(gbase + S_A_BYTES + S_B_BYTES);
-  const uint32_t bar_w = base + S_A_BYTES + S_B_BYTES + S_PATCH_BYTES;  // weights landed
-  const uint32_t bar_mma = bar_w + 8;                                   // accumulator ready
-  const uint32_t tmem_slot = bar_w + 16;
+  const uint32_t sA = base, sB = base + 2 * S_A_BYTES;
+  __half* patch0 = reinterpret_cast<__half*>(gbase + 2 * S_A_BYTES + S_B_BYTES);
+  const uint32_t bars = base + 2 * S_A_BYTES + S_B_BYTES + 2 * S_PATCH_BYTES;
+  const uint32_t bar_w = bars;  // weights landed
+  auto a_full = [&](int b) { return bars + 8u * (1 + b); };
+  auto a_empty = [&](int b) { return bars + 8u * (3 + b); };
+  auto t_full = [&](int b) { return bars + 8u * (5 + b); };
+  auto t_empty = [&](int b) { return bars + 8u * (7 + b); };
+  const uint32_t tmem_slot = bars + 8u * 9;
+  float* bias_s = reinterpret_cast<float*>(gbase + 2 * S_A_BYTES + S_B_BYTES + 2 * S_PATCH_BYTES + 128);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < 64) bias_s[tid] = p.bias[tid];
   if (tid == 0) {
     mbar_init(bar_w, 1);
-    mbar_init(bar_mma, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(a_full(b), STEM_BUILDERS / 32);  // one arrive per builder warp
+      mbar_init(a_empty(b), 1);
+      mbar_init(t_full(b), 1);
+      mbar_init(t_empty(b), 4);
+    }
     fence_barrier_init();
     tma_prefetch_desc(&p.w_map);
   }
-  if (warp == 0) tmem_alloc<64>(tmem_slot);
-  // the three zero chunks (k = 168..191) of every pixel never change: chunks 5,6,7 of slab 2
-  for (int q = tid; q < 128 * 3; q += STEM_TC_THREADS) {
-    const int px = q & 127, ch = 5 + (q >> 7);
-    *reinterpret_cast<uint4*>(gbase + 2 * A_TILE_BYTES + px * 128 + ((ch ^ (px & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+  if (warp == 8) tmem_alloc<128>(tmem_slot);
+  if (tid < STEM_BUILDERS) {
+    // the three zero chunks (k = 168..191) of every pixel never change: chunks 5,6,7 of slab 2, both buffers
+    for (int q = tid; q < 2 * 128 * 3; q += STEM_BUILDERS) {
+      const int buf = q / 384, qq = q - buf * 384, px = qq & 127, ch = 5 + (qq >> 7);
+      *reinterpret_cast<uint4*>(gbase + buf * S_A_BYTES + 2 * A_TILE_BYTES + px * 128 + ((ch ^ (px & 7)) << 4)) =
+          make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  if (tid == 0) {
-    mbar_arrive_expect_tx(bar_w, S_B_BYTES);
-    for (int kb = 0; kb < 3; ++kb) tma_load_2d(sB + kb * 64 * 128, &p.w_map, bar_w, kb * 64, 0);
-  }
   const int tiles_per_img = p.tiles_h * p.tiles_w;
   const int num_tiles = p.n_img * tiles_per_img;
-  uint32_t mma_phase = 0;
-  bool w_ready = false;
-  constexpr int NPRE = (3 * S_PH * S_PW + STEM_TC_THREADS - 1) / STEM_TC_THREADS;  // 11 loads in flight / thread
-  float pre[NPRE];
-  auto load_patch = [&](int tile) {  // fp32 NCHW -> registers, zero outside the image
-    const int img = tile / tiles_per_img, tr = tile - img * tiles_per_img;
-    const int ih0 = 2 * ((tr / p.tiles_w) * S_TH) - 3, iw0 = 2 * ((tr % p.tiles_w) * S_TW) - 3;
+
+  if (tid < STEM_BUILDERS) {
+    constexpr int NPRE = (3 * S_PH * S_PW + STEM_BUILDERS - 1) / STEM_BUILDERS;  // 11 loads in flight / thread
+    float pre[NPRE];
+    auto load_patch = [&](int tile) {  // fp32 NCHW -> registers, zero outside the image
+      const int img = tile / tiles_per_img, tr = tile - img * tiles_per_img;
+      const int ih0 = 2 * ((tr / p.tiles_w) * S_TH) - 3, iw0 = 2 * ((tr % p.tiles_w) * S_TW) - 3;
 #pragma unroll
-    for (int j = 0; j < NPRE; ++j) {
-      const int e = tid + j * STEM_TC_THREADS;
-      const int c = e / (S_PH * S_PW), rem = e - c * (S_PH * S_PW), ph = rem / S_PW, pw = rem - ph * S_PW;
-      const int ih = ih0 + ph, iw = iw0 + pw;
-      float v = 0.f;
-      if (e < 3 * S_PH * S_PW && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W)
-        v = __ldg(p.x + (((size_t)img * 3 + c) * p.H + ih) * p.W + iw);
-      pre[j] = v;
-    }
-  };
-  if ((int)blockIdx.x < num_tiles) load_patch(blockIdx.x);
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int img = tile / tiles_per_img, tr = tile - img * tiles_per_img;
-    const int oh0 = (tr / p.tiles_w) * S_TH, ow0 = (tr % p.tiles_w) * S_TW;
-    // ---- input patch: registers -> fp16 [3][13][72] in shared memory ----
-#pragma unroll
-    for (int j = 0; j < NPRE; ++j) {
-      const int e = tid + j * STEM_TC_THREADS;
-      if (e < 3 * S_PH * S_PW) patch[e] = __float2half_rn(pre[j]);
-    }
-    __syncthreads();
-    // the next tile's patch travels from HBM while this tile is assembled, multiplied and stored
-    if (tile + (int)gridDim.x < num_tiles) load_patch(tile + gridDim.x);
-    // ---- operand tile: chunk (pixel px, group cr) = patch[c][2*(px/32) + r][2*(px%32) .. +7] ----
-    for (int q = tid; q < 128 * 21; q += STEM_TC_THREADS) {
-      const int px = q & 127, cr = q >> 7;
-      const int c = cr / 7, r = cr - c * 7;
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(patch + (c * S_PH + 2 * (px >> 5) + r) * S_PW + 2 * (px & 31));
-      const uint4 v = make_uint4(src[0], src[1], src[2], src[3]);
-      const int slab = cr >> 3, ch = cr & 7;
-      *reinterpret_cast<uint4*>(gbase + slab * A_TILE_BYTES + px * 128 + ((ch ^ (px & 7)) << 4)) = v;
-    }
-    fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-    __syncthreads();
-    if (tid == 0) {
-      if (!w_ready) mbar_wait(bar_w, 0);
-      tc_fence_after();
-      constexpr uint32_t idesc = make_idesc_f16(128, 64);
-#pragma unroll
-      for (int kb = 0; kb < 3; ++kb) {
-        const uint64_t da = make_sw128_kmajor_desc(sA + kb * A_TILE_BYTES);
-        const uint64_t db = make_sw128_kmajor_desc(sB + kb * 64 * 128);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16(tmem_base, desc_advance_k(da, k), desc_advance_k(db, k), idesc, (kb | k) ? 1u : 0u);
+      for (int j = 0; j < NPRE; ++j) {
+        const int e = tid + j * STEM_BUILDERS;
+        const int c = e / (S_PH * S_PW), rem = e - c * (S_PH * S_PW), ph = rem / S_PW, pw = rem - ph * S_PW;
+        const int ih = ih0 + ph, iw = iw0 + pw;
+        float v = 0.f;
+        if (e < 3 * S_PH * S_PW && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W)
+          v = __ldg(p.x + (((size_t)img * 3 + c) * p.H + ih) * p.W + iw);
+        pre[j] = v;
       }
-      umma_commit(bar_mma);
-    }
-    w_ready = true;
-    mbar_wait(bar_mma, mma_phase);
-    mma_phase ^= 1u;
-    tc_fence_after();
-    if (warp < 4) {
-      const int px = warp * 32 + lane;
-      const int oh = oh0 + (px >> 5), ow = ow0 + (px & 31);
-      const bool ok = oh < p.Ho && ow < p.Wo;
-      __half* dst = p.out + (((size_t)img * p.Ho + oh) * p.Wo + ow) * 64;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[16];
-        tmem_ld16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c * 16, r);
-        tmem_ld_wait();
-        if (ok) {
-          uint4 oa, ob;
-          __half2* pa = reinterpret_cast<__half2*>(&oa);
-          __half2* pb = reinterpret_cast<__half2*>(&ob);
+    };
+    // per-thread constants of the operand assembly: pixel px, (c, r) groups cr = 2 i + hi
+    const int px = tid & 127, hi = tid >> 7;
+    int src_off[11], dst_off[11];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float a0 = __uint_as_float(r[2 * j]) + __ldg(p.bias + c * 16 + 2 * j);
-            float a1 = __uint_as_float(r[2 * j + 1]) + __ldg(p.bias + c * 16 + 2 * j + 1);
-            if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-            if (j < 4) pa[j] = __floats2half2_rn(a0, a1); else pb[j - 4] = __floats2half2_rn(a0, a1);
-          }
-          *reinterpret_cast<uint4*>(dst + c * 16) = oa;
-          *reinterpret_cast<uint4*>(dst + c * 16 + 8) = ob;
+    for (int i = 0; i < 11; ++i) {
+      const int cr = 2 * i + hi, c = cr / 7, r = cr - c * 7;
+      src_off[i] = (c * S_PH + 2 * (px >> 5) + r) * S_PW + 2 * (px & 31);
+      dst_off[i] = (cr >> 3) * A_TILE_BYTES + px * 128 + (((cr & 7) ^ (px & 7)) << 4);
+    }
+    if ((int)blockIdx.x < num_tiles) load_patch(blockIdx.x);
+    int buf = 0;
+    uint32_t eph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      __half* patch = patch0 + buf * (S_PATCH_BYTES / 2);
+#pragma unroll
+      for (int j = 0; j < NPRE; ++j) {
+        const int e = tid + j * STEM_BUILDERS;
+        if (e < 3 * S_PH * S_PW) patch[e] = __float2half_rn(pre[j]);
+      }
+      named_bar_sync(2, STEM_BUILDERS);  // patch[buf] complete (its previous readers finished two tiles ago)
+      if (tile + (int)gridDim.x < num_tiles) load_patch(tile + gridDim.x);  // next patch travels during the build
+      mbar_wait(a_empty(buf), eph ^ 1u);  // the MMAs that read A[buf] two tiles ago have completed
+      uint8_t* A = gbase + buf * S_A_BYTES;
+#pragma unroll
+      for (int i = 0; i < 11; ++i) {
+        if (2 * i + hi < 21) {
+          const uint32_t* src = reinterpret_cast<const uint32_t*>(patch + src_off[i]);
+          *reinterpret_cast<uint4*>(A + dst_off[i]) = make_uint4(src[0], src[1], src[2], src[3]);
+        }
+      }
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full(buf));
+      if (++buf == 2) {
+        buf = 0;
+        eph ^= 1u;
+      }
+    }
+  } else if (warp == 8) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_w, S_B_BYTES);
+      for (int kb = 0; kb < 3; ++kb) tma_load_2d(sB + kb * 64 * 128, &p.w_map, bar_w, kb * 64, 0);
+      mbar_wait(bar_w, 0);
+      constexpr uint32_t idesc = make_idesc_f16(128, 64);
+      int buf = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(t_empty(buf), ph ^ 1u);  // accumulator stage drained
+        mbar_wait(a_full(buf), ph);        // operand tile assembled
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 3; ++kb) {
+          const uint64_t da = make_sw128_kmajor_desc(sA + buf * S_A_BYTES + kb * A_TILE_BYTES);
+          const uint64_t db = make_sw128_kmajor_desc(sB + kb * 64 * 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_base + buf * 64, desc_advance_k(da, k), desc_advance_k(db, k), idesc, (kb | k) ? 1u : 0u);
+        }
+        umma_commit(a_empty(buf));
+        umma_commit(t_full(buf));
+        if (++buf == 2) {
+          buf = 0;
+          ph ^= 1u;
         }
       }
     }
-    tc_fence_before();
-    __syncthreads();  // accumulator drained, patch and operand tile free for the next tile
-    tc_fence_after();
+  } else {
+    const int quarter = warp & 3;  // warps 9..12 -> quarters 1,2,3,0
+    const int px = quarter * 32 + lane;
+    int buf = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int img = tile / tiles_per_img, tr = tile - img * tiles_per_img;
+      const int oh = (tr / p.tiles_w) * S_TH + (px >> 5), ow = (tr % p.tiles_w) * S_TW + (px & 31);
+      const bool ok = oh < p.Ho && ow < p.Wo;
+      __half* dst = p.out + (((size_t)img * p.Ho + oh) * p.Wo + ow) * 64;
+      mbar_wait(t_full(buf), ph);
+      tc_fence_after();
+      uint32_t r[64];
+      const uint32_t t0 = tmem_base + buf * 64 + (static_cast<uint32_t>(quarter * 32) << 16);
+      tmem_ld16(t0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+      tmem_ld16(t0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+      tmem_ld16(t0 + 32, *reinterpret_cast<uint32_t(*)[16]>(&r[32]));
+      tmem_ld16(t0 + 48, *reinterpret_cast<uint32_t(*)[16]>(&r[48]));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty(buf));
+      if (ok) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 o;
+          __half2* po = reinterpret_cast<__half2*>(&o);
+          const float4 bA = *reinterpret_cast<const float4*>(bias_s + c * 8);
+          const float4 bB = *reinterpret_cast<const float4*>(bias_s + c * 8 + 4);
+          const float bv[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float a0 = __uint_as_float(r[c * 8 + 2 * q]) + bv[2 * q];
+            float a1 = __uint_as_float(r[c * 8 + 2 * q + 1]) + bv[2 * q + 1];
+            if (p.relu) {
+              a0 = fmaxf(a0, 0.f);
+              a1 = fmaxf(a1, 0.f);
+            }
+            po[q] = __floats2half2_rn(a0, a1);
+          }
+          *reinterpret_cast<uint4*>(dst + c * 8) = o;
+        }
+      }
+      if (++buf == 2) {
+        buf = 0;
+        ph ^= 1u;
+      }
+    }
   }
-  if (warp == 0) {
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
     __syncwarp();
-    tmem_dealloc<64>(tmem_base);
+    tc_fence_after();
+    tmem_dealloc<128>(tmem_base);
   }
 }
 
@@ -889,7 +952,7 @@ int ctl_stem_conv7x7_tc(const float* x_nchw, int32_t n, int32_t h, int32_t w, co
     attr_set = true;
   }
   const long long tiles = (long long)n * p.tiles_h * p.tiles_w;
-  const int grid = (int)std::min<long long>(tiles, 2LL * sm_count());
+  const int grid = (int)std::min<long long>(tiles, (long long)sm_count());
   stem_tc_kernel<<<grid, STEM_TC_THREADS, STEM_TC_SMEM, (cudaStream_t)stream>>>(p);
   CTL_LAUNCH_CHECK();
   return 0;
