@@ -449,11 +449,13 @@ static constexpr int STEM_TC_THREADS = STEM_BUILDERS + 32 + 128;  // + MMA warp 
 static constexpr int S_A_BYTES = 3 * A_TILE_BYTES;          // 48 KiB: three [128][64] fp16 slabs
 static constexpr int S_B_BYTES = 3 * 64 * 128;              // 24 KiB: three [64][64] fp16 slabs
 static constexpr int S_PATCH_BYTES = 3 * S_PH * S_PW * 2;   // 5.6 KiB
-static constexpr size_t STEM_TC_SMEM = 2 * S_A_BYTES + S_B_BYTES + 2 * S_PATCH_BYTES + 1024 + 128 + 256;
+static constexpr size_t STEM_TC_SMEM =
+    2 * S_A_BYTES + S_B_BYTES + 2 * A_TILE_BYTES /*store staging*/ + 2 * S_PATCH_BYTES + 1024 + 128 + 256;
 
 struct StemParams {
-  CUtensorMap w_map;  // [64][192] fp16, box {64, 64}
-  const float* x;     // NCHW fp32
+  CUtensorMap w_map;    // [64][192] fp16, box {64, 64}
+  CUtensorMap out_map;  // NHWC fp16 output, box {64 ch, 32, 4, 1}
+  const float* x;       // NCHW fp32
   const float* bias;
   __half* out;        // NHWC fp16 [n, Ho, Wo, 64]
   int n_img, H, W, Ho, Wo, tiles_h, tiles_w, relu;
@@ -468,16 +470,17 @@ __global__ void __launch_bounds__(STEM_TC_THREADS, 1) stem_tc_kernel(const __gri
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t sA = base, sB = base + 2 * S_A_BYTES;
-  __half* patch0 = reinterpret_cast<__half*>(gbase + 2 * S_A_BYTES + S_B_BYTES);
-  const uint32_t bars = base + 2 * S_A_BYTES + S_B_BYTES + 2 * S_PATCH_BYTES;
+  const uint32_t sA = base, sB = base + 2 * S_A_BYTES, sO = sB + S_B_BYTES;
+  constexpr int S_FIXED = 2 * S_A_BYTES + S_B_BYTES + 2 * A_TILE_BYTES;
+  __half* patch0 = reinterpret_cast<__half*>(gbase + S_FIXED);
+  const uint32_t bars = base + S_FIXED + 2 * S_PATCH_BYTES;
   const uint32_t bar_w = bars;  // weights landed
   auto a_full = [&](int b) { return bars + 8u * (1 + b); };
   auto a_empty = [&](int b) { return bars + 8u * (3 + b); };
   auto t_full = [&](int b) { return bars + 8u * (5 + b); };
   auto t_empty = [&](int b) { return bars + 8u * (7 + b); };
   const uint32_t tmem_slot = bars + 8u * 9;
-  float* bias_s = reinterpret_cast<float*>(gbase + 2 * S_A_BYTES + S_B_BYTES + 2 * S_PATCH_BYTES + 128);
+  float* bias_s = reinterpret_cast<float*>(gbase + S_FIXED + 2 * S_PATCH_BYTES + 128);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid < 64) bias_s[tid] = p.bias[tid];
   if (tid == 0) {
@@ -490,6 +493,7 @@ __global__ void __launch_bounds__(STEM_TC_THREADS, 1) stem_tc_kernel(const __gri
     }
     fence_barrier_init();
     tma_prefetch_desc(&p.w_map);
+    tma_prefetch_desc(&p.out_map);
   }
   if (warp == 8) tmem_alloc<128>(tmem_slot);
   if (tid < STEM_BUILDERS) {
@@ -595,13 +599,12 @@ __global__ void __launch_bounds__(STEM_TC_THREADS, 1) stem_tc_kernel(const __gri
   } else {
     const int quarter = warp & 3;  // warps 9..12 -> quarters 1,2,3,0
     const int px = quarter * 32 + lane;
+    const bool leader = (warp == 9 && lane == 0);
     int buf = 0;
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int img = tile / tiles_per_img, tr = tile - img * tiles_per_img;
-      const int oh = (tr / p.tiles_w) * S_TH + (px >> 5), ow = (tr % p.tiles_w) * S_TW + (px & 31);
-      const bool ok = oh < p.Ho && ow < p.Wo;
-      __half* dst = p.out + (((size_t)img * p.Ho + oh) * p.Wo + ow) * 64;
+      const int oh0 = (tr / p.tiles_w) * S_TH, ow0 = (tr % p.tiles_w) * S_TW;
       mbar_wait(t_full(buf), ph);
       tc_fence_after();
       uint32_t r[64];
@@ -610,36 +613,44 @@ __global__ void __launch_bounds__(STEM_TC_THREADS, 1) stem_tc_kernel(const __gri
       tmem_ld16(t0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
       tmem_ld16(t0 + 32, *reinterpret_cast<uint32_t(*)[16]>(&r[32]));
       tmem_ld16(t0 + 48, *reinterpret_cast<uint32_t(*)[16]>(&r[48]));
+      if (leader) tma_store_wait_read<1>();  // staging slab `buf` was stored two tiles ago
+      named_bar_sync(3, 128);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(t_empty(buf));
-      if (ok) {
+      uint8_t* slab = gbase + 2 * S_A_BYTES + S_B_BYTES + buf * A_TILE_BYTES + px * 128;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          uint4 o;
-          __half2* po = reinterpret_cast<__half2*>(&o);
-          const float4 bA = *reinterpret_cast<const float4*>(bias_s + c * 8);
-          const float4 bB = *reinterpret_cast<const float4*>(bias_s + c * 8 + 4);
-          const float bv[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+      for (int c = 0; c < 8; ++c) {
+        uint4 o;
+        __half2* po = reinterpret_cast<__half2*>(&o);
+        const float4 bA = *reinterpret_cast<const float4*>(bias_s + c * 8);
+        const float4 bB = *reinterpret_cast<const float4*>(bias_s + c * 8 + 4);
+        const float bv[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float a0 = __uint_as_float(r[c * 8 + 2 * q]) + bv[2 * q];
-            float a1 = __uint_as_float(r[c * 8 + 2 * q + 1]) + bv[2 * q + 1];
-            if (p.relu) {
-              a0 = fmaxf(a0, 0.f);
-              a1 = fmaxf(a1, 0.f);
-            }
-            po[q] = __floats2half2_rn(a0, a1);
+        for (int q = 0; q < 4; ++q) {
+          float a0 = __uint_as_float(r[c * 8 + 2 * q]) + bv[2 * q];
+          float a1 = __uint_as_float(r[c * 8 + 2 * q + 1]) + bv[2 * q + 1];
+          if (p.relu) {
+            a0 = fmaxf(a0, 0.f);
+            a1 = fmaxf(a1, 0.f);
           }
-          *reinterpret_cast<uint4*>(dst + c * 8) = o;
+          po[q] = __floats2half2_rn(a0, a1);
         }
+        *reinterpret_cast<uint4*>(slab + ((c ^ (px & 7)) << 4)) = o;
+      }
+      fence_proxy_async();
+      named_bar_sync(3, 128);
+      if (leader) {
+        tma_store_4d(&p.out_map, sO + buf * A_TILE_BYTES, 0, ow0, oh0, img);
+        tma_store_commit();
       }
       if (++buf == 2) {
         buf = 0;
         ph ^= 1u;
       }
     }
+    if (leader) tma_store_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -946,6 +957,14 @@ int ctl_stem_conv7x7_tc(const float* x_nchw, int32_t n, int32_t h, int32_t w, co
   if ((rc = encode_tensor_map(&p.w_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 2, weight_k192_f16, dims, strd, box,
                               CU_TENSOR_MAP_SWIZZLE_128B)))
     return rc;
+  {
+    const uint64_t odims[4] = {64, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)n};
+    const uint64_t ostr[4] = {2, 128, (uint64_t)p.Wo * 128, (uint64_t)p.Ho * p.Wo * 128};
+    const uint32_t obox[4] = {64, S_TW, S_TH, 1};
+    if ((rc = encode_tensor_map(&p.out_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, out_nhwc_f16, odims, ostr, obox,
+                                CU_TENSOR_MAP_SWIZZLE_128B)))
+      return rc;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     CTL_CUDA(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEM_TC_SMEM));
