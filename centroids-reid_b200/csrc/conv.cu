@@ -516,17 +516,24 @@ __global__ void __launch_bounds__(STEM_TC_THREADS, 1) stem_tc_kernel(const __gri
   if (tid < STEM_BUILDERS) {
     constexpr int NPRE = (3 * S_PH * S_PW + STEM_BUILDERS - 1) / STEM_BUILDERS;  // 11 loads in flight / thread
     float pre[NPRE];
+    // tile-independent part of every patch element this thread owns: offset inside the image and (ph, pw)
+    int p_off[NPRE], p_hw[NPRE];
+#pragma unroll
+    for (int j = 0; j < NPRE; ++j) {
+      const int e = tid + j * STEM_BUILDERS;
+      const int c = e / (S_PH * S_PW), rem = e - c * (S_PH * S_PW), ph = rem / S_PW, pw = rem - ph * S_PW;
+      p_off[j] = (c * p.H + ph) * p.W + pw;
+      p_hw[j] = e < 3 * S_PH * S_PW ? ((ph << 16) | pw) : (1 << 30);  // out-of-range marker fails the row test
+    }
     auto load_patch = [&](int tile) {  // fp32 NCHW -> registers, zero outside the image
       const int img = tile / tiles_per_img, tr = tile - img * tiles_per_img;
       const int ih0 = 2 * ((tr / p.tiles_w) * S_TH) - 3, iw0 = 2 * ((tr % p.tiles_w) * S_TW) - 3;
+      const float* xb = p.x + (size_t)img * 3 * p.H * p.W + (long long)ih0 * p.W + iw0;
 #pragma unroll
       for (int j = 0; j < NPRE; ++j) {
-        const int e = tid + j * STEM_BUILDERS;
-        const int c = e / (S_PH * S_PW), rem = e - c * (S_PH * S_PW), ph = rem / S_PW, pw = rem - ph * S_PW;
-        const int ih = ih0 + ph, iw = iw0 + pw;
+        const int ih = ih0 + (p_hw[j] >> 16), iw = iw0 + (p_hw[j] & 0xFFFF);
         float v = 0.f;
-        if (e < 3 * S_PH * S_PW && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W)
-          v = __ldg(p.x + (((size_t)img * 3 + c) * p.H + ih) * p.W + iw);
+        if ((unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W) v = __ldg(xb + p_off[j]);
         pre[j] = v;
       }
     };

@@ -22,3 +22,16 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / iters
 print(f"trunk fwd bs={bs}: {ms:.3f} ms -> {bs/ms*1e3:.0f} img/s, {bs*8.1065/ms:.1f} TFLOP/s")
+if os.environ.get("CTL_GRAPH", "1") == "1":
+    from ctl_b200.modelling.backbones.engine import GraphedForward
+    gf = GraphedForward(eng, x, want_emb=False)
+    for _ in range(3):
+        gf()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        gf()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    print(f"trunk fwd bs={bs} (CUDA graph): {ms:.3f} ms -> {bs/ms*1e3:.0f} img/s, {bs*8.1065/ms:.1f} TFLOP/s")
