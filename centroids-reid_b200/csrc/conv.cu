@@ -19,6 +19,8 @@
 // Roofline: tensor pipe for the 3x3 and wide 1x1 convolutions, HBM for the narrow 1x1s
 // (arithmetic intensity 2*Cin*Cout/(2*(Cin+Cout)) flop/B < 221); algorithmic bytes per conv =
 // 2*(M*Cin [if read once] + M*Cout [+ M*Cout residual]) + 2*K*Cout.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.h"
@@ -354,6 +356,282 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     __syncwarp();
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2) for the compute-bound wide convolutions.
+//
+// Two CTAs of a cluster own two neighbouring 128-pixel tiles and the SAME 256 output channels.
+// CTA 0 issues one tcgen05.mma.cta_group::2 (M = 256, N = 256) per 16-wide k-step: rows 0-127 of A
+// come from CTA 0's shared memory, rows 128-255 from CTA 1's; each CTA stages only HALF of the weight
+// tile (128 of the 256 output channels).  Per CTA and k-block that is 16 KiB of activations + 16 KiB of
+// weights instead of 16 + 32 KiB: the shared-memory fill rate (~50-60 B/clk/SM measured), not the
+// tensor pipe, is what bounds the single-CTA kernel on these layers.
+// Protocol: both producers credit their TMA bytes to CTA 0's `full` barrier; the leader's commits are
+// multicast to both CTAs' `empty` / `tmem_full` barriers; both epilogues release the accumulator
+// stage on CTA 0's `tmem_empty` barrier.  Each CTA drains its own 128 TMEM lanes.
+// ---------------------------------------------------------------------------------------
+struct PairCfg {
+  static constexpr int BN = 256;
+  static constexpr int B_HALF_BYTES = (BN / 2) * CBK * 2;        // 16 KiB
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_HALF_BYTES;  // 32 KiB
+  static constexpr int STAGES = 4;
+  static constexpr int OUT_SLABS = 4;
+  static constexpr int IDENT_BYTES = 32 * CBK * 2;  // this CTA's 32 rows of the 64x64 identity
+  static constexpr int BIAS_BYTES = 2 * BN * 4;
+  static constexpr size_t SMEM =
+      (size_t)STAGES * STAGE_BYTES + OUT_SLABS * A_TILE_BYTES + IDENT_BYTES + BIAS_BYTES + 1024 + 256;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
+    conv_gemm_pair_kernel(const __grid_constant__ ConvKernelParams p) {
+  using Cfg = PairCfg;
+  constexpr int BN = Cfg::BN;
+  constexpr int NSUB = BN / 64;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t out_stage = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  const uint32_t ident = out_stage + Cfg::OUT_SLABS * A_TILE_BYTES;
+  const uint32_t bias_sm = ident + Cfg::IDENT_BYTES;
+  const uint32_t bar_base = bias_sm + Cfg::BIAS_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };                         // used in CTA 0 only
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };         // per CTA
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };     // per CTA
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + s); };  // used in CTA 0 only
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
+  uint8_t* gsm = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool is_leader = rank == 0;
+  const int n_clusters = (int)gridDim.x >> 1, cid = (int)blockIdx.x >> 1;
+  const int m_pairs = p.m_tiles >> 1;
+  const int num_tiles = m_pairs * p.n_tiles;  // pair tiles
+  const int conv_kblocks = p.n_taps * p.cin_blocks;
+  const int per = num_tiles / n_clusters, rem = num_tiles - per * n_clusters;
+  const int t_begin = cid * per + min(cid, rem);
+  const int t_end = t_begin + per + (cid < rem ? 1 : 0);
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  // pair tile -> (n tile, this CTA's 128-pixel tile); n fastest
+  auto coords = [&](int tile, int& nt, int& w0, int& h0, int& img) {
+    const int pm = tile / p.n_tiles;
+    nt = tile - pm * p.n_tiles;
+    const int mt = 2 * pm + (int)rank;
+    img = mt / tiles_per_img;
+    const int tr = mt - img * tiles_per_img;
+    h0 = (tr / p.tiles_w) * p.TH;
+    w0 = (tr % p.tiles_w) * p.TW;
+  };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), 2);   // one arrive per producer of the pair (+ both CTAs' TMA bytes)
+      mbar_init(empty_bar(s), 1);  // leader's multicast commit
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);    // leader's multicast commit
+      mbar_init(tempty_bar(s), 16);  // 8 epilogue warps of each CTA
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.a_map[i]);
+    tma_prefetch_desc(&p.b_map);
+    tma_prefetch_desc(&p.out_map);
+    tma_prefetch_desc(&p.res_map);
+  }
+  if (warp == 1) tmem_alloc2<512>(tmem_slot);
+  {  // this CTA's half (rows 32*rank .. +31) of the 64x64 identity, K-major, SWIZZLE_128B
+    uint8_t* id = gsm + (ident - smem_base);
+    for (int i = threadIdx.x; i < Cfg::IDENT_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(id)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int r = threadIdx.x, k = 32 * (int)rank + r;
+      *reinterpret_cast<__half*>(id + r * 128 + (((k >> 3) ^ (r & 7)) << 4) + (k & 7) * 2) = __float2half(1.f);
+    }
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / TMA credit
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        int nt, w0, h0, img;
+        coords(tile, nt, w0, h0, img);
+        for (int t = 0; t < p.n_taps; ++t) {
+          const ConvTap tap = p.taps[t];
+          for (int cb = 0; cb < p.cin_blocks; ++cb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t dst = smem_base + stage * Cfg::STAGE_BYTES;
+            if (is_leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+            else mbar_arrive_cta0(full_bar(stage));
+            tma2_load_4d(dst, &p.a_map[tap.map], full_bar(stage), cb * CBK, w0 + tap.dw, h0 + tap.dh, img);
+            tma2_load_2d(dst + A_TILE_BYTES, &p.b_map, full_bar(stage), tap.koff + cb * CBK,
+                         nt * BN + (int)rank * (BN / 2));
+            if (++stage == Cfg::STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+        if (p.has_residual) {
+          for (int j = 0; j < NSUB; ++j) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            if (is_leader) mbar_arrive_expect_tx(full_bar(stage), 2 * A_TILE_BYTES);
+            else mbar_arrive_cta0(full_bar(stage));
+            tma2_load_4d(smem_base + stage * Cfg::STAGE_BYTES, &p.res_map, full_bar(stage), nt * BN + j * 64, w0, h0, img);
+            if (++stage == Cfg::STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (is_leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(256, BN);
+      constexpr uint32_t idesc64 = make_idesc_f16(256, 64);
+      const uint64_t d_ident = make_sw128_kmajor_desc(ident);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + as * BN;
+        for (int kb = 0; kb < conv_kblocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t base = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint64_t da = make_sw128_kmajor_desc(base);
+          const uint64_t db = make_sw128_kmajor_desc(base + A_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < CBK / 16; ++k)
+            umma2_f16(acc, desc_advance_k(da, k), desc_advance_k(db, k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma2_commit_mc(empty_bar(stage), 3);
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        if (p.has_residual) {
+          for (int j = 0; j < NSUB; ++j) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint64_t da = make_sw128_kmajor_desc(smem_base + stage * Cfg::STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < CBK / 16; ++k)
+              umma2_f16(acc + j * 64, desc_advance_k(da, k), desc_advance_k(d_ident, k), idesc64, 1u);
+            umma2_commit_mc(empty_bar(stage), 3);
+            if (++stage == Cfg::STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+        umma2_commit_mc(tfull_bar(as), 3);
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs, own 128 TMEM lanes) =====================
+    const int ew = warp - 2;
+    const int et = threadIdx.x - 64;
+    const int quarter = warp & 3;
+    const int chalf = ew >> 2;
+    const int pix = quarter * 32 + lane;
+    const bool leader_thread = (ew == 0 && lane == 0);
+    const uint32_t row_off = pix * 128;
+    const uint32_t sw = pix & 7;
+    uint8_t* oslabs = gsm + (out_stage - smem_base);
+    float* bias_s = reinterpret_cast<float*>(gsm + (bias_sm - smem_base));
+    int as = 0;
+    uint32_t aphase = 0;
+    uint32_t g = 0;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      int nt, w0, h0, img;
+      coords(tile, nt, w0, h0, img);
+      float* bias_t = bias_s + ((tile - t_begin) & 1) * BN;
+      if (et < BN) bias_t[et] = __ldg(p.bias + nt * BN + et);
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const uint32_t t0 = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16) + chalf * 32;
+#pragma unroll 1
+      for (int j = 0; j < NSUB; ++j, ++g) {
+        const uint32_t b = g & (Cfg::OUT_SLABS - 1);
+        const int ch0 = j * 64 + chalf * 32;
+        uint32_t r[32];
+        tmem_ld16(t0 + j * 64, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+        tmem_ld16(t0 + j * 64 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+        if (leader_thread) tma_store_wait_read<Cfg::OUT_SLABS - 1>();
+        named_bar_sync(1, 256);
+        tmem_ld_wait();
+        if (j == NSUB - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cta0(tempty_bar(as));
+        }
+        uint8_t* oslab = oslabs + b * A_TILE_BYTES + row_off;
+        const bool do_relu = p.relu && (nt * BN + ch0) >= p.relu_from;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 b0 = *reinterpret_cast<const float4*>(bias_t + ch0 + c * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(bias_t + ch0 + c * 8 + 4);
+          float v[8];
+          v[0] = __uint_as_float(r[c * 8 + 0]) + b0.x;
+          v[1] = __uint_as_float(r[c * 8 + 1]) + b0.y;
+          v[2] = __uint_as_float(r[c * 8 + 2]) + b0.z;
+          v[3] = __uint_as_float(r[c * 8 + 3]) + b0.w;
+          v[4] = __uint_as_float(r[c * 8 + 4]) + b1.x;
+          v[5] = __uint_as_float(r[c * 8 + 5]) + b1.y;
+          v[6] = __uint_as_float(r[c * 8 + 6]) + b1.z;
+          v[7] = __uint_as_float(r[c * 8 + 7]) + b1.w;
+          if (do_relu) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
+          }
+          uint4 o;
+          __half2* po = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) po[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+          *reinterpret_cast<uint4*>(oslab + (((uint32_t)(chalf * 4 + c) ^ sw) << 4)) = o;
+        }
+        fence_proxy_async();
+        named_bar_sync(1, 256);
+        if (leader_thread) {
+          tma_store_4d(&p.out_map, out_stage + b * A_TILE_BYTES, nt * BN + j * 64, w0, h0, img);
+          tma_store_commit();
+        }
+      }
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1u;
+      }
+    }
+    if (leader_thread) tma_store_wait<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's shared memory / barriers stay valid until both CTAs are done
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc2<512>(tmem_base);
   }
 }
 
@@ -828,6 +1106,19 @@ static int launch_conv(const ConvKernelParams& p, cudaStream_t st) {
   return 0;
 }
 
+static int launch_conv_pair(const ConvKernelParams& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CTL_CUDA(cudaFuncSetAttribute(conv_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PairCfg::SMEM));
+    attr_set = true;
+  }
+  const long long tiles = (long long)(p.m_tiles / 2) * p.n_tiles;
+  const int clusters = (int)std::min<long long>(tiles, sm_count() / 2);
+  conv_gemm_pair_kernel<<<2 * clusters, CONV_THREADS, PairCfg::SMEM, st>>>(p);
+  CTL_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace ctl
 
 using namespace ctl;
@@ -913,6 +1204,11 @@ int ctl_conv2d_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, int32_t 
                               CU_TENSOR_MAP_SWIZZLE_128B)))
     return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  // CTA pairs for the wide, K-heavy (compute-bound) layers; CTL_CONV_PAIR=0/1 overrides for A/B runs
+  static const int pair_mode = [] { const char* e = getenv("CTL_CONV_PAIR"); return e ? atoi(e) : -1; }();
+  const bool pair_ok = BN == 256 && (p.m_tiles % 2 == 0) && p.m_tiles >= 2;
+  const bool pair_want = pair_mode == 1 || (pair_mode == -1 && ksize * ksize * cin >= 512);
+  if (pair_ok && pair_want) return launch_conv_pair(p, st);
   if (BN == 256) return launch_conv<256>(p, st);
   if (BN == 128) return launch_conv<128>(p, st);
   return launch_conv<64>(p, st);

@@ -8,6 +8,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace ctl {
 
@@ -190,6 +191,69 @@ __device__ __forceinline__ uint64_t desc_advance_k(uint64_t desc, uint32_t k_ste
 // 1 = bf16), both K-major, N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t m, uint32_t n, bool bf16 = false) {
   return (1u << 4) | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+// ----------------------------------------------------------------------------------------
+// CTA-pair (cta_group::2) variants.  Inside a 2-CTA cluster, bit 24 of a shared::cluster address
+// selects the CTA of the pair; clearing it addresses the same offset in CTA 0 (the MMA leader).
+// ----------------------------------------------------------------------------------------
+static constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same offset in CTA 0 of the pair (remote for CTA 1)
+__device__ __forceinline__ void mbar_arrive_cta0(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+}
+// TMA loads of a CTA pair: data lands in the issuing CTA, the byte count is credited to CTA 0's barrier
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                             int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc2(uint32_t smem_dst) {  // one warp in EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B with M = 256 (128 rows per CTA), B rows split between the CTAs
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit of the leader: arrives on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma2_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
 }
 
 }  // namespace ctl
