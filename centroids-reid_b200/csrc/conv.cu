@@ -1197,18 +1197,19 @@ int ctl_conv2d_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, int32_t 
                                 ostr, obox, CU_TENSOR_MAP_SWIZZLE_128B)))
       return rc;
   }
-  const uint64_t bdims[2] = {(uint64_t)ksize * ksize * cin, (uint64_t)cout};
-  const uint64_t bstr[2] = {2, (uint64_t)ksize * ksize * cin * 2};
-  const uint32_t bbox[2] = {CBK, (uint32_t)BN};
-  if ((rc = encode_tensor_map(&p.b_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 2, weight, bdims, bstr, bbox,
-                              CU_TENSOR_MAP_SWIZZLE_128B)))
-    return rc;
   cudaStream_t st = (cudaStream_t)stream;
   // CTA pairs for the wide, K-heavy (compute-bound) layers; CTL_CONV_PAIR=0/1 overrides for A/B runs
   static const int pair_mode = [] { const char* e = getenv("CTL_CONV_PAIR"); return e ? atoi(e) : -1; }();
   const bool pair_ok = BN == 256 && (p.m_tiles % 2 == 0) && p.m_tiles >= 2;
   const bool pair_want = pair_mode == 1 || (pair_mode == -1 && ksize * ksize * cin >= 512);
-  if (pair_ok && pair_want) return launch_conv_pair(p, st);
+  const bool use_pair = pair_ok && pair_want;
+  const uint64_t bdims[2] = {(uint64_t)ksize * ksize * cin, (uint64_t)cout};
+  const uint64_t bstr[2] = {2, (uint64_t)ksize * ksize * cin * 2};
+  const uint32_t bbox[2] = {CBK, (uint32_t)(use_pair ? BN / 2 : BN)};  // a pair CTA stages half of the weight tile
+  if ((rc = encode_tensor_map(&p.b_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 2, weight, bdims, bstr, bbox,
+                              CU_TENSOR_MAP_SWIZZLE_128B)))
+    return rc;
+  if (use_pair) return launch_conv_pair(p, st);
   if (BN == 256) return launch_conv<256>(p, st);
   if (BN == 128) return launch_conv<128>(p, st);
   return launch_conv<64>(p, st);
