@@ -50,31 +50,48 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed regions (B200_PROFILING.md).  The sampler
+    process is started once (nvidia-smi needs ~0.5 s to come up) and polls every 20 ms; `window()`
+    marks the wall-clock intervals of the timed loops and only samples inside them are summarised."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.gpu, self.rows, self.proc, self.windows = gpu_index, [], None, []
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            time.sleep(0.7)
         except Exception:
             self.proc = None
         return self
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def window(self):
+        sampler = self
+
+        class _W:
+            def __enter__(self):
+                self.t0 = time.time()
+
+            def __exit__(self, *exc):
+                sampler.windows.append((self.t0, time.time()))
+                return False
+
+        return _W()
 
     def __exit__(self, *exc):
         if self.proc is not None:
+            time.sleep(0.05)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
@@ -84,7 +101,9 @@ class ClockSampler:
 
     def summary(self):
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for t, r in self.rows:
+            if self.windows and not any(a - 0.01 <= t <= b + 0.03 for a, b in self.windows):
+                continue
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -94,9 +113,9 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
-        busy = [s for s in sm if s > 0.5 * max(mx)] or sm
-        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no nvidia-smi sample inside the timed windows"],
+                    "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def dist_env():
@@ -165,8 +184,12 @@ def run_embed(args, world, rank, local):
             dist.all_gather(gathered, emb)
         return emb
 
-    with ClockSampler(local) as clk:
-        ms = timed_steps(step, args.steps, args.warmup, world)
+    clk = ClockSampler(local)
+    clk.__enter__()
+    for i in range(args.warmup):
+        step(i)
+    with clk.window():
+        ms = timed_steps(step, args.steps, 0, world)
     launches = graphs[0].launches * args.steps
     value = world * BATCH * args.steps / (ms / 1e3)
 
@@ -206,11 +229,13 @@ def run_embed(args, world, rank, local):
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    e2e_loop(args.steps, args.warmup)
-    torch.cuda.synchronize()
+    with clk.window():
+        e2e_loop(args.steps, args.warmup)
+        torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e2e_s = time.perf_counter() - t0
+    clk.__exit__(None, None, None)
     if world > 1:
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -433,7 +458,8 @@ def main():
                                                      "sample": f"128 of {RET_Q} queries x {RET_G} gallery through oracle.r1_map_compute, {rdt:.1f} s"}
         else:
             with ClockSampler(local) as clk:
-                r = run_retrieval(args, world, rank, local)
+                with clk.window():
+                    r = run_retrieval(args, world, rank, local)
             line = {"metric": r["metric"], "value": r["value"], "unit": r["unit"], "n_gpus": world, "steps": args.steps,
                     "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                     "vs_baseline": None, "dtype": "f16x3 (fp32-equivalent split)", "data": "synthetic",
