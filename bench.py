@@ -362,12 +362,15 @@ def run_retrieval(args, world, rank, local, steps=None, warmup=None):
 def _host_threads():
     """All the host threads torch can use productively: its own default is one per physical core;
     hyper-thread oversubscription (os.cpu_count()) was measured 19x SLOWER on the 128-thread box."""
-    return torch.get_num_threads()
+    n = max(1, (os.cpu_count() or 2) // 2)  # torchrun exports OMP_NUM_THREADS=1: set the count explicitly
+    torch.set_num_threads(n)
+    return n
 
 
 def cpu_embed(n_images, reps):
     from oracle import ctl_oracle as O  # the one place the bench executes the oracle
 
+    _host_threads()
     sd = O.make_trunk_state(seed=0)
     g = torch.Generator().manual_seed(10_000)
     bn = dict(weight=0.5 + torch.rand(2048, generator=g), bias=torch.zeros(2048),
@@ -385,6 +388,7 @@ def cpu_embed(n_images, reps):
 def cpu_retrieval(nq):
     from oracle import ctl_oracle as O
 
+    _host_threads()
     feats, pids, cams = O.synth_retrieval(RET_Q, RET_G, RET_IDS, RET_D, 3.0, 0)
     q, g = feats[:nq], feats[RET_Q:]
     t0 = time.perf_counter()

@@ -636,6 +636,201 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
 }
 
 // ---------------------------------------------------------------------------------------
+// 3x3 / stride 1 / 64 -> 64 channels (layer1.conv2, the most fill-bound layer of the trunk: the
+// generic kernel re-reads the activation tile once per filter tap, 216 KiB of shared-memory fill
+// for 9.4 MFLOP).  Here the 9 x [64 x 64] weight slabs (72 KiB) stay RESIDENT in shared memory and
+// each 16 x 8 output tile loads ONE halo slab -- 18 rows x 16 pixel lines x 128 B, i.e. the 18 x 10
+// halo padded to a 2 KiB row pitch -- by a single TMA box; the nine taps are nine SHIFTED VIEWS of
+// that slab: descriptor start = slab + (r*16 + s)*128 B, 8-row groups 2 KiB apart (one output row
+// each), base_offset = s so the 128-byte-swizzle phase matches what TMA wrote.  36 KiB of fill per
+// tile instead of 216 KiB.
+// ---------------------------------------------------------------------------------------
+static constexpr int C64_HALO_BYTES = 18 * 16 * 128;  // 36 KiB
+static constexpr int C64_W_BYTES = 9 * 64 * 128;      // 72 KiB
+static constexpr int C64_HALOS = 2;
+static constexpr int C64_OUT_SLABS = 4;
+static constexpr size_t C64_SMEM = C64_W_BYTES + C64_HALOS * C64_HALO_BYTES + C64_OUT_SLABS * A_TILE_BYTES + 512 + 1024 + 256;
+
+struct C64Params {
+  CUtensorMap x_map;    // NHWC input, box {64, 16, 18, 1}
+  CUtensorMap w_map;    // [64][576] weights, box {64, 64}
+  CUtensorMap out_map;  // NHWC output, box {64, 8, 16, 1}
+  const float* bias;
+  int n_img, H, W, tiles_h, tiles_w, relu, use_base_offset;
+};
+
+__global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_c64_kernel(const __grid_constant__ C64Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_sm = smem_base;
+  const uint32_t halo_sm = w_sm + C64_W_BYTES;
+  const uint32_t out_stage = halo_sm + C64_HALOS * C64_HALO_BYTES;
+  const uint32_t bias_sm = out_stage + C64_OUT_SLABS * A_TILE_BYTES;
+  const uint32_t bar_base = bias_sm + 512;
+  const uint32_t w_bar = bar_base;
+  auto full_bar = [&](int s) { return bar_base + 8u * (1 + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (1 + C64_HALOS + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (1 + 2 * C64_HALOS + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (3 + 2 * C64_HALOS + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (5 + 2 * C64_HALOS);
+  uint8_t* gsm = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_img = p.tiles_h * p.tiles_w;
+  const int num_tiles = p.n_img * tiles_per_img;
+  const int per = num_tiles / (int)gridDim.x, rem = num_tiles - per * (int)gridDim.x;
+  const int t_begin = (int)blockIdx.x * per + min((int)blockIdx.x, rem);
+  const int t_end = t_begin + per + ((int)blockIdx.x < rem ? 1 : 0);
+  auto coords = [&](int tile, int& w0, int& h0, int& img) {
+    img = tile / tiles_per_img;
+    const int tr = tile - img * tiles_per_img;
+    h0 = (tr / p.tiles_w) * 16;
+    w0 = (tr % p.tiles_w) * 8;
+  };
+  if (threadIdx.x == 0) {
+    mbar_init(w_bar, 1);
+    for (int s = 0; s < C64_HALOS; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 8);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&p.x_map);
+    tma_prefetch_desc(&p.w_map);
+    tma_prefetch_desc(&p.out_map);
+  }
+  if (warp == 1) tmem_alloc<128>(tmem_slot);
+  if (threadIdx.x >= 64 && threadIdx.x < 128) reinterpret_cast<float*>(gsm + (bias_sm - smem_base))[threadIdx.x - 64] = p.bias[threadIdx.x - 64];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_bar, C64_W_BYTES);
+      for (int t = 0; t < 9; ++t) tma_load_2d(w_sm + t * 64 * 128, &p.w_map, w_bar, t * 64, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        int w0, h0, img;
+        coords(tile, w0, h0, img);
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_arrive_expect_tx(full_bar(stage), C64_HALO_BYTES);
+        tma_load_4d(halo_sm + stage * C64_HALO_BYTES, &p.x_map, full_bar(stage), 0, w0 - 1, h0 - 1, img);
+        if (++stage == C64_HALOS) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(128, 64);
+      mbar_wait(w_bar, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t slab = halo_sm + stage * C64_HALO_BYTES;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int r = t / 3, s = t - 3 * r;
+          const uint32_t a0 = slab + (r * 16 + s) * 128;
+          const uint64_t da = make_sw128_kmajor_desc_ex(a0, 2048, p.use_base_offset ? ((a0 >> 7) & 7u) : 0u);
+          const uint64_t db = make_sw128_kmajor_desc(w_sm + t * 64 * 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_base + as * 64, desc_advance_k(da, k), desc_advance_k(db, k), idesc, (t | k) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(stage));
+        umma_commit(tfull_bar(as));
+        if (++stage == C64_HALOS) {
+          stage = 0;
+          phase ^= 1u;
+        }
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1u;
+        }
+      }
+    }
+  } else {
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int chalf = ew >> 2;
+    const int pix = quarter * 32 + lane;  // output pixel (row = pix / 8, col = pix % 8) == TMEM lane
+    const bool leader = (ew == 0 && lane == 0);
+    const uint32_t row_off = pix * 128, sw = pix & 7;
+    uint8_t* oslabs = gsm + (out_stage - smem_base);
+    const float* bias_s = reinterpret_cast<const float*>(gsm + (bias_sm - smem_base));
+    int as = 0;
+    uint32_t aphase = 0, g = 0;
+    for (int tile = t_begin; tile < t_end; ++tile, ++g) {
+      int w0, h0, img;
+      coords(tile, w0, h0, img);
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const uint32_t b = g & (C64_OUT_SLABS - 1);
+      uint32_t r[32];
+      const uint32_t t0 = tmem_base + as * 64 + (static_cast<uint32_t>(quarter * 32) << 16) + chalf * 32;
+      tmem_ld16(t0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+      tmem_ld16(t0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+      if (leader) tma_store_wait_read<C64_OUT_SLABS - 1>();
+      named_bar_sync(1, 256);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+      uint8_t* oslab = oslabs + b * A_TILE_BYTES + row_off;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 b0 = *reinterpret_cast<const float4*>(bias_s + chalf * 32 + c * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias_s + chalf * 32 + c * 8 + 4);
+        float v[8] = {__uint_as_float(r[c * 8 + 0]) + b0.x, __uint_as_float(r[c * 8 + 1]) + b0.y,
+                      __uint_as_float(r[c * 8 + 2]) + b0.z, __uint_as_float(r[c * 8 + 3]) + b0.w,
+                      __uint_as_float(r[c * 8 + 4]) + b1.x, __uint_as_float(r[c * 8 + 5]) + b1.y,
+                      __uint_as_float(r[c * 8 + 6]) + b1.z, __uint_as_float(r[c * 8 + 7]) + b1.w};
+        if (p.relu) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
+        }
+        uint4 o;
+        __half2* po = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) po[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+        *reinterpret_cast<uint4*>(oslab + (((uint32_t)(chalf * 4 + c) ^ sw) << 4)) = o;
+      }
+      fence_proxy_async();
+      named_bar_sync(1, 256);
+      if (leader) {
+        tma_store_4d(&p.out_map, out_stage + b * A_TILE_BYTES, 0, w0, h0, img);
+        tma_store_commit();
+      }
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1u;
+      }
+    }
+    if (leader) tma_store_wait<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<128>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // stem: conv 7x7 / 2, pad 3, 3 -> 64 (+ folded BN, optional ReLU) from NCHW fp32 to NHWC fp16
 // (modelling/backbones/resnet.py:93-97,122-125 -- NO ReLU; resnet_ibn_a.py:84-86,126-129 -- ReLU)
 // Direct convolution on the CUDA cores: K = 147 with Cin = 3 does not map on TMA channel slabs.
@@ -1106,6 +1301,39 @@ static int launch_conv(const ConvKernelParams& p, cudaStream_t st) {
   return 0;
 }
 
+static int launch_c64(const void* x, int n, int h, int w, const void* weight, const float* bias, void* out, int relu,
+                      cudaStream_t st) {
+  C64Params p = {};
+  p.bias = bias;
+  p.n_img = n;
+  p.H = h;
+  p.W = w;
+  p.tiles_h = (h + 15) / 16;
+  p.tiles_w = (w + 7) / 8;
+  p.relu = relu;
+  static const int baseoff = [] { const char* e = getenv("CTL_C64_BASEOFF"); return e ? atoi(e) : 1; }();
+  p.use_base_offset = baseoff;
+  int rc;
+  const uint64_t dims[4] = {64, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+  const uint64_t strd[4] = {2, 128, (uint64_t)w * 128, (uint64_t)h * w * 128};
+  const uint32_t xbox[4] = {64, 16, 18, 1}, obox[4] = {64, 8, 16, 1};
+  if ((rc = encode_tensor_map(&p.x_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, x, dims, strd, xbox, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = encode_tensor_map(&p.out_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, out, dims, strd, obox, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  const uint64_t wd[2] = {576, 64}, ws[2] = {2, 576 * 2};
+  const uint32_t wbox[2] = {64, 64};
+  if ((rc = encode_tensor_map(&p.w_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 2, weight, wd, ws, wbox, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CTL_CUDA(cudaFuncSetAttribute(conv3x3_c64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C64_SMEM));
+    attr_set = true;
+  }
+  const long long tiles = (long long)n * p.tiles_h * p.tiles_w;
+  const int grid = (int)std::min<long long>(tiles, sm_count());
+  conv3x3_c64_kernel<<<grid, CONV_THREADS, C64_SMEM, st>>>(p);
+  CTL_LAUNCH_CHECK();
+  return 0;
+}
+
 static int launch_conv_pair(const ConvKernelParams& p, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -1138,6 +1366,11 @@ int ctl_conv2d_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, int32_t 
   if (rc) return rc;
   const int pad = ksize == 3 ? 1 : 0;
   const int Ho = (h + 2 * pad - ksize) / stride + 1, Wo = (w + 2 * pad - ksize) / stride + 1;
+  {
+    static const int c64_mode = [] { const char* e = getenv("CTL_CONV_C64"); return e ? atoi(e) : 1; }();
+    if (c64_mode && ksize == 3 && stride == 1 && cin == 64 && cout == 64 && !residual && relu_from == 0)
+      return launch_c64(x, n, h, w, weight, bias, out, relu, (cudaStream_t)stream);
+  }
   ConvKernelParams p = {};
   pick_tile(Ho, Wo, &p.TH, &p.TW);
   p.tiles_h = (Ho + p.TH - 1) / p.TH;

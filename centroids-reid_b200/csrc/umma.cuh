@@ -183,6 +183,20 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// General form: 8-row groups `sbo_bytes` apart, and a start address that need not sit on a 1024-byte
+// swizzle-pattern boundary: base_offset (bits [49,52)) = (start >> 7) & 7 tells the hardware the phase
+// of the 128-byte-swizzle pattern at the first row (PTX ISA, matrix-descriptor "base offset").
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc_ex(uint32_t smem_addr, uint32_t sbo_bytes,
+                                                              uint32_t base_offset) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(base_offset & 7u) << 49;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // Advancing by one UMMA_K (16 fp16 = 32 bytes) inside the 128-byte swizzle row.
 __device__ __forceinline__ uint64_t desc_advance_k(uint64_t desc, uint32_t k_step) {
   return desc + static_cast<uint64_t>((k_step * 32u) >> 4);
