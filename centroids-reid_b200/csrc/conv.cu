@@ -642,8 +642,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
 // each 16 x 8 output tile loads ONE halo slab -- 18 rows x 16 pixel lines x 128 B, i.e. the 18 x 10
 // halo padded to a 2 KiB row pitch -- by a single TMA box; the nine taps are nine SHIFTED VIEWS of
 // that slab: descriptor start = slab + (r*16 + s)*128 B, 8-row groups 2 KiB apart (one output row
-// each), base_offset = s so the 128-byte-swizzle phase matches what TMA wrote.  36 KiB of fill per
-// tile instead of 216 KiB.
+// each).  MEASURED on B200: the tensor core derives the 128-byte-swizzle XOR from the absolute
+// shared-memory address bits [7,10) -- exactly what the TMA unit used when it wrote the slab -- so
+// a start address shifted by whole 128-byte lines needs NO descriptor base_offset (base_offset = s
+// gives wrong results; tests/test_trunk_gpu.py::test_conv_shapes[case3] pins this).  36 KiB of fill
+// per tile instead of 216 KiB.
 // ---------------------------------------------------------------------------------------
 static constexpr int C64_HALO_BYTES = 18 * 16 * 128;  // 36 KiB
 static constexpr int C64_W_BYTES = 9 * 64 * 128;      // 72 KiB
@@ -1311,8 +1314,7 @@ static int launch_c64(const void* x, int n, int h, int w, const void* weight, co
   p.tiles_h = (h + 15) / 16;
   p.tiles_w = (w + 7) / 8;
   p.relu = relu;
-  static const int baseoff = [] { const char* e = getenv("CTL_C64_BASEOFF"); return e ? atoi(e) : 1; }();
-  p.use_base_offset = baseoff;
+  p.use_base_offset = 0;  // see the kernel comment: shifted views need no base_offset
   int rc;
   const uint64_t dims[4] = {64, (uint64_t)w, (uint64_t)h, (uint64_t)n};
   const uint64_t strd[4] = {2, 128, (uint64_t)w * 128, (uint64_t)h * w * 128};
