@@ -161,7 +161,7 @@ def _aggregate(ranks: np.ndarray, ap: np.ndarray, n_pos: np.ndarray, q_pids, num
     topk = np.stack([(first <= k).astype(np.int64) for k in K_LIST], 1)
     q_idx = np.nonzero(valid)[0]
     aps = ap[valid]
-    single = np.array([[int(i), q_pids[i], a] for i, a in zip(q_idx, aps)])
+    single = np.column_stack((q_idx.astype(np.float64), np.asarray(q_pids)[q_idx].astype(np.float64), aps))
     return EvalResult(cmc.astype(np.float32), float(np.mean(aps)), np.mean(topk, 0), single, ranks)
 
 
