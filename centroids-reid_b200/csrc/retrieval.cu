@@ -31,9 +31,10 @@ static constexpr int BK = 64;       // fp16 elements per k-block = one 128-byte 
 static constexpr int STAGES = 3;
 static constexpr int TILE_BYTES = BM * BK * 2;          // 16 KiB
 static constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // q_hi, q_lo, g_hi, g_lo
-static constexpr int GEMM_THREADS = 192;
+static constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 static constexpr int GROUP_W = 16;                      // columns per group-min
-static constexpr size_t GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+static constexpr int META_BYTES = 2 * BN * (4 + 4 + 4 + 8);  // double-buffered per-tile column metadata
+static constexpr size_t GEMM_SMEM = STAGES * STAGE_BYTES + META_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 // ---------------------------------------------------------------------------------------
 // (distance, index) keys: ascending uint64 order == ascending (distance, index)
@@ -217,7 +218,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     dist_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmPass p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t meta_base = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t bar_base = meta_base + META_BYTES;
   // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);
+      mbar_init(tempty_bar(s), 8);
     }
     fence_barrier_init();
   }
@@ -319,16 +321,38 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       }
     }
   } else {
-    // ===================== epilogue: 4 warps, warp%4 selects the 32-lane TMEM quarter ========
+    // ===================== epilogue: 8 warps, two per 32-lane TMEM quarter (64 columns each) =====
+    // Per-tile column metadata (|g|^2, 1/scale, pid, camera mask of the 128 gallery rows) is staged
+    // once in shared memory; every thread then reads it by broadcast instead of 4 global loads per
+    // element.
+    const int ew = warp - 2;
+    const int et = threadIdx.x - 64;  // 0..255
     const int quarter = warp & 3;
+    const int chalf = ew >> 2;        // columns [64*chalf, 64*chalf + 64) of the tile
     const int row_in_tile = quarter * 32 + lane;
+    float* cm_sq = reinterpret_cast<float*>(smem_raw + (meta_base - smem_u32(smem_raw)));  // [2][128]
+    float* cm_is = cm_sq + 2 * BN;
+    int* cm_pid = reinterpret_cast<int*>(cm_is + 2 * BN);
+    unsigned long long* cm_mask = reinterpret_cast<unsigned long long*>(cm_pid + 2 * BN);
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       int mt, nt;
       tile_coords(tile, p.m_tiles, p.n_tiles, mt, nt);
       const int row = mt * BM + row_in_tile;
       const bool row_ok = row < p.nq;
+      const int mb = (it & 1) * BN;  // double-buffered metadata slice
+      if (et < BN) {
+        const int col = nt * BN + et;
+        const bool ok = col < p.ng;
+        cm_sq[mb + et] = ok ? p.g_sq[col] : 0.f;
+        cm_is[mb + et] = ok ? p.g_is[col] : 0.f;
+        if (p.q_pid) {
+          cm_pid[mb + et] = ok ? p.g_pid[col] : -2;
+          cm_mask[mb + et] = ok ? p.g_mask[col] : 0ull;
+        }
+      }
       float qq = 0.f, qis = 0.f, tau = -CUDART_INF_F;
       int qpid = -1, qcam = 0, npos = 0;
       unsigned long long maxkey = 0ull;
@@ -347,20 +371,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       }
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-      const uint32_t t0 = tmem_base + as * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
-      for (int c = 0; c < BN / 16; ++c) {
+      named_bar_sync(1, 256);  // metadata slice published
+      const uint32_t t0 = tmem_base + as * 256 + (static_cast<uint32_t>(quarter * 32) << 16) + chalf * 64;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
         uint32_t r0[16], r1[16];
         tmem_ld16(t0 + c * 16, r0);
         tmem_ld16(t0 + 128 + c * 16, r1);
         tmem_ld_wait();
-        const int col0 = nt * BN + c * 16;
+        const int cl0 = chalf * 64 + c * 16;  // column inside the tile
+        const int col0 = nt * BN + cl0;
         float gmin = CUDART_INF_F;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int col = col0 + j;
           if (col < p.ng && row_ok) {  // col bound is warp-uniform
-            const float dist = dist_from_acc(__uint_as_float(r0[j]), __uint_as_float(r1[j]), qis, __ldg(p.g_is + col),
-                                             qq, __ldg(p.g_sq + col), p.cosine);
+            const float dist = dist_from_acc(__uint_as_float(r0[j]), __uint_as_float(r1[j]), qis, cm_is[mb + cl0 + j],
+                                             qq, cm_sq[mb + cl0 + j], p.cosine);
             const unsigned int gidx = static_cast<unsigned int>(col + p.g_off);
             if (p.dist_out) p.dist_out[(size_t)row * p.ld_out + col] = dist;
             gmin = fminf(gmin, dist);
@@ -372,8 +399,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 *p.overflow = 1;
             }
             if (p.q_pid) {
-              const bool same = __ldg(p.g_pid + col) == qpid;
-              const bool junk = same && ((__ldg(p.g_mask + col) >> qcam) & 1ull);
+              const bool same = cm_pid[mb + cl0 + j] == qpid;
+              const bool junk = same && ((cm_mask[mb + cl0 + j] >> qcam) & 1ull);
               if (p.pos_keys && same && !junk) {
                 const int slot = atomicAdd(p.pos_count + row, 1);
                 if (slot < p.max_pos)
