@@ -5,7 +5,7 @@
 set -u
 mkdir -p gpurun_out
 NCU="ncu --clock-control none"
-KERN='conv_gemm|stem|maxpool|gap_bn|instnorm'
+KERN='conv|stem|maxpool|gap_bn|instnorm'
 CTL_GRAPH=0 $NCU --metrics gpu__time_duration.sum -k regex:"$KERN" -s 165 -c 55 --csv \
     --log-file gpurun_out/launches_trunk.csv python tools/bench_trunk.py 256 > gpurun_out/ncu_trunk_run.log 2>&1
 echo "launch list exit $?"
@@ -13,7 +13,7 @@ METRICS='dram__bytes_read.sum|dram__bytes_write.sum|gpu__time_duration.sum|sm__p
 i=0
 for skip in 157 159 199; do
   i=$((i+1))
-  CTL_GRAPH=0 $NCU --set full --import-source on -k regex:conv_gemm -s $skip -c 1 -f -o gpurun_out/prof_conv_$i python tools/bench_trunk.py 256 > /dev/null 2>&1
+  CTL_GRAPH=0 $NCU --set full --import-source on -k regex:conv -s $skip -c 1 -f -o gpurun_out/prof_conv_$i python tools/bench_trunk.py 256 > /dev/null 2>&1
   ncu -i gpurun_out/prof_conv_$i.ncu-rep --page raw --csv 2>/dev/null | python tools/ncu_pick.py "$METRICS" > gpurun_out/prof_conv_$i.txt
   ncu -i gpurun_out/prof_conv_$i.ncu-rep --page details 2>/dev/null | grep -E "Duration|Throughput|Registers|Grid Size|Tensor|Achieved Occupancy|L2 Hit|DRAM" | head -40 >> gpurun_out/prof_conv_$i.txt
   rm -f gpurun_out/prof_conv_$i.ncu-rep
