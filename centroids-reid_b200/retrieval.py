@@ -139,6 +139,30 @@ def encode_identities(q_pids, g_pids, q_camids, g_camids, respect_camids: bool):
 
 
 @dataclass
+class EncodedIds:
+    """Device-resident identity arrays of one (query set, gallery set): encode once per validation set
+    (identities do not change between epochs) and pass as `ids=` to skip the host re-labelling."""
+
+    q_pid: torch.Tensor
+    q_cam: torch.Tensor
+    g_pid: torch.Tensor
+    g_mask: torch.Tensor
+    max_pos: int
+
+
+def encode_ids(q_pids, g_pids, q_camids, g_camids, respect_camids: bool, device, global_labels: bool = False) -> EncodedIds:
+    if global_labels:
+        arrs = _encode_identities_global(q_pids, g_pids, q_camids, g_camids)
+    else:
+        arrs = encode_identities(q_pids, g_pids, q_camids, g_camids, respect_camids)
+
+    def to_dev(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=True)
+
+    return EncodedIds(to_dev(arrs[0]), to_dev(arrs[1]), to_dev(arrs[2]), to_dev(arrs[3].view(np.int64)), arrs[4])
+
+
+@dataclass
 class EvalResult:
     cmc: np.ndarray          # float32 [max_rank]
     mAP: float
@@ -177,6 +201,7 @@ def evaluate_streamed(
     g_index_offset: int = 0,
     group=None,
     total_gallery: Optional[int] = None,
+    ids: "Optional[EncodedIds]" = None,
 ) -> EvalResult:
     """eval_func semantics (utils/eval_reid.py:25-92) straight from the features: two tensor-
     core passes (collect the positives' distances; count kept rows before each positive),
@@ -188,18 +213,12 @@ def evaluate_streamed(
     dev = qp.buf.device
     nq, ng = qp.n, gp.n
     world = dist.get_world_size(group) if group is not None else 1
-    q_pid, q_cam, g_pid, g_mask, max_pos_local = encode_identities(q_pids, g_pids, q_camids, g_camids, respect_camids)
-    if world > 1:
-        # dense re-labelling must agree across ranks: callers pass globally consistent int
-        # pids / cams, so re-label with the identity map instead of np.unique
-        if not np.issubdtype(np.asarray(q_pids).dtype, np.integer):
+    if ids is None:
+        if world > 1 and not np.issubdtype(np.asarray(q_pids).dtype, np.integer):
             raise ValueError("sharded evaluation needs integer pids")
-        q_pid, q_cam, g_pid, g_mask, max_pos_local = _encode_identities_global(q_pids, g_pids, q_camids, g_camids)
-    def to_dev(a):
-        return torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
-
-    d_qpid, d_qcam, d_gpid = to_dev(q_pid), to_dev(q_cam), to_dev(g_pid)
-    d_gmask = to_dev(g_mask.view(np.int64))
+        # sharded: dense re-labelling must agree across ranks -> identity map instead of np.unique
+        ids = encode_ids(q_pids, g_pids, q_camids, g_camids, respect_camids, dev, global_labels=world > 1)
+    d_qpid, d_qcam, d_gpid, d_gmask, max_pos_local = ids.q_pid, ids.q_cam, ids.g_pid, ids.g_mask, ids.max_pos
     max_pos = max_pos_local
     if world > 1:
         mp = torch.tensor([max_pos_local], device=dev, dtype=torch.int64)
@@ -303,7 +322,7 @@ def topk_sharded(q_local: torch.Tensor, g_local: torch.Tensor, k: int, g_index_o
 
 
 def topk_and_eval(qp: Planes, gp: Planes, k: int, q_pids, g_pids, q_camids, g_camids, max_rank: int = 50,
-                  respect_camids: bool = False):
+                  respect_camids: bool = False, ids: "Optional[EncodedIds]" = None):
     """BASELINE config 3 in TWO tensor-core passes: per-query top-k (ascending (distance, index))
     AND eval_func's CMC / mAP, neither materialising the distance matrix.
       pass 1: 16-column group minima (-> tau) + the positives' distances
@@ -317,12 +336,9 @@ def topk_and_eval(qp: Planes, gp: Planes, k: int, q_pids, g_pids, q_camids, g_ca
     k = int(min(k, ng))
     emit_all, n_groups, merge, cap = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
     N.check(L.ctl_topk_plan(ng, k, C.byref(emit_all), C.byref(n_groups), C.byref(merge), C.byref(cap)))
-    q_pid, q_cam, g_pid, g_mask, max_pos = encode_identities(q_pids, g_pids, q_camids, g_camids, respect_camids)
-
-    def to_dev(a):
-        return torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
-
-    d_qpid, d_qcam, d_gpid, d_gmask = to_dev(q_pid), to_dev(q_cam), to_dev(g_pid), to_dev(g_mask.view(np.int64))
+    if ids is None:
+        ids = encode_ids(q_pids, g_pids, q_camids, g_camids, respect_camids, dev)
+    d_qpid, d_qcam, d_gpid, d_gmask, max_pos = ids.q_pid, ids.q_cam, ids.g_pid, ids.g_mask, ids.max_pos
     gmin = torch.empty(nq, n_groups.value, dtype=torch.float32, device=dev)
     tau = torch.empty(nq, dtype=torch.float32, device=dev)
     cand = torch.empty(nq, cap.value, dtype=torch.int64, device=dev)
@@ -335,10 +351,10 @@ def topk_and_eval(qp: Planes, gp: Planes, k: int, q_pids, g_pids, q_camids, g_ca
     ranks = torch.empty(nq, max_pos, dtype=torch.int32, device=dev)
     ap = torch.empty(nq, dtype=torch.float64, device=dev)
     s = N.stream_ptr
-    ids = dict(q_pid=d_qpid.data_ptr(), q_cam=d_qcam.data_ptr(), g_pid=d_gpid.data_ptr(),
+    idp = dict(q_pid=d_qpid.data_ptr(), q_cam=d_qcam.data_ptr(), g_pid=d_gpid.data_ptr(),
                g_cammask=d_gmask.data_ptr(), max_pos=max_pos, overflow=ovf.data_ptr())
     with torch.cuda.device(dev):
-        p1 = N.PassDesc(pos_keys=pos_keys.data_ptr(), pos_count=pos_count.data_ptr(), **ids)
+        p1 = N.PassDesc(pos_keys=pos_keys.data_ptr(), pos_count=pos_count.data_ptr(), **idp)
         if not emit_all.value:
             p1.gmin = gmin.data_ptr()
         N.check(L.ctl_dist_pass(qp.ptr, nq, gp.ptr, ng, qp.d, qp.flags, C.byref(p1), s()))
@@ -349,7 +365,7 @@ def topk_and_eval(qp: Planes, gp: Planes, k: int, q_pids, g_pids, q_camids, g_ca
         N.check(L.ctl_sort_key_rows(pos_keys.data_ptr(), pos_count.data_ptr(), nq, max_pos, s()))
         p2 = N.PassDesc(tau=tau.data_ptr(), cand_keys=cand.data_ptr(), cand_count=cand_count.data_ptr(),
                         cand_cap=cap.value, thr_keys=pos_keys.data_ptr(), thr_count=pos_count.data_ptr(),
-                        buckets=buckets.data_ptr(), **ids)
+                        buckets=buckets.data_ptr(), **idp)
         N.check(L.ctl_dist_pass(qp.ptr, nq, gp.ptr, ng, qp.d, qp.flags, C.byref(p2), s()))
         N.check(L.ctl_sort_key_rows(cand.data_ptr(), cand_count.data_ptr(), nq, cap.value, s()))
         N.check(L.ctl_topk_emit(cand.data_ptr(), cand_count.data_ptr(), nq, cap.value, k, idx.data_ptr(),
