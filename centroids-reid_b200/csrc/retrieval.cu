@@ -369,6 +369,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           if (npos > 0) maxkey = p.thr_keys[(size_t)row * p.max_pos + npos - 1];
         }
       }
+      // distance parts of this row's first 32 sorted positives, in registers: the bucket of a gallery row
+      // is then a branch-free count instead of a dependent chain of global loads
+      uint32_t thr_d[32];
+      if (p.buckets) {
+        const unsigned long long* thr = p.thr_keys + (size_t)(row_ok ? row : 0) * p.max_pos;
+#pragma unroll
+        for (int t = 0; t < 32; ++t) thr_d[t] = (row_ok && t < npos) ? (uint32_t)(thr[t] >> 32) : 0xFFFFFFFFu;
+      }
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       named_bar_sync(1, 256);  // metadata slice published
@@ -411,12 +419,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               if (p.buckets && !junk && npos > 0) {
                 const unsigned long long key = make_key(dist, gidx);
                 if (key < maxkey) {
-                  // first positive that sorts strictly after this row
-                  const unsigned long long* thr = p.thr_keys + (size_t)row * p.max_pos;
-                  int lo_i = 0, hi_i = npos - 1;  // thr[hi_i] = maxkey > key
-                  while (lo_i < hi_i) {
-                    const int mid = (lo_i + hi_i) >> 1;
-                    if (thr[mid] > key) hi_i = mid; else lo_i = mid + 1;
+                  // index of the first positive that sorts strictly after this gallery row
+                  const uint32_t kd = (uint32_t)(key >> 32);
+                  int lt = 0, eq = 0;
+#pragma unroll
+                  for (int t = 0; t < 32; ++t) {
+                    lt += thr_d[t] < kd ? 1 : 0;
+                    eq += thr_d[t] == kd ? 1 : 0;
+                  }
+                  int lo_i = lt;
+                  if (eq != 0 || (lt == 32 && npos > 32)) {
+                    // exact distance tie with a positive, or beyond the 32 register-resident ones: 64-bit search
+                    const unsigned long long* thr = p.thr_keys + (size_t)row * p.max_pos;
+                    int hi_i = npos - 1;  // thr[hi_i] = maxkey > key
+                    lo_i = 0;
+                    while (lo_i < hi_i) {
+                      const int mid = (lo_i + hi_i) >> 1;
+                      if (thr[mid] > key) hi_i = mid; else lo_i = mid + 1;
+                    }
                   }
                   atomicAdd(p.buckets + (size_t)row * (p.max_pos + 1) + lo_i, 1);
                 }

@@ -183,3 +183,20 @@ def test_fused_two_pass_topk_and_eval(R):
         assert torch.equal(idx, idx2) and torch.equal(dst, dst2)
         assert np.array_equal(res.cmc, res2.cmc) and res.mAP == res2.mAP
         assert np.array_equal(res.ranks, res2.ranks)
+
+
+def test_eval_many_positives_per_query(R):
+    """> 32 positives per query: beyond the register-resident thresholds of the count pass (global
+    64-bit search fallback), plus exact distance ties between positives (duplicated gallery rows)."""
+    nq, ng, nid = 64, 3000, 20
+    feats, pids, cams = O.synth_retrieval(nq, ng, nid, 256, 2.5, 17, num_cams=5)
+    feats[nq + 100:nq + 140] = feats[nq + 200:nq + 240]      # 40 duplicated gallery rows -> exact ties
+    pids[nq + 100:nq + 140] = pids[nq + 200:nq + 240]
+    q, gal = feats[:nq].cuda(), feats[nq:].cuda()
+    d = R.dist_matrix(q, gal).cpu().numpy()
+    _, (cmc_o, map_o, _, single_o) = _eval_from_matrix(d, pids, cams, nq)
+    res = R.evaluate_streamed(R.build_planes(q), R.build_planes(gal), pids[:nq], pids[nq:], cams[:nq], cams[nq:])
+    assert res.ranks.shape[1] > 32
+    assert np.array_equal(res.cmc, cmc_o)
+    np.testing.assert_allclose(res.mAP, map_o, rtol=1e-12)
+    np.testing.assert_allclose(res.single_performance[:, 2].astype(np.float64), single_o[:, 2].astype(np.float64), rtol=1e-12)
