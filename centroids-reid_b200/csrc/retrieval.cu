@@ -34,7 +34,9 @@ static constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // q_hi, q_lo, g_hi, g_l
 static constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 static constexpr int GROUP_W = 16;                      // columns per group-min
 static constexpr int META_BYTES = 2 * BN * (4 + 4 + 4 + 8);  // double-buffered per-tile column metadata
-static constexpr size_t GEMM_SMEM = STAGES * STAGE_BYTES + META_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+static constexpr int THR_MAX = 44, THR_STRIDE = 45;         // positives per query held in shared memory
+static constexpr int THR_BYTES = BM * THR_STRIDE * 4;
+static constexpr size_t GEMM_SMEM = STAGES * STAGE_BYTES + META_BYTES + THR_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 // ---------------------------------------------------------------------------------------
 // (distance, index) keys: ascending uint64 order == ascending (distance, index)
@@ -203,6 +205,17 @@ __device__ __forceinline__ float dist_from_acc(float acc0, float acc1, float q_i
   return (cosine & 4) ? __fsqrt_rn(fmaxf(sqd, 1e-12f)) : sqd;
 }
 
+// exact (distance, index) search in the sorted positives of one query: first entry > key (entry npos-1 is > key)
+__device__ __noinline__ int bucket_search_global(const unsigned long long* __restrict__ thr, int npos,
+                                                 unsigned long long key) {
+  int lo = 0, hi = npos - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (thr[mid] > key) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
 __device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, int& mt, int& nt) {
   // bands of 16 gallery tiles, query tiles fastest inside a band-row: the CTAs that run
   // concurrently touch a compact (m x n) block, so each operand tile is fetched from HBM ~once
@@ -219,7 +232,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t meta_base = smem_base + STAGES * STAGE_BYTES;
-  const uint32_t bar_base = meta_base + META_BYTES;
+  const uint32_t thr_base = meta_base + META_BYTES;
+  const uint32_t bar_base = thr_base + THR_BYTES;
   // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -334,6 +348,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     float* cm_is = cm_sq + 2 * BN;
     int* cm_pid = reinterpret_cast<int*>(cm_is + 2 * BN);
     unsigned long long* cm_mask = reinterpret_cast<unsigned long long*>(cm_pid + 2 * BN);
+    uint32_t* thr_s = reinterpret_cast<uint32_t*>(smem_raw + (thr_base - smem_u32(smem_raw)));
     int as = 0;
     uint32_t aphase = 0;
     int it = 0;
@@ -369,13 +384,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           if (npos > 0) maxkey = p.thr_keys[(size_t)row * p.max_pos + npos - 1];
         }
       }
-      // distance parts of this row's first 32 sorted positives, in registers: the bucket of a gallery row
-      // is then a branch-free count instead of a dependent chain of global loads
-      uint32_t thr_d[32];
-      if (p.buckets) {
-        const unsigned long long* thr = p.thr_keys + (size_t)(row_ok ? row : 0) * p.max_pos;
-#pragma unroll
-        for (int t = 0; t < 32; ++t) thr_d[t] = (row_ok && t < npos) ? (uint32_t)(thr[t] >> 32) : 0xFFFFFFFFu;
+      // distance parts of this row's sorted positives staged in shared memory (row stride 45 words: conflict-
+      // free for 32 consecutive rows), so the bucket of a gallery row is a short LDS binary search instead of a
+      // dependent chain of L2 loads.  Both warps of a row quarter fill disjoint entries.
+      const bool thr_in_smem = p.buckets && p.max_pos <= THR_MAX;
+      uint32_t* thr_row = thr_s + row_in_tile * THR_STRIDE;
+      if (thr_in_smem && row_ok) {
+        const unsigned long long* thr = p.thr_keys + (size_t)row * p.max_pos;
+        for (int t = chalf; t < npos; t += 2) thr_row[t] = (uint32_t)(thr[t] >> 32);
       }
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
@@ -420,24 +436,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 const unsigned long long key = make_key(dist, gidx);
                 if (key < maxkey) {
                   // index of the first positive that sorts strictly after this gallery row
-                  const uint32_t kd = (uint32_t)(key >> 32);
-                  int lt = 0, eq = 0;
-#pragma unroll
-                  for (int t = 0; t < 32; ++t) {
-                    lt += thr_d[t] < kd ? 1 : 0;
-                    eq += thr_d[t] == kd ? 1 : 0;
-                  }
-                  int lo_i = lt;
-                  if (eq != 0 || (lt == 32 && npos > 32)) {
-                    // exact distance tie with a positive, or beyond the 32 register-resident ones: 64-bit search
-                    const unsigned long long* thr = p.thr_keys + (size_t)row * p.max_pos;
-                    int hi_i = npos - 1;  // thr[hi_i] = maxkey > key
-                    lo_i = 0;
-                    while (lo_i < hi_i) {
-                      const int mid = (lo_i + hi_i) >> 1;
-                      if (thr[mid] > key) hi_i = mid; else lo_i = mid + 1;
+                  int lo_i;
+                  bool exact = true;
+                  if (thr_in_smem) {
+                    const uint32_t kd = (uint32_t)(key >> 32);
+                    int lo = 0, hi = npos - 1;  // thr_row[hi] >= kd because key < maxkey
+                    while (lo < hi) {
+                      const int mid = (lo + hi) >> 1;
+                      if (thr_row[mid] > kd) hi = mid; else lo = mid + 1;
                     }
+                    lo_i = lo;
+                    // `lo` = first entry with a LARGER distance; a positive with the SAME distance (lo > 0 and
+                    // thr_row[lo-1] == kd, or the last entry) needs the 64-bit (distance, index) comparison
+                    exact = (lo > 0 && thr_row[lo - 1] == kd) || thr_row[lo] == kd;
                   }
+                  if (exact) lo_i = bucket_search_global(p.thr_keys + (size_t)row * p.max_pos, npos, key);
                   atomicAdd(p.buckets + (size_t)row * (p.max_pos + 1) + lo_i, 1);
                 }
               }
@@ -449,6 +462,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (thr_in_smem) named_bar_sync(2, 256);  // nobody still reads this tile's thresholds
       if (++as == 2) {
         as = 0;
         aphase ^= 1u;
