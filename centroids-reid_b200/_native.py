@@ -69,6 +69,7 @@ SIGNATURES = {
     "ctl_eval_count": (C.c_int, [_p, _i64, _p, _i64, _i32, _i32, _p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p]),
     "ctl_eval_finalize": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p]),
     "ctl_dist_pass": (C.c_int, [_p, _i64, _p, _i64, _i32, _i32, C.POINTER(PassDesc), _p]),
+    "ctl_debug_set_dist_profile": (None, [_p]),
     "ctl_topk_plan": (C.c_int, [_i64, _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     "ctl_select_tau": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p]),
     "ctl_fill_f32": (C.c_int, [_p, _i64, C.c_float, _p]),

@@ -187,6 +187,7 @@ struct GemmPass {
   const int* thr_count;
   int* buckets;
   int* overflow;
+  long long* prof;  // debug: [grid][8] epilogue cycle counters (tools/prof_retrieval.py)
 };
 
 struct GemmMaps {
@@ -352,6 +353,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     int as = 0;
     uint32_t aphase = 0;
     int it = 0;
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = clock64();
+#define CTL_STAMP(i)                \
+  if (p.prof) {                     \
+    const long long _t = clock64(); \
+    pc[i] += _t - tprev;            \
+    tprev = _t;                     \
+  }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       int mt, nt;
       tile_coords(tile, p.m_tiles, p.n_tiles, mt, nt);
@@ -389,13 +398,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       // dependent chain of L2 loads.  Both warps of a row quarter fill disjoint entries.
       const bool thr_in_smem = p.buckets && p.max_pos <= THR_MAX;
       uint32_t* thr_row = thr_s + row_in_tile * THR_STRIDE;
-      if (thr_in_smem && row_ok) {
-        const unsigned long long* thr = p.thr_keys + (size_t)row * p.max_pos;
-        for (int t = chalf; t < npos; t += 2) thr_row[t] = (uint32_t)(thr[t] >> 32);
+      if (thr_in_smem) {
+        // the 128 rows of this tile own one contiguous [128][max_pos] block of sorted keys: coalesced copy of the
+        // distance halves (entries beyond a row's count are never read)
+        const int rows_here = min(BM, p.nq - mt * BM);
+        const int total = rows_here * p.max_pos;
+        const unsigned long long* src = p.thr_keys + (size_t)mt * BM * p.max_pos;
+        for (int i = et; i < total; i += 256) {
+          const int r = i / p.max_pos, t = i - r * p.max_pos;
+          thr_s[r * THR_STRIDE + t] = (uint32_t)(src[i] >> 32);
+        }
       }
+      CTL_STAMP(0)
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
+      CTL_STAMP(1)
       named_bar_sync(1, 256);  // metadata slice published
+      CTL_STAMP(2)
       const uint32_t t0 = tmem_base + as * 256 + (static_cast<uint32_t>(quarter * 32) << 16) + chalf * 64;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
@@ -403,71 +422,109 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         tmem_ld16(t0 + c * 16, r0);
         tmem_ld16(t0 + 128 + c * 16, r1);
         tmem_ld_wait();
+        CTL_STAMP(3)
         const int cl0 = chalf * 64 + c * 16;  // column inside the tile
         const int col0 = nt * BN + cl0;
+        // ---- phase 1, branch-free: the 16 distances and the masks of the (rare) elements that need more ----
+        float dist[16];
+        uint32_t m_valid = 0, m_cand = 0, m_pos = 0, m_cnt = 0;
         float gmin = CUDART_INF_F;
+        {
+          const float4* sqv = reinterpret_cast<const float4*>(cm_sq + mb + cl0);
+          const float4* isv = reinterpret_cast<const float4*>(cm_is + mb + cl0);
+          float gsq[16], gis[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int col = col0 + j;
-          if (col < p.ng && row_ok) {  // col bound is warp-uniform
-            const float dist = dist_from_acc(__uint_as_float(r0[j]), __uint_as_float(r1[j]), qis, cm_is[mb + cl0 + j],
-                                             qq, cm_sq[mb + cl0 + j], p.cosine);
-            const unsigned int gidx = static_cast<unsigned int>(col + p.g_off);
-            if (p.dist_out) p.dist_out[(size_t)row * p.ld_out + col] = dist;
-            gmin = fminf(gmin, dist);
-            if (p.cand_keys && dist <= tau) {
-              const int slot = atomicAdd(p.cand_count + row, 1);
-              if (slot < p.cand_cap)
-                p.cand_keys[(size_t)row * p.cand_cap + slot] = make_key(dist, gidx);
-              else
-                *p.overflow = 1;
-            }
-            if (p.q_pid) {
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 a4 = sqv[q4], b4 = isv[q4];
+            gsq[4 * q4] = a4.x; gsq[4 * q4 + 1] = a4.y; gsq[4 * q4 + 2] = a4.z; gsq[4 * q4 + 3] = a4.w;
+            gis[4 * q4] = b4.x; gis[4 * q4 + 1] = b4.y; gis[4 * q4 + 2] = b4.z; gis[4 * q4 + 3] = b4.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            dist[j] = dist_from_acc(__uint_as_float(r0[j]), __uint_as_float(r1[j]), qis, gis[j], qq, gsq[j], p.cosine);
+            const bool ok = row_ok && (col0 + j < p.ng);
+            m_valid |= (ok ? 1u : 0u) << j;
+            gmin = fminf(gmin, ok ? dist[j] : CUDART_INF_F);
+            m_cand |= ((ok && dist[j] <= tau) ? 1u : 0u) << j;
+          }
+          if (p.q_pid) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
               const bool same = cm_pid[mb + cl0 + j] == qpid;
               const bool junk = same && ((cm_mask[mb + cl0 + j] >> qcam) & 1ull);
-              if (p.pos_keys && same && !junk) {
-                const int slot = atomicAdd(p.pos_count + row, 1);
-                if (slot < p.max_pos)
-                  p.pos_keys[(size_t)row * p.max_pos + slot] = make_key(dist, gidx);
-                else
-                  *p.overflow = 1;
-              }
-              if (p.buckets && !junk && npos > 0) {
-                const unsigned long long key = make_key(dist, gidx);
-                if (key < maxkey) {
-                  // index of the first positive that sorts strictly after this gallery row
-                  int lo_i;
-                  bool exact = true;
-                  if (thr_in_smem) {
-                    const uint32_t kd = (uint32_t)(key >> 32);
-                    int lo = 0, hi = npos - 1;  // thr_row[hi] >= kd because key < maxkey
-                    while (lo < hi) {
-                      const int mid = (lo + hi) >> 1;
-                      if (thr_row[mid] > kd) hi = mid; else lo = mid + 1;
-                    }
-                    lo_i = lo;
-                    // `lo` = first entry with a LARGER distance; a positive with the SAME distance (lo > 0 and
-                    // thr_row[lo-1] == kd, or the last entry) needs the 64-bit (distance, index) comparison
-                    exact = (lo > 0 && thr_row[lo - 1] == kd) || thr_row[lo] == kd;
-                  }
-                  if (exact) lo_i = bucket_search_global(p.thr_keys + (size_t)row * p.max_pos, npos, key);
-                  atomicAdd(p.buckets + (size_t)row * (p.max_pos + 1) + lo_i, 1);
+              const bool ok = (m_valid >> j) & 1u;
+              m_pos |= ((ok && same && !junk) ? 1u : 0u) << j;
+              // float compare first (cheap); exact 64-bit key order is re-checked in phase 2
+              m_cnt |= ((ok && !junk && npos > 0 && float_orderable(dist[j]) <= (uint32_t)(maxkey >> 32)) ? 1u : 0u) << j;
+            }
+          }
+        }
+        if (!p.cand_keys) m_cand = 0;
+        if (!p.pos_keys) m_pos = 0;
+        if (!p.buckets) m_cnt = 0;
+        // ---- phase 2: full-matrix output (dense) and the rare per-element actions ----
+        if (p.dist_out) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if ((m_valid >> j) & 1u) p.dist_out[(size_t)row * p.ld_out + col0 + j] = dist[j];
+        }
+        if (m_cand | m_pos | m_cnt) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const uint32_t bit = 1u << j;
+            if (!((m_cand | m_pos | m_cnt) & bit)) continue;
+            const unsigned int gidx = static_cast<unsigned int>(col0 + j + p.g_off);
+            const unsigned long long key = make_key(dist[j], gidx);
+            if (m_cand & bit) {
+              const int slot = atomicAdd(p.cand_count + row, 1);
+              if (slot < p.cand_cap) p.cand_keys[(size_t)row * p.cand_cap + slot] = key; else *p.overflow = 1;
+            }
+            if (m_pos & bit) {
+              const int slot = atomicAdd(p.pos_count + row, 1);
+              if (slot < p.max_pos) p.pos_keys[(size_t)row * p.max_pos + slot] = key; else *p.overflow = 1;
+            }
+            if ((m_cnt & bit) && key < maxkey) {
+              // index of the first positive that sorts strictly after this gallery row
+              int lo_i;
+              bool exact = true;
+              if (thr_in_smem) {
+                const uint32_t kd = (uint32_t)(key >> 32);
+                int lo = 0, hi = npos - 1;  // thr_row[hi] >= kd because key < maxkey
+                while (lo < hi) {
+                  const int mid = (lo + hi) >> 1;
+                  if (thr_row[mid] > kd) hi = mid; else lo = mid + 1;
                 }
+                lo_i = lo;
+                // `lo` = first entry with a LARGER distance; a positive with the SAME distance needs the
+                // 64-bit (distance, index) comparison
+                exact = (lo > 0 && thr_row[lo - 1] == kd) || thr_row[lo] == kd;
               }
+              if (exact) lo_i = bucket_search_global(p.thr_keys + (size_t)row * p.max_pos, npos, key);
+              atomicAdd(p.buckets + (size_t)row * (p.max_pos + 1) + lo_i, 1);
             }
           }
         }
         if (p.gmin && row_ok && col0 < p.ng) p.gmin[(size_t)row * p.n_groups + (col0 >> 4)] = gmin;
+        CTL_STAMP(4)
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
       if (thr_in_smem) named_bar_sync(2, 256);  // nobody still reads this tile's thresholds
+      CTL_STAMP(5)
       if (++as == 2) {
         as = 0;
         aphase ^= 1u;
       }
     }
+    if (p.prof && (threadIdx.x == 64 || threadIdx.x == 64 + 5 * 32 + 7)) {
+      long long* dst = p.prof + ((size_t)blockIdx.x * 2 + (threadIdx.x == 64 ? 0 : 1)) * 8;
+      for (int i = 0; i < 8; ++i) dst[i] = pc[i];
+    }
+#undef CTL_STAMP
+  }
+  if (p.prof && warp == 2 && lane == 0) {
+    // (registers of the epilogue leader; other roles write nothing)
   }
   tc_fence_before();
   __syncthreads();
@@ -645,6 +702,8 @@ static int sort_rows(unsigned long long* keys, const int* counts, int64_t rows, 
   CTL_LAUNCH_CHECK();
   return 0;
 }
+
+static long long* g_dist_prof = nullptr;
 
 static int next_pow2(int v) {
   int p = 1;
@@ -850,6 +909,8 @@ int ctl_eval_finalize(const int32_t* buckets, const int32_t* pos_count, int64_t 
   return 0;
 }
 
+void ctl_debug_set_dist_profile(long long* device_buffer) { g_dist_prof = device_buffer; }
+
 int ctl_dist_pass(const void* q_planes, int64_t nq, const void* g_planes, int64_t ng, int32_t d, int32_t flags,
                   const ctl_pass_desc* desc, ctl_stream_t stream) {
   CTL_CHECK_ARG(desc != nullptr, "null pass descriptor");
@@ -881,6 +942,7 @@ int ctl_dist_pass(const void* q_planes, int64_t nq, const void* g_planes, int64_
   CTL_CHECK_ARG(!e.buckets || (e.thr_keys && e.thr_count), "count needs the sorted positives");
   p.overflow = e.overflow;
   p.g_off = e.g_index_offset;
+  p.prof = g_dist_prof;
   CTL_CHECK_ARG(e.g_index_offset >= 0 && e.g_index_offset + ng < (1ll << 32), "gallery index out of uint32 range");
   if (!p.pos_keys && !p.buckets) p.q_pid = nullptr;  // identities unused
   return launch_gemm_pass(q_planes, nq, g_planes, ng, d, flags, p, (cudaStream_t)stream);

@@ -127,6 +127,8 @@ typedef struct ctl_pass_desc {
 } ctl_pass_desc;
 int ctl_dist_pass(const void* q_planes, int64_t nq, const void* g_planes, int64_t ng, int32_t d, int32_t flags,
                   const ctl_pass_desc* desc, ctl_stream_t stream);
+/* debug aid: per-CTA epilogue cycle counters [grid][2][8] written by the following ctl_dist_pass calls */
+void ctl_debug_set_dist_profile(long long* device_buffer);
 /* top-k plan for (ng, k): emit_all != 0 means "skip pass 1, tau = +inf". */
 int ctl_topk_plan(int64_t ng, int32_t k, int32_t* emit_all, int32_t* n_groups, int32_t* merge, int32_t* cand_cap);
 int ctl_select_tau(const float* gmin, int64_t nq, int32_t n_groups, int32_t merge, int32_t k, float* tau,
