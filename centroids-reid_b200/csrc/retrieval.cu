@@ -396,19 +396,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       // distance parts of this row's sorted positives staged in shared memory (row stride 45 words: conflict-
       // free for 32 consecutive rows), so the bucket of a gallery row is a short LDS binary search instead of a
       // dependent chain of L2 loads.  Both warps of a row quarter fill disjoint entries.
-      const bool thr_in_smem = p.buckets && p.max_pos <= THR_MAX;
+      // The distance halves of each row's first THR_MAX sorted positives are staged in shared memory (row
+      // stride 45 words: conflict-free), so the bucket of a gallery row is a short LDS binary search instead of a
+      // dependent chain of L2 loads; deeper positives (rare) and exact distance ties use the 64-bit global search.
+      const bool thr_in_smem = p.buckets != nullptr;
+      const int n_stage = min(p.max_pos, THR_MAX);
       uint32_t* thr_row = thr_s + row_in_tile * THR_STRIDE;
       if (thr_in_smem) {
-        // the 128 rows of this tile own one contiguous [128][max_pos] block of sorted keys: coalesced copy of the
-        // distance halves (entries beyond a row's count are never read)
         const int rows_here = min(BM, p.nq - mt * BM);
-        const int total = rows_here * p.max_pos;
         const unsigned long long* src = p.thr_keys + (size_t)mt * BM * p.max_pos;
-        for (int i = et; i < total; i += 256) {
-          const int r = i / p.max_pos, t = i - r * p.max_pos;
-          thr_s[r * THR_STRIDE + t] = (uint32_t)(src[i] >> 32);
-        }
+        for (int r = ew; r < rows_here; r += 8)  // one warp per row: coalesced along the sorted entries
+          for (int t = lane; t < n_stage; t += 32) thr_s[r * THR_STRIDE + t] = (uint32_t)(src[(size_t)r * p.max_pos + t] >> 32);
       }
+      const int nps = min(npos, THR_MAX);
       CTL_STAMP(0)
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
@@ -487,9 +487,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               // index of the first positive that sorts strictly after this gallery row
               int lo_i;
               bool exact = true;
-              if (thr_in_smem) {
-                const uint32_t kd = (uint32_t)(key >> 32);
-                int lo = 0, hi = npos - 1;  // thr_row[hi] >= kd because key < maxkey
+              const uint32_t kd = (uint32_t)(key >> 32);
+              if (nps == npos || kd < thr_row[nps - 1]) {
+                int lo = 0, hi = nps - 1;  // thr_row[hi] >= kd
                 while (lo < hi) {
                   const int mid = (lo + hi) >> 1;
                   if (thr_row[mid] > kd) hi = mid; else lo = mid + 1;

@@ -19,8 +19,8 @@ print("encode_identities (host) %.3f ms" % T(lambda: R.encode_identities(pids[:3
 print("topk only (2 passes)     %.3f ms" % T(lambda: R.topk(qp, gp, 100)))
 print("evaluate_streamed        %.3f ms" % T(lambda: R.evaluate_streamed(qp, gp, pids[:3368], pids[3368:], cams[:3368], cams[3368:])))
 print("topk_and_eval (fused)    %.3f ms" % T(lambda: R.topk_and_eval(qp, gp, 100, pids[:3368], pids[3368:], cams[:3368], cams[3368:])))
-ids = R.encode_ids(pids[:3368], pids[3368:], cams[:3368], cams[3368:], False, q.device)
-print("evaluate_streamed (ids cached) %.3f ms" % T(lambda: R.evaluate_streamed(qp, gp, pids[:3368], pids[3368:], cams[:3368], cams[3368:], ids=ids)))
+print("max_pos probe"); ids = R.encode_ids(pids[:3368], pids[3368:], cams[:3368], cams[3368:], False, q.device)
+print("max_pos =", ids.max_pos); print("evaluate_streamed (ids cached) %.3f ms" % T(lambda: R.evaluate_streamed(qp, gp, pids[:3368], pids[3368:], cams[:3368], cams[3368:], ids=ids)))
 print("topk_and_eval (ids cached)     %.3f ms" % T(lambda: R.topk_and_eval(qp, gp, 100, pids[:3368], pids[3368:], cams[:3368], cams[3368:], ids=ids)))
 import ctypes as C
 from ctl_b200 import _native as N
