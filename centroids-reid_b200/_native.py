@@ -51,7 +51,7 @@ class PassDesc(C.Structure):
 
     _fields_ = [("dist_out", _p), ("ld_out", _i64), ("gmin", _p), ("tau", _p), ("cand_keys", _p),
                 ("cand_count", _p), ("cand_cap", _i32), ("q_pid", _p), ("q_cam", _p), ("g_pid", _p),
-                ("g_cammask", _p), ("g_idword", _p), ("pos_keys", _p), ("pos_count", _p), ("max_pos", _i32), ("thr_keys", _p),
+                ("g_cammask", _p), ("pos_keys", _p), ("pos_count", _p), ("max_pos", _i32), ("thr_keys", _p),
                 ("thr_count", _p), ("buckets", _p), ("overflow", _p), ("g_index_offset", _i64)]
 
 # name -> (restype, argtypes); kept in one table so tests can check it against the header

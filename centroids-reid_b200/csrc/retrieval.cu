@@ -33,8 +33,8 @@ static constexpr int TILE_BYTES = BM * BK * 2;          // 16 KiB
 static constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // q_hi, q_lo, g_hi, g_lo
 static constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 static constexpr int GROUP_W = 16;                      // columns per group-min
-static constexpr int META_BYTES = 2 * BN * (4 + 4 + 4 + 8 + 4);  // double-buffered per-tile column metadata
-static constexpr int THR_MAX = 36, THR_STRIDE = 36;         // positives per query held in shared memory (stride: LDS.128 conflict-free)
+static constexpr int META_BYTES = 2 * BN * (4 + 4 + 4 + 8);  // double-buffered per-tile column metadata
+static constexpr int THR_MAX = 44, THR_STRIDE = 45;         // positives per query held in shared memory
 static constexpr int THR_BYTES = BM * THR_STRIDE * 4;
 static constexpr size_t GEMM_SMEM = STAGES * STAGE_BYTES + META_BYTES + THR_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
@@ -180,7 +180,6 @@ struct GemmPass {
   const int* q_cam;
   const int* g_pid;
   const unsigned long long* g_mask;
-  const unsigned int* g_word;  // optional: (pid << 8) | camera index per gallery row (single-camera rows)
   unsigned long long* pos_keys;  // collect
   int* pos_count;
   int max_pos;
@@ -350,7 +349,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     float* cm_is = cm_sq + 2 * BN;
     int* cm_pid = reinterpret_cast<int*>(cm_is + 2 * BN);
     unsigned long long* cm_mask = reinterpret_cast<unsigned long long*>(cm_pid + 2 * BN);
-    unsigned int* cm_word = reinterpret_cast<unsigned int*>(cm_mask + 2 * BN);
     uint32_t* thr_s = reinterpret_cast<uint32_t*>(smem_raw + (thr_base - smem_u32(smem_raw)));
     int as = 0;
     uint32_t aphase = 0;
@@ -375,12 +373,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         cm_sq[mb + et] = ok ? p.g_sq[col] : 0.f;
         cm_is[mb + et] = ok ? p.g_is[col] : 0.f;
         if (p.q_pid) {
-          if (p.g_word) {
-            cm_word[mb + et] = ok ? p.g_word[col] : 0xFFFFFFFFu;
-          } else {
-            cm_pid[mb + et] = ok ? p.g_pid[col] : -2;
-            cm_mask[mb + et] = ok ? p.g_mask[col] : 0ull;
-          }
+          cm_pid[mb + et] = ok ? p.g_pid[col] : -2;
+          cm_mask[mb + et] = ok ? p.g_mask[col] : 0ull;
         }
       }
       float qq = 0.f, qis = 0.f, tau = -CUDART_INF_F;
@@ -409,17 +403,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const int n_stage = min(p.max_pos, THR_MAX);
       uint32_t* thr_row = thr_s + row_in_tile * THR_STRIDE;
       if (thr_in_smem) {
-        // thread (row = et / 2, half = et % 2) copies 18 of the row's first 36 distance halves: 18 independent
-        // loads in flight per thread (one latency per tile instead of one per entry)
-        const int r = et >> 1, tb = (et & 1) * (THR_MAX / 2);
-        if (mt * BM + r < p.nq) {
-          const unsigned long long* src = p.thr_keys + (size_t)(mt * BM + r) * p.max_pos;
-          uint32_t v[THR_MAX / 2];
-#pragma unroll
-          for (int t = 0; t < THR_MAX / 2; ++t) v[t] = (tb + t < n_stage) ? (uint32_t)(src[tb + t] >> 32) : 0xFFFFFFFFu;
-#pragma unroll
-          for (int t = 0; t < THR_MAX / 2; ++t) thr_s[r * THR_STRIDE + tb + t] = v[t];
-        }
+        const int rows_here = min(BM, p.nq - mt * BM);
+        const unsigned long long* src = p.thr_keys + (size_t)mt * BM * p.max_pos;
+        for (int r = ew; r < rows_here; r += 8)  // one warp per row: coalesced along the sorted entries
+          for (int t = lane; t < n_stage; t += 32) thr_s[r * THR_STRIDE + t] = (uint32_t)(src[(size_t)r * p.max_pos + t] >> 32);
       }
       const int nps = min(npos, THR_MAX);
       CTL_STAMP(0)
@@ -461,41 +448,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             m_cand |= ((ok && dist[j] <= tau) ? 1u : 0u) << j;
           }
           if (p.q_pid) {
-            const uint32_t maxd = (uint32_t)(maxkey >> 32);
-            if (p.g_word) {
-              // single-camera gallery rows: one 32-bit word (pid << 8 | camera) per column, 4 x LDS.128 per chunk
-              const uint4* wv = reinterpret_cast<const uint4*>(cm_word + mb + cl0);
-              uint32_t w[16];
 #pragma unroll
-              for (int q4 = 0; q4 < 4; ++q4) {
-                const uint4 a4 = wv[q4];
-                w[4 * q4] = a4.x; w[4 * q4 + 1] = a4.y; w[4 * q4 + 2] = a4.z; w[4 * q4 + 3] = a4.w;
-              }
-              const uint32_t qword = ((uint32_t)qpid << 8) | (uint32_t)qcam;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const uint32_t x = w[j] ^ qword;
-                const bool ok = (m_valid >> j) & 1u;
-                m_pos |= ((ok && x < 256u && x != 0u) ? 1u : 0u) << j;                      // same pid, other camera
-                m_cnt |= ((ok && x != 0u && npos > 0 && float_orderable(dist[j]) <= maxd) ? 1u : 0u) << j;  // kept
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const bool same = cm_pid[mb + cl0 + j] == qpid;
-                const bool junk = same && ((cm_mask[mb + cl0 + j] >> qcam) & 1ull);
-                const bool ok = (m_valid >> j) & 1u;
-                m_pos |= ((ok && same && !junk) ? 1u : 0u) << j;
-                // float compare first (cheap); exact 64-bit key order is re-checked in phase 2
-                m_cnt |= ((ok && !junk && npos > 0 && float_orderable(dist[j]) <= maxd) ? 1u : 0u) << j;
-              }
+            for (int j = 0; j < 16; ++j) {
+              const bool same = cm_pid[mb + cl0 + j] == qpid;
+              const bool junk = same && ((cm_mask[mb + cl0 + j] >> qcam) & 1ull);
+              const bool ok = (m_valid >> j) & 1u;
+              m_pos |= ((ok && same && !junk) ? 1u : 0u) << j;
+              // float compare first (cheap); exact 64-bit key order is re-checked in phase 2
+              m_cnt |= ((ok && !junk && npos > 0 && float_orderable(dist[j]) <= (uint32_t)(maxkey >> 32)) ? 1u : 0u) << j;
             }
           }
         }
         if (!p.cand_keys) m_cand = 0;
         if (!p.pos_keys) m_pos = 0;
         if (!p.buckets) m_cnt = 0;
-        CTL_STAMP(6)
         // ---- phase 2: full-matrix output (dense) and the rare per-element actions ----
         if (p.dist_out) {
 #pragma unroll
@@ -518,23 +484,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               if (slot < p.max_pos) p.pos_keys[(size_t)row * p.max_pos + slot] = key; else *p.overflow = 1;
             }
             if ((m_cnt & bit) && key < maxkey) {
-              if (p.prof) pc[7] += 1;  // debug: bucket updates by this thread
               // index of the first positive that sorts strictly after this gallery row
               int lo_i;
               bool exact = true;
               const uint32_t kd = (uint32_t)(key >> 32);
-              {
-                // branch-free scan of the staged distances (padded with 0xFFFFFFFF): 9 independent LDS.128
-                const uint4* tv = reinterpret_cast<const uint4*>(thr_row);
-                int lt = 0, eq = 0;
-#pragma unroll
-                for (int q4 = 0; q4 < THR_MAX / 4; ++q4) {
-                  const uint4 a4 = tv[q4];
-                  lt += (a4.x < kd) + (a4.y < kd) + (a4.z < kd) + (a4.w < kd);
-                  eq += (a4.x == kd) + (a4.y == kd) + (a4.z == kd) + (a4.w == kd);
+              if (nps == npos || kd < thr_row[nps - 1]) {
+                int lo = 0, hi = nps - 1;  // thr_row[hi] >= kd
+                while (lo < hi) {
+                  const int mid = (lo + hi) >> 1;
+                  if (thr_row[mid] > kd) hi = mid; else lo = mid + 1;
                 }
-                lo_i = lt;  // = first positive with a larger distance, when there is no distance tie
-                exact = eq != 0 || (lt >= nps && npos > nps);  // tie, or beyond the staged entries
+                lo_i = lo;
+                // `lo` = first entry with a LARGER distance; a positive with the SAME distance needs the
+                // 64-bit (distance, index) comparison
+                exact = (lo > 0 && thr_row[lo - 1] == kd) || thr_row[lo] == kd;
               }
               if (exact) lo_i = bucket_search_global(p.thr_keys + (size_t)row * p.max_pos, npos, key);
               atomicAdd(p.buckets + (size_t)row * (p.max_pos + 1) + lo_i, 1);
@@ -967,7 +930,6 @@ int ctl_dist_pass(const void* q_planes, int64_t nq, const void* g_planes, int64_
   p.q_cam = e.q_cam;
   p.g_pid = e.g_pid;
   p.g_mask = reinterpret_cast<const unsigned long long*>(e.g_cammask);
-  p.g_word = e.g_idword;
   CTL_CHECK_ARG(!(e.pos_keys || e.buckets) || (e.q_pid && e.q_cam && e.g_pid && e.g_cammask && e.max_pos >= 1),
                 "evaluation epilogues need the identity arrays and max_pos");
   p.pos_keys = reinterpret_cast<unsigned long long*>(e.pos_keys);

@@ -148,15 +148,6 @@ class EncodedIds:
     g_pid: torch.Tensor
     g_mask: torch.Tensor
     max_pos: int
-    g_word: Optional[torch.Tensor] = None  # (pid << 8) | camera, when every gallery row has ONE camera
-
-    def desc(self):
-        """Keyword arguments of _native.PassDesc for these identities."""
-        d = dict(q_pid=self.q_pid.data_ptr(), q_cam=self.q_cam.data_ptr(), g_pid=self.g_pid.data_ptr(),
-                 g_cammask=self.g_mask.data_ptr(), max_pos=self.max_pos)
-        if self.g_word is not None:
-            d["g_idword"] = self.g_word.data_ptr()
-        return d
 
 
 def encode_ids(q_pids, g_pids, q_camids, g_camids, respect_camids: bool, device, global_labels: bool = False) -> EncodedIds:
@@ -168,13 +159,7 @@ def encode_ids(q_pids, g_pids, q_camids, g_camids, respect_camids: bool, device,
     def to_dev(a):
         return torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=True)
 
-    g_word = None
-    gm, gp = arrs[3], arrs[2]
-    if len(gm) and np.all(gm & (gm - np.uint64(1)) == 0) and np.all(gm != 0) and int(gp.max(initial=0)) < (1 << 23) \
-            and int(gp.min(initial=0)) >= 0 and int(arrs[0].min(initial=0)) >= 0 and int(arrs[0].max(initial=0)) < (1 << 23):
-        cam_idx = np.log2(gm.astype(np.float64)).astype(np.uint32)  # exact for single-bit masks
-        g_word = to_dev(((gp.astype(np.uint32) << np.uint32(8)) | cam_idx).view(np.int32))
-    return EncodedIds(to_dev(arrs[0]), to_dev(arrs[1]), to_dev(arrs[2]), to_dev(arrs[3].view(np.int64)), arrs[4], g_word)
+    return EncodedIds(to_dev(arrs[0]), to_dev(arrs[1]), to_dev(arrs[2]), to_dev(arrs[3].view(np.int64)), arrs[4])
 
 
 @dataclass
@@ -244,17 +229,16 @@ def evaluate_streamed(
     ovf = torch.zeros(1, dtype=torch.int32, device=dev)
     s = N.stream_ptr
     with torch.cuda.device(dev):
-        import ctypes as C
-
-        idk = dict(ids.desc(), max_pos=max_pos, g_index_offset=g_index_offset)
-        d1 = N.PassDesc(pos_keys=pos_keys.data_ptr(), pos_count=pos_count.data_ptr(), overflow=ovf.data_ptr(), **idk)
-        N.check(L.ctl_dist_pass(qp.ptr, nq, gp.ptr, ng, qp.d, qp.flags, C.byref(d1), s()))
+        N.check(L.ctl_eval_collect(qp.ptr, nq, gp.ptr, ng, qp.d, qp.flags, d_qpid.data_ptr(), d_qcam.data_ptr(),
+                                   d_gpid.data_ptr(), d_gmask.data_ptr(), g_index_offset, max_pos,
+                                   pos_keys.data_ptr(), pos_count.data_ptr(), ovf.data_ptr(), s()))
         if world > 1:
             pos_keys, pos_count = _allgather_keys(pos_keys, pos_count, max_pos, group)
         N.check(L.ctl_sort_key_rows(pos_keys.data_ptr(), pos_count.data_ptr(), nq, max_pos, s()))
         buckets = torch.zeros(nq, max_pos + 1, dtype=torch.int32, device=dev)
-        d2 = N.PassDesc(thr_keys=pos_keys.data_ptr(), thr_count=pos_count.data_ptr(), buckets=buckets.data_ptr(), **idk)
-        N.check(L.ctl_dist_pass(qp.ptr, nq, gp.ptr, ng, qp.d, qp.flags, C.byref(d2), s()))
+        N.check(L.ctl_eval_count(qp.ptr, nq, gp.ptr, ng, qp.d, qp.flags, d_qpid.data_ptr(), d_qcam.data_ptr(),
+                                 d_gpid.data_ptr(), d_gmask.data_ptr(), g_index_offset, max_pos,
+                                 pos_keys.data_ptr(), pos_count.data_ptr(), buckets.data_ptr(), s()))
         if world > 1:
             dist.all_reduce(buckets, op=dist.ReduceOp.SUM, group=group)
         ranks = torch.empty(nq, max_pos, dtype=torch.int32, device=dev)
@@ -367,7 +351,8 @@ def topk_and_eval(qp: Planes, gp: Planes, k: int, q_pids, g_pids, q_camids, g_ca
     ranks = torch.empty(nq, max_pos, dtype=torch.int32, device=dev)
     ap = torch.empty(nq, dtype=torch.float64, device=dev)
     s = N.stream_ptr
-    idp = dict(ids.desc(), overflow=ovf.data_ptr())
+    idp = dict(q_pid=d_qpid.data_ptr(), q_cam=d_qcam.data_ptr(), g_pid=d_gpid.data_ptr(),
+               g_cammask=d_gmask.data_ptr(), max_pos=max_pos, overflow=ovf.data_ptr())
     with torch.cuda.device(dev):
         p1 = N.PassDesc(pos_keys=pos_keys.data_ptr(), pos_count=pos_count.data_ptr(), **idp)
         if not emit_all.value:

@@ -116,8 +116,6 @@ typedef struct ctl_pass_desc {
   const int32_t* q_cam;
   const int32_t* g_pid;
   const uint64_t* g_cammask;
-  const uint32_t* g_idword;   /* optional fast path: (pid << 8) | camera index per gallery row, valid when every
-                                 gallery row has exactly one camera bit and pid < 2^24 (else NULL) */
   uint64_t* pos_keys;         /* [nq, max_pos] (collect) */
   int32_t* pos_count;         /* [nq], zeroed by the caller */
   int32_t max_pos;

@@ -35,7 +35,7 @@ def gpu_ms(desc, n=10):
         N.check(L.ctl_dist_pass(qp.ptr, nq, gp.ptr, ng, 2048, qp.flags, C.byref(desc), N.stream_ptr()))
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
-idk = ids.desc(); print('packed id words:', ids.g_word is not None)
+idk = dict(q_pid=ids.q_pid.data_ptr(), q_cam=ids.q_cam.data_ptr(), g_pid=ids.g_pid.data_ptr(), g_cammask=ids.g_mask.data_ptr(), max_pos=ids.max_pos)
 ovf = torch.zeros(1, dtype=torch.int32, device="cuda")
 pos_keys = torch.zeros(nq, ids.max_pos, dtype=torch.int64, device="cuda"); pos_count = torch.zeros(nq, dtype=torch.int32, device="cuda")
 print("pass gmin only            %.3f ms" % gpu_ms(N.PassDesc(gmin=gmin.data_ptr())))
@@ -47,7 +47,7 @@ buckets = torch.zeros(nq, ids.max_pos + 1, dtype=torch.int32, device="cuda")
 print("pass count                %.3f ms" % gpu_ms(N.PassDesc(thr_keys=pos_keys.data_ptr(), thr_count=pos_count.data_ptr(), buckets=buckets.data_ptr(), **idk)))
 tau = torch.full((nq,), 1.9, device="cuda"); cand = torch.empty(nq, 4096, dtype=torch.int64, device="cuda"); cc = torch.zeros(nq, dtype=torch.int32, device="cuda")
 print("pass cand(tau=1.9)+count  %.3f ms" % gpu_ms(N.PassDesc(tau=tau.data_ptr(), cand_keys=cand.data_ptr(), cand_count=cc.data_ptr(), cand_cap=4096, overflow=ovf.data_ptr(), thr_keys=pos_keys.data_ptr(), thr_count=pos_count.data_ptr(), buckets=buckets.data_ptr(), **idk)))
-PH = ["tile_setup", "wait_acc", "bar_meta", "tmem_wait", "phase2", "tile_end", "phase1", "n_bucket_updates"]
+PH = ["tile_setup", "wait_acc", "bar_meta", "tmem_wait", "element_loop", "tile_end", "-", "-"]
 def phases(name, desc):
     prof = torch.zeros(148 * 2 * 8, dtype=torch.int64, device="cuda")
     L.ctl_debug_set_dist_profile(prof.data_ptr())
@@ -55,7 +55,7 @@ def phases(name, desc):
     torch.cuda.synchronize()
     L.ctl_debug_set_dist_profile(None)
     pm = prof.view(148, 2, 8).double().mean(0)
-    print(name, "| thread A:", ", ".join(f"{PH[i]}={pm[0, i].item():.0f}" for i in range(8)), "| thread B:", ", ".join(f"{PH[i]}={pm[1, i].item():.0f}" for i in range(8)))
+    print(name, "| thread A:", ", ".join(f"{PH[i]}={pm[0, i].item():.0f}" for i in range(6)), "| thread B:", ", ".join(f"{PH[i]}={pm[1, i].item():.0f}" for i in range(6)))
 phases("gmin", N.PassDesc(gmin=gmin.data_ptr()))
 phases("count", N.PassDesc(thr_keys=pos_keys.data_ptr(), thr_count=pos_count.data_ptr(), buckets=buckets.data_ptr(), **idk))
 print("dist_matrix (1 pass)     %.3f ms" % T(lambda: R.dist_matrix(q, g)))
