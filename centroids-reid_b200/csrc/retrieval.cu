@@ -196,6 +196,18 @@ struct GemmMaps {
 
 // The ONE place a distance is formed from the accumulators: every pass must produce
 // bit-identical values for the same (query, gallery) pair.
+// d[j] for a runtime j without spilling the array to local memory: a 4-level select tree (15 FSEL)
+__device__ __forceinline__ float select16(const float (&d)[16], int j) {
+  float a[8], b[4], c[2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = (j & 1) ? d[2 * i + 1] : d[2 * i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) b[i] = (j & 2) ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) c[i] = (j & 4) ? b[2 * i + 1] : b[2 * i];
+  return (j & 8) ? c[1] : c[0];
+}
+
 __device__ __forceinline__ float dist_from_acc(float acc0, float acc1, float q_is, float g_is, float qq, float gg,
                                                int cosine) {
   float dot = __fmaf_rn(acc1, 4.8828125e-4f /* 2^-11 */, acc0);
@@ -405,8 +417,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       if (thr_in_smem) {
         const int rows_here = min(BM, p.nq - mt * BM);
         const unsigned long long* src = p.thr_keys + (size_t)mt * BM * p.max_pos;
-        for (int r = ew; r < rows_here; r += 8)  // one warp per row: coalesced along the sorted entries
-          for (int t = lane; t < n_stage; t += 32) thr_s[r * THR_STRIDE + t] = (uint32_t)(src[(size_t)r * p.max_pos + t] >> 32);
+        // warp `ew` stages rows ew, ew+8, ...: coalesced along the sorted entries, and all 32 loads of a thread
+        // are issued before the first shared store (one memory latency per tile, not one per row)
+        const uint32_t* src_hi = reinterpret_cast<const uint32_t*>(src) + 1;  // distance half of a key
+        uint32_t v0[BM / 8], v1[BM / 8];
+        const bool in0 = lane < n_stage, in1 = lane + 32 < n_stage;
+#pragma unroll
+        for (int i = 0; i < BM / 8; ++i) {
+          const int r = ew + 8 * i;
+          const size_t o = 2 * ((size_t)r * p.max_pos + lane);
+          v0[i] = (r < rows_here && in0) ? src_hi[o] : 0xFFFFFFFFu;
+          v1[i] = (r < rows_here && in1) ? src_hi[o + 64] : 0xFFFFFFFFu;
+        }
+#pragma unroll
+        for (int i = 0; i < BM / 8; ++i) {
+          const int r = ew + 8 * i;
+          thr_s[r * THR_STRIDE + lane] = v0[i];
+          if (lane + 32 < THR_MAX) thr_s[r * THR_STRIDE + lane + 32] = v1[i];
+        }
       }
       const int nps = min(npos, THR_MAX);
       CTL_STAMP(0)
@@ -468,13 +496,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           for (int j = 0; j < 16; ++j)
             if ((m_valid >> j) & 1u) p.dist_out[(size_t)row * p.ld_out + col0 + j] = dist[j];
         }
-        if (m_cand | m_pos | m_cnt) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
+        // One rolled loop over the set bits (the code of the rare actions is emitted once, and a warp iterates
+        // max-popcount times instead of visiting all 16 column positions).
+        uint32_t m_any = m_cand | m_pos | m_cnt;
+        {
+#pragma unroll 1
+          while (m_any) {
+            const int j = __ffs(m_any) - 1;
             const uint32_t bit = 1u << j;
-            if (!((m_cand | m_pos | m_cnt) & bit)) continue;
+            m_any &= ~bit;
+            const float dj = select16(dist, j);
             const unsigned int gidx = static_cast<unsigned int>(col0 + j + p.g_off);
-            const unsigned long long key = make_key(dist[j], gidx);
+            const unsigned long long key = make_key(dj, gidx);
             if (m_cand & bit) {
               const int slot = atomicAdd(p.cand_count + row, 1);
               if (slot < p.cand_cap) p.cand_keys[(size_t)row * p.cand_cap + slot] = key; else *p.overflow = 1;
