@@ -154,6 +154,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();  // the next kernel may begin its prologue
+  pdl_wait();               // activations of the previous kernel are complete and visible
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -456,6 +458,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
   __syncthreads();
   cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / TMA credit
   tc_fence_after();
+  pdl_launch_dependents();  // the next kernel may begin its prologue
+  pdl_wait();               // activations of the previous kernel are complete and visible
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -709,6 +713,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_c64_kernel(const __gr
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();  // the next kernel may begin its prologue
+  pdl_wait();               // activations of the previous kernel are complete and visible
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -984,6 +990,8 @@ __global__ void __launch_bounds__(STEM_TC_THREADS, 1) stem_tc_kernel(const __gri
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();  // the next kernel may begin its prologue
+  pdl_wait();               // activations of the previous kernel are complete and visible
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   const int tiles_per_img = p.tiles_h * p.tiles_w;
@@ -1147,6 +1155,8 @@ __global__ void __launch_bounds__(STEM_TC_THREADS, 1) stem_tc_kernel(const __gri
 // maxpool 3x3 / 2, pad 1, NHWC fp16; one thread = 8 channels of one output pixel
 __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __half* __restrict__ x, int N, int H, int W, int C,
                                                            __half* __restrict__ out, int Ho, int Wo) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int cv = C / 8;
   const size_t total = (size_t)N * Ho * Wo * cv;
@@ -1186,6 +1196,8 @@ __global__ void __launch_bounds__(256) gap_bn_kernel(const __half* __restrict__ 
                                                      const float* __restrict__ bn_scale /*gamma/sqrt(var+eps)*/,
                                                      const float* __restrict__ bn_shift, float* __restrict__ feat,
                                                      float* __restrict__ emb) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = blockIdx.y;
   const int c2 = blockIdx.x * blockDim.x + threadIdx.x;
   if (c2 * 2 >= C) return;
@@ -1213,6 +1225,8 @@ __global__ void __launch_bounds__(256) gap_bn_kernel(const __half* __restrict__ 
 __global__ void __launch_bounds__(256) instnorm_relu_kernel(__half* __restrict__ x, int HW, int C, int half,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_sum[8][8], s_sq[8][8];
   __shared__ float s_mean[8], s_istd[8];
   const int n = blockIdx.y, c0 = blockIdx.x * 8;
@@ -1287,6 +1301,31 @@ static void pick_tile(int Ho, int Wo, int* TH, int* TW) {
   *TW = btw;
 }
 
+// Launch with programmatic stream serialization (PDL): the next kernel's prologue overlaps this one's drain; every
+// kernel of this file calls pdl_wait() before it touches activations.  CTL_PDL=0 restores ordinary launches.
+static bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CTL_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 static long long* g_conv_prof = nullptr;
 
 template <int BN>
@@ -1299,7 +1338,7 @@ static int launch_conv(const ConvKernelParams& p, cudaStream_t st) {
   }
   const long long tiles = (long long)p.m_tiles * p.n_tiles;
   const int grid = (int)std::min<long long>(tiles, sm_count());
-  conv_gemm_kernel<BN><<<grid, CONV_THREADS, ConvCfg<BN>::SMEM, st>>>(p);
+  CTL_CUDA(launch_k(conv_gemm_kernel<BN>, dim3(grid), dim3(CONV_THREADS), ConvCfg<BN>::SMEM, st, p));
   CTL_LAUNCH_CHECK();
   return 0;
 }
@@ -1331,7 +1370,7 @@ static int launch_c64(const void* x, int n, int h, int w, const void* weight, co
   }
   const long long tiles = (long long)n * p.tiles_h * p.tiles_w;
   const int grid = (int)std::min<long long>(tiles, sm_count());
-  conv3x3_c64_kernel<<<grid, CONV_THREADS, C64_SMEM, st>>>(p);
+  CTL_CUDA(launch_k(conv3x3_c64_kernel, dim3(grid), dim3(CONV_THREADS), C64_SMEM, st, p));
   CTL_LAUNCH_CHECK();
   return 0;
 }
@@ -1344,7 +1383,7 @@ static int launch_conv_pair(const ConvKernelParams& p, cudaStream_t st) {
   }
   const long long tiles = (long long)(p.m_tiles / 2) * p.n_tiles;
   const int clusters = (int)std::min<long long>(tiles, sm_count() / 2);
-  conv_gemm_pair_kernel<<<2 * clusters, CONV_THREADS, PairCfg::SMEM, st>>>(p);
+  CTL_CUDA(launch_k(conv_gemm_pair_kernel, dim3(2 * clusters), dim3(CONV_THREADS), PairCfg::SMEM, st, p));
   CTL_LAUNCH_CHECK();
   return 0;
 }
@@ -1511,7 +1550,7 @@ int ctl_stem_conv7x7_tc(const float* x_nchw, int32_t n, int32_t h, int32_t w, co
   }
   const long long tiles = (long long)n * p.tiles_h * p.tiles_w;
   const int grid = (int)std::min<long long>(tiles, (long long)sm_count());
-  stem_tc_kernel<<<grid, STEM_TC_THREADS, STEM_TC_SMEM, (cudaStream_t)stream>>>(p);
+  CTL_CUDA(launch_k(stem_tc_kernel, dim3(grid), dim3(STEM_TC_THREADS), STEM_TC_SMEM, (cudaStream_t)stream, p));
   CTL_LAUNCH_CHECK();
   return 0;
 }
@@ -1523,8 +1562,8 @@ int ctl_maxpool3x3s2_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, in
   if (rc) return rc;
   const int Ho = (h + 2 - 3) / 2 + 1, Wo = (w + 2 - 3) / 2 + 1;
   const size_t total = (size_t)n * Ho * Wo * (c / 8);
-  maxpool3x3s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      static_cast<const __half*>(x), n, h, w, c, static_cast<__half*>(out), Ho, Wo);
+  CTL_CUDA(launch_k(maxpool3x3s2_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream,
+                    static_cast<const __half*>(x), (int)n, (int)h, (int)w, (int)c, static_cast<__half*>(out), Ho, Wo));
   CTL_LAUNCH_CHECK();
   return 0;
 }
@@ -1536,8 +1575,8 @@ int ctl_gap_bn_nhwc_f16(const void* x, int32_t n, int32_t hw, int32_t c, const f
   int rc = ctl_device_check();
   if (rc) return rc;
   dim3 grid((c / 2 + 255) / 256, n);
-  gap_bn_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const __half*>(x), hw, c, bn_scale, bn_shift, feat,
-                                                       emb);
+  CTL_CUDA(launch_k(gap_bn_kernel, grid, dim3(256), 0, (cudaStream_t)stream, static_cast<const __half*>(x), (int)hw, (int)c,
+                    bn_scale, bn_shift, feat, emb));
   CTL_LAUNCH_CHECK();
   return 0;
 }
@@ -1548,7 +1587,8 @@ int ctl_instnorm_relu_nhwc_f16(void* x, int32_t n, int32_t hw, int32_t c, int32_
   int rc = ctl_device_check();
   if (rc) return rc;
   dim3 grid(half / 8, n);
-  instnorm_relu_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<__half*>(x), hw, c, half, gamma, beta, eps);
+  CTL_CUDA(launch_k(instnorm_relu_kernel, grid, dim3(256), 0, (cudaStream_t)stream, static_cast<__half*>(x), (int)hw, (int)c,
+                    (int)half, gamma, beta, eps));
   CTL_LAUNCH_CHECK();
   return 0;
 }

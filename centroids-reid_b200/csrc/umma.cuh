@@ -270,4 +270,11 @@ __device__ __forceinline__ void umma2_commit_mc(uint32_t bar, uint16_t mask) {
                : "memory");
 }
 
+
+// Programmatic dependent launch: a kernel launched with programmaticStreamSerialization may start (barrier
+// init, TMEM allocation, descriptor prefetch) while its predecessor drains; pdl_wait() blocks until the
+// predecessor grid has completed and its writes are visible.  No-ops for an ordinary launch.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 }  // namespace ctl
