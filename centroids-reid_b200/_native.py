@@ -87,6 +87,8 @@ SIGNATURES = {
     "ctl_debug_set_conv_profile": (None, [_p]),
     "ctl_stem_conv7x7": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _i32, _p, _p]),
     "ctl_stem_conv7x7_tc": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _i32, _p, _p]),
+    "ctl_stem_pad_bytes": (C.c_size_t, [_i32, _i32, _i32]),
+    "ctl_stem_pool_fused": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _p, _i32, _p, _p]),
     "ctl_maxpool3x3s2_nhwc_f16": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p]),
     "ctl_gap_bn_nhwc_f16": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
     "ctl_instnorm_relu_nhwc_f16": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p, _f, _p]),

@@ -1152,6 +1152,277 @@ __global__ void __launch_bounds__(STEM_TC_THREADS, 1) stem_tc_kernel(const __gri
   }
 }
 
+// =======================================================================================
+// Fused stem: conv 7x7 / 2 (+folded BN, optional ReLU) -> maxpool 3x3 / 2, for inputs up to 128 pixels wide.
+//
+// The input is first packed to zero-bordered NHWC4 fp16 (stem_pack_input_kernel: [N][H+6][136][4], 8 bytes per
+// pixel, 3 border pixels left/top).  In that layout the 7-pixel window of output column ox starts 16 bytes after
+// the window of ox-1 (stride 2 x 8 bytes), which is exactly the row pitch of a K-major NO-SWIZZLE UMMA core
+// matrix (8 rows, 16 bytes apart).  So the im2col operand is never built: shared memory holds raw input rows
+// (cut into 8 overlapping 192-byte pieces of 8 output columns each by one TMA box with overlapping strides) and
+// the A descriptor (LBO = 16 B, SBO = 192 B) walks the windows in place.  Per output-row pair the CTA loads
+// 10 input-row slots (15 KiB) instead of a 56 KiB im2col tile; K = 7 kernel rows x (8 px x 4 ch) = 224.
+// Even/odd input rows sit in separate slot runs so that "+1 slot" = "+2 input rows" = the second output row
+// (rows 64..127 of the M = 128 tile).
+//
+// The epilogue writes the conv tile (2 output rows x 64 columns x 64 ch, fp16) to a triple-buffered smem tile and
+// pools it together with the last row of the previous tile; only the pooled tensor goes to HBM.  A CTA walks a
+// contiguous range of row pairs; a range that starts inside an image first recomputes the row pair above it.
+// =======================================================================================
+static constexpr int S3_THREADS = 448;                 // TMA warp, MMA warp, 8 epilogue warps, 4 pool warps
+static constexpr int S3_STAGES = 4;
+static constexpr int S3_PIECE = 256;                   // bytes: 8 windows (stride 2 px) of 8 px need 176; 256 keeps core matrices 128 B-aligned
+static constexpr int S3_SLOT = 8 * S3_PIECE;           // one input row cut into 8 pieces
+static constexpr int S3_STAGE_BYTES = 10 * S3_SLOT;    // 5 even + 5 odd input rows
+static constexpr int S3_W_BYTES = 28 * 64 * 16;        // [k chunk of 8][cout][8] fp16
+static constexpr int S3_TILE_BYTES = 128 * 128;        // conv tile, one 128-byte line per pixel
+static constexpr int S3_WP = 136;                      // padded input row, pixels
+static constexpr size_t S3_SMEM = 1024 + S3_STAGES * S3_STAGE_BYTES + S3_W_BYTES + 3 * S3_TILE_BYTES + 256 + 256;
+
+struct Stem3Params {
+  CUtensorMap x_map;  // 5-D overlapping view of the packed input: {96 el, 8 pieces, row pair, parity, image}
+  const __half* w;    // packed weights [28][64][8]
+  const float* bias;
+  __half* out;        // pooled NHWC fp16 [n][hp][wp][64]
+  int n_img, hp, wp, Wo, relu;
+};
+
+// NCHW fp32 -> zero-bordered NHWC4 fp16; block = 64 x 4 threads, a thread converts two adjacent pixels of one row
+__global__ void __launch_bounds__(256) stem_pack_input_kernel(const float* __restrict__ x, int N, int H, int W,
+                                                              __half* __restrict__ xp) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 6);  // n * H + y
+  const int xw = 2 * (threadIdx.x & 63);
+  if (row >= N * H || xw >= W) return;
+  const int n = row / H, y = row - n * H;
+  const size_t plane = (size_t)H * W;
+  const float* src = x + (size_t)n * 3 * plane + (size_t)y * W + xw;
+  const float2 c0 = *reinterpret_cast<const float2*>(src);
+  const float2 c1 = *reinterpret_cast<const float2*>(src + plane);
+  const float2 c2 = *reinterpret_cast<const float2*>(src + 2 * plane);
+  const __half2 a0 = __floats2half2_rn(c0.x, c1.x), b0 = __floats2half2_rn(c2.x, 0.f);
+  const __half2 a1 = __floats2half2_rn(c0.y, c1.y), b1 = __floats2half2_rn(c2.y, 0.f);
+  uint2* dst = reinterpret_cast<uint2*>(xp + (((size_t)n * (H + 6) + y + 3) * S3_WP + xw + 3) * 4);
+  dst[0] = make_uint2(*reinterpret_cast<const uint32_t*>(&a0), *reinterpret_cast<const uint32_t*>(&b0));
+  dst[1] = make_uint2(*reinterpret_cast<const uint32_t*>(&a1), *reinterpret_cast<const uint32_t*>(&b1));
+}
+
+__global__ void __launch_bounds__(S3_THREADS, 1) stem_pool_kernel(const __grid_constant__ Stem3Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sA = base, sW = sA + S3_STAGES * S3_STAGE_BYTES, sT = sW + S3_W_BYTES;
+  uint8_t* tile_g = gbase + (sT - base);
+  float* bias_s = reinterpret_cast<float*>(gbase + (sT - base) + 3 * S3_TILE_BYTES);
+  const uint32_t bars = sT + 3 * S3_TILE_BYTES + 256;
+  const uint32_t bar_w = bars;
+  auto full_bar = [&](int s) { return bars + 8u * (1 + s); };
+  auto empty_bar = [&](int s) { return bars + 8u * (1 + S3_STAGES + s); };
+  auto tfull_bar = [&](int s) { return bars + 8u * (1 + 2 * S3_STAGES + s); };
+  auto tempty_bar = [&](int s) { return bars + 8u * (3 + 2 * S3_STAGES + s); };
+  auto sfull_bar = [&](int s) { return bars + 8u * (5 + 2 * S3_STAGES + s); };   // conv tile written (8 warps)
+  auto sempty_bar = [&](int s) { return bars + 8u * (8 + 2 * S3_STAGES + s); };  // conv tile no longer needed (4 warps)
+  const uint32_t tmem_slot = bars + 8u * (11 + 2 * S3_STAGES);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < 64) bias_s[tid] = p.bias[tid];
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    for (int s = 0; s < S3_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 8);
+    }
+    for (int s = 0; s < 3; ++s) {
+      mbar_init(sfull_bar(s), 8);
+      mbar_init(sempty_bar(s), 4);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&p.x_map);
+  }
+  if (warp == 1) tmem_alloc<128>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  // contiguous, balanced range of row pairs; a range that starts inside an image recomputes the pair above it
+  const int num_tiles = p.n_img * p.hp;
+  const int per = num_tiles / (int)gridDim.x, rem = num_tiles - per * (int)gridDim.x;
+  const int t_begin = (int)blockIdx.x * per + min((int)blockIdx.x, rem);
+  const int t_end = t_begin + per + ((int)blockIdx.x < rem ? 1 : 0);
+  const int t_first = (t_begin < t_end && (t_begin % p.hp) != 0) ? t_begin - 1 : t_begin;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_w, S3_W_BYTES);
+      bulk_copy_g2s(sW, p.w, S3_W_BYTES, bar_w);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = t_first; t < t_end; ++t) {
+        const int n = t / p.hp, py = t - n * p.hp;
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t dst = sA + stage * S3_STAGE_BYTES;
+        mbar_arrive_expect_tx(full_bar(stage), S3_STAGE_BYTES);
+        tma_load_5d(dst, &p.x_map, full_bar(stage), 0, 0, 2 * py, 0, n);                   // padded rows 4py, +2, .., +8
+        tma_load_5d(dst + 5 * S3_SLOT, &p.x_map, full_bar(stage), 0, 0, 2 * py, 1, n);     // padded rows 4py+1, .., +9
+        if (++stage == S3_STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(128, 64);
+      mbar_wait(bar_w, 0);
+      tc_fence_after();
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int t = t_first; t < t_end; ++t) {
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t a0 = sA + stage * S3_STAGE_BYTES;
+        const uint32_t acc = tmem_base + as * 64;
+#pragma unroll
+        for (int r = 0; r < 7; ++r) {
+          // kernel row r of output row 0 = padded input row 4py + r: slot r/2 of the even or odd run; rows 64..127
+          // of the tile (output row 1) land one slot further (SBO * 8 = one slot)
+          const uint32_t arow = a0 + ((r & 1) * 5 + (r >> 1)) * S3_SLOT;
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const uint64_t da = make_noswizzle_kmajor_desc(arow + 32 * kk, 16, S3_PIECE);
+            const uint64_t db = make_noswizzle_kmajor_desc(sW + (r * 4 + 2 * kk) * 1024, 1024, 128);
+            umma_f16(acc, da, db, idesc, (r > 0 || kk > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(empty_bar(stage));
+        umma_commit(tfull_bar(as));
+        if (++stage == S3_STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1u;
+        }
+      }
+    }
+  } else if (warp < 10) {
+    // ---- epilogue warps: TMEM -> +bias (+ReLU) -> fp16 -> conv tile in shared memory (ring of 3) ----
+    const int ew = warp - 2;
+    const int quarter = warp & 3, chalf = ew >> 2;
+    const int px = quarter * 32 + lane;  // tile row: output row px / 64, column px % 64
+    int as = 0, buf = 0;
+    uint32_t aphase = 0, bphase = 0;
+    float bs[32];  // this thread's 32 channels never change: bias lives in registers (no per-tile LDS)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) bs[j] = bias_s[chalf * 32 + j];
+    for (int t = t_first; t < t_end; ++t) {
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      uint32_t r0[16], r1[16];
+      const uint32_t taddr = tmem_base + as * 64 + chalf * 32 + (static_cast<uint32_t>(quarter * 32) << 16);
+      tmem_ld16(taddr, r0);
+      tmem_ld16(taddr + 16, r1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+      uint8_t* tl = tile_g + buf * S3_TILE_BYTES;
+      uint32_t h[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v0 = __uint_as_float(r0[2 * j]) + bs[2 * j], v1 = __uint_as_float(r0[2 * j + 1]) + bs[2 * j + 1];
+        float v2 = __uint_as_float(r1[2 * j]) + bs[16 + 2 * j], v3 = __uint_as_float(r1[2 * j + 1]) + bs[16 + 2 * j + 1];
+        if (p.relu) {
+          v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
+        }
+        const __half2 a = __floats2half2_rn(v0, v1), b = __floats2half2_rn(v2, v3);
+        h[j] = *reinterpret_cast<const uint32_t*>(&a);
+        h[8 + j] = *reinterpret_cast<const uint32_t*>(&b);
+      }
+      mbar_wait(sempty_bar(buf), bphase ^ 1u);  // the pool warps are done with the tile that lived here
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int chunk = chalf * 4 + q;
+        *reinterpret_cast<uint4*>(tl + px * 128 + ((chunk ^ (px & 7)) << 4)) =
+            make_uint4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sfull_bar(buf));
+      if (++buf == 3) {
+        buf = 0;
+        bphase ^= 1u;
+      }
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1u;
+      }
+    }
+  } else {
+    // ---- pool warps: 3x3/2 max over the conv tile and the last row of the previous one -> HBM ----
+    const int pt = tid - 320;  // 0..127
+    int buf = 0;
+    uint32_t bphase = 0;
+    for (int t = t_first; t < t_end; ++t) {
+      const int n = t / p.hp, py = t - n * p.hp;
+      mbar_wait(sfull_bar(buf), bphase);
+      const int pbuf = buf == 0 ? 2 : buf - 1;
+      if (t >= t_begin) {
+        const uint8_t* tl = tile_g + buf * S3_TILE_BYTES;
+        const uint8_t* prev = tile_g + pbuf * S3_TILE_BYTES;
+        // Out-of-range taps are replaced by an in-window duplicate (max is idempotent): all 9 loads of an output are
+        // unconditional and issued back to back (one shared-memory round trip, not nine).
+        const uint8_t* rows[3] = {py == 0 ? tl : prev + 64 * 128, tl, tl + 64 * 128};
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const int item = pt + it * 128;
+          const int ppx = min(item >> 3, p.wp - 1), pch = item & 7;  // pooled column, 8-channel chunk
+          const int cxs[3] = {max(2 * ppx - 1, 0), 2 * ppx, min(2 * ppx + 1, p.Wo - 1)};
+          uint4 v[9];
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx)
+              v[dy * 3 + dx] = *reinterpret_cast<const uint4*>(rows[dy] + cxs[dx] * 128 + ((pch ^ (cxs[dx] & 7)) << 4));
+          uint4 m = v[0];
+          __half2* mm = reinterpret_cast<__half2*>(&m);
+#pragma unroll
+          for (int q = 1; q < 9; ++q) {
+            const __half2* vv = reinterpret_cast<const __half2*>(&v[q]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) mm[e] = __hmax2(mm[e], vv[e]);
+          }
+          if ((item >> 3) < p.wp)
+            *reinterpret_cast<uint4*>(p.out + (((size_t)n * p.hp + py) * p.wp + ppx) * 64 + pch * 8) = m;
+        }
+      }
+      __syncwarp();
+      if (lane == 0 && t > t_first) mbar_arrive(sempty_bar(pbuf));  // the previous tile is no longer needed
+      if (++buf == 3) {
+        buf = 0;
+        bphase ^= 1u;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<128>(tmem_base);
+  }
+}
+
 // maxpool 3x3 / 2, pad 1, NHWC fp16; one thread = 8 channels of one output pixel
 __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __half* __restrict__ x, int N, int H, int W, int C,
                                                            __half* __restrict__ out, int Ho, int Wo) {
@@ -1552,6 +1823,50 @@ int ctl_stem_conv7x7_tc(const float* x_nchw, int32_t n, int32_t h, int32_t w, co
   const int grid = (int)std::min<long long>(tiles, (long long)sm_count());
   CTL_CUDA(launch_k(stem_tc_kernel, dim3(grid), dim3(STEM_TC_THREADS), STEM_TC_SMEM, (cudaStream_t)stream, p));
   CTL_LAUNCH_CHECK();
+  return 0;
+}
+
+size_t ctl_stem_pad_bytes(int32_t n, int32_t h, int32_t w) {
+  (void)w;
+  if (n < 1 || h < 1) return 0;
+  return (size_t)n * (h + 6) * S3_WP * 4 * sizeof(__half) + 256;  // + slack: the last piece of a row is read 256 B wide
+}
+
+int ctl_stem_pool_fused(const float* x_nchw, int32_t n, int32_t h, int32_t w, void* xpad, const void* weight_packed_f16,
+                        const float* bias, int32_t relu, void* out_pooled_nhwc_f16, ctl_stream_t stream) {
+  CTL_CHECK_ARG(x_nchw && xpad && weight_packed_f16 && bias && out_pooled_nhwc_f16, "null pointer");
+  CTL_CHECK_ARG(n >= 1 && h >= 8 && w >= 8 && h % 4 == 0 && w % 2 == 0 && w <= 128,
+                "the fused stem needs h % 4 == 0, even w <= 128 (use ctl_stem_conv7x7_tc + ctl_maxpool3x3s2_nhwc_f16)");
+  int rc = ctl_device_check();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  CTL_CUDA(launch_k(stem_pack_input_kernel, dim3((unsigned)(((size_t)n * h + 3) / 4)), dim3(256), 0, st, x_nchw, (int)n, (int)h,
+                    (int)w, static_cast<__half*>(xpad)));
+  Stem3Params p = {};
+  p.w = static_cast<const __half*>(weight_packed_f16);
+  p.bias = bias;
+  p.out = static_cast<__half*>(out_pooled_nhwc_f16);
+  p.n_img = n;
+  const int Ho = h / 2;
+  p.Wo = w / 2;
+  p.hp = Ho / 2;
+  p.wp = (p.Wo + 2 - 3) / 2 + 1;
+  p.relu = relu;
+  const uint64_t pitch = (uint64_t)S3_WP * 8, hp_rows = (uint64_t)h + 6;
+  // overlapping view: piece g of a row starts 128 bytes (16 pixels) after piece g-1 and is 192 bytes long
+  const uint64_t dims[5] = {(uint64_t)S3_WP * 4, 8, hp_rows / 2, 2, (uint64_t)n};
+  const uint64_t strd[5] = {2, 128, 2 * pitch, pitch, hp_rows * pitch};
+  const uint32_t box[5] = {S3_PIECE / 2, 8, 5, 1, 1};
+  if ((rc = encode_tensor_map(&p.x_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 5, xpad, dims, strd, box, CU_TENSOR_MAP_SWIZZLE_NONE)))
+    return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CTL_CUDA(cudaFuncSetAttribute(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S3_SMEM));
+    attr_set = true;
+  }
+  const long long tiles = (long long)n * p.hp;
+  const int grid = (int)std::min<long long>(tiles, (long long)sm_count());
+  CTL_CUDA(launch_k(stem_pool_kernel, dim3(grid), dim3(S3_THREADS), S3_SMEM, st, p));
   return 0;
 }
 

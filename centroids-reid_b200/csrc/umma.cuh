@@ -99,6 +99,21 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, 
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1,
+                                            int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6, %7}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+// plain (non-tensor) bulk copy global -> shared, completing `bytes` on the mbarrier; 16-byte aligned, size % 16 == 0
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
 // smem -> global tensor store (bulk async group completion)
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
@@ -195,6 +210,18 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc_ex(uint32_t smem_addr
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(base_offset & 7u) << 49;
   d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// K-major operand WITHOUT swizzle ("interleave"): core matrices of 8 rows x 16 bytes, the 8 rows 16 bytes apart;
+// `lbo_bytes` = distance between the two 16-byte K chunks of one UMMA_K, `sbo_bytes` = distance between 8-row groups.
+// Neither stride has to be the dense one: overlapping rows/groups are legal (the unit just reads the addresses),
+// which is how the stem reads its 7x7/stride-2 im2col windows straight out of raw input rows.
+__device__ __forceinline__ uint64_t make_noswizzle_kmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
   return d;
 }
 // Advancing by one UMMA_K (16 fp16 = 32 bytes) inside the 128-byte swizzle row.

@@ -12,6 +12,7 @@ bn(backbone(x)) of modelling/bases.py:169-177.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -42,6 +43,14 @@ class _Conv:
         self.cin, self.cout, self.k, self.stride, self.relu, self.relu_from = cin, cout, k, stride, relu, relu_from
 
 
+def pack_stem_fused(w_folded: torch.Tensor) -> torch.Tensor:
+    """[64, 3, 7, 7] folded stem weights -> the fused stem's operand [28][64][8] fp16 (include/ctl_b200.h,
+    ctl_stem_pool_fused): chunk c = r * 4 + s // 2, element e = (s % 2) * 4 + ch; ch == 3 and s == 7 are zero."""
+    wk = torch.zeros(64, 7, 8, 4, device=w_folded.device)            # [o][r][s][ch]
+    wk[:, :, :7, :3] = w_folded.float().permute(0, 2, 3, 1)
+    return wk.reshape(64, 28, 8).permute(1, 0, 2).contiguous().half()  # [c = r*4 + s//2][o][e = (s%2)*4 + ch]
+
+
 class TrunkEngine:
     """Packed weights + forward.  `state` is the `base.*`-stripped trunk state_dict on any
     device; `bn_head` optionally the BatchNorm1d(2048) of ModelBase (bases.py:83) for `embed`."""
@@ -57,6 +66,8 @@ class TrunkEngine:
         wk[:, :, :7] = w.reshape(64, 21, 7)
         self.stem_w = torch.cat((wk.reshape(64, 168), torch.zeros(64, 24, device=self.device)), 1).half().contiguous()
         self.stem_b = b.contiguous()
+        self.stem_w3 = pack_stem_fused(w)
+        self._stem_pad = {}  # (n, H, W) -> zero-bordered NHWC4 staging buffer of the fused stem
         self.blocks = []
         for li, (planes, nblk) in enumerate(zip((64, 128, 256, 512), layers), start=1):
             stride0 = 1 if li == 1 else (last_stride if li == 4 else 2)
@@ -121,14 +132,25 @@ class TrunkEngine:
         self.launches_per_forward = 0
         with torch.cuda.device(self.device):
             h, w = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
-            s = torch.empty(n, h, w, 64, dtype=torch.float16, device=self.device)
-            with self._timed("stem_conv", 2.0 * n * h * w * 64 * 147, n * (3.0 * H * W * 4 + h * w * 64 * 2)):
-                N.check(L.ctl_stem_conv7x7_tc(x.data_ptr(), n, H, W, self.stem_w.data_ptr(), self.stem_b.data_ptr(),
-                                              int(self.ibn), s.data_ptr(), N.stream_ptr()))
             hp, wp = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
             a = torch.empty(n, hp, wp, 64, dtype=torch.float16, device=self.device)
-            with self._timed("maxpool", 0.0, n * 64 * 2.0 * (h * w + hp * wp)):
-                N.check(L.ctl_maxpool3x3s2_nhwc_f16(s.data_ptr(), n, h, w, 64, a.data_ptr(), N.stream_ptr()))
+            if H % 4 == 0 and W % 2 == 0 and W <= 128 and os.environ.get("CTL_STEM_FUSED", "1") == "1":
+                # conv1 + bn1 (+ReLU) + maxpool in one pass; only the pooled tensor is written
+                pad = self._stem_pad.get((n, H, W))
+                if pad is None:
+                    pad = torch.zeros(L.ctl_stem_pad_bytes(n, H, W), dtype=torch.uint8, device=self.device)
+                    self._stem_pad[(n, H, W)] = pad
+                with self._timed("stem_pool", 2.0 * n * h * w * 64 * 147, n * (3.0 * H * W * 4 + hp * wp * 64 * 2)):
+                    N.check(L.ctl_stem_pool_fused(x.data_ptr(), n, H, W, pad.data_ptr(), self.stem_w3.data_ptr(),
+                                                  self.stem_b.data_ptr(), int(self.ibn), a.data_ptr(), N.stream_ptr()))
+                self.launches_per_forward += 1  # pack + conv/pool kernels
+            else:
+                s = torch.empty(n, h, w, 64, dtype=torch.float16, device=self.device)
+                with self._timed("stem_conv", 2.0 * n * h * w * 64 * 147, n * (3.0 * H * W * 4 + h * w * 64 * 2)):
+                    N.check(L.ctl_stem_conv7x7_tc(x.data_ptr(), n, H, W, self.stem_w.data_ptr(), self.stem_b.data_ptr(),
+                                                  int(self.ibn), s.data_ptr(), N.stream_ptr()))
+                with self._timed("maxpool", 0.0, n * 64 * 2.0 * (h * w + hp * wp)):
+                    N.check(L.ctl_maxpool3x3s2_nhwc_f16(s.data_ptr(), n, h, w, 64, a.data_ptr(), N.stream_ptr()))
             h, w = hp, wp
             for blk in self.blocks:
                 o1, h1, w1 = self._conv(a, n, h, w, blk["conv1"])

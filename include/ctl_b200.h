@@ -223,6 +223,15 @@ int ctl_stem_conv7x7(const float* x_nchw, int32_t n, int32_t h, int32_t w, const
 /* tensor-core stem: weight_k192_f16 = [64][192] fp16, k = (c*7 + r)*8 + s (s = 7 and k >= 168 zero) */
 int ctl_stem_conv7x7_tc(const float* x_nchw, int32_t n, int32_t h, int32_t w, const void* weight_k192_f16,
                         const float* bias, int32_t relu, void* out_nhwc_f16, ctl_stream_t stream);
+/* Fused stem for inputs up to 128 pixels wide (h % 4 == 0, w even): conv1 7x7/2 + folded bn1 (+ReLU for IBN-a) +
+ * maxpool 3x3/2 in one pass; replaces resnet.py:123-126 / resnet_ibn_a.py:127-130.  `xpad` is a caller-owned
+ * workspace of ctl_stem_pad_bytes(n, h, w) bytes that must have been zero-filled ONCE before its first use with a
+ * given (n, h, w) (the call rewrites only the interior: zero-bordered NHWC4 fp16 copy of x).  `weight_packed_f16`
+ * is [28][64][8] fp16: element (c, o, e) = folded weight w[o][ch = e % 4][r = c / 4][s = 2 * (c % 4) + e / 4],
+ * zero for ch == 3 or s == 7.  Output: pooled NHWC fp16 [n][h/4][(w/2 - 1)/2 + 1][64]. */
+size_t ctl_stem_pad_bytes(int32_t n, int32_t h, int32_t w);
+int ctl_stem_pool_fused(const float* x_nchw, int32_t n, int32_t h, int32_t w, void* xpad, const void* weight_packed_f16,
+                        const float* bias, int32_t relu, void* out_pooled_nhwc_f16, ctl_stream_t stream);
 int ctl_maxpool3x3s2_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, void* out,
                               ctl_stream_t stream);
 int ctl_gap_bn_nhwc_f16(const void* x, int32_t n, int32_t hw, int32_t c, const float* bn_scale, const float* bn_shift,
