@@ -264,14 +264,25 @@ def run_embed(args, world, rank, local):
         tot_ms = sum(v[2] for v in agg.values())
         c = agg["conv_gemm"]
         ach = c[0] / (c[2] * 1e-3) / 1e12
-        roof = {"kernel": "conv_gemm_kernel (52 launches/step, fused conv+BN+residual+ReLU)", "bound": "tensor",
+        roof = {"kernel": "conv_gemm kernels (52 launches/step, fused conv+BN+residual+ReLU)", "bound": "tensor",
                 "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
-                "peak_source": pk["src"] + ", bf16 sustained", "traffic": None,
+                "peak_source": pk["src"] + ", bf16 sustained", "traffic": conv_traffic(),
                 "share_of_step": c[2] / tot_ms,
                 "hbm_achieved_gbs": c[1] / (c[2] * 1e-3) / 1e9, "hbm_peak_gbs": pk["hbm"],
                 "other_kernels_ms": {k: round(v[2], 4) for k, v in agg.items() if k != "conv_gemm"},
                 "conv_ms": round(c[2], 4)}
     return ms, value, launches, e2e, roof, clk.summary()
+
+
+def conv_traffic():
+    """DRAM bytes (read + write) of the 52 conv launches of one bs-256 forward, from the committed ncu metrics
+    pass (profiles/conv_traffic.json, written by tools/ncu_traffic.py on the GPU box); None if absent."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "conv_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f)["dram_bytes_per_step"]
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 # ----------------------------------------------------------------------------------------------
@@ -343,7 +354,7 @@ def run_retrieval(args, world, rank, local, steps=None, warmup=None):
     torch.cuda.synchronize()
     pass_ms = e0.elapsed_time(e1) / 5
     pk = peaks()
-    flops = 3 * 2.0 * RET_Q * RET_G * RET_D  # three fp16 products per (q, g, d)
+    flops = 2.0 * RET_Q * RET_G * RET_D  # algorithmic (2*D flop per pair); the kernel issues 3 fp16 products
     ach = flops / (pass_ms * 1e-3) / 1e12
     return {
         "metric": "QxG top-k pairs/sec (3368x15913x2048, top-100 + CMC/mAP)", "value": RET_Q * RET_G / dt,
@@ -353,7 +364,10 @@ def run_retrieval(args, world, rank, local, steps=None, warmup=None):
         "roofline": {"kernel": "dist_gemm_kernel (split-fp16 x3 tcgen05, one pass)", "bound": "tensor",
                      "achieved": ach, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"],
                      "peak_source": pk["src"] + ", bf16 burst", "pass_ms": pass_ms, "traffic": None,
-                     "note": "achieved counts the 3 fp16 MMA products per element (6*Q*G*D flop per pass)"},
+                     "tensor_pipe_tflops": 3 * ach,
+                     "note": "achieved = algorithmic 2*Q*G*D flop per pass; the fp32-equivalent split issues 3 fp16 "
+                             "MMA products per element (tensor_pipe_tflops = 3 x achieved, %.2f of the burst peak)"
+                             % (3 * ach / pk["tf_burst"])},
         "gpu_launches_per_step": 9,
     }
 

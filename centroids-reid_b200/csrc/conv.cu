@@ -65,7 +65,7 @@ struct ConvCfg {
   static constexpr int TMEM_COLS = BN == 64 ? 128 : (BN == 128 ? 256 : 512);  // 2 accumulator stages
   static constexpr int OUT_SLABS = 4;                  // [128 px][64 ch] fp16 staging slabs for the TMA stores
   static constexpr int IDENT_BYTES = 64 * CBK * 2;     // 64x64 identity operand (residual add on the tensor core)
-  static constexpr int BIAS_BYTES = 2 * BN * 4;        // double-buffered bias slice
+  static constexpr int BIAS_BYTES = 2048 * 4;          // the layer's whole bias vector (Cout <= 2048), loaded once
   static constexpr size_t SMEM =
       (size_t)STAGES * STAGE_BYTES + OUT_SLABS * A_TILE_BYTES + IDENT_BYTES + BIAS_BYTES + 1024 + 256;
 };
@@ -141,6 +141,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     tma_prefetch_desc(&p.res_map);
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x)
+    reinterpret_cast<float*>(gsm + (bias_sm - smem_base))[i] = p.bias[i];
   {  // 64x64 fp16 identity, K-major, SWIZZLE_128B: row r holds a single 1.0 at k = r
     uint8_t* id = gsm + (ident - smem_base);
     for (int i = threadIdx.x; i < Cfg::IDENT_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(id)[i] = make_uint4(0, 0, 0, 0);
@@ -280,8 +282,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     if (t_begin < t_end) it.init(t_begin, p);
     for (int tile = t_begin; tile < t_end; ++tile, it.next(p)) {
       const int h0 = it.th * p.TH, w0 = it.tw * p.TW;
-      float* bias_t = bias_s + ((tile - t_begin) & 1) * BN;  // double-buffered: the previous tile may still read its slice
-      if (et < BN) bias_t[et] = __ldg(p.bias + it.nt * BN + et);
+      const float* bias_t = bias_s + it.nt * BN;  // whole bias vector staged in the prologue
       CTL_STAMP(7)
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
@@ -381,7 +382,7 @@ struct PairCfg {
   static constexpr int STAGES = 4;
   static constexpr int OUT_SLABS = 4;
   static constexpr int IDENT_BYTES = 32 * CBK * 2;  // this CTA's 32 rows of the 64x64 identity
-  static constexpr int BIAS_BYTES = 2 * BN * 4;
+  static constexpr int BIAS_BYTES = 2048 * 4;  // the layer's whole bias vector, loaded once
   static constexpr size_t SMEM =
       (size_t)STAGES * STAGE_BYTES + OUT_SLABS * A_TILE_BYTES + IDENT_BYTES + BIAS_BYTES + 1024 + 256;
 };
@@ -415,15 +416,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
   const int t_begin = cid * per + min(cid, rem);
   const int t_end = t_begin + per + (cid < rem ? 1 : 0);
   const int tiles_per_img = p.tiles_w * p.tiles_h;
-  // pair tile -> (n tile, this CTA's 128-pixel tile); n fastest
-  auto coords = [&](int tile, int& nt, int& w0, int& h0, int& img) {
-    const int pm = tile / p.n_tiles;
-    nt = tile - pm * p.n_tiles;
-    const int mt = 2 * pm + (int)rank;
-    img = mt / tiles_per_img;
-    const int tr = mt - img * tiles_per_img;
-    h0 = (tr / p.tiles_w) * p.TH;
-    w0 = (tr % p.tiles_w) * p.TW;
+  // pair tile -> (n tile, this CTA's 128-pixel tile); n fastest.  Coordinates advance by carries: one set of
+  // integer divisions per role, not per tile.
+  struct PairIter {
+    int nt, w_t, h_t, img;
+    __device__ __forceinline__ void init(int tile, const ConvKernelParams& q, int rank_, int per_img) {
+      const int pm = tile / q.n_tiles;
+      nt = tile - pm * q.n_tiles;
+      const int mt = 2 * pm + rank_;
+      img = mt / per_img;
+      const int tr = mt - img * per_img;
+      h_t = tr / q.tiles_w;
+      w_t = tr - h_t * q.tiles_w;
+    }
+    __device__ __forceinline__ void next(const ConvKernelParams& q) {
+      if (++nt < q.n_tiles) return;
+      nt = 0;
+      w_t += 2;  // the pair advances by two 128-pixel tiles
+      while (w_t >= q.tiles_w) {
+        w_t -= q.tiles_w;
+        if (++h_t == q.tiles_h) {
+          h_t = 0;
+          ++img;
+        }
+      }
+    }
   };
 
   if (threadIdx.x == 0) {
@@ -444,6 +461,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
     tma_prefetch_desc(&p.res_map);
   }
   if (warp == 1) tmem_alloc2<512>(tmem_slot);
+  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x)
+    reinterpret_cast<float*>(gsm + (bias_sm - smem_base))[i] = p.bias[i];
   {  // this CTA's half (rows 32*rank .. +31) of the 64x64 identity, K-major, SWIZZLE_128B
     uint8_t* id = gsm + (ident - smem_base);
     for (int i = threadIdx.x; i < Cfg::IDENT_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(id)[i] = make_uint4(0, 0, 0, 0);
@@ -468,9 +487,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = t_begin; tile < t_end; ++tile) {
-        int nt, w0, h0, img;
-        coords(tile, nt, w0, h0, img);
+      PairIter it;
+      if (t_begin < t_end) it.init(t_begin, p, (int)rank, tiles_per_img);
+      for (int tile = t_begin; tile < t_end; ++tile, it.next(p)) {
+        const int nt = it.nt, w0 = it.w_t * p.TW, h0 = it.h_t * p.TH, img = it.img;
         for (int t = 0; t < p.n_taps; ++t) {
           const ConvTap tap = p.taps[t];
           for (int cb = 0; cb < p.cin_blocks; ++cb) {
@@ -567,13 +587,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
     int as = 0;
     uint32_t aphase = 0;
     uint32_t g = 0;
-    for (int tile = t_begin; tile < t_end; ++tile) {
-      int nt, w0, h0, img;
-      coords(tile, nt, w0, h0, img);
-      float* bias_t = bias_s + ((tile - t_begin) & 1) * BN;
-      if (et < BN) bias_t[et] = __ldg(p.bias + nt * BN + et);
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = clock64();
+#define CTL_STAMP(i)                \
+  if (p.prof) {                     \
+    const long long _t = clock64(); \
+    pc[i] += _t - tprev;            \
+    tprev = _t;                     \
+  }
+    PairIter it;
+    if (t_begin < t_end) it.init(t_begin, p, (int)rank, tiles_per_img);
+    for (int tile = t_begin; tile < t_end; ++tile, it.next(p)) {
+      const int nt = it.nt, w0 = it.w_t * p.TW, h0 = it.h_t * p.TH, img = it.img;
+      const float* bias_t = bias_s + nt * BN;  // whole bias vector staged in the prologue
+      CTL_STAMP(7)
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
+      CTL_STAMP(0)
       const uint32_t t0 = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16) + chalf * 32;
 #pragma unroll 1
       for (int j = 0; j < NSUB; ++j, ++g) {
@@ -583,8 +613,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
         tmem_ld16(t0 + j * 64, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
         tmem_ld16(t0 + j * 64 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
         if (leader_thread) tma_store_wait_read<Cfg::OUT_SLABS - 1>();
+        CTL_STAMP(1)
         named_bar_sync(1, 256);
+        CTL_STAMP(2)
         tmem_ld_wait();
+        CTL_STAMP(4)
         if (j == NSUB - 1) {
           tc_fence_before();
           __syncwarp();
@@ -615,12 +648,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
           for (int q = 0; q < 4; ++q) po[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
           *reinterpret_cast<uint4*>(oslab + (((uint32_t)(chalf * 4 + c) ^ sw) << 4)) = o;
         }
+        CTL_STAMP(5)
         fence_proxy_async();
         named_bar_sync(1, 256);
         if (leader_thread) {
           tma_store_4d(&p.out_map, out_stage + b * A_TILE_BYTES, nt * BN + j * 64, w0, h0, img);
           tma_store_commit();
         }
+        CTL_STAMP(6)
       }
       if (++as == 2) {
         as = 0;
@@ -628,6 +663,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
       }
     }
     if (leader_thread) tma_store_wait<0>();
+    CTL_STAMP(3)
+    if (p.prof && is_leader && (leader_thread || (ew == 5 && lane == 7))) {
+      long long* dst = p.prof + ((size_t)cid * 2 + (leader_thread ? 0 : 1)) * 8;
+      for (int i = 0; i < 8; ++i) dst[i] = pc[i];
+    }
+#undef CTL_STAMP
   }
   tc_fence_before();
   __syncthreads();
@@ -1671,6 +1712,7 @@ int ctl_conv2d_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, int32_t 
   CTL_CHECK_ARG(x && weight && bias && out, "null pointer");
   CTL_CHECK_ARG(n >= 1 && h >= 1 && w >= 1, "bad activation shape");
   CTL_CHECK_ARG(cin % 64 == 0 && cout % 64 == 0, "Cin=%d and Cout=%d must be multiples of 64", cin, cout);
+  CTL_CHECK_ARG(cout <= 2048, "Cout=%d exceeds 2048 (bias staging)", cout);
   CTL_CHECK_ARG((ksize == 1 || ksize == 3) && (stride == 1 || stride == 2), "only 1x1 / 3x3, stride 1 / 2");
   CTL_CHECK_ARG(relu_from % 32 == 0, "relu_from=%d must be a multiple of 32", relu_from);
   CTL_CHECK_ARG(stride == 1 || (h % 2 == 0 && w % 2 == 0), "stride 2 needs even H, W (got %dx%d)", h, w);
