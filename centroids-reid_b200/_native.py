@@ -92,6 +92,8 @@ SIGNATURES = {
     "ctl_maxpool3x3s2_nhwc_f16": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p]),
     "ctl_gap_bn_nhwc_f16": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
     "ctl_instnorm_relu_nhwc_f16": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p, _f, _p]),
+    "ctl_conv2d_wgrad_workspace_bytes": (C.c_size_t, [_i32, _i32, _i32, _i32, _i32, _i32, _i32]),
+    "ctl_conv2d_wgrad_nhwc_f16": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _i32, _i32, _i32, _p, C.c_size_t, _p, _p]),
 }
 
 _lib = None

@@ -7,6 +7,9 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+
+#include <utility>
 
 #include "../../include/ctl_b200.h"
 
@@ -66,5 +69,49 @@ struct Workspace {
     return p;
   }
 };
+
+// ---- shared by conv.cu / train.cu ----
+// pixel tile TH x TW = 128 of an Ho x Wo map
+inline void pick_tile(int Ho, int Wo, int* TH, int* TW) {
+  // TH*TW = 128, minimise the over-covered area; prefer wide tiles (longer contiguous runs)
+  int best = -1, bth = 1, btw = 128;
+  for (int tw = 128; tw >= 1; tw >>= 1) {
+    const int th = 128 / tw;
+    const long long cover = (long long)((Ho + th - 1) / th) * th * ((Wo + tw - 1) / tw) * tw;
+    if (best < 0 || cover < best) {
+      best = (int)cover;
+      bth = th;
+      btw = tw;
+    }
+  }
+  *TH = bth;
+  *TW = btw;
+}
+
+// Launch with programmatic stream serialization (PDL): the next kernel's prologue overlaps this one's drain; every
+// kernel of this file calls pdl_wait() before it touches activations.  CTL_PDL=0 restores ordinary launches.
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CTL_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 
 }  // namespace ctl

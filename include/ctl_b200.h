@@ -239,6 +239,19 @@ int ctl_gap_bn_nhwc_f16(const void* x, int32_t n, int32_t hw, int32_t c, const f
 int ctl_instnorm_relu_nhwc_f16(void* x, int32_t n, int32_t hw, int32_t c, int32_t half, const float* gamma,
                                const float* beta, float eps, ctl_stream_t stream);
 
+/* ---- training-side trunk kernels (autograd through modelling/backbones/resnet.py:67-87 in train mode) ---- */
+
+/* Weight gradient of ctl_conv2d_nhwc_f16's convolution (torch.nn.Conv2d backward w.r.t. weight):
+ *   dw[co][r][s][ci] = sum_{n,ho,wo} dy[n][ho][wo][co] * x[n][ho*stride + r - pad][wo*stride + s - pad][ci]
+ * x: NHWC fp16 [n][h][w][cin]; dy: NHWC fp16 [n][ho][wo][cout]; dw: fp32 [cout][k][k][cin] (the layout of the
+ * forward's weight operand).  fp32 accumulation, deterministic (fixed split + fixed-order reduction).
+ * `workspace` holds the per-split partial tiles: ctl_conv2d_wgrad_workspace_bytes(...) bytes. */
+size_t ctl_conv2d_wgrad_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t cin, int32_t cout, int32_t ksize,
+                                        int32_t stride);
+int ctl_conv2d_wgrad_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, int32_t cin, const void* dy, int32_t cout,
+                              int32_t ksize, int32_t stride, void* workspace, size_t workspace_bytes, float* dw,
+                              ctl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
