@@ -259,6 +259,401 @@ static int wgrad_plan(int n, int h, int w, int cin, int cout, int ksize, int str
   return Ho * 65536 + Wo;
 }
 
+
+// =======================================================================================
+// 2. BatchNorm2d with batch statistics over NHWC fp16 ([rows = N*H*W][C]) -- forward and backward.
+//    A thread owns 8 consecutive channels (one 16-byte load per row); a block walks a contiguous slab of rows,
+//    its threads tiled (channel group, row lane); per-block partial sums go to a workspace and are combined in a
+//    fixed order in double precision (deterministic, no atomics).
+// =======================================================================================
+static constexpr int BN_THREADS = 256;
+static constexpr int BN_MAX_BLOCKS = 1184;  // 148 SMs x 8
+
+struct BnGeom {
+  int groups;         // C / 8
+  int lanes;          // row lanes per block = BN_THREADS / groups (>= 1)
+  int blocks;         // row slabs
+  long long rows_per_block;
+};
+
+static BnGeom bn_geom(long long rows, int C) {
+  BnGeom g;
+  g.groups = C / 8;
+  g.lanes = std::max(1, BN_THREADS / g.groups);
+  const long long iters = (rows + g.lanes - 1) / g.lanes;
+  g.blocks = (int)std::min<long long>(BN_MAX_BLOCKS, std::max<long long>(1, iters / 4));
+  g.rows_per_block = (rows + g.blocks - 1) / g.blocks;
+  return g;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 v;
+  __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+
+// Block-level reduction of per-thread 8-channel partials over the row lanes -> part[block][which][C].
+// blockDim.x = groups * lanes when groups <= 256; for C > 2048 a thread loops over several groups (gstride).
+template <int NQ>
+__device__ __forceinline__ void bn_block_store(float (&acc)[NQ][8], int group, int lane_row, int lanes, int C,
+                                               float* __restrict__ part_block, float* sred) {
+  // sred: [lanes][NQ][C] floats would be too big for large C; reduce lane by lane through registers of lane 0
+  // using shared memory slabs of [NQ][C] (lanes is small when C is large and vice versa: lanes * C = 2048)
+  for (int q = 0; q < NQ; ++q)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sred[((size_t)lane_row * NQ + q) * C + group * 8 + i] = acc[q][i];
+  __syncthreads();
+  if (lane_row == 0) {
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float t = 0.f;
+        for (int l = 0; l < lanes; ++l) t += sred[((size_t)l * NQ + q) * C + group * 8 + i];
+        part_block[(size_t)q * C + group * 8 + i] = t;
+      }
+  }
+}
+
+// pass A of the forward: per-block sum and sum of squares of y
+__global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const __half* __restrict__ y, long long rows, int C,
+                                                              long long rows_per_block, int lanes,
+                                                              float* __restrict__ part) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float sred[];
+  const int groups = C / 8;
+  const int group = threadIdx.x % groups, lane_row = threadIdx.x / groups;
+  float acc[2][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.f;
+  if (lane_row < lanes) {
+    const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    for (long long r = r0 + lane_row; r < r1; r += lanes) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(y + r * C + group * 8), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[0][i] += f[i];
+        acc[1][i] = fmaf(f[i], f[i], acc[1][i]);
+      }
+    }
+  }
+  if (lane_row < lanes) bn_block_store<2>(acc, group, lane_row, lanes, C, part + (size_t)blockIdx.x * 2 * C, sred);
+}
+
+// finalize of the forward: batch mean / biased variance -> invstd, scale = gamma*invstd, shift = beta - mean*scale;
+// running statistics updated like torch (momentum, unbiased variance).
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ part, int blocks, int C, double count,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float eps, float momentum, float* __restrict__ running_mean,
+                                                          float* __restrict__ running_var, float* __restrict__ mean,
+                                                          float* __restrict__ invstd, float* __restrict__ scale,
+                                                          float* __restrict__ shift) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, ss = 0.0;
+  for (int b = 0; b < blocks; ++b) {
+    s += (double)part[(size_t)b * 2 * C + c];
+    ss += (double)part[(size_t)b * 2 * C + C + c];
+  }
+  const double m = s / count;
+  double var = ss / count - m * m;
+  if (var < 0.0) var = 0.0;
+  const float is = (float)(1.0 / sqrt(var + (double)eps));
+  mean[c] = (float)m;
+  invstd[c] = is;
+  const float sc = gamma[c] * is;
+  scale[c] = sc;
+  shift[c] = beta[c] - (float)m * sc;
+  if (running_mean) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// z = [relu](y * scale + shift [+ residual]) -> fp16
+__global__ void __launch_bounds__(256) bn_apply_kernel(const __half* __restrict__ y, long long rows, int C,
+                                                       const float* __restrict__ scale, const float* __restrict__ shift,
+                                                       const __half* __restrict__ residual, int relu,
+                                                       __half* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int groups = C / 8;
+  const long long total = rows * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    float f[8], sc[8], sh[8];
+    unpack8(*reinterpret_cast<const uint4*>(y + i * 8), f);
+    *reinterpret_cast<float4*>(&sc[0]) = *reinterpret_cast<const float4*>(scale + g * 8);
+    *reinterpret_cast<float4*>(&sc[4]) = *reinterpret_cast<const float4*>(scale + g * 8 + 4);
+    *reinterpret_cast<float4*>(&sh[0]) = *reinterpret_cast<const float4*>(shift + g * 8);
+    *reinterpret_cast<float4*>(&sh[4]) = *reinterpret_cast<const float4*>(shift + g * 8 + 4);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], sc[k], sh[k]);
+    if (residual) {
+      float r[8];
+      unpack8(*reinterpret_cast<const uint4*>(residual + i * 8), r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] += r[k];
+    }
+    if (relu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) = pack8(f);
+  }
+}
+
+// pass A of the backward: g = dz * (z > 0) (written to g_out when a ReLU mask is given), per-block sum g and
+// sum g * xhat with xhat = (y - mean) * invstd
+__global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const __half* __restrict__ dz, const __half* __restrict__ z,
+                                                                   const __half* __restrict__ y, long long rows, int C,
+                                                                   long long rows_per_block, int lanes,
+                                                                   const float* __restrict__ mean,
+                                                                   const float* __restrict__ invstd,
+                                                                   __half* __restrict__ g_out, float* __restrict__ part) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float sred[];
+  const int groups = C / 8;
+  const int group = threadIdx.x % groups, lane_row = threadIdx.x / groups;
+  float acc[2][8], mu[8], is[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc[0][i] = acc[1][i] = 0.f;
+    mu[i] = mean[group * 8 + i];
+    is[i] = invstd[group * 8 + i];
+  }
+  if (lane_row < lanes) {
+    const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    for (long long r = r0 + lane_row; r < r1; r += lanes) {
+      const size_t off = (size_t)r * C + group * 8;
+      float g[8], yv[8];
+      unpack8(*reinterpret_cast<const uint4*>(dz + off), g);
+      unpack8(*reinterpret_cast<const uint4*>(y + off), yv);
+      if (z) {
+        float zv[8];
+        unpack8(*reinterpret_cast<const uint4*>(z + off), zv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = zv[i] > 0.f ? g[i] : 0.f;
+        *reinterpret_cast<uint4*>(g_out + off) = pack8(g);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[0][i] += g[i];
+        acc[1][i] = fmaf(g[i], (yv[i] - mu[i]) * is[i], acc[1][i]);
+      }
+    }
+    bn_block_store<2>(acc, group, lane_row, lanes, C, part + (size_t)blockIdx.x * 2 * C, sred);
+  }
+}
+
+// finalize of the backward: dgamma, dbeta (multiplied by `grad_unscale`), and the per-channel coefficients of
+// dy = A * g + B * y + Cc  (= gamma*invstd * (g - dbeta/M - xhat * dgamma/M))
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ part, int blocks, int C, double count,
+                                                              const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                              const float* __restrict__ invstd, float grad_unscale,
+                                                              float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                              float* __restrict__ coef) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double sg = 0.0, sgx = 0.0;
+  for (int b = 0; b < blocks; ++b) {
+    sg += (double)part[(size_t)b * 2 * C + c];
+    sgx += (double)part[(size_t)b * 2 * C + C + c];
+  }
+  dbeta[c] = (float)sg * grad_unscale;
+  dgamma[c] = (float)sgx * grad_unscale;
+  const double k1 = (double)gamma[c] * invstd[c];
+  const double k2 = sg / count;
+  const double k3 = sgx / count * invstd[c];
+  coef[c] = (float)k1;
+  coef[C + c] = (float)(-k1 * k3);
+  coef[2 * C + c] = (float)(k1 * ((double)mean[c] * k3 - k2));
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __half* __restrict__ g, const __half* __restrict__ y,
+                                                           long long rows, int C, const float* __restrict__ coef,
+                                                           __half* __restrict__ dy) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int groups = C / 8;
+  const long long total = rows * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int gi = (int)(i % groups);
+    float gv[8], yv[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(g + i * 8), gv);
+    unpack8(*reinterpret_cast<const uint4*>(y + i * 8), yv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = gi * 8 + k;
+      o[k] = fmaf(coef[c], gv[k], fmaf(coef[C + c], yv[k], coef[2 * C + c]));
+    }
+    *reinterpret_cast<uint4*>(dy + i * 8) = pack8(o);
+  }
+}
+
+// =======================================================================================
+// 3. small backward helpers: global-average-pool, max-pool 3x3/2, zero-insertion upsampling (stride-2 dgrad)
+// =======================================================================================
+__global__ void __launch_bounds__(256) gap_backward_kernel(const float* __restrict__ dfeat, int N, int HW, int C, float scale,
+                                                           __half* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int groups = C / 8;
+  const long long total = (long long)N * HW * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const int n = (int)(i / ((long long)HW * groups));
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = dfeat[(size_t)n * C + g * 8 + k] * scale;
+    *reinterpret_cast<uint4*>(out + i * 8) = pack8(f);
+  }
+}
+
+// dx[p] = sum over the (<= 4) windows that contain p of dy[window] * [p is the window's first maximum in scan order]
+// (torch max_pool2d keeps the first maximum: the forward updates only on `val > max`)
+__global__ void __launch_bounds__(256) maxpool_backward_kernel(const __half* __restrict__ x, const __half* __restrict__ dy,
+                                                               int N, int H, int W, int C, int Ho, int Wo,
+                                                               __half* __restrict__ dx) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int groups = C / 8;
+  const long long total = (long long)N * H * W * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long long t = i / groups;
+    const int pw = (int)(t % W);
+    t /= W;
+    const int ph = (int)(t % H);
+    const int n = (int)(t / H);
+    const __half* xn = x + (size_t)n * H * W * C + g * 8;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int oy = (ph + 1) / 2 - ((ph & 1) ? 1 : 0); oy <= (ph + 1) / 2; ++oy) {
+      if (oy < 0 || oy >= Ho || 2 * oy - 1 > ph || 2 * oy + 1 < ph) continue;
+      for (int ox = (pw + 1) / 2 - ((pw & 1) ? 1 : 0); ox <= (pw + 1) / 2; ++ox) {
+        if (ox < 0 || ox >= Wo || 2 * ox - 1 > pw || 2 * ox + 1 < pw) continue;
+        // first maximum of window (oy, ox), per channel
+        float best[8];
+        int arg[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          best[k] = -INFINITY;
+          arg[k] = -1;
+        }
+        for (int r = 0; r < 3; ++r) {
+          const int yy = 2 * oy - 1 + r;
+          if (yy < 0 || yy >= H) continue;
+          for (int s = 0; s < 3; ++s) {
+            const int xx = 2 * ox - 1 + s;
+            if (xx < 0 || xx >= W) continue;
+            float v[8];
+            unpack8(*reinterpret_cast<const uint4*>(xn + ((size_t)yy * W + xx) * C), v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (v[k] > best[k] || arg[k] < 0) {
+                best[k] = v[k];
+                arg[k] = yy * W + xx;
+              }
+          }
+        }
+        float d[8];
+        unpack8(*reinterpret_cast<const uint4*>(dy + (((size_t)n * Ho + oy) * Wo + ox) * C + g * 8), d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (arg[k] == ph * W + pw) acc[k] += d[k];
+      }
+    }
+    *reinterpret_cast<uint4*>(dx + i * 8) = pack8(acc);
+  }
+}
+
+// out[n][2i][2j] = x[n][i][j] (+ add), every other position = add (or 0): the transposed view of a stride-2 subsampling
+__global__ void __launch_bounds__(256) upsample2_zero_kernel(const __half* __restrict__ x, int N, int H, int W, int C,
+                                                             const __half* __restrict__ add, __half* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int groups = C / 8;
+  const int H2 = 2 * H, W2 = 2 * W;
+  const long long total = (long long)N * H2 * W2 * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long long t = i / groups;
+    const int xx = (int)(t % W2);
+    t /= W2;
+    const int yy = (int)(t % H2);
+    const int n = (int)(t / H2);
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = 0.f;
+    if (((xx | yy) & 1) == 0)
+      unpack8(*reinterpret_cast<const uint4*>(x + (((size_t)n * H + yy / 2) * W + xx / 2) * C + g * 8), f);
+    if (add) {
+      float a[8];
+      unpack8(*reinterpret_cast<const uint4*>(add + i * 8), a);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] += a[k];
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) = pack8(f);
+  }
+}
+
+// im2col of the stem for its weight gradient: out[pixel][k], k = (c*7 + r)*8 + s (s = 7 and k >= 168 zero): the K
+// ordering of ctl_stem_conv7x7_tc's weight operand, fp16
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, int N, int H, int W, int Ho, int Wo,
+                                                          __half* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long total = (long long)N * Ho * Wo * 24;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int chunk = (int)(i % 24);
+    long long t = i / 24;
+    const int ox = (int)(t % Wo);
+    t /= Wo;
+    const int oy = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = 0.f;
+    if (chunk < 21) {
+      const int c = chunk / 7, r = chunk - c * 7;
+      const int yy = 2 * oy - 3 + r;
+      if (yy >= 0 && yy < H) {
+        const float* row = x + (((size_t)n * 3 + c) * H + yy) * W;
+#pragma unroll
+        for (int s = 0; s < 7; ++s) {
+          const int xx = 2 * ox - 3 + s;
+          if (xx >= 0 && xx < W) f[s] = row[xx];
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) = pack8(f);
+  }
+}
+
+static int ew_grid(long long total) {
+  return (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
+}
+
 }  // namespace ctl
 
 using namespace ctl;
@@ -340,6 +735,111 @@ int ctl_conv2d_wgrad_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, in
   const int rgrid = (int)std::min<size_t>((n4 + 255) / 256, (size_t)sm_count() * 8);
   CTL_CUDA(launch_k(wgrad_reduce_kernel, dim3(rgrid), dim3(256), 0, st, (const float*)p.part, p.splits, p.cout_pad, (int)cout,
                     p.n_taps * (int)cin, dw));
+  return 0;
+}
+
+
+size_t ctl_bn_workspace_bytes(int64_t rows, int32_t c) {
+  if (rows < 1 || c < 64 || c > 2048 || (c & (c - 1)) != 0) return 0;
+  const BnGeom g = bn_geom(rows, c);
+  return ((size_t)g.blocks * 2 * c + 4 * (size_t)c) * sizeof(float) + 256;
+}
+
+static int bn_check(const char* what, int64_t rows, int32_t c, const void* ws, size_t ws_bytes) {
+  CTL_CHECK_ARG(rows >= 1 && c >= 64 && c <= 2048 && (c & (c - 1)) == 0, "%s: C=%d must be a power of two in [64, 2048]", what, c);
+  CTL_CHECK_ARG(ws && ws_bytes >= ctl_bn_workspace_bytes(rows, c) - 256, "%s: workspace too small", what);
+  CTL_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 15u) == 0, "%s: workspace must be 16-byte aligned", what);
+  return ctl_device_check();
+}
+
+int ctl_bn_train_forward_nhwc_f16(const void* y, int64_t rows, int32_t c, const float* gamma, const float* beta, float eps,
+                                  float momentum, float* running_mean, float* running_var, const void* residual,
+                                  int32_t relu, void* workspace, size_t workspace_bytes, float* save_mean,
+                                  float* save_invstd, void* out, ctl_stream_t stream) {
+  CTL_CHECK_ARG(y && gamma && beta && save_mean && save_invstd && out, "null pointer");
+  CTL_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "running_mean / running_var: both or neither");
+  int rc = bn_check("bn forward", rows, c, workspace, workspace_bytes);
+  if (rc) return rc;
+  const BnGeom g = bn_geom(rows, c);
+  float* part = static_cast<float*>(workspace);
+  float* scale = part + (size_t)g.blocks * 2 * c;
+  float* shift = scale + c;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t sm = (size_t)g.lanes * 2 * c * sizeof(float);
+  CTL_CUDA(launch_k(bn_stats_kernel, dim3(g.blocks), dim3(BN_THREADS), sm, st, static_cast<const __half*>(y), (long long)rows,
+                    (int)c, g.rows_per_block, g.lanes, part));
+  CTL_CUDA(launch_k(bn_finalize_kernel, dim3((c + 255) / 256), dim3(256), 0, st, (const float*)part, g.blocks, (int)c,
+                    (double)rows, gamma, beta, eps, momentum, running_mean, running_var, save_mean, save_invstd, scale, shift));
+  CTL_CUDA(launch_k(bn_apply_kernel, dim3(ew_grid(rows * (c / 8))), dim3(256), 0, st, static_cast<const __half*>(y),
+                    (long long)rows, (int)c, (const float*)scale, (const float*)shift, static_cast<const __half*>(residual),
+                    (int)relu, static_cast<__half*>(out)));
+  return 0;
+}
+
+int ctl_bn_train_backward_nhwc_f16(const void* dz, const void* z, const void* y, int64_t rows, int32_t c, const float* gamma,
+                                   const float* save_mean, const float* save_invstd, float grad_unscale, void* workspace,
+                                   size_t workspace_bytes, void* g_out, float* dgamma, float* dbeta, void* dy,
+                                   ctl_stream_t stream) {
+  CTL_CHECK_ARG(dz && y && gamma && save_mean && save_invstd && dgamma && dbeta && dy, "null pointer");
+  CTL_CHECK_ARG(z == nullptr || g_out != nullptr, "a ReLU mask (z) needs g_out (it may alias dz)");
+  int rc = bn_check("bn backward", rows, c, workspace, workspace_bytes);
+  if (rc) return rc;
+  const BnGeom g = bn_geom(rows, c);
+  float* part = static_cast<float*>(workspace);
+  float* coef = part + (size_t)g.blocks * 2 * c;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t sm = (size_t)g.lanes * 2 * c * sizeof(float);
+  CTL_CUDA(launch_k(bn_bwd_reduce_kernel, dim3(g.blocks), dim3(BN_THREADS), sm, st, static_cast<const __half*>(dz),
+                    static_cast<const __half*>(z), static_cast<const __half*>(y), (long long)rows, (int)c, g.rows_per_block,
+                    g.lanes, save_mean, save_invstd, static_cast<__half*>(g_out), part));
+  CTL_CUDA(launch_k(bn_bwd_finalize_kernel, dim3((c + 255) / 256), dim3(256), 0, st, (const float*)part, g.blocks, (int)c,
+                    (double)rows, gamma, save_mean, save_invstd, grad_unscale, dgamma, dbeta, coef));
+  const __half* gsrc = z ? static_cast<const __half*>(g_out) : static_cast<const __half*>(dz);
+  CTL_CUDA(launch_k(bn_bwd_apply_kernel, dim3(ew_grid(rows * (c / 8))), dim3(256), 0, st, gsrc, static_cast<const __half*>(y),
+                    (long long)rows, (int)c, (const float*)coef, static_cast<__half*>(dy)));
+  return 0;
+}
+
+int ctl_gap_backward_nhwc_f16(const float* dfeat, int32_t n, int32_t hw, int32_t c, float scale, void* out,
+                              ctl_stream_t stream) {
+  CTL_CHECK_ARG(dfeat && out && n >= 1 && hw >= 1 && c % 8 == 0, "bad arguments");
+  int rc = ctl_device_check();
+  if (rc) return rc;
+  CTL_CUDA(launch_k(gap_backward_kernel, dim3(ew_grid((long long)n * hw * (c / 8))), dim3(256), 0, (cudaStream_t)stream, dfeat,
+                    (int)n, (int)hw, (int)c, scale, static_cast<__half*>(out)));
+  return 0;
+}
+
+int ctl_maxpool3x3s2_backward_nhwc_f16(const void* x, const void* dy, int32_t n, int32_t h, int32_t w, int32_t c, void* dx,
+                                       ctl_stream_t stream) {
+  CTL_CHECK_ARG(x && dy && dx && n >= 1 && h >= 1 && w >= 1 && c % 8 == 0, "bad arguments");
+  int rc = ctl_device_check();
+  if (rc) return rc;
+  const int Ho = (h + 2 - 3) / 2 + 1, Wo = (w + 2 - 3) / 2 + 1;
+  CTL_CUDA(launch_k(maxpool_backward_kernel, dim3(ew_grid((long long)n * h * w * (c / 8))), dim3(256), 0, (cudaStream_t)stream,
+                    static_cast<const __half*>(x), static_cast<const __half*>(dy), (int)n, (int)h, (int)w, (int)c, Ho, Wo,
+                    static_cast<__half*>(dx)));
+  return 0;
+}
+
+int ctl_upsample2_zero_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, const void* add, void* out,
+                                ctl_stream_t stream) {
+  CTL_CHECK_ARG(x && out && n >= 1 && h >= 1 && w >= 1 && c % 8 == 0, "bad arguments");
+  int rc = ctl_device_check();
+  if (rc) return rc;
+  CTL_CUDA(launch_k(upsample2_zero_kernel, dim3(ew_grid((long long)n * 4 * h * w * (c / 8))), dim3(256), 0, (cudaStream_t)stream,
+                    static_cast<const __half*>(x), (int)n, (int)h, (int)w, (int)c, static_cast<const __half*>(add),
+                    static_cast<__half*>(out)));
+  return 0;
+}
+
+int ctl_stem_im2col_f16(const float* x_nchw, int32_t n, int32_t h, int32_t w, void* out, ctl_stream_t stream) {
+  CTL_CHECK_ARG(x_nchw && out && n >= 1 && h >= 7 && w >= 7, "bad arguments");
+  int rc = ctl_device_check();
+  if (rc) return rc;
+  const int Ho = (h + 6 - 7) / 2 + 1, Wo = (w + 6 - 7) / 2 + 1;
+  CTL_CUDA(launch_k(stem_im2col_kernel, dim3(ew_grid((long long)n * Ho * Wo * 24)), dim3(256), 0, (cudaStream_t)stream, x_nchw,
+                    (int)n, (int)h, (int)w, Ho, Wo, static_cast<__half*>(out)));
   return 0;
 }
 

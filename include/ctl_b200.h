@@ -252,6 +252,36 @@ int ctl_conv2d_wgrad_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, in
                               int32_t ksize, int32_t stride, void* workspace, size_t workspace_bytes, float* dw,
                               ctl_stream_t stream);
 
+/* BatchNorm2d with batch statistics (torch.nn.BatchNorm2d in train mode, resnet.py:72-85) over NHWC fp16
+ * [rows = N*H*W][c]; c a power of two in [64, 2048].  forward: mean / biased variance over the rows (fp32 partial
+ * sums combined in double, deterministic), running statistics updated in place when given (momentum, unbiased
+ * variance), out = [relu](gamma * (y - mean) * invstd + beta [+ residual]) rounded to fp16; save_mean / save_invstd
+ * feed the backward.  backward: g = dz * (z > 0) when the ReLU output z is given (g is written to g_out, which may
+ * alias dz) else g = dz; dgamma = sum g * xhat, dbeta = sum g (both multiplied by grad_unscale, fp32);
+ * dy = gamma * invstd * (g - mean_rows(g) - xhat * mean_rows(g * xhat)) rounded to fp16.
+ * Workspace: ctl_bn_workspace_bytes(rows, c). */
+size_t ctl_bn_workspace_bytes(int64_t rows, int32_t c);
+int ctl_bn_train_forward_nhwc_f16(const void* y, int64_t rows, int32_t c, const float* gamma, const float* beta, float eps,
+                                  float momentum, float* running_mean, float* running_var, const void* residual,
+                                  int32_t relu, void* workspace, size_t workspace_bytes, float* save_mean,
+                                  float* save_invstd, void* out, ctl_stream_t stream);
+int ctl_bn_train_backward_nhwc_f16(const void* dz, const void* z, const void* y, int64_t rows, int32_t c, const float* gamma,
+                                   const float* save_mean, const float* save_invstd, float grad_unscale, void* workspace,
+                                   size_t workspace_bytes, void* g_out, float* dgamma, float* dbeta, void* dy,
+                                   ctl_stream_t stream);
+/* Backward helpers of the trunk: global average pool (out[n][p][c] = dfeat[n][c] * scale, fp16), max-pool 3x3/2 pad 1
+ * (gradient routed to the first maximum of every window, like torch), zero-insertion upsampling
+ * out[n][2i][2j] = x[n][i][j] (+ add) (the transpose of a stride-2 subsampling), and the stem's im2col
+ * ([n*ho*wo][192] fp16, k = (c*7 + r)*8 + s) that turns the 7x7 weight gradient into ctl_conv2d_wgrad_nhwc_f16
+ * with cin = 192, ksize = 1. */
+int ctl_gap_backward_nhwc_f16(const float* dfeat, int32_t n, int32_t hw, int32_t c, float scale, void* out,
+                              ctl_stream_t stream);
+int ctl_maxpool3x3s2_backward_nhwc_f16(const void* x, const void* dy, int32_t n, int32_t h, int32_t w, int32_t c, void* dx,
+                                       ctl_stream_t stream);
+int ctl_upsample2_zero_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, const void* add, void* out,
+                                ctl_stream_t stream);
+int ctl_stem_im2col_f16(const float* x_nchw, int32_t n, int32_t h, int32_t w, void* out, ctl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

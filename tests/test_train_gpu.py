@@ -49,3 +49,112 @@ def test_conv_wgrad(shape):
                                         nbytes, dw2.data_ptr(), N.stream_ptr()))
     torch.cuda.synchronize()
     assert torch.equal(dw, dw2)
+
+
+@pytest.mark.parametrize("rows,c,relu,res", [(1000, 64, 1, 0), (4096, 256, 1, 1), (333, 2048, 0, 0), (20000, 128, 1, 1)])
+def test_bn_train_forward_backward(rows, c, relu, res):
+    from ctl_b200 import _native as N
+
+    L = N.lib()
+    g = torch.Generator().manual_seed(rows + c)
+    y = (torch.randn(rows, c, generator=g) * 1.5 + 0.3).half()
+    r = torch.randn(rows, c, generator=g).half() if res else None
+    gamma, beta = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.2
+    rm, rv = torch.randn(c, generator=g) * 0.1, torch.rand(c, generator=g) + 0.5
+    dz = (torch.randn(rows, c, generator=g) * 0.1).half()
+    eps, mom = 1e-5, 0.1
+    # float64 reference on the fp16-rounded operands
+    yd = y.double().requires_grad_(True)
+    gd, bd = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    mean, var = yd.mean(0), yd.var(0, unbiased=False)
+    pre = (yd - mean) / torch.sqrt(var + eps) * gd + bd + (r.double() if res else 0.0)
+    zref = pre.clamp(min=0) if relu else pre
+    zref16 = zref.detach().half()
+    mask = (zref16 > 0).double() if relu else torch.ones_like(pre)
+    (pre * (dz.double() * mask)).sum().backward()  # d/dpre = dz * mask, the engine's definition of g
+
+    yc, dzc = y.cuda(), dz.cuda()
+    rc_ = r.cuda() if res else None
+    gam, bet, rmc, rvc = gamma.cuda(), beta.cuda(), rm.cuda(), rv.cuda()
+    nb = L.ctl_bn_workspace_bytes(rows, c)
+    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    sm, si = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
+    out = torch.empty(rows, c, dtype=torch.float16, device="cuda")
+    N.check(L.ctl_bn_train_forward_nhwc_f16(yc.data_ptr(), rows, c, gam.data_ptr(), bet.data_ptr(), eps, mom, rmc.data_ptr(),
+                                            rvc.data_ptr(), N.ptr(rc_), relu, ws.data_ptr(), nb, sm.data_ptr(), si.data_ptr(),
+                                            out.data_ptr(), N.stream_ptr()))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(sm.cpu().numpy(), mean.detach().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(si.cpu().numpy(), (1 / torch.sqrt(var + eps)).detach().numpy(), rtol=1e-5)
+    np.testing.assert_allclose(rmc.cpu().numpy(), (0.9 * rm.double() + 0.1 * mean.detach()).numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(rvc.cpu().numpy(), (0.9 * rv.double() + 0.1 * yd.detach().var(0, unbiased=True)).numpy(), rtol=1e-5)
+    err = (out.cpu().double() - zref.detach()).abs().max()
+    assert float(err) <= float(zref.abs().max()) * 2.0 ** -10 + 1e-6  # one fp16 rounding
+
+    dgam, dbet = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
+    dy = torch.empty(rows, c, dtype=torch.float16, device="cuda")
+    gbuf = torch.empty_like(dzc)
+    zc = zref16.cuda()
+    N.check(L.ctl_bn_train_backward_nhwc_f16(dzc.data_ptr(), zc.data_ptr() if relu else None, yc.data_ptr(), rows, c,
+                                             gam.data_ptr(), sm.data_ptr(), si.data_ptr(), 0.5, ws.data_ptr(), nb,
+                                             gbuf.data_ptr() if relu else None, dgam.data_ptr(), dbet.data_ptr(),
+                                             dy.data_ptr(), N.stream_ptr()))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(dgam.cpu().numpy(), 0.5 * gd.grad.numpy(), rtol=2e-4, atol=2e-4 * float(gd.grad.abs().max()))
+    np.testing.assert_allclose(dbet.cpu().numpy(), 0.5 * bd.grad.numpy(), rtol=2e-4, atol=2e-4 * float(bd.grad.abs().max()))
+    dyr = yd.grad
+    assert float((dy.cpu().double() - dyr).abs().max()) <= float(dyr.abs().max()) * 2.0 ** -9 + 1e-7
+    if relu:
+        assert torch.equal(gbuf.cpu(), (dz.double() * mask).half())
+
+
+def test_pool_gap_upsample_im2col_backward_helpers():
+    from ctl_b200 import _native as N
+
+    L = N.lib()
+    g = torch.Generator().manual_seed(9)
+    # max-pool backward vs autograd (fp16 values, including exact ties from a ReLU)
+    n, h, w, c = 3, 12, 10, 64
+    x = torch.randn(n, h, w, c, generator=g).clamp(min=0).half()
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    dy = torch.randn(n, ho, wo, c, generator=g).half()
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    F.max_pool2d(xr, 3, 2, 1).backward(dy.float().permute(0, 3, 1, 2))
+    xd, dyd = x.cuda(), dy.cuda()
+    dx = torch.empty_like(xd)
+    N.check(L.ctl_maxpool3x3s2_backward_nhwc_f16(xd.data_ptr(), dyd.data_ptr(), n, h, w, c, dx.data_ptr(), N.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = xr.grad.permute(0, 2, 3, 1)
+    assert float((dx.cpu().float() - ref).abs().max()) <= 2.0 ** -9 * float(ref.abs().max())
+    # global-average-pool backward
+    df = torch.randn(4, 128, generator=g)
+    out = torch.empty(4, 6, 128, dtype=torch.float16, device="cuda")
+    dfd = df.cuda()
+    N.check(L.ctl_gap_backward_nhwc_f16(dfd.data_ptr(), 4, 6, 128, 0.25, out.data_ptr(), N.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), (df * 0.25).half()[:, None, :].expand(4, 6, 128))
+    # zero-insertion upsampling (+ add)
+    xs = torch.randn(2, 3, 5, 64, generator=g).half()
+    add = torch.randn(2, 6, 10, 64, generator=g).half()
+    xsd, addd = xs.cuda(), add.cuda()
+    up = torch.empty(2, 6, 10, 64, dtype=torch.float16, device="cuda")
+    for a in (None, addd):
+        N.check(L.ctl_upsample2_zero_nhwc_f16(xsd.data_ptr(), 2, 3, 5, 64, N.ptr(a), up.data_ptr(), N.stream_ptr()))
+        torch.cuda.synchronize()
+        ref = torch.zeros(2, 6, 10, 64)
+        ref[:, ::2, ::2] = xs.float()
+        if a is not None:
+            ref = ref + add.float()
+        assert torch.equal(up.cpu(), ref.half())
+    # stem im2col: k = (c*7 + r)*8 + s
+    xi = torch.randn(2, 3, 16, 12, generator=g)
+    ho, wo = 8, 6
+    col = torch.empty(2 * ho * wo, 192, dtype=torch.float16, device="cuda")
+    xid = xi.cuda()
+    N.check(L.ctl_stem_im2col_f16(xid.data_ptr(), 2, 16, 12, col.data_ptr(), N.stream_ptr()))
+    torch.cuda.synchronize()
+    unf = F.unfold(xi, 7, padding=3, stride=2).reshape(2, 3, 7, 7, ho * wo).permute(0, 4, 1, 2, 3)  # [n][pix][c][r][s]
+    ref = torch.zeros(2, ho * wo, 3, 7, 8)
+    ref[..., :7] = unf
+    ref = torch.cat((ref.reshape(2 * ho * wo, 168), torch.zeros(2 * ho * wo, 24)), 1).half()
+    assert torch.equal(col.cpu(), ref)
