@@ -1,0 +1,236 @@
+"""Train-mode ResNet-50 trunk on the B200 kernels: forward with batch-statistics BatchNorm and the full backward
+(what autograd does through modelling/backbones/resnet.py:67-87,122-133 + baseline.py:91-96 in the reference).
+
+Per conv+BN of the forward:   conv (tcgen05 implicit GEMM, raw fp16 output y)  ->  batch statistics  ->
+z = [relu](gamma * xhat + beta [+ shortcut])  (fp16).  The backward walks the blocks in reverse:
+BN/ReLU backward (masked grad g, dgamma, dbeta, dy), weight gradient (tcgen05 GEMM over the pixel dimension),
+data gradient = the forward conv kernel on dy with the transposed / flipped weights (stride-2 layers through
+zero-insertion upsampling), shortcut gradients folded into conv1's data gradient through the kernel's residual
+input.  Activations and activation gradients are fp16, every reduction and all parameter gradients fp32.
+
+Gradients are computed on `grad_scale * dfeat` (a fixed loss scale against fp16 underflow, the role of the AMP
+GradScaler in the reference's PL trainer) and un-scaled in fp32.  ResNet-50 only: the IBN-a variant's
+InstanceNorm has no training kernels yet.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from ... import _native as N
+
+BN_EPS = 1e-5
+R50_LAYERS = (3, 4, 6, 3)
+
+
+class _Saved:
+    __slots__ = ("a", "y", "z", "mean", "invstd", "shape_in", "shape_out", "conv", "bn", "k", "stride", "relu")
+
+
+class TrunkTrainer:
+    """`params`: name -> tensor with the reference's `base.*`-stripped names (conv weights [Cout, Cin, k, k], BN
+    weight / bias fp32 on the device; BN running_mean / running_var are updated in place)."""
+
+    def __init__(self, device, last_stride: int = 1, layers=R50_LAYERS, grad_scale: float = 1024.0,
+                 momentum: float = 0.1):
+        self.device = torch.device(device)
+        self.last_stride, self.layers, self.grad_scale, self.momentum = last_stride, layers, float(grad_scale), momentum
+        self._zero_bias = torch.zeros(2048, device=self.device)
+        self._ws_bn = None
+        self._ws_wg = None
+        self.saved: List[_Saved] = []
+        self.launches = 0
+
+    # ---------------------------------------------------------------- helpers
+    def _bn_ws(self, rows, c):
+        need = N.lib().ctl_bn_workspace_bytes(rows, c)
+        if self._ws_bn is None or self._ws_bn.numel() < need:
+            self._ws_bn = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws_bn
+
+    def _conv(self, a, n, h, w, wf, cout, k, stride, residual=None):
+        cin = a.shape[-1]
+        pad = 1 if k == 3 else 0
+        ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+        out = torch.empty(n, ho, wo, cout, dtype=torch.float16, device=self.device)
+        N.check(N.lib().ctl_conv2d_nhwc_f16(a.data_ptr(), n, h, w, cin, wf.data_ptr(), self._zero_bias.data_ptr(),
+                                            N.ptr(residual), out.data_ptr(), cout, k, stride, 0, 0, N.stream_ptr()))
+        self.launches += 1
+        return out, ho, wo
+
+    def _conv_bn(self, a, n, h, w, params, conv, bn, k, stride, relu, residual=None):
+        wt = params[conv + ".weight"]
+        cout = wt.shape[0]
+        wf = wt.detach().permute(0, 2, 3, 1).contiguous().half()  # forward operand [Cout][k][k][Cin]
+        y, ho, wo = self._conv(a, n, h, w, wf, cout, k, stride)
+        rows = n * ho * wo
+        z = torch.empty_like(y)
+        mean = torch.empty(cout, device=self.device)
+        invstd = torch.empty(cout, device=self.device)
+        ws = self._bn_ws(rows, cout)
+        rm, rv = params.get(bn + ".running_mean"), params.get(bn + ".running_var")
+        N.check(N.lib().ctl_bn_train_forward_nhwc_f16(
+            y.data_ptr(), rows, cout, params[bn + ".weight"].data_ptr(), params[bn + ".bias"].data_ptr(), BN_EPS,
+            self.momentum, N.ptr(rm), N.ptr(rv), N.ptr(residual), int(relu), ws.data_ptr(), ws.numel(), mean.data_ptr(),
+            invstd.data_ptr(), z.data_ptr(), N.stream_ptr()))
+        self.launches += 3
+        s = _Saved()
+        s.a, s.y, s.z, s.mean, s.invstd = a, y, z, mean, invstd
+        s.shape_in, s.shape_out, s.conv, s.bn, s.k, s.stride, s.relu = (n, h, w), (n, ho, wo), conv, bn, k, stride, relu
+        self.saved.append(s)
+        return z, ho, wo, s
+
+    # ---------------------------------------------------------------- forward
+    def forward(self, x: torch.Tensor, params: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """x: [B, 3, H, W] fp32 NCHW on the device -> global_feat [B, 2048] fp32; keeps what backward needs."""
+        N.require_cuda(x)
+        x = x.float().contiguous()
+        n, _, H, W = x.shape
+        L = N.lib()
+        self.saved, self.launches = [], 0
+        self._params = params
+        self._x = x
+        with torch.cuda.device(self.device):
+            # stem: raw 7x7/2 conv (tensor-core stem, zero bias, no ReLU) -> BN (no ReLU, resnet.py:125) -> max-pool
+            w0 = params["conv1.weight"].detach()
+            wk = torch.zeros(64, 21, 8, device=self.device)
+            wk[:, :, :7] = w0.reshape(64, 21, 7)
+            stem_w = torch.cat((wk.reshape(64, 168), torch.zeros(64, 24, device=self.device)), 1).half().contiguous()
+            h, w = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+            y0 = torch.empty(n, h, w, 64, dtype=torch.float16, device=self.device)
+            N.check(L.ctl_stem_conv7x7_tc(x.data_ptr(), n, H, W, stem_w.data_ptr(), self._zero_bias.data_ptr(), 0,
+                                          y0.data_ptr(), N.stream_ptr()))
+            rows = n * h * w
+            z0 = torch.empty_like(y0)
+            m0, i0 = torch.empty(64, device=self.device), torch.empty(64, device=self.device)
+            ws = self._bn_ws(rows, 64)
+            N.check(L.ctl_bn_train_forward_nhwc_f16(
+                y0.data_ptr(), rows, 64, params["bn1.weight"].data_ptr(), params["bn1.bias"].data_ptr(), BN_EPS,
+                self.momentum, N.ptr(params.get("bn1.running_mean")), N.ptr(params.get("bn1.running_var")), None, 0,
+                ws.data_ptr(), ws.numel(), m0.data_ptr(), i0.data_ptr(), z0.data_ptr(), N.stream_ptr()))
+            hp, wp = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+            a = torch.empty(n, hp, wp, 64, dtype=torch.float16, device=self.device)
+            N.check(L.ctl_maxpool3x3s2_nhwc_f16(z0.data_ptr(), n, h, w, 64, a.data_ptr(), N.stream_ptr()))
+            self.launches += 5
+            self._stem = (y0, z0, m0, i0, (n, H, W, h, w, hp, wp))
+            h, w = hp, wp
+            self._blocks = []
+            for li, (planes, nblk) in enumerate(zip((64, 128, 256, 512), self.layers), start=1):
+                stride0 = 1 if li == 1 else (self.last_stride if li == 4 else 2)
+                for bi in range(nblk):
+                    p = f"layer{li}.{bi}"
+                    stride = stride0 if bi == 0 else 1
+                    o1, h1, w1, s1 = self._conv_bn(a, n, h, w, params, p + ".conv1", p + ".bn1", 1, 1, True)
+                    o2, h2, w2, s2 = self._conv_bn(o1, n, h1, w1, params, p + ".conv2", p + ".bn2", 3, stride, True)
+                    sd = None
+                    res = a
+                    if bi == 0:
+                        res, _, _, sd = self._conv_bn(a, n, h, w, params, p + ".downsample.0", p + ".downsample.1", 1,
+                                                      stride, False)
+                    a, h, w, s3 = self._conv_bn(o2, n, h2, w2, params, p + ".conv3", p + ".bn3", 1, 1, True, residual=res)
+                    self._blocks.append((s1, s2, s3, sd))
+            c = a.shape[-1]
+            feat = torch.empty(n, c, dtype=torch.float32, device=self.device)
+            N.check(L.ctl_gap_bn_nhwc_f16(a.data_ptr(), n, h * w, c, None, None, feat.data_ptr(), None, N.stream_ptr()))
+            self.launches += 1
+            self._last = (n, h, w, c)
+        return feat
+
+    # ---------------------------------------------------------------- backward
+    def _bn_bwd(self, s: _Saved, dz, relu_mask: bool, params, grads):
+        n, ho, wo = s.shape_out
+        c = s.y.shape[-1]
+        rows = n * ho * wo
+        dg, db = torch.empty(c, device=self.device), torch.empty(c, device=self.device)
+        dy = torch.empty_like(s.y)
+        ws = self._bn_ws(rows, c)
+        N.check(N.lib().ctl_bn_train_backward_nhwc_f16(
+            dz.data_ptr(), s.z.data_ptr() if relu_mask else None, s.y.data_ptr(), rows, c,
+            params[s.bn + ".weight"].data_ptr(), s.mean.data_ptr(), s.invstd.data_ptr(), 1.0 / self.grad_scale,
+            ws.data_ptr(), ws.numel(), dz.data_ptr() if relu_mask else None, dg.data_ptr(), db.data_ptr(), dy.data_ptr(),
+            N.stream_ptr()))
+        self.launches += 3
+        grads[s.bn + ".weight"], grads[s.bn + ".bias"] = dg, db
+        return dy  # (dz now holds g = dz * mask when relu_mask)
+
+    def _wgrad(self, a, shape_in, dy, cout, k, stride):
+        n, h, w = shape_in
+        cin = a.shape[-1]
+        L = N.lib()
+        need = L.ctl_conv2d_wgrad_workspace_bytes(n, h, w, cin, cout, k, stride)
+        if self._ws_wg is None or self._ws_wg.numel() < need:
+            self._ws_wg = torch.empty(need, dtype=torch.uint8, device=self.device)
+        dw = torch.empty(cout, k, k, cin, device=self.device)
+        N.check(L.ctl_conv2d_wgrad_nhwc_f16(a.data_ptr(), n, h, w, cin, dy.data_ptr(), cout, k, stride,
+                                            self._ws_wg.data_ptr(), self._ws_wg.numel(), dw.data_ptr(), N.stream_ptr()))
+        self.launches += 2
+        return dw
+
+    def _conv_bwd(self, s: _Saved, dy, params, grads, need_dx=True, residual=None):
+        """weight gradient of s.conv and (optionally) the data gradient w.r.t. s.a (+ residual)."""
+        wt = params[s.conv + ".weight"].detach()
+        cout, cin, k = wt.shape[0], wt.shape[1], s.k
+        dw = self._wgrad(s.a, s.shape_in, dy, cout, k, s.stride)
+        grads[s.conv + ".weight"] = dw.permute(0, 3, 1, 2).mul(1.0 / self.grad_scale)  # -> [Cout, Cin, k, k]
+        if not need_dx:
+            return None
+        n, h, w = s.shape_in
+        _, ho, wo = s.shape_out
+        wd = wt.flip(2, 3).permute(1, 2, 3, 0).contiguous().half()  # [Cin][k][k][Cout]: the transposed convolution
+        L = N.lib()
+        if s.stride == 1:
+            dx, _, _ = self._conv(dy, n, ho, wo, wd, cin, k, 1, residual=residual)
+            return dx
+        if k == 1:
+            low, _, _ = self._conv(dy, n, ho, wo, wd, cin, 1, 1)
+            dx = torch.empty(n, h, w, cin, dtype=torch.float16, device=self.device)
+            N.check(L.ctl_upsample2_zero_nhwc_f16(low.data_ptr(), n, ho, wo, cin, N.ptr(residual), dx.data_ptr(),
+                                                  N.stream_ptr()))
+            self.launches += 1
+            return dx
+        up = torch.empty(n, h, w, cout, dtype=torch.float16, device=self.device)
+        N.check(L.ctl_upsample2_zero_nhwc_f16(dy.data_ptr(), n, ho, wo, cout, None, up.data_ptr(), N.stream_ptr()))
+        self.launches += 1
+        dx, _, _ = self._conv(up, n, h, w, wd, cin, 3, 1, residual=residual)
+        return dx
+
+    def backward(self, dfeat: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """dfeat: [B, 2048] fp32 = dLoss/dglobal_feat -> {param name: fp32 gradient in the reference's layout}."""
+        params, grads = self._params, {}
+        L = N.lib()
+        n, h, w, c = self._last
+        with torch.cuda.device(self.device):
+            dz = torch.empty(n, h, w, c, dtype=torch.float16, device=self.device)
+            dfeat = dfeat.float().contiguous()
+            N.check(L.ctl_gap_backward_nhwc_f16(dfeat.data_ptr(), n, h * w, c, self.grad_scale / (h * w), dz.data_ptr(),
+                                                N.stream_ptr()))
+            self.launches += 1
+            for s1, s2, s3, sd in reversed(self._blocks):
+                dy3 = self._bn_bwd(s3, dz, True, params, grads)  # dz becomes g3, the shortcut's gradient
+                g3 = dz
+                d2 = self._conv_bwd(s3, dy3, params, grads)
+                dy2 = self._bn_bwd(s2, d2, True, params, grads)
+                d1 = self._conv_bwd(s2, dy2, params, grads)
+                dy1 = self._bn_bwd(s1, d1, True, params, grads)
+                if sd is not None:
+                    dyd = self._bn_bwd(sd, g3, False, params, grads)
+                    shortcut = self._conv_bwd(sd, dyd, params, grads)
+                else:
+                    shortcut = g3
+                dz = self._conv_bwd(s1, dy1, params, grads, residual=shortcut)
+            # stem: max-pool -> BN (no ReLU) -> 7x7 weight gradient through the im2col GEMM
+            y0, z0, m0, i0, (n, H, W, h, w, hp, wp) = self._stem
+            dz0 = torch.empty_like(z0)
+            N.check(L.ctl_maxpool3x3s2_backward_nhwc_f16(z0.data_ptr(), dz.data_ptr(), n, h, w, 64, dz0.data_ptr(),
+                                                         N.stream_ptr()))
+            st = _Saved()
+            st.y, st.z, st.mean, st.invstd, st.bn, st.shape_out = y0, z0, m0, i0, "bn1", (n, h, w)
+            dy0 = self._bn_bwd(st, dz0, False, params, grads)
+            col = torch.empty(n, h, w, 192, dtype=torch.float16, device=self.device)
+            N.check(L.ctl_stem_im2col_f16(self._x.data_ptr(), n, H, W, col.data_ptr(), N.stream_ptr()))
+            self.launches += 2
+            dw = self._wgrad(col, (n, h, w), dy0, 64, 1, 1)  # [64][1][1][192]
+            grads["conv1.weight"] = dw.reshape(64, 192)[:, :168].reshape(64, 3, 7, 8)[..., :7].mul(1.0 / self.grad_scale)
+        self.saved, self._blocks = [], []
+        return grads

@@ -2,7 +2,9 @@
 
 Parameters live in reference-layout modules (`self.base.*`); eval-mode forward runs the B200
 engine, whose packed operands are rebuilt lazily whenever the parameters change
-(`invalidate()`; call it after `opt.step()` / `load_state_dict`).
+(`invalidate()`; call it after `opt.step()` / `load_state_dict`).  Train-mode forward (ResNet-50) runs the
+training engine (batch-statistics BatchNorm, running statistics updated in place) and is differentiable:
+`global_feat.backward()` fills `.grad` of every trunk parameter through the B200 backward kernels.
 """
 from __future__ import annotations
 
@@ -10,10 +12,28 @@ import torch
 from torch import nn
 
 from .backbones.engine import TrunkEngine
+from .backbones.engine_train import TrunkTrainer
 from .backbones.resnet import ResNetParams
 
 _LAYERS = {"resnet50": ((3, 4, 6, 3), False), "resnet101": ((3, 4, 23, 3), False), "resnet152": ((3, 8, 36, 3), False),
            "resnet50_ibn_a": ((3, 4, 6, 3), True), "resnet101_ibn_a": ((3, 4, 23, 3), True)}
+
+
+class _TrunkTrainFn(torch.autograd.Function):
+    """global_feat = trunk(x; parameters) with the B200 training engine; backward returns the parameter gradients
+    (the input crops get no gradient, like the reference's data tensors)."""
+
+    @staticmethod
+    def forward(ctx, x, trainer, names, buffers, *tensors):
+        params = dict(zip(names, tensors))
+        params.update(buffers)
+        ctx.trainer, ctx.names = trainer, names
+        return trainer.forward(x, params)
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        grads = ctx.trainer.backward(dfeat)
+        return (None, None, None, None) + tuple(grads.get(n) for n in ctx.names)
 
 
 class Baseline(nn.Module):
@@ -34,6 +54,7 @@ class Baseline(nn.Module):
         self.gap = nn.AdaptiveAvgPool2d(1)
         self._engine = None
         self._engine_key = None
+        self._trainer = None
 
     def invalidate(self):
         self._engine = None
@@ -55,9 +76,21 @@ class Baseline(nn.Module):
     def forward(self, x):
         """modelling/baseline.py:91-96.  base_out is returned in the reference's NCHW view."""
         if self.training:
-            raise NotImplementedError(
-                "training-mode trunk (batch-statistics BatchNorm + dgrad/wgrad kernels) is not built yet; "
-                "only the eval forward runs on the B200 engine (DESIGN.md section 7)")
+            if self.base.ibn:
+                raise NotImplementedError("train-mode IBN-a trunk (InstanceNorm training kernels) is not built; "
+                                          "resnet50/101/152 train on the B200 engine (DESIGN.md)")
+            dev = next(self.base.parameters()).device
+            if self._trainer is None or self._trainer.device != dev:
+                self._trainer = TrunkTrainer(dev, last_stride=self.base.last_stride, layers=self.base.layers_cfg)
+            names = [k for k, _ in self.base.named_parameters()]
+            tensors = [v for _, v in self.base.named_parameters()]
+            buffers = {k: v for k, v in self.base.named_buffers() if "running" in k}
+            feat = _TrunkTrainFn.apply(x, self._trainer, names, buffers, *tensors)
+            self.invalidate()  # running statistics changed: the eval engine must refold them
+            for k, v in self.base.named_buffers():
+                if k.endswith("num_batches_tracked"):
+                    v += 1
+            return None, feat  # callers use only global_feat (train_ctl_model.py:55); base_out is not kept
         out = self.engine().forward(x, want_base=True)
         return out["base_out_nhwc"].permute(0, 3, 1, 2), out["global_feat"]
 

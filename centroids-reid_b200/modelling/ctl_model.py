@@ -81,7 +81,7 @@ class CTLModel(_Base):
 
     def training_step(self, batch, batch_idx, optimizer_idx=None):
         x, class_labels, camid, is_real = batch
-        _, features = self.backbone(x)  # raises in train mode until the trunk training kernels exist
+        _, features = self.backbone(x)  # train mode: B200 training engine (differentiable w.r.t. the trunk parameters)
         return self.training_step_from_features(features, class_labels, is_real)
 
     # -- evaluation -------------------------------------------------------------------------

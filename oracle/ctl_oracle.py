@@ -568,6 +568,77 @@ def trunk_forward_fp16sim(x, sd, last_stride=1, ibn=False, layers=R50_LAYERS):
     return x, x.mean(dim=(2, 3))
 
 
+class _RoundHalfSTE(torch.autograd.Function):
+    """fp16 storage rounding in the forward, identity in the backward (the engine's backward is checked against
+    the exact derivative of the rounded forward)."""
+
+    @staticmethod
+    def forward(ctx, t):
+        return t.half().to(t.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def trunk_train_fp16sim(x, sd, dfeat=None, last_stride=1, layers=R50_LAYERS, momentum=0.1, forced=None):
+    """Train-mode trunk (ResNet.forward resnet.py:122-133 with BatchNorm2d batch statistics, Bottleneck.forward
+    :67-87) in float64 with the B200 training path's rounding points: fp16 crops and conv weights, every stored
+    activation (conv output, BN/ReLU output) rounded to fp16, statistics / BN arithmetic / GAP in full precision.
+    Returns (global_feat, grads, running) where grads maps state_dict names -> d(sum(global_feat * dfeat))/d(param)
+    and running holds the updated running statistics.  ResNet-50 family only (no IBN).
+
+    `forced`: optional list of (y, z) NCHW tensors, one per conv+BN in execution order (stem, then per block conv1,
+    conv2, [downsample], conv3): the VALUES of the stored activations are replaced by these (the engine's own fp16
+    tensors) while the derivative still flows through this function's arithmetic.  ReLU masks are discontinuous,
+    so two correct fp16 forwards that differ in the last bit produce visibly different gradients; teacher-forcing
+    the stored activations isolates the backward arithmetic from that effect."""
+    eps = 1e-5
+    q = _RoundHalfSTE.apply
+    P = {k: v.detach().double().requires_grad_(True) for k, v in sd.items()
+         if v.is_floating_point() and "running" not in k}
+    running = {}
+    it = iter(forced) if forced is not None else None
+
+    def force(t, val):
+        return t if val is None else val.double() + (t - t.detach())
+
+    def conv_bn(a, conv, name, k, stride, res=None, relu=True):
+        fy, fz = next(it) if it is not None else (None, None)
+        y = force(q(F.conv2d(a, q(P[conv + ".weight"]), None, stride, k // 2)), fy)
+        mean = y.mean(dim=(0, 2, 3))
+        var = y.var(dim=(0, 2, 3), unbiased=False)
+        cnt = y.numel() / y.shape[1]
+        running[name + ".running_mean"] = (1 - momentum) * sd[name + ".running_mean"].double() + momentum * mean.detach()
+        running[name + ".running_var"] = ((1 - momentum) * sd[name + ".running_var"].double()
+                                          + momentum * var.detach() * cnt / max(cnt - 1, 1))
+        z = ((y - mean[None, :, None, None]) / torch.sqrt(var + eps)[None, :, None, None]
+             * P[name + ".weight"][None, :, None, None] + P[name + ".bias"][None, :, None, None])
+        if res is not None:
+            z = z + res
+        return force(q(F.relu(z) if relu else z), fz)
+
+    a = conv_bn(q(x.double()), "conv1", "bn1", 7, 2, relu=False)  # resnet.py:125: no ReLU after the stem
+    a = F.max_pool2d(a, 3, 2, 1)
+    for li, (planes, nblk) in enumerate(zip((64, 128, 256, 512), layers), start=1):
+        stride0 = 1 if li == 1 else (last_stride if li == 4 else 2)
+        for bi in range(nblk):
+            p = f"layer{li}.{bi}"
+            stride = stride0 if bi == 0 else 1
+            o1 = conv_bn(a, p + ".conv1", p + ".bn1", 1, 1)
+            o2 = conv_bn(o1, p + ".conv2", p + ".bn2", 3, stride)
+            res = a
+            if bi == 0:
+                res = conv_bn(a, p + ".downsample.0", p + ".downsample.1", 1, stride, relu=False)
+            a = conv_bn(o2, p + ".conv3", p + ".bn3", 1, 1, res=res)
+    feat = a.mean(dim=(2, 3))
+    grads = None
+    if dfeat is not None:
+        (feat * dfeat.double()).sum().backward()
+        grads = {k: v.grad for k, v in P.items()}
+    return feat.detach(), grads, running
+
+
 # --------------------------------------------------------------------------------------
 # synthetic workloads shared by tests / bench (SURVEY 8d "Synthetic inputs")
 # --------------------------------------------------------------------------------------

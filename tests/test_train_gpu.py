@@ -158,3 +158,82 @@ def test_pool_gap_upsample_im2col_backward_helpers():
     ref[..., :7] = unf
     ref = torch.cat((ref.reshape(2 * ho * wo, 168), torch.zeros(2 * ho * wo, 24)), 1).half()
     assert torch.equal(col.cpu(), ref)
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).abs().max()) / (float(b.double().abs().max()) + 1e-30)
+
+
+def test_trunk_train_step_against_float64_autograd():
+    """Train-mode ResNet-50 forward + full backward on the B200 kernels vs float64 autograd of the same network
+    with the engine's fp16 rounding points (oracle.trunk_train_fp16sim).
+
+    (1) independent forward: features within 2e-2; gradients agree in direction and size (ReLU masks are
+        discontinuous, so last-bit differences between two correct fp16 forwards show up as ~10 % max-norm
+        gradient noise: cosine >= 0.98, norm within 3 %);
+    (2) teacher-forced: the oracle differentiates through the ENGINE's stored activations, which isolates the
+        backward arithmetic: every parameter gradient within 2e-2 (max-norm relative)."""
+    from oracle import ctl_oracle as O
+    from ctl_b200.modelling.backbones.engine_train import TrunkTrainer
+
+    sd = O.make_trunk_state(seed=7)
+    g = torch.Generator().manual_seed(1)
+    n, H, W = 8, 128, 64
+    x = torch.randn(n, 3, H, W, generator=g)
+    dfeat = torch.randn(n, 2048, generator=g) * 1e-3
+    feat_o, grads_o, running_o = O.trunk_train_fp16sim(x, sd, dfeat)
+
+    params = {k: v.clone().cuda() for k, v in sd.items() if v.is_floating_point()}
+    tr = TrunkTrainer("cuda", grad_scale=4096.0)
+    feat = tr.forward(x.cuda(), params)
+    torch.cuda.synchronize()
+    assert _rel(feat.cpu(), feat_o) <= 2e-2
+    nchw = lambda t: t.cpu().float().permute(0, 3, 1, 2)  # noqa: E731
+    forced = [(nchw(tr._stem[0]), nchw(tr._stem[1]))] + [(nchw(s.y), nchw(s.z)) for s in tr.saved]
+    grads = tr.backward(dfeat.cuda())
+    torch.cuda.synchronize()
+    assert set(grads.keys()) == set(grads_o.keys())
+    gscale = max(float(v.abs().max()) for v in grads_o.values())
+    for k, go in grads_o.items():
+        gk = grads[k].cpu().double()
+        assert gk.shape == go.shape and torch.isfinite(gk).all(), k
+        if float(go.abs().max()) < 1e-6 * gscale:  # stem bn1.bias: exactly cancelled by the next batch-stat BN
+            assert float(gk.abs().max()) <= 1e-3 * gscale, k
+            continue
+        cos = float((gk * go).sum() / (gk.norm() * go.norm()))
+        assert cos >= 0.98 and abs(float(gk.norm() / go.norm()) - 1) <= 3e-2, (k, cos)
+    for k, v in running_o.items():
+        assert _rel(params[k].cpu(), v) <= 2e-2, k
+    # (2) teacher-forced backward check
+    feat_f, grads_f, _ = O.trunk_train_fp16sim(x, sd, dfeat, forced=forced)
+    assert _rel(feat.cpu(), feat_f) <= 1e-5
+    bad = {}
+    for k, go in grads_f.items():
+        if float(go.abs().max()) < 1e-6 * gscale:
+            continue
+        r = _rel(grads[k].cpu(), go)
+        if r > 2e-2:
+            bad[k] = r
+    assert not bad, f"gradient mismatch (max-norm relative): {sorted(bad.items(), key=lambda t: -t[1])[:8]}"
+
+
+def test_baseline_train_mode_is_differentiable():
+    from oracle import ctl_oracle as O
+    from ctl_b200.modelling.baseline import Baseline
+    from test_modules_gpu import _cfg
+
+    model = Baseline(_cfg()).cuda().train()
+    model.base.load_state_dict(O.make_trunk_state(seed=2))
+    x = torch.randn(4, 3, 64, 32, generator=torch.Generator().manual_seed(4)).cuda()
+    rm0 = model.base.bn1.running_mean.clone()
+    base_out, feat = model(x)
+    assert base_out is None and feat.shape == (4, 2048) and feat.requires_grad
+    (feat * 1e-3).sum().backward()
+    names = [k for k, _ in model.base.named_parameters()]
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.base.parameters()), names
+    assert float(model.base.layer4[2].conv3.weight.grad.abs().max()) > 0 and float(model.base.conv1.weight.grad.abs().max()) > 0
+    assert not torch.equal(rm0, model.base.bn1.running_mean) and int(model.base.bn1.num_batches_tracked) == 1
+    model.eval()
+    with torch.no_grad():
+        _, f2 = model(x)  # eval engine refolds the updated running statistics
+    assert torch.isfinite(f2).all()
