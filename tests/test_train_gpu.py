@@ -237,3 +237,38 @@ def test_baseline_train_mode_is_differentiable():
     with torch.no_grad():
         _, f2 = model(x)  # eval engine refolds the updated running statistics
     assert torch.isfinite(f2).all()
+
+
+def test_ctl_training_step_end_to_end():
+    """CTLModel.training_step (train_ctl_model.py:38-152): train-mode trunk -> CTL / center / xent / query-triplet
+    losses -> backward through the fused loss step AND the trunk, on a P x K batch with padded (mock) rows."""
+    from oracle import ctl_oracle as O
+    from ctl_b200.modelling.ctl_model import CTLModel
+    from test_modules_gpu import _cfg
+
+    torch.manual_seed(0)
+    P_, K_ = 4, 4
+    model = CTLModel(_cfg(), num_classes=16, num_query=4).cuda().train()
+    sd = O.make_trunk_state(seed=9)
+    model.backbone.base.load_state_dict(sd)
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(P_ * K_, 3, 64, 32, generator=g)
+    labels = torch.arange(P_).repeat_interleave(K_) + 3
+    is_real = torch.ones(P_ * K_, dtype=torch.bool)
+    is_real[K_ - 1] = False  # last slot of the first pid is a mock image (all-zero crop, datasets/bases.py:378-391)
+    x[K_ - 1] = 0
+    out = model.training_step((x.cuda(), labels.cuda(), torch.zeros(P_ * K_, dtype=torch.long).cuda(), is_real.cuda()), 0)
+    loss = out["loss"]
+    assert torch.isfinite(loss)
+    loss.backward()
+    for name, p in model.named_parameters():
+        if name == "bn.bias":  # frozen in the reference (bases.py:83-84)
+            continue
+        assert p.grad is not None and torch.isfinite(p.grad).all(), name
+    assert float(model.backbone.base.layer1[0].conv1.weight.grad.abs().max()) > 0
+    # loss value against the oracle: fp16-sim train-mode features -> the reference's loss arithmetic
+    feat_o, _, _ = O.trunk_train_fp16sim(x, sd)
+    hs = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    ref = O.ctl_step_losses(feat_o.float(), labels, is_real, K_, hs["center_loss.centers"], hs["bn.weight"], hs["bn.bias"],
+                            hs["fc_query.weight"])
+    np.testing.assert_allclose(float(loss), float(ref["total"]), rtol=5e-3)
