@@ -285,6 +285,58 @@ def conv_traffic():
         return None
 
 
+def run_train_step(local, steps=5, warmup=2):
+    """BASELINE config 2: one CTL training step (ResNet-50 256x128, 16 ids x 16 instances, fp16 activations):
+    train-mode trunk forward (batch-stat BN) -> fused CTL/center/xent/triplet loss step -> backward through the
+    loss and the trunk (all parameter gradients).  Device-timed with CUDA events; no optimizer step (solver/build.py
+    is outside the hot path)."""
+    import ctl_b200  # noqa: F401
+    from ctl_b200.modelling.ctl_model import CTLModel
+
+    dev = torch.device("cuda", local)
+
+    class _C(dict):
+        __getattr__ = dict.__getitem__
+
+    if True:
+        cfg = _C(MODEL=_C(NAME="resnet50", LAST_STRIDE=1, PRETRAINED=False, PRETRAIN_PATH="", BACKBONE_EMB_SIZE=2048,
+                          USE_CENTROIDS=False, KEEP_CAMID_CENTROIDS=True, RESUME_TRAINING=False),
+                 SOLVER=_C(MARGIN=0.5, DISTANCE_FUNC="euclidean", CENTER_LOSS_WEIGHT=5e-4, QUERY_XENT_WEIGHT=1.0,
+                           QUERY_CONTRASTIVE_WEIGHT=1.0, CENTROID_CONTRASTIVE_WEIGHT=1.0),
+                 DATALOADER=_C(NUM_INSTANCE=16), TEST=_C(FEAT_NORM=True, ONLY_TEST=False, VISUALIZE="no"),
+                 USE_MIXED_PRECISION=True)
+    torch.manual_seed(0)
+    model = CTLModel(cfg, num_classes=751, num_query=0).to(dev).train()
+    P, K = 16, 16
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(P * K, 3, H, W, generator=g).to(dev)
+    labels = torch.arange(P).repeat_interleave(K).to(dev)
+    cam = torch.zeros(P * K, dtype=torch.long, device=dev)
+    is_real = torch.ones(P * K, dtype=torch.bool, device=dev)
+
+    def step():
+        for p_ in model.parameters():
+            p_.grad = None
+        out = model.training_step((x, labels, cam, is_real), 0)
+        out["loss"].backward()
+        return out["loss"]
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"metric": "CTL training step images/sec (resnet50 256x128, 16 ids x 16 instances, fwd+loss+bwd)",
+            "value": P * K / ms * 1e3, "unit": "images/s", "ms_per_step": ms, "steps": steps, "loss": float(loss),
+            "tflops": 3 * P * K * GFLOP_PER_IMG / ms, "note": "3 x forward FLOPs per image; optimizer step not included",
+            "peak_mem_gib": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+
+
 # ----------------------------------------------------------------------------------------------
 # retrieval workload (metric M2)
 # ----------------------------------------------------------------------------------------------
@@ -471,6 +523,7 @@ def main():
                     "clocks": clocks}
             if rank == 0 and not args.no_secondary and world == 1:
                 line["retrieval"] = run_retrieval(args, world, rank, local, steps=5, warmup=3)
+                line["train_step"] = run_train_step(local)
                 v, dt = cpu_embed(64, 2)
                 line["cpu_baseline"] = {"value": v, "unit": "embeddings/s", "cores": _host_threads(), "kind": "port",
                                         "sample": f"128 crops (2 x 64) through oracle.embed_forward, torch-CPU fp32, {dt:.1f} s"}
