@@ -267,7 +267,7 @@ static int wgrad_plan(int n, int h, int w, int cin, int cout, int ksize, int str
 //    fixed order in double precision (deterministic, no atomics).
 // =======================================================================================
 static constexpr int BN_THREADS = 256;
-static constexpr int BN_MAX_BLOCKS = 1184;  // 148 SMs x 8
+static constexpr int BN_MAX_BLOCKS = 592;  // 148 SMs x 4
 
 struct BnGeom {
   int groups;         // C / 8
@@ -354,6 +354,29 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const __half* __re
 
 // finalize of the forward: batch mean / biased variance -> invstd, scale = gamma*invstd, shift = beta - mean*scale;
 // running statistics updated like torch (momentum, unbiased variance).
+// Sum of the per-block partials of 32 channels: 8 warps split the block index (stride 8), partial sums are combined in
+// a fixed order (deterministic).  Returns the two totals of channel `c` to the threads with part == 0.
+__device__ __forceinline__ void bn_sum_partials(const float* __restrict__ part, int blocks, int C, int c, int part_id,
+                                                double (*sh)[2][32], double& s0, double& s1) {
+  double a = 0.0, b = 0.0;
+  if (c < C)
+    for (int blk = part_id; blk < blocks; blk += 8) {
+      a += (double)part[(size_t)blk * 2 * C + c];
+      b += (double)part[(size_t)blk * 2 * C + C + c];
+    }
+  sh[part_id][0][threadIdx.x & 31] = a;
+  sh[part_id][1][threadIdx.x & 31] = b;
+  __syncthreads();
+  s0 = s1 = 0.0;
+  if (part_id == 0)
+    for (int q = 0; q < 8; ++q) {
+      s0 += sh[q][0][threadIdx.x & 31];
+      s1 += sh[q][1][threadIdx.x & 31];
+    }
+}
+
+// finalize of the forward: batch mean / biased variance -> invstd, scale = gamma*invstd, shift = beta - mean*scale;
+// running statistics updated like torch (momentum, unbiased variance).  grid = C / 32 blocks of 256 threads.
 __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ part, int blocks, int C, double count,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           float eps, float momentum, float* __restrict__ running_mean,
@@ -362,13 +385,11 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
                                                           float* __restrict__ shift) {
   pdl_launch_dependents();
   pdl_wait();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, ss = 0.0;
-  for (int b = 0; b < blocks; ++b) {
-    s += (double)part[(size_t)b * 2 * C + c];
-    ss += (double)part[(size_t)b * 2 * C + C + c];
-  }
+  __shared__ double sh[8][2][32];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), part_id = threadIdx.x >> 5;
+  double s, ss;
+  bn_sum_partials(part, blocks, C, c, part_id, sh, s, ss);
+  if (part_id != 0 || c >= C) return;
   const double m = s / count;
   double var = ss / count - m * m;
   if (var < 0.0) var = 0.0;
@@ -385,36 +406,39 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
   }
 }
 
-// z = [relu](y * scale + shift [+ residual]) -> fp16
-__global__ void __launch_bounds__(256) bn_apply_kernel(const __half* __restrict__ y, long long rows, int C,
-                                                       const float* __restrict__ scale, const float* __restrict__ shift,
-                                                       const __half* __restrict__ residual, int relu,
-                                                       __half* __restrict__ out) {
+// z = [relu](y * scale + shift [+ residual]) -> fp16.  A thread keeps the coefficients of its 8 channels in registers
+// and walks rows (blockDim = groups * lanes, like the statistics kernels).
+__global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const __half* __restrict__ y, long long rows, int C, int lanes,
+                                                              const float* __restrict__ scale, const float* __restrict__ shift,
+                                                              const __half* __restrict__ residual, int relu,
+                                                              __half* __restrict__ out) {
   pdl_launch_dependents();
   pdl_wait();
   const int groups = C / 8;
-  const long long total = rows * groups;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % groups);
-    float f[8], sc[8], sh[8];
-    unpack8(*reinterpret_cast<const uint4*>(y + i * 8), f);
-    *reinterpret_cast<float4*>(&sc[0]) = *reinterpret_cast<const float4*>(scale + g * 8);
-    *reinterpret_cast<float4*>(&sc[4]) = *reinterpret_cast<const float4*>(scale + g * 8 + 4);
-    *reinterpret_cast<float4*>(&sh[0]) = *reinterpret_cast<const float4*>(shift + g * 8);
-    *reinterpret_cast<float4*>(&sh[4]) = *reinterpret_cast<const float4*>(shift + g * 8 + 4);
+  const int group = threadIdx.x % groups, lane_row = threadIdx.x / groups;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    sc[k] = scale[group * 8 + k];
+    sh[k] = shift[group * 8 + k];
+  }
+  for (long long r = (long long)blockIdx.x * lanes + lane_row; r < rows; r += (long long)gridDim.x * lanes) {
+    const size_t off = (size_t)r * C + group * 8;
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(y + off), f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], sc[k], sh[k]);
     if (residual) {
-      float r[8];
-      unpack8(*reinterpret_cast<const uint4*>(residual + i * 8), r);
+      float rr[8];
+      unpack8(*reinterpret_cast<const uint4*>(residual + off), rr);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) f[k] += r[k];
+      for (int k = 0; k < 8; ++k) f[k] += rr[k];
     }
     if (relu) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
     }
-    *reinterpret_cast<uint4*>(out + i * 8) = pack8(f);
+    *reinterpret_cast<uint4*>(out + off) = pack8(f);
   }
 }
 
@@ -471,13 +495,11 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
                                                               float* __restrict__ coef) {
   pdl_launch_dependents();
   pdl_wait();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double sg = 0.0, sgx = 0.0;
-  for (int b = 0; b < blocks; ++b) {
-    sg += (double)part[(size_t)b * 2 * C + c];
-    sgx += (double)part[(size_t)b * 2 * C + C + c];
-  }
+  __shared__ double sh[8][2][32];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), part_id = threadIdx.x >> 5;
+  double sg, sgx;
+  bn_sum_partials(part, blocks, C, c, part_id, sh, sg, sgx);
+  if (part_id != 0 || c >= C) return;
   dbeta[c] = (float)sg * grad_unscale;
   dgamma[c] = (float)sgx * grad_unscale;
   const double k1 = (double)gamma[c] * invstd[c];
@@ -488,24 +510,28 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
   coef[2 * C + c] = (float)(k1 * ((double)mean[c] * k3 - k2));
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __half* __restrict__ g, const __half* __restrict__ y,
-                                                           long long rows, int C, const float* __restrict__ coef,
-                                                           __half* __restrict__ dy) {
+__global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const __half* __restrict__ g, const __half* __restrict__ y,
+                                                                  long long rows, int C, int lanes,
+                                                                  const float* __restrict__ coef, __half* __restrict__ dy) {
   pdl_launch_dependents();
   pdl_wait();
   const int groups = C / 8;
-  const long long total = rows * groups;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int gi = (int)(i % groups);
-    float gv[8], yv[8], o[8];
-    unpack8(*reinterpret_cast<const uint4*>(g + i * 8), gv);
-    unpack8(*reinterpret_cast<const uint4*>(y + i * 8), yv);
+  const int group = threadIdx.x % groups, lane_row = threadIdx.x / groups;
+  float ca[8], cb[8], cc[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int c = gi * 8 + k;
-      o[k] = fmaf(coef[c], gv[k], fmaf(coef[C + c], yv[k], coef[2 * C + c]));
-    }
-    *reinterpret_cast<uint4*>(dy + i * 8) = pack8(o);
+  for (int k = 0; k < 8; ++k) {
+    ca[k] = coef[group * 8 + k];
+    cb[k] = coef[C + group * 8 + k];
+    cc[k] = coef[2 * C + group * 8 + k];
+  }
+  for (long long r = (long long)blockIdx.x * lanes + lane_row; r < rows; r += (long long)gridDim.x * lanes) {
+    const size_t off = (size_t)r * C + group * 8;
+    float gv[8], yv[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(g + off), gv);
+    unpack8(*reinterpret_cast<const uint4*>(y + off), yv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = fmaf(ca[k], gv[k], fmaf(cb[k], yv[k], cc[k]));
+    *reinterpret_cast<uint4*>(dy + off) = pack8(o);
   }
 }
 
@@ -650,6 +676,9 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
   }
 }
 
+static int row_grid(long long rows, int lanes) {
+  return (int)std::min<long long>((rows + lanes - 1) / lanes, (long long)sm_count() * 8);
+}
 static int ew_grid(long long total) {
   return (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
 }
@@ -768,10 +797,10 @@ int ctl_bn_train_forward_nhwc_f16(const void* y, int64_t rows, int32_t c, const 
   const size_t sm = (size_t)g.lanes * 2 * c * sizeof(float);
   CTL_CUDA(launch_k(bn_stats_kernel, dim3(g.blocks), dim3(BN_THREADS), sm, st, static_cast<const __half*>(y), (long long)rows,
                     (int)c, g.rows_per_block, g.lanes, part));
-  CTL_CUDA(launch_k(bn_finalize_kernel, dim3((c + 255) / 256), dim3(256), 0, st, (const float*)part, g.blocks, (int)c,
+  CTL_CUDA(launch_k(bn_finalize_kernel, dim3((c + 31) / 32), dim3(256), 0, st, (const float*)part, g.blocks, (int)c,
                     (double)rows, gamma, beta, eps, momentum, running_mean, running_var, save_mean, save_invstd, scale, shift));
-  CTL_CUDA(launch_k(bn_apply_kernel, dim3(ew_grid(rows * (c / 8))), dim3(256), 0, st, static_cast<const __half*>(y),
-                    (long long)rows, (int)c, (const float*)scale, (const float*)shift, static_cast<const __half*>(residual),
+  CTL_CUDA(launch_k(bn_apply_kernel, dim3(row_grid(rows, g.lanes)), dim3(BN_THREADS), 0, st, static_cast<const __half*>(y),
+                    (long long)rows, (int)c, g.lanes, (const float*)scale, (const float*)shift, static_cast<const __half*>(residual),
                     (int)relu, static_cast<__half*>(out)));
   return 0;
 }
@@ -792,11 +821,11 @@ int ctl_bn_train_backward_nhwc_f16(const void* dz, const void* z, const void* y,
   CTL_CUDA(launch_k(bn_bwd_reduce_kernel, dim3(g.blocks), dim3(BN_THREADS), sm, st, static_cast<const __half*>(dz),
                     static_cast<const __half*>(z), static_cast<const __half*>(y), (long long)rows, (int)c, g.rows_per_block,
                     g.lanes, save_mean, save_invstd, static_cast<__half*>(g_out), part));
-  CTL_CUDA(launch_k(bn_bwd_finalize_kernel, dim3((c + 255) / 256), dim3(256), 0, st, (const float*)part, g.blocks, (int)c,
+  CTL_CUDA(launch_k(bn_bwd_finalize_kernel, dim3((c + 31) / 32), dim3(256), 0, st, (const float*)part, g.blocks, (int)c,
                     (double)rows, gamma, save_mean, save_invstd, grad_unscale, dgamma, dbeta, coef));
   const __half* gsrc = z ? static_cast<const __half*>(g_out) : static_cast<const __half*>(dz);
-  CTL_CUDA(launch_k(bn_bwd_apply_kernel, dim3(ew_grid(rows * (c / 8))), dim3(256), 0, st, gsrc, static_cast<const __half*>(y),
-                    (long long)rows, (int)c, (const float*)coef, static_cast<__half*>(dy)));
+  CTL_CUDA(launch_k(bn_bwd_apply_kernel, dim3(row_grid(rows, g.lanes)), dim3(BN_THREADS), 0, st, gsrc, static_cast<const __half*>(y),
+                    (long long)rows, (int)c, g.lanes, (const float*)coef, static_cast<__half*>(dy)));
   return 0;
 }
 
