@@ -339,7 +339,23 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const __half* __re
   for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.f;
   if (lane_row < lanes) {
     const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
-    for (long long r = r0 + lane_row; r < r1; r += lanes) {
+    long long r = r0 + lane_row;
+    for (; r + 3LL * lanes < r1; r += 4LL * lanes) {  // four independent 16-byte loads in flight per thread
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(y + (r + (long long)u * lanes) * C + group * 8);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(v[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[0][i] += f[i];
+          acc[1][i] = fmaf(f[i], f[i], acc[1][i]);
+        }
+      }
+    }
+    for (; r < r1; r += lanes) {
       float f[8];
       unpack8(*reinterpret_cast<const uint4*>(y + r * C + group * 8), f);
 #pragma unroll
@@ -613,6 +629,94 @@ __global__ void __launch_bounds__(256) maxpool_backward_kernel(const __half* __r
   }
 }
 
+// Training forward of the pool: also records, per output element, which of the 9 window taps (r*3 + s) held the
+// first maximum (one byte per channel) so that the backward is a 4-window gather instead of 36 loads per pixel.
+__global__ void __launch_bounds__(256) maxpool_arg_kernel(const __half* __restrict__ x, int N, int H, int W, int C, int Ho,
+                                                          int Wo, __half* __restrict__ out, uint2* __restrict__ arg) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int groups = C / 8;
+  const long long total = (long long)N * Ho * Wo * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long long t = i / groups;
+    const int ox = (int)(t % Wo);
+    t /= Wo;
+    const int oy = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    float best[8];
+    unsigned a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      best[k] = -INFINITY;
+      a[k] = 255u;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int yy = 2 * oy - 1 + r;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int s2 = 0; s2 < 3; ++s2) {
+        const int xx = 2 * ox - 1 + s2;
+        if (xx < 0 || xx >= W) continue;
+        float v[8];
+        unpack8(*reinterpret_cast<const uint4*>(x + (((size_t)n * H + yy) * W + xx) * C + g * 8), v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (v[k] > best[k] || a[k] == 255u) {
+            best[k] = v[k];
+            a[k] = r * 3 + s2;
+          }
+      }
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) = pack8(best);
+    arg[i] = make_uint2(a[0] | (a[1] << 8) | (a[2] << 16) | (a[3] << 24), a[4] | (a[5] << 8) | (a[6] << 16) | (a[7] << 24));
+  }
+}
+
+__global__ void __launch_bounds__(256) maxpool_backward_arg_kernel(const uint2* __restrict__ arg, const __half* __restrict__ dy,
+                                                                   int N, int H, int W, int C, int Ho, int Wo,
+                                                                   __half* __restrict__ dx) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int groups = C / 8;
+  const long long total = (long long)N * H * W * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long long t = i / groups;
+    const int pw = (int)(t % W);
+    t /= W;
+    const int ph = (int)(t % H);
+    const int n = (int)(t / H);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    const int oy0 = ph / 2, ox0 = pw / 2;  // windows (oy0 [, oy0 + 1 when ph is odd]) x (ox0 [, ox0 + 1])
+#pragma unroll
+    for (int dyi = 0; dyi < 2; ++dyi) {
+      const int oy = oy0 + dyi;
+      if ((dyi == 1 && !(ph & 1)) || oy >= Ho) continue;
+      const int r = ph - (2 * oy - 1);
+#pragma unroll
+      for (int dxi = 0; dxi < 2; ++dxi) {
+        const int ox = ox0 + dxi;
+        if ((dxi == 1 && !(pw & 1)) || ox >= Wo) continue;
+        const unsigned tap = (unsigned)(r * 3 + pw - (2 * ox - 1));
+        const size_t o = (((size_t)n * Ho + oy) * Wo + ox) * groups + g;
+        const uint2 a = arg[o];
+        float d[8];
+        unpack8(*reinterpret_cast<const uint4*>(dy + o * 8), d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const unsigned ak = ((k < 4 ? a.x : a.y) >> (8 * (k & 3))) & 255u;
+          if (ak == tap) acc[k] += d[k];
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(dx + i * 8) = pack8(acc);
+  }
+}
+
 // out[n][2i][2j] = x[n][i][j] (+ add), every other position = add (or 0): the transposed view of a stride-2 subsampling
 __global__ void __launch_bounds__(256) upsample2_zero_kernel(const __half* __restrict__ x, int N, int H, int W, int C,
                                                              const __half* __restrict__ add, __half* __restrict__ out) {
@@ -677,7 +781,7 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
 }
 
 static int row_grid(long long rows, int lanes) {
-  return (int)std::min<long long>((rows + lanes - 1) / lanes, (long long)sm_count() * 8);
+  return (int)std::min<long long>((rows + lanes - 1) / lanes, (long long)sm_count() * 32);
 }
 static int ew_grid(long long total) {
   return (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
@@ -848,6 +952,30 @@ int ctl_maxpool3x3s2_backward_nhwc_f16(const void* x, const void* dy, int32_t n,
   CTL_CUDA(launch_k(maxpool_backward_kernel, dim3(ew_grid((long long)n * h * w * (c / 8))), dim3(256), 0, (cudaStream_t)stream,
                     static_cast<const __half*>(x), static_cast<const __half*>(dy), (int)n, (int)h, (int)w, (int)c, Ho, Wo,
                     static_cast<__half*>(dx)));
+  return 0;
+}
+
+int ctl_maxpool3x3s2_argmax_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, void* out, void* arg_u8,
+                                     ctl_stream_t stream) {
+  CTL_CHECK_ARG(x && out && arg_u8 && n >= 1 && h >= 1 && w >= 1 && c % 8 == 0, "bad arguments");
+  int rc = ctl_device_check();
+  if (rc) return rc;
+  const int Ho = (h + 2 - 3) / 2 + 1, Wo = (w + 2 - 3) / 2 + 1;
+  CTL_CUDA(launch_k(maxpool_arg_kernel, dim3(ew_grid((long long)n * Ho * Wo * (c / 8))), dim3(256), 0, (cudaStream_t)stream,
+                    static_cast<const __half*>(x), (int)n, (int)h, (int)w, (int)c, Ho, Wo, static_cast<__half*>(out),
+                    static_cast<uint2*>(arg_u8)));
+  return 0;
+}
+
+int ctl_maxpool3x3s2_backward_argmax_nhwc_f16(const void* arg_u8, const void* dy, int32_t n, int32_t h, int32_t w, int32_t c,
+                                              void* dx, ctl_stream_t stream) {
+  CTL_CHECK_ARG(arg_u8 && dy && dx && n >= 1 && h >= 1 && w >= 1 && c % 8 == 0, "bad arguments");
+  int rc = ctl_device_check();
+  if (rc) return rc;
+  const int Ho = (h + 2 - 3) / 2 + 1, Wo = (w + 2 - 3) / 2 + 1;
+  CTL_CUDA(launch_k(maxpool_backward_arg_kernel, dim3(ew_grid((long long)n * h * w * (c / 8))), dim3(256), 0,
+                    (cudaStream_t)stream, static_cast<const uint2*>(arg_u8), static_cast<const __half*>(dy), (int)n, (int)h,
+                    (int)w, (int)c, Ho, Wo, static_cast<__half*>(dx)));
   return 0;
 }
 

@@ -111,9 +111,11 @@ class TrunkTrainer:
                 ws.data_ptr(), ws.numel(), m0.data_ptr(), i0.data_ptr(), z0.data_ptr(), N.stream_ptr()))
             hp, wp = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
             a = torch.empty(n, hp, wp, 64, dtype=torch.float16, device=self.device)
-            N.check(L.ctl_maxpool3x3s2_nhwc_f16(z0.data_ptr(), n, h, w, 64, a.data_ptr(), N.stream_ptr()))
+            arg = torch.empty(n, hp, wp, 64, dtype=torch.uint8, device=self.device)
+            N.check(L.ctl_maxpool3x3s2_argmax_nhwc_f16(z0.data_ptr(), n, h, w, 64, a.data_ptr(), arg.data_ptr(),
+                                                       N.stream_ptr()))
             self.launches += 5
-            self._stem = (y0, z0, m0, i0, (n, H, W, h, w, hp, wp))
+            self._stem = (y0, z0, m0, i0, (n, H, W, h, w, hp, wp), arg)
             h, w = hp, wp
             self._blocks = []
             for li, (planes, nblk) in enumerate(zip((64, 128, 256, 512), self.layers), start=1):
@@ -220,10 +222,10 @@ class TrunkTrainer:
                     shortcut = g3
                 dz = self._conv_bwd(s1, dy1, params, grads, residual=shortcut)
             # stem: max-pool -> BN (no ReLU) -> 7x7 weight gradient through the im2col GEMM
-            y0, z0, m0, i0, (n, H, W, h, w, hp, wp) = self._stem
+            y0, z0, m0, i0, (n, H, W, h, w, hp, wp), arg = self._stem
             dz0 = torch.empty_like(z0)
-            N.check(L.ctl_maxpool3x3s2_backward_nhwc_f16(z0.data_ptr(), dz.data_ptr(), n, h, w, 64, dz0.data_ptr(),
-                                                         N.stream_ptr()))
+            N.check(L.ctl_maxpool3x3s2_backward_argmax_nhwc_f16(arg.data_ptr(), dz.data_ptr(), n, h, w, 64, dz0.data_ptr(),
+                                                                N.stream_ptr()))
             st = _Saved()
             st.y, st.z, st.mean, st.invstd, st.bn, st.shape_out = y0, z0, m0, i0, "bn1", (n, h, w)
             dy0 = self._bn_bwd(st, dz0, False, params, grads)

@@ -278,6 +278,12 @@ int ctl_gap_backward_nhwc_f16(const float* dfeat, int32_t n, int32_t hw, int32_t
                               ctl_stream_t stream);
 int ctl_maxpool3x3s2_backward_nhwc_f16(const void* x, const void* dy, int32_t n, int32_t h, int32_t w, int32_t c, void* dx,
                                        ctl_stream_t stream);
+/* Training pair of the pool: the forward also records which window tap (r*3 + s, one byte per output element,
+ * [n][ho][wo][c] uint8) held the first maximum; the backward gathers from the <= 4 windows of a pixel. */
+int ctl_maxpool3x3s2_argmax_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, void* out, void* arg_u8,
+                                     ctl_stream_t stream);
+int ctl_maxpool3x3s2_backward_argmax_nhwc_f16(const void* arg_u8, const void* dy, int32_t n, int32_t h, int32_t w, int32_t c,
+                                              void* dx, ctl_stream_t stream);
 int ctl_upsample2_zero_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, const void* add, void* out,
                                 ctl_stream_t stream);
 int ctl_stem_im2col_f16(const float* x_nchw, int32_t n, int32_t h, int32_t w, void* out, ctl_stream_t stream);

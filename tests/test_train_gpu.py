@@ -126,6 +126,16 @@ def test_pool_gap_upsample_im2col_backward_helpers():
     torch.cuda.synchronize()
     ref = xr.grad.permute(0, 2, 3, 1)
     assert float((dx.cpu().float() - ref).abs().max()) <= 2.0 ** -9 * float(ref.abs().max())
+    # training pair: forward that records the argmax tap + gather backward
+    pooled = torch.empty(n, ho, wo, c, dtype=torch.float16, device="cuda")
+    arg = torch.empty(n, ho, wo, c, dtype=torch.uint8, device="cuda")
+    N.check(L.ctl_maxpool3x3s2_argmax_nhwc_f16(xd.data_ptr(), n, h, w, c, pooled.data_ptr(), arg.data_ptr(), N.stream_ptr()))
+    dx2 = torch.empty_like(xd)
+    N.check(L.ctl_maxpool3x3s2_backward_argmax_nhwc_f16(arg.data_ptr(), dyd.data_ptr(), n, h, w, c, dx2.data_ptr(),
+                                                        N.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(pooled.cpu().float(), F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1))
+    assert torch.equal(dx2.cpu(), dx.cpu())
     # global-average-pool backward
     df = torch.randn(4, 128, generator=g)
     out = torch.empty(4, 6, 128, dtype=torch.float16, device="cuda")
