@@ -281,7 +281,9 @@ static BnGeom bn_geom(long long rows, int C) {
   g.groups = C / 8;
   g.lanes = std::max(1, BN_THREADS / g.groups);
   const long long iters = (rows + g.lanes - 1) / g.lanes;
-  g.blocks = (int)std::min<long long>(BN_MAX_BLOCKS, std::max<long long>(1, iters / 4));
+  // enough row slabs to fill the machine, but not so many that the finalize pass (blocks x C partials) dominates
+  const long long cap = std::max<long long>(sm_count(), std::min<long long>(BN_MAX_BLOCKS, 262144 / C));
+  g.blocks = (int)std::min<long long>(cap, std::max<long long>(1, iters / 4));
   g.rows_per_block = (rows + g.blocks - 1) / g.blocks;
   return g;
 }
@@ -370,13 +372,13 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const __half* __re
 
 // finalize of the forward: batch mean / biased variance -> invstd, scale = gamma*invstd, shift = beta - mean*scale;
 // running statistics updated like torch (momentum, unbiased variance).
-// Sum of the per-block partials of 32 channels: 8 warps split the block index (stride 8), partial sums are combined in
+// Sum of the per-block partials of 32 channels: 32 warps split the block index (stride 32), partial sums are combined in
 // a fixed order (deterministic).  Returns the two totals of channel `c` to the threads with part == 0.
 __device__ __forceinline__ void bn_sum_partials(const float* __restrict__ part, int blocks, int C, int c, int part_id,
-                                                double (*sh)[2][32], double& s0, double& s1) {
+                                                double (*sh)[2][32], double& s0, double& s1) {  // sh[32][2][32]
   double a = 0.0, b = 0.0;
   if (c < C)
-    for (int blk = part_id; blk < blocks; blk += 8) {
+    for (int blk = part_id; blk < blocks; blk += 32) {
       a += (double)part[(size_t)blk * 2 * C + c];
       b += (double)part[(size_t)blk * 2 * C + C + c];
     }
@@ -385,15 +387,15 @@ __device__ __forceinline__ void bn_sum_partials(const float* __restrict__ part, 
   __syncthreads();
   s0 = s1 = 0.0;
   if (part_id == 0)
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < 32; ++q) {
       s0 += sh[q][0][threadIdx.x & 31];
       s1 += sh[q][1][threadIdx.x & 31];
     }
 }
 
 // finalize of the forward: batch mean / biased variance -> invstd, scale = gamma*invstd, shift = beta - mean*scale;
-// running statistics updated like torch (momentum, unbiased variance).  grid = C / 32 blocks of 256 threads.
-__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ part, int blocks, int C, double count,
+// running statistics updated like torch (momentum, unbiased variance).  grid = C / 32 blocks of 1024 threads.
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ part, int blocks, int C, double count,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           float eps, float momentum, float* __restrict__ running_mean,
                                                           float* __restrict__ running_var, float* __restrict__ mean,
@@ -401,7 +403,7 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
                                                           float* __restrict__ shift) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ double sh[8][2][32];
+  __shared__ double sh[32][2][32];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31), part_id = threadIdx.x >> 5;
   double s, ss;
   bn_sum_partials(part, blocks, C, c, part_id, sh, s, ss);
@@ -438,23 +440,36 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const __half* __re
     sc[k] = scale[group * 8 + k];
     sh[k] = shift[group * 8 + k];
   }
-  for (long long r = (long long)blockIdx.x * lanes + lane_row; r < rows; r += (long long)gridDim.x * lanes) {
-    const size_t off = (size_t)r * C + group * 8;
-    float f[8];
-    unpack8(*reinterpret_cast<const uint4*>(y + off), f);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], sc[k], sh[k]);
+  const long long step = (long long)gridDim.x * lanes;
+  for (long long r = (long long)blockIdx.x * lanes + lane_row; r < rows; r += 2 * step) {
+    const bool two = r + step < rows;
+    const size_t off0 = (size_t)r * C + group * 8, off1 = two ? off0 + (size_t)step * C : off0;
+    const uint4 v0 = *reinterpret_cast<const uint4*>(y + off0);
+    const uint4 v1 = *reinterpret_cast<const uint4*>(y + off1);
+    uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
     if (residual) {
-      float rr[8];
-      unpack8(*reinterpret_cast<const uint4*>(residual + off), rr);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) f[k] += rr[k];
+      r0 = *reinterpret_cast<const uint4*>(residual + off0);
+      r1 = *reinterpret_cast<const uint4*>(residual + off1);
     }
-    if (relu) {
+    float f[8], g2[8], rr[8];
+    unpack8(v0, f);
+    unpack8(v1, g2);
+    unpack8(r0, rr);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
+    for (int k = 0; k < 8; ++k) {
+      f[k] = fmaf(f[k], sc[k], sh[k]) + rr[k];
+      if (relu) f[k] = fmaxf(f[k], 0.f);
     }
-    *reinterpret_cast<uint4*>(out + off) = pack8(f);
+    *reinterpret_cast<uint4*>(out + off0) = pack8(f);
+    if (two) {
+      unpack8(r1, rr);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        g2[k] = fmaf(g2[k], sc[k], sh[k]) + rr[k];
+        if (relu) g2[k] = fmaxf(g2[k], 0.f);
+      }
+      *reinterpret_cast<uint4*>(out + off1) = pack8(g2);
+    }
   }
 }
 
@@ -504,14 +519,14 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const __half*
 
 // finalize of the backward: dgamma, dbeta (multiplied by `grad_unscale`), and the per-channel coefficients of
 // dy = A * g + B * y + Cc  (= gamma*invstd * (g - dbeta/M - xhat * dgamma/M))
-__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ part, int blocks, int C, double count,
+__global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __restrict__ part, int blocks, int C, double count,
                                                               const float* __restrict__ gamma, const float* __restrict__ mean,
                                                               const float* __restrict__ invstd, float grad_unscale,
                                                               float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                               float* __restrict__ coef) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ double sh[8][2][32];
+  __shared__ double sh[32][2][32];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31), part_id = threadIdx.x >> 5;
   double sg, sgx;
   bn_sum_partials(part, blocks, C, c, part_id, sh, sg, sgx);
@@ -540,14 +555,25 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const __half* 
     cb[k] = coef[C + group * 8 + k];
     cc[k] = coef[2 * C + group * 8 + k];
   }
-  for (long long r = (long long)blockIdx.x * lanes + lane_row; r < rows; r += (long long)gridDim.x * lanes) {
-    const size_t off = (size_t)r * C + group * 8;
+  const long long step = (long long)gridDim.x * lanes;
+  for (long long r = (long long)blockIdx.x * lanes + lane_row; r < rows; r += 2 * step) {
+    const bool two = r + step < rows;
+    const size_t off0 = (size_t)r * C + group * 8, off1 = two ? off0 + (size_t)step * C : off0;
+    const uint4 a0 = *reinterpret_cast<const uint4*>(g + off0), b0 = *reinterpret_cast<const uint4*>(y + off0);
+    const uint4 a1 = *reinterpret_cast<const uint4*>(g + off1), b1 = *reinterpret_cast<const uint4*>(y + off1);
     float gv[8], yv[8], o[8];
-    unpack8(*reinterpret_cast<const uint4*>(g + off), gv);
-    unpack8(*reinterpret_cast<const uint4*>(y + off), yv);
+    unpack8(a0, gv);
+    unpack8(b0, yv);
 #pragma unroll
     for (int k = 0; k < 8; ++k) o[k] = fmaf(ca[k], gv[k], fmaf(cb[k], yv[k], cc[k]));
-    *reinterpret_cast<uint4*>(dy + off) = pack8(o);
+    *reinterpret_cast<uint4*>(dy + off0) = pack8(o);
+    if (two) {
+      unpack8(a1, gv);
+      unpack8(b1, yv);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = fmaf(ca[k], gv[k], fmaf(cb[k], yv[k], cc[k]));
+      *reinterpret_cast<uint4*>(dy + off1) = pack8(o);
+    }
   }
 }
 
@@ -781,7 +807,7 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
 }
 
 static int row_grid(long long rows, int lanes) {
-  return (int)std::min<long long>((rows + lanes - 1) / lanes, (long long)sm_count() * 32);
+  return (int)std::min<long long>((rows + 2 * lanes - 1) / (2 * lanes), (long long)sm_count() * 8);
 }
 static int ew_grid(long long total) {
   return (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
@@ -901,7 +927,7 @@ int ctl_bn_train_forward_nhwc_f16(const void* y, int64_t rows, int32_t c, const 
   const size_t sm = (size_t)g.lanes * 2 * c * sizeof(float);
   CTL_CUDA(launch_k(bn_stats_kernel, dim3(g.blocks), dim3(BN_THREADS), sm, st, static_cast<const __half*>(y), (long long)rows,
                     (int)c, g.rows_per_block, g.lanes, part));
-  CTL_CUDA(launch_k(bn_finalize_kernel, dim3((c + 31) / 32), dim3(256), 0, st, (const float*)part, g.blocks, (int)c,
+  CTL_CUDA(launch_k(bn_finalize_kernel, dim3((c + 31) / 32), dim3(1024), 0, st, (const float*)part, g.blocks, (int)c,
                     (double)rows, gamma, beta, eps, momentum, running_mean, running_var, save_mean, save_invstd, scale, shift));
   CTL_CUDA(launch_k(bn_apply_kernel, dim3(row_grid(rows, g.lanes)), dim3(BN_THREADS), 0, st, static_cast<const __half*>(y),
                     (long long)rows, (int)c, g.lanes, (const float*)scale, (const float*)shift, static_cast<const __half*>(residual),
@@ -925,7 +951,7 @@ int ctl_bn_train_backward_nhwc_f16(const void* dz, const void* z, const void* y,
   CTL_CUDA(launch_k(bn_bwd_reduce_kernel, dim3(g.blocks), dim3(BN_THREADS), sm, st, static_cast<const __half*>(dz),
                     static_cast<const __half*>(z), static_cast<const __half*>(y), (long long)rows, (int)c, g.rows_per_block,
                     g.lanes, save_mean, save_invstd, static_cast<__half*>(g_out), part));
-  CTL_CUDA(launch_k(bn_bwd_finalize_kernel, dim3((c + 31) / 32), dim3(256), 0, st, (const float*)part, g.blocks, (int)c,
+  CTL_CUDA(launch_k(bn_bwd_finalize_kernel, dim3((c + 31) / 32), dim3(1024), 0, st, (const float*)part, g.blocks, (int)c,
                     (double)rows, gamma, save_mean, save_invstd, grad_unscale, dgamma, dbeta, coef));
   const __half* gsrc = z ? static_cast<const __half*>(g_out) : static_cast<const __half*>(dz);
   CTL_CUDA(launch_k(bn_bwd_apply_kernel, dim3(row_grid(rows, g.lanes)), dim3(BN_THREADS), 0, st, gsrc, static_cast<const __half*>(y),

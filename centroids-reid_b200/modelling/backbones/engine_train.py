@@ -33,7 +33,7 @@ class TrunkTrainer:
     weight / bias fp32 on the device; BN running_mean / running_var are updated in place)."""
 
     def __init__(self, device, last_stride: int = 1, layers=R50_LAYERS, grad_scale: float = 1024.0,
-                 momentum: float = 0.1):
+                 momentum: float = 0.1, graphs: bool = False):
         self.device = torch.device(device)
         self.last_stride, self.layers, self.grad_scale, self.momentum = last_stride, layers, float(grad_scale), momentum
         self._zero_bias = torch.zeros(2048, device=self.device)
@@ -41,6 +41,11 @@ class TrunkTrainer:
         self._ws_wg = None
         self.saved: List[_Saved] = []
         self.launches = 0
+        # graphs=True: forward and backward are captured once per (input shape, parameter storage) into two CUDA
+        # graphs and replayed (the ~540 launches and ~300 torch glue ops of a step cost more CPU time than the GPU
+        # needs to run them); the stored activations live in the graphs' private pool
+        self.graphs = graphs
+        self._graph = None
 
     # ---------------------------------------------------------------- helpers
     def _bn_ws(self, rows, c):
@@ -84,6 +89,49 @@ class TrunkTrainer:
     # ---------------------------------------------------------------- forward
     def forward(self, x: torch.Tensor, params: Dict[str, torch.Tensor]) -> torch.Tensor:
         """x: [B, 3, H, W] fp32 NCHW on the device -> global_feat [B, 2048] fp32; keeps what backward needs."""
+        if not self.graphs:
+            return self._forward_impl(x, params)
+        N.require_cuda(x)
+        key = (tuple(x.shape), tuple(sorted((k, v.data_ptr()) for k, v in params.items())))
+        g = self._graph
+        if g is None or g["key"] != key:
+            g = self._capture(x, params, key)
+        g["x"].copy_(x)
+        g["fwd"].replay()
+        return g["feat"].clone()
+
+    def backward(self, dfeat: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """dfeat: [B, 2048] fp32 = dLoss/dglobal_feat -> {param name: fp32 gradient in the reference's layout}."""
+        if not self.graphs:
+            return self._backward_impl(dfeat)
+        g = self._graph
+        g["dfeat"].copy_(dfeat)
+        g["bwd"].replay()
+        return {k: v.clone() for k, v in g["grads"].items()}
+
+    def _capture(self, x, params, key):
+        self._graph = None
+        sx = x.detach().float().contiguous().clone()
+        running = {k: v.clone() for k, v in params.items() if "running" in k}
+        sdf = torch.zeros(x.shape[0], 2048, device=self.device)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):  # eager warm-up: function attributes, workspaces, allocator pools
+            self._forward_impl(sx, params)
+            self._backward_impl(sdf)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        fwd, bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(fwd):
+            feat = self._forward_impl(sx, params)
+        with torch.cuda.graph(bwd, pool=fwd.pool()):
+            grads = self._backward_impl(sdf)
+        for k, v in running.items():  # the warm-up and capture passes must not count as training steps
+            params[k].copy_(v)
+        self._graph = {"key": key, "x": sx, "dfeat": sdf, "fwd": fwd, "bwd": bwd, "feat": feat, "grads": grads}
+        return self._graph
+
+    def _forward_impl(self, x: torch.Tensor, params: Dict[str, torch.Tensor]) -> torch.Tensor:
         N.require_cuda(x)
         x = x.float().contiguous()
         n, _, H, W = x.shape
@@ -197,8 +245,7 @@ class TrunkTrainer:
         dx, _, _ = self._conv(up, n, h, w, wd, cin, 3, 1, residual=residual)
         return dx
 
-    def backward(self, dfeat: torch.Tensor) -> Dict[str, torch.Tensor]:
-        """dfeat: [B, 2048] fp32 = dLoss/dglobal_feat -> {param name: fp32 gradient in the reference's layout}."""
+    def _backward_impl(self, dfeat: torch.Tensor) -> Dict[str, torch.Tensor]:
         params, grads = self._params, {}
         L = N.lib()
         n, h, w, c = self._last
@@ -234,5 +281,4 @@ class TrunkTrainer:
             self.launches += 2
             dw = self._wgrad(col, (n, h, w), dy0, 64, 1, 1)  # [64][1][1][192]
             grads["conv1.weight"] = dw.reshape(64, 192)[:, :168].reshape(64, 3, 7, 8)[..., :7].mul(1.0 / self.grad_scale)
-        self.saved, self._blocks = [], []
         return grads

@@ -8,6 +8,8 @@ training engine (batch-statistics BatchNorm, running statistics updated in place
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch import nn
 
@@ -81,7 +83,8 @@ class Baseline(nn.Module):
                                           "resnet50/101/152 train on the B200 engine (DESIGN.md)")
             dev = next(self.base.parameters()).device
             if self._trainer is None or self._trainer.device != dev:
-                self._trainer = TrunkTrainer(dev, last_stride=self.base.last_stride, layers=self.base.layers_cfg)
+                self._trainer = TrunkTrainer(dev, last_stride=self.base.last_stride, layers=self.base.layers_cfg,
+                                             graphs=os.environ.get("CTL_TRAIN_GRAPHS", "1") == "1")
             names = [k for k, _ in self.base.named_parameters()]
             tensors = [v for _, v in self.base.named_parameters()]
             buffers = {k: v for k, v in self.base.named_buffers() if "running" in k}

@@ -282,3 +282,31 @@ def test_ctl_training_step_end_to_end():
     ref = O.ctl_step_losses(feat_o.float(), labels, is_real, K_, hs["center_loss.centers"], hs["bn.weight"], hs["bn.bias"],
                             hs["fc_query.weight"])
     np.testing.assert_allclose(float(loss), float(ref["total"]), rtol=5e-3)
+
+
+def test_trunk_train_cuda_graphs_reproduce_eager_bits():
+    """graphs=True replays the captured forward/backward; kernels are deterministic, so features, gradients and
+    running statistics are bit-identical to the eager path, step after step."""
+    from oracle import ctl_oracle as O
+    from ctl_b200.modelling.backbones.engine_train import TrunkTrainer
+
+    sd = O.make_trunk_state(seed=3)
+    g = torch.Generator().manual_seed(8)
+    xs = [torch.randn(4, 3, 64, 32, generator=g).cuda() for _ in range(2)]
+    dfs = [(torch.randn(4, 2048, generator=g) * 1e-3).cuda() for _ in range(2)]
+    outs = []
+    for graphs in (False, True):
+        params = {k: v.clone().cuda() for k, v in sd.items() if v.is_floating_point()}
+        tr = TrunkTrainer("cuda", graphs=graphs)
+        res = []
+        for x, df in zip(xs, dfs):
+            feat = tr.forward(x, params)
+            grads = tr.backward(df)
+            res.append((feat.clone(), {k: v.clone() for k, v in grads.items()}))
+        torch.cuda.synchronize()
+        outs.append((res, {k: v.clone() for k, v in params.items() if "running" in k}))
+    (eager, run_e), (graph, run_g) = outs
+    for (fe, ge), (fg, gg) in zip(eager, graph):
+        assert torch.equal(fe, fg)
+        assert all(torch.equal(ge[k], gg[k]) for k in ge)
+    assert all(torch.equal(run_e[k], run_g[k]) for k in run_e)

@@ -9,10 +9,10 @@ from ctl_b200.modelling.backbones.engine_train import TrunkTrainer
 bs = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 sd = O.make_trunk_state(seed=0)
 params = {k: v.clone().cuda() for k, v in sd.items() if v.is_floating_point()}
-tr = TrunkTrainer("cuda")
+tr = TrunkTrainer("cuda", graphs=os.environ.get("CTL_TRAIN_GRAPHS", "1") == "1")
 x = torch.randn(bs, 3, 256, 128, device="cuda")
 df = torch.randn(bs, 2048, device="cuda") * 1e-3
-for _ in range(2):
+for _ in range(3):
     tr.forward(x, params); tr.backward(df)
 torch.cuda.synchronize()
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
