@@ -103,3 +103,43 @@ def test_sharded_merge_world2_gloo():
         p.join(60)
     assert ok_topk, "merged per-shard top-k differs from the global stable ranking"
     assert ok_eval, "sharded CMC/mAP differs from eval_func on the full ranking"
+
+
+def _grad_worker(rank, world, port, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import ctl_b200  # noqa: F401
+    from ctl_b200 import parallel
+
+    g = torch.Generator().manual_seed(100 + rank)
+    shapes = [(64, 3, 7, 7), (64,), (256, 64, 1, 1), (751, 2048), (5,)]
+    params = [torch.nn.Parameter(torch.zeros(s)) for s in shapes]
+    for p_ in params:
+        p_.grad = torch.randn(p_.shape, generator=g)
+    local = [p_.grad.clone() for p_ in params]
+    calls = parallel.allreduce_gradients(params, bucket_bytes=1 << 20)  # small buckets: several collectives
+    gathered = [[torch.empty_like(t) for _ in range(world)] for t in local]
+    for lst, t in zip(gathered, local):
+        dist.all_gather(lst, t)
+    ok = all(torch.allclose(p_.grad, torch.stack(lst).mean(0), rtol=0, atol=1e-7) for p_, lst in zip(params, gathered))
+    pids = np.arange(37)
+    mine = parallel.shard_pids(pids, world, rank)
+    sizes = [torch.tensor([len(mine)]) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([len(mine)]))
+    ok_shard = sum(int(t) for t in sizes) == 37 and np.array_equal(mine, np.array_split(pids, world)[rank])
+    out_q.put((rank, bool(ok), calls, bool(ok_shard)))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_and_pid_sharding_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p_ in procs:
+        p_.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p_ in procs:
+        p_.join(60)
+    assert all(ok and ok_shard for _, ok, _, ok_shard in res), res
+    assert all(calls >= 2 for _, _, calls, _ in res), res
