@@ -375,11 +375,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
 // multicast to both CTAs' `empty` / `tmem_full` barriers; both epilogues release the accumulator
 // stage on CTA 0's `tmem_empty` barrier.  Each CTA drains its own 128 TMEM lanes.
 // ---------------------------------------------------------------------------------------
+template <int BN_>
 struct PairCfg {
-  static constexpr int BN = 256;
-  static constexpr int B_HALF_BYTES = (BN / 2) * CBK * 2;        // 16 KiB
-  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_HALF_BYTES;  // 32 KiB
-  static constexpr int STAGES = 4;
+  static constexpr int BN = BN_;                                  // 256 or 128 output channels per pair tile
+  static constexpr int B_HALF_BYTES = (BN / 2) * CBK * 2;         // this CTA's half of the weight tile: 16 / 8 KiB
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_HALF_BYTES;  // 32 / 24 KiB
+  static constexpr int STAGES = BN == 256 ? 4 : 5;
+  static constexpr int TMEM_COLS = 2 * BN;                        // two accumulator stages
   static constexpr int OUT_SLABS = 4;
   static constexpr int IDENT_BYTES = 32 * CBK * 2;  // this CTA's 32 rows of the 64x64 identity
   static constexpr int BIAS_BYTES = 2048 * 4;  // the layer's whole bias vector, loaded once
@@ -387,9 +389,10 @@ struct PairCfg {
       (size_t)STAGES * STAGE_BYTES + OUT_SLABS * A_TILE_BYTES + IDENT_BYTES + BIAS_BYTES + 1024 + 256;
 };
 
+template <int BN_T>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
     conv_gemm_pair_kernel(const __grid_constant__ ConvKernelParams p) {
-  using Cfg = PairCfg;
+  using Cfg = PairCfg<BN_T>;
   constexpr int BN = Cfg::BN;
   constexpr int NSUB = BN / 64;
   extern __shared__ uint8_t smem_raw[];
@@ -460,7 +463,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
     tma_prefetch_desc(&p.out_map);
     tma_prefetch_desc(&p.res_map);
   }
-  if (warp == 1) tmem_alloc2<512>(tmem_slot);
+  if (warp == 1) tmem_alloc2<Cfg::TMEM_COLS>(tmem_slot);
   for (int i = threadIdx.x; i < p.Cout; i += blockDim.x)
     reinterpret_cast<float*>(gsm + (bias_sm - smem_base))[i] = p.bias[i];
   {  // this CTA's half (rows 32*rank .. +31) of the 64x64 identity, K-major, SWIZZLE_128B
@@ -676,7 +679,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc2<512>(tmem_base);
+    tmem_dealloc2<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -1646,15 +1649,17 @@ static int launch_c64(const void* x, int n, int h, int w, const void* weight, co
   return 0;
 }
 
+template <int BN>
 static int launch_conv_pair(const ConvKernelParams& p, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    CTL_CUDA(cudaFuncSetAttribute(conv_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PairCfg::SMEM));
+    CTL_CUDA(cudaFuncSetAttribute(conv_gemm_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)PairCfg<BN>::SMEM));
     attr_set = true;
   }
   const long long tiles = (long long)(p.m_tiles / 2) * p.n_tiles;
   const int clusters = (int)std::min<long long>(tiles, sm_count() / 2);
-  CTL_CUDA(launch_k(conv_gemm_pair_kernel, dim3(2 * clusters), dim3(CONV_THREADS), PairCfg::SMEM, st, p));
+  CTL_CUDA(launch_k(conv_gemm_pair_kernel<BN>, dim3(2 * clusters), dim3(CONV_THREADS), PairCfg<BN>::SMEM, st, p));
   CTL_LAUNCH_CHECK();
   return 0;
 }
@@ -1746,7 +1751,8 @@ int ctl_conv2d_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, int32_t 
   cudaStream_t st = (cudaStream_t)stream;
   // CTA pairs for every 256-channel-tile layer with an even tile count; CTL_CONV_PAIR=0 forces the single-CTA kernel (A/B runs)
   static const int pair_mode = [] { const char* e = getenv("CTL_CONV_PAIR"); return e ? atoi(e) : -1; }();
-  const bool pair_ok = BN == 256 && (p.m_tiles % 2 == 0) && p.m_tiles >= 2;
+  static const int pair128 = [] { const char* e = getenv("CTL_CONV_PAIR128"); return e ? atoi(e) : 1; }();
+  const bool pair_ok = (BN == 256 || (BN == 128 && pair128)) && (p.m_tiles % 2 == 0) && p.m_tiles >= 2;
   const bool pair_want = pair_mode != 0;  // measured faster than the single-CTA kernel on every BN = 256 layer of the trunk
   const bool use_pair = pair_ok && pair_want;
   const uint64_t bdims[2] = {(uint64_t)ksize * ksize * cin, (uint64_t)cout};
@@ -1755,7 +1761,7 @@ int ctl_conv2d_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, int32_t 
   if ((rc = encode_tensor_map(&p.b_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 2, weight, bdims, bstr, bbox,
                               CU_TENSOR_MAP_SWIZZLE_128B)))
     return rc;
-  if (use_pair) return launch_conv_pair(p, st);
+  if (use_pair) return BN == 256 ? launch_conv_pair<256>(p, st) : launch_conv_pair<128>(p, st);
   if (BN == 256) return launch_conv<256>(p, st);
   if (BN == 128) return launch_conv<128>(p, st);
   return launch_conv<64>(p, st);
