@@ -282,7 +282,7 @@ static BnGeom bn_geom(long long rows, int C) {
   g.lanes = std::max(1, BN_THREADS / g.groups);
   const long long iters = (rows + g.lanes - 1) / g.lanes;
   // enough row slabs to fill the machine, but not so many that the finalize pass (blocks x C partials) dominates
-  const long long cap = std::max<long long>(sm_count(), std::min<long long>(BN_MAX_BLOCKS, 262144 / C));
+  const long long cap = std::max<long long>(2 * sm_count(), std::min<long long>(BN_MAX_BLOCKS, 1048576 / C));
   g.blocks = (int)std::min<long long>(cap, std::max<long long>(1, iters / 4));
   g.rows_per_block = (rows + g.blocks - 1) / g.blocks;
   return g;
