@@ -288,8 +288,7 @@ def conv_traffic():
 def run_train_step(local, steps=5, warmup=2):
     """BASELINE config 2: one CTL training step (ResNet-50 256x128, 16 ids x 16 instances, fp16 activations):
     train-mode trunk forward (batch-stat BN) -> fused CTL/center/xent/triplet loss step -> backward through the
-    loss and the trunk (all parameter gradients).  Device-timed with CUDA events; no optimizer step (solver/build.py
-    is outside the hot path)."""
+    loss and the trunk (all parameter gradients) -> fused Adam + center-SGD step.  Device-timed with CUDA events."""
     import ctl_b200  # noqa: F401
     from ctl_b200.modelling.ctl_model import CTLModel
 
@@ -302,7 +301,9 @@ def run_train_step(local, steps=5, warmup=2):
         cfg = _C(MODEL=_C(NAME="resnet50", LAST_STRIDE=1, PRETRAINED=False, PRETRAIN_PATH="", BACKBONE_EMB_SIZE=2048,
                           USE_CENTROIDS=False, KEEP_CAMID_CENTROIDS=True, RESUME_TRAINING=False),
                  SOLVER=_C(MARGIN=0.5, DISTANCE_FUNC="euclidean", CENTER_LOSS_WEIGHT=5e-4, QUERY_XENT_WEIGHT=1.0,
-                           QUERY_CONTRASTIVE_WEIGHT=1.0, CENTROID_CONTRASTIVE_WEIGHT=1.0),
+                           QUERY_CONTRASTIVE_WEIGHT=1.0, CENTROID_CONTRASTIVE_WEIGHT=1.0, OPTIMIZER_NAME="Adam",
+                           BASE_LR=1e-4, WEIGHT_DECAY=5e-4, CENTER_LR=0.5, LR_SCHEDULER_NAME="multistep_lr",
+                           LR_STEPS=(40, 70), GAMMA=0.1, USE_WARMUP_LR=True, WARMUP_EPOCHS=10),
                  DATALOADER=_C(NUM_INSTANCE=16), TEST=_C(FEAT_NORM=True, ONLY_TEST=False, VISUALIZE="no"),
                  USE_MIXED_PRECISION=True)
     torch.manual_seed(0)
@@ -314,11 +315,14 @@ def run_train_step(local, steps=5, warmup=2):
     cam = torch.zeros(P * K, dtype=torch.long, device=dev)
     is_real = torch.ones(P * K, dtype=torch.bool, device=dev)
 
+    (opt, opt_center), _ = model.configure_optimizers()
+
     def step():
         for p_ in model.parameters():
             p_.grad = None
         out = model.training_step((x, labels, cam, is_real), 0)
         out["loss"].backward()
+        model.optimizer_step_manual(opt, opt_center, epoch=0)  # fused Adam + center SGD (solver/build.py)
         return out["loss"]
 
     for _ in range(warmup):
@@ -331,9 +335,9 @@ def run_train_step(local, steps=5, warmup=2):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    return {"metric": "CTL training step images/sec (resnet50 256x128, 16 ids x 16 instances, fwd+loss+bwd)",
+    return {"metric": "CTL training step images/sec (resnet50 256x128, 16 ids x 16 instances, fwd+loss+bwd+optimizer)",
             "value": P * K / ms * 1e3, "unit": "images/s", "ms_per_step": ms, "steps": steps, "loss": float(loss),
-            "tflops": 3 * P * K * GFLOP_PER_IMG / ms, "note": "3 x forward FLOPs per image; optimizer step not included",
+            "tflops": 3 * P * K * GFLOP_PER_IMG / ms, "note": "3 x forward FLOPs per image; includes the fused Adam / center-SGD step",
             "peak_mem_gib": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
 
 

@@ -84,6 +84,27 @@ class CTLModel(_Base):
         _, features = self.backbone(x)  # train mode: B200 training engine (differentiable w.r.t. the trunk parameters)
         return self.training_step_from_features(features, class_labels, is_real)
 
+    def configure_optimizers(self):
+        """modelling/bases.py:97-100 with the fused optimizers of ctl_b200.solver.build."""
+        from ..solver.build import build_optimizer, build_scheduler
+
+        optimizers_list = build_optimizer(self.named_parameters(), self.hparams)
+        self.lr_scheduler = build_scheduler(optimizers_list[0], self.hparams)
+        return optimizers_list, self.lr_scheduler
+
+    def optimizer_step_manual(self, opt, opt_center, epoch: int = 0):
+        """The tail of train_ctl_model.py:154-159 after `manual_backward`: warm-up LR rule (bases.py:115-121),
+        `opt.step()`, center gradients rescaled by 1 / CENTER_LOSS_WEIGHT, `opt_center.step()`; the packed eval
+        weights are invalidated because the parameters changed."""
+        from ..solver.build import apply_warmup_lr
+
+        apply_warmup_lr(opt, epoch, self.hparams)
+        opt.step()
+        for param in self.center_loss.parameters():
+            param.grad.data *= 1.0 / self.hparams.SOLVER.CENTER_LOSS_WEIGHT
+        opt_center.step()
+        self.backbone.invalidate()
+
     # -- evaluation -------------------------------------------------------------------------
     def validation_step(self, batch, batch_idx):
         """modelling/bases.py:169-177."""

@@ -1,0 +1,135 @@
+"""Drop-in for solver/build.py: `build_optimizer(named_parameters, hparams)` -> [Adam over everything but the
+centers, SGD over the centers], `build_scheduler`, plus the warm-up rule of ModelBase.optimizer_step
+(modelling/bases.py:102-133).
+
+The Adam step over the ~160 parameter tensors is ONE multi-tensor kernel launch (`ctl_adam_multi_step`) instead of
+torch's per-tensor op chains; state keys (`step`, `exp_avg`, `exp_avg_sq`) and `param_groups` are those of
+torch.optim.Adam, so optimizer state_dicts of the reference load unchanged and torch's LR schedulers drive it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _native as N
+
+_CHUNK = 8192  # CTL_OPT_CHUNK
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam(params, lr, betas, eps, weight_decay) semantics (L2 weight decay, no amsgrad)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        if lr < 0 or eps < 0 or not 0 <= betas[0] < 1 or not 0 <= betas[1] < 1 or weight_decay < 0:
+            raise ValueError("invalid Adam hyper-parameters")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.grad_mul = 1.0  # e.g. 1 / loss_scale
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        L = N.lib()
+        for group in self.param_groups:
+            by_step, keep = {}, []
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                N.require_cuda(p)
+                if p.dtype != torch.float32 or p.grad.dtype != torch.float32 or not p.is_contiguous():
+                    raise TypeError("FusedAdam expects contiguous fp32 parameters and gradients")
+                st = self.state[p]
+                if len(st) == 0:
+                    st["step"] = torch.tensor(0.0)
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["step"] += 1
+                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                keep.append(g)
+                # tensors that skipped steps (no gradient) carry their own bias correction: one launch per step count
+                by_step.setdefault(int(st["step"]), []).append(
+                    [p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(), 0])
+            b1, b2 = group["betas"]
+            for step, rows in by_step.items():
+                chunks = 0
+                for r in rows:
+                    r[5] = chunks
+                    chunks += (r[4] + _CHUNK - 1) // _CHUNK
+                table = torch.from_numpy(np.asarray(rows, dtype=np.int64)).to(group["params"][0].device, non_blocking=True)
+                N.check(L.ctl_adam_multi_step(table.data_ptr(), len(rows), chunks, float(group["lr"]), float(b1), float(b2),
+                                              float(group["eps"]), float(group["weight_decay"]), step, float(self.grad_mul),
+                                              N.stream_ptr()))
+                keep.append(table)
+        return loss
+
+
+class CenterSGD(torch.optim.Optimizer):
+    """torch.optim.SGD(params, lr) without momentum, with the reference's gradient rescale folded in:
+    `param.grad *= 1 / CENTER_LOSS_WEIGHT; opt_center.step()` (train_ctl_model.py:157-159) == step(grad_mul=1/w)."""
+
+    def __init__(self, params, lr, grad_mul: float = 1.0):
+        super().__init__(params, dict(lr=lr))
+        self.grad_mul = grad_mul
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                N.require_cuda(p)
+                g = p.grad.contiguous()
+                N.check(N.lib().ctl_sgd_step(p.data_ptr(), g.data_ptr(), p.numel(), float(group["lr"]), float(self.grad_mul),
+                                             N.stream_ptr()))
+        return loss
+
+
+def build_optimizer(named_parameters, hparams, fold_center_rescale: bool = False):
+    """solver/build.py:9-47.  Returns [model_optimizer, optimizer_center].  With fold_center_rescale=True the center
+    optimizer applies the 1 / CENTER_LOSS_WEIGHT gradient rescale itself (then the caller must NOT rescale)."""
+    regular, regular_names, center, center_names = [], [], [], []
+    for name, parameter in named_parameters:
+        if parameter.requires_grad is False:
+            print(f"Parameter {name} does not need a Grad. Excluding from the optimizer...")
+            continue
+        if "center" in name:
+            center.append(parameter)
+            center_names.append(name)
+        else:
+            regular.append(parameter)
+            regular_names.append(name)
+    if hparams.SOLVER.OPTIMIZER_NAME != "Adam":
+        raise NotImplementedError(f"No such optimizer {hparams.SOLVER.OPTIMIZER_NAME}")
+    model_optimizer = FusedAdam([{"params": regular, "names": regular_names}], lr=hparams.SOLVER.BASE_LR,
+                                weight_decay=hparams.SOLVER.WEIGHT_DECAY)
+    mul = 1.0 / hparams.SOLVER.CENTER_LOSS_WEIGHT if fold_center_rescale else 1.0
+    optimizer_center = CenterSGD([{"params": center, "names": center_names}], lr=hparams.SOLVER.CENTER_LR, grad_mul=mul)
+    return [model_optimizer, optimizer_center]
+
+
+def build_scheduler(model_optimizer, hparams):
+    """solver/build.py:50-63 (torch's schedulers drive `param_groups[...]['lr']` of the fused optimizer)."""
+    if hparams.SOLVER.LR_SCHEDULER_NAME == "cosine_annealing":
+        return torch.optim.lr_scheduler.CosineAnnealingLR(model_optimizer, hparams.SOLVER.MAX_EPOCHS,
+                                                          eta_min=hparams.SOLVER.MIN_LR)
+    if hparams.SOLVER.LR_SCHEDULER_NAME == "multistep_lr":
+        return torch.optim.lr_scheduler.MultiStepLR(model_optimizer, milestones=hparams.SOLVER.LR_STEPS,
+                                                    gamma=hparams.SOLVER.GAMMA)
+    raise NotImplementedError(f"No such scheduler {hparams.SOLVER.LR_SCHEDULER_NAME}")
+
+
+def apply_warmup_lr(optimizer, epoch: int, hparams) -> None:
+    """ModelBase.optimizer_step's rule (modelling/bases.py:115-121): lr = min(1, (epoch + 1) / WARMUP_EPOCHS) * BASE_LR
+    during the warm-up epochs (applied to whichever optimizer is stepped, like the reference)."""
+    if hparams.SOLVER.USE_WARMUP_LR and epoch < hparams.SOLVER.WARMUP_EPOCHS:
+        lr_scale = min(1.0, float(epoch + 1) / float(hparams.SOLVER.WARMUP_EPOCHS))
+        for pg in optimizer.param_groups:
+            pg["lr"] = lr_scale * hparams.SOLVER.BASE_LR

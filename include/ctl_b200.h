@@ -288,6 +288,27 @@ int ctl_upsample2_zero_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, 
                                 ctl_stream_t stream);
 int ctl_stem_im2col_f16(const float* x_nchw, int32_t n, int32_t h, int32_t w, void* out, ctl_stream_t stream);
 
+/* ---- optimizer step (solver/build.py:9-47, train_ctl_model.py:155-159, modelling/bases.py:102-133) ---- */
+
+/* One table entry per parameter tensor, resident on the device; chunk_begin = running sum of
+ * ceil(numel / CTL_OPT_CHUNK) over the preceding entries. */
+#define CTL_OPT_CHUNK 8192
+typedef struct ctl_adam_entry {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t numel;
+  int64_t chunk_begin;
+} ctl_adam_entry;
+/* torch.optim.Adam (L2 weight decay added to the gradient, bias-corrected, no amsgrad) on every tensor of the table
+ * in one launch; `step` is the 1-based step count after this update; gradients are read as grad * grad_mul. */
+int ctl_adam_multi_step(const void* table_device, int32_t n_tensors, int64_t n_chunks, float lr, float beta1, float beta2,
+                        float eps, float weight_decay, int64_t step, float grad_mul, ctl_stream_t stream);
+/* torch.optim.SGD without momentum: param -= lr * grad * grad_mul (the center parameters; grad_mul =
+ * 1 / SOLVER.CENTER_LOSS_WEIGHT, train_ctl_model.py:157-158). */
+int ctl_sgd_step(float* param, const float* grad, int64_t numel, float lr, float grad_mul, ctl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

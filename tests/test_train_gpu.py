@@ -310,3 +310,36 @@ def test_trunk_train_cuda_graphs_reproduce_eager_bits():
         assert torch.equal(fe, fg)
         assert all(torch.equal(ge[k], gg[k]) for k in ge)
     assert all(torch.equal(run_e[k], run_g[k]) for k in run_e)
+
+
+def test_full_training_iterations_reduce_the_loss():
+    """Three complete iterations (train-mode trunk -> losses -> backward -> fused Adam + center SGD) on one batch:
+    finite everywhere, parameters move, the loss decreases."""
+    from oracle import ctl_oracle as O
+    from ctl_b200.modelling.ctl_model import CTLModel
+    from test_modules_gpu import _cfg
+
+    torch.manual_seed(0)
+    cfg = _cfg()
+    cfg["SOLVER"].update(dict(OPTIMIZER_NAME="Adam", BASE_LR=3.5e-4, WEIGHT_DECAY=5e-4, CENTER_LR=0.5,
+                              LR_SCHEDULER_NAME="multistep_lr", LR_STEPS=(40, 70), GAMMA=0.1, USE_WARMUP_LR=False,
+                              WARMUP_EPOCHS=10))
+    model = CTLModel(cfg, num_classes=16, num_query=4).cuda().train()
+    model.backbone.base.load_state_dict(O.make_trunk_state(seed=11))
+    (opt, opt_center), _ = model.configure_optimizers()
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(16, 3, 64, 32, generator=g).cuda()
+    labels = (torch.arange(4).repeat_interleave(4) + 1).cuda()
+    batch = (x, labels, torch.zeros(16, dtype=torch.long).cuda(), torch.ones(16, dtype=torch.bool).cuda())
+    w0 = model.backbone.base.layer2[0].conv2.weight.detach().clone()
+    losses = []
+    for _ in range(3):
+        for p_ in model.parameters():
+            p_.grad = None
+        out = model.training_step(batch, 0)
+        out["loss"].backward()
+        model.optimizer_step_manual(opt, opt_center, epoch=20)
+        losses.append(float(out["loss"]))
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+    assert not torch.equal(w0, model.backbone.base.layer2[0].conv2.weight)
+    assert all(torch.isfinite(p_).all() for p_ in model.parameters())
