@@ -309,6 +309,15 @@ int ctl_adam_multi_step(const void* table_device, int32_t n_tensors, int64_t n_c
  * 1 / SOLVER.CENTER_LOSS_WEIGHT, train_ctl_model.py:157-158). */
 int ctl_sgd_step(float* param, const float* grad, int64_t numel, float lr, float grad_mul, ctl_stream_t stream);
 
+/* ---- training-time augmentation (datasets/transforms/build.py:15-27, random_erasing.py:30-55) ---- */
+
+/* images: uint8 NHWC [n][h][w][3], already resized (T.Resize stays on the host); params_device: int32 [n][8] =
+ * {flip, crop_top, crop_left (offsets inside the padded image, 0..2*pad), erase_row, erase_col, erase_h, erase_w
+ * (erase_h == 0: none), is_real (0: mock image -> zeros)}; mean / std: 3 floats on the HOST.
+ * out = RandomErasing(Normalize(ToTensor(RandomCrop(Pad(Flip(image)))))) as fp32 NCHW [n][3][h][w]. */
+int ctl_augment_batch_u8(const void* images_u8_nhwc, int32_t n, int32_t h, int32_t w, int32_t pad, const int32_t* params_device,
+                         const float* mean3_host, const float* std3_host, float* out_nchw, ctl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -639,6 +639,33 @@ def trunk_train_fp16sim(x, sd, dfeat=None, last_stride=1, layers=R50_LAYERS, mom
     return feat.detach(), grads, running
 
 
+def augment_batch(images_u8, params, pixel_mean=(0.485, 0.456, 0.406), pixel_std=(0.229, 0.224, 0.225), pad=10):
+    """datasets/transforms/build.py:18-27 after T.Resize, per image with GIVEN random draws (params int [B, 8] =
+    flip, crop_top, crop_left, erase_row, erase_col, erase_h, erase_w, is_real): hflip -> Pad(pad, fill 0) ->
+    crop to the original size -> ToTensor (/255) -> Normalize -> RandomErasing (random_erasing.py:44-51: the erased
+    rectangle takes the RAW pixel mean, written after normalisation).  Mock images (is_real = 0) are all zeros
+    (datasets/bases.py:378-391).  images_u8: uint8 [B, H, W, 3] -> float32 [B, 3, H, W]."""
+    imgs = torch.as_tensor(images_u8)
+    B, H, W, _ = imgs.shape
+    mean = torch.tensor(pixel_mean, dtype=torch.float32)[:, None, None]
+    std = torch.tensor(pixel_std, dtype=torch.float32)[:, None, None]
+    out = torch.zeros(B, 3, H, W)
+    for b in range(B):
+        flip, top, left, er, ec, eh, ew, real = [int(v) for v in params[b]]
+        if not real:
+            continue
+        im = imgs[b].permute(2, 0, 1)
+        if flip:
+            im = im.flip(2)
+        im = F.pad(im, (pad, pad, pad, pad), value=0)[:, top:top + H, left:left + W]
+        t = (im.float() / 255.0 - mean) / std
+        if eh > 0:
+            for c in range(3):
+                t[c, er:er + eh, ec:ec + ew] = pixel_mean[c]
+        out[b] = t
+    return out
+
+
 # --------------------------------------------------------------------------------------
 # synthetic workloads shared by tests / bench (SURVEY 8d "Synthetic inputs")
 # --------------------------------------------------------------------------------------

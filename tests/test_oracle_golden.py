@@ -140,3 +140,38 @@ def test_retrieval_market_shape_matches_reference():
     _close(mAP, float(g["mAP"]), 1e-5)
     _close(topk, g["all_topk"], 0, 1e-3)
     assert np.array_equal(single[:, 0].astype(np.int32), g["valid_q"])
+
+
+def test_oracle_augment_pinned_against_reference_random_erasing():
+    """oracle.augment_batch (normalise + random erasing with given draws) against the reference's own RandomErasing
+    class (datasets/transforms/random_erasing.py, importable as-is) driven by the same `random` stream."""
+    import importlib.util
+    import math
+    import os
+    import random
+
+    path = "/root/reference/datasets/transforms/random_erasing.py"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    spec = importlib.util.spec_from_file_location("ref_random_erasing", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    H, W, pad = 32, 20, 10
+    rng = np.random.default_rng(1)
+    img = torch.from_numpy(rng.integers(0, 256, (1, H, W, 3), dtype=np.uint8))
+    norm = (img[0].permute(2, 0, 1).float() / 255.0 - torch.tensor(mean)[:, None, None]) / torch.tensor(std)[:, None, None]
+    for seed in range(5):
+        random.seed(seed)
+        out_ref = mod.RandomErasing(probability=1.0, mean=mean)(norm.clone())
+        random.seed(seed)  # replay the reference's draws to recover the rectangle
+        random.uniform(0, 1)
+        for _ in range(100):
+            ta = random.uniform(0.02, 0.4) * H * W
+            ar = random.uniform(0.3, 1 / 0.3)
+            h, w = int(round(math.sqrt(ta * ar))), int(round(math.sqrt(ta / ar)))
+            if w < W and h < H:
+                x1, y1 = random.randint(0, H - h), random.randint(0, W - w)
+                break
+        got = O.augment_batch(img, np.array([[0, pad, pad, x1, y1, h, w, 1]]), mean, std, pad)[0]
+        assert torch.allclose(got, out_ref, rtol=0, atol=1e-6)
