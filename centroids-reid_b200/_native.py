@@ -93,8 +93,10 @@ SIGNATURES = {
     "ctl_gap_bn_nhwc_f16": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
     "ctl_instnorm_relu_nhwc_f16": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p, _f, _p]),
     "ctl_bn_workspace_bytes": (C.c_size_t, [C.c_int64, _i32]),
-    "ctl_bn_train_forward_nhwc_f16": (C.c_int, [_p, C.c_int64, _i32, _p, _p, _f, _f, _p, _p, _p, _i32, _p, C.c_size_t, _p, _p, _p, _p]),
-    "ctl_bn_train_backward_nhwc_f16": (C.c_int, [_p, _p, _p, C.c_int64, _i32, _p, _p, _p, _f, _p, C.c_size_t, _p, _p, _p, _p, _p]),
+    "ctl_bn_train_forward_nhwc_f16": (C.c_int, [_p, C.c_int64, _i32, _i32, _p, _p, _f, _f, _p, _p, _p, _i32, _p, C.c_size_t, _p, _p, _p, _p]),
+    "ctl_bn_train_backward_nhwc_f16": (C.c_int, [_p, _p, _p, C.c_int64, _i32, _i32, _p, _p, _p, _f, _p, C.c_size_t, _p, _p, _p, _p, _p]),
+    "ctl_instnorm_train_forward_nhwc_f16": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p, _f, _p, _p, _p, _p]),
+    "ctl_instnorm_train_backward_nhwc_f16": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _f, _p, _p, _p, _p]),
     "ctl_gap_backward_nhwc_f16": (C.c_int, [_p, _i32, _i32, _i32, _f, _p, _p]),
     "ctl_maxpool3x3s2_backward_nhwc_f16": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p, _p]),
     "ctl_maxpool3x3s2_argmax_nhwc_f16": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p, _p]),

@@ -328,7 +328,7 @@ __device__ __forceinline__ void bn_block_store(float (&acc)[NQ][8], int group, i
 }
 
 // pass A of the forward: per-block sum and sum of squares of y
-__global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const __half* __restrict__ y, long long rows, int C,
+__global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const __half* __restrict__ y, long long rows, int C, int pitch,
                                                               long long rows_per_block, int lanes,
                                                               float* __restrict__ part) {
   pdl_launch_dependents();
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const __half* __re
     for (; r + 3LL * lanes < r1; r += 4LL * lanes) {  // four independent 16-byte loads in flight per thread
       uint4 v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(y + (r + (long long)u * lanes) * C + group * 8);
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(y + (r + (long long)u * lanes) * pitch + group * 8);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         float f[8];
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const __half* __re
     }
     for (; r < r1; r += lanes) {
       float f[8];
-      unpack8(*reinterpret_cast<const uint4*>(y + r * C + group * 8), f);
+      unpack8(*reinterpret_cast<const uint4*>(y + r * pitch + group * 8), f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         acc[0][i] += f[i];
@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
 
 // z = [relu](y * scale + shift [+ residual]) -> fp16.  A thread keeps the coefficients of its 8 channels in registers
 // and walks rows (blockDim = groups * lanes, like the statistics kernels).
-__global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const __half* __restrict__ y, long long rows, int C, int lanes,
+__global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const __half* __restrict__ y, long long rows, int C, int pitch, int lanes,
                                                               const float* __restrict__ scale, const float* __restrict__ shift,
                                                               const __half* __restrict__ residual, int relu,
                                                               __half* __restrict__ out) {
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const __half* __re
   const long long step = (long long)gridDim.x * lanes;
   for (long long r = (long long)blockIdx.x * lanes + lane_row; r < rows; r += 2 * step) {
     const bool two = r + step < rows;
-    const size_t off0 = (size_t)r * C + group * 8, off1 = two ? off0 + (size_t)step * C : off0;
+    const size_t off0 = (size_t)r * pitch + group * 8, off1 = two ? off0 + (size_t)step * pitch : off0;
     const uint4 v0 = *reinterpret_cast<const uint4*>(y + off0);
     const uint4 v1 = *reinterpret_cast<const uint4*>(y + off1);
     uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const __half* __re
 // pass A of the backward: g = dz * (z > 0) (written to g_out when a ReLU mask is given), per-block sum g and
 // sum g * xhat with xhat = (y - mean) * invstd
 __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const __half* __restrict__ dz, const __half* __restrict__ z,
-                                                                   const __half* __restrict__ y, long long rows, int C,
+                                                                   const __half* __restrict__ y, long long rows, int C, int pitch,
                                                                    long long rows_per_block, int lanes,
                                                                    const float* __restrict__ mean,
                                                                    const float* __restrict__ invstd,
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const __half*
   if (lane_row < lanes) {
     const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
     for (long long r = r0 + lane_row; r < r1; r += lanes) {
-      const size_t off = (size_t)r * C + group * 8;
+      const size_t off = (size_t)r * pitch + group * 8;
       float g[8], yv[8];
       unpack8(*reinterpret_cast<const uint4*>(dz + off), g);
       unpack8(*reinterpret_cast<const uint4*>(y + off), yv);
@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __re
 }
 
 __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const __half* __restrict__ g, const __half* __restrict__ y,
-                                                                  long long rows, int C, int lanes,
+                                                                  long long rows, int C, int pitch, int lanes,
                                                                   const float* __restrict__ coef, __half* __restrict__ dy) {
   pdl_launch_dependents();
   pdl_wait();
@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const __half* 
   const long long step = (long long)gridDim.x * lanes;
   for (long long r = (long long)blockIdx.x * lanes + lane_row; r < rows; r += 2 * step) {
     const bool two = r + step < rows;
-    const size_t off0 = (size_t)r * C + group * 8, off1 = two ? off0 + (size_t)step * C : off0;
+    const size_t off0 = (size_t)r * pitch + group * 8, off1 = two ? off0 + (size_t)step * pitch : off0;
     const uint4 a0 = *reinterpret_cast<const uint4*>(g + off0), b0 = *reinterpret_cast<const uint4*>(y + off0);
     const uint4 a1 = *reinterpret_cast<const uint4*>(g + off1), b1 = *reinterpret_cast<const uint4*>(y + off1);
     float gv[8], yv[8], o[8];
@@ -574,6 +574,134 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const __half* 
       for (int k = 0; k < 8; ++k) o[k] = fmaf(ca[k], gv[k], fmaf(cb[k], yv[k], cc[k]));
       *reinterpret_cast<uint4*>(dy + off1) = pack8(o);
     }
+  }
+}
+
+// =======================================================================================
+// 2b. InstanceNorm2d(affine) + ReLU on the first `half` channels of an IBN layer (resnet_ibn_a.py:18-32), train mode:
+//     statistics per (image, channel) over the H*W positions -- always instance statistics, no running buffers.
+//     One block per (image, 8-channel group); the block reduction order is fixed (deterministic).
+// =======================================================================================
+__device__ __forceinline__ void in_block_reduce(float (&acc)[2][8], float* sred /* [256][16] */, float (&tot)[2][8]) {
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sred[threadIdx.x * 16 + q * 8 + i] = acc[q][i];
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) sred[threadIdx.x * 16 + j] += sred[(threadIdx.x + off) * 16 + j];
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot[q][i] = sred[q * 8 + i];
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) in_train_forward_kernel(const __half* __restrict__ y, int HW, int pitch, int half,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               float eps, float* __restrict__ save_mean,
+                                                               float* __restrict__ save_invstd, __half* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float sred[256 * 16];
+  const int g = blockIdx.x, n = blockIdx.y;
+  const size_t base = (size_t)n * HW * pitch + g * 8;
+  float acc[2][8], tot[2][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.f;
+  for (int r = threadIdx.x; r < HW; r += blockDim.x) {
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(y + base + (size_t)r * pitch), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[0][i] += f[i];
+      acc[1][i] = fmaf(f[i], f[i], acc[1][i]);
+    }
+  }
+  in_block_reduce(acc, sred, tot);
+  float sc[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float m = tot[0][i] / HW;
+    const float var = fmaxf(tot[1][i] / HW - m * m, 0.f);
+    const float is = rsqrtf(var + eps);
+    sc[i] = gamma[g * 8 + i] * is;
+    sh[i] = beta[g * 8 + i] - m * sc[i];
+    if (threadIdx.x == 0) {
+      save_mean[(size_t)n * half + g * 8 + i] = m;
+      save_invstd[(size_t)n * half + g * 8 + i] = is;
+    }
+  }
+  for (int r = threadIdx.x; r < HW; r += blockDim.x) {
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(y + base + (size_t)r * pitch), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = fmaxf(fmaf(f[i], sc[i], sh[i]), 0.f);
+    *reinterpret_cast<uint4*>(out + base + (size_t)r * pitch) = pack8(f);
+  }
+}
+
+// g = dz * (z > 0) (written back over dz), per-instance sums -> dy; per-(image, channel) dgamma / dbeta partials
+__global__ void __launch_bounds__(256) in_train_backward_kernel(__half* __restrict__ dz, const __half* __restrict__ z,
+                                                                const __half* __restrict__ y, int HW, int pitch, int half,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ save_mean,
+                                                                const float* __restrict__ save_invstd, float grad_unscale,
+                                                                float* __restrict__ dgamma_part, float* __restrict__ dbeta_part,
+                                                                __half* __restrict__ dy) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float sred[256 * 16];
+  const int g = blockIdx.x, n = blockIdx.y;
+  const size_t base = (size_t)n * HW * pitch + g * 8;
+  float mu[8], is[8], acc[2][8], tot[2][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc[0][i] = acc[1][i] = 0.f;
+    mu[i] = save_mean[(size_t)n * half + g * 8 + i];
+    is[i] = save_invstd[(size_t)n * half + g * 8 + i];
+  }
+  for (int r = threadIdx.x; r < HW; r += blockDim.x) {
+    const size_t off = base + (size_t)r * pitch;
+    float gv[8], zv[8], yv[8];
+    unpack8(*reinterpret_cast<const uint4*>(dz + off), gv);
+    unpack8(*reinterpret_cast<const uint4*>(z + off), zv);
+    unpack8(*reinterpret_cast<const uint4*>(y + off), yv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      gv[i] = zv[i] > 0.f ? gv[i] : 0.f;
+      acc[0][i] += gv[i];
+      acc[1][i] = fmaf(gv[i], (yv[i] - mu[i]) * is[i], acc[1][i]);
+    }
+    *reinterpret_cast<uint4*>(dz + off) = pack8(gv);
+  }
+  in_block_reduce(acc, sred, tot);
+  float ca[8], cb[8], cc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float k1 = gamma[g * 8 + i] * is[i];
+    const float k2 = tot[0][i] / HW;
+    const float k3 = tot[1][i] / HW * is[i];
+    ca[i] = k1;
+    cb[i] = -k1 * k3;
+    cc[i] = k1 * (mu[i] * k3 - k2);
+    if (threadIdx.x == 0) {
+      dbeta_part[(size_t)n * half + g * 8 + i] = tot[0][i] * grad_unscale;
+      dgamma_part[(size_t)n * half + g * 8 + i] = tot[1][i] * grad_unscale;
+    }
+  }
+  for (int r = threadIdx.x; r < HW; r += blockDim.x) {
+    const size_t off = base + (size_t)r * pitch;
+    float gv[8], yv[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(dz + off), gv);  // this thread's own writes of the first loop
+    unpack8(*reinterpret_cast<const uint4*>(y + off), yv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = fmaf(ca[i], gv[i], fmaf(cb[i], yv[i], cc[i]));
+    *reinterpret_cast<uint4*>(dy + off) = pack8(o);
   }
 }
 
@@ -899,24 +1027,28 @@ int ctl_conv2d_wgrad_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, in
 
 
 size_t ctl_bn_workspace_bytes(int64_t rows, int32_t c) {
-  if (rows < 1 || c < 64 || c > 2048 || (c & (c - 1)) != 0) return 0;
+  if (rows < 1 || c < 32 || c > 2048 || (c & (c - 1)) != 0) return 0;
   const BnGeom g = bn_geom(rows, c);
   return ((size_t)g.blocks * 2 * c + 4 * (size_t)c) * sizeof(float) + 256;
 }
 
 static int bn_check(const char* what, int64_t rows, int32_t c, const void* ws, size_t ws_bytes) {
-  CTL_CHECK_ARG(rows >= 1 && c >= 64 && c <= 2048 && (c & (c - 1)) == 0, "%s: C=%d must be a power of two in [64, 2048]", what, c);
+  CTL_CHECK_ARG(rows >= 1 && c >= 32 && c <= 2048 && (c & (c - 1)) == 0, "%s: C=%d must be a power of two in [32, 2048]", what, c);
   CTL_CHECK_ARG(ws && ws_bytes >= ctl_bn_workspace_bytes(rows, c) - 256, "%s: workspace too small", what);
   CTL_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 15u) == 0, "%s: workspace must be 16-byte aligned", what);
   return ctl_device_check();
 }
 
-int ctl_bn_train_forward_nhwc_f16(const void* y, int64_t rows, int32_t c, const float* gamma, const float* beta, float eps,
+int ctl_bn_train_forward_nhwc_f16(const void* y, int64_t rows, int32_t c, int32_t pitch, const float* gamma, const float* beta, float eps,
                                   float momentum, float* running_mean, float* running_var, const void* residual,
                                   int32_t relu, void* workspace, size_t workspace_bytes, float* save_mean,
                                   float* save_invstd, void* out, ctl_stream_t stream) {
   CTL_CHECK_ARG(y && gamma && beta && save_mean && save_invstd && out, "null pointer");
   CTL_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "running_mean / running_var: both or neither");
+  CTL_CHECK_ARG(pitch >= c && pitch % 8 == 0, "pitch=%d must be a multiple of 8 and >= C=%d", pitch, c);
+  CTL_CHECK_ARG((reinterpret_cast<uintptr_t>(y) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0 &&
+                    (reinterpret_cast<uintptr_t>(residual) & 15u) == 0,
+                "tensors (channel-slice base pointers) must be 16-byte aligned");
   int rc = bn_check("bn forward", rows, c, workspace, workspace_bytes);
   if (rc) return rc;
   const BnGeom g = bn_geom(rows, c);
@@ -926,21 +1058,23 @@ int ctl_bn_train_forward_nhwc_f16(const void* y, int64_t rows, int32_t c, const 
   cudaStream_t st = (cudaStream_t)stream;
   const size_t sm = (size_t)g.lanes * 2 * c * sizeof(float);
   CTL_CUDA(launch_k(bn_stats_kernel, dim3(g.blocks), dim3(BN_THREADS), sm, st, static_cast<const __half*>(y), (long long)rows,
-                    (int)c, g.rows_per_block, g.lanes, part));
+                    (int)c, (int)pitch, g.rows_per_block, g.lanes, part));
   CTL_CUDA(launch_k(bn_finalize_kernel, dim3((c + 31) / 32), dim3(1024), 0, st, (const float*)part, g.blocks, (int)c,
                     (double)rows, gamma, beta, eps, momentum, running_mean, running_var, save_mean, save_invstd, scale, shift));
   CTL_CUDA(launch_k(bn_apply_kernel, dim3(row_grid(rows, g.lanes)), dim3(BN_THREADS), 0, st, static_cast<const __half*>(y),
-                    (long long)rows, (int)c, g.lanes, (const float*)scale, (const float*)shift, static_cast<const __half*>(residual),
+                    (long long)rows, (int)c, (int)pitch, g.lanes, (const float*)scale, (const float*)shift, static_cast<const __half*>(residual),
                     (int)relu, static_cast<__half*>(out)));
   return 0;
 }
 
-int ctl_bn_train_backward_nhwc_f16(const void* dz, const void* z, const void* y, int64_t rows, int32_t c, const float* gamma,
+int ctl_bn_train_backward_nhwc_f16(const void* dz, const void* z, const void* y, int64_t rows, int32_t c, int32_t pitch,
+                                   const float* gamma,
                                    const float* save_mean, const float* save_invstd, float grad_unscale, void* workspace,
                                    size_t workspace_bytes, void* g_out, float* dgamma, float* dbeta, void* dy,
                                    ctl_stream_t stream) {
   CTL_CHECK_ARG(dz && y && gamma && save_mean && save_invstd && dgamma && dbeta && dy, "null pointer");
   CTL_CHECK_ARG(z == nullptr || g_out != nullptr, "a ReLU mask (z) needs g_out (it may alias dz)");
+  CTL_CHECK_ARG(pitch >= c && pitch % 8 == 0, "pitch=%d must be a multiple of 8 and >= C=%d", pitch, c);
   int rc = bn_check("bn backward", rows, c, workspace, workspace_bytes);
   if (rc) return rc;
   const BnGeom g = bn_geom(rows, c);
@@ -949,13 +1083,40 @@ int ctl_bn_train_backward_nhwc_f16(const void* dz, const void* z, const void* y,
   cudaStream_t st = (cudaStream_t)stream;
   const size_t sm = (size_t)g.lanes * 2 * c * sizeof(float);
   CTL_CUDA(launch_k(bn_bwd_reduce_kernel, dim3(g.blocks), dim3(BN_THREADS), sm, st, static_cast<const __half*>(dz),
-                    static_cast<const __half*>(z), static_cast<const __half*>(y), (long long)rows, (int)c, g.rows_per_block,
+                    static_cast<const __half*>(z), static_cast<const __half*>(y), (long long)rows, (int)c, (int)pitch, g.rows_per_block,
                     g.lanes, save_mean, save_invstd, static_cast<__half*>(g_out), part));
   CTL_CUDA(launch_k(bn_bwd_finalize_kernel, dim3((c + 31) / 32), dim3(1024), 0, st, (const float*)part, g.blocks, (int)c,
                     (double)rows, gamma, save_mean, save_invstd, grad_unscale, dgamma, dbeta, coef));
   const __half* gsrc = z ? static_cast<const __half*>(g_out) : static_cast<const __half*>(dz);
   CTL_CUDA(launch_k(bn_bwd_apply_kernel, dim3(row_grid(rows, g.lanes)), dim3(BN_THREADS), 0, st, gsrc, static_cast<const __half*>(y),
-                    (long long)rows, (int)c, g.lanes, (const float*)coef, static_cast<__half*>(dy)));
+                    (long long)rows, (int)c, (int)pitch, g.lanes, (const float*)coef, static_cast<__half*>(dy)));
+  return 0;
+}
+
+int ctl_instnorm_train_forward_nhwc_f16(const void* y, int32_t n, int32_t hw, int32_t pitch, int32_t half, const float* gamma,
+                                        const float* beta, float eps, float* save_mean, float* save_invstd, void* out,
+                                        ctl_stream_t stream) {
+  CTL_CHECK_ARG(y && gamma && beta && save_mean && save_invstd && out, "null pointer");
+  CTL_CHECK_ARG(n >= 1 && hw >= 1 && half >= 8 && half % 8 == 0 && pitch >= half && pitch % 8 == 0, "bad shape");
+  int rc = ctl_device_check();
+  if (rc) return rc;
+  CTL_CUDA(launch_k(in_train_forward_kernel, dim3(half / 8, n), dim3(256), 0, (cudaStream_t)stream,
+                    static_cast<const __half*>(y), (int)hw, (int)pitch, (int)half, gamma, beta, eps, save_mean, save_invstd,
+                    static_cast<__half*>(out)));
+  return 0;
+}
+
+int ctl_instnorm_train_backward_nhwc_f16(void* dz, const void* z, const void* y, int32_t n, int32_t hw, int32_t pitch,
+                                         int32_t half, const float* gamma, const float* save_mean, const float* save_invstd,
+                                         float grad_unscale, float* dgamma_part, float* dbeta_part, void* dy,
+                                         ctl_stream_t stream) {
+  CTL_CHECK_ARG(dz && z && y && gamma && save_mean && save_invstd && dgamma_part && dbeta_part && dy, "null pointer");
+  CTL_CHECK_ARG(n >= 1 && hw >= 1 && half >= 8 && half % 8 == 0 && pitch >= half && pitch % 8 == 0, "bad shape");
+  int rc = ctl_device_check();
+  if (rc) return rc;
+  CTL_CUDA(launch_k(in_train_backward_kernel, dim3(half / 8, n), dim3(256), 0, (cudaStream_t)stream, static_cast<__half*>(dz),
+                    static_cast<const __half*>(z), static_cast<const __half*>(y), (int)hw, (int)pitch, (int)half, gamma,
+                    save_mean, save_invstd, grad_unscale, dgamma_part, dbeta_part, static_cast<__half*>(dy)));
   return 0;
 }
 

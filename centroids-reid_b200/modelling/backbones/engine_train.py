@@ -9,8 +9,9 @@ zero-insertion upsampling), shortcut gradients folded into conv1's data gradient
 input.  Activations and activation gradients are fp16, every reduction and all parameter gradients fp32.
 
 Gradients are computed on `grad_scale * dfeat` (a fixed loss scale against fp16 underflow, the role of the AMP
-GradScaler in the reference's PL trainer) and un-scaled in fp32.  ResNet-50 only: the IBN-a variant's
-InstanceNorm has no training kernels yet.
+GradScaler in the reference's PL trainer) and un-scaled in fp32.  `ibn=True` runs the IBN-a variant
+(resnet_ibn_a.py): ReLU after the stem, and bn1 of layer1-3 = InstanceNorm on the first half of the channels
+(per-image statistics) + batch-statistics BatchNorm on the rest, both through channel-slice (row pitch) kernels.
 """
 from __future__ import annotations
 
@@ -25,7 +26,7 @@ R50_LAYERS = (3, 4, 6, 3)
 
 
 class _Saved:
-    __slots__ = ("a", "y", "z", "mean", "invstd", "shape_in", "shape_out", "conv", "bn", "k", "stride", "relu")
+    __slots__ = ("a", "y", "z", "mean", "invstd", "shape_in", "shape_out", "conv", "bn", "k", "stride", "relu", "ibn")
 
 
 class TrunkTrainer:
@@ -33,8 +34,9 @@ class TrunkTrainer:
     weight / bias fp32 on the device; BN running_mean / running_var are updated in place)."""
 
     def __init__(self, device, last_stride: int = 1, layers=R50_LAYERS, grad_scale: float = 1024.0,
-                 momentum: float = 0.1, graphs: bool = False):
+                 momentum: float = 0.1, graphs: bool = False, ibn: bool = False):
         self.device = torch.device(device)
+        self.ibn = ibn  # resnet_ibn_a.py: ReLU after the stem, IBN (InstanceNorm half + BatchNorm half) as bn1 of layer1-3
         self.last_stride, self.layers, self.grad_scale, self.momentum = last_stride, layers, float(grad_scale), momentum
         self._zero_bias = torch.zeros(2048, device=self.device)
         self._ws_bn = None
@@ -64,23 +66,45 @@ class TrunkTrainer:
         self.launches += 1
         return out, ho, wo
 
-    def _conv_bn(self, a, n, h, w, params, conv, bn, k, stride, relu, residual=None):
+    def _conv_bn(self, a, n, h, w, params, conv, bn, k, stride, relu, residual=None, ibn=False):
         wt = params[conv + ".weight"]
         cout = wt.shape[0]
         wf = wt.detach().permute(0, 2, 3, 1).contiguous().half()  # forward operand [Cout][k][k][Cin]
         y, ho, wo = self._conv(a, n, h, w, wf, cout, k, stride)
         rows = n * ho * wo
         z = torch.empty_like(y)
-        mean = torch.empty(cout, device=self.device)
-        invstd = torch.empty(cout, device=self.device)
-        ws = self._bn_ws(rows, cout)
-        rm, rv = params.get(bn + ".running_mean"), params.get(bn + ".running_var")
-        N.check(N.lib().ctl_bn_train_forward_nhwc_f16(
-            y.data_ptr(), rows, cout, params[bn + ".weight"].data_ptr(), params[bn + ".bias"].data_ptr(), BN_EPS,
-            self.momentum, N.ptr(rm), N.ptr(rv), N.ptr(residual), int(relu), ws.data_ptr(), ws.numel(), mean.data_ptr(),
-            invstd.data_ptr(), z.data_ptr(), N.stream_ptr()))
-        self.launches += 3
+        L = N.lib()
         s = _Saved()
+        if not ibn:
+            mean = torch.empty(cout, device=self.device)
+            invstd = torch.empty(cout, device=self.device)
+            ws = self._bn_ws(rows, cout)
+            rm, rv = params.get(bn + ".running_mean"), params.get(bn + ".running_var")
+            N.check(L.ctl_bn_train_forward_nhwc_f16(
+                y.data_ptr(), rows, cout, cout, params[bn + ".weight"].data_ptr(), params[bn + ".bias"].data_ptr(), BN_EPS,
+                self.momentum, N.ptr(rm), N.ptr(rv), N.ptr(residual), int(relu), ws.data_ptr(), ws.numel(),
+                mean.data_ptr(), invstd.data_ptr(), z.data_ptr(), N.stream_ptr()))
+            self.launches += 3
+            s.ibn = None
+        else:
+            # IBN (resnet_ibn_a.py:18-32): InstanceNorm on channels [0, half), batch-stat BatchNorm on [half, C); ReLU
+            half = cout // 2
+            im = torch.empty(n, half, device=self.device)
+            ii = torch.empty(n, half, device=self.device)
+            N.check(L.ctl_instnorm_train_forward_nhwc_f16(
+                y.data_ptr(), n, ho * wo, cout, half, params[bn + ".IN.weight"].data_ptr(),
+                params[bn + ".IN.bias"].data_ptr(), BN_EPS, im.data_ptr(), ii.data_ptr(), z.data_ptr(), N.stream_ptr()))
+            mean = torch.empty(cout - half, device=self.device)
+            invstd = torch.empty(cout - half, device=self.device)
+            ws = self._bn_ws(rows, cout - half)
+            off = half * 2  # bytes
+            N.check(L.ctl_bn_train_forward_nhwc_f16(
+                y.data_ptr() + off, rows, cout - half, cout, params[bn + ".BN.weight"].data_ptr(),
+                params[bn + ".BN.bias"].data_ptr(), BN_EPS, self.momentum, N.ptr(params.get(bn + ".BN.running_mean")),
+                N.ptr(params.get(bn + ".BN.running_var")), None, 1, ws.data_ptr(), ws.numel(), mean.data_ptr(),
+                invstd.data_ptr(), z.data_ptr() + off, N.stream_ptr()))
+            self.launches += 4
+            s.ibn = (half, im, ii)
         s.a, s.y, s.z, s.mean, s.invstd = a, y, z, mean, invstd
         s.shape_in, s.shape_out, s.conv, s.bn, s.k, s.stride, s.relu = (n, h, w), (n, ho, wo), conv, bn, k, stride, relu
         self.saved.append(s)
@@ -154,9 +178,9 @@ class TrunkTrainer:
             m0, i0 = torch.empty(64, device=self.device), torch.empty(64, device=self.device)
             ws = self._bn_ws(rows, 64)
             N.check(L.ctl_bn_train_forward_nhwc_f16(
-                y0.data_ptr(), rows, 64, params["bn1.weight"].data_ptr(), params["bn1.bias"].data_ptr(), BN_EPS,
-                self.momentum, N.ptr(params.get("bn1.running_mean")), N.ptr(params.get("bn1.running_var")), None, 0,
-                ws.data_ptr(), ws.numel(), m0.data_ptr(), i0.data_ptr(), z0.data_ptr(), N.stream_ptr()))
+                y0.data_ptr(), rows, 64, 64, params["bn1.weight"].data_ptr(), params["bn1.bias"].data_ptr(), BN_EPS,
+                self.momentum, N.ptr(params.get("bn1.running_mean")), N.ptr(params.get("bn1.running_var")), None,
+                int(self.ibn), ws.data_ptr(), ws.numel(), m0.data_ptr(), i0.data_ptr(), z0.data_ptr(), N.stream_ptr()))
             hp, wp = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
             a = torch.empty(n, hp, wp, 64, dtype=torch.float16, device=self.device)
             arg = torch.empty(n, hp, wp, 64, dtype=torch.uint8, device=self.device)
@@ -171,7 +195,8 @@ class TrunkTrainer:
                 for bi in range(nblk):
                     p = f"layer{li}.{bi}"
                     stride = stride0 if bi == 0 else 1
-                    o1, h1, w1, s1 = self._conv_bn(a, n, h, w, params, p + ".conv1", p + ".bn1", 1, 1, True)
+                    o1, h1, w1, s1 = self._conv_bn(a, n, h, w, params, p + ".conv1", p + ".bn1", 1, 1, True,
+                                                   ibn=self.ibn and planes != 512)
                     o2, h2, w2, s2 = self._conv_bn(o1, n, h1, w1, params, p + ".conv2", p + ".bn2", 3, stride, True)
                     sd = None
                     res = a
@@ -192,17 +217,38 @@ class TrunkTrainer:
         n, ho, wo = s.shape_out
         c = s.y.shape[-1]
         rows = n * ho * wo
-        dg, db = torch.empty(c, device=self.device), torch.empty(c, device=self.device)
         dy = torch.empty_like(s.y)
-        ws = self._bn_ws(rows, c)
-        N.check(N.lib().ctl_bn_train_backward_nhwc_f16(
-            dz.data_ptr(), s.z.data_ptr() if relu_mask else None, s.y.data_ptr(), rows, c,
-            params[s.bn + ".weight"].data_ptr(), s.mean.data_ptr(), s.invstd.data_ptr(), 1.0 / self.grad_scale,
-            ws.data_ptr(), ws.numel(), dz.data_ptr() if relu_mask else None, dg.data_ptr(), db.data_ptr(), dy.data_ptr(),
+        L = N.lib()
+        if getattr(s, "ibn", None) is None:
+            dg, db = torch.empty(c, device=self.device), torch.empty(c, device=self.device)
+            ws = self._bn_ws(rows, c)
+            N.check(L.ctl_bn_train_backward_nhwc_f16(
+                dz.data_ptr(), s.z.data_ptr() if relu_mask else None, s.y.data_ptr(), rows, c, c,
+                params[s.bn + ".weight"].data_ptr(), s.mean.data_ptr(), s.invstd.data_ptr(), 1.0 / self.grad_scale,
+                ws.data_ptr(), ws.numel(), dz.data_ptr() if relu_mask else None, dg.data_ptr(), db.data_ptr(),
+                dy.data_ptr(), N.stream_ptr()))
+            self.launches += 3
+            grads[s.bn + ".weight"], grads[s.bn + ".bias"] = dg, db
+            return dy  # (dz now holds g = dz * mask when relu_mask)
+        half, im, ii = s.ibn
+        dgp, dbp = torch.empty(n, half, device=self.device), torch.empty(n, half, device=self.device)
+        N.check(L.ctl_instnorm_train_backward_nhwc_f16(
+            dz.data_ptr(), s.z.data_ptr(), s.y.data_ptr(), n, ho * wo, c, half, params[s.bn + ".IN.weight"].data_ptr(),
+            im.data_ptr(), ii.data_ptr(), 1.0 / self.grad_scale, dgp.data_ptr(), dbp.data_ptr(), dy.data_ptr(),
             N.stream_ptr()))
-        self.launches += 3
-        grads[s.bn + ".weight"], grads[s.bn + ".bias"] = dg, db
-        return dy  # (dz now holds g = dz * mask when relu_mask)
+        grads[s.bn + ".IN.weight"], grads[s.bn + ".IN.bias"] = dgp.sum(0), dbp.sum(0)
+        cb = c - half
+        dg, db = torch.empty(cb, device=self.device), torch.empty(cb, device=self.device)
+        ws = self._bn_ws(rows, cb)
+        off = half * 2
+        N.check(L.ctl_bn_train_backward_nhwc_f16(
+            dz.data_ptr() + off, s.z.data_ptr() + off, s.y.data_ptr() + off, rows, cb, c,
+            params[s.bn + ".BN.weight"].data_ptr(), s.mean.data_ptr(), s.invstd.data_ptr(), 1.0 / self.grad_scale,
+            ws.data_ptr(), ws.numel(), dz.data_ptr() + off, dg.data_ptr(), db.data_ptr(), dy.data_ptr() + off,
+            N.stream_ptr()))
+        self.launches += 6
+        grads[s.bn + ".BN.weight"], grads[s.bn + ".BN.bias"] = dg, db
+        return dy
 
     def _wgrad(self, a, shape_in, dy, cout, k, stride):
         n, h, w = shape_in
@@ -275,7 +321,8 @@ class TrunkTrainer:
                                                                 N.stream_ptr()))
             st = _Saved()
             st.y, st.z, st.mean, st.invstd, st.bn, st.shape_out = y0, z0, m0, i0, "bn1", (n, h, w)
-            dy0 = self._bn_bwd(st, dz0, False, params, grads)
+            st.ibn = None
+            dy0 = self._bn_bwd(st, dz0, self.ibn, params, grads)  # IBN-a keeps the ReLU after the stem
             col = torch.empty(n, h, w, 192, dtype=torch.float16, device=self.device)
             N.check(L.ctl_stem_im2col_f16(self._x.data_ptr(), n, H, W, col.data_ptr(), N.stream_ptr()))
             self.launches += 2

@@ -78,13 +78,10 @@ class Baseline(nn.Module):
     def forward(self, x):
         """modelling/baseline.py:91-96.  base_out is returned in the reference's NCHW view."""
         if self.training:
-            if self.base.ibn:
-                raise NotImplementedError("train-mode IBN-a trunk (InstanceNorm training kernels) is not built; "
-                                          "resnet50/101/152 train on the B200 engine (DESIGN.md)")
             dev = next(self.base.parameters()).device
             if self._trainer is None or self._trainer.device != dev:
                 self._trainer = TrunkTrainer(dev, last_stride=self.base.last_stride, layers=self.base.layers_cfg,
-                                             graphs=os.environ.get("CTL_TRAIN_GRAPHS", "1") == "1")
+                                             graphs=os.environ.get("CTL_TRAIN_GRAPHS", "1") == "1", ibn=self.base.ibn)
             names = [k for k, _ in self.base.named_parameters()]
             tensors = [v for _, v in self.base.named_parameters()]
             buffers = {k: v for k, v in self.base.named_buffers() if "running" in k}

@@ -253,7 +253,9 @@ int ctl_conv2d_wgrad_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, in
                               ctl_stream_t stream);
 
 /* BatchNorm2d with batch statistics (torch.nn.BatchNorm2d in train mode, resnet.py:72-85) over NHWC fp16
- * [rows = N*H*W][c]; c a power of two in [64, 2048].  forward: mean / biased variance over the rows (fp32 partial
+ * [rows = N*H*W] rows of `pitch` elements, normalising the c channels that start at the given pointers (pitch == c
+ * for a dense tensor; pitch > c addresses a channel slice, e.g. the BatchNorm half of an IBN layer); c a power of two
+ * in [32, 2048].  forward: mean / biased variance over the rows (fp32 partial
  * sums combined in double, deterministic), running statistics updated in place when given (momentum, unbiased
  * variance), out = [relu](gamma * (y - mean) * invstd + beta [+ residual]) rounded to fp16; save_mean / save_invstd
  * feed the backward.  backward: g = dz * (z > 0) when the ReLU output z is given (g is written to g_out, which may
@@ -261,14 +263,25 @@ int ctl_conv2d_wgrad_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, in
  * dy = gamma * invstd * (g - mean_rows(g) - xhat * mean_rows(g * xhat)) rounded to fp16.
  * Workspace: ctl_bn_workspace_bytes(rows, c). */
 size_t ctl_bn_workspace_bytes(int64_t rows, int32_t c);
-int ctl_bn_train_forward_nhwc_f16(const void* y, int64_t rows, int32_t c, const float* gamma, const float* beta, float eps,
+int ctl_bn_train_forward_nhwc_f16(const void* y, int64_t rows, int32_t c, int32_t pitch, const float* gamma, const float* beta, float eps,
                                   float momentum, float* running_mean, float* running_var, const void* residual,
                                   int32_t relu, void* workspace, size_t workspace_bytes, float* save_mean,
                                   float* save_invstd, void* out, ctl_stream_t stream);
-int ctl_bn_train_backward_nhwc_f16(const void* dz, const void* z, const void* y, int64_t rows, int32_t c, const float* gamma,
+int ctl_bn_train_backward_nhwc_f16(const void* dz, const void* z, const void* y, int64_t rows, int32_t c, int32_t pitch, const float* gamma,
                                    const float* save_mean, const float* save_invstd, float grad_unscale, void* workspace,
                                    size_t workspace_bytes, void* g_out, float* dgamma, float* dbeta, void* dy,
                                    ctl_stream_t stream);
+/* InstanceNorm2d(affine) + ReLU of an IBN layer's first `half` channels in train mode (resnet_ibn_a.py:18-32): y, out,
+ * dz, z, dy are NHWC fp16 with rows of `pitch` elements ([n][hw][pitch]); instance statistics (biased variance) per
+ * (image, channel) are saved as [n][half] fp32.  backward: g = dz * (z > 0) is written back over dz; dgamma_part /
+ * dbeta_part are per-image partials [n][half] (sum over n = the parameter gradient), multiplied by grad_unscale. */
+int ctl_instnorm_train_forward_nhwc_f16(const void* y, int32_t n, int32_t hw, int32_t pitch, int32_t half, const float* gamma,
+                                        const float* beta, float eps, float* save_mean, float* save_invstd, void* out,
+                                        ctl_stream_t stream);
+int ctl_instnorm_train_backward_nhwc_f16(void* dz, const void* z, const void* y, int32_t n, int32_t hw, int32_t pitch,
+                                         int32_t half, const float* gamma, const float* save_mean, const float* save_invstd,
+                                         float grad_unscale, float* dgamma_part, float* dbeta_part, void* dy,
+                                         ctl_stream_t stream);
 /* Backward helpers of the trunk: global average pool (out[n][p][c] = dfeat[n][c] * scale, fp16), max-pool 3x3/2 pad 1
  * (gradient routed to the first maximum of every window, like torch), zero-insertion upsampling
  * out[n][2i][2j] = x[n][i][j] (+ add) (the transpose of a stride-2 subsampling), and the stem's im2col

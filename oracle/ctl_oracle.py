@@ -581,12 +581,14 @@ class _RoundHalfSTE(torch.autograd.Function):
         return g
 
 
-def trunk_train_fp16sim(x, sd, dfeat=None, last_stride=1, layers=R50_LAYERS, momentum=0.1, forced=None):
+def trunk_train_fp16sim(x, sd, dfeat=None, last_stride=1, layers=R50_LAYERS, momentum=0.1, forced=None, ibn=False):
     """Train-mode trunk (ResNet.forward resnet.py:122-133 with BatchNorm2d batch statistics, Bottleneck.forward
     :67-87) in float64 with the B200 training path's rounding points: fp16 crops and conv weights, every stored
     activation (conv output, BN/ReLU output) rounded to fp16, statistics / BN arithmetic / GAP in full precision.
     Returns (global_feat, grads, running) where grads maps state_dict names -> d(sum(global_feat * dfeat))/d(param)
-    and running holds the updated running statistics.  ResNet-50 family only (no IBN).
+    and running holds the updated running statistics.  ibn=True: the IBN-a variant (resnet_ibn_a.py:18-32,54-74,126-141:
+    ReLU after the stem; bn1 of layer1-3 = InstanceNorm2d(affine) on the first half of the channels, BatchNorm2d on
+    the rest).
 
     `forced`: optional list of (y, z) NCHW tensors, one per conv+BN in execution order (stem, then per block conv1,
     conv2, [downsample], conv3): the VALUES of the stored activations are replaced by these (the engine's own fp16
@@ -603,29 +605,37 @@ def trunk_train_fp16sim(x, sd, dfeat=None, last_stride=1, layers=R50_LAYERS, mom
     def force(t, val):
         return t if val is None else val.double() + (t - t.detach())
 
-    def conv_bn(a, conv, name, k, stride, res=None, relu=True):
-        fy, fz = next(it) if it is not None else (None, None)
-        y = force(q(F.conv2d(a, q(P[conv + ".weight"]), None, stride, k // 2)), fy)
+    def batch_norm(y, name):
         mean = y.mean(dim=(0, 2, 3))
         var = y.var(dim=(0, 2, 3), unbiased=False)
         cnt = y.numel() / y.shape[1]
         running[name + ".running_mean"] = (1 - momentum) * sd[name + ".running_mean"].double() + momentum * mean.detach()
         running[name + ".running_var"] = ((1 - momentum) * sd[name + ".running_var"].double()
                                           + momentum * var.detach() * cnt / max(cnt - 1, 1))
-        z = ((y - mean[None, :, None, None]) / torch.sqrt(var + eps)[None, :, None, None]
-             * P[name + ".weight"][None, :, None, None] + P[name + ".bias"][None, :, None, None])
+        return ((y - mean[None, :, None, None]) / torch.sqrt(var + eps)[None, :, None, None]
+                * P[name + ".weight"][None, :, None, None] + P[name + ".bias"][None, :, None, None])
+
+    def conv_bn(a, conv, name, k, stride, res=None, relu=True, ibn_layer=False):
+        fy, fz = next(it) if it is not None else (None, None)
+        y = force(q(F.conv2d(a, q(P[conv + ".weight"]), None, stride, k // 2)), fy)
+        if ibn_layer:
+            half = y.shape[1] // 2
+            z = torch.cat((F.instance_norm(y[:, :half], None, None, P[name + ".IN.weight"], P[name + ".IN.bias"], True, 0.1, eps),
+                           batch_norm(y[:, half:], name + ".BN")), 1)
+        else:
+            z = batch_norm(y, name)
         if res is not None:
             z = z + res
         return force(q(F.relu(z) if relu else z), fz)
 
-    a = conv_bn(q(x.double()), "conv1", "bn1", 7, 2, relu=False)  # resnet.py:125: no ReLU after the stem
+    a = conv_bn(q(x.double()), "conv1", "bn1", 7, 2, relu=ibn)  # resnet.py:125: no ReLU after the stem; IBN-a has one
     a = F.max_pool2d(a, 3, 2, 1)
     for li, (planes, nblk) in enumerate(zip((64, 128, 256, 512), layers), start=1):
         stride0 = 1 if li == 1 else (last_stride if li == 4 else 2)
         for bi in range(nblk):
             p = f"layer{li}.{bi}"
             stride = stride0 if bi == 0 else 1
-            o1 = conv_bn(a, p + ".conv1", p + ".bn1", 1, 1)
+            o1 = conv_bn(a, p + ".conv1", p + ".bn1", 1, 1, ibn_layer=ibn and planes != 512)
             o2 = conv_bn(o1, p + ".conv2", p + ".bn2", 3, stride)
             res = a
             if bi == 0:

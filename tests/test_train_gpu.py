@@ -80,7 +80,7 @@ def test_bn_train_forward_backward(rows, c, relu, res):
     ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
     sm, si = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
     out = torch.empty(rows, c, dtype=torch.float16, device="cuda")
-    N.check(L.ctl_bn_train_forward_nhwc_f16(yc.data_ptr(), rows, c, gam.data_ptr(), bet.data_ptr(), eps, mom, rmc.data_ptr(),
+    N.check(L.ctl_bn_train_forward_nhwc_f16(yc.data_ptr(), rows, c, c, gam.data_ptr(), bet.data_ptr(), eps, mom, rmc.data_ptr(),
                                             rvc.data_ptr(), N.ptr(rc_), relu, ws.data_ptr(), nb, sm.data_ptr(), si.data_ptr(),
                                             out.data_ptr(), N.stream_ptr()))
     torch.cuda.synchronize()
@@ -95,7 +95,7 @@ def test_bn_train_forward_backward(rows, c, relu, res):
     dy = torch.empty(rows, c, dtype=torch.float16, device="cuda")
     gbuf = torch.empty_like(dzc)
     zc = zref16.cuda()
-    N.check(L.ctl_bn_train_backward_nhwc_f16(dzc.data_ptr(), zc.data_ptr() if relu else None, yc.data_ptr(), rows, c,
+    N.check(L.ctl_bn_train_backward_nhwc_f16(dzc.data_ptr(), zc.data_ptr() if relu else None, yc.data_ptr(), rows, c, c,
                                              gam.data_ptr(), sm.data_ptr(), si.data_ptr(), 0.5, ws.data_ptr(), nb,
                                              gbuf.data_ptr() if relu else None, dgam.data_ptr(), dbet.data_ptr(),
                                              dy.data_ptr(), N.stream_ptr()))
@@ -343,3 +343,43 @@ def test_full_training_iterations_reduce_the_loss():
     assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
     assert not torch.equal(w0, model.backbone.base.layer2[0].conv2.weight)
     assert all(torch.isfinite(p_).all() for p_ in model.parameters())
+
+
+def test_ibn_trunk_train_step_teacher_forced():
+    """ResNet50-IBN-a train step (resnet_ibn_a.py): ReLU after the stem, InstanceNorm half + BatchNorm half as bn1 of
+    layer1-3 (channel-slice kernels), 80x40 crops (non-power-of-two maps, partial tiles) -- same two-level check as the
+    plain trunk."""
+    from oracle import ctl_oracle as O
+    from ctl_b200.modelling.backbones.engine_train import TrunkTrainer
+
+    sd = O.make_trunk_state(seed=13, ibn=True)
+    g = torch.Generator().manual_seed(5)
+    n, H, W = 6, 160, 80
+    x = torch.randn(n, 3, H, W, generator=g)
+    dfeat = torch.randn(n, 2048, generator=g) * 1e-3
+    params = {k: v.clone().cuda() for k, v in sd.items() if v.is_floating_point()}
+    tr = TrunkTrainer("cuda", grad_scale=4096.0, ibn=True)
+    feat = tr.forward(x.cuda(), params)
+    torch.cuda.synchronize()
+    nchw = lambda t: t.cpu().float().permute(0, 3, 1, 2)  # noqa: E731
+    forced = [(nchw(tr._stem[0]), nchw(tr._stem[1]))] + [(nchw(s.y), nchw(s.z)) for s in tr.saved]
+    grads = tr.backward(dfeat.cuda())
+    torch.cuda.synchronize()
+    feat_o, _, running_o = O.trunk_train_fp16sim(x, sd, ibn=True)
+    assert _rel(feat.cpu(), feat_o) <= 2e-2
+    for k, v in running_o.items():
+        assert _rel(params[k].cpu(), v) <= 2e-2, k
+    feat_f, grads_f, _ = O.trunk_train_fp16sim(x, sd, dfeat, forced=forced, ibn=True)
+    grads_f = {k: v for k, v in grads_f.items() if v is not None}  # the unused ImageNet fc head has no gradient
+    assert set(grads.keys()) == set(grads_f.keys())
+    assert _rel(feat.cpu(), feat_f) <= 1e-5
+    gscale = max(float(v.abs().max()) for v in grads_f.values())
+    bad = {}
+    for k, go in grads_f.items():
+        assert torch.isfinite(grads[k]).all(), k
+        if float(go.abs().max()) < 1e-6 * gscale:
+            continue
+        r = _rel(grads[k].cpu(), go)
+        if r > 2e-2:
+            bad[k] = r
+    assert not bad, f"gradient mismatch (max-norm relative): {sorted(bad.items(), key=lambda t: -t[1])[:8]}"
