@@ -285,10 +285,13 @@ def conv_traffic():
         return None
 
 
-def run_train_step(local, steps=5, warmup=2):
-    """BASELINE config 2: one CTL training step (ResNet-50 256x128, 16 ids x 16 instances, fp16 activations):
-    train-mode trunk forward (batch-stat BN) -> fused CTL/center/xent/triplet loss step -> backward through the
-    loss and the trunk (all parameter gradients) -> fused Adam + center-SGD step.  Device-timed with CUDA events."""
+def run_train_step(local, steps=5, warmup=2, model_name="resnet50", size=(256, 128), P=16, K=16, world=1):
+    """BASELINE config 2 (and, with model_name="resnet50_ibn_a", size=(320, 320), P=32, K=4, world=8, config 4):
+    one complete CTL training iteration per step -- train-mode trunk forward (batch-stat BN) -> fused
+    CTL/center/xent/triplet loss step -> backward through the loss and the trunk (all parameter gradients) ->
+    [world > 1: NCCL mean all-reduce of the gradients in flat buckets] -> fused Adam + center-SGD step.
+    Every rank trains on its own P x K batch (weak scaling, like the reference's DDP).  Device-timed with CUDA
+    events; the caller takes the max over ranks."""
     import ctl_b200  # noqa: F401
     from ctl_b200.modelling.ctl_model import CTLModel
 
@@ -304,13 +307,14 @@ def run_train_step(local, steps=5, warmup=2):
                            QUERY_CONTRASTIVE_WEIGHT=1.0, CENTROID_CONTRASTIVE_WEIGHT=1.0, OPTIMIZER_NAME="Adam",
                            BASE_LR=1e-4, WEIGHT_DECAY=5e-4, CENTER_LR=0.5, LR_SCHEDULER_NAME="multistep_lr",
                            LR_STEPS=(40, 70), GAMMA=0.1, USE_WARMUP_LR=True, WARMUP_EPOCHS=10),
-                 DATALOADER=_C(NUM_INSTANCE=16), TEST=_C(FEAT_NORM=True, ONLY_TEST=False, VISUALIZE="no"),
+                 DATALOADER=_C(NUM_INSTANCE=K), TEST=_C(FEAT_NORM=True, ONLY_TEST=False, VISUALIZE="no"),
                  USE_MIXED_PRECISION=True)
     torch.manual_seed(0)
+    from ctl_b200 import parallel
+
     model = CTLModel(cfg, num_classes=751, num_query=0).to(dev).train()
-    P, K = 16, 16
-    g = torch.Generator().manual_seed(1234)
-    x = torch.randn(P * K, 3, H, W, generator=g).to(dev)
+    g = torch.Generator().manual_seed(1234 + local)
+    x = torch.randn(P * K, 3, size[0], size[1], generator=g).to(dev)
     labels = torch.arange(P).repeat_interleave(K).to(dev)
     cam = torch.zeros(P * K, dtype=torch.long, device=dev)
     is_real = torch.ones(P * K, dtype=torch.bool, device=dev)
@@ -322,6 +326,8 @@ def run_train_step(local, steps=5, warmup=2):
             p_.grad = None
         out = model.training_step((x, labels, cam, is_real), 0)
         out["loss"].backward()
+        if world > 1:
+            parallel.allreduce_gradients(model.parameters())  # one mean all-reduce over NCCL, flat fp32 buckets
         model.optimizer_step_manual(opt, opt_center, epoch=0)  # fused Adam + center SGD (solver/build.py)
         return out["loss"]
 
@@ -335,9 +341,18 @@ def run_train_step(local, steps=5, warmup=2):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    return {"metric": "CTL training step images/sec (resnet50 256x128, 16 ids x 16 instances, fwd+loss+bwd+optimizer)",
-            "value": P * K / ms * 1e3, "unit": "images/s", "ms_per_step": ms, "steps": steps, "loss": float(loss),
-            "tflops": 3 * P * K * GFLOP_PER_IMG / ms, "note": "3 x forward FLOPs per image; includes the fused Adam / center-SGD step",
+    if world > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    gflop = GFLOP_PER_IMG if (model_name == "resnet50" and tuple(size) == (256, 128)) else None
+    return {"metric": f"CTL training step images/sec ({model_name} {size[0]}x{size[1]}, {P} ids x {K} instances per GPU, "
+                      "fwd+loss+bwd+optimizer)",
+            "value": world * P * K / ms * 1e3, "unit": "images/s", "ms_per_step": ms, "steps": steps, "loss": float(loss.detach()),
+            "tflops": (3 * world * P * K * gflop / ms) if gflop else None,
+            "note": "3 x forward FLOPs per image; includes the gradient all-reduce (N > 1) and the fused Adam / center-SGD step",
             "peak_mem_gib": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
 
 
@@ -477,7 +492,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="embed", choices=["embed", "retrieval"])
+    ap.add_argument("--workload", default="embed", choices=["embed", "retrieval", "train"])
+    ap.add_argument("--train-model", default="resnet50", choices=["resnet50", "resnet50_ibn_a"])
+    ap.add_argument("--train-size", default="256x128", help="HxW of the training crops (config 4: 320x320)")
+    ap.add_argument("--train-pk", default="16x16", help="ids x instances per GPU (config 4: 32x4)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary metric and the CPU baseline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -534,6 +552,23 @@ def main():
                 rv, rdt = cpu_retrieval(128)
                 line["retrieval"]["cpu_baseline"] = {"value": rv, "unit": "pairs/s", "cores": _host_threads(), "kind": "port",
                                                      "sample": f"128 of {RET_Q} queries x {RET_G} gallery through oracle.r1_map_compute, {rdt:.1f} s"}
+        elif args.workload == "train":
+            hh, ww = (int(v) for v in args.train_size.split("x"))
+            pp, kk = (int(v) for v in args.train_pk.split("x"))
+            if world > 1:
+                dist.barrier()
+            with ClockSampler(local) as clk:
+                with clk.window():
+                    r = run_train_step(local, steps=args.steps, warmup=args.warmup, model_name=args.train_model,
+                                       size=(hh, ww), P=pp, K=kk, world=world)
+            line = {"metric": r["metric"], "value": r["value"], "unit": r["unit"], "n_gpus": world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+                    "config": {"workload": f"CTL training iteration, {args.train_model} {hh}x{ww}, {pp} ids x {kk} instances per GPU, "
+                                           "random-init weights", "global_batch": pp * kk * world,
+                               "parallelism": f"dp{world}: per-rank P x K batches, one NCCL mean all-reduce of the gradients"},
+                    "tflops": r["tflops"], "loss": r["loss"], "peak_mem_gib": r["peak_mem_gib"], "clocks": clk.summary(),
+                    "roofline": None, "e2e": None, "note": r["note"]}
         else:
             with ClockSampler(local) as clk:
                 with clk.window():
