@@ -581,7 +581,8 @@ class _RoundHalfSTE(torch.autograd.Function):
         return g
 
 
-def trunk_train_fp16sim(x, sd, dfeat=None, last_stride=1, layers=R50_LAYERS, momentum=0.1, forced=None, ibn=False):
+def trunk_train_fp16sim(x, sd, dfeat=None, last_stride=1, layers=R50_LAYERS, momentum=0.1, forced=None, ibn=False,
+                        round_fp16=True):
     """Train-mode trunk (ResNet.forward resnet.py:122-133 with BatchNorm2d batch statistics, Bottleneck.forward
     :67-87) in float64 with the B200 training path's rounding points: fp16 crops and conv weights, every stored
     activation (conv output, BN/ReLU output) rounded to fp16, statistics / BN arithmetic / GAP in full precision.
@@ -596,7 +597,9 @@ def trunk_train_fp16sim(x, sd, dfeat=None, last_stride=1, layers=R50_LAYERS, mom
     so two correct fp16 forwards that differ in the last bit produce visibly different gradients; teacher-forcing
     the stored activations isolates the backward arithmetic from that effect."""
     eps = 1e-5
-    q = _RoundHalfSTE.apply
+    # round_fp16=False drops the engine's storage rounding: the function is then the reference's own train-mode
+    # arithmetic in float64 (pinned against the reference run in fp32, tests/golden/trunk_train.npz)
+    q = _RoundHalfSTE.apply if round_fp16 else (lambda t: t)
     P = {k: v.detach().double().requires_grad_(True) for k, v in sd.items()
          if v.is_floating_point() and "running" not in k}
     running = {}

@@ -243,9 +243,57 @@ def gen_trunk(ref):
     np.savez_compressed(os.path.join(GOLD, "trunk.npz"), **out)
 
 
+TRAIN_GRAD_KEYS = ("conv1.weight", "bn1.weight", "layer1.0.conv2.weight", "layer1.0.bn1.{bn}weight", "layer2.0.downsample.0.weight",
+                   "layer3.2.conv1.weight", "layer4.2.conv3.weight", "layer4.2.bn3.weight", "layer4.2.bn3.bias")
+
+
+def grad_sample(t, n=4096):
+    """<= n evenly strided elements of a gradient, followed by its sum and its absolute sum (keeps the fixture small)."""
+    f = t.detach().flatten().double()
+    stride = max(1, f.numel() // n)
+    return torch.cat((f[::stride][:n], f.sum()[None], f.abs().sum()[None])).numpy()
+
+
+def gen_trunk_train(ref):
+    """The reference's own trunk in TRAIN mode (batch-statistics BatchNorm, IBN) under torch autograd on the CPU
+    (float64 for the plain ResNet; fp32 for IBN-a, whose InstanceNorm over 8 positions amplifies fp32 round-off to
+    ~3e-3): global_feat, a sample of parameter gradients of
+    sum(global_feat * dfeat), and updated running statistics."""
+    out = {}
+    for ibn, mname in ((False, "resnet50"), (True, "resnet50_ibn_a")):
+        tag = "ibn" if ibn else "r50"
+        sd = O.make_trunk_state(seed=17, ibn=ibn)
+        cfg = default_cfg(ref)
+        cfg.MODEL.NAME = mname
+        base = ref.baseline.Baseline(cfg)
+        base.base.load_state_dict(sd, strict=True)
+        # plain ResNet: float64 run of the same code; IBN-a casts its InstanceNorm input to fp32 itself
+        # (resnet_ibn_a.py:29), so that variant can only run in fp32
+        dt = torch.float32 if ibn else torch.float64
+        base.to(dt).train()
+        g = torch.Generator().manual_seed(23)
+        x = torch.randn(4, 3, 64, 32, generator=g)
+        dfeat = torch.randn(4, 2048, generator=g) * 1e-2
+        _, feat = base(x.to(dt))
+        (feat * dfeat.to(dt)).sum().backward()
+        params = dict(base.base.named_parameters())
+        out[f"{tag}_in_checksum"] = checksum(torch.cat((x.flatten(), dfeat.flatten())))
+        out[f"{tag}_feat"] = feat.detach().numpy()
+        for key in TRAIN_GRAD_KEYS:
+            k = key.format(bn="BN." if ibn else "")
+            out[f"{tag}_grad_{k}"] = grad_sample(params[k].grad)
+        if ibn:
+            out[f"{tag}_grad_layer1.0.bn1.IN.weight"] = grad_sample(params["layer1.0.bn1.IN.weight"].grad)
+        bufs = dict(base.base.named_buffers())
+        for k in ("bn1.running_mean", "layer4.2.bn3.running_var"):
+            out[f"{tag}_run_{k}"] = bufs[k].numpy()
+        print(f"trunk train {tag}: feat std {float(feat.std()):.4f}, |dW conv1| {float(params['conv1.weight'].grad.abs().max()):.4e}")
+    np.savez_compressed(os.path.join(GOLD, "trunk_train.npz"), **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="loss,masks,retrieval,centroids,trunk,market")
+    ap.add_argument("--only", default="loss,masks,retrieval,centroids,trunk,trunk_train,market")
     args = ap.parse_args()
     only = set(args.only.split(","))
     os.makedirs(GOLD, exist_ok=True)
@@ -263,6 +311,8 @@ def main():
         gen_centroids(ref)
     if "trunk" in only:
         gen_trunk(ref)
+    if "trunk_train" in only:
+        gen_trunk_train(ref)
     if "market" in only:
         # BASELINE config 3 shape; the reference's per-query python loop takes ~80 s here
         gen_retrieval(ref, "market", 3368, 15913, 751, 3.0, 0, store_dist=False)

@@ -175,3 +175,41 @@ def test_oracle_augment_pinned_against_reference_random_erasing():
                 break
         got = O.augment_batch(img, np.array([[0, pad, pad, x1, y1, h, w, 1]]), mean, std, pad)[0]
         assert torch.allclose(got, out_ref, rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("tag,ibn", [("r50", False), ("ibn", True)])
+def test_train_mode_oracle_pinned_against_reference_autograd(tag, ibn):
+    """oracle.trunk_train_fp16sim with the storage rounding switched off IS the reference's train-mode trunk
+    (batch-stat BN / IBN, autograd): features, sampled parameter gradients and running statistics against the
+    reference code run in float64 (tests/golden/trunk_train.npz, oracle/make_golden.py:gen_trunk_train); with the rounding on
+    (what the B200 engine is checked against) it stays within fp16 distance of the same numbers."""
+    from oracle.make_golden import TRAIN_GRAD_KEYS, grad_sample
+
+    gd = load_golden("trunk_train.npz")
+    sd = O.make_trunk_state(seed=17, ibn=ibn)
+    g = torch.Generator().manual_seed(23)
+    x = torch.randn(4, 3, 64, 32, generator=g)
+    dfeat = torch.randn(4, 2048, generator=g) * 1e-2
+    assert np.array_equal(gd[f"{tag}_in_checksum"], checksum(torch.cat((x.flatten(), dfeat.flatten()))))
+    keys = [k.format(bn="BN." if ibn else "") for k in TRAIN_GRAD_KEYS] + (["layer1.0.bn1.IN.weight"] if ibn else [])
+    for rnd, tol in ((False, 6e-3 if ibn else 1e-7), (True, 1e-1)):  # the IBN golden is an fp32 run (see make_golden)
+        feat, grads, running = O.trunk_train_fp16sim(x, sd, dfeat, ibn=ibn, round_fp16=rnd)
+        ref = gd[f"{tag}_feat"]
+        assert np.abs(feat.numpy() - ref).max() <= (tol if not rnd else 5e-3) * np.abs(ref).max()
+        for k in keys:
+            got, exp = grad_sample(grads[k]), gd[f"{tag}_grad_{k}"]
+            scale = np.abs(exp[:-2]).max()
+            if not rnd and not ibn:
+                assert np.abs(got[:-2] - exp[:-2]).max() <= tol * scale, k
+                assert abs(got[-1] - exp[-1]) <= tol * exp[-1], k
+            elif not rnd:
+                # fp32 golden: a handful of ReLU masks flip against the float64 oracle (isolated elements off by a few
+                # per cent), everything else agrees to fp32 round-off
+                err = np.abs(got[:-2] - exp[:-2])
+                cos = float(np.dot(got[:-2], exp[:-2]) / (np.linalg.norm(got[:-2]) * np.linalg.norm(exp[:-2])))
+                assert np.quantile(err, 0.99) <= tol * scale and cos >= 0.9995 and abs(got[-1] / exp[-1] - 1) <= tol, (k, cos)
+            else:  # ReLU masks flip under fp16 rounding: direction and size only
+                cos = float(np.dot(got[:-2], exp[:-2]) / (np.linalg.norm(got[:-2]) * np.linalg.norm(exp[:-2])))
+                assert cos >= 0.97 and abs(got[-1] / exp[-1] - 1) <= tol, (k, cos)
+        for k in ("bn1.running_mean", "layer4.2.bn3.running_var"):
+            np.testing.assert_allclose(running[k].numpy(), gd[f"{tag}_run_{k}"], rtol=5e-3 if (rnd or ibn) else 1e-6, atol=1e-5 if (rnd or ibn) else 1e-9)
