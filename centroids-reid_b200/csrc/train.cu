@@ -25,9 +25,16 @@ struct ConvTapW {
 
 static constexpr int WG_THREADS = 192;            // TMA warp, MMA warp, 4 epilogue warps
 static constexpr int WG_BOX_BYTES = 128 * 64 * 2;  // one [128 px][64 ch] box
-static constexpr int WG_STAGES = 3;
-static constexpr int WG_STAGE_BYTES = 4 * WG_BOX_BYTES;  // dy: 2 boxes (128 cout), x: up to 2 boxes (128 cin)
-static constexpr size_t WG_SMEM = 1024 + WG_STAGES * WG_STAGE_BYTES + 256;
+// two shapes of the work item: N (cin per item) up to 128 with a 3-stage ring, or up to 256 with a 2-stage ring
+// (one dy tile then feeds twice the MMA work: less TMA fill per flop, but a shallower pipeline; CTL_WGRAD_WIDE)
+template <bool WIDE>
+struct WgCfg {
+  static constexpr int XBOXES = WIDE ? 4 : 2;
+  static constexpr int STAGES = WIDE ? 2 : 3;
+  static constexpr int STAGE_BYTES = (2 + XBOXES) * WG_BOX_BYTES;  // dy: 2 boxes (128 cout) + x boxes
+  static constexpr int ACC_COLS = WIDE ? 256 : 128;
+  static constexpr size_t SMEM = 1024 + STAGES * STAGE_BYTES + 256;
+};
 
 struct WgradParams {
   CUtensorMap x_map[4];
@@ -35,7 +42,7 @@ struct WgradParams {
   ConvTapW taps[9];
   int n_taps, cin, cout;
   int TW, TH, tiles_w, tiles_h, m_tiles;
-  int bnw;         // cin per work item: 64 or 128
+  int bnw;         // cin per work item: 64, 128 or (wide kernel) 256
   int cin_chunks;  // cin / bnw
   int cout_tiles;  // ceil(cout / 128)
   int n_items;     // cout_tiles * n_taps * cin_chunks
@@ -56,7 +63,9 @@ __device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, 
   return d;
 }
 
+template <bool WIDE>
 __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
+  constexpr int WG_STAGES = WgCfg<WIDE>::STAGES, WG_STAGE_BYTES = WgCfg<WIDE>::STAGE_BYTES, ACC_COLS = WgCfg<WIDE>::ACC_COLS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + WG_STAGES * WG_STAGE_BYTES;
@@ -80,7 +89,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
     tma_prefetch_desc(&p.dy_map);
     for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.x_map[i]);
   }
-  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  if (warp == 1) tmem_alloc<2 * ACC_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -152,7 +161,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
         unit_range(u, item, t0, t1);
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
-        const uint32_t acc = tmem_base + as * 128;
+        const uint32_t acc = tmem_base + as * ACC_COLS;
         for (int t = t0; t < t1; ++t) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
@@ -190,7 +199,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       float* dst = p.part + ((size_t)split * p.cout_pad + ct * 128 + row) * ktot + tapi * p.cin + chunk * p.bnw;
-      const uint32_t taddr = tmem_base + as * 128 + (static_cast<uint32_t>(quarter * 32) << 16);
+      const uint32_t taddr = tmem_base + as * ACC_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
       for (int c = 0; c < p.bnw; c += 16) {
         uint32_t r[16];
         tmem_ld16(taddr + c, r);
@@ -215,7 +224,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc<256>(tmem_base);
+    tmem_dealloc<2 * ACC_COLS>(tmem_base);
   }
 }
 
@@ -249,7 +258,8 @@ static int wgrad_plan(int n, int h, int w, int cin, int cout, int ksize, int str
   p->n_taps = ksize * ksize;
   p->cin = cin;
   p->cout = cout;
-  p->bnw = cin % 128 == 0 ? 128 : 64;
+  static const int wide_mode = [] { const char* e = getenv("CTL_WGRAD_WIDE"); return e ? atoi(e) : 0; }();
+  p->bnw = (wide_mode && cin % 256 == 0) ? 256 : (cin % 128 == 0 ? 128 : 64);
   p->cin_chunks = cin / p->bnw;
   p->cout_tiles = (cout + 127) / 128;
   p->cout_pad = p->cout_tiles * 128;
@@ -1012,12 +1022,18 @@ int ctl_conv2d_wgrad_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, in
   }
   static bool attr_set = false;
   if (!attr_set) {
-    CTL_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM));
+    CTL_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)WgCfg<false>::SMEM));
+    CTL_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)WgCfg<true>::SMEM));
     attr_set = true;
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = std::min(p.n_items * p.splits, sm_count());
-  CTL_CUDA(launch_k(conv_wgrad_kernel, dim3(grid), dim3(WG_THREADS), WG_SMEM, st, p));
+  if (p.bnw == 256)
+    CTL_CUDA(launch_k(conv_wgrad_kernel<true>, dim3(grid), dim3(WG_THREADS), WgCfg<true>::SMEM, st, p));
+  else
+    CTL_CUDA(launch_k(conv_wgrad_kernel<false>, dim3(grid), dim3(WG_THREADS), WgCfg<false>::SMEM, st, p));
   const size_t n4 = (size_t)cout * p.n_taps * cin / 4;
   const int rgrid = (int)std::min<size_t>((n4 + 255) / 256, (size_t)sm_count() * 8);
   CTL_CUDA(launch_k(wgrad_reduce_kernel, dim3(rgrid), dim3(256), 0, st, (const float*)p.part, p.splits, p.cout_pad, (int)cout,
