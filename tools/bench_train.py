@@ -3,11 +3,11 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import ctl_b200
-from oracle import ctl_oracle as O
+from ctl_b200 import synth
 from ctl_b200.modelling.backbones.engine_train import TrunkTrainer
 
 bs = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-sd = O.make_trunk_state(seed=0)
+sd = synth.make_trunk_state(seed=0)
 params = {k: v.clone().cuda() for k, v in sd.items() if v.is_floating_point()}
 tr = TrunkTrainer("cuda", graphs=os.environ.get("CTL_TRAIN_GRAPHS", "1") == "1")
 x = torch.randn(bs, 3, 256, 128, device="cuda")

@@ -4,10 +4,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import ctl_b200
 from ctl_b200.modelling.backbones.engine import TrunkEngine
-from oracle import ctl_oracle as O
+from ctl_b200 import synth
 
 bs = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-eng = TrunkEngine(O.make_trunk_state(seed=0), "cuda")
+eng = TrunkEngine(synth.make_trunk_state(seed=0), "cuda")
 x = torch.randn(bs, 3, 256, 128, device="cuda")
 for _ in range(3):
     eng.forward(x)
