@@ -75,3 +75,41 @@ def test_pid_path_index_and_no_cpu_fallback(tmp_path):
         raise AssertionError("expected RuntimeError")
     except RuntimeError as e:
         assert "no CPU path" in str(e)
+
+
+def test_c_abi_argument_errors_are_reported_without_a_gpu():
+    """Shape / contract violations are rejected by the C ABI before any device work (status CTL_ERR_INVALID_ARGUMENT,
+    message in ctl_last_error(), mapped to ValueError by the shim) -- the reference raises on the same conditions with
+    Python asserts; nothing silently falls back."""
+    import ctypes as C
+
+    import pytest
+
+    from ctl_b200 import _native as N
+
+    L = N.lib()
+    one = C.c_void_p(16)  # a non-null, 16-byte-aligned dummy pointer: argument checks come before any dereference
+    cases = [
+        lambda: L.ctl_conv2d_nhwc_f16(one, 1, 8, 8, 48, one, one, None, one, 64, 1, 1, 0, 0, None),          # Cin % 64
+        lambda: L.ctl_conv2d_nhwc_f16(one, 1, 8, 8, 64, one, one, None, one, 64, 5, 1, 0, 0, None),          # 5x5
+        lambda: L.ctl_conv2d_nhwc_f16(one, 1, 7, 8, 64, one, one, None, one, 64, 3, 2, 0, 0, None),          # odd H, stride 2
+        lambda: L.ctl_conv2d_wgrad_nhwc_f16(one, 1, 8, 8, 64, one, 96, 1, 1, one, 1 << 30, one, None),       # Cout % 64
+        lambda: L.ctl_bn_train_forward_nhwc_f16(one, 10, 48, 48, one, one, 1e-5, 0.1, None, None, None, 0, one, 1 << 20,
+                                                 one, one, one, None),                                         # C not a power of two
+        lambda: L.ctl_bn_train_forward_nhwc_f16(one, 10, 64, 32, one, one, 1e-5, 0.1, None, None, None, 0, one, 1 << 20,
+                                                 one, one, one, None),                                         # pitch < C
+        lambda: L.ctl_bn_train_backward_nhwc_f16(one, one, one, 10, 64, 64, one, one, one, 1.0, one, 1 << 20, None, one, one,
+                                                  one, None),                                                  # mask without g_out
+        lambda: L.ctl_stem_pool_fused(one, 1, 30, 64, one, one, one, 0, one, None),                           # H % 4
+        lambda: L.ctl_stem_pool_fused(one, 1, 32, 256, one, one, one, 0, one, None),                          # W > 128
+        lambda: L.ctl_instnorm_train_forward_nhwc_f16(one, 1, 16, 64, 12, one, one, 1e-5, one, one, one, None),  # half % 8
+        lambda: L.ctl_adam_multi_step(one, 0, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, 1.0, None),                  # no tensors
+        lambda: L.ctl_augment_batch_u8(one, 1, 8, 8, -1, one, (C.c_float * 3)(0, 0, 0), (C.c_float * 3)(1, 1, 1), one, None),
+    ]
+    for i, call in enumerate(cases):
+        rc = call()
+        assert rc == -1, (i, rc, L.ctl_last_error())
+        assert len(L.ctl_last_error()) > 0
+        with pytest.raises(ValueError):
+            N.check(rc)
+    assert L.ctl_bn_workspace_bytes(10, 48) == 0 and L.ctl_conv2d_wgrad_workspace_bytes(1, 8, 8, 60, 64, 1, 1) == 0
