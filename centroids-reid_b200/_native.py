@@ -84,7 +84,7 @@ SIGNATURES = {
     "ctl_center_loss_step": (C.c_int, [_p, _i32, _i32, _p, _p, _i32, _p, _p, _p, _p, _sz, _p]),
     "ctl_xent_smooth_step": (C.c_int, [_p, _i32, _i32, _p, _f, _p, _p, _p, _sz, _p]),
     "ctl_conv2d_nhwc_f16": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
-    "ctl_debug_set_conv_profile": (None, [_p]),
+    "ctl_conv1x1_dual_nhwc_f16": (C.c_int, [_p, _i32, _p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _p]),
     "ctl_stem_conv7x7": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _i32, _p, _p]),
     "ctl_stem_conv7x7_tc": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _i32, _p, _p]),
     "ctl_stem_pad_bytes": (C.c_size_t, [_i32, _i32, _i32]),
@@ -126,7 +126,7 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name, None)
             if fn is None:
-                continue  # symbol checks live in tests/test_abi.py
+                continue  # symbol checks live in tests/test_host_logic.py
             fn.restype = res
             fn.argtypes = args
         _lib = handle

@@ -34,9 +34,10 @@ static constexpr int CONV_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warp
 static constexpr int A_TILE_BYTES = CBM * CBK * 2;
 
 struct ConvTap {
-  int map;   // which A tensor map (parity view)
+  int map;      // which A tensor map (parity view, or the second source of a K-concatenated 1x1)
   int dh, dw;
-  int koff;  // offset of this tap's channel slab inside the weight K dimension
+  int koff;     // offset of this tap's channel slab inside the weight K dimension
+  int cblocks;  // 64-channel slabs of this tap (its source's Cin / 64)
 };
 
 struct ConvKernelParams {
@@ -46,7 +47,7 @@ struct ConvKernelParams {
   CUtensorMap res_map;  // residual, same geometry
   ConvTap taps[9];
   int n_taps;
-  int cin_blocks;  // Cin / 64
+  int k_blocks;  // sum of the taps' cblocks = K / 64
   int n_img, Ho, Wo, Cout;
   int TW, TH, tiles_w, tiles_h;
   int m_tiles, n_tiles;
@@ -54,7 +55,6 @@ struct ConvKernelParams {
   int has_residual;
   int relu;                 // apply ReLU to channels >= relu_from
   int relu_from;
-  long long* prof;          // optional [gridDim.x][8] cycle counters (tools/prof_conv.py), else null
 };
 
 template <int BN>
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.m_tiles * p.n_tiles;
-  const int conv_kblocks = p.n_taps * p.cin_blocks;
+  const int conv_kblocks = p.k_blocks;
   // contiguous, balanced tile range of this CTA
   const int per = num_tiles / (int)gridDim.x, rem = num_tiles - per * (int)gridDim.x;
   const int t_begin = (int)blockIdx.x * per + min((int)blockIdx.x, rem);
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
         const int h0 = it.th * p.TH, w0 = it.tw * p.TW;
         for (int t = 0; t < p.n_taps; ++t) {
           const ConvTap tap = p.taps[t];
-          for (int cb = 0; cb < p.cin_blocks; ++cb) {
+          for (int cb = 0; cb < tap.cblocks; ++cb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t dst = smem_base + stage * Cfg::STAGE_BYTES;
             mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
@@ -270,23 +270,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     int as = 0;
     uint32_t aphase = 0;
     uint32_t g = 0;  // running sub-tile counter -> staging slab
-    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long tprev = clock64();
-#define CTL_STAMP(i)                         \
-  if (p.prof) {                              \
-    const long long _t = clock64();          \
-    pc[i] += _t - tprev;                     \
-    tprev = _t;                              \
-  }
     TileIter it;
     if (t_begin < t_end) it.init(t_begin, p);
     for (int tile = t_begin; tile < t_end; ++tile, it.next(p)) {
       const int h0 = it.th * p.TH, w0 = it.tw * p.TW;
       const float* bias_t = bias_s + it.nt * BN;  // whole bias vector staged in the prologue
-      CTL_STAMP(7)
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-      CTL_STAMP(0)
       const uint32_t t0 = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16) + chalf * 32;
 #pragma unroll 1
       for (int j = 0; j < NSUB; ++j, ++g) {
@@ -297,11 +287,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
         tmem_ld16(t0 + j * 64 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
         // slab b was handed to a TMA store OUT_SLABS sub-tiles ago: wait until that store has read it
         if (leader) tma_store_wait_read<Cfg::OUT_SLABS - 1>();
-        CTL_STAMP(1)
         named_bar_sync(1, 256);  // also publishes this tile's bias slice
-        CTL_STAMP(2)
         tmem_ld_wait();
-        CTL_STAMP(4)
         if (j == NSUB - 1) {  // last TMEM read of this accumulator stage: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -332,14 +319,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
           for (int q = 0; q < 4; ++q) po[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
           *reinterpret_cast<uint4*>(oslab + (((uint32_t)(chalf * 4 + c) ^ sw) << 4)) = o;
         }
-        CTL_STAMP(5)
         fence_proxy_async();     // staging writes (generic proxy) -> visible to the TMA store (async proxy)
         named_bar_sync(1, 256);  // slab complete
         if (leader) {
           tma_store_4d(&p.out_map, out_stage + b * A_TILE_BYTES, it.nt * BN + j * 64, w0, h0, it.img);
           tma_store_commit();
         }
-        CTL_STAMP(6)
       }
       if (++as == 2) {
         as = 0;
@@ -347,11 +332,6 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       }
     }
     if (leader) tma_store_wait<0>();  // shared memory must outlive the last stores
-    if (p.prof && (leader || (ew == 5 && lane == 7))) {
-      long long* dst = p.prof + ((size_t)blockIdx.x * 2 + (leader ? 0 : 1)) * 8;
-      for (int i = 0; i < 8; ++i) dst[i] = pc[i];
-    }
-#undef CTL_STAMP
   }
   tc_fence_before();
   __syncthreads();
@@ -375,20 +355,53 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
 // multicast to both CTAs' `empty` / `tmem_full` barriers; both epilogues release the accumulator
 // stage on CTA 0's `tmem_empty` barrier.  Each CTA drains its own 128 TMEM lanes.
 // ---------------------------------------------------------------------------------------
-// VAR selects the smem split between the operand ring and the output staging slabs (CTL_PAIR_VARIANT, A/B runs):
-//   0: 4 stages + 4 slabs (5 + 4 for 128-wide tiles)   1 (default): one more stage, 2 slabs
-template <int BN_, int VAR_ = 0>
+// VAR selects the shared-memory split (the total is the 227 KiB of one SM):
+//   1: non-residual layers -- 5 operand stages (6 for 128-wide tiles) + 2 output staging slabs
+//      (measured 2.5-3 % faster than 4 + 4 on the bs-256 trunk);
+//   2: residual layers     -- 4 (5) operand stages + 5 staging slabs that double as residual landing
+//      buffers: the residual tile is TMA-loaded INTO the staging slab three sub-tiles ahead, the
+//      epilogue adds it in place (ld.shared / add / st.shared on the thread's own 64 bytes) and the
+//      same slab is TMA-stored.  Round 1 added the residual with an identity MMA through the operand
+//      ring, which cost 16 N=64 MMAs per 256x256 tile (25 % of the tensor time of a K=512 layer).
+template <int BN_, int VAR_ = 1>
 struct PairCfg {
   static constexpr int BN = BN_;                                  // 256 or 128 output channels per pair tile
+  static constexpr bool RES = VAR_ == 2;
   static constexpr int B_HALF_BYTES = (BN / 2) * CBK * 2;         // this CTA's half of the weight tile: 16 / 8 KiB
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_HALF_BYTES;  // 32 / 24 KiB
-  static constexpr int STAGES = (BN == 256 ? 4 : 5) + (VAR_ == 1 ? 1 : 0);
+  static constexpr int STAGES = (BN == 256 ? 4 : 5) + (RES ? 0 : 1);
   static constexpr int TMEM_COLS = 2 * BN;                        // two accumulator stages
-  static constexpr int OUT_SLABS = VAR_ == 1 ? 2 : 4;
-  static constexpr int IDENT_BYTES = 32 * CBK * 2;  // this CTA's 32 rows of the 64x64 identity
+  static constexpr int OUT_SLABS = RES ? 5 : 2;
+  static constexpr int RES_AHEAD = 3;                             // residual prefetch distance, sub-tiles
   static constexpr int BIAS_BYTES = 2048 * 4;  // the layer's whole bias vector, loaded once
-  static constexpr size_t SMEM =
-      (size_t)STAGES * STAGE_BYTES + OUT_SLABS * A_TILE_BYTES + IDENT_BYTES + BIAS_BYTES + 1024 + 256;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + OUT_SLABS * A_TILE_BYTES + BIAS_BYTES + 1024 + 256;
+};
+
+// pair tile -> (n tile, this CTA's 128-pixel tile); n fastest.  Coordinates advance by carries: one set of
+// integer divisions per role, not per tile.
+struct PairIter {
+  int nt, w_t, h_t, img;
+  __device__ __forceinline__ void init(int tile, const ConvKernelParams& q, int rank_, int per_img) {
+    const int pm = tile / q.n_tiles;
+    nt = tile - pm * q.n_tiles;
+    const int mt = 2 * pm + rank_;
+    img = mt / per_img;
+    const int tr = mt - img * per_img;
+    h_t = tr / q.tiles_w;
+    w_t = tr - h_t * q.tiles_w;
+  }
+  __device__ __forceinline__ void next(const ConvKernelParams& q) {
+    if (++nt < q.n_tiles) return;
+    nt = 0;
+    w_t += 2;  // the pair advances by two 128-pixel tiles
+    while (w_t >= q.tiles_w) {
+      w_t -= q.tiles_w;
+      if (++h_t == q.tiles_h) {
+        h_t = 0;
+        ++img;
+      }
+    }
+  }
 };
 
 template <int BN_T, int VAR_T>
@@ -397,17 +410,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
   using Cfg = PairCfg<BN_T, VAR_T>;
   constexpr int BN = Cfg::BN;
   constexpr int NSUB = BN / 64;
+  constexpr int SLABS = Cfg::OUT_SLABS;
+  constexpr int RES_WAIT = Cfg::RES ? SLABS - Cfg::RES_AHEAD - 1 : 0;  // stores that may still be reading their slab
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t out_stage = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
-  const uint32_t ident = out_stage + Cfg::OUT_SLABS * A_TILE_BYTES;
-  const uint32_t bias_sm = ident + Cfg::IDENT_BYTES;
+  const uint32_t bias_sm = out_stage + SLABS * A_TILE_BYTES;
   const uint32_t bar_base = bias_sm + Cfg::BIAS_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };                         // used in CTA 0 only
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };         // per CTA
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };     // per CTA
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + s); };  // used in CTA 0 only
-  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
+  auto res_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 4 + s); };   // per CTA: residual landed in slab s
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4 + SLABS);
   uint8_t* gsm = smem_raw + (smem_base - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -416,37 +431,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
   const int n_clusters = (int)gridDim.x >> 1, cid = (int)blockIdx.x >> 1;
   const int m_pairs = p.m_tiles >> 1;
   const int num_tiles = m_pairs * p.n_tiles;  // pair tiles
-  const int conv_kblocks = p.n_taps * p.cin_blocks;
+  const int conv_kblocks = p.k_blocks;
   const int per = num_tiles / n_clusters, rem = num_tiles - per * n_clusters;
   const int t_begin = cid * per + min(cid, rem);
   const int t_end = t_begin + per + (cid < rem ? 1 : 0);
   const int tiles_per_img = p.tiles_w * p.tiles_h;
-  // pair tile -> (n tile, this CTA's 128-pixel tile); n fastest.  Coordinates advance by carries: one set of
-  // integer divisions per role, not per tile.
-  struct PairIter {
-    int nt, w_t, h_t, img;
-    __device__ __forceinline__ void init(int tile, const ConvKernelParams& q, int rank_, int per_img) {
-      const int pm = tile / q.n_tiles;
-      nt = tile - pm * q.n_tiles;
-      const int mt = 2 * pm + rank_;
-      img = mt / per_img;
-      const int tr = mt - img * per_img;
-      h_t = tr / q.tiles_w;
-      w_t = tr - h_t * q.tiles_w;
-    }
-    __device__ __forceinline__ void next(const ConvKernelParams& q) {
-      if (++nt < q.n_tiles) return;
-      nt = 0;
-      w_t += 2;  // the pair advances by two 128-pixel tiles
-      while (w_t >= q.tiles_w) {
-        w_t -= q.tiles_w;
-        if (++h_t == q.tiles_h) {
-          h_t = 0;
-          ++img;
-        }
-      }
-    }
-  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -457,6 +446,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
       mbar_init(tfull_bar(s), 1);    // leader's multicast commit
       mbar_init(tempty_bar(s), 16);  // 8 epilogue warps of each CTA
     }
+    for (int s = 0; s < SLABS; ++s) mbar_init(res_bar(s), 1);
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -468,16 +458,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
   if (warp == 1) tmem_alloc2<Cfg::TMEM_COLS>(tmem_slot);
   for (int i = threadIdx.x; i < p.Cout; i += blockDim.x)
     reinterpret_cast<float*>(gsm + (bias_sm - smem_base))[i] = p.bias[i];
-  {  // this CTA's half (rows 32*rank .. +31) of the 64x64 identity, K-major, SWIZZLE_128B
-    uint8_t* id = gsm + (ident - smem_base);
-    for (int i = threadIdx.x; i < Cfg::IDENT_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(id)[i] = make_uint4(0, 0, 0, 0);
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      const int r = threadIdx.x, k = 32 * (int)rank + r;
-      *reinterpret_cast<__half*>(id + r * 128 + (((k >> 3) ^ (r & 7)) << 4) + (k & 7) * 2) = __float2half(1.f);
-    }
-    fence_proxy_async();
-  }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / TMA credit
@@ -498,7 +478,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
         const int nt = it.nt, w0 = it.w_t * p.TW, h0 = it.h_t * p.TH, img = it.img;
         for (int t = 0; t < p.n_taps; ++t) {
           const ConvTap tap = p.taps[t];
-          for (int cb = 0; cb < p.cin_blocks; ++cb) {
+          for (int cb = 0; cb < tap.cblocks; ++cb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t dst = smem_base + stage * Cfg::STAGE_BYTES;
             if (is_leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
@@ -512,26 +492,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
             }
           }
         }
-        if (p.has_residual) {
-          for (int j = 0; j < NSUB; ++j) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            if (is_leader) mbar_arrive_expect_tx(full_bar(stage), 2 * A_TILE_BYTES);
-            else mbar_arrive_cta0(full_bar(stage));
-            tma2_load_4d(smem_base + stage * Cfg::STAGE_BYTES, &p.res_map, full_bar(stage), nt * BN + j * 64, w0, h0, img);
-            if (++stage == Cfg::STAGES) {
-              stage = 0;
-              phase ^= 1u;
-            }
-          }
-        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (is_leader && lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(256, BN);
-      constexpr uint32_t idesc64 = make_idesc_f16(256, 64);
-      const uint64_t d_ident = make_sw128_kmajor_desc(ident);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -555,21 +521,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
             phase ^= 1u;
           }
         }
-        if (p.has_residual) {
-          for (int j = 0; j < NSUB; ++j) {
-            mbar_wait(full_bar(stage), phase);
-            tc_fence_after();
-            const uint64_t da = make_sw128_kmajor_desc(smem_base + stage * Cfg::STAGE_BYTES);
-#pragma unroll
-            for (int k = 0; k < CBK / 16; ++k)
-              umma2_f16(acc + j * 64, desc_advance_k(da, k), desc_advance_k(d_ident, k), idesc64, 1u);
-            umma2_commit_mc(empty_bar(stage), 3);
-            if (++stage == Cfg::STAGES) {
-              stage = 0;
-              phase ^= 1u;
-            }
-          }
-        }
         umma2_commit_mc(tfull_bar(as), 3);
         if (++as == 2) {
           as = 0;
@@ -579,8 +530,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
     }
   } else {
     // ===================== epilogue (both CTAs, own 128 TMEM lanes) =====================
+    // Per 64-channel sub-tile: TMEM -> registers -> (+bias, +residual from the staging slab, ReLU) -> fp16 ->
+    // swizzled staging slab -> one TMA store.  No global memory access is issued by these warps.
     const int ew = warp - 2;
-    const int et = threadIdx.x - 64;
     const int quarter = warp & 3;
     const int chalf = ew >> 2;
     const int pix = quarter * 32 + lane;
@@ -589,40 +541,59 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
     const uint32_t sw = pix & 7;
     uint8_t* oslabs = gsm + (out_stage - smem_base);
     float* bias_s = reinterpret_cast<float*>(gsm + (bias_sm - smem_base));
+    const bool with_res = Cfg::RES && p.has_residual;
     int as = 0;
     uint32_t aphase = 0;
-    uint32_t g = 0;
-    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long tprev = clock64();
-#define CTL_STAMP(i)                \
-  if (p.prof) {                     \
-    const long long _t = clock64(); \
-    pc[i] += _t - tprev;            \
-    tprev = _t;                     \
-  }
+    int b = 0;            // staging slab of the current sub-tile
+    uint32_t bphase = 0;  // parity of res_bar(b)
+    // residual prefetch state (leader thread): the sub-tile RES_AHEAD ahead of the one being drained
+    PairIter pit;
+    int ptile = t_begin, pj = 0, pb = 0;
+    auto prefetch_res = [&]() {
+      if (ptile < t_end) {
+        mbar_arrive_expect_tx(res_bar(pb), A_TILE_BYTES);
+        tma_load_4d(out_stage + pb * A_TILE_BYTES, &p.res_map, res_bar(pb), pit.nt * BN + pj * 64, pit.w_t * p.TW,
+                    pit.h_t * p.TH, pit.img);
+        if (++pb == SLABS) pb = 0;
+        if (++pj == NSUB) {
+          pj = 0;
+          ++ptile;
+          pit.next(p);
+        }
+      }
+    };
+    if (with_res && leader_thread && t_begin < t_end) {
+      pit.init(t_begin, p, (int)rank, tiles_per_img);
+      for (int i = 0; i < Cfg::RES_AHEAD; ++i) prefetch_res();
+    }
     PairIter it;
     if (t_begin < t_end) it.init(t_begin, p, (int)rank, tiles_per_img);
     for (int tile = t_begin; tile < t_end; ++tile, it.next(p)) {
       const int nt = it.nt, w0 = it.w_t * p.TW, h0 = it.h_t * p.TH, img = it.img;
       const float* bias_t = bias_s + nt * BN;  // whole bias vector staged in the prologue
-      CTL_STAMP(7)
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-      CTL_STAMP(0)
       const uint32_t t0 = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16) + chalf * 32;
 #pragma unroll 1
-      for (int j = 0; j < NSUB; ++j, ++g) {
-        const uint32_t b = g & (Cfg::OUT_SLABS - 1);
+      for (int j = 0; j < NSUB; ++j) {
         const int ch0 = j * 64 + chalf * 32;
         uint32_t r[32];
         tmem_ld16(t0 + j * 64, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
         tmem_ld16(t0 + j * 64 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
-        if (leader_thread) tma_store_wait_read<Cfg::OUT_SLABS - 1>();
-        CTL_STAMP(1)
-        named_bar_sync(1, 256);
-        CTL_STAMP(2)
+        if (with_res) {
+          // the slab RES_AHEAD sub-tiles ahead was stored SLABS - RES_AHEAD sub-tiles ago: once that store has
+          // read it, the next residual tile may land there
+          if (leader_thread) {
+            tma_store_wait_read<RES_WAIT>();
+            prefetch_res();
+          }
+          mbar_wait(res_bar(b), bphase);  // this sub-tile's residual is in slab b (which is therefore free)
+        } else {
+          // slab b was handed to a TMA store SLABS sub-tiles ago: wait until that store has read it
+          if (leader_thread) tma_store_wait_read<SLABS - 1>();
+          named_bar_sync(1, 256);
+        }
         tmem_ld_wait();
-        CTL_STAMP(4)
         if (j == NSUB - 1) {
           tc_fence_before();
           __syncwarp();
@@ -632,6 +603,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
         const bool do_relu = p.relu && (nt * BN + ch0) >= p.relu_from;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
+          uint4* slot = reinterpret_cast<uint4*>(oslab + (((uint32_t)(chalf * 4 + c) ^ sw) << 4));
           const float4 b0 = *reinterpret_cast<const float4*>(bias_t + ch0 + c * 8);
           const float4 b1 = *reinterpret_cast<const float4*>(bias_t + ch0 + c * 8 + 4);
           float v[8];
@@ -643,6 +615,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
           v[5] = __uint_as_float(r[c * 8 + 5]) + b1.y;
           v[6] = __uint_as_float(r[c * 8 + 6]) + b1.z;
           v[7] = __uint_as_float(r[c * 8 + 7]) + b1.w;
+          if (with_res) {
+            const uint4 rv = *slot;
+            const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 f = __half22float2(rh[q]);
+              v[2 * q] += f.x;
+              v[2 * q + 1] += f.y;
+            }
+          }
           if (do_relu) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
@@ -651,16 +633,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
           __half2* po = reinterpret_cast<__half2*>(&o);
 #pragma unroll
           for (int q = 0; q < 4; ++q) po[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
-          *reinterpret_cast<uint4*>(oslab + (((uint32_t)(chalf * 4 + c) ^ sw) << 4)) = o;
+          *slot = o;
         }
-        CTL_STAMP(5)
         fence_proxy_async();
         named_bar_sync(1, 256);
         if (leader_thread) {
           tma_store_4d(&p.out_map, out_stage + b * A_TILE_BYTES, nt * BN + j * 64, w0, h0, img);
           tma_store_commit();
         }
-        CTL_STAMP(6)
+        if (++b == SLABS) {
+          b = 0;
+          bphase ^= 1u;
+        }
       }
       if (++as == 2) {
         as = 0;
@@ -668,12 +652,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
       }
     }
     if (leader_thread) tma_store_wait<0>();
-    CTL_STAMP(3)
-    if (p.prof && is_leader && (leader_thread || (ew == 5 && lane == 7))) {
-      long long* dst = p.prof + ((size_t)cid * 2 + (leader_thread ? 0 : 1)) * 8;
-      for (int i = 0; i < 8; ++i) dst[i] = pc[i];
-    }
-#undef CTL_STAMP
   }
   tc_fence_before();
   __syncthreads();
@@ -1602,8 +1580,6 @@ __global__ void __launch_bounds__(256) instnorm_relu_kernel(__half* __restrict__
 // ---------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------
-static long long* g_conv_prof = nullptr;
-
 template <int BN>
 static int launch_conv(const ConvKernelParams& p, cudaStream_t st) {
   static bool attr_set = false;
@@ -1668,9 +1644,78 @@ static int launch_conv_pair_v(const ConvKernelParams& p, cudaStream_t st) {
 
 template <int BN>
 static int launch_conv_pair(const ConvKernelParams& p, cudaStream_t st) {
-  // measured on B200 (bs 256 trunk): one more operand stage + 2 staging slabs is 2.5-3 % faster than 4 + 4
-  static const int variant = [] { const char* e = getenv("CTL_PAIR_VARIANT"); return e ? atoi(e) : 1; }();
-  return variant == 1 ? launch_conv_pair_v<BN, 1>(p, st) : launch_conv_pair_v<BN, 0>(p, st);
+  return p.has_residual ? launch_conv_pair_v<BN, 2>(p, st) : launch_conv_pair_v<BN, 1>(p, st);
+}
+
+// Fills the tile geometry, the output / residual / weight maps and dispatches.  The caller has filled the A maps,
+// the taps and k_blocks; `ktot` = row length of the weight matrix [Cout][ktot].
+static int finish_and_launch(ConvKernelParams& p, int n, int Ho, int Wo, int cout, int ktot, const void* weight,
+                             const float* bias, const void* residual, void* out, int relu, int relu_from,
+                             cudaStream_t st) {
+  int rc;
+  p.n_img = n;
+  p.Ho = Ho;
+  p.Wo = Wo;
+  p.Cout = cout;
+  p.bias = bias;
+  p.has_residual = residual != nullptr;
+  p.relu = relu;
+  p.relu_from = relu_from;
+  p.m_tiles = n * p.tiles_h * p.tiles_w;
+  const int BN = cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64);
+  p.n_tiles = cout / BN;
+  {
+    const uint64_t odims[4] = {(uint64_t)cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)n};
+    const uint64_t ostr[4] = {2, (uint64_t)cout * 2, (uint64_t)Wo * cout * 2, (uint64_t)Ho * Wo * cout * 2};
+    const uint32_t obox[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+    if ((rc = encode_tensor_map(&p.out_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, out, odims, ostr, obox,
+                                CU_TENSOR_MAP_SWIZZLE_128B)))
+      return rc;
+    if ((rc = encode_tensor_map(&p.res_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, residual ? residual : out, odims,
+                                ostr, obox, CU_TENSOR_MAP_SWIZZLE_128B)))
+      return rc;
+  }
+  // CTA pairs for every 256- / 128-channel-tile layer with an even tile count; CTL_CONV_PAIR=0 forces the single-CTA
+  // kernel (A/B runs)
+  static const int pair_mode = [] { const char* e = getenv("CTL_CONV_PAIR"); return e ? atoi(e) : -1; }();
+  const bool use_pair = (BN == 256 || BN == 128) && (p.m_tiles % 2 == 0) && p.m_tiles >= 2 && pair_mode != 0;
+  const uint64_t bdims[2] = {(uint64_t)ktot, (uint64_t)cout};
+  const uint64_t bstr[2] = {2, (uint64_t)ktot * 2};
+  const uint32_t bbox[2] = {CBK, (uint32_t)(use_pair ? BN / 2 : BN)};  // a pair CTA stages half of the weight tile
+  if ((rc = encode_tensor_map(&p.b_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 2, weight, bdims, bstr, bbox,
+                              CU_TENSOR_MAP_SWIZZLE_128B)))
+    return rc;
+  if (use_pair) return BN == 256 ? launch_conv_pair<256>(p, st) : launch_conv_pair<128>(p, st);
+  if (BN == 256) return launch_conv<256>(p, st);
+  if (BN == 128) return launch_conv<128>(p, st);
+  return launch_conv<64>(p, st);
+}
+
+// A tensor maps of one NHWC source [n, h, w, cin] read at `stride`: stride 1 -> map 0..3 identical; stride 2 -> the four
+// parity views (view (ph, pw) holds input pixels (2i + ph, 2j + pw)), so every box is a dense stride-1 box.
+static int encode_source(CUtensorMap* maps, int count, const void* x, int n, int h, int w, int cin, int stride, int TH,
+                         int TW) {
+  int rc;
+  const __half* xb = static_cast<const __half*>(x);
+  const uint32_t abox[4] = {CBK, (uint32_t)TW, (uint32_t)TH, 1};
+  if (stride == 1) {
+    const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+    const uint64_t strd[4] = {2, (uint64_t)cin * 2, (uint64_t)w * cin * 2, (uint64_t)h * w * cin * 2};
+    for (int i = 0; i < count; ++i)
+      if ((rc = encode_tensor_map(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, xb, dims, strd, abox,
+                                  CU_TENSOR_MAP_SWIZZLE_128B)))
+        return rc;
+    return 0;
+  }
+  const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)(w / 2), (uint64_t)(h / 2), (uint64_t)n};
+  const uint64_t strd[4] = {2, (uint64_t)cin * 4, (uint64_t)w * cin * 4, (uint64_t)h * w * cin * 2};
+  for (int v = 0; v < count; ++v) {
+    const int ph = v >> 1, pw = v & 1;
+    if ((rc = encode_tensor_map(&maps[v], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, xb + ((size_t)ph * w + pw) * cin, dims,
+                                strd, abox, CU_TENSOR_MAP_SWIZZLE_128B)))
+      return rc;
+  }
+  return 0;
 }
 
 }  // namespace ctl
@@ -1702,82 +1747,52 @@ int ctl_conv2d_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, int32_t 
   pick_tile(Ho, Wo, &p.TH, &p.TW);
   p.tiles_h = (Ho + p.TH - 1) / p.TH;
   p.tiles_w = (Wo + p.TW - 1) / p.TW;
-  p.n_img = n;
-  p.Ho = Ho;
-  p.Wo = Wo;
-  p.Cout = cout;
-  p.cin_blocks = cin / 64;
-  p.bias = bias;
-  p.has_residual = residual != nullptr;
-  p.relu = relu;
-  p.relu_from = relu_from;
-  p.prof = g_conv_prof;
-  p.m_tiles = n * p.tiles_h * p.tiles_w;
-  const int BN = cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64);
-  p.n_tiles = cout / BN;
-  const __half* xb = static_cast<const __half*>(x);
-  const uint32_t abox[4] = {CBK, (uint32_t)p.TW, (uint32_t)p.TH, 1};
-  if (stride == 1) {
-    const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
-    const uint64_t strd[4] = {2, (uint64_t)cin * 2, (uint64_t)w * cin * 2, (uint64_t)h * w * cin * 2};
-    for (int i = 0; i < 4; ++i)
-      if ((rc = encode_tensor_map(&p.a_map[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, xb, dims, strd, abox,
-                                  CU_TENSOR_MAP_SWIZZLE_128B)))
-        return rc;
-    p.n_taps = ksize * ksize;
-    for (int r = 0; r < ksize; ++r)
-      for (int s = 0; s < ksize; ++s) p.taps[r * ksize + s] = ConvTap{0, r - pad, s - pad, (r * ksize + s) * cin};
-  } else {
-    // parity views: view (ph, pw) holds input pixels (2i + ph, 2j + pw)
-    const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)(w / 2), (uint64_t)(h / 2), (uint64_t)n};
-    const uint64_t strd[4] = {2, (uint64_t)cin * 4, (uint64_t)w * cin * 4, (uint64_t)h * w * cin * 2};
-    for (int ph = 0; ph < 2; ++ph)
-      for (int pw = 0; pw < 2; ++pw)
-        if ((rc = encode_tensor_map(&p.a_map[ph * 2 + pw], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4,
-                                    xb + ((size_t)ph * w + pw) * cin, dims, strd, abox, CU_TENSOR_MAP_SWIZZLE_128B)))
-          return rc;
-    p.n_taps = ksize * ksize;
-    for (int r = 0; r < ksize; ++r)
-      for (int s = 0; s < ksize; ++s) {
+  if ((rc = encode_source(p.a_map, 4, x, n, h, w, cin, stride, p.TH, p.TW))) return rc;
+  p.n_taps = ksize * ksize;
+  p.k_blocks = p.n_taps * (cin / 64);
+  for (int r = 0; r < ksize; ++r)
+    for (int s = 0; s < ksize; ++s) {
+      if (stride == 1) {
+        p.taps[r * ksize + s] = ConvTap{0, r - pad, s - pad, (r * ksize + s) * cin, cin / 64};
+      } else {
         // input row 2*ho + r - pad = 2*(ho + dh) + ph
         const int ar = r - pad, as = s - pad;
         const int ph = ((ar % 2) + 2) % 2, pw = ((as % 2) + 2) % 2;
         const int dh = (ar - ph) / 2, dw = (as - pw) / 2;
-        p.taps[r * ksize + s] = ConvTap{ph * 2 + pw, dh, dw, (r * ksize + s) * cin};
+        p.taps[r * ksize + s] = ConvTap{ph * 2 + pw, dh, dw, (r * ksize + s) * cin, cin / 64};
       }
-  }
-  {
-    const uint64_t odims[4] = {(uint64_t)cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)n};
-    const uint64_t ostr[4] = {2, (uint64_t)cout * 2, (uint64_t)Wo * cout * 2, (uint64_t)Ho * Wo * cout * 2};
-    const uint32_t obox[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, 1};
-    if ((rc = encode_tensor_map(&p.out_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, out, odims, ostr, obox,
-                                CU_TENSOR_MAP_SWIZZLE_128B)))
-      return rc;
-    if ((rc = encode_tensor_map(&p.res_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, residual ? residual : out, odims,
-                                ostr, obox, CU_TENSOR_MAP_SWIZZLE_128B)))
-      return rc;
-  }
-  cudaStream_t st = (cudaStream_t)stream;
-  // CTA pairs for every 256-channel-tile layer with an even tile count; CTL_CONV_PAIR=0 forces the single-CTA kernel (A/B runs)
-  static const int pair_mode = [] { const char* e = getenv("CTL_CONV_PAIR"); return e ? atoi(e) : -1; }();
-  static const int pair128 = [] { const char* e = getenv("CTL_CONV_PAIR128"); return e ? atoi(e) : 1; }();
-  const bool pair_ok = (BN == 256 || (BN == 128 && pair128)) && (p.m_tiles % 2 == 0) && p.m_tiles >= 2;
-  const bool pair_want = pair_mode != 0;  // measured faster than the single-CTA kernel on every BN = 256 layer of the trunk
-  const bool use_pair = pair_ok && pair_want;
-  const uint64_t bdims[2] = {(uint64_t)ksize * ksize * cin, (uint64_t)cout};
-  const uint64_t bstr[2] = {2, (uint64_t)ksize * ksize * cin * 2};
-  const uint32_t bbox[2] = {CBK, (uint32_t)(use_pair ? BN / 2 : BN)};  // a pair CTA stages half of the weight tile
-  if ((rc = encode_tensor_map(&p.b_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 2, weight, bdims, bstr, bbox,
-                              CU_TENSOR_MAP_SWIZZLE_128B)))
-    return rc;
-  if (use_pair) return BN == 256 ? launch_conv_pair<256>(p, st) : launch_conv_pair<128>(p, st);
-  if (BN == 256) return launch_conv<256>(p, st);
-  if (BN == 128) return launch_conv<128>(p, st);
-  return launch_conv<64>(p, st);
+    }
+  return finish_and_launch(p, n, Ho, Wo, cout, ksize * ksize * cin, weight, bias, residual, out, relu, relu_from,
+                           (cudaStream_t)stream);
 }
 
-/* debug: per-CTA epilogue cycle counters [sm_count][2][8] written by the next conv launches */
-void ctl_debug_set_conv_profile(long long* device_buffer) { g_conv_prof = device_buffer; }
+int ctl_conv1x1_dual_nhwc_f16(const void* x1, int32_t cin1, const void* x2, int32_t h2, int32_t w2, int32_t cin2,
+                              int32_t stride2, int32_t n, const void* weight_cat, const float* bias, void* out,
+                              int32_t cout, int32_t relu, ctl_stream_t stream) {
+  CTL_CHECK_ARG(x1 && x2 && weight_cat && bias && out, "null pointer");
+  CTL_CHECK_ARG(n >= 1 && h2 >= 1 && w2 >= 1, "bad activation shape");
+  CTL_CHECK_ARG(cin1 % 64 == 0 && cin2 % 64 == 0 && cout % 64 == 0 && cin1 >= 64 && cin2 >= 64,
+                "Cin1=%d, Cin2=%d and Cout=%d must be multiples of 64", cin1, cin2, cout);
+  CTL_CHECK_ARG(cout <= 2048, "Cout=%d exceeds 2048 (bias staging)", cout);
+  CTL_CHECK_ARG(stride2 == 1 || (stride2 == 2 && h2 % 2 == 0 && w2 % 2 == 0), "stride2 must be 1, or 2 with even H2, W2");
+  int rc = ctl_device_check();
+  if (rc) return rc;
+  const int Ho = h2 / stride2, Wo = w2 / stride2;
+  ConvKernelParams p = {};
+  pick_tile(Ho, Wo, &p.TH, &p.TW);
+  p.tiles_h = (Ho + p.TH - 1) / p.TH;
+  p.tiles_w = (Wo + p.TW - 1) / p.TW;
+  // map 0: x1 at the output resolution; map 1: x2 (its (0, 0) parity view when strided); maps 2, 3 unused
+  if ((rc = encode_source(&p.a_map[0], 1, x1, n, Ho, Wo, cin1, 1, p.TH, p.TW))) return rc;
+  if ((rc = encode_source(&p.a_map[1], 1, x2, n, h2, w2, cin2, stride2, p.TH, p.TW))) return rc;
+  p.a_map[2] = p.a_map[0];
+  p.a_map[3] = p.a_map[0];
+  p.n_taps = 2;
+  p.taps[0] = ConvTap{0, 0, 0, 0, cin1 / 64};
+  p.taps[1] = ConvTap{1, 0, 0, cin1, cin2 / 64};
+  p.k_blocks = (cin1 + cin2) / 64;
+  return finish_and_launch(p, n, Ho, Wo, cout, cin1 + cin2, weight_cat, bias, nullptr, out, relu, 0, (cudaStream_t)stream);
+}
 
 int ctl_stem_conv7x7(const float* x_nchw, int32_t n, int32_t h, int32_t w, const float* weight_k64, const float* bias,
                      int32_t relu, void* out_nhwc_f16, ctl_stream_t stream) {

@@ -90,8 +90,14 @@ class TrunkEngine:
                 if bi == 0:
                     blk["down"] = _Conv(*_fold(sd[p + ".downsample.0.weight"], _bn(sd, p + ".downsample.1")),
                                         stride, False)
+                    # conv3 + shortcut as ONE GEMM over the concatenated K dimension (ctl_conv1x1_dual_nhwc_f16):
+                    # [W3 | Wd] fp16 (each folded matrix rounded exactly as in the two-launch form), bias3 + bias_d
+                    c3, cd = blk["conv3"], blk["down"]
+                    blk["dual_w"] = torch.cat((c3.w.reshape(c3.cout, c3.cin), cd.w.reshape(cd.cout, cd.cin)), 1).contiguous()
+                    blk["dual_b"] = (c3.b + cd.b).contiguous()
                 self.blocks.append(blk)
         self.out_channels = self.blocks[-1]["conv3"].cout
+        self.fuse_shortcut = os.environ.get("CTL_FUSE_SHORTCUT", "1") == "1"  # A/B switch (two-launch form when 0)
         self.profile = None  # set to a list to record (kernel, flops, bytes, start_evt, end_evt) per launch
         self.launches_per_forward = 0
         self.head = None
@@ -116,6 +122,19 @@ class TrunkEngine:
                                                 N.ptr(residual), out.data_ptr(), c.cout, c.k, c.stride, int(c.relu),
                                                 c.relu_from, N.stream_ptr()))
         return out, ho, wo
+
+    def _dual(self, o2, a, n, h, w, h2, w2, blk):
+        """relu(bn3(conv3(o2)) + bn_d(downsample(a))) in one launch; the shortcut tensor never exists."""
+        c3, cd = blk["conv3"], blk["down"]
+        out = torch.empty(n, h2, w2, c3.cout, dtype=torch.float16, device=self.device)
+        m = n * h2 * w2
+        flops = 2.0 * m * c3.cout * (c3.cin + cd.cin)
+        nbytes = 2.0 * (m * (c3.cin + cd.cin) + m * c3.cout + c3.cout * (c3.cin + cd.cin))
+        with self._timed("conv_gemm", flops, nbytes):
+            N.check(N.lib().ctl_conv1x1_dual_nhwc_f16(o2.data_ptr(), c3.cin, a.data_ptr(), h, w, cd.cin, cd.stride, n,
+                                                      blk["dual_w"].data_ptr(), blk["dual_b"].data_ptr(),
+                                                      out.data_ptr(), c3.cout, 1, N.stream_ptr()))
+        return out, h2, w2
 
     def _timed(self, name, flops=0.0, nbytes=0.0):
         return _Timed(self, name, flops, nbytes)
@@ -160,6 +179,9 @@ class TrunkEngine:
                         N.check(L.ctl_instnorm_relu_nhwc_f16(o1.data_ptr(), n, h1 * w1, blk["conv1"].cout, half,
                                                              g.data_ptr(), b.data_ptr(), BN_EPS, N.stream_ptr()))
                 o2, h2, w2 = self._conv(o1, n, h1, w1, blk["conv2"])
+                if "down" in blk and self.fuse_shortcut:
+                    a, h, w = self._dual(o2, a, n, h, w, h2, w2, blk)
+                    continue
                 res = a
                 if "down" in blk:
                     res, _, _ = self._conv(a, n, h, w, blk["down"])

@@ -289,14 +289,43 @@ def _allgather_keys(pos_keys, pos_count, max_pos, group):
 
 def merge_topk(idx_list: Sequence[torch.Tensor], dist_list: Sequence[torch.Tensor], k: int):
     """k-way merge of per-shard (ascending) top-k lists under the canonical (distance, index)
-    order -- deterministic regardless of world size."""
+    order -- deterministic regardless of world size.  CUDA inputs are merged by the native packed-key row sort
+    (one launch, integer-exact); host tensors (the gloo tests) by two stable argsorts."""
     idx = torch.cat(list(idx_list), 1)
     dst = torch.cat(list(dist_list), 1)
+    if idx.is_cuda:
+        return merge_topk_keys(pack_keys(dst, idx), k)
     # sort by index first (stable), then by distance (stable): lexicographic (distance, index)
     o1 = torch.argsort(idx, dim=1, stable=True)
     idx, dst = idx.gather(1, o1), dst.gather(1, o1)
     o2 = torch.argsort(dst, dim=1, stable=True)
     return idx.gather(1, o2)[:, :k], dst.gather(1, o2)[:, :k]
+
+
+def pack_keys(dst: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """(distance fp32, index) -> the kernels' uint64 key (carried as int64): orderable(fp32) << 32 | index, whose
+    UNSIGNED integer order is the canonical ascending (distance, index) order (ctl_key_encode)."""
+    b = dst.contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    o = torch.where(b >= 0x80000000, b ^ 0xFFFFFFFF, b | 0x80000000)  # sign-magnitude float bits -> unsigned order
+    return (o << 32) | (idx.to(torch.int64) & 0xFFFFFFFF)
+
+
+def merge_topk_keys(keys: torch.Tensor, k: int):
+    """keys: int64 [nq, m] packed (distance, index) keys in any order (m >= k) -> the k smallest per row as
+    (idx int64 [nq, k], dist float32 [nq, k]): ctl_sort_key_rows + ctl_topk_emit."""
+    L = N.lib()
+    keys = keys.contiguous()
+    nq, m = keys.shape
+    dev = keys.device
+    counts = torch.full((nq,), m, dtype=torch.int32, device=dev)
+    idx = torch.empty(nq, k, dtype=torch.int64, device=dev)
+    dst = torch.empty(nq, k, dtype=torch.float32, device=dev)
+    ovf = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        N.check(L.ctl_sort_key_rows(keys.data_ptr(), counts.data_ptr(), nq, m, N.stream_ptr()))
+        N.check(L.ctl_topk_emit(keys.data_ptr(), counts.data_ptr(), nq, m, k, idx.data_ptr(), dst.data_ptr(),
+                                ovf.data_ptr(), N.stream_ptr()))
+    return idx, dst
 
 
 def topk_sharded(q_local: torch.Tensor, g_local: torch.Tensor, k: int, g_index_offset: int, group,
@@ -376,3 +405,89 @@ def topk_and_eval(qp: Planes, gp: Planes, k: int, q_pids, g_pids, q_camids, g_ca
     if ovf_h:
         raise OverflowError("a device-side list overflowed (exact ties at the k-th distance, or max_pos)")
     return idx, dst, _aggregate(ranks_h, ap_h, cnt_h, np.asarray(q_pids), ng, max_rank)
+
+
+def encode_ids_sharded(q_pids, g_pids_local, q_camids, g_camids_local, device, group) -> EncodedIds:
+    """Identity arrays of (all queries, THIS rank's gallery shard) for topk_and_eval_sharded: raw integer pids (every
+    rank must agree on the labelling, so no np.unique), camera ids in [0, 64); `max_pos` = the largest number of
+    same-pid rows of any shard (one MAX all-reduce, done once per validation set)."""
+    import torch.distributed as dist
+
+    ids = encode_ids(q_pids, g_pids_local, q_camids, g_camids_local, False, device, global_labels=True)
+    mp = torch.tensor([ids.max_pos], device=device, dtype=torch.int64)
+    dist.all_reduce(mp, op=dist.ReduceOp.MAX, group=group)
+    ids.max_pos = int(mp.item())
+    return ids
+
+
+def topk_and_eval_sharded(qp: Planes, gp_local: Planes, k: int, ids: EncodedIds, q_pids, g_index_offset: int,
+                          total_gallery: int, group, max_rank: int = 50):
+    """BASELINE config 5: topk_and_eval with the GALLERY AXIS SHARDED over the ranks of `group` (queries replicated:
+    all-gather them once before building `qp`).  Every rank runs the two tensor-core passes over its own shard; the
+    exchange steps are (utils/reid_metric.py:112-136 + utils/eval_reid.py:25-92 semantics, bit-identical to one GPU):
+      after pass 1: all-gather of the positives' (distance, index) keys [nq, max_pos] -> one sorted threshold list
+      after pass 2: all-reduce(sum) of the integer bucket counts; all-gather of each rank's k best packed keys and a
+                    k-way merge by integer key order (world-size independent).
+    Returns (idx [nq, k] global gallery rows, dist [nq, k], EvalResult) on every rank."""
+    import ctypes as C
+
+    import torch.distributed as dist
+
+    L = N.lib()
+    dev = qp.buf.device
+    world = dist.get_world_size(group)
+    nq, ng = qp.n, gp_local.n
+    k_loc = int(min(k, ng))
+    emit_all, n_groups, merge, cap = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+    N.check(L.ctl_topk_plan(ng, k_loc, C.byref(emit_all), C.byref(n_groups), C.byref(merge), C.byref(cap)))
+    mp_l = ids.max_pos            # per-shard capacity (same on every rank)
+    mp = mp_l * world             # capacity of the merged threshold list
+    gmin = torch.empty(nq, n_groups.value, dtype=torch.float32, device=dev)
+    tau = torch.empty(nq, dtype=torch.float32, device=dev)
+    cand = torch.empty(nq, cap.value, dtype=torch.int64, device=dev)
+    zeros = torch.zeros(2 * nq + 1, dtype=torch.int32, device=dev)
+    cand_count, pos_count, ovf = zeros[:nq], zeros[nq: 2 * nq], zeros[2 * nq:]
+    pos_keys = torch.empty(nq, mp_l, dtype=torch.int64, device=dev)
+    buckets = torch.zeros(nq, mp + 1, dtype=torch.int32, device=dev)
+    ranks = torch.empty(nq, mp, dtype=torch.int32, device=dev)
+    ap = torch.empty(nq, dtype=torch.float64, device=dev)
+    s = N.stream_ptr
+    idp = dict(q_pid=ids.q_pid.data_ptr(), q_cam=ids.q_cam.data_ptr(), g_pid=ids.g_pid.data_ptr(),
+               g_cammask=ids.g_mask.data_ptr(), overflow=ovf.data_ptr(), g_index_offset=g_index_offset)
+    with torch.cuda.device(dev):
+        p1 = N.PassDesc(pos_keys=pos_keys.data_ptr(), pos_count=pos_count.data_ptr(), max_pos=mp_l, **idp)
+        if not emit_all.value:
+            p1.gmin = gmin.data_ptr()
+        N.check(L.ctl_dist_pass(qp.ptr, nq, gp_local.ptr, ng, qp.d, qp.flags, C.byref(p1), s()))
+        if emit_all.value:
+            N.check(L.ctl_fill_f32(tau.data_ptr(), nq, float("inf"), s()))
+        else:
+            N.check(L.ctl_select_tau(gmin.data_ptr(), nq, n_groups.value, merge.value, k_loc, tau.data_ptr(), s()))
+        # exchange 1: every rank's positives, unused slots = the largest key, so ONE row sort packs and orders them
+        col = torch.arange(mp_l, device=dev)[None, :]
+        masked = torch.where(col < pos_count[:, None].clamp(max=mp_l), pos_keys, torch.full_like(pos_keys, -1))
+        g_keys = torch.empty(world, nq, mp_l, dtype=torch.int64, device=dev)
+        g_cnt = torch.empty(world, nq, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(g_keys, masked, group=group)
+        dist.all_gather_into_tensor(g_cnt, pos_count.contiguous(), group=group)
+        thr = g_keys.permute(1, 0, 2).reshape(nq, mp).contiguous()
+        thr_count = g_cnt.sum(0, dtype=torch.int32)
+        full = torch.full((nq,), mp, dtype=torch.int32, device=dev)
+        N.check(L.ctl_sort_key_rows(thr.data_ptr(), full.data_ptr(), nq, mp, s()))
+        p2 = N.PassDesc(tau=tau.data_ptr(), cand_keys=cand.data_ptr(), cand_count=cand_count.data_ptr(),
+                        cand_cap=cap.value, thr_keys=thr.data_ptr(), thr_count=thr_count.data_ptr(),
+                        buckets=buckets.data_ptr(), max_pos=mp, **idp)
+        N.check(L.ctl_dist_pass(qp.ptr, nq, gp_local.ptr, ng, qp.d, qp.flags, C.byref(p2), s()))
+        N.check(L.ctl_sort_key_rows(cand.data_ptr(), cand_count.data_ptr(), nq, cap.value, s()))
+        # exchange 2: bucket counts (integers) and the k best keys of every shard
+        dist.all_reduce(buckets, op=dist.ReduceOp.SUM, group=group)
+        best = cand[:, :k_loc].contiguous()
+        g_best = torch.empty(world, nq, k_loc, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(g_best, best, group=group)
+        dist.all_reduce(ovf, op=dist.ReduceOp.MAX, group=group)
+        idx, dst = merge_topk_keys(g_best.permute(1, 0, 2).reshape(nq, world * k_loc), int(min(k, world * k_loc)))
+        N.check(L.ctl_eval_finalize(buckets.data_ptr(), thr_count.data_ptr(), nq, mp, ranks.data_ptr(), ap.data_ptr(), s()))
+    ranks_h, ap_h, cnt_h, ovf_h = ranks.cpu().numpy(), ap.cpu().numpy(), thr_count.cpu().numpy(), int(ovf.item())
+    if ovf_h:
+        raise OverflowError("a device-side list overflowed on some rank (exact ties at the k-th distance, or max_pos)")
+    return idx, dst, _aggregate(ranks_h, ap_h, cnt_h, np.asarray(q_pids), total_gallery, max_rank)

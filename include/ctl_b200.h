@@ -215,9 +215,15 @@ int ctl_xent_smooth_step(const float* logits, int32_t b, int32_t c, const int32_
 int ctl_conv2d_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, int32_t cin, const void* weight,
                         const float* bias, const void* residual, void* out, int32_t cout, int32_t ksize,
                         int32_t stride, int32_t relu, int32_t relu_from, ctl_stream_t stream);
-/* debug aid (not part of the drop-in surface): when non-NULL, the epilogue of the following
- * ctl_conv2d_nhwc_f16 launches adds its per-phase clock64() cycles into [grid][2][8] int64 slots. */
-void ctl_debug_set_conv_profile(long long* device_buffer);
+/* Two 1x1 convolutions summed in ONE GEMM over the concatenated K dimension -- the last layer of a bottleneck's
+ * first block, out = act(bn3(conv3(x1)) + bn_d(downsample(x2))) (resnet.py:75-85 with a downsample branch):
+ *   out[n][i][j][:] = act( W[:, :cin1] x1[n][i][j][:] + W[:, cin1:] x2[n][i*stride2][j*stride2][:] + bias )
+ * x1: NHWC fp16 [n][h2/stride2][w2/stride2][cin1]; x2: NHWC fp16 [n][h2][w2][cin2]; weight_cat: [cout][cin1 + cin2]
+ * fp16 (both folded weight matrices side by side), bias = sum of the two folded biases.  The shortcut tensor is
+ * never written to or re-read from HBM. */
+int ctl_conv1x1_dual_nhwc_f16(const void* x1, int32_t cin1, const void* x2, int32_t h2, int32_t w2, int32_t cin2,
+                              int32_t stride2, int32_t n, const void* weight_cat, const float* bias, void* out,
+                              int32_t cout, int32_t relu, ctl_stream_t stream);
 int ctl_stem_conv7x7(const float* x_nchw, int32_t n, int32_t h, int32_t w, const float* weight_k64, const float* bias,
                      int32_t relu, void* out_nhwc_f16, ctl_stream_t stream);
 /* tensor-core stem: weight_k192_f16 = [64][192] fp16, k = (c*7 + r)*8 + s (s = 7 and k >= 168 zero) */

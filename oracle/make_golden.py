@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz by running the UNMODIFIED
 reference (/root/reference, through oracle/ref_import.py) on seeded synthetic inputs.
 
-    python -m oracle.make_golden [--only loss,retrieval,trunk,masks,centroids,market]
+    python -m oracle.make_golden [--only loss,retrieval,trunk,trunk_train,trunk_autocast,masks,centroids,market]
 
 The reference has no tests and no golden vectors of its own; these
 files are what pins the oracle restatement (oracle/ctl_oracle.py) and, through it, the
@@ -291,9 +291,63 @@ def gen_trunk_train(ref):
     np.savez_compressed(os.path.join(GOLD, "trunk_train.npz"), **out)
 
 
+def gen_trunk_autocast(ref):
+    """The reference's own trunk at the precision its configs actually run at: torch fp16 autocast
+    (USE_MIXED_PRECISION -> PL native AMP, utils/misc.py:111), executed here with the CPU autocast backend (fp16 conv /
+    linear outputs, fp32 BatchNorm statistics, IBN's InstanceNorm in fp32 by its own cast, resnet_ibn_a.py:29).
+    Eval: R50 2x256x128 (the inputs of trunk.npz), IBN-a 2x320x320 (config 4 geometry) and 2x128x64, each stored next to
+    the fp32 run of the same module so that the reference's OWN fp16-vs-fp32 distance is on record.
+    Train: R50 / IBN-a 4x64x32 (the inputs of trunk_train.npz), features and a sample of parameter gradients of
+    sum(feat * dfeat) * 1024 (a fixed loss scale, unscaled afterwards) under autocast."""
+    out = {}
+    cases = (("r50", False, "resnet50", (256, 128)), ("ibn320", True, "resnet50_ibn_a", (320, 320)),
+             ("ibn", True, "resnet50_ibn_a", (128, 64)))
+    for tag, ibn, mname, hw in cases:
+        sd = O.make_trunk_state(seed=7, ibn=ibn)
+        cfg = default_cfg(ref)
+        cfg.MODEL.NAME = mname
+        base = ref.baseline.Baseline(cfg)
+        base.base.load_state_dict(sd, strict=True)
+        base.eval()
+        x = torch.randn(2, 3, *hw, generator=torch.Generator().manual_seed(21))
+        with torch.no_grad():
+            _, f32 = base(x)
+            with torch.autocast("cpu", dtype=torch.float16):
+                _, f16 = base(x)
+        out[f"{tag}_in_checksum"] = checksum(x)
+        out[f"{tag}_eval_feat_fp32"] = f32.float().numpy()
+        out[f"{tag}_eval_feat_amp"] = f16.float().numpy()
+        rel = float((f16.float() - f32).abs().max() / f32.abs().max())
+        out[f"{tag}_amp_vs_fp32"] = rel
+        print(f"trunk autocast {tag}: reference fp16-autocast vs its own fp32: {rel:.3e} of the feature scale")
+    scale = 1024.0
+    for ibn, mname in ((False, "resnet50"), (True, "resnet50_ibn_a")):
+        tag = "ibn" if ibn else "r50"
+        sd = O.make_trunk_state(seed=17, ibn=ibn)
+        cfg = default_cfg(ref)
+        cfg.MODEL.NAME = mname
+        base = ref.baseline.Baseline(cfg)
+        base.base.load_state_dict(sd, strict=True)
+        base.train()
+        g = torch.Generator().manual_seed(23)
+        x = torch.randn(4, 3, 64, 32, generator=g)
+        dfeat = torch.randn(4, 2048, generator=g) * 1e-2
+        with torch.autocast("cpu", dtype=torch.float16):
+            _, feat = base(x)
+        ((feat.float() * dfeat).sum() * scale).backward()
+        params = dict(base.base.named_parameters())
+        out[f"{tag}_train_in_checksum"] = checksum(torch.cat((x.flatten(), dfeat.flatten())))
+        out[f"{tag}_train_feat_amp"] = feat.detach().float().numpy()
+        for key in TRAIN_GRAD_KEYS:
+            k = key.format(bn="BN." if ibn else "")
+            out[f"{tag}_train_grad_{k}"] = grad_sample(params[k].grad / scale)
+        print(f"trunk autocast train {tag}: feat std {float(feat.float().std()):.4f}")
+    np.savez_compressed(os.path.join(GOLD, "trunk_autocast.npz"), **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="loss,masks,retrieval,centroids,trunk,trunk_train,market")
+    ap.add_argument("--only", default="loss,masks,retrieval,centroids,trunk,trunk_train,trunk_autocast,market")
     args = ap.parse_args()
     only = set(args.only.split(","))
     os.makedirs(GOLD, exist_ok=True)
@@ -313,6 +367,8 @@ def main():
         gen_trunk(ref)
     if "trunk_train" in only:
         gen_trunk_train(ref)
+    if "trunk_autocast" in only:
+        gen_trunk_autocast(ref)
     if "market" in only:
         # BASELINE config 3 shape; the reference's per-query python loop takes ~80 s here
         gen_retrieval(ref, "market", 3368, 15913, 751, 3.0, 0, store_dist=False)

@@ -12,8 +12,11 @@ defaults (``use_gpu=True`` with hard ``.cuda()`` calls, losses/center_loss.py:21
 losses/triplet_loss.py:187,202) are switched to ``use_gpu=False`` -- that is the only
 behavioural patch, and it does not touch any arithmetic.
 
-/root/reference does not exist on the GPU box: nothing under ``-m gpu`` tests, ``smoke()``
-or ``bench.py`` imports this module.
+/root/reference does not exist on the GPU box.  There the module imports the verbatim copy
+``oracle/_ref`` made by ``oracle/vendor_ref.py`` (git-ignored, shipped with the snapshot); it is
+used only by ``bench.py --impl reference`` / the ``cpu_baseline`` legs (the reference timed on the
+host cores) and by ``tests/test_reference_autocast_gpu.py`` (the reference under CUDA autocast as
+the same-precision checker).  Tests that need it skip with a message when the copy is absent.
 """
 from __future__ import annotations
 
@@ -22,7 +25,16 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("CTL_REFERENCE_ROOT", "/root/reference")
+_VENDORED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")  # oracle/vendor_ref.py (git-ignored)
+
+
+def _default_root():
+    if os.path.isfile("/root/reference/train_ctl_model.py"):
+        return "/root/reference"
+    return _VENDORED  # the GPU box: the verbatim copy that travelled with the snapshot
+
+
+REFERENCE_ROOT = os.environ.get("CTL_REFERENCE_ROOT") or _default_root()
 
 
 def reference_available() -> bool:

@@ -213,3 +213,25 @@ def test_train_mode_oracle_pinned_against_reference_autograd(tag, ibn):
                 assert cos >= 0.97 and abs(got[-1] / exp[-1] - 1) <= tol, (k, cos)
         for k in ("bn1.running_mean", "layer4.2.bn3.running_var"):
             np.testing.assert_allclose(running[k].numpy(), gd[f"{tag}_run_{k}"], rtol=5e-3 if (rnd or ibn) else 1e-6, atol=1e-5 if (rnd or ibn) else 1e-9)
+
+
+@pytest.mark.parametrize("tag,ibn,hw", [("r50", False, (256, 128)), ("ibn", True, (128, 64))])
+def test_fp16sim_checker_pinned_against_reference_under_autocast(tag, ibn, hw):
+    """The builder's same-precision checker (trunk_forward_fp16sim: fp16 operands, BN folded into fp16 weights, fp16
+    activations) is itself pinned against the UNMODIFIED reference run under fp16 autocast
+    (tests/golden/trunk_autocast.npz): it must sit as close to the reference-under-autocast as the reference's own fp16
+    run sits to its fp32 run (a few 1e-4 of the feature scale), i.e. it is a fair stand-in at sizes the goldens do not
+    cover."""
+    g = load_golden("trunk_autocast.npz")
+    sd = O.make_trunk_state(seed=7, ibn=ibn)
+    x = torch.randn(2, 3, *hw, generator=torch.Generator().manual_seed(21))
+    np.testing.assert_allclose(checksum(x), g[f"{tag}_in_checksum"], rtol=1e-9)
+    with torch.no_grad():
+        _, sim = O.trunk_forward_fp16sim(x, sd, ibn=ibn)
+    amp, f32 = torch.from_numpy(g[f"{tag}_eval_feat_amp"]), torch.from_numpy(g[f"{tag}_eval_feat_fp32"])
+    scale = float(f32.abs().max())
+    d_amp = float((sim - amp).abs().max()) / scale
+    d_f32 = float((sim - f32).abs().max()) / scale
+    print(f"{tag}: fp16sim vs reference-autocast {d_amp:.3e}, vs reference fp32 {d_f32:.3e}, "
+          f"reference autocast vs fp32 {float(g[f'{tag}_amp_vs_fp32']):.3e}")
+    assert d_amp <= 2e-3 and d_f32 <= 2e-3

@@ -1,0 +1,110 @@
+"""Same-precision parity AT THE BENCH SHAPES against the UNMODIFIED reference executed on the GPU box.
+
+The reference's Python sources travel as the git-ignored verbatim copy ``oracle/_ref`` (recipe: oracle/vendor_ref.py);
+here its own trunk modules (modelling/backbones/resnet.py:122-133, resnet_ibn_a.py:126-141, modelling/baseline.py:91-96)
+run on cuda:0 under ``torch.autocast(dtype=float16)`` -- the precision the reference's configs train and validate at
+(USE_MIXED_PRECISION -> PL native AMP, utils/misc.py:111) -- and are the checker for
+
+  * the eval embedding at metric M1's configuration (256 crops of 256x128, ResNet50) and at config 4's per-GPU eval shape
+    (128 crops of 320x320, ResNet50-IBN-a): every image, tolerance 2e-3 of the feature scale (two correct fp16
+    evaluations of this network differ by a few 1e-4; north_star's 1e-4 is an fp32-vs-fp32 bound and the reference's own
+    autocast run is 4-7e-4 away from its fp32 run, tests/golden/trunk_autocast.npz);
+  * one training step at config 2's shape (16 ids x 16 instances of 256x128) and config 4's per-GPU shape (32 x 4 of
+    320x320, IBN-a): train-mode features within 2e-2, every parameter gradient by direction and size (cosine >= 0.97,
+    norm within 5 %: ReLU masks make element-wise comparison of two fp16 backward passes meaningless).
+
+Skipped (with the reason) when the vendored copy is absent; the committed goldens of the small shapes
+(test_trunk_gpu.py::test_trunk_matches_reference_under_autocast, test_train_gpu.py::..._under_autocast) always run.
+"""
+import os
+
+import pytest
+import torch
+
+from oracle import ctl_oracle as O
+from oracle import ref_import
+
+pytestmark = pytest.mark.gpu
+
+needs_ref = pytest.mark.skipif(not ref_import.reference_available(),
+                               reason="oracle/_ref absent: run `python -m oracle.vendor_ref` where /root/reference is mounted")
+
+
+def _ref_base(ibn, sd):
+    ref = ref_import.load_reference()
+    cfg = ref_import.default_cfg(ref)
+    cfg.MODEL.NAME = "resnet50_ibn_a" if ibn else "resnet50"
+    base = ref.baseline.Baseline(cfg)
+    base.base.load_state_dict(sd, strict=True)
+    return base.cuda()
+
+
+@needs_ref
+@pytest.mark.parametrize("tag,ibn,hw,bs", [("r50", False, (256, 128), 256), ("ibn", True, (320, 320), 128)])
+def test_eval_embedding_at_bench_shape_vs_reference_cuda_autocast(tag, ibn, hw, bs):
+    from ctl_b200.modelling.backbones.engine import TrunkEngine
+
+    sd = O.make_trunk_state(seed=7, ibn=ibn)
+    x = torch.randn(bs, 3, *hw, generator=torch.Generator().manual_seed(77)).cuda()
+    base = _ref_base(ibn, sd).eval()
+    with torch.no_grad():
+        _, f32 = base(x)
+        with torch.autocast("cuda", dtype=torch.float16):
+            _, amp = base(x)
+    feat = TrunkEngine(sd, "cuda", ibn=ibn).forward(x)["global_feat"]
+    scale = float(f32.abs().max())
+    e_amp = float((feat - amp.float()).abs().max()) / scale
+    e_f32 = float((feat - f32).abs().max()) / scale
+    own = float((amp.float() - f32).abs().max()) / scale
+    print(f"{tag} bs {bs} {hw}: engine vs reference CUDA-autocast {e_amp:.3e}; engine vs reference fp32 {e_f32:.3e}; "
+          f"reference CUDA-autocast vs its own fp32 {own:.3e}")
+    assert torch.isfinite(feat).all()
+    assert e_amp <= 2e-3
+    assert e_f32 <= max(3.0 * own, 1.5e-3)
+
+
+@needs_ref
+@pytest.mark.parametrize("tag,ibn,hw,P,K", [("r50 cfg2", False, (256, 128), 16, 16), ("ibn cfg4/gpu", True, (320, 320), 32, 4)])
+def test_training_step_at_bench_shape_vs_reference_cuda_autocast(tag, ibn, hw, P, K):
+    from ctl_b200.modelling.backbones.engine_train import TrunkTrainer
+
+    n = P * K
+    scale = 1024.0
+    sd = O.make_trunk_state(seed=17, ibn=ibn)
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(n, 3, *hw, generator=gen).cuda()
+    dfeat = (torch.randn(n, 2048, generator=gen) * 1e-3).cuda()
+    base = _ref_base(ibn, sd).train()
+    with torch.autocast("cuda", dtype=torch.float16):
+        _, rfeat = base(x)
+    ((rfeat.float() * dfeat).sum() * scale).backward()
+    rgrads = {k: (p.grad / scale) for k, p in base.base.named_parameters() if p.grad is not None}
+    rfeat = rfeat.detach().float()
+    del base
+    torch.cuda.empty_cache()
+    params = {k: v.clone().cuda() for k, v in sd.items() if v.is_floating_point()}
+    tr = TrunkTrainer("cuda", grad_scale=scale, ibn=ibn)
+    feat = tr.forward(x, params)
+    grads = tr.backward(dfeat)
+    torch.cuda.synchronize()
+    fscale = float(rfeat.abs().max())
+    e = float((feat - rfeat).abs().max()) / fscale
+    gmax = max(float(v.abs().max()) for v in rgrads.values())
+    worst_cos, worst_norm = (1.0, None), (0.0, None)
+    for k, rg in rgrads.items():
+        gk = grads[k].double()
+        rg = rg.double()
+        assert torch.isfinite(gk).all(), k
+        if float(rg.abs().max()) < 1e-5 * gmax:  # exactly-cancelled gradients (a bias in front of a batch-stat BN)
+            continue
+        cos = float((gk * rg).sum() / (gk.norm() * rg.norm()))
+        nr = abs(float(gk.norm() / rg.norm()) - 1)
+        if cos < worst_cos[0]:
+            worst_cos = (cos, k)
+        if nr > worst_norm[0]:
+            worst_norm = (nr, k)
+    print(f"{tag}: train features vs reference CUDA-autocast {e:.3e}; worst gradient cosine {worst_cos[0]:.4f} "
+          f"({worst_cos[1]}), worst norm deviation {worst_norm[0]:.3e} ({worst_norm[1]}) over {len(rgrads)} tensors")
+    assert e <= 2e-2
+    assert worst_cos[0] >= 0.97, worst_cos
+    assert worst_norm[0] <= 5e-2, worst_norm

@@ -383,3 +383,44 @@ def test_ibn_trunk_train_step_teacher_forced():
         if r > 2e-2:
             bad[k] = r
     assert not bad, f"gradient mismatch (max-norm relative): {sorted(bad.items(), key=lambda t: -t[1])[:8]}"
+
+
+@pytest.mark.parametrize("tag,ibn", [("r50", False), ("ibn", True)])
+def test_trunk_train_matches_reference_under_autocast(tag, ibn):
+    """Train-mode features and parameter gradients against the UNMODIFIED reference run under fp16 autocast with a fixed
+    loss scale (tests/golden/trunk_autocast.npz, oracle/make_golden.py::gen_trunk_autocast) -- the same-precision
+    checker.  Two correct fp16 train steps differ through ReLU masks (see test_trunk_train_step_against_float64_autograd),
+    so gradients are compared by direction and size on the golden's evenly strided samples: cosine >= 0.97, norm within
+    5 %; features within 2e-2 of the feature scale (measured values are printed)."""
+    from oracle import ctl_oracle as O
+    from oracle.make_golden import TRAIN_GRAD_KEYS, grad_sample
+    from conftest import load_golden
+    from ctl_b200.modelling.backbones.engine_train import TrunkTrainer
+
+    g = load_golden("trunk_autocast.npz")
+    sd = O.make_trunk_state(seed=17, ibn=ibn)
+    gen = torch.Generator().manual_seed(23)
+    x = torch.randn(4, 3, 64, 32, generator=gen)
+    dfeat = torch.randn(4, 2048, generator=gen) * 1e-2
+    params = {k: v.clone().cuda() for k, v in sd.items() if v.is_floating_point()}
+    tr = TrunkTrainer("cuda", grad_scale=1024.0, ibn=ibn)
+    feat = tr.forward(x.cuda(), params)
+    grads = tr.backward(dfeat.cuda())
+    torch.cuda.synchronize()
+    ref_feat = torch.from_numpy(g[f"{tag}_train_feat_amp"])
+    e = _rel(feat.cpu(), ref_feat)
+    print(f"{tag}: train-mode features vs reference-under-autocast {e:.3e}")
+    assert e <= 2e-2
+    worst = (1.0, None)
+    for key in TRAIN_GRAD_KEYS:
+        k = key.format(bn="BN." if ibn else "")
+        want = torch.from_numpy(g[f"{tag}_train_grad_{k}"])[:-2]
+        got = torch.from_numpy(grad_sample(grads[k].cpu()))[:-2]
+        if float(want.abs().max()) < 1e-7:
+            continue
+        cos = float((got * want).sum() / (got.norm() * want.norm()))
+        nr = float(got.norm() / want.norm())
+        if cos < worst[0]:
+            worst = (cos, k)
+        assert cos >= 0.97 and abs(nr - 1) <= 5e-2, (k, cos, nr)
+    print(f"{tag}: worst gradient cosine vs reference-under-autocast {worst[0]:.4f} ({worst[1]})")

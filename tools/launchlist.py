@@ -2,10 +2,14 @@
 with layer names; with DRAM metrics present also prints per-launch traffic and writes the conv total to
 profiles/conv_traffic.json (read by bench.py for roofline.traffic)."""
 import csv, json, os, sys
+FUSED = os.environ.get("CTL_FUSE_SHORTCUT", "1") == "1"  # conv3 + shortcut in one launch (51 launches), else 55
 names = ["stem_pack", "stem_pool"]
 for li, nb in zip((1, 2, 3, 4), (3, 4, 6, 3)):
     for b in range(nb):
-        names += [f"L{li}b{b}.conv1", f"L{li}b{b}.conv2"] + ([f"L{li}b{b}.down"] if b == 0 else []) + [f"L{li}b{b}.conv3"]
+        names += [f"L{li}b{b}.conv1", f"L{li}b{b}.conv2"]
+        if b == 0 and not FUSED:
+            names += [f"L{li}b{b}.down"]
+        names += [f"L{li}b{b}.conv3" + ("+down" if (b == 0 and FUSED) else "")]
 names.append("gap_bn")
 lines = [l for l in open(sys.argv[1]) if not l.startswith("==")]
 rows = list(csv.DictReader(lines))
@@ -46,4 +50,4 @@ if have_dram:
     if len(sys.argv) > 2:
         with open(sys.argv[2], "w") as f:
             json.dump({"dram_bytes_per_step": conv_bytes, "source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, "
-                       "52 conv launches of one bs-256 forward (tools/ncu_trunk.sh)"}, f)
+                       f"{sum('conv' in n for n in names)} conv launches of one bs-256 forward (tools/ncu_final.sh)"}, f)
