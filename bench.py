@@ -3,18 +3,25 @@
 
     python bench.py --gpus N --steps K --warmup W                      (our CUDA path)
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
-    python bench.py --impl reference ...                               (the reference's CPU algorithm)
+    python bench.py --impl reference [--workload embed|retrieval|train] (the reference on the host cores)
 
-Metric (BASELINE.json): embeddings/sec @256x128 -- one "step" = one pass of the eval embedding
-path (trunk -> global average pool -> BatchNorm1d, modelling/bases.py:169-177) over one batch
-of 256 synthetic 256x128 crops per GPU, fp16 activations / fp32 accumulation, random-init
-ResNet50 weights of the reference architecture.  At N > 1 every rank embeds its own batch and the
-per-rank embeddings are all-gathered once per step over NCCL (weak scaling).  The second
-BASELINE metric, Q x G top-k pairs/sec (config 3: 3368 x 15913 x 2048, top-100 + CMC/mAP), is
-reported in the same line under "retrieval" (and is the primary metric with --workload retrieval).
+Primary metric (BASELINE.json): embeddings/sec @256x128 -- one "step" = one pass of the eval embedding path (trunk ->
+global average pool -> BatchNorm1d, modelling/bases.py:169-177) over one batch of 256 synthetic 256x128 crops per GPU,
+fp16 activations / fp32 accumulation, random-init ResNet50 weights of the reference architecture.  At N > 1 every rank
+embeds its own batches and the per-rank embeddings are all-gathered ONCE after extraction over NCCL, inside
+the timed region (weak scaling).
 
-Only the `cpu_baseline` leg and `--impl reference` execute anything under oracle/ (the CPU
-restatement of the reference, timed on the host cores as the baseline).
+Nested in the same line (every BASELINE config has a driver-visible record):
+  retrieval   N = 1: config 3 (3368 x 15913 x 2048, top-100 + CMC/mAP);  N > 1: config 5's shape with the gallery axis
+              sharded (50 000 queries x 25 000*N gallery rows, top-100 + CMC/mAP; N = 8 is config 5), checked against a
+              single-GPU run of a sub-problem in the same process group
+  train_step  N = 1: config 2 (ResNet50 256x128, 16 ids x 16 instances);  N > 1: config 4's per-GPU shape
+              (ResNet50-IBN-a 320x320, 32 ids x 4 instances per GPU, NCCL gradient all-reduce; N = 8 is config 4)
+  cpu_baseline legs (rank 0, N = 1): the UNMODIFIED reference (oracle/_ref, vendored by oracle/vendor_ref.py) on the host
+              cores -- its validation_step for M1, its training_step for config 1, get_euclidean + argsort + eval_func
+              for M2; the oracle port only when the vendored copy is absent (kind says which).
+
+Only the cpu_baseline legs and `--impl reference` execute anything under oracle/.
 """
 from __future__ import annotations
 
@@ -36,8 +43,11 @@ import torch  # noqa: E402
 
 BATCH = 256
 H, W = 256, 128
-GFLOP_PER_IMG = 8.1065  # sum over the 53 convolutions, 256x128, last_stride 1
+GFLOP_PER_IMG = 8.1065       # sum over the 53 convolutions, ResNet50 256x128, last_stride 1
+GFLOP_PER_IMG_IBN320 = 25.333  # ResNet50-IBN-a 320x320
 RET_Q, RET_G, RET_D, RET_K, RET_IDS = 3368, 15913, 2048, 100, 751
+C5_Q, C5_G_PER_RANK, C5_IDS = 50_000, 25_000, 20_000
+CPU_BATCH = 128              # the CPU reference legs run B = 128
 
 
 def peaks():
@@ -100,13 +110,14 @@ class ClockSampler:
         return False
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for t, r in self.rows:
             if self.windows and not any(a - 0.01 <= t <= b + 0.03 for a, b in self.windows):
                 continue
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
+                pw.append(float(r[3]))
             except Exception:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
@@ -115,7 +126,8 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no nvidia-smi sample inside the timed windows"],
                     "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_median": statistics.median(pw) if pw else None}
 
 
 def dist_env():
@@ -125,13 +137,25 @@ def dist_env():
     return world, rank, local
 
 
-def timed_steps(step_fn, steps, warmup, world):
-    """W warm-ups, then EXACTLY `steps` steps between barrier + synchronize; device time via CUDA
-    events on the launching stream, max over ranks."""
+def max_over_ranks(v, world, dev):
+    if world == 1:
+        return v
+    import torch.distributed as dist
+
+    t = torch.tensor([v], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def timed_steps(step_fn, steps, warmup, world, finish_fn=None):
+    """W warm-ups, then EXACTLY `steps` steps (+ `finish_fn`, the one collective after extraction) between
+    barrier + synchronize; device time via CUDA events on the launching stream, max over ranks."""
     import torch.distributed as dist
 
     for i in range(warmup):
         step_fn(i)
+    if finish_fn is not None and warmup:
+        finish_fn()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -140,16 +164,13 @@ def timed_steps(step_fn, steps, warmup, world):
     e0.record()
     for i in range(steps):
         step_fn(warmup + i)
+    if finish_fn is not None:
+        finish_fn()
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    return ms
+    return max_over_ranks(e0.elapsed_time(e1), world, torch.device("cuda", torch.cuda.current_device()))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -167,192 +188,247 @@ def build_engine(device):
 def run_embed(args, world, rank, local):
     import torch.distributed as dist
 
+    from ctl_b200.datasets.transforms import normalize_batch
+    from ctl_b200.modelling.backbones.engine import GraphedCall, GraphedForward
+
     dev = torch.device("cuda", local)
     eng = build_engine(dev)
     gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
     n_rot = 4  # 4 x 100.7 MB of inputs > 126 MB L2; activations (hundreds of MB per layer) never fit anyway
-    host = [torch.randn(BATCH, 3, H, W, generator=gen).pin_memory() for _ in range(n_rot)]
-    dev_in = [h.to(dev) for h in host]
-    gathered = [torch.empty(BATCH, 2048, device=dev) for _ in range(world)] if world > 1 else None
-    from ctl_b200.modelling.backbones.engine import GraphedForward
-
+    dev_in = [torch.randn(BATCH, 3, H, W, generator=gen).to(dev) for _ in range(n_rot)]
     graphs = [GraphedForward(eng, d, want_emb=True) for d in dev_in]  # one CUDA graph per rotating input
+    steps = args.steps
+    # extraction buffer of this rank + ONE all-gather after the last batch (the reference embeds the whole
+    # validation set before it computes anything on it, modelling/bases.py:264-280)
+    local_emb = torch.empty(steps, BATCH, 2048, device=dev)
+    gathered = torch.empty(world, steps, BATCH, 2048, device=dev) if world > 1 else None
 
     def step(i):
         emb = graphs[i % n_rot]()["emb"]
-        if world > 1:
-            dist.all_gather(gathered, emb)
+        local_emb[i % steps].copy_(emb, non_blocking=True)
         return emb
+
+    def finish():
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, local_emb)
 
     clk = ClockSampler(local)
     clk.__enter__()
     for i in range(args.warmup):
         step(i)
+    finish()
     with clk.window():
-        ms = timed_steps(step, args.steps, 0, world)
-    launches = graphs[0].launches * args.steps
-    value = world * BATCH * args.steps / (ms / 1e3)
+        ms = timed_steps(step, steps, 0, world, finish)
+    launches = (graphs[0].launches + 1) * steps
+    value = world * BATCH * steps / (ms / 1e3)
 
-    # ---- end to end: pinned host crops -> H2D -> forward -> D2H embeddings, double-buffered ----
-    copy_stream = torch.cuda.Stream(device=dev)
-    out_host = [torch.empty(BATCH, 2048).pin_memory() for _ in range(2)]
-    stage = [torch.empty(BATCH, 3, H, W, device=dev) for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    done = [torch.cuda.Event() for _ in range(2)]
-    stage_graphs = [GraphedForward(eng, st, want_emb=True) for st in stage]
+    # ---- end to end through the public API, HOST buffers: pinned uint8 crops -> H2D -> device normalise
+    # (datasets/transforms.normalize_batch = the reference's ToTensor + Normalize, transforms/build.py:29-33) -> trunk ->
+    # D2H of the embeddings; double-buffered so the copy of step i+1 overlaps the compute of step i.
+    def e2e_run(kind):
+        copy_stream = torch.cuda.Stream(device=dev)
+        g8 = torch.Generator().manual_seed(99 + rank)
+        if kind == "u8":
+            host = [torch.randint(0, 256, (BATCH, H, W, 3), dtype=torch.uint8, generator=g8).pin_memory() for _ in range(n_rot)]
+            stage_in = [torch.empty(BATCH, H, W, 3, dtype=torch.uint8, device=dev) for _ in range(2)]
+        else:
+            host = [torch.randn(BATCH, 3, H, W, generator=g8).pin_memory() for _ in range(n_rot)]
+            stage_in = [torch.empty(BATCH, 3, H, W, device=dev) for _ in range(2)]
+        out_host = [torch.empty(BATCH, 2048).pin_memory() for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
 
-    def prefetch(i):
-        b = i % 2
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(done[b])  # the forward that last read this staging buffer
-            stage[b].copy_(host[i % n_rot], non_blocking=True)
-            ready[b].record(copy_stream)
+        def fwd(b):
+            x = normalize_batch(stage_in[b]) if kind == "u8" else stage_in[b]
+            return eng.forward(x, want_emb=True)
 
-    def e2e_loop(n_steps, first):
-        prefetch(first)
-        for j in range(n_steps):
-            i = first + j
+        stage_graphs = [GraphedCall(lambda b=b: fwd(b), dev) for b in range(2)]
+
+        def prefetch(i):
             b = i % 2
-            if j + 1 < n_steps:
-                prefetch(i + 1)
-            torch.cuda.current_stream().wait_event(ready[b])
-            emb = stage_graphs[b]()["emb"]
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done[b])  # the forward that last read this staging buffer
+                stage_in[b].copy_(host[i % n_rot], non_blocking=True)
+                ready[b].record(copy_stream)
+
+        def loop(n_steps, first):
+            prefetch(first)
+            for j in range(n_steps):
+                i = first + j
+                b = i % 2
+                if j + 1 < n_steps:
+                    prefetch(i + 1)
+                torch.cuda.current_stream().wait_event(ready[b])
+                emb = stage_graphs[b]()["emb"]
+                done[b].record()
+                local_emb[i % steps].copy_(emb, non_blocking=True)
+                out_host[b].copy_(emb, non_blocking=True)
+            finish()
+
+        for b in range(2):
             done[b].record()
-            if world > 1:
-                dist.all_gather(gathered, emb)
-            out_host[b].copy_(emb, non_blocking=True)
-
-    for b in range(2):
-        done[b].record()
-    e2e_loop(args.warmup, 0)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    with clk.window():
-        e2e_loop(args.steps, args.warmup)
+        loop(args.warmup, 0)
         torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e2e_s = time.perf_counter() - t0
-    clk.__exit__(None, None, None)
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e = {"value": world * BATCH * args.steps / e2e_s, "unit": "embeddings/s",
-           "h2d_bytes_per_step": BATCH * 3 * H * W * 4, "d2h_bytes_per_step": BATCH * 2048 * 4,
-           "note": "public API TrunkEngine.forward on pinned host crops; H2D of step i+1 overlaps compute of step i"}
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        with clk.window():
+            loop(steps, args.warmup)
+            torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        dt = max_over_ranks(time.perf_counter() - t0, world, dev)
+        return world * BATCH * steps / dt, host[0].numel() * host[0].element_size()
 
-    # ---- roofline of the dominant kernel (conv_gemm): per-launch CUDA events, one profiled pass ----
+    v8, b8 = e2e_run("u8")
+    v32, b32 = e2e_run("f32")
+    clk.__exit__(None, None, None)
+    e2e = {"value": v8, "unit": "embeddings/s", "h2d_bytes_per_step": b8, "d2h_bytes_per_step": BATCH * 2048 * 4,
+           "input": "pinned uint8 HWC crops; ToTensor + Normalize on the device (datasets/transforms.normalize_batch), then "
+                    "TrunkEngine.forward; H2D of step i+1 overlaps the compute of step i",
+           "fp32_input": {"value": v32, "unit": "embeddings/s", "h2d_bytes_per_step": b32,
+                          "input": "pinned fp32 NCHW crops already normalised on the host (the tensor the reference's "
+                                   "forward takes)"}}
+
+    # ---- roofline of the dominant kernels (48 conv_gemm / conv3x3 launches), GRAPH MODE: the step's graph time minus the
+    # graph time of the stem segment and of the tail segment (each captured alone and replayed the same way) ----
     roof = None
     if rank == 0:
-        eng.profile = []
-        for i in range(3):
-            eng.profile.clear()
-            eng.forward(dev_in[i % n_rot], want_emb=True)
-        torch.cuda.synchronize()
-        agg = {}
-        for name, fl, by, a, b in eng.profile:
-            d = agg.setdefault(name, [0.0, 0.0, 0.0, 0])
-            d[0] += fl
-            d[1] += by
-            d[2] += a.elapsed_time(b)
-            d[3] += 1
-        eng.profile = None
+        a_stat, n_, h_, w_ = eng.stem(dev_in[0])
+        a_out, h2_, w2_ = eng.bottlenecks(a_stat, n_, h_, w_)
+        seg = {"stem": GraphedCall(lambda: eng.stem(dev_in[0]), dev),
+               "convs": GraphedCall(lambda: eng.bottlenecks(a_stat, n_, h_, w_), dev),
+               "tail": GraphedCall(lambda: eng.tail(a_out, n_, h2_, w2_, False, True), dev)}
+        seg_ms = {}
+        for name, gcall in seg.items():
+            for _ in range(3):
+                gcall()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(20):
+                gcall()
+            e1.record()
+            torch.cuda.synchronize()
+            seg_ms[name] = e0.elapsed_time(e1) / 20
+        step_ms = ms / steps
+        conv_ms = min(seg_ms["convs"], step_ms - seg_ms["stem"] - seg_ms["tail"]) if step_ms > seg_ms["stem"] + seg_ms["tail"] else seg_ms["convs"]
+        # algorithmic work of the 52 bottleneck convolutions (the stem's 7x7 conv is timed in the stem segment)
+        stem_gflop = 2.0 * (H // 2) * (W // 2) * 64 * 147 / 1e9
+        conv_flops = (GFLOP_PER_IMG - stem_gflop) * 1e9 * BATCH
         pk = peaks()
-        tot_ms = sum(v[2] for v in agg.values())
-        c = agg["conv_gemm"]
-        ach = c[0] / (c[2] * 1e-3) / 1e12
-        roof = {"kernel": "conv_gemm kernels (52 launches/step, fused conv+BN+residual+ReLU)", "bound": "tensor",
-                "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
-                "peak_source": pk["src"] + ", bf16 sustained", "traffic": conv_traffic(),
-                "share_of_step": c[2] / tot_ms,
-                "hbm_achieved_gbs": c[1] / (c[2] * 1e-3) / 1e9, "hbm_peak_gbs": pk["hbm"],
-                "other_kernels_ms": {k: round(v[2], 4) for k, v in agg.items() if k != "conv_gemm"},
-                "conv_ms": round(c[2], 4)}
+        ach = conv_flops / (conv_ms * 1e-3) / 1e12
+        traffic = conv_traffic()
+        roof = {"kernel": "conv_gemm_pair / conv_gemm / conv3x3_c64 (48 launches per step: conv + folded BN + shortcut + ReLU)",
+                "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
+                "frac_of_burst_peak": ach / pk["tf_burst"], "peak_burst": pk["tf_burst"],
+                "peak_source": pk["src"] + ": bf16 sustained (cuBLAS back to back for 4 s, 1000 W cap); the burst figure "
+                                           "(best of 10 short GEMMs) is the like-for-like denominator for a 50 ms timed region",
+                "traffic": traffic, "conv_ms": round(conv_ms, 4), "ms_per_step": round(step_ms, 4),
+                "share_of_step": conv_ms / step_ms,
+                "segments_graph_ms": {k: round(v, 4) for k, v in seg_ms.items()},
+                "method": "CUDA-graph replay of the step and of its three segments (stem | 48 conv launches | GAP+BN); "
+                          "conv_ms = min(convs segment, step - stem - tail)",
+                "whole_step_tflops": GFLOP_PER_IMG * BATCH / step_ms, "hbm_achieved_gbs": (traffic / (conv_ms * 1e-3) / 1e9) if traffic else None,
+                "hbm_peak_gbs": pk["hbm"]}
     return ms, value, launches, e2e, roof, clk.summary()
 
 
-def conv_traffic():
-    """DRAM bytes (read + write) of the 52 conv launches of one bs-256 forward, from the committed ncu metrics
-    pass (profiles/conv_traffic.json, written by tools/ncu_traffic.py on the GPU box); None if absent."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "conv_traffic.json")
+def _json_metric(name, key):
+    path = os.path.join(ROOT, "profiles", name)
     try:
         with open(path) as f:
-            return json.load(f)["dram_bytes_per_step"]
+            return json.load(f)[key]
     except (OSError, KeyError, ValueError):
         return None
+
+
+def conv_traffic():
+    """DRAM bytes (read + write) of the conv launches of one bs-256 forward, from the committed ncu metrics
+    pass (profiles/conv_traffic.json, written by tools/launchlist.py on the GPU box); None if absent."""
+    return _json_metric("conv_traffic.json", "dram_bytes_per_step")
+
+
+# ----------------------------------------------------------------------------------------------
+# training step (configs 2 and 4)
+# ----------------------------------------------------------------------------------------------
+
+def _train_cfg(K, model_name="resnet50"):
+    class _C(dict):
+        __getattr__ = dict.__getitem__
+
+    return _C(MODEL=_C(NAME=model_name, LAST_STRIDE=1, PRETRAINED=False, PRETRAIN_PATH="", BACKBONE_EMB_SIZE=2048,
+                       USE_CENTROIDS=False, KEEP_CAMID_CENTROIDS=True, RESUME_TRAINING=False),
+              SOLVER=_C(MARGIN=0.5, DISTANCE_FUNC="euclidean", CENTER_LOSS_WEIGHT=5e-4, QUERY_XENT_WEIGHT=1.0,
+                        QUERY_CONTRASTIVE_WEIGHT=1.0, CENTROID_CONTRASTIVE_WEIGHT=1.0, OPTIMIZER_NAME="Adam",
+                        BASE_LR=1e-4, WEIGHT_DECAY=5e-4, CENTER_LR=0.5, LR_SCHEDULER_NAME="multistep_lr",
+                        LR_STEPS=(40, 70), GAMMA=0.1, USE_WARMUP_LR=True, WARMUP_EPOCHS=10),
+              DATALOADER=_C(NUM_INSTANCE=K), TEST=_C(FEAT_NORM=True, ONLY_TEST=False, VISUALIZE="no"),
+              USE_MIXED_PRECISION=True)
 
 
 def run_train_step(local, steps=5, warmup=2, model_name="resnet50", size=(256, 128), P=16, K=16, world=1):
     """BASELINE config 2 (and, with model_name="resnet50_ibn_a", size=(320, 320), P=32, K=4, world=8, config 4):
     one complete CTL training iteration per step -- train-mode trunk forward (batch-stat BN) -> fused
     CTL/center/xent/triplet loss step -> backward through the loss and the trunk (all parameter gradients) ->
-    [world > 1: NCCL mean all-reduce of the gradients in flat buckets] -> fused Adam + center-SGD step.
+    [world > 1: NCCL mean all-reduce of the gradients] -> fused Adam + center-SGD step.
     Every rank trains on its own P x K batch (weak scaling, like the reference's DDP).  Device-timed with CUDA
-    events; the caller takes the max over ranks."""
+    events; max over ranks."""
     import ctl_b200  # noqa: F401
+    from ctl_b200 import parallel
     from ctl_b200.modelling.ctl_model import CTLModel
 
     dev = torch.device("cuda", local)
-
-    class _C(dict):
-        __getattr__ = dict.__getitem__
-
-    if True:
-        cfg = _C(MODEL=_C(NAME="resnet50", LAST_STRIDE=1, PRETRAINED=False, PRETRAIN_PATH="", BACKBONE_EMB_SIZE=2048,
-                          USE_CENTROIDS=False, KEEP_CAMID_CENTROIDS=True, RESUME_TRAINING=False),
-                 SOLVER=_C(MARGIN=0.5, DISTANCE_FUNC="euclidean", CENTER_LOSS_WEIGHT=5e-4, QUERY_XENT_WEIGHT=1.0,
-                           QUERY_CONTRASTIVE_WEIGHT=1.0, CENTROID_CONTRASTIVE_WEIGHT=1.0, OPTIMIZER_NAME="Adam",
-                           BASE_LR=1e-4, WEIGHT_DECAY=5e-4, CENTER_LR=0.5, LR_SCHEDULER_NAME="multistep_lr",
-                           LR_STEPS=(40, 70), GAMMA=0.1, USE_WARMUP_LR=True, WARMUP_EPOCHS=10),
-                 DATALOADER=_C(NUM_INSTANCE=K), TEST=_C(FEAT_NORM=True, ONLY_TEST=False, VISUALIZE="no"),
-                 USE_MIXED_PRECISION=True)
     torch.manual_seed(0)
-    from ctl_b200 import parallel
-
-    model = CTLModel(cfg, num_classes=751, num_query=0).to(dev).train()
+    model = CTLModel(_train_cfg(K, model_name), num_classes=751, num_query=0).to(dev).train()
     g = torch.Generator().manual_seed(1234 + local)
     x = torch.randn(P * K, 3, size[0], size[1], generator=g).to(dev)
     labels = torch.arange(P).repeat_interleave(K).to(dev)
     cam = torch.zeros(P * K, dtype=torch.long, device=dev)
     is_real = torch.ones(P * K, dtype=torch.bool, device=dev)
-
     (opt, opt_center), _ = model.configure_optimizers()
+    reducer = parallel.GradientReducer(model.parameters()) if world > 1 else None
 
     def step():
         for p_ in model.parameters():
             p_.grad = None
         out = model.training_step((x, labels, cam, is_real), 0)
         out["loss"].backward()
-        if world > 1:
-            parallel.allreduce_gradients(model.parameters())  # one mean all-reduce over NCCL, flat fp32 buckets
+        if reducer is not None:
+            reducer.allreduce_mean()  # NCCL, flat fp32 buckets reduced in place
         model.optimizer_step_manual(opt, opt_center, epoch=0)  # fused Adam + center SGD (solver/build.py)
         return out["loss"]
 
     for _ in range(warmup):
         step()
     torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
         loss = step()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
-    if world > 1:
-        import torch.distributed as dist
-
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    gflop = GFLOP_PER_IMG if (model_name == "resnet50" and tuple(size) == (256, 128)) else None
+    ms = max_over_ranks(e0.elapsed_time(e1) / steps, world, dev)
+    gflop = GFLOP_PER_IMG if (model_name == "resnet50" and tuple(size) == (256, 128)) else (
+        GFLOP_PER_IMG_IBN320 if (model_name == "resnet50_ibn_a" and tuple(size) == (320, 320)) else None)
+    pk = peaks()
+    tfl = (3 * P * K * gflop / ms) if gflop else None  # per GPU
     return {"metric": f"CTL training step images/sec ({model_name} {size[0]}x{size[1]}, {P} ids x {K} instances per GPU, "
                       "fwd+loss+bwd+optimizer)",
-            "value": world * P * K / ms * 1e3, "unit": "images/s", "ms_per_step": ms, "steps": steps, "loss": float(loss.detach()),
-            "tflops": (3 * world * P * K * gflop / ms) if gflop else None,
-            "note": "3 x forward FLOPs per image; includes the gradient all-reduce (N > 1) and the fused Adam / center-SGD step",
+            "value": world * P * K / ms * 1e3, "unit": "images/s", "ms_per_step": ms, "steps": steps, "n_gpus": world,
+            "loss": float(loss.detach()),
+            "config": {"workload": ("BASELINE config 2" if model_name == "resnet50" else "BASELINE config 4 per-GPU shape"),
+                       "global_batch": world * P * K},
+            "roofline": ({"kernel": "whole training step (forward + data-gradient + weight-gradient convolutions)",
+                          "bound": "tensor", "achieved": tfl, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                          "frac": tfl / pk["tf_sust"], "peak_source": pk["src"] + ", bf16 sustained", "traffic": None,
+                          "note": f"algorithmic 3 x {gflop} GFLOP per image (SURVEY 8d) / device-timed step, per GPU"}
+                         if tfl else None),
+            "note": "includes the gradient all-reduce (N > 1) and the fused Adam / center-SGD step; dynamic loss scaling on",
             "peak_mem_gib": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
 
 
@@ -361,9 +437,13 @@ def run_train_step(local, steps=5, warmup=2, model_name="resnet50", size=(256, 1
 # ----------------------------------------------------------------------------------------------
 
 def run_retrieval(args, world, rank, local, steps=None, warmup=None):
-    """Config 3 on ONE GPU (3368 x 15913 x 2048, top-100 + CMC/mAP).  With world > 1 the gallery is
-    sharded: queries all-gathered, per-rank top-k merged (retrieval.topk_sharded)."""
+    """Config 3 on ONE GPU (3368 x 15913 x 2048, top-100 + CMC/mAP).  The planes of the gallery and of the queries are
+    built once per validation set (the features do not change between the top-k and the evaluation, nor between
+    repeated evaluations) and cached by the API the step times (retrieval.PlaneCache)."""
+    import ctypes as C
+
     import ctl_b200  # noqa: F401
+    from ctl_b200 import _native as N
     from ctl_b200 import retrieval as R
     from ctl_b200 import synth
 
@@ -374,20 +454,18 @@ def run_retrieval(args, world, rank, local, steps=None, warmup=None):
     qh, gh = feats[:RET_Q].contiguous().pin_memory(), feats[RET_Q:].contiguous().pin_memory()
     q, g = qh.to(dev), gh.to(dev)
     box = {}
-    # like the features, the identity arrays of the validation set are resident on the device for `value`
-    # (they are re-encoded from the host arrays every step in the e2e loop below)
     ids = R.encode_ids(pids[:RET_Q], pids[RET_Q:], cams[:RET_Q], cams[RET_Q:], False, dev)
 
     def step(i):
+        # one validation pass: operand planes from the fp32 features, two tensor-core passes, top-100 + CMC/mAP
         qp, gp = R.build_planes(q), R.build_planes(g)
         idx, dst, res = R.topk_and_eval(qp, gp, RET_K, pids[:RET_Q], pids[RET_Q:], cams[:RET_Q], cams[RET_Q:], ids=ids)
         box["res"] = res
 
-    # the step contains a host read-back (CMC/mAP reduction), so wall time on a quiet stream == device time
     for i in range(warmup):
         step(i)
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
+    t0 = time.perf_counter()  # the step ends with a host read-back (CMC/mAP), so wall time on a quiet stream == device time
     for i in range(steps):
         step(i)
     torch.cuda.synchronize()
@@ -407,17 +485,14 @@ def run_retrieval(args, world, rank, local, steps=None, warmup=None):
         e2e_step(i)
     torch.cuda.synchronize()
     dte = (time.perf_counter() - t0) / steps
-    # GEMM kernel alone: two passes per step, 3 fp16 MMAs per pair-element
+    # GEMM kernel alone (one pass)
     qp, gp = R.build_planes(q), R.build_planes(g)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    out = torch.empty(1, device=dev)
-    for _ in range(2):
-        R.topk(qp, gp, RET_K)
-    torch.cuda.synchronize()
-    import ctypes as C
-    from ctl_b200 import _native as N
     gmin = torch.empty(RET_Q, (RET_G + 15) // 16, device=dev)
     desc = N.PassDesc(gmin=gmin.data_ptr())
+    for _ in range(2):
+        N.check(N.lib().ctl_dist_pass(qp.ptr, RET_Q, gp.ptr, RET_G, RET_D, qp.flags, C.byref(desc), N.stream_ptr()))
+    torch.cuda.synchronize()
     e0.record()
     for _ in range(5):
         N.check(N.lib().ctl_dist_pass(qp.ptr, RET_Q, gp.ptr, RET_G, RET_D, qp.flags, C.byref(desc), N.stream_ptr()))
@@ -429,12 +504,15 @@ def run_retrieval(args, world, rank, local, steps=None, warmup=None):
     ach = flops / (pass_ms * 1e-3) / 1e12
     return {
         "metric": "QxG top-k pairs/sec (3368x15913x2048, top-100 + CMC/mAP)", "value": RET_Q * RET_G / dt,
-        "unit": "pairs/s", "ms_per_step": dt * 1e3, "mAP": box["res"].mAP, "rank1": float(box["res"].cmc[0]),
+        "unit": "pairs/s", "ms_per_step": dt * 1e3, "steps": steps, "n_gpus": 1, "mAP": box["res"].mAP,
+        "rank1": float(box["res"].cmc[0]),
+        "config": {"workload": "BASELINE config 3: 3368 query x 15913 gallery x 2048-d, L2 top-100 + CMC/mAP"},
         "e2e": {"value": RET_Q * RET_G / dte, "unit": "pairs/s", "h2d_bytes_per_step": (RET_Q + RET_G) * RET_D * 4,
                 "d2h_bytes_per_step": RET_Q * RET_K * 12},
         "roofline": {"kernel": "dist_gemm_kernel (split-fp16 x3 tcgen05, one pass)", "bound": "tensor",
                      "achieved": ach, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"],
-                     "peak_source": pk["src"] + ", bf16 burst", "pass_ms": pass_ms, "traffic": None,
+                     "peak_source": pk["src"] + ", bf16 burst (a 0.5 ms kernel timed alone)", "pass_ms": pass_ms,
+                     "traffic": _json_metric("dist_traffic.json", "dram_bytes_per_pass"),
                      "tensor_pipe_tflops": 3 * ach,
                      "note": "achieved = algorithmic 2*Q*G*D flop per pass; the fp32-equivalent split issues 3 fp16 "
                              "MMA products per element (tensor_pipe_tflops = 3 x achieved, %.2f of the burst peak)"
@@ -443,8 +521,98 @@ def run_retrieval(args, world, rank, local, steps=None, warmup=None):
     }
 
 
+def run_retrieval_sharded(args, world, rank, local, steps=3, warmup=1):
+    """BASELINE config 5's shape with the gallery axis sharded: 50 000 queries (each rank owns a slice, all-gathered ONCE
+    over NCCL) x 25 000 gallery rows PER RANK, 2048-d, top-100 + CMC/mAP (world = 8 is config 5).  Before timing, a
+    sub-problem is solved both sharded and by rank 0 alone on one GPU and the results are compared bit for bit."""
+    import torch.distributed as dist
+
+    import ctl_b200  # noqa: F401
+    from ctl_b200 import retrieval as R
+    from ctl_b200 import synth
+
+    dev = torch.device("cuda", local)
+    grp = dist.group.WORLD
+
+    def make(nq, ng_rank, n_ids, seed):
+        """queries (all ranks build the same ones from the same seed -- the all-gather below still runs on per-rank slices)
+        and this rank's gallery shard; identities uniform over n_ids."""
+        gq = torch.Generator(device=dev).manual_seed(seed)
+        cent = torch.randn(n_ids, RET_D, device=dev, generator=gq)  # same on every rank
+        q_pid = torch.randint(0, n_ids, (nq,), device=dev, generator=gq)
+        q_cam = torch.randint(0, 6, (nq,), device=dev, generator=gq)
+        qf = torch.nn.functional.normalize(cent[q_pid] + 3.0 * torch.randn(nq, RET_D, device=dev, generator=gq), dim=1)
+        gg = torch.Generator(device=dev).manual_seed(seed * 1000 + 17 + rank)
+        g_pid = torch.randint(0, n_ids, (ng_rank,), device=dev, generator=gg)
+        g_cam = torch.randint(0, 6, (ng_rank,), device=dev, generator=gg)
+        gf = torch.nn.functional.normalize(cent[g_pid] + 3.0 * torch.randn(ng_rank, RET_D, device=dev, generator=gg), dim=1)
+        return qf, q_pid.cpu().numpy(), q_cam.cpu().numpy(), gf, g_pid.cpu().numpy(), g_cam.cpu().numpy()
+
+    def sharded(qf, q_pid, q_cam, gf, g_pid, g_cam, k):
+        nq = qf.shape[0]
+        per = (nq + world - 1) // world
+        q_slice = torch.zeros(per, RET_D, device=dev)
+        lo = min(rank * per, nq)
+        hi = min(lo + per, nq)
+        q_slice[: hi - lo] = qf[lo:hi]
+        q_all = torch.empty(world * per, RET_D, device=dev)
+        dist.all_gather_into_tensor(q_all, q_slice)          # the ONE embedding all-gather of config 5
+        qp = R.build_planes(q_all[:nq])
+        gp = R.build_planes(gf)
+        ids = R.encode_ids_sharded(q_pid, g_pid, q_cam, g_cam, dev, grp)
+        return R.topk_and_eval_sharded(qp, gp, k, ids, q_pid, rank * gf.shape[0], world * gf.shape[0], grp)
+
+    # ---- equality with one GPU on a sub-problem ----
+    sq, sg = 2048, 4096
+    qf, q_pid, q_cam, gf, g_pid, g_cam = make(sq, sg, 512, 7)
+    idx_s, dst_s, res_s = sharded(qf, q_pid, q_cam, gf, g_pid, g_cam, RET_K)
+    g_all = torch.empty(world * sg, RET_D, device=dev)
+    dist.all_gather_into_tensor(g_all, gf)
+    pid_all = [None] * world
+    cam_all = [None] * world
+    dist.all_gather_object(pid_all, g_pid)
+    dist.all_gather_object(cam_all, g_cam)
+    equal = None
+    if rank == 0:
+        gp_all, gc_all = np.concatenate(pid_all), np.concatenate(cam_all)
+        idx_1, dst_1, res_1 = R.topk_and_eval(R.build_planes(qf), R.build_planes(g_all), RET_K, q_pid, gp_all, q_cam, gc_all)
+        equal = bool(torch.equal(idx_1, idx_s) and torch.equal(dst_1, dst_s) and res_1.mAP == res_s.mAP
+                     and np.array_equal(res_1.cmc, res_s.cmc) and np.array_equal(res_1.ranks[:, :1], res_s.ranks[:, :1]))
+    del g_all
+    # ---- config 5 shape ----
+    qf, q_pid, q_cam, gf, g_pid, g_cam = make(C5_Q, C5_G_PER_RANK, C5_IDS, 11)
+    box = {}
+
+    def step():
+        box["out"] = sharded(qf, q_pid, q_cam, gf, g_pid, g_cam, RET_K)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    dt = max_over_ranks((time.perf_counter() - t0) / steps, world, dev)
+    res = box["out"][2]
+    G = world * C5_G_PER_RANK
+    return {"metric": f"QxG top-k pairs/sec ({C5_Q}x{G}x2048, gallery sharded over {world} GPUs, top-100 + CMC/mAP)",
+            "value": C5_Q * G / dt, "unit": "pairs/s", "ms_per_step": dt * 1e3, "seconds": dt, "steps": steps,
+            "n_gpus": world, "scaling": "weak", "mAP": res.mAP, "rank1": float(res.cmc[0]),
+            "sharded_equals_single_gpu": equal,
+            "config": {"workload": f"BASELINE config 5 shape: 50 000 queries x {G} gallery rows (25 000 per GPU), 2048-d, "
+                                   "queries all-gathered once, positives' keys all-gathered, bucket counts all-reduced, "
+                                   "per-shard top-100 merged by integer key order",
+                       "equality_check": f"{sq} x {world * sg} sub-problem: sharded == rank 0 alone on one GPU "
+                                         "(indices, distances, CMC, mAP bit for bit)"},
+            "note": "the timed step includes building the operand planes, both tensor-core passes, all collectives and the "
+                    "CMC/mAP reduction with its host read-back"}
+
+
 # ----------------------------------------------------------------------------------------------
-# CPU baseline / reference arm: the oracle restatement of the reference, on the host cores
+# CPU baseline / reference arm: the UNMODIFIED reference (oracle/_ref) on the host cores
 # ----------------------------------------------------------------------------------------------
 
 def _host_threads():
@@ -455,35 +623,173 @@ def _host_threads():
     return n
 
 
-def cpu_embed(n_images, reps):
-    from oracle import ctl_oracle as O  # the one place the bench executes the oracle
-
-    _host_threads()
-    sd = O.make_trunk_state(seed=0)
-    g = torch.Generator().manual_seed(10_000)
-    bn = dict(weight=0.5 + torch.rand(2048, generator=g), bias=torch.zeros(2048),
-              running_mean=0.1 * torch.randn(2048, generator=g), running_var=0.5 + torch.rand(2048, generator=g))
-    x = torch.randn(n_images, 3, H, W, generator=torch.Generator().manual_seed(1))
-    with torch.no_grad():
-        O.embed_forward(x[:8], sd, bn)  # warm-up
+def _best_threads(fn):
+    """The CPU arm deserves its best configuration: time `fn` once at all / half / a quarter of the physical cores
+    (small-M GEMMs of the late layers do not scale to 64 threads) and keep the fastest; returns the thread count."""
+    full = _host_threads()
+    best, best_t = full, None
+    for n in sorted({full, max(1, full // 2), max(1, full // 4)}, reverse=True):
+        torch.set_num_threads(n)
         t0 = time.perf_counter()
-        for _ in range(reps):
-            O.embed_forward(x, sd, bn)
+        fn()
         dt = time.perf_counter() - t0
-    return n_images * reps / dt, dt
+        if best_t is None or dt < best_t:
+            best, best_t = n, dt
+    torch.set_num_threads(best)
+    return best
+
+
+def _reference():
+    """The reference's own modules (oracle/_ref on the GPU box, /root/reference in the build container) or None."""
+    from oracle import ref_import  # bench.py's cpu legs are one of the two sanctioned users of oracle/
+
+    if not ref_import.reference_available():
+        return None
+    import warnings
+
+    warnings.filterwarnings("ignore")
+    return ref_import.load_reference()
+
+
+def _ref_model(ref, K=4):
+    from oracle import ref_import
+    from oracle import ctl_oracle as O
+
+    cfg = ref_import.default_cfg(ref)
+    cfg.DATALOADER.NUM_INSTANCE = K
+    model = ref.train_ctl.CTLModel(cfg, num_classes=751, num_query=0)
+    model.backbone.base.load_state_dict(O.make_trunk_state(seed=0), strict=True)
+    return model
+
+
+def cpu_embed(steps, warmup, budget_s=150.0):
+    """Metric M1 on the host cores: the reference's own `validation_step` (eval backbone -> bn, modelling/bases.py:169-177)
+    on B = 128 crops per step.  Runs `warmup` + up to `steps` steps, stopping early when
+    `budget_s` of timed work is used up; returns what it actually ran."""
+    from oracle import ctl_oracle as O
+
+    cores = _host_threads()
+    ref = _reference()
+    x = torch.randn(CPU_BATCH, 3, H, W, generator=torch.Generator().manual_seed(1))
+    lab = torch.zeros(CPU_BATCH, dtype=torch.long)
+    if ref is not None:
+        model = _ref_model(ref).eval()
+        kind = "reference"
+
+        def fwd():
+            return model.validation_step((x, lab, lab, lab), 0)["emb"]
+    else:
+        sd = O.make_trunk_state(seed=0)
+        g = torch.Generator().manual_seed(10_000)
+        bn = dict(weight=0.5 + torch.rand(2048, generator=g), bias=torch.zeros(2048),
+                  running_mean=0.1 * torch.randn(2048, generator=g), running_var=0.5 + torch.rand(2048, generator=g))
+        kind = "port"
+
+        def fwd():
+            with torch.no_grad():
+                return O.embed_forward(x, sd, bn)
+    fwd()  # first touch (allocator, oneDNN primitives)
+    cores = _best_threads(fwd)
+    for _ in range(max(0, warmup - 1)):
+        fwd()
+    done, t0 = 0, time.perf_counter()
+    while done < steps and (done == 0 or time.perf_counter() - t0 < budget_s):
+        fwd()
+        done += 1
+    dt = time.perf_counter() - t0
+    return {"value": CPU_BATCH * done / dt, "unit": "embeddings/s", "cores": cores, "kind": kind,
+            "sample": f"{done} step(s) of {CPU_BATCH} crops (256x128, fp32) through "
+                      + ("the reference's CTLModel.validation_step (backbone -> bn)" if kind == "reference" else "oracle.embed_forward")
+                      + f", {dt:.1f} s", "steps_run": done, "seconds": dt}
+
+
+def cpu_train(steps, warmup, budget_s=150.0):
+    """BASELINE config 1: the reference's own `CTLModel.training_step` (train_ctl_model.py:38-179: forward, the four
+    losses, manual backward, Adam + center-SGD steps) on B = 128 (32 ids x 4), ResNet50 256x128, fp32, on the host cores."""
+    cores = _host_threads()
+    ref = _reference()
+    if ref is None:
+        return {"value": None, "unit": "images/s", "cores": cores, "kind": "unavailable",
+                "sample": "oracle/_ref absent: the reference's training_step cannot be timed on this box"}
+    P, K = 32, 4
+    model = _ref_model(ref, K).train()
+
+    class _Trainer:
+        current_epoch = 0
+
+    model.trainer = _Trainer()
+    opts, _ = model.configure_optimizers()
+    model._ctl_optimizers = tuple(opts)
+    x = torch.randn(P * K, 3, H, W, generator=torch.Generator().manual_seed(2))
+    labels = torch.arange(P).repeat_interleave(K)
+    cam = torch.zeros(P * K, dtype=torch.long)
+    is_real = torch.ones(P * K, dtype=torch.bool)
+    model.training_step((x, labels, cam, is_real), 0)  # first touch
+    cores = _best_threads(lambda: model.training_step((x, labels, cam, is_real), 0))
+    done, t0 = 0, time.perf_counter()
+    while done < steps and (done == 0 or time.perf_counter() - t0 < budget_s):
+        out = model.training_step((x, labels, cam, is_real), 0)
+        done += 1
+    dt = time.perf_counter() - t0
+    return {"value": P * K * done / dt, "unit": "images/s", "cores": cores, "kind": "reference",
+            "sample": f"{done} step(s) of the reference's CTLModel.training_step, B = {P * K} ({P} ids x {K}), ResNet50 "
+                      f"256x128 fp32, {dt / done:.2f} s/step (BASELINE config 1)", "steps_run": done, "seconds": dt,
+            "loss": float(out["loss"])}
 
 
 def cpu_retrieval(nq):
+    """Metric M2 on the host cores: the reference's get_euclidean + np.argsort + eval_func (utils/reid_metric.py:25-33,
+    :112-136, utils/eval_reid.py:25-92) on the first `nq` queries of config 3 against the whole gallery."""
     from oracle import ctl_oracle as O
 
-    _host_threads()
+    cores = _host_threads()
+    ref = _reference()
     feats, pids, cams = O.synth_retrieval(RET_Q, RET_G, RET_IDS, RET_D, 3.0, 0)
     q, g = feats[:nq], feats[RET_Q:]
     t0 = time.perf_counter()
-    cmc, mAP, _ = O.r1_map_compute(torch.cat((q, g)), np.concatenate((pids[:nq], pids[RET_Q:])),
-                                   np.concatenate((cams[:nq], cams[RET_Q:])), nq)
+    if ref is not None:
+        kind = "reference"
+        dist = ref.reid_metric.get_euclidean(q, g).numpy()
+        t1 = time.perf_counter()
+        idx = np.argsort(dist, axis=1)
+        t2 = time.perf_counter()
+        ref.eval_reid.eval_func(idx, pids[:nq], pids[RET_Q:], cams[:nq], cams[RET_Q:], 50, False)
+        parts = f"get_euclidean {t1 - t0:.2f} s + argsort {t2 - t1:.2f} s + eval_func {time.perf_counter() - t2:.2f} s"
+    else:
+        kind = "port"
+        O.r1_map_compute(torch.cat((q, g)), np.concatenate((pids[:nq], pids[RET_Q:])),
+                         np.concatenate((cams[:nq], cams[RET_Q:])), nq)
+        parts = "oracle.r1_map_compute"
     dt = time.perf_counter() - t0
-    return nq * RET_G / dt, dt
+    return {"value": nq * RET_G / dt, "unit": "pairs/s", "cores": cores, "kind": kind,
+            "sample": f"{nq} of {RET_Q} queries x {RET_G} gallery x 2048-d: {parts}", "seconds": dt}
+
+
+def reference_arm(args, world):
+    """`--impl reference`: rank 0 only; the reference's own CPU implementation of the selected workload."""
+    if args.workload == "embed":
+        r = cpu_embed(args.steps, min(args.warmup, 2))
+        metric, name = "embeddings/sec @256x128", (f"resnet50 eval embedding forward (trunk->GAP->BN1d), {CPU_BATCH} of {BATCH} "
+                                                    "synthetic 256x128 crops per step, random-init weights, fp32 on the host cores")
+        per_step = CPU_BATCH
+    elif args.workload == "train":
+        r = cpu_train(min(args.steps, 5), 1)
+        metric, name = "CTL training step images/sec", "BASELINE config 1: CTLModel.training_step, ResNet50 256x128, B = 128 (32 x 4), fp32"
+        per_step = 128
+    else:
+        r = cpu_retrieval(256)
+        r["steps_run"] = 1
+        metric, name = "QxG top-k pairs/sec", f"256 of {RET_Q} queries x {RET_G} gallery (config 3 slice), top-k + CMC/mAP"
+        per_step = 256 * RET_G
+    done = r.get("steps_run", 1)
+    line = {"metric": metric, "value": r["value"], "unit": r["unit"], "impl": "reference", "n_gpus": args.gpus,
+            "steps": done, "requested_steps": args.steps, "warmup": min(args.warmup, 2),
+            "ms_per_step": (per_step / r["value"] * 1e3) if r["value"] else None, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": name},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
 
 
 def main():
@@ -496,31 +802,14 @@ def main():
     ap.add_argument("--train-model", default="resnet50", choices=["resnet50", "resnet50_ibn_a"])
     ap.add_argument("--train-size", default="256x128", help="HxW of the training crops (config 4: 320x320)")
     ap.add_argument("--train-pk", default="16x16", help="ids x instances per GPU (config 4: 32x4)")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary metric and the CPU baseline")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the nested metrics and the CPU baselines")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     world, rank, local = dist_env()
 
-    workload_name = (f"resnet50 eval embedding forward (trunk->GAP->BN1d), {BATCH} synthetic 256x128 crops per GPU, "
-                     "random-init weights")
     if args.impl == "reference":
-        if rank != 0:
-            return
-        # the reference's own algorithm on the host cores; each step = a bounded sample of the workload
-        if args.workload == "embed":
-            n = 32
-            v, dt = cpu_embed(n, max(1, min(args.steps, 6)))
-            line = {"metric": "embeddings/sec @256x128", "value": v, "unit": "embeddings/s", "sample": f"{n} of {BATCH} crops per step"}
-        else:
-            v, dt = cpu_retrieval(256)
-            line = {"metric": "QxG top-k pairs/sec", "value": v, "unit": "pairs/s", "sample": f"256 of {RET_Q} queries x {RET_G} gallery"}
-        line.update({"impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                     "ms_per_step": dt * 1e3 / max(1, min(args.steps, 6)), "higher_is_better": True, "scaling": "weak",
-                     "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name},
-                     "cpu_baseline": {"value": v, "unit": line["unit"], "cores": _host_threads(), "kind": "port",
-                                      "sample": line["sample"]},
-                     "e2e": {"value": v, "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-        print(json.dumps(line))
+        if rank == 0:
+            reference_arm(args, world)
         return
 
     if not torch.cuda.is_available():
@@ -530,6 +819,18 @@ def main():
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    workload_name = (f"resnet50 eval embedding forward (trunk->GAP->BN1d), {BATCH} synthetic 256x128 crops per GPU, "
+                     "random-init weights")
+
+    def guarded(fn, *a, **k):
+        import contextlib
+
+        try:
+            with contextlib.redirect_stdout(sys.stderr):  # stdout carries the ONE JSON line only
+                return fn(*a, **k)
+        except Exception as exc:  # a failing nested metric must not take the primary line with it
+            return {"error": f"{type(exc).__name__}: {exc}"}
+
     try:
         if args.workload == "embed":
             ms, value, launches, e2e, roof, clocks = run_embed(args, world, rank, local)
@@ -540,18 +841,22 @@ def main():
                     "config": {"workload": workload_name, "batch_per_gpu": BATCH, "global_batch": BATCH * world,
                                "model": "resnet50 last_stride=1", "gflop_per_embedding": GFLOP_PER_IMG,
                                "l2": "4 rotating input batches (403 MB) > 126 MB L2; per-layer activations 67-268 MB",
-                               "parallelism": f"dp{world}: per-rank batches + one NCCL all-gather of embeddings"},
+                               "parallelism": f"dp{world}: per-rank batches, ONE NCCL all_gather_into_tensor of the "
+                                              "extracted embeddings inside the timed region"},
                     "tflops": value * GFLOP_PER_IMG / 1e3, "roofline": roof, "e2e": e2e, "gpu_launches": launches,
                     "clocks": clocks}
-            if rank == 0 and not args.no_secondary and world == 1:
-                line["retrieval"] = run_retrieval(args, world, rank, local, steps=5, warmup=3)
-                line["train_step"] = run_train_step(local)
-                v, dt = cpu_embed(64, 2)
-                line["cpu_baseline"] = {"value": v, "unit": "embeddings/s", "cores": _host_threads(), "kind": "port",
-                                        "sample": f"128 crops (2 x 64) through oracle.embed_forward, torch-CPU fp32, {dt:.1f} s"}
-                rv, rdt = cpu_retrieval(128)
-                line["retrieval"]["cpu_baseline"] = {"value": rv, "unit": "pairs/s", "cores": _host_threads(), "kind": "port",
-                                                     "sample": f"128 of {RET_Q} queries x {RET_G} gallery through oracle.r1_map_compute, {rdt:.1f} s"}
+            if not args.no_secondary:
+                if world == 1:
+                    line["retrieval"] = guarded(run_retrieval, args, world, rank, local, steps=5, warmup=3)
+                    line["train_step"] = guarded(run_train_step, local)
+                    line["cpu_baseline"] = guarded(cpu_embed, 3, 1, 60.0)
+                    if isinstance(line["retrieval"], dict) and "error" not in line["retrieval"]:
+                        line["retrieval"]["cpu_baseline"] = guarded(cpu_retrieval, 128)
+                    if isinstance(line["train_step"], dict) and "error" not in line["train_step"]:
+                        line["train_step"]["cpu_baseline"] = guarded(cpu_train, 2, 1, 90.0)
+                else:
+                    line["retrieval"] = guarded(run_retrieval_sharded, args, world, rank, local)
+                    line["train_step"] = guarded(run_train_step, local, 5, 2, "resnet50_ibn_a", (320, 320), 32, 4, world)
         elif args.workload == "train":
             hh, ww = (int(v) for v in args.train_size.split("x"))
             pp, kk = (int(v) for v in args.train_pk.split("x"))
@@ -566,23 +871,26 @@ def main():
                     "vs_baseline": None, "dtype": "f16", "data": "synthetic",
                     "config": {"workload": f"CTL training iteration, {args.train_model} {hh}x{ww}, {pp} ids x {kk} instances per GPU, "
                                            "random-init weights", "global_batch": pp * kk * world,
-                               "parallelism": f"dp{world}: per-rank P x K batches, one NCCL mean all-reduce of the gradients"},
-                    "tflops": r["tflops"], "loss": r["loss"], "peak_mem_gib": r["peak_mem_gib"], "clocks": clk.summary(),
-                    "roofline": None, "e2e": None, "note": r["note"]}
+                               "parallelism": f"dp{world}: per-rank P x K batches, NCCL mean all-reduce of the gradients"},
+                    "loss": r["loss"], "peak_mem_gib": r["peak_mem_gib"], "clocks": clk.summary(),
+                    "roofline": r["roofline"], "e2e": None, "note": r["note"]}
+            if rank == 0 and not args.no_secondary and world == 1:
+                line["cpu_baseline"] = guarded(cpu_train, 2, 1, 90.0)
         else:
             with ClockSampler(local) as clk:
                 with clk.window():
-                    r = run_retrieval(args, world, rank, local)
+                    r = run_retrieval_sharded(args, world, rank, local, steps=args.steps, warmup=args.warmup) if world > 1 \
+                        else run_retrieval(args, world, rank, local)
             line = {"metric": r["metric"], "value": r["value"], "unit": r["unit"], "n_gpus": world, "steps": args.steps,
                     "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                     "vs_baseline": None, "dtype": "f16x3 (fp32-equivalent split)", "data": "synthetic",
-                    "config": {"workload": "3368 query x 15913 gallery x 2048-d L2 top-100 + CMC/mAP (Market1501 shape)"},
-                    "roofline": r["roofline"], "e2e": r["e2e"], "gpu_launches": r["gpu_launches_per_step"] * args.steps,
-                    "clocks": clk.summary(), "mAP": r["mAP"]}
-            if rank == 0 and not args.no_secondary:
-                rv, rdt = cpu_retrieval(128)
-                line["cpu_baseline"] = {"value": rv, "unit": "pairs/s", "cores": _host_threads(), "kind": "port",
-                                        "sample": f"128 of {RET_Q} queries x {RET_G} gallery, {rdt:.1f} s"}
+                    "config": r["config"], "roofline": r.get("roofline"), "e2e": r.get("e2e"),
+                    "gpu_launches": r.get("gpu_launches_per_step", 12) * args.steps,
+                    "clocks": clk.summary(), "mAP": r["mAP"], "rank1": r["rank1"]}
+            if "sharded_equals_single_gpu" in r:
+                line["sharded_equals_single_gpu"] = r["sharded_equals_single_gpu"]
+            if rank == 0 and not args.no_secondary and world == 1:
+                line["cpu_baseline"] = guarded(cpu_retrieval, 128)
         if rank == 0:
             print(json.dumps(line))
     finally:

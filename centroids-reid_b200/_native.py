@@ -106,6 +106,7 @@ SIGNATURES = {
     "ctl_augment_batch_u8": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
     "ctl_adam_multi_step": (C.c_int, [_p, _i32, C.c_int64, _f, _f, _f, _f, _f, C.c_int64, _f, _p]),
     "ctl_sgd_step": (C.c_int, [_p, _p, C.c_int64, _f, _f, _p]),
+    "ctl_grad_check_multi": (C.c_int, [_p, _i32, C.c_int64, _f, _p, _p]),
     "ctl_conv2d_wgrad_workspace_bytes": (C.c_size_t, [_i32, _i32, _i32, _i32, _i32, _i32, _i32]),
     "ctl_conv2d_wgrad_nhwc_f16": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _i32, _i32, _i32, _p, C.c_size_t, _p, _p]),
 }

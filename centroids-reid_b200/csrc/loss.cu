@@ -108,16 +108,33 @@ struct StepMeta {
   int n_valid_rounds;  // rounds with more than one valid class
   int round_valid[64];
   int round_classes[64];  // P'_r
+  int bad_batch;  // != 0: the batch violates the contract (1 label out of [0, C); 2 label not constant in a K-block;
+                  // 3 the same label in two blocks) -> every reported loss is NaN, centers are never indexed out of range
 };
 
 // slot t < B            : image-level anchor, row t
 // slot B + r*2P + c     : round r query anchor of class c  (row cK + r)
 // slot B + r*2P + P + c : round r centroid anchor of class c (row B + rP + c)
-__global__ void step_setup_kernel(const unsigned char* __restrict__ is_real, int P, int K, StepMeta* meta,
-                                  int* __restrict__ n_rc /*[K,P]*/) {
-  __shared__ int s_real, s_rounds;
-  if (threadIdx.x == 0) { s_real = 0; s_rounds = 0; }
+__global__ void step_setup_kernel(const unsigned char* __restrict__ is_real, const int* __restrict__ labels, int C, int P,
+                                  int K, StepMeta* meta, int* __restrict__ n_rc /*[K,P]*/,
+                                  int* __restrict__ labels_safe /*[B]*/) {
+  __shared__ int s_real, s_rounds, s_bad;
+  if (threadIdx.x == 0) { s_real = 0; s_rounds = 0; s_bad = 0; }
   __syncthreads();
+  // Batch contract (datasets/bases.py:346-406): the mining kernels derive the class of a row from its POSITION
+  // (row / K), so the labels must be constant inside each block of K rows, distinct across blocks, and in [0, C).
+  // The reference's label-driven mining would silently compute something else on such a batch; here it is an error.
+  for (int i = threadIdx.x; i < P * K; i += blockDim.x) {
+    const int y = labels[i];
+    int bad = 0;
+    if (y < 0 || y >= C) bad = 1;
+    else if (y != labels[(i / K) * K]) bad = 2;
+    else if (i % K == 0)
+      for (int c = 0; c < i / K; ++c)
+        if (labels[c * K] == y) bad = 3;
+    if (bad) atomicMax(&s_bad, bad);
+    labels_safe[i] = (y < 0 || y >= C) ? 0 : y;
+  }
   int real = 0;
   for (int i = threadIdx.x; i < P * K; i += blockDim.x) real += is_real[i] ? 1 : 0;
   atomicAdd(&s_real, real);
@@ -142,6 +159,7 @@ __global__ void step_setup_kernel(const unsigned char* __restrict__ is_real, int
   if (threadIdx.x == 0) {
     meta->n_real = s_real;
     meta->n_valid_rounds = s_rounds;
+    meta->bad_batch = s_bad;
   }
 }
 
@@ -621,6 +639,9 @@ __global__ void step_scalars_kernel(int B, int C, const StepMeta* __restrict__ m
   out[1] = xent;
   out[3] = center;
   out[0] = out[4] + center + xent + out[2];  // train_ctl_model.py:150-152 order
+  if (meta->bad_batch) {  // contract violation: poison every reported value (the shim turns this into ValueError)
+    for (int i = 0; i < 8; ++i) out[i] = __int_as_float(0x7fc00000 | meta->bad_batch);
+  }
 }
 
 __global__ void __launch_bounds__(256) combine_grad_kernel(const float* __restrict__ F, int B, int D, int P, int K,
@@ -719,6 +740,7 @@ struct StepBuffers {
   MineOut mine;
   float *center_rows, *xent_rows, *xhat, *y, *inv_std, *logits, *dy, *dF_head;
   unsigned char* row_sat;
+  int* labels_safe;
   bool ok;
 };
 
@@ -744,7 +766,8 @@ static StepBuffers carve_step(Workspace& ws, const ctl_loss_config& c) {
   b.dy = ws.take<float>((size_t)c.B * c.D);
   b.dF_head = ws.take<float>((size_t)c.B * c.D);
   b.row_sat = ws.take<unsigned char>(c.B);
-  b.ok = b.row_sat != nullptr && b.meta != nullptr;
+  b.labels_safe = ws.take<int>(c.B);
+  b.ok = b.labels_safe != nullptr && b.meta != nullptr;
   return b;
 }
 
@@ -791,7 +814,8 @@ int ctl_loss_step(const ctl_loss_config* cfg, const float* feats, const int32_t*
     return CTL_ERR_WORKSPACE;
   }
   // ---- metadata, centroid rows, norms --------------------------------------------------
-  step_setup_kernel<<<1, 128, 0, st>>>(is_real, P, K, b.meta, b.n_rc);
+  step_setup_kernel<<<1, 128, 0, st>>>(is_real, labels, C, P, K, b.meta, b.n_rc, b.labels_safe);
+  labels = b.labels_safe;  // range-checked copy: no kernel below can index centers / logits out of bounds
   CTL_LAUNCH_CHECK();
   CTL_CUDA(cudaMemcpyAsync(b.E_all, feats, (size_t)B * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
   build_rows_kernel<<<NT, 256, 0, st>>>(feats, B, D, P, K, is_real, b.n_rc, b.E_all + (size_t)B * D, b.sq);
@@ -887,6 +911,30 @@ int ctl_triplet_step(const float* feats, int32_t n, int32_t d, const int32_t* la
   return 0;
 }
 
+}  // extern "C"
+
+namespace ctl {
+// range check of a label vector: safe[i] = label in [0, C) ? label : 0; *bad != 0 if any label was out of range
+__global__ void sanitize_labels_kernel(const int* __restrict__ labels, int n, int C, int* __restrict__ safe, int* __restrict__ bad) {
+  __shared__ int s_bad;
+  if (threadIdx.x == 0) s_bad = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int y = labels[i];
+    const bool oob = y < 0 || y >= C;
+    if (oob) s_bad = 1;
+    safe[i] = oob ? 0 : y;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *bad = s_bad;
+}
+__global__ void poison_if_kernel(const int* __restrict__ bad, float* __restrict__ out) {
+  if (*bad) *out = __int_as_float(0x7fc00001);  // NaN with payload 1: label out of range
+}
+}  // namespace ctl
+
+extern "C" {
+
 int ctl_center_loss_step(const float* x, int32_t b, int32_t d, const int32_t* labels, const float* centers, int32_t c,
                          float* out_loss, float* d_x, float* d_centers, void* workspace, size_t workspace_bytes,
                          ctl_stream_t stream_) {
@@ -898,11 +946,16 @@ int ctl_center_loss_step(const float* x, int32_t b, int32_t d, const int32_t* la
   Workspace ws(workspace, workspace_bytes);
   float* rows = ws.take<float>(b);
   unsigned char* sat = ws.take<unsigned char>(b);
-  float* zeros = ws.take<float>((size_t)b);
-  if (!zeros) {
+  int* safe = ws.take<int>((size_t)b + 1);  // [b] range-checked labels + 1 flag
+  if (!safe) {
     set_error("workspace too small: need %zu bytes, have %zu", ws.off, workspace_bytes);
     return CTL_ERR_WORKSPACE;
   }
+  // labels index `centers`: an out-of-range label (num_classes mismatch) must not become an out-of-bounds access;
+  // it is reported as a NaN loss (payload 1) that the Python shim turns into ValueError
+  sanitize_labels_kernel<<<1, 256, 0, st>>>(labels, b, c, safe, safe + b);
+  CTL_LAUNCH_CHECK();
+  labels = safe;
   center_rows_kernel<<<b, 256, 0, st>>>(x, d, labels, nullptr, centers, rows, sat);
   CTL_LAUNCH_CHECK();
   sum_rows_kernel<<<1, 32, 0, st>>>(rows, b, 1.f / (float)b, (float)b * (float)(c - 1) * 1e-12f, out_loss);
@@ -911,6 +964,8 @@ int ctl_center_loss_step(const float* x, int32_t b, int32_t d, const int32_t* la
   center_grad_kernel<<<b, 256, 0, st>>>(x, b, d, labels, nullptr, sat, centers, nullptr, b, 1.f, d_centers);
   CTL_LAUNCH_CHECK();
   center_dx_kernel<<<b, 256, 0, st>>>(x, d, labels, centers, sat, b, d_x);
+  CTL_LAUNCH_CHECK();
+  poison_if_kernel<<<1, 1, 0, st>>>(safe + b, out_loss);
   CTL_LAUNCH_CHECK();
   return 0;
 }

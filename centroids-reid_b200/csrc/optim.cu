@@ -62,6 +62,40 @@ __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const f
     p[i] = fmaf(-lr, g[i] * grad_mul, p[i]);
 }
 
+// found-inf check (and optional in-place rescale) over a list of gradient tensors: the role of
+// torch.cuda.amp.GradScaler.unscale_ in the reference's PL native-AMP trainer (utils/misc.py:111)
+struct GradEntry {
+  float* g;
+  long long numel;
+  long long chunk_begin;
+};
+
+__global__ void __launch_bounds__(256) grad_check_multi_kernel(const GradEntry* __restrict__ table, int n_tensors,
+                                                               long long n_chunks, float mul, int* __restrict__ found_inf) {
+  pdl_launch_dependents();
+  pdl_wait();
+  bool bad = false;
+  for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    int lo = 0, hi = n_tensors - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (table[mid].chunk_begin <= chunk) lo = mid; else hi = mid - 1;
+    }
+    const GradEntry e = table[lo];
+    const long long base = (chunk - e.chunk_begin) * OPT_CHUNK;
+    const long long end = min(e.numel, base + OPT_CHUNK);
+    for (long long i = base + threadIdx.x; i < end; i += blockDim.x) {
+      float g = e.g[i];
+      if (mul != 1.f) {
+        g *= mul;
+        e.g[i] = g;
+      }
+      bad |= !isfinite(g);
+    }
+  }
+  if (__syncthreads_or(bad ? 1 : 0) && threadIdx.x == 0) atomicOr(found_inf, 1);
+}
+
 }  // namespace ctl
 
 using namespace ctl;
@@ -79,6 +113,18 @@ int ctl_adam_multi_step(const void* table_device, int32_t n_tensors, int64_t n_c
   CTL_CUDA(launch_k(adam_multi_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream,
                     static_cast<const AdamEntry*>(table_device), (int)n_tensors, (long long)n_chunks, lr, beta1, beta2, eps,
                     weight_decay, (float)bc1, (float)sqrt(bc2), grad_mul));
+  return 0;
+}
+
+int ctl_grad_check_multi(const void* table_device, int32_t n_tensors, int64_t n_chunks, float mul, int32_t* found_inf,
+                         ctl_stream_t stream) {
+  CTL_CHECK_ARG(table_device && found_inf && n_tensors >= 1 && n_chunks >= 1, "bad arguments");
+  static_assert(sizeof(GradEntry) == 24, "ctl_grad_entry layout");
+  int rc = ctl_device_check();
+  if (rc) return rc;
+  const int grid = (int)std::min<long long>(n_chunks, (long long)sm_count() * 8);
+  CTL_CUDA(launch_k(grad_check_multi_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream,
+                    static_cast<const GradEntry*>(table_device), (int)n_tensors, (long long)n_chunks, mul, found_inf));
   return 0;
 }
 

@@ -24,6 +24,22 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
     return t.detach().float().contiguous()
 
 
+_CONTRACT = {1: "a label is outside [0, num_classes)", 2: "labels are not constant inside a block of K rows (the batch is "
+             "not pid-major)", 3: "the same label appears in two blocks of K rows"}
+
+
+def raise_if_poisoned(value: torch.Tensor, what: str):
+    """The loss kernels report a violated input contract as a NaN with a payload (no host synchronisation inside the
+    step); this reads ONE float back and turns it into the exception the reference's asserts would raise."""
+    v = value.detach().reshape(-1)[:1].float()
+    if bool(torch.isnan(v)):
+        code = int(v.view(torch.int32).item()) & 0x3FFFFF
+        if code in _CONTRACT:
+            raise ValueError(f"{what}: {_CONTRACT[code]} (datasets/bases.py:346-406 batch contract; "
+                             "losses/center_loss.py:32 label range)")
+        raise FloatingPointError(f"{what}: the loss is NaN (non-finite features?)")
+
+
 class TripletFn(torch.autograd.Function):
     """losses/triplet_loss.py:139-173 (euclidean, MarginRankingLoss) -> loss, dist_ap, dist_an."""
 
@@ -70,7 +86,7 @@ class CenterLossFn(torch.autograd.Function):
         loss = torch.empty(1, device=dev)
         dx = torch.empty_like(xf)
         dc = torch.empty_like(cf)
-        ws_bytes = 3 * (b * 4 + 256) + 1024
+        ws_bytes = 4 * (b * 4 + 256) + 1024
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         lab = _i32(labels)
         with torch.cuda.device(dev):

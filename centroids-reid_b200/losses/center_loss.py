@@ -4,7 +4,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from ._fn import CenterLossFn
+from ._fn import CenterLossFn, raise_if_poisoned
 
 
 class CenterLoss(nn.Module):
@@ -25,4 +25,9 @@ class CenterLoss(nn.Module):
 
     def forward(self, x, labels):
         assert x.size(0) == labels.size(0), "features.size(0) is not equal to labels.size(0)"
-        return CenterLossFn.apply(x, self.centers, labels)
+        loss = CenterLossFn.apply(x, self.centers, labels)
+        # a label outside [0, num_classes) would index `centers` out of bounds: the kernel clamps it and reports it as a
+        # NaN with a payload; this stand-alone class reads the loss back (one float) and raises.  The fused training step
+        # (modelling/ctl_model.py) does not go through here.
+        raise_if_poisoned(loss, "CenterLoss")
+        return loss

@@ -146,53 +146,68 @@ class TrunkEngine:
         if x.dim() != 4 or x.shape[1] != 3:
             raise ValueError(f"expected [B, 3, H, W], got {tuple(x.shape)}")
         x = x.float().contiguous()
-        n, _, H, W = x.shape
-        L = N.lib()
         self.launches_per_forward = 0
         with torch.cuda.device(self.device):
-            h, w = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
-            hp, wp = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
-            a = torch.empty(n, hp, wp, 64, dtype=torch.float16, device=self.device)
-            if H % 4 == 0 and W % 2 == 0 and W <= 128 and os.environ.get("CTL_STEM_FUSED", "1") == "1":
-                # conv1 + bn1 (+ReLU) + maxpool in one pass; only the pooled tensor is written
-                pad = self._stem_pad.get((n, H, W))
-                if pad is None:
-                    pad = torch.zeros(L.ctl_stem_pad_bytes(n, H, W), dtype=torch.uint8, device=self.device)
-                    self._stem_pad[(n, H, W)] = pad
-                with self._timed("stem_pool", 2.0 * n * h * w * 64 * 147, n * (3.0 * H * W * 4 + hp * wp * 64 * 2)):
-                    N.check(L.ctl_stem_pool_fused(x.data_ptr(), n, H, W, pad.data_ptr(), self.stem_w3.data_ptr(),
-                                                  self.stem_b.data_ptr(), int(self.ibn), a.data_ptr(), N.stream_ptr()))
-                self.launches_per_forward += 1  # pack + conv/pool kernels
-            else:
-                s = torch.empty(n, h, w, 64, dtype=torch.float16, device=self.device)
-                with self._timed("stem_conv", 2.0 * n * h * w * 64 * 147, n * (3.0 * H * W * 4 + h * w * 64 * 2)):
-                    N.check(L.ctl_stem_conv7x7_tc(x.data_ptr(), n, H, W, self.stem_w.data_ptr(), self.stem_b.data_ptr(),
-                                                  int(self.ibn), s.data_ptr(), N.stream_ptr()))
-                with self._timed("maxpool", 0.0, n * 64 * 2.0 * (h * w + hp * wp)):
-                    N.check(L.ctl_maxpool3x3s2_nhwc_f16(s.data_ptr(), n, h, w, 64, a.data_ptr(), N.stream_ptr()))
-            h, w = hp, wp
-            for blk in self.blocks:
-                o1, h1, w1 = self._conv(a, n, h, w, blk["conv1"])
-                if "in" in blk:
-                    half, g, b = blk["in"]
-                    with self._timed("instnorm_relu", 0.0, 2.0 * 2 * n * h1 * w1 * half):
-                        N.check(L.ctl_instnorm_relu_nhwc_f16(o1.data_ptr(), n, h1 * w1, blk["conv1"].cout, half,
-                                                             g.data_ptr(), b.data_ptr(), BN_EPS, N.stream_ptr()))
-                o2, h2, w2 = self._conv(o1, n, h1, w1, blk["conv2"])
-                if "down" in blk and self.fuse_shortcut:
-                    a, h, w = self._dual(o2, a, n, h, w, h2, w2, blk)
-                    continue
-                res = a
-                if "down" in blk:
-                    res, _, _ = self._conv(a, n, h, w, blk["down"])
-                a, h, w = self._conv(o2, n, h2, w2, blk["conv3"], residual=res)
-            c = self.out_channels
-            feat = torch.empty(n, c, dtype=torch.float32, device=self.device)
-            emb = torch.empty(n, c, dtype=torch.float32, device=self.device) if (want_emb and self.head) else None
-            sc, sh = self.head if self.head else (None, None)
-            with self._timed("gap_bn", 0.0, n * c * (2.0 * h * w + 8)):
-                N.check(L.ctl_gap_bn_nhwc_f16(a.data_ptr(), n, h * w, c, N.ptr(sc), N.ptr(sh), feat.data_ptr(),
-                                              N.ptr(emb), N.stream_ptr()))
+            a, n, h, w = self.stem(x)
+            a, h, w = self.bottlenecks(a, n, h, w)
+            return self.tail(a, n, h, w, want_base, want_emb)
+
+    # The three segments of the forward (bench.py captures each as its own CUDA graph to attribute the graph-mode step
+    # time to the convolution kernels without leaving graph / PDL mode).
+    def stem(self, x: torch.Tensor):
+        """conv1 7x7/2 + bn1 (+ReLU for IBN-a) + maxpool 3x3/2 -> NHWC fp16 [n, hp, wp, 64]."""
+        n, _, H, W = x.shape
+        L = N.lib()
+        h, w = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+        hp, wp = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+        a = torch.empty(n, hp, wp, 64, dtype=torch.float16, device=self.device)
+        if H % 4 == 0 and W % 2 == 0 and W <= 128 and os.environ.get("CTL_STEM_FUSED", "1") == "1":
+            # conv1 + bn1 (+ReLU) + maxpool in one pass; only the pooled tensor is written
+            pad = self._stem_pad.get((n, H, W))
+            if pad is None:
+                pad = torch.zeros(L.ctl_stem_pad_bytes(n, H, W), dtype=torch.uint8, device=self.device)
+                self._stem_pad[(n, H, W)] = pad
+            with self._timed("stem_pool", 2.0 * n * h * w * 64 * 147, n * (3.0 * H * W * 4 + hp * wp * 64 * 2)):
+                N.check(L.ctl_stem_pool_fused(x.data_ptr(), n, H, W, pad.data_ptr(), self.stem_w3.data_ptr(),
+                                              self.stem_b.data_ptr(), int(self.ibn), a.data_ptr(), N.stream_ptr()))
+            self.launches_per_forward += 1  # pack + conv/pool kernels
+        else:
+            s = torch.empty(n, h, w, 64, dtype=torch.float16, device=self.device)
+            with self._timed("stem_conv", 2.0 * n * h * w * 64 * 147, n * (3.0 * H * W * 4 + h * w * 64 * 2)):
+                N.check(L.ctl_stem_conv7x7_tc(x.data_ptr(), n, H, W, self.stem_w.data_ptr(), self.stem_b.data_ptr(),
+                                              int(self.ibn), s.data_ptr(), N.stream_ptr()))
+            with self._timed("maxpool", 0.0, n * 64 * 2.0 * (h * w + hp * wp)):
+                N.check(L.ctl_maxpool3x3s2_nhwc_f16(s.data_ptr(), n, h, w, 64, a.data_ptr(), N.stream_ptr()))
+        return a, n, hp, wp
+
+    def bottlenecks(self, a, n, h, w):
+        L = N.lib()
+        for blk in self.blocks:
+            o1, h1, w1 = self._conv(a, n, h, w, blk["conv1"])
+            if "in" in blk:
+                half, g, b = blk["in"]
+                with self._timed("instnorm_relu", 0.0, 2.0 * 2 * n * h1 * w1 * half):
+                    N.check(L.ctl_instnorm_relu_nhwc_f16(o1.data_ptr(), n, h1 * w1, blk["conv1"].cout, half,
+                                                         g.data_ptr(), b.data_ptr(), BN_EPS, N.stream_ptr()))
+            o2, h2, w2 = self._conv(o1, n, h1, w1, blk["conv2"])
+            if "down" in blk and self.fuse_shortcut and h % blk["down"].stride == 0 and w % blk["down"].stride == 0:
+                a, h, w = self._dual(o2, a, n, h, w, h2, w2, blk)
+                continue
+            res = a
+            if "down" in blk:
+                res, _, _ = self._conv(a, n, h, w, blk["down"])
+            a, h, w = self._conv(o2, n, h2, w2, blk["conv3"], residual=res)
+        return a, h, w
+
+    def tail(self, a, n, h, w, want_base=False, want_emb=False):
+        """global average pool (+ the folded eval BatchNorm1d head)."""
+        c = self.out_channels
+        feat = torch.empty(n, c, dtype=torch.float32, device=self.device)
+        emb = torch.empty(n, c, dtype=torch.float32, device=self.device) if (want_emb and self.head) else None
+        sc, sh = self.head if self.head else (None, None)
+        with self._timed("gap_bn", 0.0, n * c * (2.0 * h * w + 8)):
+            N.check(N.lib().ctl_gap_bn_nhwc_f16(a.data_ptr(), n, h * w, c, N.ptr(sc), N.ptr(sh), feat.data_ptr(),
+                                                N.ptr(emb), N.stream_ptr()))
         out = {"global_feat": feat}
         if want_base:
             out["base_out_nhwc"] = a
@@ -201,8 +216,28 @@ class TrunkEngine:
         return out
 
 
+class GraphedCall:
+    """A CUDA graph of any launch sequence `fn()` on static buffers (two eager warm-ups on a side stream, then capture)."""
+
+    def __init__(self, fn, device):
+        cur = torch.cuda.current_stream(device)
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                fn()
+        cur.wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = fn()
+
+    def __call__(self):
+        self.graph.replay()
+        return self.out
+
+
 class GraphedForward:
-    """One CUDA graph of TrunkEngine.forward on a fixed input buffer: 55 launches replayed with a
+    """One CUDA graph of TrunkEngine.forward on a fixed input buffer: 51 launches replayed with a
     single cudaGraphLaunch (no per-launch host work, no tensor-map re-encoding).  `x` is read in
     place at every replay; outputs are static tensors overwritten by each replay."""
 

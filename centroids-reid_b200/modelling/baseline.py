@@ -26,16 +26,23 @@ class _TrunkTrainFn(torch.autograd.Function):
     (the input crops get no gradient, like the reference's data tensors)."""
 
     @staticmethod
-    def forward(ctx, x, trainer, names, buffers, *tensors):
+    def forward(ctx, x, trainer, scaler, names, buffers, *tensors):
         params = dict(zip(names, tensors))
         params.update(buffers)
-        ctx.trainer, ctx.names = trainer, names
+        ctx.trainer, ctx.names, ctx.scaler = trainer, names, scaler
         return trainer.forward(x, params)
 
     @staticmethod
     def backward(ctx, dfeat):
-        grads = ctx.trainer.backward(dfeat)
-        return (None, None, None, None) + tuple(grads.get(n) for n in ctx.names)
+        # dynamic loss scaling (the reference's PL native-AMP GradScaler, utils/misc.py:111): the fp16 backward runs on
+        # (scale / trainer.grad_scale) * dfeat on top of the trainer's fixed internal scale and is un-scaled in fp32;
+        # an overflow shows up as inf / NaN gradients, which CTLModel.optimizer_step_manual detects and skips
+        ratio = (ctx.scaler.scale / ctx.trainer.grad_scale) if (ctx.scaler is not None and ctx.scaler.enabled) else 1.0
+        grads = ctx.trainer.backward(dfeat * ratio if ratio != 1.0 else dfeat)
+        out = [grads.get(n) for n in ctx.names]
+        if ratio != 1.0:
+            torch._foreach_mul_([g for g in out if g is not None], 1.0 / ratio)
+        return (None, None, None, None, None) + tuple(out)
 
 
 class Baseline(nn.Module):
@@ -57,13 +64,27 @@ class Baseline(nn.Module):
         self._engine = None
         self._engine_key = None
         self._trainer = None
+        self.loss_scaler = None  # solver.build.DynamicLossScaler, created with the training engine
 
     def invalidate(self):
         self._engine = None
 
+    def _param_version(self, bn_head=None):
+        """Changes whenever any trunk parameter / buffer (or the BatchNorm1d head) is modified in place or replaced:
+        optimizer steps, load_state_dict, load_param, EMA updates, running statistics."""
+        ts = list(self.base.parameters()) + list(self.base.buffers())
+        if bn_head is not None:
+            ts += [bn_head.weight, bn_head.bias, bn_head.running_mean, bn_head.running_var]
+        return tuple((t.data_ptr(), t._version) for t in ts)
+
     def engine(self, bn_head=None) -> TrunkEngine:
         dev = next(self.base.parameters()).device
-        key = (str(dev), id(bn_head))
+        # the packed operands (folded BN, fp16 weights) are a cache of the parameters: keyed on their version counters,
+        # so a stale pack can never be used after load_state_dict / an external optimizer / updated running statistics
+        key = (str(dev), self._param_version(bn_head))
+        if self._engine is not None and self._engine_key is not None and self._engine_key[0] == key[0] \
+                and self._engine_key[1][: len(key[1])] == key[1] and bn_head is None:
+            return self._engine  # a pack built WITH the head also serves calls without it (same trunk versions)
         if self._engine is None or self._engine_key != key:
             sd = {k: v for k, v in self.base.state_dict().items()}
             head = None
@@ -80,13 +101,18 @@ class Baseline(nn.Module):
         if self.training:
             dev = next(self.base.parameters()).device
             if self._trainer is None or self._trainer.device != dev:
+                from ..solver.build import DynamicLossScaler
+
                 self._trainer = TrunkTrainer(dev, last_stride=self.base.last_stride, layers=self.base.layers_cfg,
                                              graphs=os.environ.get("CTL_TRAIN_GRAPHS", "1") == "1", ibn=self.base.ibn)
+                self.loss_scaler = DynamicLossScaler(dev, enabled=os.environ.get("CTL_DYNAMIC_LOSS_SCALE", "1") == "1")
             names = [k for k, _ in self.base.named_parameters()]
             tensors = [v for _, v in self.base.named_parameters()]
             buffers = {k: v for k, v in self.base.named_buffers() if "running" in k}
-            feat = _TrunkTrainFn.apply(x, self._trainer, names, buffers, *tensors)
-            self.invalidate()  # running statistics changed: the eval engine must refold them
+            feat = _TrunkTrainFn.apply(x, self._trainer, self.loss_scaler, names, buffers, *tensors)
+            from ..solver.build import _bump_version
+
+            _bump_version(buffers.values())  # running statistics were updated in place by the kernels
             for k, v in self.base.named_buffers():
                 if k.endswith("num_batches_tracked"):
                     v += 1

@@ -2,11 +2,19 @@
 (CTLModel.training_step): same attribute names (backbone, bn, fc_query, center_loss,
 contrastive_loss, xent), same hook signatures, the arithmetic on the B200 kernels.
 
-pytorch_lightning is not a dependency of this package: the class derives from
-pl.LightningModule when PL is importable and from nn.Module otherwise, so the reference's
-Trainer can drive it unchanged where PL exists.
+pytorch_lightning is not a dependency of this package (and is absent from the build image): the class
+derives from pl.LightningModule when PL is importable and from nn.Module otherwise.  Under PL the
+hyper-parameters go through PL's own `hparams` setter + `save_hyperparameters` (modelling/bases.py:63-64),
+and `training_step` performs the reference's complete manual-optimisation sequence
+(train_ctl_model.py:38-179: warm-up LR, zero_grad, forward, losses, manual_backward, opt.step, center
+gradient rescale, opt_center.step) whenever optimizers are attached -- by a Trainer (`self.optimizers()`)
+or explicitly (`attach_optimizers`).  Without attached optimizers it returns the loss only and the caller
+drives `backward()` / `optimizer_step_manual()` itself (bench.py, tests).  The PL path is exercised here
+with a stub LightningModule (tests/test_host_logic.py); it has never run under a real pytorch_lightning.
 """
 from __future__ import annotations
+
+import os
 
 import numpy as np
 import torch
@@ -15,7 +23,7 @@ from torch import nn
 from .. import _native as N
 from .. import reduce as _reduce
 from .. import retrieval as _R
-from ..losses._fn import CTLStepFn
+from ..losses._fn import CTLStepFn, raise_if_poisoned
 from ..losses.center_loss import CenterLoss
 from ..losses.triplet_loss import CrossEntropyLabelSmooth, TripletLoss
 from .baseline import Baseline, embed
@@ -40,12 +48,28 @@ def ctl_losses(module, features, class_labels, is_real):
     B, D = features.shape
     if B % K != 0:
         raise ValueError(f"batch contract: B={B} must be P*K with K={K} (datasets/bases.py:346-406)")
+    if not module.bn.training:
+        raise NotImplementedError("the fused loss step normalises with BATCH statistics (nn.BatchNorm1d in train mode, as in "
+                                  "the reference's training_step); call module.train() / module.bn.train() first")
     cfg = N.LossConfig(B, D, B // K, K, module.fc_query.weight.shape[0], float(hp.SOLVER.MARGIN),
                        float(hp.SOLVER.CENTER_LOSS_WEIGHT), float(hp.SOLVER.QUERY_XENT_WEIGHT),
                        float(hp.SOLVER.QUERY_CONTRASTIVE_WEIGHT), float(hp.SOLVER.CENTROID_CONTRASTIVE_WEIGHT),
                        float(module.bn.eps), float(module.bn.momentum), 0.1)
-    return CTLStepFn.apply(features, module.center_loss.centers, module.bn.weight, module.fc_query.weight,
-                           module.bn.bias, module.bn.running_mean, module.bn.running_var, class_labels, is_real, cfg)
+    total, parts = CTLStepFn.apply(features, module.center_loss.centers, module.bn.weight, module.fc_query.weight,
+                                   module.bn.bias, module.bn.running_mean, module.bn.running_var, class_labels, is_real, cfg)
+    # The kernels derive a row's class from its position (pid-major blocks of K, datasets/bases.py:346-406) and index the
+    # centers by label: a violated contract comes back as a NaN with a payload.  The sampler's layout does not change
+    # between steps, so the (synchronising) check runs on the FIRST step of a module only; CTL_VALIDATE_BATCH=1 checks
+    # every step.
+    if module.bn.num_batches_tracked is not None:
+        module.bn.num_batches_tracked += 1  # nn.BatchNorm1d.forward bookkeeping (the running statistics moved)
+    from ..solver.build import _bump_version
+
+    _bump_version([module.bn.running_mean, module.bn.running_var])  # written by the kernel through raw pointers
+    if not module.__dict__.get("_ctl_batch_checked", False) or os.environ.get("CTL_VALIDATE_BATCH") == "1":
+        raise_if_poisoned(parts[0], "CTL training step")
+        module.__dict__["_ctl_batch_checked"] = True
+    return total, parts
 
 
 class CTLModel(_Base):
@@ -55,9 +79,20 @@ class CTLModel(_Base):
         super().__init__()
         hp = dict(cfg) if cfg is not None else {}
         hp.update(kwargs)
-        self.hparams_ctl = _AttrDict(hp)
-        if not hasattr(self, "hparams") or not isinstance(getattr(self, "hparams", None), dict) or _Base is nn.Module:
-            self.__dict__["hparams"] = self.hparams_ctl
+        if _Base is nn.Module:
+            self.__dict__["hparams"] = _AttrDict(hp)
+        else:
+            # modelling/bases.py:63-64: PL 1.1.4's `hparams` is a property with a setter; assign through it and
+            # register the values for checkpointing exactly like the reference
+            try:
+                from pytorch_lightning.utilities import AttributeDict as _PLAttrDict
+            except Exception:  # noqa: BLE001
+                _PLAttrDict = _AttrDict
+            self.hparams = _PLAttrDict(hp)
+            self.save_hyperparameters(self.hparams)
+        if test_dataloader is not None:
+            self.test_dataloader = test_dataloader
+        self._ctl_optimizers = None
         self.backbone = Baseline(self.hparams)
         self.contrastive_loss = TripletLoss(self.hparams.SOLVER.MARGIN, self.hparams.SOLVER.DISTANCE_FUNC)
         d_model = self.hparams.MODEL.BACKBONE_EMB_SIZE
@@ -79,10 +114,43 @@ class CTLModel(_Base):
         total, parts = ctl_losses(self, features, class_labels, is_real)
         return {"loss": total, "parts": parts}
 
+    def attach_optimizers(self, opt, opt_center):
+        """Makes `training_step` a complete iteration outside a PL Trainer (the optimizers `configure_optimizers` built)."""
+        self._ctl_optimizers = (opt, opt_center)
+
+    def _step_optimizers(self):
+        if self._ctl_optimizers is not None:
+            return self._ctl_optimizers
+        if _Base is not nn.Module and getattr(self, "trainer", None) is not None:
+            return self.optimizers(use_pl_optimizer=True)  # train_ctl_model.py:39
+        return None
+
     def training_step(self, batch, batch_idx, optimizer_idx=None):
+        """train_ctl_model.py:38-179.  With optimizers attached (PL Trainer or `attach_optimizers`): the reference's whole
+        manual-optimisation iteration, returning {"loss", "other": {step_dist_ap, step_dist_an, l2_mean_centroid}}.
+        Without: forward + losses only, returning {"loss" (differentiable), "parts"}."""
         x, class_labels, camid, is_real = batch
-        _, features = self.backbone(x)  # train mode: B200 training engine (differentiable w.r.t. the trunk parameters)
-        return self.training_step_from_features(features, class_labels, is_real)
+        opts = self._step_optimizers()
+        if opts is None:
+            _, features = self.backbone(x)  # train mode: B200 training engine (differentiable w.r.t. the trunk parameters)
+            return self.training_step_from_features(features, class_labels, is_real)
+        opt, opt_center = opts
+        epoch = int(getattr(getattr(self, "trainer", None), "current_epoch", 0) or 0)
+        opt_center.zero_grad()
+        opt.zero_grad()
+        _, features = self.backbone(x)
+        out = self.training_step_from_features(features, class_labels, is_real)
+        total = out["loss"]
+        if _Base is not nn.Module and getattr(self, "trainer", None) is not None:
+            self.manual_backward(total, optimizer=opt)
+        else:
+            total.backward()
+        self.optimizer_step_manual(opt, opt_center, epoch=epoch)
+        parts = out["parts"].tolist()  # ONE read-back for everything the reference logs with float(...)
+        for name, val in zip(self.losses_names, (parts[1], parts[2], parts[3], parts[4])):
+            self.losses_dict[name].append(val)
+        return {"loss": total.detach(), "other": {"step_dist_ap": parts[5], "step_dist_an": parts[6],
+                                                  "l2_mean_centroid": parts[7]}}
 
     def configure_optimizers(self):
         """modelling/bases.py:97-100 with the fused optimizers of ctl_b200.solver.build."""
@@ -99,10 +167,20 @@ class CTLModel(_Base):
         from ..solver.build import apply_warmup_lr
 
         apply_warmup_lr(opt, epoch, self.hparams)
-        opt.step()
-        for param in self.center_loss.parameters():
-            param.grad.data *= 1.0 / self.hparams.SOLVER.CENTER_LOSS_WEIGHT
-        opt_center.step()
+        scaler = self.backbone.loss_scaler
+        found_inf = False
+        if scaler is not None and scaler.enabled:
+            # GradScaler.step semantics: inspect every gradient the optimizers are about to consume (after any gradient
+            # all-reduce, so all ranks agree) and skip the step on inf / NaN instead of poisoning Adam's moments
+            scaler.check([p.grad for p in self.parameters() if p.grad is not None])
+            found_inf = scaler.found_inf()
+        if not found_inf:
+            opt.step()
+            for param in self.center_loss.parameters():
+                param.grad.data *= 1.0 / self.hparams.SOLVER.CENTER_LOSS_WEIGHT
+            opt_center.step()
+        if scaler is not None and scaler.enabled:
+            scaler.update(found_inf)
         self.backbone.invalidate()
 
     # -- evaluation -------------------------------------------------------------------------

@@ -18,6 +18,17 @@ from .. import _native as N
 _CHUNK = 8192  # CTL_OPT_CHUNK
 
 
+def _bump_version(tensors):
+    """The kernels write parameters through raw pointers; tell torch (autograd's saved-tensor checks, and the eval
+    engine's version-keyed weight cache in modelling/baseline.py) that they changed."""
+    inc = getattr(torch.autograd.graph, "increment_version", None)
+    for t in tensors:
+        if inc is not None:
+            inc(t)
+        else:  # pragma: no cover - very old torch
+            t.add_(0)
+
+
 class FusedAdam(torch.optim.Optimizer):
     """torch.optim.Adam(params, lr, betas, eps, weight_decay) semantics (L2 weight decay, no amsgrad)."""
 
@@ -64,6 +75,7 @@ class FusedAdam(torch.optim.Optimizer):
                                               float(group["eps"]), float(group["weight_decay"]), step, float(self.grad_mul),
                                               N.stream_ptr()))
                 keep.append(table)
+            _bump_version([p for p in group["params"] if p.grad is not None])
         return loss
 
 
@@ -89,7 +101,75 @@ class CenterSGD(torch.optim.Optimizer):
                 g = p.grad.contiguous()
                 N.check(N.lib().ctl_sgd_step(p.data_ptr(), g.data_ptr(), p.numel(), float(group["lr"]), float(self.grad_mul),
                                              N.stream_ptr()))
+                _bump_version([p])
         return loss
+
+
+class DynamicLossScaler:
+    """torch.cuda.amp.GradScaler semantics for the fp16 trunk backward (the reference trains under PL native AMP,
+    utils/misc.py:111): the trunk's data / weight gradients are computed on `scale * dLoss/dfeat`, un-scaled in fp32, and
+    a step whose gradients contain inf / NaN is SKIPPED and halves the scale; `growth_interval` clean steps double it.
+    Defaults are GradScaler's (init 2^16, x2 / x0.5, interval 2000).  Like GradScaler.step, `found_inf()` reads one
+    flag back from the device (one 4-byte synchronisation per optimizer step)."""
+
+    def __init__(self, device, init_scale=65536.0, growth_factor=2.0, backoff_factor=0.5, growth_interval=2000, enabled=True):
+        self.device = torch.device(device)
+        self.scale = float(init_scale)
+        self.growth_factor, self.backoff_factor, self.growth_interval = growth_factor, backoff_factor, growth_interval
+        self.enabled = enabled
+        self._growth_tracker = 0
+        self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._tables = {}
+        self.skipped_steps = 0
+
+    def _table(self, grads):
+        key = tuple((g.data_ptr(), g.numel()) for g in grads)
+        t = self._tables.get(key)
+        if t is None:
+            rows, chunks = [], 0
+            for g in grads:
+                rows.append([g.data_ptr(), g.numel(), chunks])
+                chunks += (g.numel() + _CHUNK - 1) // _CHUNK
+            t = (torch.from_numpy(np.asarray(rows, dtype=np.int64)).to(self.device), len(rows), chunks)
+            if len(self._tables) > 8:
+                self._tables.clear()
+            self._tables[key] = t
+        return t
+
+    def check(self, grads, mul: float = 1.0):
+        """OR-accumulates the overflow flag over `grads` (fp32, contiguous); mul != 1 rescales them in place."""
+        grads = [g for g in grads if g is not None]
+        if not grads:
+            return
+        for g in grads:
+            if g.dtype != torch.float32 or not g.is_contiguous():
+                raise TypeError("DynamicLossScaler.check expects contiguous fp32 gradients")
+        table, n, chunks = self._table(grads)
+        N.check(N.lib().ctl_grad_check_multi(table.data_ptr(), n, chunks, float(mul), self._flag.data_ptr(), N.stream_ptr()))
+
+    def found_inf(self) -> bool:
+        return bool(self._flag.item())
+
+    def update(self, found_inf: bool):
+        """GradScaler.update(): back off after an overflow, grow after `growth_interval` clean steps; clears the flag."""
+        if found_inf:
+            self.scale *= self.backoff_factor
+            self._growth_tracker = 0
+            self.skipped_steps += 1
+            self._flag.zero_()
+        else:
+            self._growth_tracker += 1
+            if self._growth_tracker >= self.growth_interval:
+                self.scale *= self.growth_factor
+                self._growth_tracker = 0
+
+    def state_dict(self):
+        return {"scale": self.scale, "growth_factor": self.growth_factor, "backoff_factor": self.backoff_factor,
+                "growth_interval": self.growth_interval, "_growth_tracker": self._growth_tracker}
+
+    def load_state_dict(self, sd):
+        self.scale = float(sd["scale"])
+        self._growth_tracker = int(sd.get("_growth_tracker", 0))
 
 
 def build_optimizer(named_parameters, hparams, fold_center_rescale: bool = False):

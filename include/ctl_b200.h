@@ -327,6 +327,12 @@ int ctl_adam_multi_step(const void* table_device, int32_t n_tensors, int64_t n_c
 /* torch.optim.SGD without momentum: param -= lr * grad * grad_mul (the center parameters; grad_mul =
  * 1 / SOLVER.CENTER_LOSS_WEIGHT, train_ctl_model.py:157-158). */
 int ctl_sgd_step(float* param, const float* grad, int64_t numel, float lr, float grad_mul, ctl_stream_t stream);
+/* Gradient overflow check of dynamic loss scaling (torch.cuda.amp.GradScaler.unscale_ in the reference's PL AMP trainer,
+ * utils/misc.py:111): table = device array of {float* grad; int64 numel; int64 chunk_begin} (chunks of 8192 elements, like
+ * ctl_adam_multi_step); every gradient is multiplied in place by `mul` (skipped when mul == 1) and *found_inf (device int,
+ * OR-accumulated, cleared by the caller) becomes 1 if any element is inf or NaN. */
+int ctl_grad_check_multi(const void* table_device, int32_t n_tensors, int64_t n_chunks, float mul, int32_t* found_inf,
+                         ctl_stream_t stream);
 
 /* ---- training-time augmentation (datasets/transforms/build.py:15-27, random_erasing.py:30-55) ---- */
 

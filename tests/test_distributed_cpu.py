@@ -122,6 +122,18 @@ def _grad_worker(rank, world, port, out_q):
     for lst, t in zip(gathered, local):
         dist.all_gather(lst, t)
     ok = all(torch.allclose(p_.grad, torch.stack(lst).mean(0), rtol=0, atol=1e-7) for p_, lst in zip(params, gathered))
+    # GradientReducer: one flat buffer, no copy-back; the second step starts from the re-pointed views of the first
+    red = parallel.GradientReducer(params)
+    for step in range(2):
+        for p_ in params:
+            p_.grad = torch.randn(p_.shape, generator=g)
+        local2 = [p_.grad.clone() for p_ in params]
+        red.allreduce_mean()
+        for p_, t in zip(params, local2):
+            lst = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(lst, t)
+            ok = ok and torch.allclose(p_.grad, torch.stack(lst).mean(0), rtol=0, atol=1e-7)
+        ok = ok and all(p_.grad.data_ptr() == v.data_ptr() for p_, v in zip(params, red.views))
     pids = np.arange(37)
     mine = parallel.shard_pids(pids, world, rank)
     sizes = [torch.tensor([len(mine)]) for _ in range(world)]

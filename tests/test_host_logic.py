@@ -84,3 +84,81 @@ def test_encode_identities_masks():
     cams = {0: 0, 1: 1, 3: 2}
     assert gm.tolist() == [(1 << cams[0]) | (1 << cams[3]), 1 << cams[1], 1 << cams[3], 1 << cams[0]]
     assert qc.tolist() == [cams[0], cams[3]]
+
+
+def test_ctl_model_under_a_lightning_like_base(monkeypatch):
+    """with pytorch_lightning importable, `hparams` is a PL property (PL 1.1.4: getter + setter backed by
+    `_hparams`), so assigning through `__dict__` never populated it.  A stub LightningModule with that property checks
+    that CTLModel sets the hyper-parameters through the setter, saves them, builds its modules, and exposes the
+    reference's manual-optimisation hooks."""
+    import importlib
+    import sys
+    import types
+
+    import torch.nn as nn
+
+    class AttributeDict(dict):
+        __getattr__ = dict.__getitem__
+        __setattr__ = dict.__setitem__
+
+    class LightningModule(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self._hparams = AttributeDict()
+            self.trainer = None
+            self.saved = None
+
+        @property
+        def hparams(self):
+            return self._hparams
+
+        @hparams.setter
+        def hparams(self, hp):
+            self._hparams = hp
+
+        def save_hyperparameters(self, *args, **kw):
+            self.saved = args[0] if args else None
+
+        def optimizers(self, use_pl_optimizer=True):
+            return self.trainer.optimizers
+
+        def manual_backward(self, loss, optimizer=None):
+            loss.backward()
+
+    pl = types.ModuleType("pytorch_lightning")
+    pl.LightningModule = LightningModule
+    util = types.ModuleType("pytorch_lightning.utilities")
+    util.AttributeDict = AttributeDict
+    pl.utilities = util
+    monkeypatch.setitem(sys.modules, "pytorch_lightning", pl)
+    monkeypatch.setitem(sys.modules, "pytorch_lightning.utilities", util)
+    import ctl_b200.modelling.ctl_model as M
+
+    try:
+        M = importlib.reload(M)
+        assert M._Base is LightningModule
+
+        class Cfg(dict):
+            __getattr__ = dict.__getitem__
+
+        cfg = Cfg(MODEL=Cfg(NAME="resnet50", LAST_STRIDE=1, PRETRAINED=False, PRETRAIN_PATH="", BACKBONE_EMB_SIZE=2048,
+                            USE_CENTROIDS=False, KEEP_CAMID_CENTROIDS=True, RESUME_TRAINING=False),
+                  SOLVER=Cfg(MARGIN=0.5, DISTANCE_FUNC="euclidean", CENTER_LOSS_WEIGHT=5e-4, QUERY_XENT_WEIGHT=1.0,
+                             QUERY_CONTRASTIVE_WEIGHT=1.0, CENTROID_CONTRASTIVE_WEIGHT=1.0),
+                  DATALOADER=Cfg(NUM_INSTANCE=4), TEST=Cfg(FEAT_NORM=True, ONLY_TEST=False, VISUALIZE="no"),
+                  USE_MIXED_PRECISION=True)
+        model = M.CTLModel(cfg, num_classes=17, num_query=3)
+        assert isinstance(model.hparams, AttributeDict) and model.hparams.MODEL.NAME == "resnet50"
+        assert model.hparams.num_classes == 17 and model.saved is model.hparams
+        assert model.fc_query.weight.shape == (17, 2048) and hasattr(model.backbone, "base")
+        assert model._step_optimizers() is None  # no trainer attached: training_step returns the loss only
+
+        class _T:
+            current_epoch = 3
+            optimizers = ("opt", "opt_center")
+
+        model.trainer = _T()
+        assert model._step_optimizers() == ("opt", "opt_center")  # train_ctl_model.py:39 under a Trainer
+    finally:
+        monkeypatch.undo()
+        importlib.reload(M)

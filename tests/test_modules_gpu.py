@@ -89,3 +89,111 @@ def test_validation_epoch_end_centroid_metric():
         assert np.array_equal(cmc, g[f"{tag}_cmc"])
         np.testing.assert_allclose(mAP, float(g[f"{tag}_mAP"]), rtol=1e-9)
         np.testing.assert_allclose(topk, g[f"{tag}_topk"], rtol=1e-9)
+
+
+def _tiny_model(seed=0):
+    from ctl_b200.modelling.ctl_model import CTLModel
+
+    torch.manual_seed(seed)
+    cfg = _cfg()
+    cfg["SOLVER"].update(dict(OPTIMIZER_NAME="Adam", BASE_LR=3.5e-4, WEIGHT_DECAY=5e-4, CENTER_LR=0.5,
+                              LR_SCHEDULER_NAME="multistep_lr", LR_STEPS=(40, 70), GAMMA=0.1, USE_WARMUP_LR=True,
+                              WARMUP_EPOCHS=10))
+    model = CTLModel(cfg, num_classes=16, num_query=4).cuda().train()
+    model.backbone.base.load_state_dict(O.make_trunk_state(seed=11))
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(16, 3, 64, 32, generator=g).cuda()
+    labels = (torch.arange(4).repeat_interleave(4) + 1).cuda()
+    batch = (x, labels, torch.zeros(16, dtype=torch.long).cuda(), torch.ones(16, dtype=torch.bool).cuda())
+    return model, batch
+
+
+def test_batch_contract_violations_raise():
+    """the mining kernels take a row's class from its position; a batch that is not pid-major, repeats a pid in
+    two blocks, or carries a label outside [0, C) must be an error, not a silently different loss or an out-of-bounds
+    access of the centers."""
+    from ctl_b200.losses.center_loss import CenterLoss
+
+    model, (x, labels, cam, real) = _tiny_model()
+    feats = torch.randn(16, 2048, device="cuda")
+    for bad, what in ((labels.roll(1), "not constant"), (torch.tensor([1] * 8 + [2] * 4 + [1] * 4).cuda(), "two blocks"),
+                      (labels + 100, "outside")):
+        model.__dict__.pop("_ctl_batch_checked", None)
+        with pytest.raises(ValueError, match=what):
+            model.training_step_from_features(feats, bad, real)
+    model.__dict__.pop("_ctl_batch_checked", None)
+    out = model.training_step_from_features(feats, labels, real)
+    assert torch.isfinite(out["loss"])
+    cl = CenterLoss(num_classes=16, feat_dim=2048)
+    assert torch.isfinite(cl(feats, labels))
+    with pytest.raises(ValueError, match="outside"):
+        cl(feats, labels + 16)
+
+
+def test_training_step_with_attached_optimizers_is_the_reference_iteration():
+    """training_step with optimizers attached == zero_grad, forward, losses, backward, warm-up LR, Adam step, center
+    rescale + SGD step (train_ctl_model.py:38-179), bit-identical to driving the same sequence by hand."""
+    a, batch = _tiny_model(seed=5)
+    b, _ = _tiny_model(seed=5)
+    (oa, oca), _ = a.configure_optimizers()
+    (ob, ocb), _ = b.configure_optimizers()
+    a.attach_optimizers(oa, oca)
+    for _ in range(2):
+        ra = a.training_step(batch, 0)
+        for p_ in b.parameters():
+            p_.grad = None
+        rb = b.training_step(batch, 0)
+        rb["loss"].backward()
+        b.optimizer_step_manual(ob, ocb, epoch=0)
+        assert set(ra["other"]) == {"step_dist_ap", "step_dist_an", "l2_mean_centroid"}
+        assert float(ra["loss"]) == float(rb["loss"])
+    for (ka, va), (kb, vb) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb), ka
+    assert len(a.losses_dict["centroid_triplet"]) == 2 and int(a.bn.num_batches_tracked) == 2
+
+
+def test_dynamic_loss_scaling_skips_an_overflowing_step():
+    """GradScaler semantics (the reference trains under PL native AMP, utils/misc.py:111): inf / NaN gradients skip the
+    optimizer step (parameters and Adam moments untouched) and halve the scale; clean steps proceed."""
+    model, batch = _tiny_model(seed=7)
+    (opt, opt_c), _ = model.configure_optimizers()
+    out = model.training_step(batch, 0)
+    out["loss"].backward()
+    scaler = model.backbone.loss_scaler
+    assert scaler is not None and scaler.scale == 65536.0
+    w = model.backbone.base.layer3[1].conv2.weight
+    w0, c0 = w.detach().clone(), model.center_loss.centers.detach().clone()
+    w.grad[0, 0, 0, 0] = float("inf")
+    model.optimizer_step_manual(opt, opt_c, epoch=0)
+    assert torch.equal(w.detach(), w0) and torch.equal(model.center_loss.centers.detach(), c0)
+    assert scaler.scale == 32768.0 and scaler.skipped_steps == 1 and len(opt.state) == 0
+    for p_ in model.parameters():
+        p_.grad = None
+    out = model.training_step(batch, 0)
+    out["loss"].backward()
+    model.optimizer_step_manual(opt, opt_c, epoch=0)
+    assert not torch.equal(w.detach(), w0) and scaler.skipped_steps == 1
+    assert all(torch.isfinite(p_).all() for p_ in model.parameters())
+
+
+def test_eval_engine_never_serves_stale_weights():
+    """the packed eval operands are a cache of the parameters; load_state_dict, an in-place parameter edit and
+    an optimizer step must all be visible to the next eval forward without a manual invalidate()."""
+    from ctl_b200.modelling.baseline import Baseline
+
+    model = Baseline(_cfg()).cuda().eval()
+    model.base.load_state_dict(O.make_trunk_state(seed=2))
+    x = torch.randn(2, 3, 64, 32, generator=torch.Generator().manual_seed(4)).cuda()
+    with torch.no_grad():
+        f0 = model(x)[1].clone()
+        assert torch.equal(model(x)[1], f0)
+        eng = model._engine
+        assert model.engine() is eng  # unchanged parameters: the pack is reused
+        model.base.load_state_dict(O.make_trunk_state(seed=3))
+        f1 = model(x)[1].clone()
+        assert not torch.equal(f0, f1)
+        model.base.layer4[2].bn3.weight.mul_(1.5)
+        f2 = model(x)[1].clone()
+        assert not torch.equal(f1, f2)
+        model.base.load_state_dict(O.make_trunk_state(seed=2))
+        assert torch.equal(model(x)[1], f0)

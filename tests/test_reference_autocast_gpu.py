@@ -95,7 +95,13 @@ def test_training_step_at_bench_shape_vs_reference_cuda_autocast(tag, ibn, hw, P
         gk = grads[k].double()
         rg = rg.double()
         assert torch.isfinite(gk).all(), k
-        if float(rg.abs().max()) < 1e-5 * gmax:  # exactly-cancelled gradients (a bias in front of a batch-stat BN)
+        if float(rg.abs().max()) < 1e-5 * gmax:
+            continue
+        if k == "bn1.bias" and not ibn:
+            # resnet.py:122-126 has no ReLU after the stem: a per-channel shift of bn1's output passes the max-pool and the
+            # 1x1 convolutions unchanged and is removed by the next batch-statistics BatchNorms -> the true gradient is
+            # EXACTLY zero and both implementations return round-off; compare its size with bn1.weight's gradient instead
+            assert float(gk.norm()) <= 2e-2 * float(grads["bn1.weight"].double().norm()) + 1e-12, "bn1.bias gradient is not ~0"
             continue
         cos = float((gk * rg).sum() / (gk.norm() * rg.norm()))
         nr = abs(float(gk.norm() / rg.norm()) - 1)
