@@ -54,6 +54,12 @@ class PassDesc(C.Structure):
                 ("g_cammask", _p), ("pos_keys", _p), ("pos_count", _p), ("max_pos", _i32), ("thr_keys", _p),
                 ("thr_count", _p), ("buckets", _p), ("overflow", _p), ("g_index_offset", _i64)]
 
+class NamedTensor(C.Structure):
+    """struct ctl_named_tensor (include/ctl_b200.h)."""
+
+    _fields_ = [("name", C.c_char_p), ("data", _p), ("numel", _i64)]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check it against the header
 SIGNATURES = {
     "ctl_last_error": (C.c_char_p, []),
@@ -85,6 +91,11 @@ SIGNATURES = {
     "ctl_xent_smooth_step": (C.c_int, [_p, _i32, _i32, _p, _f, _p, _p, _p, _sz, _p]),
     "ctl_conv2d_nhwc_f16": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
     "ctl_conv1x1_dual_nhwc_f16": (C.c_int, [_p, _i32, _p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _p]),
+    "ctl_trunk_create": (C.c_int, [C.POINTER(_p), _i32, _i32]),
+    "ctl_trunk_destroy": (None, [_p]),
+    "ctl_weights_pack": (C.c_int, [_p, C.POINTER(NamedTensor), _i32, _p]),
+    "ctl_embed_workspace_bytes": (_sz, [_p, _i32, _i32, _i32]),
+    "ctl_embed_forward": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _sz, _p]),
     "ctl_stem_conv7x7": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _i32, _p, _p]),
     "ctl_stem_conv7x7_tc": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _i32, _p, _p]),
     "ctl_stem_pad_bytes": (C.c_size_t, [_i32, _i32, _i32]),
@@ -104,9 +115,10 @@ SIGNATURES = {
     "ctl_upsample2_zero_nhwc_f16": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p, _p]),
     "ctl_stem_im2col_f16": (C.c_int, [_p, _i32, _i32, _i32, _p, _p]),
     "ctl_augment_batch_u8": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
-    "ctl_adam_multi_step": (C.c_int, [_p, _i32, C.c_int64, _f, _f, _f, _f, _f, C.c_int64, _f, _p]),
-    "ctl_sgd_step": (C.c_int, [_p, _p, C.c_int64, _f, _f, _p]),
-    "ctl_grad_check_multi": (C.c_int, [_p, _i32, C.c_int64, _f, _p, _p]),
+    "ctl_adam_multi_step": (C.c_int, [_p, _i32, C.c_int64, _f, _f, _f, _f, _f, C.c_int64, _f, _p, _p]),
+    "ctl_sgd_step": (C.c_int, [_p, _p, C.c_int64, _f, _f, _p, _p]),
+    "ctl_loss_scale_update": (C.c_int, [_p, _p, _p, _p, _f, _f, _f, _i32, _p]),
+    "ctl_grad_check_multi": (C.c_int, [_p, _i32, C.c_int64, _f, _p, _p, _p]),
     "ctl_conv2d_wgrad_workspace_bytes": (C.c_size_t, [_i32, _i32, _i32, _i32, _i32, _i32, _i32]),
     "ctl_conv2d_wgrad_nhwc_f16": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _i32, _i32, _i32, _p, C.c_size_t, _p, _p]),
 }

@@ -216,6 +216,61 @@ class TrunkEngine:
         return out
 
 
+class NativeTrunk:
+    """The same embedding path with the LAYER GRAPH behind the C ABI (ctl_trunk_create / ctl_weights_pack /
+    ctl_embed_forward, csrc/trunk.cu): what a non-Python host binds.  Packs on the device from the fp32 state_dict;
+    bit-identical to TrunkEngine (tests/test_trunk_gpu.py::test_native_trunk_handle_matches_engine)."""
+
+    def __init__(self, state: Dict[str, torch.Tensor], device, ibn: bool = False, last_stride: int = 1,
+                 bn_head: Optional[Dict[str, torch.Tensor]] = None):
+        import ctypes as C
+
+        self.device = torch.device(device)
+        self._h = C.c_void_p()
+        N.check(N.lib().ctl_trunk_create(C.byref(self._h), int(ibn), int(last_stride)))
+        self._ws = None
+        self.pack(state, bn_head)
+
+    def pack(self, state, bn_head=None):
+        tensors = {k: v.detach().to(self.device, torch.float32).contiguous() for k, v in state.items() if v.is_floating_point()}
+        if bn_head is not None:
+            for k in ("weight", "bias", "running_mean", "running_var"):
+                tensors["bn_head." + k] = bn_head[k].detach().to(self.device, torch.float32).contiguous()
+        arr = (N.NamedTensor * len(tensors))()
+        for i, (k, v) in enumerate(tensors.items()):
+            arr[i].name, arr[i].data, arr[i].numel = k.encode(), v.data_ptr(), v.numel()
+        with torch.cuda.device(self.device):
+            N.check(N.lib().ctl_weights_pack(self._h, arr, len(tensors), N.stream_ptr()))
+            torch.cuda.current_stream().synchronize()  # the fp32 sources may be freed once the pack kernels have run
+        self.has_head = bn_head is not None
+
+    def forward(self, x: torch.Tensor, want_emb: bool = False):
+        N.require_cuda(x)
+        x = x.float().contiguous()
+        n, _, H, W = x.shape
+        L = N.lib()
+        need = L.ctl_embed_workspace_bytes(self._h, n, H, W)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        feat = torch.empty(n, 2048, device=self.device)
+        emb = torch.empty(n, 2048, device=self.device) if (want_emb and self.has_head) else None
+        with torch.cuda.device(self.device):
+            N.check(L.ctl_embed_forward(self._h, x.data_ptr(), n, H, W, feat.data_ptr(), N.ptr(emb), self._ws.data_ptr(),
+                                        self._ws.numel(), N.stream_ptr()))
+        out = {"global_feat": feat}
+        if emb is not None:
+            out["emb"] = emb
+        return out
+
+    def __del__(self):
+        try:
+            if self._h:
+                N.lib().ctl_trunk_destroy(self._h)
+                self._h = None
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
+
 class GraphedCall:
     """A CUDA graph of any launch sequence `fn()` on static buffers (two eager warm-ups on a side stream, then capture)."""
 

@@ -37,11 +37,11 @@ class _TrunkTrainFn(torch.autograd.Function):
         # dynamic loss scaling (the reference's PL native-AMP GradScaler, utils/misc.py:111): the fp16 backward runs on
         # (scale / trainer.grad_scale) * dfeat on top of the trainer's fixed internal scale and is un-scaled in fp32;
         # an overflow shows up as inf / NaN gradients, which CTLModel.optimizer_step_manual detects and skips
-        ratio = (ctx.scaler.scale / ctx.trainer.grad_scale) if (ctx.scaler is not None and ctx.scaler.enabled) else 1.0
-        grads = ctx.trainer.backward(dfeat * ratio if ratio != 1.0 else dfeat)
+        sc = ctx.scaler if (ctx.scaler is not None and ctx.scaler.enabled) else None
+        grads = ctx.trainer.backward(dfeat * sc.ratio if sc is not None else dfeat)  # ratio: a DEVICE scalar
         out = [grads.get(n) for n in ctx.names]
-        if ratio != 1.0:
-            torch._foreach_mul_([g for g in out if g is not None], 1.0 / ratio)
+        if sc is not None:  # un-scale (and look for inf / NaN while the data is in flight): one multi-tensor launch
+            sc.check([g for g in out if g is not None], mul_dev=sc.inv_ratio)
         return (None, None, None, None, None) + tuple(out)
 
 
@@ -105,7 +105,8 @@ class Baseline(nn.Module):
 
                 self._trainer = TrunkTrainer(dev, last_stride=self.base.last_stride, layers=self.base.layers_cfg,
                                              graphs=os.environ.get("CTL_TRAIN_GRAPHS", "1") == "1", ibn=self.base.ibn)
-                self.loss_scaler = DynamicLossScaler(dev, enabled=os.environ.get("CTL_DYNAMIC_LOSS_SCALE", "1") == "1")
+                self.loss_scaler = DynamicLossScaler(dev, base_scale=self._trainer.grad_scale,
+                                                     enabled=os.environ.get("CTL_DYNAMIC_LOSS_SCALE", "1") == "1")
             names = [k for k, _ in self.base.named_parameters()]
             tensors = [v for _, v in self.base.named_parameters()]
             buffers = {k: v for k, v in self.base.named_buffers() if "running" in k}

@@ -168,19 +168,20 @@ class CTLModel(_Base):
 
         apply_warmup_lr(opt, epoch, self.hparams)
         scaler = self.backbone.loss_scaler
-        found_inf = False
         if scaler is not None and scaler.enabled:
-            # GradScaler.step semantics: inspect every gradient the optimizers are about to consume (after any gradient
-            # all-reduce, so all ranks agree) and skip the step on inf / NaN instead of poisoning Adam's moments
+            # GradScaler.step / update without a host synchronisation: one pass over every gradient the optimizers are
+            # about to consume (after any gradient all-reduce, so all ranks agree) raises a DEVICE flag; the optimizer
+            # kernels skip themselves when it is set (Adam's moments are never poisoned); the scale backs off / grows on
+            # the device; the step counters are corrected one step late (DynamicLossScaler.settle)
+            scaler.settle(opt, opt_center)
             scaler.check([p.grad for p in self.parameters() if p.grad is not None])
-            found_inf = scaler.found_inf()
-        if not found_inf:
-            opt.step()
-            for param in self.center_loss.parameters():
-                param.grad.data *= 1.0 / self.hparams.SOLVER.CENTER_LOSS_WEIGHT
-            opt_center.step()
+            opt.skip_flag = opt_center.skip_flag = scaler.flag
+        opt.step()
+        for param in self.center_loss.parameters():
+            param.grad.data *= 1.0 / self.hparams.SOLVER.CENTER_LOSS_WEIGHT
+        opt_center.step()
         if scaler is not None and scaler.enabled:
-            scaler.update(found_inf)
+            scaler.update()
         self.backbone.invalidate()
 
     # -- evaluation -------------------------------------------------------------------------

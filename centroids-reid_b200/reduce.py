@@ -1,13 +1,12 @@
 """Per-identity centroid builders on the segmented-mean kernel (ctl_segment_mean).
 
 Host-side mirrors of modelling/bases.py:92-95,179-262 and
-inference/inference_utils.py:147-159.  The grouping logic (which rows form a centroid) is the
-reference's own host logic, kept verbatim in behaviour including its quirks; only the
-reductions run on the device, as ONE launch over a CSR description of all groups.
+inference/inference_utils.py:147-159.  `validation_create_centroids` builds its groups ON THE DEVICE
+(sort by label, segment boundaries, camera-set bit masks, one expand + filter) and reduces them
+with ONE ctl_segment_mean launch over the resulting CSR description; the reference's behaviour,
+quirks included, is kept (see its docstring).
 """
 from __future__ import annotations
-
-from collections import defaultdict
 
 import numpy as np
 import torch
@@ -51,49 +50,106 @@ def calculate_centroids(embeddings, pid_path_index):
     return cents.cpu().numpy(), np.array(pids, dtype=np.str_)
 
 
-def validation_create_centroids(embeddings, labels, camids, num_query, respect_camids=False):
-    """ModelBase.validation_create_centroids (modelling/bases.py:179-262).
+def segment_mean_csr(x: torch.Tensor, indptr: torch.Tensor, indices: torch.Tensor) -> torch.Tensor:
+    """ctl_segment_mean on a CSR description that already lives on the device (int64 indptr [n_seg + 1], indices)."""
+    N.require_cuda(x, indptr, indices)
+    x = x.detach().float().contiguous()
+    n, d = x.shape
+    n_seg = indptr.numel() - 1
+    out = torch.empty(n_seg, d, dtype=torch.float32, device=x.device)
+    if n_seg == 0:
+        return out
+    with torch.cuda.device(x.device):
+        N.check(N.lib().ctl_segment_mean(x.data_ptr(), n, d, indptr.contiguous().data_ptr(), indices.contiguous().data_ptr(),
+                                         n_seg, out.data_ptr(), N.stream_ptr()))
+    return out
 
-    Returns (embeddings [num_query + n_centroids, d] on the DEVICE, labels, camids) -- the
-    reference moves everything to the CPU here because its metric runs there (bases.py:262);
-    this engine's metric runs on the GPU, so the features stay resident.
-    """
+
+def validation_create_centroids(embeddings, labels, camids, num_query, respect_camids=False):
+    """ModelBase.validation_create_centroids (modelling/bases.py:179-262) with the GROUPING on the device.
+
+    The reference walks the identities in a Python loop (dict of index lists, np.unique / np.where / list comprehensions
+    per identity and per query camera).  Here the gallery rows are sorted once by (label, row) on the device, identities
+    are the segments of that order, the "cameras seen for this identity" sets are 64-bit masks built by one scatter, the
+    candidate (identity, query camera) pairs come from one `unique`, and the members of every centroid are produced by
+    one expand + filter -- a CSR description handed straight to ctl_segment_mean.  Semantics kept, quirk included:
+      * one centroid per identity (sorted by label), or with respect_camids one per DISTINCT set of "other cameras"
+        {c in cams(identity) : c != q} over the identity's query cameras q in ascending order, first occurrence wins,
+        empty sets skipped (bases.py:208-236);
+      * bases.py:214 indexes the FULL camid array with gallery-relative indices: the camera of gallery row i is taken
+        from camids[i], not camids[num_query + i];
+      * without respect_camids the dummy camids are 0 for queries, 1 for centroids, and the gallery part is sized from the
+        CONCATENATED label array (bases.py:255-260).
+    Returns (embeddings [num_query + n_centroids, d] on the DEVICE, labels, camids) -- the reference moves everything to the
+    CPU because its metric runs there (bases.py:262); this engine's metric runs on the GPU."""
     emb = torch.as_tensor(embeddings)
     emb = emb if emb.is_cuda else emb.cuda(non_blocking=True)
+    dev = emb.device
     labels = np.asarray(labels)
     camids = np.asarray(camids)
     lab_q, lab_g = labels[:num_query], labels[num_query:]
-    l2i, l2i_q = defaultdict(list), defaultdict(list)
-    for i, l in enumerate(lab_g.tolist()):
-        l2i[l].append(i)
-    for i, l in enumerate(lab_q.tolist()):
-        l2i_q[l].append(i)
-    groups, cent_lab, cent_cam = [], [], []
-    for label in sorted(l2i.keys()):
-        inds = np.asarray(l2i[label])
-        if respect_camids:
-            seen = set()
-            cam_g = camids[inds]  # reference quirk (bases.py:214): FULL camid array, gallery-relative indices
-            cam_q = camids[l2i_q[label]]
-            for cur in sorted(np.unique(cam_q).tolist()):
-                sel = np.where(cam_g != cur)[0]
-                if sel.shape[0] == 0:
-                    continue
-                used = tuple(sorted(np.unique([c for c in cam_g.tolist() if c != cur]).tolist()))
-                if used not in seen:
-                    seen.add(used)
-                    groups.append(num_query + inds[sel])
-                    cent_cam.append(list(used))
-                    cent_lab.append(label)
-        else:
-            cent_lab.append(label)
-            groups.append(num_query + inds)
-    cents = segment_mean(emb, groups)
-    out_emb = torch.cat((emb[:num_query].float(), cents), 0)
-    out_lab = np.hstack((lab_q, np.asarray(cent_lab)))
-    if respect_camids:
-        out_cam = [[c] for c in camids[:num_query].tolist()] + cent_cam
-    else:
-        # bases.py:255-260 sizes the dummy gallery camids from the concatenated label array
+    n_g = lab_g.shape[0]
+    # dense label ids in sorted label order (vectorised host relabelling; everything below is on the device)
+    uniq_lab, dense_g = np.unique(lab_g, return_inverse=True)
+    n_lab = uniq_lab.shape[0]
+    d_lab = torch.from_numpy(dense_g.astype(np.int64)).to(dev, non_blocking=True)
+    order = torch.argsort(d_lab, stable=True)                      # gallery rows by (label, row)
+    counts = torch.bincount(d_lab, minlength=n_lab)
+    seg_start = torch.cumsum(counts, 0) - counts
+    if not respect_camids:
+        indptr = torch.cat((seg_start, counts.sum()[None]))
+        cents = segment_mean_csr(emb, indptr, order + num_query)
+        out_lab = np.hstack((lab_q, uniq_lab))
         out_cam = np.hstack((np.zeros_like(lab_q), np.ones_like(out_lab)))
+        return torch.cat((emb[:num_query].float(), cents), 0), out_lab, out_cam
+
+    cam_vals, cam_dense = np.unique(camids, return_inverse=True)
+    if cam_vals.shape[0] > 63:
+        raise NotImplementedError(f"{cam_vals.shape[0]} distinct cameras; camera sets are packed into 64-bit masks")
+    cam_dense = cam_dense.astype(np.int64)
+    d_cam_g = torch.from_numpy(cam_dense[:n_g]).to(dev, non_blocking=True)          # bases.py:214 quirk
+    # queries whose label exists in the gallery -> candidate (label, query camera) pairs, sorted, unique
+    pos = np.searchsorted(uniq_lab, lab_q)
+    pos = np.clip(pos, 0, max(n_lab - 1, 0))
+    has = uniq_lab[pos] == lab_q if n_lab else np.zeros_like(lab_q, dtype=bool)
+    d_ql = torch.from_numpy(pos[has].astype(np.int64)).to(dev, non_blocking=True)
+    d_qc = torch.from_numpy(cam_dense[:num_query][has]).to(dev, non_blocking=True)
+    cand = torch.unique(d_ql * 64 + d_qc)                                            # ascending (label, camera)
+    c_lab, c_cam = cand // 64, cand % 64
+    present = torch.zeros(n_lab, 64, dtype=torch.bool, device=dev)
+    present[d_lab, d_cam_g] = True                                                   # cameras seen per identity
+    weights = (torch.ones(64, dtype=torch.int64, device=dev) << torch.arange(64, device=dev))
+    mask = (present.to(torch.int64) * weights).sum(1)                                # [n_lab] camera bit sets
+    m = mask[c_lab]
+    used = m & ~(torch.ones_like(c_cam) << c_cam)
+    full = used == m                                                                 # query camera not in the set
+    # first occurrence of each distinct set per identity: sets that drop a camera are distinct by construction; the
+    # "nothing dropped" set repeats for every query camera outside the identity's cameras -> keep its first one only
+    full_idx = torch.nonzero(full).flatten()
+    keep = used != 0
+    if full_idx.numel():
+        fl = c_lab[full_idx]
+        first = torch.ones_like(fl, dtype=torch.bool)
+        first[1:] = fl[1:] != fl[:-1]
+        dup = torch.zeros_like(keep)
+        dup[full_idx[~first]] = True
+        keep = keep & ~dup
+    k_lab, k_used = c_lab[keep], used[keep]
+    n_cent = int(k_lab.numel())
+    # members: expand every centroid over its identity's segment, keep the rows whose camera is in the set
+    seg_len = counts[k_lab]
+    cent_of = torch.repeat_interleave(torch.arange(n_cent, device=dev), seg_len)
+    offs = torch.arange(cent_of.numel(), device=dev) - torch.repeat_interleave(torch.cumsum(seg_len, 0) - seg_len, seg_len)
+    rows = order[seg_start[k_lab][cent_of] + offs]                                   # gallery-relative, ascending per centroid
+    sel = ((k_used[cent_of] >> d_cam_g[rows]) & 1).bool()
+    members, owner = rows[sel], cent_of[sel]
+    mcount = torch.bincount(owner, minlength=n_cent)
+    indptr = torch.cat((torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(mcount, 0)))
+    cents = segment_mean_csr(emb, indptr, members + num_query)
+    out_emb = torch.cat((emb[:num_query].float(), cents), 0)
+    k_lab_h, k_used_h = k_lab.cpu().numpy(), k_used.cpu().numpy()
+    out_lab = np.hstack((lab_q, uniq_lab[k_lab_h]))
+    bits = (k_used_h[:, None] >> np.arange(cam_vals.shape[0])[None, :]) & 1
+    cent_cam = [cam_vals[np.nonzero(b)[0]].tolist() for b in bits]
+    out_cam = [[c] for c in camids[:num_query].tolist()] + cent_cam
     return out_emb, out_lab, out_cam

@@ -162,31 +162,62 @@ def encode_ids(q_pids, g_pids, q_camids, g_camids, respect_camids: bool, device,
     return EncodedIds(to_dev(arrs[0]), to_dev(arrs[1]), to_dev(arrs[2]), to_dev(arrs[3].view(np.int64)), arrs[4])
 
 
-@dataclass
 class EvalResult:
-    cmc: np.ndarray          # float32 [max_rank]
-    mAP: float
-    all_topk: np.ndarray     # float64 [5]
-    single_performance: np.ndarray  # [n_valid, 3] (q_idx, q_pid, AP)
-    ranks: np.ndarray        # int32 [nq, max_pos] 1-based kept ranks of the positives (-1 pad)
+    """eval_func's outputs (utils/eval_reid.py:86-92).  `cmc`, `mAP`, `all_topk` are reduced from ONE packed read-back
+    of (AP, first hit rank, positive count) per query; `single_performance` is assembled and the full `ranks` matrix
+    ([nq, max_pos] 1-based kept ranks of every positive, -1 padded) is copied from the device on first access."""
+
+    def __init__(self, cmc, mAP, all_topk, valid_idx, aps, q_pids, ranks_dev):
+        self.cmc = cmc                    # float32 [max_rank]
+        self.mAP = mAP
+        self.all_topk = all_topk          # float64 [5]
+        self._valid_idx, self._aps, self._q_pids, self._ranks_dev = valid_idx, aps, q_pids, ranks_dev
+        self._ranks = None
+
+    @property
+    def single_performance(self) -> np.ndarray:  # [n_valid, 3] (q_idx, q_pid, AP)
+        q = self._valid_idx
+        return np.column_stack((q.astype(np.float64), np.asarray(self._q_pids)[q].astype(np.float64), self._aps))
+
+    @property
+    def ranks(self) -> np.ndarray:
+        if self._ranks is None:
+            r = self._ranks_dev
+            self._ranks = r.cpu().numpy() if torch.is_tensor(r) else np.asarray(r)
+        return self._ranks
 
 
-def _aggregate(ranks: np.ndarray, ap: np.ndarray, n_pos: np.ndarray, q_pids, num_g: int, max_rank: int) -> EvalResult:
-    """The reductions at the end of eval_func (utils/eval_reid.py:86-92) from per-query ranks."""
+def _aggregate(ranks, ap: np.ndarray, n_pos: np.ndarray, q_pids, num_g: int, max_rank: int, first=None) -> EvalResult:
+    """The reductions at the end of eval_func (utils/eval_reid.py:86-92) from per-query results: O(nq) on the host
+    (a histogram of the first-hit ranks gives the whole CMC curve), bit-identical to the reference's float32 / float64
+    reductions.  `ranks` may stay on the device (only `first` = ranks[:, 0] is needed here)."""
     max_rank = min(max_rank, num_g)
     valid = n_pos > 0
     if not valid.any():
         raise RuntimeError("no valid query: no query identity appears in the gallery")
-    first = ranks[valid, 0].astype(np.int64)  # sorted ascending -> first hit
-    thresholds = np.arange(1, max_rank + 1)
-    cmc_rows = (first[:, None] <= thresholds[None, :]).astype(np.float32)
-    num_valid = float(valid.sum())
-    cmc = cmc_rows.sum(0) / num_valid  # float32 / python float, as the reference
-    topk = np.stack([(first <= k).astype(np.int64) for k in K_LIST], 1)
-    q_idx = np.nonzero(valid)[0]
+    if first is None:
+        first = np.asarray(ranks)[:, 0]
+    first = first[valid].astype(np.int64)  # ranks are sorted ascending -> the first hit
+    num_valid = int(valid.sum())
+    hist = np.bincount(np.minimum(first, max_rank + 1), minlength=max_rank + 2)[1: max_rank + 1]
+    hits = np.cumsum(hist)                                     # queries whose first hit is at rank <= r
+    cmc = hits.astype(np.float32) / np.float32(num_valid)      # float32 sum of 0/1 rows / count, as the reference
+    topk = np.asarray([float(hits[k - 1]) if k <= max_rank else float(num_valid) for k in K_LIST]) / float(num_valid)
     aps = ap[valid]
-    single = np.column_stack((q_idx.astype(np.float64), np.asarray(q_pids)[q_idx].astype(np.float64), aps))
-    return EvalResult(cmc.astype(np.float32), float(np.mean(aps)), np.mean(topk, 0), single, ranks)
+    return EvalResult(cmc, float(np.mean(aps)), topk, np.nonzero(valid)[0], aps, q_pids, ranks)
+
+
+def _read_back(ranks: torch.Tensor, ap: torch.Tensor, count: torch.Tensor, ovf: torch.Tensor):
+    """ONE device->host copy for everything the host reduction needs: per query (AP, first-hit rank, #positives) and the
+    overflow flag, packed as float64 (exact for these integers)."""
+    nq = ap.shape[0]
+    pack = torch.empty(nq + 1, 3, dtype=torch.float64, device=ap.device)
+    pack[:nq, 0] = ap
+    pack[:nq, 1] = ranks[:, 0]
+    pack[:nq, 2] = count
+    pack[nq, 0] = ovf[0]
+    h = pack.cpu().numpy()
+    return h[:nq, 0], h[:nq, 1].astype(np.int64), h[:nq, 2].astype(np.int32), int(h[nq, 0])
 
 
 def evaluate_streamed(
@@ -245,12 +276,11 @@ def evaluate_streamed(
         ap = torch.empty(nq, dtype=torch.float64, device=dev)
         N.check(L.ctl_eval_finalize(buckets.data_ptr(), pos_count.data_ptr(), nq, max_pos, ranks.data_ptr(),
                                     ap.data_ptr(), s()))
-    # one read-back for everything the host reduction needs
-    ranks_h, ap_h, cnt_h, ovf_h = ranks.cpu().numpy(), ap.cpu().numpy(), pos_count.cpu().numpy(), int(ovf.item())
+    ap_h, first_h, cnt_h, ovf_h = _read_back(ranks, ap, pos_count, ovf)
     if ovf_h:
         raise OverflowError("positives list overflowed (max_pos too small)")
     num_g = total_gallery if total_gallery is not None else ng
-    return _aggregate(ranks_h, ap_h, cnt_h, np.asarray(q_pids), num_g, max_rank)
+    return _aggregate(ranks, ap_h, cnt_h, np.asarray(q_pids), num_g, max_rank, first=first_h)
 
 
 def _encode_identities_global(q_pids, g_pids, q_camids, g_camids):
@@ -401,10 +431,10 @@ def topk_and_eval(qp: Planes, gp: Planes, k: int, q_pids, g_pids, q_camids, g_ca
                                 dst.data_ptr(), ovf.data_ptr(), s()))
         N.check(L.ctl_eval_finalize(buckets.data_ptr(), pos_count.data_ptr(), nq, max_pos, ranks.data_ptr(),
                                     ap.data_ptr(), s()))
-    ranks_h, ap_h, cnt_h, ovf_h = ranks.cpu().numpy(), ap.cpu().numpy(), pos_count.cpu().numpy(), int(ovf.item())
+    ap_h, first_h, cnt_h, ovf_h = _read_back(ranks, ap, pos_count, ovf)
     if ovf_h:
         raise OverflowError("a device-side list overflowed (exact ties at the k-th distance, or max_pos)")
-    return idx, dst, _aggregate(ranks_h, ap_h, cnt_h, np.asarray(q_pids), ng, max_rank)
+    return idx, dst, _aggregate(ranks, ap_h, cnt_h, np.asarray(q_pids), ng, max_rank, first=first_h)
 
 
 def encode_ids_sharded(q_pids, g_pids_local, q_camids, g_camids_local, device, group) -> EncodedIds:
@@ -487,7 +517,7 @@ def topk_and_eval_sharded(qp: Planes, gp_local: Planes, k: int, ids: EncodedIds,
         dist.all_reduce(ovf, op=dist.ReduceOp.MAX, group=group)
         idx, dst = merge_topk_keys(g_best.permute(1, 0, 2).reshape(nq, world * k_loc), int(min(k, world * k_loc)))
         N.check(L.ctl_eval_finalize(buckets.data_ptr(), thr_count.data_ptr(), nq, mp, ranks.data_ptr(), ap.data_ptr(), s()))
-    ranks_h, ap_h, cnt_h, ovf_h = ranks.cpu().numpy(), ap.cpu().numpy(), thr_count.cpu().numpy(), int(ovf.item())
+    ap_h, first_h, cnt_h, ovf_h = _read_back(ranks, ap, thr_count, ovf)
     if ovf_h:
         raise OverflowError("a device-side list overflowed on some rank (exact ties at the k-th distance, or max_pos)")
-    return idx, dst, _aggregate(ranks_h, ap_h, cnt_h, np.asarray(q_pids), total_gallery, max_rank)
+    return idx, dst, _aggregate(ranks, ap_h, cnt_h, np.asarray(q_pids), total_gallery, max_rank, first=first_h)

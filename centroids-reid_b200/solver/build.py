@@ -37,6 +37,14 @@ class FusedAdam(torch.optim.Optimizer):
             raise ValueError("invalid Adam hyper-parameters")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.grad_mul = 1.0  # e.g. 1 / loss_scale
+        self.skip_flag = None  # device int32[1] (DynamicLossScaler): non-zero at execution time -> the kernels do nothing
+
+    def undo_step_count(self):
+        """A step that the device skipped (overflow) must not count for the bias correction: DynamicLossScaler calls this
+        when it learns, one step late, that the previous step was skipped."""
+        for st in self.state.values():
+            if "step" in st and float(st["step"]) > 0:
+                st["step"] -= 1
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -73,7 +81,7 @@ class FusedAdam(torch.optim.Optimizer):
                 table = torch.from_numpy(np.asarray(rows, dtype=np.int64)).to(group["params"][0].device, non_blocking=True)
                 N.check(L.ctl_adam_multi_step(table.data_ptr(), len(rows), chunks, float(group["lr"]), float(b1), float(b2),
                                               float(group["eps"]), float(group["weight_decay"]), step, float(self.grad_mul),
-                                              N.stream_ptr()))
+                                              N.ptr(self.skip_flag), N.stream_ptr()))
                 keep.append(table)
             _bump_version([p for p in group["params"] if p.grad is not None])
         return loss
@@ -86,6 +94,7 @@ class CenterSGD(torch.optim.Optimizer):
     def __init__(self, params, lr, grad_mul: float = 1.0):
         super().__init__(params, dict(lr=lr))
         self.grad_mul = grad_mul
+        self.skip_flag = None  # see FusedAdam.skip_flag
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -100,7 +109,7 @@ class CenterSGD(torch.optim.Optimizer):
                 N.require_cuda(p)
                 g = p.grad.contiguous()
                 N.check(N.lib().ctl_sgd_step(p.data_ptr(), g.data_ptr(), p.numel(), float(group["lr"]), float(self.grad_mul),
-                                             N.stream_ptr()))
+                                             N.ptr(self.skip_flag), N.stream_ptr()))
                 _bump_version([p])
         return loss
 
@@ -109,18 +118,44 @@ class DynamicLossScaler:
     """torch.cuda.amp.GradScaler semantics for the fp16 trunk backward (the reference trains under PL native AMP,
     utils/misc.py:111): the trunk's data / weight gradients are computed on `scale * dLoss/dfeat`, un-scaled in fp32, and
     a step whose gradients contain inf / NaN is SKIPPED and halves the scale; `growth_interval` clean steps double it.
-    Defaults are GradScaler's (init 2^16, x2 / x0.5, interval 2000).  Like GradScaler.step, `found_inf()` reads one
-    flag back from the device (one 4-byte synchronisation per optimizer step)."""
+    Defaults are GradScaler's (init 2^16, x2 / x0.5, interval 2000).
 
-    def __init__(self, device, init_scale=65536.0, growth_factor=2.0, backoff_factor=0.5, growth_interval=2000, enabled=True):
+    Unlike GradScaler.step (which reads found_inf back every step), nothing here synchronises: the scale, the growth
+    tracker and the overflow flag live on the device, the optimizer kernels skip themselves when the flag is set
+    (`skip_flag`), `ctl_loss_scale_update` is GradScaler.update() as a one-thread kernel, and the only thing the host
+    needs -- Adam's step COUNT must not include skipped steps -- is corrected one step late from a pinned copy of the
+    flag (`settle`), before the next optimizer launch and after a wait on an event that completed a whole step ago."""
+
+    def __init__(self, device, init_scale=65536.0, growth_factor=2.0, backoff_factor=0.5, growth_interval=2000,
+                 base_scale=1024.0, enabled=True):
         self.device = torch.device(device)
-        self.scale = float(init_scale)
-        self.growth_factor, self.backoff_factor, self.growth_interval = growth_factor, backoff_factor, growth_interval
+        self.base_scale = float(base_scale)  # the fixed scale baked into the training engine's kernels / CUDA graphs
+        self.growth_factor, self.backoff_factor, self.growth_interval = growth_factor, backoff_factor, int(growth_interval)
         self.enabled = enabled
-        self._growth_tracker = 0
-        self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.state = torch.tensor([init_scale, init_scale / base_scale, base_scale / init_scale], dtype=torch.float32,
+                                  device=self.device)  # scale, ratio, 1 / ratio
+        self._ints = torch.zeros(3, dtype=torch.int32, device=self.device)  # tracker, found_inf, last_found
+        self._pinned = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._event = None
         self._tables = {}
         self.skipped_steps = 0
+
+    # device scalars consumed by the backward (no host value is ever baked into a launch)
+    @property
+    def ratio(self) -> torch.Tensor:
+        return self.state[1]
+
+    @property
+    def inv_ratio(self) -> torch.Tensor:
+        return self.state[2]
+
+    @property
+    def flag(self) -> torch.Tensor:
+        return self._ints[1:2]
+
+    @property
+    def scale(self) -> float:
+        return float(self.state[0].item())  # synchronises: logging / tests / state_dict only
 
     def _table(self, grads):
         key = tuple((g.data_ptr(), g.numel()) for g in grads)
@@ -136,8 +171,9 @@ class DynamicLossScaler:
             self._tables[key] = t
         return t
 
-    def check(self, grads, mul: float = 1.0):
-        """OR-accumulates the overflow flag over `grads` (fp32, contiguous); mul != 1 rescales them in place."""
+    def check(self, grads, mul: float = 1.0, mul_dev=None):
+        """OR-accumulates the overflow flag over `grads` (fp32, contiguous) in ONE multi-tensor launch; a factor
+        mul * (*mul_dev) != 1 rescales them in place (mul_dev: a device scalar, e.g. `inv_ratio`)."""
         grads = [g for g in grads if g is not None]
         if not grads:
             return
@@ -145,31 +181,43 @@ class DynamicLossScaler:
             if g.dtype != torch.float32 or not g.is_contiguous():
                 raise TypeError("DynamicLossScaler.check expects contiguous fp32 gradients")
         table, n, chunks = self._table(grads)
-        N.check(N.lib().ctl_grad_check_multi(table.data_ptr(), n, chunks, float(mul), self._flag.data_ptr(), N.stream_ptr()))
+        N.check(N.lib().ctl_grad_check_multi(table.data_ptr(), n, chunks, float(mul), N.ptr(mul_dev), self.flag.data_ptr(),
+                                             N.stream_ptr()))
 
-    def found_inf(self) -> bool:
-        return bool(self._flag.item())
-
-    def update(self, found_inf: bool):
-        """GradScaler.update(): back off after an overflow, grow after `growth_interval` clean steps; clears the flag."""
-        if found_inf:
-            self.scale *= self.backoff_factor
-            self._growth_tracker = 0
+    def settle(self, *optimizers) -> bool:
+        """Call before launching an optimizer step: if the PREVIOUS step was skipped on the device, take it back out of
+        the optimizers' step counters.  Waits on an event recorded a whole step ago (no pipeline bubble)."""
+        if self._event is None:
+            return False
+        self._event.synchronize()
+        self._event = None
+        skipped = bool(int(self._pinned[0]))
+        if skipped:
             self.skipped_steps += 1
-            self._flag.zero_()
-        else:
-            self._growth_tracker += 1
-            if self._growth_tracker >= self.growth_interval:
-                self.scale *= self.growth_factor
-                self._growth_tracker = 0
+            for o in optimizers:
+                if hasattr(o, "undo_step_count"):
+                    o.undo_step_count()
+        return skipped
+
+    def update(self):
+        """GradScaler.update() on the device (after the optimizer launches of this step), plus the asynchronous copy of
+        this step's verdict that `settle` reads before the next one."""
+        i = self._ints
+        N.check(N.lib().ctl_loss_scale_update(self.state.data_ptr(), i[0:1].data_ptr(), i[1:2].data_ptr(), i[2:3].data_ptr(),
+                                              self.base_scale, float(self.growth_factor), float(self.backoff_factor),
+                                              self.growth_interval, N.stream_ptr()))
+        self._pinned.copy_(i[2:3], non_blocking=True)
+        self._event = torch.cuda.Event()
+        self._event.record()
 
     def state_dict(self):
         return {"scale": self.scale, "growth_factor": self.growth_factor, "backoff_factor": self.backoff_factor,
-                "growth_interval": self.growth_interval, "_growth_tracker": self._growth_tracker}
+                "growth_interval": self.growth_interval, "_growth_tracker": int(self._ints[0].item())}
 
     def load_state_dict(self, sd):
-        self.scale = float(sd["scale"])
-        self._growth_tracker = int(sd.get("_growth_tracker", 0))
+        sc = float(sd["scale"])
+        self.state.copy_(torch.tensor([sc, sc / self.base_scale, self.base_scale / sc]))
+        self._ints[0] = int(sd.get("_growth_tracker", 0))
 
 
 def build_optimizer(named_parameters, hparams, fold_center_rescale: bool = False):

@@ -245,6 +245,33 @@ int ctl_gap_bn_nhwc_f16(const void* x, int32_t n, int32_t hw, int32_t c, const f
 int ctl_instnorm_relu_nhwc_f16(void* x, int32_t n, int32_t hw, int32_t c, int32_t half, const float* gamma,
                                const float* beta, float eps, ctl_stream_t stream);
 
+/* ---- whole-trunk entry points: the eval embedding path bn(backbone(x)) behind an opaque handle ----
+ * replaces: ResNet.forward / ResNet_IBN.forward (modelling/backbones/resnet.py:122-133, resnet_ibn_a.py:126-141),
+ * Baseline.forward's pooling (modelling/baseline.py:91-96), ModelBase.validation_step / inference_utils._inference
+ * (modelling/bases.py:169-177, inference/inference_utils.py:104-113).
+ *   ctl_trunk_create   : ResNet50 (3,4,6,3 bottlenecks) or ResNet50-IBN-a (`ibn` != 0), MODEL.LAST_STRIDE 1 or 2.
+ *   ctl_weights_pack   : `tensors` = the reference's `base.*`-stripped state_dict as DEVICE fp32 pointers, by name
+ *                        ("conv1.weight", "bn1.running_var", "layer3.0.downsample.1.bias", "layer1.0.bn1.IN.weight", ...),
+ *                        plus optionally "bn_head.weight|bias|running_mean|running_var" (ModelBase.bn, [2048]).  Folds every
+ *                        eval BatchNorm into fp16 weights + fp32 biases on the device and keeps the packed operands in the
+ *                        handle.  Call again whenever the parameters change (after opt.step(), load_state_dict).
+ *   ctl_embed_forward  : x NCHW fp32 [n][3][h][w] on the device -> out_feat [n][2048] (global_feat) and / or out_emb
+ *                        [n][2048] (= eval BatchNorm1d(global_feat); needs the bn_head.* tensors).  Activations live in the
+ *                        caller's workspace of ctl_embed_workspace_bytes(...) bytes.  All launches go to `stream`.
+ * The handle is per device and not thread-safe; a missing / mis-sized tensor is CTL_ERR_INVALID_ARGUMENT naming it. */
+typedef struct ctl_trunk ctl_trunk;
+typedef struct ctl_named_tensor {
+  const char* name;
+  const float* data; /* device pointer */
+  int64_t numel;
+} ctl_named_tensor;
+int ctl_trunk_create(ctl_trunk** out, int32_t ibn, int32_t last_stride);
+void ctl_trunk_destroy(ctl_trunk* h);
+int ctl_weights_pack(ctl_trunk* h, const ctl_named_tensor* tensors, int32_t n_tensors, ctl_stream_t stream);
+size_t ctl_embed_workspace_bytes(const ctl_trunk* h, int32_t n, int32_t height, int32_t width);
+int ctl_embed_forward(ctl_trunk* h, const float* x_nchw, int32_t n, int32_t height, int32_t width, float* out_feat,
+                      float* out_emb, void* workspace, size_t workspace_bytes, ctl_stream_t stream);
+
 /* ---- training-side trunk kernels (autograd through modelling/backbones/resnet.py:67-87 in train mode) ---- */
 
 /* Weight gradient of ctl_conv2d_nhwc_f16's convolution (torch.nn.Conv2d backward w.r.t. weight):
@@ -323,16 +350,25 @@ typedef struct ctl_adam_entry {
 /* torch.optim.Adam (L2 weight decay added to the gradient, bias-corrected, no amsgrad) on every tensor of the table
  * in one launch; `step` is the 1-based step count after this update; gradients are read as grad * grad_mul. */
 int ctl_adam_multi_step(const void* table_device, int32_t n_tensors, int64_t n_chunks, float lr, float beta1, float beta2,
-                        float eps, float weight_decay, int64_t step, float grad_mul, ctl_stream_t stream);
+                        float eps, float weight_decay, int64_t step, float grad_mul, const int32_t* skip_flag,
+                        ctl_stream_t stream);
 /* torch.optim.SGD without momentum: param -= lr * grad * grad_mul (the center parameters; grad_mul =
  * 1 / SOLVER.CENTER_LOSS_WEIGHT, train_ctl_model.py:157-158). */
-int ctl_sgd_step(float* param, const float* grad, int64_t numel, float lr, float grad_mul, ctl_stream_t stream);
+int ctl_sgd_step(float* param, const float* grad, int64_t numel, float lr, float grad_mul, const int32_t* skip_flag,
+                 ctl_stream_t stream);
+/* `skip_flag` (device int, may be NULL) of the two optimizer entry points: when non-zero at execution time the kernel
+ * returns without touching parameters or moments -- GradScaler.step's "skip the step on inf / NaN gradients" without a
+ * host synchronisation.  ctl_loss_scale_update is GradScaler.update() on the device: state3 = {scale, scale / base_scale,
+ * base_scale / scale}; *found_inf is copied to *last_found and cleared. */
+int ctl_loss_scale_update(float* state3, int32_t* tracker, int32_t* found_inf, int32_t* last_found, float base_scale,
+                          float growth_factor, float backoff_factor, int32_t growth_interval, ctl_stream_t stream);
 /* Gradient overflow check of dynamic loss scaling (torch.cuda.amp.GradScaler.unscale_ in the reference's PL AMP trainer,
  * utils/misc.py:111): table = device array of {float* grad; int64 numel; int64 chunk_begin} (chunks of 8192 elements, like
- * ctl_adam_multi_step); every gradient is multiplied in place by `mul` (skipped when mul == 1) and *found_inf (device int,
+ * ctl_adam_multi_step); every gradient is multiplied in place by `mul` * (*mul_device if non-NULL: a device scalar such as
+ * base_scale / scale) -- skipped when that factor is exactly 1 -- and *found_inf (device int,
  * OR-accumulated, cleared by the caller) becomes 1 if any element is inf or NaN. */
-int ctl_grad_check_multi(const void* table_device, int32_t n_tensors, int64_t n_chunks, float mul, int32_t* found_inf,
-                         ctl_stream_t stream);
+int ctl_grad_check_multi(const void* table_device, int32_t n_tensors, int64_t n_chunks, float mul, const float* mul_device,
+                         int32_t* found_inf, ctl_stream_t stream);
 
 /* ---- training-time augmentation (datasets/transforms/build.py:15-27, random_erasing.py:30-55) ---- */
 

@@ -103,7 +103,9 @@ def test_c_abi_argument_errors_are_reported_without_a_gpu():
         lambda: L.ctl_stem_pool_fused(one, 1, 30, 64, one, one, one, 0, one, None),                           # H % 4
         lambda: L.ctl_stem_pool_fused(one, 1, 32, 256, one, one, one, 0, one, None),                          # W > 128
         lambda: L.ctl_instnorm_train_forward_nhwc_f16(one, 1, 16, 64, 12, one, one, 1e-5, one, one, one, None),  # half % 8
-        lambda: L.ctl_adam_multi_step(one, 0, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, 1.0, None),                  # no tensors
+        lambda: L.ctl_adam_multi_step(one, 0, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, 1.0, None, None),            # no tensors
+        lambda: L.ctl_loss_scale_update(one, one, one, one, 1024.0, 0.5, 0.5, 2000, None),                    # growth < 1
+        lambda: L.ctl_conv1x1_dual_nhwc_f16(one, 64, one, 7, 8, 64, 2, 1, one, one, one, 256, 1, None),       # odd H2, stride 2
         lambda: L.ctl_augment_batch_u8(one, 1, 8, 8, -1, one, (C.c_float * 3)(0, 0, 0), (C.c_float * 3)(1, 1, 1), one, None),
     ]
     for i, call in enumerate(cases):

@@ -54,8 +54,7 @@ def test_ctl_model_hooks():
     assert float((out["emb"].cpu() - ref).abs().max()) <= 1e-2 * scale  # fp16 trunk vs fp32 oracle
     model.train()
     assert model.backbone(x.cuda())[1].requires_grad  # train mode: differentiable B200 training engine
-    model.eval()
-    # training_step tail from prescribed features == the reference's training_step golden
+    # training_step tail from prescribed features == the reference's training_step golden (train mode, like the reference)
     name = "p8k4_pad"
     g = load_golden(f"loss_{name}.npz")
     P, K, pad, seed, scale_f = LOSS_CASES[name]
@@ -153,8 +152,9 @@ def test_training_step_with_attached_optimizers_is_the_reference_iteration():
 
 
 def test_dynamic_loss_scaling_skips_an_overflowing_step():
-    """GradScaler semantics (the reference trains under PL native AMP, utils/misc.py:111): inf / NaN gradients skip the
-    optimizer step (parameters and Adam moments untouched) and halve the scale; clean steps proceed."""
+    """GradScaler semantics (the reference trains under PL native AMP, utils/misc.py:111) without host synchronisation:
+    inf / NaN gradients make the optimizer kernels skip themselves (parameters and Adam moments untouched), the scale is
+    halved on the device, the skipped step is taken back out of Adam's step count one step later; clean steps proceed."""
     model, batch = _tiny_model(seed=7)
     (opt, opt_c), _ = model.configure_optimizers()
     out = model.training_step(batch, 0)
@@ -165,15 +165,23 @@ def test_dynamic_loss_scaling_skips_an_overflowing_step():
     w0, c0 = w.detach().clone(), model.center_loss.centers.detach().clone()
     w.grad[0, 0, 0, 0] = float("inf")
     model.optimizer_step_manual(opt, opt_c, epoch=0)
+    torch.cuda.synchronize()
     assert torch.equal(w.detach(), w0) and torch.equal(model.center_loss.centers.detach(), c0)
-    assert scaler.scale == 32768.0 and scaler.skipped_steps == 1 and len(opt.state) == 0
+    assert scaler.scale == 32768.0
+    assert all(float(st["exp_avg"].abs().max()) == 0 and float(st["exp_avg_sq"].abs().max()) == 0 for st in opt.state.values())
     for p_ in model.parameters():
         p_.grad = None
     out = model.training_step(batch, 0)
     out["loss"].backward()
     model.optimizer_step_manual(opt, opt_c, epoch=0)
-    assert not torch.equal(w.detach(), w0) and scaler.skipped_steps == 1
+    torch.cuda.synchronize()
+    assert scaler.skipped_steps == 1 and all(int(st["step"]) == 1 for st in opt.state.values())  # the skipped step does not count
+    assert not torch.equal(w.detach(), w0) and scaler.scale == 32768.0
     assert all(torch.isfinite(p_).all() for p_ in model.parameters())
+    # the bias correction of this first REAL step is that of step 1: same update as a fresh torch.optim.Adam step
+    g = w.grad.detach()
+    expect = w0 - opt.param_groups[0]["lr"] * (g + 5e-4 * w0) / ((g + 5e-4 * w0).abs() + 1e-8)
+    assert float((w.detach() - expect).abs().max()) <= 1e-6 * float(w0.abs().max()) + 1e-9
 
 
 def test_eval_engine_never_serves_stale_weights():
@@ -197,3 +205,28 @@ def test_eval_engine_never_serves_stale_weights():
         assert not torch.equal(f1, f2)
         model.base.load_state_dict(O.make_trunk_state(seed=2))
         assert torch.equal(model(x)[1], f0)
+
+
+@pytest.mark.parametrize("seed,n_ids,n_cams", [(0, 12, 3), (1, 40, 6), (2, 7, 2), (3, 25, 9)])
+def test_device_grouping_matches_the_reference_host_loop(seed, n_ids, n_cams):
+    """validation_create_centroids with the grouping done on the device (sort / segments / camera-set bit masks) against
+    the oracle's restatement of the reference's per-identity host loop (bases.py:179-262, pinned to the reference by
+    tests/golden/centroids.npz): random identities with few rows, query cameras that do not occur in the gallery,
+    identities present on one side only, single-camera identities (empty "other camera" sets) -- both camid modes."""
+    from ctl_b200 import reduce as RD
+
+    rng = np.random.default_rng(seed)
+    nq, ng, d = 60, 400, 64
+    labels = np.concatenate((rng.integers(0, n_ids + 3, nq), rng.integers(2, n_ids + 2, ng))) * 7 + 11   # sparse pids
+    camids = rng.integers(0, n_cams, nq + ng) * 3 + 1
+    camids[:nq][rng.random(nq) < 0.2] = 100                       # a query camera no gallery row has
+    emb = torch.randn(nq + ng, d, generator=torch.Generator().manual_seed(seed))
+    for respect in (False, True):
+        e_ref, l_ref, c_ref = O.validation_create_centroids(emb, labels, camids, nq, respect_camids=respect)
+        e, l, c = RD.validation_create_centroids(emb.cuda(), labels, camids, nq, respect_camids=respect)
+        assert np.array_equal(l, np.asarray(l_ref))
+        if respect:
+            assert [list(map(int, x)) for x in c] == [list(map(int, np.atleast_1d(x))) for x in c_ref]
+        else:
+            assert np.array_equal(np.asarray(c), np.asarray(c_ref))
+        np.testing.assert_allclose(e.cpu().numpy(), np.asarray(e_ref), rtol=1e-6, atol=1e-6)

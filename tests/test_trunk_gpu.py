@@ -292,3 +292,31 @@ def test_trunk_matches_reference_under_autocast(tag, ibn, hw):
           f"reference autocast vs its own fp32 {ref_own:.3e}  (north_star 1e-4 is an fp32-vs-fp32 bound)")
     assert e_amp <= AMP_TOL
     assert e_f32 <= 3.0 * ref_own
+
+
+@pytest.mark.parametrize("ibn,hw,n", [(False, (256, 128), 6), (True, (320, 320), 3), (True, (128, 64), 5), (False, (96, 48), 2)])
+def test_native_trunk_handle_matches_engine(ibn, hw, n):
+    """ctl_trunk_create + ctl_weights_pack + ctl_embed_forward -- the layer graph behind the C ABI, packing
+    done on the device from the fp32 state_dict -- must reproduce the Python-hosted engine BIT FOR BIT (same kernels,
+    same folded operands), with and without the BatchNorm1d head, across re-packs."""
+    from ctl_b200 import _native as N
+    from ctl_b200.modelling.backbones.engine import NativeTrunk, TrunkEngine
+
+    sd = O.make_trunk_state(seed=5, ibn=ibn)
+    head = dict(weight=torch.rand(2048) + 0.5, bias=torch.randn(2048) * 0.1, running_mean=torch.randn(2048) * 0.1,
+                running_var=torch.rand(2048) + 0.5)
+    x = torch.randn(n, 3, *hw, generator=torch.Generator().manual_seed(8)).cuda()
+    ref = TrunkEngine(sd, "cuda", ibn=ibn, bn_head=head).forward(x, want_emb=True)
+    nat = NativeTrunk(sd, "cuda", ibn=ibn, bn_head=head)
+    out = nat.forward(x, want_emb=True)
+    assert torch.equal(out["global_feat"], ref["global_feat"]) and torch.equal(out["emb"], ref["emb"])
+    sd2 = O.make_trunk_state(seed=6, ibn=ibn)
+    nat.pack(sd2)  # re-pack (parameters changed), this time without a head
+    out2 = nat.forward(x)
+    assert torch.equal(out2["global_feat"], TrunkEngine(sd2, "cuda", ibn=ibn).forward(x)["global_feat"])
+    with pytest.raises(ValueError, match="bn_head"):
+        N.check(N.lib().ctl_embed_forward(nat._h, x.data_ptr(), n, hw[0], hw[1], out["global_feat"].data_ptr(),
+                                          out["emb"].data_ptr(), nat._ws.data_ptr(), nat._ws.numel(), N.stream_ptr()))
+    bad = {k: v for k, v in sd.items() if k != "layer2.1.bn2.running_var"}
+    with pytest.raises(ValueError, match="layer2.1.bn2.running_var"):
+        nat.pack(bad)
