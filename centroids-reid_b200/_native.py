@@ -87,6 +87,7 @@ SIGNATURES = {
     "ctl_loss_step": (C.c_int, [_cfgp] + [_p] * 14 + [_p, _sz, _p]),
     "ctl_triplet_workspace_bytes": (_sz, [_i32, _i32]),
     "ctl_triplet_step": (C.c_int, [_p, _i32, _i32, _p, _p, _f, _p, _p, _p, _p, _p, _sz, _p]),
+    "ctl_triplet_step_ex": (C.c_int, [_p, _i32, _i32, _p, _p, _f, _i32, _i32, _p, _p, _p, _p, _p, _sz, _p]),
     "ctl_center_loss_step": (C.c_int, [_p, _i32, _i32, _p, _p, _i32, _p, _p, _p, _p, _sz, _p]),
     "ctl_xent_smooth_step": (C.c_int, [_p, _i32, _i32, _p, _f, _p, _p, _p, _sz, _p]),
     "ctl_conv2d_nhwc_f16": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
@@ -121,6 +122,8 @@ SIGNATURES = {
     "ctl_grad_check_multi": (C.c_int, [_p, _i32, C.c_int64, _f, _p, _p, _p]),
     "ctl_conv2d_wgrad_workspace_bytes": (C.c_size_t, [_i32, _i32, _i32, _i32, _i32, _i32, _i32]),
     "ctl_conv2d_wgrad_nhwc_f16": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _i32, _i32, _i32, _p, C.c_size_t, _p, _p]),
+    "ctl_conv2d_wgrad_nhwc_f16_ex": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _i32, _i32, _i32, _p, C.c_size_t, _p, _f, _i32, _p]),
+    "ctl_train_pack_weights": (C.c_int, [_p, _i32, C.c_int64, _p]),
 }
 
 _lib = None

@@ -217,11 +217,22 @@ __device__ __forceinline__ float pair_dist(const float* __restrict__ G, int ld, 
   return __fsqrt_rn(fmaxf(s, 1e-12f));
 }
 
-// generic single-problem variant (standalone TripletLoss): candidates are all N rows
+// cosine_dist (losses/triplet_loss.py:58-65) from the Gram matrix of the NORMALISED rows: clamp(|1 - cos|, 1e-12);
+// *sgn = d(distance)/d(1 - cos) (0 where the clamp saturates)
+__device__ __forceinline__ float pair_dist_cos(const float* __restrict__ G, int ld, int i, int j, float* sgn) {
+  const float s = __fsub_rn(1.f, G[(size_t)i * ld + j]);
+  const float a = fabsf(s);
+  *sgn = a < 1e-12f ? 0.f : (s >= 0.f ? 1.f : -1.f);
+  return fmaxf(a, 1e-12f);
+}
+
+// generic single-problem variant (standalone TripletLoss): candidates are all N rows.
+// `cosine`: distances are cosine distances of pre-normalised rows; `soft`: SoftMarginLoss(d_an - d_ap, 1) =
+// log(1 + exp(d_ap - d_an)) instead of the hinge (TripletLoss(margin=None), triplet_loss.py:130-131,157-158).
 __global__ void __launch_bounds__(128) mine_single_kernel(const float* __restrict__ G, const float* __restrict__ sq,
                                                           const int* __restrict__ labels,
                                                           const unsigned char* __restrict__ anchor_mask, int N,
-                                                          float margin, MineOut o) {
+                                                          float margin, int soft, int cosine, MineOut o) {
   __shared__ float s_v[128];
   __shared__ int s_i[128];
   const int a = blockIdx.x;
@@ -230,7 +241,8 @@ __global__ void __launch_bounds__(128) mine_single_kernel(const float* __restric
   int ip = -1, in = -1;
   for (int j = threadIdx.x; j < N; j += blockDim.x) {
     bool sat;
-    const float d = pair_dist(G, N, sq, a, j, &sat);
+    float sg;
+    const float d = cosine ? pair_dist_cos(G, N, a, j, &sg) : pair_dist(G, N, sq, a, j, &sat);
     if (labels[j] == la) {
       if (d > best_p) { best_p = d; ip = j; }
     } else {
@@ -265,19 +277,64 @@ __global__ void __launch_bounds__(128) mine_single_kernel(const float* __restric
   const float dan = s_v[0]; const int nidx = s_i[0];
   if (threadIdx.x == 0) {
     const bool active = anchor_mask == nullptr || anchor_mask[a];
-    const float h = dap - dan + margin;
+    const float x = dap - dan;
+    // hinge: max(0, x + margin); soft margin: log(1 + exp(x)), slope sigmoid(x)
+    const float h = soft ? (fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)))) : fmaxf(x + margin, 0.f);
+    const float slope = soft ? 1.f / (1.f + expf(-x)) : ((x + margin > 0.f) ? 1.f : 0.f);
     o.a_row[a] = active ? a : -1;
     o.p_row[a] = pidx;
     o.n_row[a] = nidx;
     o.d_ap[a] = dap;
     o.d_an[a] = dan;
-    o.hinge[a] = (active && nidx >= 0) ? fmaxf(h, 0.f) : 0.f;
-    bool sp, sn;
-    pair_dist(G, N, sq, a, pidx, &sp);
-    if (nidx >= 0) pair_dist(G, N, sq, a, nidx, &sn); else sn = true;
-    const bool on = active && nidx >= 0 && h > 0.f;
-    o.cap[a] = (on && !sp) ? 1.f / dap : 0.f;   // scaled by the problem weight later
-    o.can[a] = (on && !sn) ? 1.f / dan : 0.f;
+    o.hinge[a] = (active && nidx >= 0) ? h : 0.f;
+    const bool on = active && nidx >= 0 && slope > 0.f;
+    if (cosine) {
+      // coefficients of d(loss)/d(cos): the combine step is dXn = -Cm Xn (no 1/d factor, no diagonal term)
+      float gp = 0.f, gn = 0.f;
+      pair_dist_cos(G, N, a, pidx, &gp);
+      if (nidx >= 0) pair_dist_cos(G, N, a, nidx, &gn);
+      o.cap[a] = on ? slope * gp : 0.f;
+      o.can[a] = on ? slope * gn : 0.f;
+    } else {
+      bool sp, sn;
+      pair_dist(G, N, sq, a, pidx, &sp);
+      if (nidx >= 0) pair_dist(G, N, sq, a, nidx, &sn); else sn = true;
+      o.cap[a] = (on && !sp) ? slope / dap : 0.f;   // scaled by the problem weight later
+      o.can[a] = (on && !sn) ? slope / dan : 0.f;
+    }
+  }
+}
+
+// rows / max(|row|, 1e-12) (cosine_similarity, triplet_loss.py:44-55) and the norms
+__global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __restrict__ X, int D, float* __restrict__ Xn,
+                                                             float* __restrict__ norm) {
+  __shared__ float sm[8];
+  const int i = blockIdx.x;
+  float ss = 0.f;
+  for (int j = threadIdx.x; j < D; j += blockDim.x) {
+    const float v = X[(size_t)i * D + j];
+    ss = __fmaf_rn(v, v, ss);
+  }
+  ss = block_sum(ss, sm);
+  const float nr = fmaxf(__fsqrt_rn(ss), 1e-12f);
+  for (int j = threadIdx.x; j < D; j += blockDim.x) Xn[(size_t)i * D + j] = __fdiv_rn(X[(size_t)i * D + j], nr);
+  if (threadIdx.x == 0) norm[i] = nr;
+}
+// backward of the row normalisation: dX = (dXn - Xn (Xn . dXn)) / |x|, with dXn = dEm (= -Cm Xn);
+// rows whose norm was clamped are constant multiples of x (x / 1e-12): dX = dXn / 1e-12
+__global__ void __launch_bounds__(256) cosine_combine_kernel(const float* __restrict__ Xn, const float* __restrict__ X, int D,
+                                                             const float* __restrict__ dXn, const float* __restrict__ norm,
+                                                             float* __restrict__ dX) {
+  __shared__ float sm[8];
+  const int i = blockIdx.x;
+  float dot = 0.f;
+  for (int j = threadIdx.x; j < D; j += blockDim.x) dot = __fmaf_rn(Xn[(size_t)i * D + j], dXn[(size_t)i * D + j], dot);
+  dot = block_sum(dot, sm);
+  const float nr = norm[i];
+  const bool clamped = nr <= 1e-12f;
+  for (int j = threadIdx.x; j < D; j += blockDim.x) {
+    const float g = dXn[(size_t)i * D + j];
+    dX[(size_t)i * D + j] = clamped ? g / nr : (g - Xn[(size_t)i * D + j] * dot) / nr;
   }
 }
 
@@ -871,12 +928,21 @@ size_t ctl_triplet_workspace_bytes(int32_t n, int32_t d) {
   ws.take<float>((size_t)n * d);
   ws.take<float>(n);
   take_mine(ws, n);
+  ws.take<float>((size_t)n * d);  // normalised rows (cosine)
+  ws.take<float>(n);              // row norms (cosine)
   return ws.off;
 }
 
 int ctl_triplet_step(const float* feats, int32_t n, int32_t d, const int32_t* labels, const uint8_t* anchor_mask,
                      float margin, float* out_loss, float* out_dist_ap, float* out_dist_an, float* d_feats,
                      void* workspace, size_t workspace_bytes, ctl_stream_t stream_) {
+  return ctl_triplet_step_ex(feats, n, d, labels, anchor_mask, margin, 0, 0, out_loss, out_dist_ap, out_dist_an, d_feats,
+                             workspace, workspace_bytes, stream_);
+}
+
+int ctl_triplet_step_ex(const float* feats, int32_t n, int32_t d, const int32_t* labels, const uint8_t* anchor_mask,
+                        float margin, int32_t soft_margin, int32_t cosine, float* out_loss, float* out_dist_ap,
+                        float* out_dist_an, float* d_feats, void* workspace, size_t workspace_bytes, ctl_stream_t stream_) {
   CTL_CHECK_ARG(feats && labels && out_loss && out_dist_ap && out_dist_an && d_feats && workspace, "null pointer");
   CTL_CHECK_ARG(n >= 2 && d >= 1, "bad shape n=%d d=%d", n, d);
   int rc = ctl_device_check();
@@ -890,21 +956,32 @@ int ctl_triplet_step(const float* feats, int32_t n, int32_t d, const int32_t* la
   float* dEm = ws.take<float>((size_t)n * d);
   float* slot_w = ws.take<float>(n);
   MineOut o = take_mine(ws, n);
-  if (!o.d_an) {
+  float* Xn = ws.take<float>((size_t)n * d);
+  float* norm = ws.take<float>(n);
+  if (!o.d_an || !norm) {
     set_error("workspace too small: need %zu bytes, have %zu", ws.off, workspace_bytes);
     return CTL_ERR_WORKSPACE;
   }
-  sqnorm_rows_kernel<<<n, 256, 0, st>>>(feats, d, sq);
+  const float* E = feats;  // the rows the Gram matrix is taken of
+  if (cosine) {
+    normalize_rows_kernel<<<n, 256, 0, st>>>(feats, d, Xn, norm);
+    E = Xn;
+  } else {
+    sqnorm_rows_kernel<<<n, 256, 0, st>>>(feats, d, sq);
+  }
   CTL_LAUNCH_CHECK();
-  if ((rc = sgemm(st, n, n, d, feats, d, 1, feats, 1, d, G, n, 1.f, 0.f))) return rc;
-  mine_single_kernel<<<n, 128, 0, st>>>(G, sq, labels, anchor_mask, n, margin, o);
+  if ((rc = sgemm(st, n, n, d, E, d, 1, E, 1, d, G, n, 1.f, 0.f))) return rc;
+  mine_single_kernel<<<n, 128, 0, st>>>(G, sq, labels, anchor_mask, n, margin, soft_margin ? 1 : 0, cosine ? 1 : 0, o);
   CTL_LAUNCH_CHECK();
   single_reduce_kernel<<<1, 32, 0, st>>>(n, o, 1.f, slot_w, out_loss);
   CTL_LAUNCH_CHECK();
   build_coef_kernel<<<n, 128, 0, st>>>(n, 0, 0, 1, 1, o, slot_w, Cm, rowsum);
   CTL_LAUNCH_CHECK();
-  if ((rc = sgemm(st, n, d, n, Cm, n, 1, feats, d, 1, dEm, d, -1.f, 0.f))) return rc;
-  single_combine_kernel<<<n, 256, 0, st>>>(feats, d, dEm, rowsum, d_feats);
+  if ((rc = sgemm(st, n, d, n, Cm, n, 1, E, d, 1, dEm, d, -1.f, 0.f))) return rc;  // -Cm E
+  if (cosine)
+    cosine_combine_kernel<<<n, 256, 0, st>>>(Xn, feats, d, dEm, norm, d_feats);
+  else
+    single_combine_kernel<<<n, 256, 0, st>>>(feats, d, dEm, rowsum, d_feats);
   CTL_LAUNCH_CHECK();
   CTL_CUDA(cudaMemcpyAsync(out_dist_ap, o.d_ap, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
   CTL_CUDA(cudaMemcpyAsync(out_dist_an, o.d_an, n * sizeof(float), cudaMemcpyDeviceToDevice, st));

@@ -248,6 +248,65 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   }
 }
 
+// same reduction, result multiplied by `scale` and written in the reference's parameter layout [Cout][Cin][k][k]
+// (torch.nn.Conv2d.weight) instead of the operand layout [Cout][k][k][Cin]: one thread per (cout, cin) pair reads its
+// k*k taps (coalesced over cin) and writes k*k consecutive floats.  Replaces a permute + mul pass per layer.
+__global__ void __launch_bounds__(256) wgrad_reduce_nchw_kernel(const float* __restrict__ part, int splits, int cout_pad,
+                                                                int cout, int cin, int kk, float scale,
+                                                                float* __restrict__ dw) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t n = (size_t)cout * cin;
+  const size_t split_stride = (size_t)cout_pad * kk * cin;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t co = i / cin, ci = i - co * cin;
+    for (int rs = 0; rs < kk; ++rs) {
+      const size_t src = (co * kk + rs) * cin + ci;
+      float acc = part[src];
+      for (int s = 1; s < splits; ++s) acc += part[src + s * split_stride];
+      dw[i * kk + rs] = acc * scale;
+    }
+  }
+}
+
+// Operand packs of ALL convolutions of a training step in one launch (replaces permute / contiguous / half / flip chains
+// per layer): src fp32 [Cout][Cin][k][k] (torch.nn.Conv2d.weight) ->
+//   fwd  fp16 [Cout][k][k][Cin]            the forward operand of ctl_conv2d_nhwc_f16
+//   dgr  fp16 [Cin][k][k][Cout], taps flipped: the operand of the data-gradient convolution (the transposed conv)
+struct PackEntry {
+  const float* src;
+  __half* fwd;
+  __half* dgr;
+  int cout, cin, k, pad_;
+  long long chunk_begin;
+};
+static constexpr int PACK_CHUNK = 8192;
+
+__global__ void __launch_bounds__(256) train_pack_kernel(const PackEntry* __restrict__ table, int n_tensors, long long n_chunks) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    int lo = 0, hi = n_tensors - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (table[mid].chunk_begin <= chunk) lo = mid; else hi = mid - 1;
+    }
+    const PackEntry e = table[lo];
+    const int kk = e.k * e.k;
+    const long long numel = (long long)e.cout * e.cin * kk;
+    const long long base = (chunk - e.chunk_begin) * PACK_CHUNK;
+    const long long end = min(numel, base + PACK_CHUNK);
+    for (long long i = base + threadIdx.x; i < end; i += blockDim.x) {
+      const int rs = (int)(i % kk);
+      const long long t = i / kk;
+      const int ci = (int)(t % e.cin), co = (int)(t / e.cin);
+      const __half v = __float2half_rn(e.src[i]);
+      e.fwd[((long long)co * kk + rs) * e.cin + ci] = v;
+      if (e.dgr) e.dgr[((long long)ci * kk + (kk - 1 - rs)) * e.cout + co] = v;
+    }
+  }
+}
+
 static int wgrad_plan(int n, int h, int w, int cin, int cout, int ksize, int stride, WgradParams* p) {
   const int pad = ksize == 3 ? 1 : 0;
   const int Ho = (h + 2 * pad - ksize) / stride + 1, Wo = (w + 2 * pad - ksize) / stride + 1;
@@ -970,6 +1029,23 @@ size_t ctl_conv2d_wgrad_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t
 int ctl_conv2d_wgrad_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, int32_t cin, const void* dy, int32_t cout,
                               int32_t ksize, int32_t stride, void* workspace, size_t workspace_bytes, float* dw,
                               ctl_stream_t stream) {
+  return ctl_conv2d_wgrad_nhwc_f16_ex(x, n, h, w, cin, dy, cout, ksize, stride, workspace, workspace_bytes, dw, 1.f, 0, stream);
+}
+
+int ctl_train_pack_weights(const void* table_device, int32_t n_tensors, int64_t n_chunks, ctl_stream_t stream) {
+  CTL_CHECK_ARG(table_device && n_tensors >= 1 && n_chunks >= 1, "bad arguments");
+  static_assert(sizeof(PackEntry) == 48, "ctl_pack_entry layout");
+  int rc = ctl_device_check();
+  if (rc) return rc;
+  const int grid = (int)std::min<long long>(n_chunks, (long long)sm_count() * 8);
+  CTL_CUDA(launch_k(train_pack_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, static_cast<const PackEntry*>(table_device),
+                    (int)n_tensors, (long long)n_chunks));
+  return 0;
+}
+
+int ctl_conv2d_wgrad_nhwc_f16_ex(const void* x, int32_t n, int32_t h, int32_t w, int32_t cin, const void* dy, int32_t cout,
+                                 int32_t ksize, int32_t stride, void* workspace, size_t workspace_bytes, float* dw,
+                                 float out_scale, int32_t param_layout, ctl_stream_t stream) {
   CTL_CHECK_ARG(x && dy && dw && workspace, "null pointer");
   CTL_CHECK_ARG(n >= 1 && h >= 1 && w >= 1, "bad activation shape");
   CTL_CHECK_ARG(cin % 64 == 0 && cout % 64 == 0, "Cin=%d and Cout=%d must be multiples of 64", cin, cout);
@@ -1034,6 +1110,18 @@ int ctl_conv2d_wgrad_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, in
     CTL_CUDA(launch_k(conv_wgrad_kernel<true>, dim3(grid), dim3(WG_THREADS), WgCfg<true>::SMEM, st, p));
   else
     CTL_CUDA(launch_k(conv_wgrad_kernel<false>, dim3(grid), dim3(WG_THREADS), WgCfg<false>::SMEM, st, p));
+  if (param_layout != 0 || out_scale != 1.f) {
+    const size_t np = (size_t)cout * cin;
+    const int rgrid = (int)std::min<size_t>((np + 255) / 256, (size_t)sm_count() * 8);
+    if (param_layout != 0) {
+      CTL_CUDA(launch_k(wgrad_reduce_nchw_kernel, dim3(rgrid), dim3(256), 0, st, (const float*)p.part, p.splits, p.cout_pad,
+                        (int)cout, (int)cin, p.n_taps, out_scale, dw));
+    } else {  // operand layout, scaled: the [Cout][k*k*Cin] matrix is the nchw form of a 1x1 with Cin' = k*k*Cin
+      CTL_CUDA(launch_k(wgrad_reduce_nchw_kernel, dim3(rgrid), dim3(256), 0, st, (const float*)p.part, p.splits, p.cout_pad,
+                        (int)cout, p.n_taps * (int)cin, 1, out_scale, dw));
+    }
+    return 0;
+  }
   const size_t n4 = (size_t)cout * p.n_taps * cin / 4;
   const int rgrid = (int)std::min<size_t>((n4 + 255) / 256, (size_t)sm_count() * 8);
   CTL_CUDA(launch_k(wgrad_reduce_kernel, dim3(rgrid), dim3(256), 0, st, (const float*)p.part, p.splits, p.cout_pad, (int)cout,

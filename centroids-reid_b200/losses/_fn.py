@@ -44,7 +44,7 @@ class TripletFn(torch.autograd.Function):
     """losses/triplet_loss.py:139-173 (euclidean, MarginRankingLoss) -> loss, dist_ap, dist_an."""
 
     @staticmethod
-    def forward(ctx, feats, labels, mask, margin):
+    def forward(ctx, feats, labels, mask, margin, soft=False, cosine=False):
         N.require_cuda(feats, labels)
         f = _f32(feats)
         n, d = f.shape
@@ -58,9 +58,9 @@ class TripletFn(torch.autograd.Function):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         lab, m = _i32(labels), _u8(mask)
         with torch.cuda.device(dev):
-            N.check(L.ctl_triplet_step(f.data_ptr(), n, d, lab.data_ptr(), N.ptr(m), float(margin), loss.data_ptr(),
-                                       ap.data_ptr(), an.data_ptr(), grad.data_ptr(), ws.data_ptr(), ws_bytes,
-                                       N.stream_ptr()))
+            N.check(L.ctl_triplet_step_ex(f.data_ptr(), n, d, lab.data_ptr(), N.ptr(m), float(margin or 0.0), int(soft),
+                                          int(cosine), loss.data_ptr(), ap.data_ptr(), an.data_ptr(), grad.data_ptr(),
+                                          ws.data_ptr(), ws_bytes, N.stream_ptr()))
         ctx.save_for_backward(grad)
         ctx.in_dtype = feats.dtype
         ctx.mark_non_differentiable(ap, an)
@@ -69,7 +69,7 @@ class TripletFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, g_ap, g_an):
         (grad,) = ctx.saved_tensors
-        return (grad * g_loss).to(ctx.in_dtype), None, None, None
+        return (grad * g_loss).to(ctx.in_dtype), None, None, None, None, None
 
 
 class CenterLossFn(torch.autograd.Function):

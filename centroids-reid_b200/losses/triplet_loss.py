@@ -48,26 +48,27 @@ class TripletLoss(object):
     ctl_triplet_step (Gram matrix, mining, hinge, and dE = rowsum(C) E - C E)."""
 
     def __init__(self, margin=None, dist_func="euclidean"):
-        self.margin = margin
+        self.margin = margin  # None -> nn.SoftMarginLoss on (dist_an - dist_ap), triplet_loss.py:130-131
         self.dist_func_name = dist_func
-        if margin is None:
-            raise NotImplementedError("SoftMarginLoss variant (margin=None) is not on the B200 path; "
-                                      "the reference always passes SOLVER.MARGIN")
-        if dist_func != "euclidean":
-            raise NotImplementedError("SOLVER.DISTANCE_FUNC='cosine' for the training loss is not built yet")
-        self.dist_func = euclidean_dist
+        if dist_func == "cosine":
+            self.dist_func = cosine_dist
+        elif dist_func == "euclidean":
+            self.dist_func = euclidean_dist
+        else:
+            raise KeyError(dist_func)
 
     def __call__(self, global_feat, labels, warmup_margin=False, print_data=False, normalize_feature=False,
                  mask=None):
         if normalize_feature:
             global_feat = normalize(global_feat, axis=-1)
-        loss, dist_ap, dist_an = TripletFn.apply(global_feat, labels, mask, self.margin)
+        loss, dist_ap, dist_an = TripletFn.apply(global_feat, labels, mask, self.margin, self.margin is None,
+                                                 self.dist_func_name == "cosine")
         if mask is not None:
             dist_ap, dist_an = dist_ap[mask], dist_an[mask]
         if print_data:
             print(f"LOSS: {loss.item()}")
             print(f"precision: {(dist_an > dist_ap).float().mean()}")
-            print(f"proportion of triplets that satisfy margin: {(dist_an > dist_ap + self.margin).float().mean()}")
+            print(f"proportion of triplets that satisfy margin: {(dist_an > dist_ap + (self.margin or 0.0)).float().mean()}")
             print(f"AP mean distance: {dist_ap.mean()}")
             print(f"AN mean distance: {dist_an.mean()}")
         return loss, dist_ap, dist_an

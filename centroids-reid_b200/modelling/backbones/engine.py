@@ -102,9 +102,13 @@ class TrunkEngine:
         self.launches_per_forward = 0
         self.head = None
         if bn_head is not None:
-            scale = bn_head["weight"].float() / torch.sqrt(bn_head["running_var"].float() + BN_EPS)
-            shift = bn_head["bias"].float() - bn_head["running_mean"].float() * scale
-            self.head = (scale.to(self.device).contiguous(), shift.to(self.device).contiguous())
+            # folded on the DEVICE like the trunk's BatchNorms (fp32 add / sqrt / div / mul / sub, each correctly rounded):
+            # torch's vectorised CPU kernels round some of these differently, and the C-ABI pack (csrc/trunk.cu) must
+            # produce the same bits
+            hb = {k: bn_head[k].detach().to(self.device, torch.float32) for k in ("weight", "bias", "running_mean", "running_var")}
+            scale = hb["weight"] / torch.sqrt(hb["running_var"] + BN_EPS)
+            shift = hb["bias"] - hb["running_mean"] * scale
+            self.head = (scale.contiguous(), shift.contiguous())
 
     # -- single ops --------------------------------------------------------------------------
     def _conv(self, x, n, h, w, c: _Conv, residual=None):

@@ -66,10 +66,37 @@ class TrunkTrainer:
         self.launches += 1
         return out, ho, wo
 
+    def _pack_weights(self, params):
+        """Forward ([Cout][k][k][Cin]) and data-gradient ([Cin][k][k][Cout], flipped taps) fp16 operands of EVERY
+        bottleneck convolution in ONE launch (ctl_train_pack_weights) -- round 1 ran a permute / contiguous / half (/ flip)
+        chain of torch kernels per layer and direction, ~1 ms of launch-bound glue per step."""
+        import numpy as np
+
+        names = [k[:-7] for k in params if k.endswith(".weight") and params[k].dim() == 4 and k != "conv1.weight"]
+        key = tuple((nm, params[nm + ".weight"].data_ptr()) for nm in names)
+        if getattr(self, "_pack_key", None) != key:
+            total = sum(params[nm + ".weight"].numel() for nm in names)
+            arena = torch.empty(2 * total, dtype=torch.float16, device=self.device)
+            rows, off, chunks, packs = [], 0, 0, {}
+            for nm in names:
+                wt = params[nm + ".weight"]
+                if wt.dtype != torch.float32 or not wt.is_contiguous():
+                    raise TypeError(f"{nm}.weight must be a contiguous fp32 tensor")
+                cout, cin, k, _ = wt.shape
+                fwd, dgr = arena[off:off + wt.numel()], arena[total + off:total + off + wt.numel()]
+                packs[nm] = (fwd, dgr)
+                rows.append([wt.data_ptr(), fwd.data_ptr(), dgr.data_ptr(), cout | (cin << 32), k, chunks])
+                chunks += (wt.numel() + 8191) // 8192
+                off += wt.numel()
+            self._pack_table = torch.from_numpy(np.asarray(rows, dtype=np.int64)).to(self.device)
+            self._pack_meta, self._pack_arena, self._packs, self._pack_key = (len(rows), chunks), arena, packs, key
+        N.check(N.lib().ctl_train_pack_weights(self._pack_table.data_ptr(), self._pack_meta[0], self._pack_meta[1], N.stream_ptr()))
+        self.launches += 1
+
     def _conv_bn(self, a, n, h, w, params, conv, bn, k, stride, relu, residual=None, ibn=False):
         wt = params[conv + ".weight"]
         cout = wt.shape[0]
-        wf = wt.detach().permute(0, 2, 3, 1).contiguous().half()  # forward operand [Cout][k][k][Cin]
+        wf = self._packs[conv][0]  # forward operand [Cout][k][k][Cin] fp16 (ctl_train_pack_weights)
         y, ho, wo = self._conv(a, n, h, w, wf, cout, k, stride)
         rows = n * ho * wo
         z = torch.empty_like(y)
@@ -188,6 +215,7 @@ class TrunkTrainer:
                                                        N.stream_ptr()))
             self.launches += 5
             self._stem = (y0, z0, m0, i0, (n, H, W, h, w, hp, wp), arg)
+            self._pack_weights(params)
             h, w = hp, wp
             self._blocks = []
             for li, (planes, nblk) in enumerate(zip((64, 128, 256, 512), self.layers), start=1):
@@ -250,16 +278,20 @@ class TrunkTrainer:
         grads[s.bn + ".BN.weight"], grads[s.bn + ".BN.bias"] = dg, db
         return dy
 
-    def _wgrad(self, a, shape_in, dy, cout, k, stride):
+    def _wgrad(self, a, shape_in, dy, cout, k, stride, param_layout=False):
+        """param_layout: dw comes back un-scaled (x 1 / grad_scale) as [Cout][Cin][k][k], torch.nn.Conv2d.weight's layout
+        (folded into the split-K reduction); else raw [Cout][k][k][Cin]."""
         n, h, w = shape_in
         cin = a.shape[-1]
         L = N.lib()
         need = L.ctl_conv2d_wgrad_workspace_bytes(n, h, w, cin, cout, k, stride)
         if self._ws_wg is None or self._ws_wg.numel() < need:
             self._ws_wg = torch.empty(need, dtype=torch.uint8, device=self.device)
-        dw = torch.empty(cout, k, k, cin, device=self.device)
-        N.check(L.ctl_conv2d_wgrad_nhwc_f16(a.data_ptr(), n, h, w, cin, dy.data_ptr(), cout, k, stride,
-                                            self._ws_wg.data_ptr(), self._ws_wg.numel(), dw.data_ptr(), N.stream_ptr()))
+        dw = torch.empty((cout, cin, k, k) if param_layout else (cout, k, k, cin), device=self.device)
+        N.check(L.ctl_conv2d_wgrad_nhwc_f16_ex(a.data_ptr(), n, h, w, cin, dy.data_ptr(), cout, k, stride,
+                                               self._ws_wg.data_ptr(), self._ws_wg.numel(), dw.data_ptr(),
+                                               1.0 / self.grad_scale if param_layout else 1.0, int(param_layout),
+                                               N.stream_ptr()))
         self.launches += 2
         return dw
 
@@ -267,13 +299,12 @@ class TrunkTrainer:
         """weight gradient of s.conv and (optionally) the data gradient w.r.t. s.a (+ residual)."""
         wt = params[s.conv + ".weight"].detach()
         cout, cin, k = wt.shape[0], wt.shape[1], s.k
-        dw = self._wgrad(s.a, s.shape_in, dy, cout, k, s.stride)
-        grads[s.conv + ".weight"] = dw.permute(0, 3, 1, 2).mul(1.0 / self.grad_scale)  # -> [Cout, Cin, k, k]
+        grads[s.conv + ".weight"] = self._wgrad(s.a, s.shape_in, dy, cout, k, s.stride, param_layout=True)
         if not need_dx:
             return None
         n, h, w = s.shape_in
         _, ho, wo = s.shape_out
-        wd = wt.flip(2, 3).permute(1, 2, 3, 0).contiguous().half()  # [Cin][k][k][Cout]: the transposed convolution
+        wd = self._packs[s.conv][1]  # [Cin][k][k][Cout], flipped taps: the transposed convolution's operand
         L = N.lib()
         if s.stride == 1:
             dx, _, _ = self._conv(dy, n, ho, wo, wd, cin, k, 1, residual=residual)

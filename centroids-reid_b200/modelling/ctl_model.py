@@ -39,11 +39,59 @@ LOSS_NAMES = ("total", "query_xent", "query_triplet", "query_center", "centroid_
               "step_dist_an", "l2_mean_centroid")
 
 
+def ctl_losses_composed(module, features, class_labels, is_real):
+    """train_ctl_model.py:54-152 for the TripletLoss variants the fused step does not cover (SOLVER.DISTANCE_FUNC =
+    'cosine', SOLVER.MARGIN = None -> SoftMarginLoss): the same arithmetic assembled from the stand-alone drop-in losses
+    (each a fused forward+backward kernel behind torch.autograd) with the masks / centroid means in closed form
+    (SURVEY appendix A.1):  M_i[c, s] = (s != i) & R[c, i] & R[c, s],  centroid_i[c] = sum_s M_i[c, s] F[cK + s] / n_i[c],
+    round i = TripletLoss over [queries F[cK + i] ; centroids_i], skipped unless more than one class has a centroid.
+    Returns (total, parts[8]) like ctl_losses; this path synchronises (boolean row selection), the fused one does not."""
+    hp = module.hparams
+    K = int(hp.DATALOADER.NUM_INSTANCE)
+    B, D = features.shape
+    P = B // K
+    S = hp.SOLVER
+    real = is_real.bool()
+    F3 = features.view(P, K, D)
+    L2 = class_labels.view(P, K)
+    R = real.view(P, K)
+    lq, _, _ = module.contrastive_loss(features, class_labels, mask=real)
+    lq = lq * S.QUERY_CONTRASTIVE_WEIGHT
+    f_real, y_real = features[real], class_labels[real]
+    center = S.CENTER_LOSS_WEIGHT * module.center_loss(f_real, y_real)
+    xent = module.xent(module.fc_query(module.bn(f_real)), y_real) * S.QUERY_XENT_WEIGHT
+    eye = torch.eye(K, dtype=torch.bool, device=features.device)
+    M = (~eye)[:, None, :] & R.t()[:, :, None] & R[None, :, :]            # [round i, class c, slot s]
+    n = M.sum(-1)                                                          # [K, P]
+    cent = torch.einsum("ics,csd->icd", M.to(features.dtype), F3) / n.clamp(min=1)[..., None].to(features.dtype)
+    valid_round = ((n > 0).sum(1) > 1).tolist()                            # train_ctl_model.py:113
+    losses, aps, ans, l2s = [], [], [], []
+    for i in range(K):
+        if not valid_round[i]:
+            continue
+        q_sel = R[:, i]
+        queries, labs = F3[:, i][q_sel], L2[:, i][q_sel]
+        c_i = cent[i]
+        c_i = c_i[c_i.abs().sum(1) > 1e-7]                                 # train_ctl_model.py:120-122
+        loss_i, ap, an = module.contrastive_loss(torch.cat((queries, c_i)), torch.cat((labs, labs)))
+        losses.append(loss_i)
+        aps.append(ap.detach().mean())
+        ans.append(an.detach().mean())
+        l2s.append(c_i.detach().norm(dim=1).mean())
+    ctl = torch.stack(losses).mean() * S.CENTROID_CONTRASTIVE_WEIGHT
+    total = ctl + center + xent + lq
+    parts = torch.stack([total.detach(), xent.detach(), lq.detach(), center.detach(), ctl.detach(),
+                         torch.stack(aps).mean(), torch.stack(ans).mean(), torch.stack(l2s).mean()]).float()
+    return total, parts
+
+
 def ctl_losses(module, features, class_labels, is_real):
     """train_ctl_model.py:54-152 in one call: returns (total_loss tensor with autograd into
     features / centers / bn.weight / fc_query.weight, parts float32[8] on the device in
     LOSS_NAMES order).  No host synchronisation."""
     hp = module.hparams
+    if hp.SOLVER.DISTANCE_FUNC != "euclidean" or hp.SOLVER.MARGIN is None:
+        return ctl_losses_composed(module, features, class_labels, is_real)
     K = int(hp.DATALOADER.NUM_INSTANCE)
     B, D = features.shape
     if B % K != 0:

@@ -191,6 +191,13 @@ size_t ctl_triplet_workspace_bytes(int32_t n, int32_t d);
 int ctl_triplet_step(const float* feats, int32_t n, int32_t d, const int32_t* labels, const uint8_t* anchor_mask,
                      float margin, float* out_loss, float* out_dist_ap, float* out_dist_an, float* d_feats,
                      void* workspace, size_t workspace_bytes, ctl_stream_t stream);
+/* The two remaining variants of TripletLoss (losses/triplet_loss.py:127-137,157-158): soft_margin != 0 = SoftMarginLoss
+ * on (dist_an - dist_ap) (TripletLoss(margin=None): log(1 + exp(d_ap - d_an)), `margin` ignored); cosine != 0 =
+ * dist_func 'cosine' (clamp(|1 - cos(x_i, x_j)|, 1e-12) with rows divided by max(|x|, 1e-12), triplet_loss.py:44-65),
+ * gradient through the normalisation included. */
+int ctl_triplet_step_ex(const float* feats, int32_t n, int32_t d, const int32_t* labels, const uint8_t* anchor_mask,
+                        float margin, int32_t soft_margin, int32_t cosine, float* out_loss, float* out_dist_ap,
+                        float* out_dist_an, float* d_feats, void* workspace, size_t workspace_bytes, ctl_stream_t stream);
 int ctl_center_loss_step(const float* x, int32_t b, int32_t d, const int32_t* labels, const float* centers, int32_t c,
                          float* out_loss, float* d_x, float* d_centers, void* workspace, size_t workspace_bytes,
                          ctl_stream_t stream);
@@ -284,6 +291,16 @@ size_t ctl_conv2d_wgrad_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t
 int ctl_conv2d_wgrad_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, int32_t cin, const void* dy, int32_t cout,
                               int32_t ksize, int32_t stride, void* workspace, size_t workspace_bytes, float* dw,
                               ctl_stream_t stream);
+/* Same, with the epilogue a training step needs folded into the split-K reduction: dw is multiplied by out_scale (the
+ * 1 / loss-scale un-scaling) and, with param_layout != 0, written as [cout][cin][k][k] -- torch.nn.Conv2d.weight's own
+ * layout -- so the gradient needs no permute / mul pass. */
+int ctl_conv2d_wgrad_nhwc_f16_ex(const void* x, int32_t n, int32_t h, int32_t w, int32_t cin, const void* dy, int32_t cout,
+                                 int32_t ksize, int32_t stride, void* workspace, size_t workspace_bytes, float* dw,
+                                 float out_scale, int32_t param_layout, ctl_stream_t stream);
+/* Operand packs of every convolution of a training step in ONE launch: table = device array of
+ * {const float* src [cout][cin][k][k]; void* fwd fp16 [cout][k][k][cin]; void* dgrad fp16 [cin][k][k][cout] with flipped
+ * taps (may be NULL); int32 cout, cin, k, pad; int64 chunk_begin} (48 bytes; chunks of 8192 source elements). */
+int ctl_train_pack_weights(const void* table_device, int32_t n_tensors, int64_t n_chunks, ctl_stream_t stream);
 
 /* BatchNorm2d with batch statistics (torch.nn.BatchNorm2d in train mode, resnet.py:72-85) over NHWC fp16
  * [rows = N*H*W] rows of `pitch` elements, normalising the c channels that start at the given pointers (pitch == c

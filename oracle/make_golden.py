@@ -70,12 +70,24 @@ def head_state(seed, num_classes=NUM_CLASSES, dim=DIM):
     )
 
 
-def gen_loss(ref):
-    for name, (P, K, pad, seed, scale) in LOSS_CASES.items():
+# TripletLoss variants reachable through the config (SOLVER.DISTANCE_FUNC = 'cosine'; margin None -> SoftMarginLoss,
+# losses/triplet_loss.py:127-137): name -> (base case, SOLVER overrides)
+LOSS_VARIANTS = {
+    "p8k4_pad_cosine": ("p8k4_pad", {"DISTANCE_FUNC": "cosine"}),
+    "p8k4_pad_softmargin": ("p8k4_pad", {"MARGIN": None}),
+}
+
+
+def gen_loss(ref, variants=False):
+    cases = {k: (LOSS_CASES[b], o) for k, (b, o) in LOSS_VARIANTS.items()} if variants else \
+        {k: (v, {}) for k, v in LOSS_CASES.items()}
+    for name, ((P, K, pad, seed, scale), solver_over) in cases.items():
         feats, labels, is_real = O.synth_batch(P, K, DIM, NUM_CLASSES, seed, pad, scale)
         hs = head_state(seed)
         cfg = default_cfg(ref)
         cfg.DATALOADER.NUM_INSTANCE = K
+        for k_, v_ in solver_over.items():
+            cfg.SOLVER[k_] = v_
         model = ref.train_ctl.CTLModel(cfg, num_classes=NUM_CLASSES, num_query=1)
         model.backbone = _FixedTrunk(feats)
         with torch.no_grad():
@@ -347,7 +359,7 @@ def gen_trunk_autocast(ref):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="loss,masks,retrieval,centroids,trunk,trunk_train,trunk_autocast,market")
+    ap.add_argument("--only", default="loss,loss_variants,masks,retrieval,centroids,trunk,trunk_train,trunk_autocast,market")
     args = ap.parse_args()
     only = set(args.only.split(","))
     os.makedirs(GOLD, exist_ok=True)
@@ -357,6 +369,8 @@ def main():
         gen_masks(ref)
     if "loss" in only:
         gen_loss(ref)
+    if "loss_variants" in only:
+        gen_loss(ref, variants=True)
     if "retrieval" in only:
         gen_retrieval(ref, "small", 64, 512, 40, 3.0, 0)
         gen_retrieval(ref, "dyadic", 96, 1000, 60, 0.0, 5, dyadic=True)

@@ -230,3 +230,42 @@ def test_device_grouping_matches_the_reference_host_loop(seed, n_ids, n_cams):
         else:
             assert np.array_equal(np.asarray(c), np.asarray(c_ref))
         np.testing.assert_allclose(e.cpu().numpy(), np.asarray(e_ref), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("name,over", [("p8k4_pad_cosine", {"SOLVER__DISTANCE_FUNC": "cosine"}),
+                                       ("p8k4_pad_softmargin", {"SOLVER__MARGIN": None}),
+                                       ("p8k4_pad", {"SOLVER__DISTANCE_FUNC": "euclidean"})])
+def test_ctl_step_triplet_variants_match_reference_training_step(name, over):
+    """SOLVER.DISTANCE_FUNC = 'cosine' and MARGIN = None (SoftMarginLoss) through CTLModel.training_step_from_features
+    against goldens produced by the reference's own training_step with those settings (oracle/make_golden.py::LOSS_VARIANTS);
+    the third case forces the composed path on the default configuration and checks it against the fused step's golden."""
+    from ctl_b200.modelling import ctl_model as M
+
+    g = load_golden(f"loss_{name}.npz")
+    base = name.replace("_cosine", "").replace("_softmargin", "")
+    P, K, pad, seed, scale_f = LOSS_CASES[base]
+    feats, labels, is_real = O.synth_batch(P, K, DIM, NUM_CLASSES, seed, pad, scale_f)
+    hs = head_state(seed)
+    torch.manual_seed(0)
+    cfg = _cfg(**over)
+    cfg["DATALOADER"]["NUM_INSTANCE"] = K
+    model = M.CTLModel(cfg, num_classes=NUM_CLASSES, num_query=24).cuda().train()
+    with torch.no_grad():
+        model.center_loss.centers.copy_(hs["centers"])
+        model.bn.weight.copy_(hs["bn_weight"])
+        model.bn.bias.copy_(hs["bn_bias"])
+        model.fc_query.weight.copy_(hs["fc_weight"])
+    f = feats.cuda().requires_grad_(True)
+    if name == "p8k4_pad":
+        total, parts = M.ctl_losses_composed(model, f, labels.cuda(), is_real.cuda())
+    else:
+        out = model.training_step_from_features(f, labels.cuda(), is_real.cuda())
+        total, parts = out["loss"], out["parts"]
+    total.backward()
+    p = parts.tolist()
+    np.testing.assert_allclose(float(total), float(g["total"]), rtol=1e-4)
+    for got, key in zip(p[1:8], ("xent", "triplet", "center", "ctl", "dist_ap", "dist_an", "l2_centroid")):
+        np.testing.assert_allclose(got, float(g[key]), rtol=2e-4, atol=1e-6)
+    np.testing.assert_allclose(f.grad.cpu().numpy(), g["grad_feats"], rtol=1e-4, atol=2e-4 * np.abs(g["grad_feats"]).max())
+    np.testing.assert_allclose(model.bn.weight.grad.cpu().numpy(), g["grad_bn_weight"], rtol=1e-3,
+                               atol=2e-4 * np.abs(g["grad_bn_weight"]).max())
