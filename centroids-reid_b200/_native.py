@@ -74,6 +74,7 @@ SIGNATURES = {
     "ctl_sort_key_rows": (C.c_int, [_p, _p, _i64, _i32, _p]),
     "ctl_eval_count": (C.c_int, [_p, _i64, _p, _i64, _i32, _i32, _p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p]),
     "ctl_eval_finalize": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p]),
+    "ctl_eval_finalize_packed": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _p, _p]),
     "ctl_dist_pass": (C.c_int, [_p, _i64, _p, _i64, _i32, _i32, C.POINTER(PassDesc), _p]),
     "ctl_debug_set_dist_profile": (None, [_p]),
     "ctl_topk_plan": (C.c_int, [_i64, _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),

@@ -690,9 +690,16 @@ __global__ void topk_emit_kernel(const unsigned long long* __restrict__ keys, co
   out_dist[i] = orderable_float((uint32_t)(key >> 32));
 }
 
+// `packed` (optional, [nq + 1][3] doubles): per query (AP, first-hit rank, #positives) and, in the last row, the
+// overflow flag -- everything the host reduction of eval_func needs, in ONE device->host copy
 __global__ void eval_finalize_kernel(const int* __restrict__ buckets, const int* __restrict__ pos_count, int64_t nq,
-                                     int max_pos, int* __restrict__ ranks, double* __restrict__ ap) {
+                                     int max_pos, int* __restrict__ ranks, double* __restrict__ ap,
+                                     double* __restrict__ packed, const int* __restrict__ overflow) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q == 0 && packed != nullptr) {
+    packed[nq * 3] = overflow ? (double)*overflow : 0.0;
+    packed[nq * 3 + 1] = packed[nq * 3 + 2] = 0.0;
+  }
   if (q >= nq) return;
   const int n = min(pos_count[q], max_pos);
   const int* b = buckets + (size_t)q * (max_pos + 1);
@@ -706,7 +713,13 @@ __global__ void eval_finalize_kernel(const int* __restrict__ buckets, const int*
     acc += (double)(j + 1) / (double)rank;  // utils/eval_reid.py:75-79
   }
   for (int j = n; j < max_pos; ++j) r[j] = -1;
-  ap[q] = n > 0 ? acc / (double)n : CUDART_NAN;
+  const double a = n > 0 ? acc / (double)n : CUDART_NAN;
+  ap[q] = a;
+  if (packed != nullptr) {
+    packed[q * 3] = a;
+    packed[q * 3 + 1] = n > 0 ? (double)r[0] : -1.0;
+    packed[q * 3 + 2] = (double)pos_count[q];
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -979,11 +992,16 @@ int ctl_eval_count(const void* q_planes, int64_t nq, const void* g_planes, int64
 
 int ctl_eval_finalize(const int32_t* buckets, const int32_t* pos_count, int64_t nq, int32_t max_pos, int32_t* ranks,
                       double* ap, ctl_stream_t stream) {
+  return ctl_eval_finalize_packed(buckets, pos_count, nq, max_pos, ranks, ap, nullptr, nullptr, stream);
+}
+
+int ctl_eval_finalize_packed(const int32_t* buckets, const int32_t* pos_count, int64_t nq, int32_t max_pos, int32_t* ranks,
+                             double* ap, double* packed, const int32_t* overflow, ctl_stream_t stream) {
   CTL_CHECK_ARG(buckets && pos_count && ranks && ap && nq > 0 && max_pos >= 1, "bad arguments");
   int rc = ctl_device_check();
   if (rc) return rc;
   eval_finalize_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, (cudaStream_t)stream>>>(buckets, pos_count, nq, max_pos,
-                                                                                       ranks, ap);
+                                                                                       ranks, ap, packed, overflow);
   CTL_LAUNCH_CHECK();
   return 0;
 }

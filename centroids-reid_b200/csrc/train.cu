@@ -249,22 +249,35 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 }
 
 // same reduction, result multiplied by `scale` and written in the reference's parameter layout [Cout][Cin][k][k]
-// (torch.nn.Conv2d.weight) instead of the operand layout [Cout][k][k][Cin]: one thread per (cout, cin) pair reads its
-// k*k taps (coalesced over cin) and writes k*k consecutive floats.  Replaces a permute + mul pass per layer.
+// (torch.nn.Conv2d.weight) instead of the operand layout [Cout][k][k][Cin].  Replaces a permute + mul pass per layer.
+// A block owns 256 consecutive (cout, cin) pairs: reads are coalesced over cin for every tap, the k*k results of the
+// block are transposed through shared memory and leave as ONE contiguous run of 256 * k*k floats.
+template <int KK>
 __global__ void __launch_bounds__(256) wgrad_reduce_nchw_kernel(const float* __restrict__ part, int splits, int cout_pad,
-                                                                int cout, int cin, int kk, float scale,
-                                                                float* __restrict__ dw) {
+                                                                int cout, int cin, float scale, float* __restrict__ dw) {
   pdl_launch_dependents();
   pdl_wait();
+  __shared__ float tile[KK > 1 ? 256 * KK : 1];
   const size_t n = (size_t)cout * cin;
-  const size_t split_stride = (size_t)cout_pad * kk * cin;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t co = i / cin, ci = i - co * cin;
-    for (int rs = 0; rs < kk; ++rs) {
-      const size_t src = (co * kk + rs) * cin + ci;
-      float acc = part[src];
-      for (int s = 1; s < splits; ++s) acc += part[src + s * split_stride];
-      dw[i * kk + rs] = acc * scale;
+  const size_t split_stride = (size_t)cout_pad * KK * cin;
+  for (size_t base = (size_t)blockIdx.x * 256; base < n; base += (size_t)gridDim.x * 256) {
+    const size_t i = base + threadIdx.x;
+    if (i < n) {
+      const size_t co = i / cin, ci = i - co * cin;
+#pragma unroll
+      for (int rs = 0; rs < KK; ++rs) {
+        const size_t src = (co * KK + rs) * cin + ci;
+        float acc = part[src];
+        for (int s = 1; s < splits; ++s) acc += part[src + s * split_stride];
+        if (KK == 1) dw[i] = acc * scale;
+        else tile[threadIdx.x * KK + rs] = acc * scale;
+      }
+    }
+    if (KK > 1) {
+      __syncthreads();
+      const size_t cnt = min((size_t)256, n - base) * KK;
+      for (size_t j = threadIdx.x; j < cnt; j += 256) dw[base * KK + j] = tile[j];
+      __syncthreads();
     }
   }
 }
@@ -445,12 +458,26 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const __half* __re
 // a fixed order (deterministic).  Returns the two totals of channel `c` to the threads with part == 0.
 __device__ __forceinline__ void bn_sum_partials(const float* __restrict__ part, int blocks, int C, int c, int part_id,
                                                 double (*sh)[2][32], double& s0, double& s1) {  // sh[32][2][32]
+  // all of this thread's partials are loaded FIRST (independent loads: one memory round trip instead of a chain of up to
+  // 19 dependent ones -- the finalize kernels were pure latency, ~15 us each, 127 launches per training step) and then
+  // summed in the same fixed order as before (bit-identical results)
+  constexpr int MAXQ = (BN_MAX_BLOCKS + 31) / 32;
+  float va[MAXQ], vb[MAXQ];
+#pragma unroll
+  for (int q = 0; q < MAXQ; ++q) {
+    const int blk = part_id + 32 * q;
+    const bool ok = c < C && blk < blocks;
+    va[q] = ok ? part[(size_t)blk * 2 * C + c] : 0.f;
+    vb[q] = ok ? part[(size_t)blk * 2 * C + C + c] : 0.f;
+  }
   double a = 0.0, b = 0.0;
-  if (c < C)
-    for (int blk = part_id; blk < blocks; blk += 32) {
-      a += (double)part[(size_t)blk * 2 * C + c];
-      b += (double)part[(size_t)blk * 2 * C + C + c];
+#pragma unroll
+  for (int q = 0; q < MAXQ; ++q) {
+    if (part_id + 32 * q < blocks) {
+      a += (double)va[q];
+      b += (double)vb[q];
     }
+  }
   sh[part_id][0][threadIdx.x & 31] = a;
   sh[part_id][1][threadIdx.x & 31] = b;
   __syncthreads();
@@ -1113,12 +1140,14 @@ int ctl_conv2d_wgrad_nhwc_f16_ex(const void* x, int32_t n, int32_t h, int32_t w,
   if (param_layout != 0 || out_scale != 1.f) {
     const size_t np = (size_t)cout * cin;
     const int rgrid = (int)std::min<size_t>((np + 255) / 256, (size_t)sm_count() * 8);
-    if (param_layout != 0) {
-      CTL_CUDA(launch_k(wgrad_reduce_nchw_kernel, dim3(rgrid), dim3(256), 0, st, (const float*)p.part, p.splits, p.cout_pad,
-                        (int)cout, (int)cin, p.n_taps, out_scale, dw));
-    } else {  // operand layout, scaled: the [Cout][k*k*Cin] matrix is the nchw form of a 1x1 with Cin' = k*k*Cin
-      CTL_CUDA(launch_k(wgrad_reduce_nchw_kernel, dim3(rgrid), dim3(256), 0, st, (const float*)p.part, p.splits, p.cout_pad,
-                        (int)cout, p.n_taps * (int)cin, 1, out_scale, dw));
+    if (param_layout != 0 && p.n_taps == 9) {
+      CTL_CUDA(launch_k(wgrad_reduce_nchw_kernel<9>, dim3(rgrid), dim3(256), 0, st, (const float*)p.part, p.splits, p.cout_pad,
+                        (int)cout, (int)cin, out_scale, dw));
+    } else {  // 1x1, or operand layout scaled: [Cout][k*k*Cin] is the parameter layout of a 1x1 with Cin' = k*k*Cin
+      const size_t np1 = (size_t)cout * p.n_taps * cin;
+      const int g1 = (int)std::min<size_t>((np1 + 255) / 256, (size_t)sm_count() * 8);
+      CTL_CUDA(launch_k(wgrad_reduce_nchw_kernel<1>, dim3(g1), dim3(256), 0, st, (const float*)p.part, p.splits, p.cout_pad,
+                        (int)cout, p.n_taps * (int)cin, out_scale, dw));
     }
     return 0;
   }

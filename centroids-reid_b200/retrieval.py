@@ -57,6 +57,26 @@ def build_planes(x: torch.Tensor, dist: str = "euclidean", normalize: bool = Fal
     return Planes(buf, n, d, flags)
 
 
+class PlaneCache:
+    """Operand planes of feature matrices that do not change between evaluations (a fixed gallery of `embeddings.npy`
+    searched by many query batches, inference/get_similar.py:104-128; or one validation set evaluated under several
+    settings): keyed on the tensor's storage pointer, shape, in-place version counter and the distance flags, so a
+    modified tensor is re-packed.  Holds at most `capacity` plane buffers."""
+
+    def __init__(self, capacity: int = 4):
+        self.capacity = capacity
+        self._items = {}
+
+    def get(self, x: torch.Tensor, dist: str = "euclidean", normalize: bool = False) -> Planes:
+        key = (x.data_ptr(), tuple(x.shape), x._version, str(x.device), dist, normalize)
+        p = self._items.get(key)
+        if p is None:
+            if len(self._items) >= self.capacity:
+                self._items.pop(next(iter(self._items)))
+            p = self._items[key] = build_planes(x, dist, normalize)
+        return p
+
+
 def dist_matrix(x: torch.Tensor, y: torch.Tensor, dist: str = "euclidean", normalize: bool = False) -> torch.Tensor:
     """get_euclidean / get_cosine (utils/reid_metric.py:25-59): the full [m, n] matrix."""
     qp, gp = build_planes(x, dist, normalize), build_planes(y, dist, normalize)
@@ -207,17 +227,18 @@ def _aggregate(ranks, ap: np.ndarray, n_pos: np.ndarray, q_pids, num_g: int, max
     return EvalResult(cmc, float(np.mean(aps)), topk, np.nonzero(valid)[0], aps, q_pids, ranks)
 
 
-def _read_back(ranks: torch.Tensor, ap: torch.Tensor, count: torch.Tensor, ovf: torch.Tensor):
-    """ONE device->host copy for everything the host reduction needs: per query (AP, first-hit rank, #positives) and the
-    overflow flag, packed as float64 (exact for these integers)."""
-    nq = ap.shape[0]
-    pack = torch.empty(nq + 1, 3, dtype=torch.float64, device=ap.device)
-    pack[:nq, 0] = ap
-    pack[:nq, 1] = ranks[:, 0]
-    pack[:nq, 2] = count
-    pack[nq, 0] = ovf[0]
+def _finalize_and_read_back(buckets, count, nq, max_pos, ovf):
+    """ctl_eval_finalize_packed + ONE device->host copy: per query (AP, first-hit rank, #positives) and the overflow flag
+    as float64 (exact for these integers).  Returns (ranks on the device, ap, first, count, overflow) -- the last four on
+    the host."""
+    dev = buckets.device
+    ranks = torch.empty(nq, max_pos, dtype=torch.int32, device=dev)
+    ap = torch.empty(nq, dtype=torch.float64, device=dev)
+    pack = torch.empty(nq + 1, 3, dtype=torch.float64, device=dev)
+    N.check(N.lib().ctl_eval_finalize_packed(buckets.data_ptr(), count.data_ptr(), nq, max_pos, ranks.data_ptr(), ap.data_ptr(),
+                                             pack.data_ptr(), ovf.data_ptr(), N.stream_ptr()))
     h = pack.cpu().numpy()
-    return h[:nq, 0], h[:nq, 1].astype(np.int64), h[:nq, 2].astype(np.int32), int(h[nq, 0])
+    return ranks, h[:nq, 0], h[:nq, 1].astype(np.int64), h[:nq, 2].astype(np.int32), int(h[nq, 0])
 
 
 def evaluate_streamed(
@@ -272,11 +293,7 @@ def evaluate_streamed(
                                  pos_keys.data_ptr(), pos_count.data_ptr(), buckets.data_ptr(), s()))
         if world > 1:
             dist.all_reduce(buckets, op=dist.ReduceOp.SUM, group=group)
-        ranks = torch.empty(nq, max_pos, dtype=torch.int32, device=dev)
-        ap = torch.empty(nq, dtype=torch.float64, device=dev)
-        N.check(L.ctl_eval_finalize(buckets.data_ptr(), pos_count.data_ptr(), nq, max_pos, ranks.data_ptr(),
-                                    ap.data_ptr(), s()))
-    ap_h, first_h, cnt_h, ovf_h = _read_back(ranks, ap, pos_count, ovf)
+        ranks, ap_h, first_h, cnt_h, ovf_h = _finalize_and_read_back(buckets, pos_count, nq, max_pos, ovf)
     if ovf_h:
         raise OverflowError("positives list overflowed (max_pos too small)")
     num_g = total_gallery if total_gallery is not None else ng
@@ -407,8 +424,6 @@ def topk_and_eval(qp: Planes, gp: Planes, k: int, q_pids, g_pids, q_camids, g_ca
     buckets = torch.zeros(nq, max_pos + 1, dtype=torch.int32, device=dev)
     idx = torch.empty(nq, k, dtype=torch.int64, device=dev)
     dst = torch.empty(nq, k, dtype=torch.float32, device=dev)
-    ranks = torch.empty(nq, max_pos, dtype=torch.int32, device=dev)
-    ap = torch.empty(nq, dtype=torch.float64, device=dev)
     s = N.stream_ptr
     idp = dict(q_pid=d_qpid.data_ptr(), q_cam=d_qcam.data_ptr(), g_pid=d_gpid.data_ptr(),
                g_cammask=d_gmask.data_ptr(), max_pos=max_pos, overflow=ovf.data_ptr())
@@ -429,9 +444,7 @@ def topk_and_eval(qp: Planes, gp: Planes, k: int, q_pids, g_pids, q_camids, g_ca
         N.check(L.ctl_sort_key_rows(cand.data_ptr(), cand_count.data_ptr(), nq, cap.value, s()))
         N.check(L.ctl_topk_emit(cand.data_ptr(), cand_count.data_ptr(), nq, cap.value, k, idx.data_ptr(),
                                 dst.data_ptr(), ovf.data_ptr(), s()))
-        N.check(L.ctl_eval_finalize(buckets.data_ptr(), pos_count.data_ptr(), nq, max_pos, ranks.data_ptr(),
-                                    ap.data_ptr(), s()))
-    ap_h, first_h, cnt_h, ovf_h = _read_back(ranks, ap, pos_count, ovf)
+        ranks, ap_h, first_h, cnt_h, ovf_h = _finalize_and_read_back(buckets, pos_count, nq, max_pos, ovf)
     if ovf_h:
         raise OverflowError("a device-side list overflowed (exact ties at the k-th distance, or max_pos)")
     return idx, dst, _aggregate(ranks, ap_h, cnt_h, np.asarray(q_pids), ng, max_rank, first=first_h)
@@ -479,8 +492,6 @@ def topk_and_eval_sharded(qp: Planes, gp_local: Planes, k: int, ids: EncodedIds,
     cand_count, pos_count, ovf = zeros[:nq], zeros[nq: 2 * nq], zeros[2 * nq:]
     pos_keys = torch.empty(nq, mp_l, dtype=torch.int64, device=dev)
     buckets = torch.zeros(nq, mp + 1, dtype=torch.int32, device=dev)
-    ranks = torch.empty(nq, mp, dtype=torch.int32, device=dev)
-    ap = torch.empty(nq, dtype=torch.float64, device=dev)
     s = N.stream_ptr
     idp = dict(q_pid=ids.q_pid.data_ptr(), q_cam=ids.q_cam.data_ptr(), g_pid=ids.g_pid.data_ptr(),
                g_cammask=ids.g_mask.data_ptr(), overflow=ovf.data_ptr(), g_index_offset=g_index_offset)
@@ -516,8 +527,7 @@ def topk_and_eval_sharded(qp: Planes, gp_local: Planes, k: int, ids: EncodedIds,
         dist.all_gather_into_tensor(g_best, best, group=group)
         dist.all_reduce(ovf, op=dist.ReduceOp.MAX, group=group)
         idx, dst = merge_topk_keys(g_best.permute(1, 0, 2).reshape(nq, world * k_loc), int(min(k, world * k_loc)))
-        N.check(L.ctl_eval_finalize(buckets.data_ptr(), thr_count.data_ptr(), nq, mp, ranks.data_ptr(), ap.data_ptr(), s()))
-    ap_h, first_h, cnt_h, ovf_h = _read_back(ranks, ap, thr_count, ovf)
+        ranks, ap_h, first_h, cnt_h, ovf_h = _finalize_and_read_back(buckets, thr_count, nq, mp, ovf)
     if ovf_h:
         raise OverflowError("a device-side list overflowed on some rank (exact ties at the k-th distance, or max_pos)")
     return idx, dst, _aggregate(ranks, ap_h, cnt_h, np.asarray(q_pids), total_gallery, max_rank, first=first_h)

@@ -98,6 +98,11 @@ int ctl_eval_count(const void* q_planes, int64_t nq, const void* g_planes, int64
                    const int32_t* pos_count, int32_t* buckets, ctl_stream_t stream);
 int ctl_eval_finalize(const int32_t* buckets, const int32_t* pos_count, int64_t nq, int32_t max_pos, int32_t* ranks,
                       double* ap, ctl_stream_t stream);
+/* ctl_eval_finalize that also fills `packed` ([nq + 1][3] doubles: per query AP, first-hit rank (-1: none), number of
+ * positives; last row: {*overflow, 0, 0}) -- everything eval_func's final reductions (utils/eval_reid.py:86-92) need, so
+ * the host does ONE device->host copy per evaluation. */
+int ctl_eval_finalize_packed(const int32_t* buckets, const int32_t* pos_count, int64_t nq, int32_t max_pos, int32_t* ranks,
+                             double* ap, double* packed, const int32_t* overflow, ctl_stream_t stream);
 /* One generic pass of the distance GEMM with any combination of the streamed epilogues (the
  * entry points above are compositions of this one).  NULL pointers disable a feature.
  * With both top-k and evaluation wanted, TWO passes serve both:
