@@ -48,6 +48,7 @@ struct WgradParams {
   int n_items;     // cout_tiles * n_taps * cin_chunks
   int splits;      // pixel-range splits
   int cout_pad;    // cout_tiles * 128
+  int pair;        // 1: conv_wgrad_pair_kernel (work items of 256 cout, one per CTA pair)
   float* part;     // [splits][cout_pad][n_taps * cin]
 };
 
@@ -228,6 +229,193 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// CTA-pair (cta_group::2) weight gradient for the wide layers (Cout % 256 == 0, Cin % 128 == 0: layer2's expand /
+// shortcut convolutions and everything in layer3 / layer4, ~2/3 of the weight-gradient FLOPs).
+//
+// The single-CTA kernel above moves 64 KiB per 128-pixel k-step for a 128 x 128 x 128 MMA block and is bound by the
+// bytes it can keep in flight (3 stages / TMA latency ~ 66 B/clk, tensor pipe 18-21 % active).  Here a cluster of two CTAs
+// owns a 256 (cout) x BNW (cin, 128 or 256) tile: CTA r stages ITS 128 cout channels of dy (2 boxes) and ITS half of the
+// cin chunk of x (BNW/128 boxes); one tcgen05.mma.cta_group::2 per 16 pixels has M = 256, N = BNW.  Per CTA and k-step
+// that is 48-64 KiB for 2-4x the FLOPs.  Same protocol as conv_gemm_pair_kernel: both producers credit CTA 0's `full`
+// barrier, the leader's commits are multicast, both epilogues release the accumulator on CTA 0's `tmem_empty`.
+// ---------------------------------------------------------------------------------------
+static constexpr int WGP_STAGES = 3;
+static constexpr int WGP_STAGE_BYTES = 4 * WG_BOX_BYTES;  // dy: 2 boxes, x: up to 2 boxes (BNW = 256)
+static constexpr size_t WGP_SMEM = 1024 + WGP_STAGES * WGP_STAGE_BYTES + 256;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1)
+    conv_wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + WGP_STAGES * WGP_STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };                          // CTA 0 only
+  auto empty_bar = [&](int s) { return bar_base + 8u * (WGP_STAGES + s); };           // per CTA
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * WGP_STAGES + s); };       // per CTA
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * WGP_STAGES + 2 + s); };  // CTA 0 only
+  const uint32_t tmem_slot = bar_base + 8u * (2 * WGP_STAGES + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool is_leader = rank == 0;
+  const int n_clusters = (int)gridDim.x >> 1, cid = (int)blockIdx.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WGP_STAGES; ++s) {
+      mbar_init(full_bar(s), 2);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 8);  // 4 epilogue warps of each CTA
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&p.dy_map);
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.x_map[i]);
+  }
+  if (warp == 1) tmem_alloc2<512>(tmem_slot);  // two accumulator stages of up to 256 columns
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int n_units = p.n_items * p.splits;
+  const int xboxes = p.bnw / 128;  // per CTA: half of the cin chunk
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  const uint32_t stage_bytes = (2 + xboxes) * WG_BOX_BYTES;
+  auto unit_range = [&](int u, int& item, int& t0, int& t1) {
+    item = u / p.splits;
+    const int s = u - item * p.splits;
+    t0 = (int)((long long)p.m_tiles * s / p.splits);
+    t1 = (int)((long long)p.m_tiles * (s + 1) / p.splits);
+  };
+  auto item_coords = [&](int item, int& ct, int& tap, int& chunk) {
+    ct = item / (p.n_taps * p.cin_chunks);
+    const int r = item - ct * (p.n_taps * p.cin_chunks);
+    tap = r / p.cin_chunks;
+    chunk = r - tap * p.cin_chunks;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = cid; u < n_units; u += n_clusters) {
+        int item, t0, t1, ct, tapi, chunk;
+        unit_range(u, item, t0, t1);
+        item_coords(item, ct, tapi, chunk);
+        const ConvTapW tap = p.taps[tapi];
+        int img = t0 / tiles_per_img;
+        int tr = t0 - img * tiles_per_img;
+        int th = tr / p.tiles_w, tw = tr - th * p.tiles_w;
+        const int co0 = ct * 256 + (int)rank * 128;
+        const int ci0 = chunk * p.bnw + (int)rank * (p.bnw / 2);
+        for (int t = t0; t < t1; ++t) {
+          const int h0 = th * p.TH, w0 = tw * p.TW;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t dst = smem_base + stage * WGP_STAGE_BYTES;
+          if (is_leader) mbar_arrive_expect_tx(full_bar(stage), 2 * stage_bytes);
+          else mbar_arrive_cta0(full_bar(stage));
+          tma2_load_4d(dst, &p.dy_map, full_bar(stage), co0, w0, h0, img);
+          tma2_load_4d(dst + WG_BOX_BYTES, &p.dy_map, full_bar(stage), co0 + 64, w0, h0, img);
+          for (int j = 0; j < xboxes; ++j)
+            tma2_load_4d(dst + (2 + j) * WG_BOX_BYTES, &p.x_map[tap.map], full_bar(stage), ci0 + 64 * j, w0 + tap.dw,
+                         h0 + tap.dh, img);
+          if (++stage == WGP_STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+          if (++tw == p.tiles_w) {
+            tw = 0;
+            if (++th == p.tiles_h) {
+              th = 0;
+              ++img;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (is_leader && lane == 0) {
+      const uint32_t idesc = make_idesc_f16(256, (uint32_t)p.bnw) | (1u << 15) | (1u << 16);  // A and B MN-major
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int u = cid; u < n_units; u += n_clusters) {
+        int item, t0, t1;
+        unit_range(u, item, t0, t1);
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + as * 256;
+        for (int t = t0; t < t1; ++t) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a0 = smem_base + stage * WGP_STAGE_BYTES, b0 = a0 + 2 * WG_BOX_BYTES;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {  // 16 pixels (rows) per MMA
+            const uint64_t da = make_sw128_mnmajor_desc(a0 + k * 2048, WG_BOX_BYTES);
+            const uint64_t db = make_sw128_mnmajor_desc(b0 + k * 2048, WG_BOX_BYTES);
+            umma2_f16(acc, da, db, idesc, (t > t0 || k > 0) ? 1u : 0u);
+          }
+          umma2_commit_mc(empty_bar(stage), 3);
+          if (++stage == WGP_STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma2_commit_mc(tfull_bar(as), 3);
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1u;
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;  // cout inside this CTA's half == TMEM lane
+    const int ktot = p.n_taps * p.cin;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int u = cid; u < n_units; u += n_clusters) {
+      int item, t0, t1, ct, tapi, chunk;
+      unit_range(u, item, t0, t1);
+      item_coords(item, ct, tapi, chunk);
+      const int split = u - item * p.splits;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      float* dst = p.part + ((size_t)split * p.cout_pad + ct * 256 + (int)rank * 128 + row) * ktot + tapi * p.cin + chunk * p.bnw;
+      const uint32_t taddr = tmem_base + as * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
+      for (int c = 0; c < p.bnw; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(dst + c + 4 * q) =
+              make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                          __uint_as_float(r[4 * q + 3]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cta0(tempty_bar(as));
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1u;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc2<512>(tmem_base);
+  }
+}
+
 // dW[row][col] = sum over splits (fixed order) of the fp32 partial tiles; rows >= cout are padding
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, int splits, int cout_pad,
                                                            int cout, int ktot, float* __restrict__ dw) {
@@ -331,6 +519,20 @@ static int wgrad_plan(int n, int h, int w, int cin, int cout, int ksize, int str
   p->cin = cin;
   p->cout = cout;
   static const int wide_mode = [] { const char* e = getenv("CTL_WGRAD_WIDE"); return e ? atoi(e) : 0; }();
+  static const int pair_mode = [] { const char* e = getenv("CTL_WGRAD_PAIR"); return e ? atoi(e) : 1; }();
+  p->pair = (pair_mode && cout % 256 == 0 && cin % 128 == 0) ? 1 : 0;
+  if (p->pair) {
+    // CTA-pair kernel: 256 cout x (256 | 128) cin per work item, one work item per CLUSTER
+    p->bnw = cin % 256 == 0 ? 256 : 128;
+    p->cin_chunks = cin / p->bnw;
+    p->cout_tiles = cout / 256;
+    p->cout_pad = cout;
+    p->n_items = p->cout_tiles * p->n_taps * p->cin_chunks;
+    const int clusters = sm_count() / 2;
+    const int want = (2 * clusters + p->n_items - 1) / p->n_items;
+    p->splits = std::max(1, std::min(want, p->m_tiles));
+    return Ho * 65536 + Wo;
+  }
   p->bnw = (wide_mode && cin % 256 == 0) ? 256 : (cin % 128 == 0 ? 128 : 64);
   p->cin_chunks = cin / p->bnw;
   p->cout_tiles = (cout + 127) / 128;
@@ -1129,11 +1331,15 @@ int ctl_conv2d_wgrad_nhwc_f16_ex(const void* x, int32_t n, int32_t h, int32_t w,
                                   (int)WgCfg<false>::SMEM));
     CTL_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)WgCfg<true>::SMEM));
+    CTL_CUDA(cudaFuncSetAttribute(conv_wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WGP_SMEM));
     attr_set = true;
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = std::min(p.n_items * p.splits, sm_count());
-  if (p.bnw == 256)
+  if (p.pair) {
+    const int clusters = std::min(p.n_items * p.splits, sm_count() / 2);
+    CTL_CUDA(launch_k(conv_wgrad_pair_kernel, dim3(2 * clusters), dim3(WG_THREADS), WGP_SMEM, st, p));
+  } else if (p.bnw == 256)
     CTL_CUDA(launch_k(conv_wgrad_kernel<true>, dim3(grid), dim3(WG_THREADS), WgCfg<true>::SMEM, st, p));
   else
     CTL_CUDA(launch_k(conv_wgrad_kernel<false>, dim3(grid), dim3(WG_THREADS), WgCfg<false>::SMEM, st, p));

@@ -15,7 +15,11 @@ WGRAD_SHAPES = [
     (2, 16, 16, 128, 128, 3, 2),
     (2, 12, 20, 64, 256, 1, 2),
     (5, 8, 4, 512, 192, 3, 1),
-    (4, 32, 16, 128, 512, 1, 1),
+    (4, 32, 16, 128, 512, 1, 1),      # CTA-pair kernel: cout % 256 == 0, cin = 128 (one x box per CTA)
+    (3, 16, 8, 256, 256, 3, 1),       # CTA-pair kernel, 3x3, cin chunk of 256 (two x boxes per CTA)
+    (6, 16, 8, 1024, 512, 1, 1),      # CTA-pair kernel: several cin chunks and cout tiles per cluster
+    (2, 32, 16, 256, 512, 1, 2),      # CTA-pair kernel on a strided shortcut (parity views)
+    (2, 20, 20, 512, 256, 3, 1),      # CTA-pair kernel, 320x320 geometry: partial pixel tiles
 ]
 
 
@@ -49,6 +53,12 @@ def test_conv_wgrad(shape):
                                         nbytes, dw2.data_ptr(), N.stream_ptr()))
     torch.cuda.synchronize()
     assert torch.equal(dw, dw2)
+    # the training engine's form: un-scaled, in torch.nn.Conv2d.weight's own layout [cout][cin][k][k]
+    dw3 = torch.full((cout, cin, k, k), float("nan"), device="cuda")
+    N.check(L.ctl_conv2d_wgrad_nhwc_f16_ex(xd.data_ptr(), n, h, w, cin, dyd.data_ptr(), cout, k, stride, ws.data_ptr(),
+                                           nbytes, dw3.data_ptr(), 0.25, 1, N.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(dw3, dw.permute(0, 3, 1, 2) * 0.25)
 
 
 @pytest.mark.parametrize("rows,c,relu,res", [(1000, 64, 1, 0), (4096, 256, 1, 1), (333, 2048, 0, 0), (20000, 128, 1, 1)])
