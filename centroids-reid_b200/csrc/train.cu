@@ -48,7 +48,6 @@ struct WgradParams {
   int n_items;     // cout_tiles * n_taps * cin_chunks
   int splits;      // pixel-range splits
   int cout_pad;    // cout_tiles * 128
-  int pair;        // 1: conv_wgrad_pair_kernel (work items of 256 cout, one per CTA pair)
   float* part;     // [splits][cout_pad][n_taps * cin]
 };
 
@@ -229,193 +228,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
   }
 }
 
-// ---------------------------------------------------------------------------------------
-// CTA-pair (cta_group::2) weight gradient for the wide layers (Cout % 256 == 0, Cin % 128 == 0: layer2's expand /
-// shortcut convolutions and everything in layer3 / layer4, ~2/3 of the weight-gradient FLOPs).
-//
-// The single-CTA kernel above moves 64 KiB per 128-pixel k-step for a 128 x 128 x 128 MMA block and is bound by the
-// bytes it can keep in flight (3 stages / TMA latency ~ 66 B/clk, tensor pipe 18-21 % active).  Here a cluster of two CTAs
-// owns a 256 (cout) x BNW (cin, 128 or 256) tile: CTA r stages ITS 128 cout channels of dy (2 boxes) and ITS half of the
-// cin chunk of x (BNW/128 boxes); one tcgen05.mma.cta_group::2 per 16 pixels has M = 256, N = BNW.  Per CTA and k-step
-// that is 48-64 KiB for 2-4x the FLOPs.  Same protocol as conv_gemm_pair_kernel: both producers credit CTA 0's `full`
-// barrier, the leader's commits are multicast, both epilogues release the accumulator on CTA 0's `tmem_empty`.
-// ---------------------------------------------------------------------------------------
-static constexpr int WGP_STAGES = 3;
-static constexpr int WGP_STAGE_BYTES = 4 * WG_BOX_BYTES;  // dy: 2 boxes, x: up to 2 boxes (BNW = 256)
-static constexpr size_t WGP_SMEM = 1024 + WGP_STAGES * WGP_STAGE_BYTES + 256;
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1)
-    conv_wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + WGP_STAGES * WGP_STAGE_BYTES;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };                          // CTA 0 only
-  auto empty_bar = [&](int s) { return bar_base + 8u * (WGP_STAGES + s); };           // per CTA
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * WGP_STAGES + s); };       // per CTA
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * WGP_STAGES + 2 + s); };  // CTA 0 only
-  const uint32_t tmem_slot = bar_base + 8u * (2 * WGP_STAGES + 4);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const bool is_leader = rank == 0;
-  const int n_clusters = (int)gridDim.x >> 1, cid = (int)blockIdx.x >> 1;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < WGP_STAGES; ++s) {
-      mbar_init(full_bar(s), 2);
-      mbar_init(empty_bar(s), 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 8);  // 4 epilogue warps of each CTA
-    }
-    fence_barrier_init();
-    tma_prefetch_desc(&p.dy_map);
-    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.x_map[i]);
-  }
-  if (warp == 1) tmem_alloc2<512>(tmem_slot);  // two accumulator stages of up to 256 columns
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  tc_fence_after();
-  pdl_launch_dependents();
-  pdl_wait();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-
-  const int n_units = p.n_items * p.splits;
-  const int xboxes = p.bnw / 128;  // per CTA: half of the cin chunk
-  const int tiles_per_img = p.tiles_w * p.tiles_h;
-  const uint32_t stage_bytes = (2 + xboxes) * WG_BOX_BYTES;
-  auto unit_range = [&](int u, int& item, int& t0, int& t1) {
-    item = u / p.splits;
-    const int s = u - item * p.splits;
-    t0 = (int)((long long)p.m_tiles * s / p.splits);
-    t1 = (int)((long long)p.m_tiles * (s + 1) / p.splits);
-  };
-  auto item_coords = [&](int item, int& ct, int& tap, int& chunk) {
-    ct = item / (p.n_taps * p.cin_chunks);
-    const int r = item - ct * (p.n_taps * p.cin_chunks);
-    tap = r / p.cin_chunks;
-    chunk = r - tap * p.cin_chunks;
-  };
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int u = cid; u < n_units; u += n_clusters) {
-        int item, t0, t1, ct, tapi, chunk;
-        unit_range(u, item, t0, t1);
-        item_coords(item, ct, tapi, chunk);
-        const ConvTapW tap = p.taps[tapi];
-        int img = t0 / tiles_per_img;
-        int tr = t0 - img * tiles_per_img;
-        int th = tr / p.tiles_w, tw = tr - th * p.tiles_w;
-        const int co0 = ct * 256 + (int)rank * 128;
-        const int ci0 = chunk * p.bnw + (int)rank * (p.bnw / 2);
-        for (int t = t0; t < t1; ++t) {
-          const int h0 = th * p.TH, w0 = tw * p.TW;
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t dst = smem_base + stage * WGP_STAGE_BYTES;
-          if (is_leader) mbar_arrive_expect_tx(full_bar(stage), 2 * stage_bytes);
-          else mbar_arrive_cta0(full_bar(stage));
-          tma2_load_4d(dst, &p.dy_map, full_bar(stage), co0, w0, h0, img);
-          tma2_load_4d(dst + WG_BOX_BYTES, &p.dy_map, full_bar(stage), co0 + 64, w0, h0, img);
-          for (int j = 0; j < xboxes; ++j)
-            tma2_load_4d(dst + (2 + j) * WG_BOX_BYTES, &p.x_map[tap.map], full_bar(stage), ci0 + 64 * j, w0 + tap.dw,
-                         h0 + tap.dh, img);
-          if (++stage == WGP_STAGES) {
-            stage = 0;
-            phase ^= 1u;
-          }
-          if (++tw == p.tiles_w) {
-            tw = 0;
-            if (++th == p.tiles_h) {
-              th = 0;
-              ++img;
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (is_leader && lane == 0) {
-      const uint32_t idesc = make_idesc_f16(256, (uint32_t)p.bnw) | (1u << 15) | (1u << 16);  // A and B MN-major
-      int stage = 0, as = 0;
-      uint32_t phase = 0, aphase = 0;
-      for (int u = cid; u < n_units; u += n_clusters) {
-        int item, t0, t1;
-        unit_range(u, item, t0, t1);
-        mbar_wait(tempty_bar(as), aphase ^ 1u);
-        tc_fence_after();
-        const uint32_t acc = tmem_base + as * 256;
-        for (int t = t0; t < t1; ++t) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t a0 = smem_base + stage * WGP_STAGE_BYTES, b0 = a0 + 2 * WG_BOX_BYTES;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {  // 16 pixels (rows) per MMA
-            const uint64_t da = make_sw128_mnmajor_desc(a0 + k * 2048, WG_BOX_BYTES);
-            const uint64_t db = make_sw128_mnmajor_desc(b0 + k * 2048, WG_BOX_BYTES);
-            umma2_f16(acc, da, db, idesc, (t > t0 || k > 0) ? 1u : 0u);
-          }
-          umma2_commit_mc(empty_bar(stage), 3);
-          if (++stage == WGP_STAGES) {
-            stage = 0;
-            phase ^= 1u;
-          }
-        }
-        umma2_commit_mc(tfull_bar(as), 3);
-        if (++as == 2) {
-          as = 0;
-          aphase ^= 1u;
-        }
-      }
-    }
-  } else {
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;  // cout inside this CTA's half == TMEM lane
-    const int ktot = p.n_taps * p.cin;
-    int as = 0;
-    uint32_t aphase = 0;
-    for (int u = cid; u < n_units; u += n_clusters) {
-      int item, t0, t1, ct, tapi, chunk;
-      unit_range(u, item, t0, t1);
-      item_coords(item, ct, tapi, chunk);
-      const int split = u - item * p.splits;
-      mbar_wait(tfull_bar(as), aphase);
-      tc_fence_after();
-      float* dst = p.part + ((size_t)split * p.cout_pad + ct * 256 + (int)rank * 128 + row) * ktot + tapi * p.cin + chunk * p.bnw;
-      const uint32_t taddr = tmem_base + as * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
-      for (int c = 0; c < p.bnw; c += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + c, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<float4*>(dst + c + 4 * q) =
-              make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
-                          __uint_as_float(r[4 * q + 3]));
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cta0(tempty_bar(as));
-      if (++as == 2) {
-        as = 0;
-        aphase ^= 1u;
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  if (warp == 1) {
-    __syncwarp();
-    tc_fence_after();
-    tmem_dealloc2<512>(tmem_base);
-  }
-}
-
 // dW[row][col] = sum over splits (fixed order) of the fp32 partial tiles; rows >= cout are padding
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, int splits, int cout_pad,
                                                            int cout, int ktot, float* __restrict__ dw) {
@@ -519,20 +331,6 @@ static int wgrad_plan(int n, int h, int w, int cin, int cout, int ksize, int str
   p->cin = cin;
   p->cout = cout;
   static const int wide_mode = [] { const char* e = getenv("CTL_WGRAD_WIDE"); return e ? atoi(e) : 0; }();
-  static const int pair_mode = [] { const char* e = getenv("CTL_WGRAD_PAIR"); return e ? atoi(e) : 1; }();
-  p->pair = (pair_mode && cout % 256 == 0 && cin % 128 == 0) ? 1 : 0;
-  if (p->pair) {
-    // CTA-pair kernel: 256 cout x (256 | 128) cin per work item, one work item per CLUSTER
-    p->bnw = cin % 256 == 0 ? 256 : 128;
-    p->cin_chunks = cin / p->bnw;
-    p->cout_tiles = cout / 256;
-    p->cout_pad = cout;
-    p->n_items = p->cout_tiles * p->n_taps * p->cin_chunks;
-    const int clusters = sm_count() / 2;
-    const int want = (2 * clusters + p->n_items - 1) / p->n_items;
-    p->splits = std::max(1, std::min(want, p->m_tiles));
-    return Ho * 65536 + Wo;
-  }
   p->bnw = (wide_mode && cin % 256 == 0) ? 256 : (cin % 128 == 0 ? 128 : 64);
   p->cin_chunks = cin / p->bnw;
   p->cout_tiles = (cout + 127) / 128;
@@ -552,6 +350,11 @@ static int wgrad_plan(int n, int h, int w, int cin, int cout, int ksize, int str
 // =======================================================================================
 static constexpr int BN_THREADS = 256;
 static constexpr int BN_MAX_BLOCKS = 592;  // 148 SMs x 4
+
+static int bn_batched() {
+  static const int v = [] { const char* e = getenv("CTL_BN_FINALIZE_BATCHED"); return e ? atoi(e) : 1; }();
+  return v;
+}
 
 struct BnGeom {
   int groups;         // C / 8
@@ -659,25 +462,37 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const __half* __re
 // Sum of the per-block partials of 32 channels: 32 warps split the block index (stride 32), partial sums are combined in
 // a fixed order (deterministic).  Returns the two totals of channel `c` to the threads with part == 0.
 __device__ __forceinline__ void bn_sum_partials(const float* __restrict__ part, int blocks, int C, int c, int part_id,
-                                                double (*sh)[2][32], double& s0, double& s1) {  // sh[32][2][32]
-  // all of this thread's partials are loaded FIRST (independent loads: one memory round trip instead of a chain of up to
-  // 19 dependent ones -- the finalize kernels were pure latency, ~15 us each, 127 launches per training step) and then
-  // summed in the same fixed order as before (bit-identical results)
-  constexpr int MAXQ = (BN_MAX_BLOCKS + 31) / 32;
-  float va[MAXQ], vb[MAXQ];
-#pragma unroll
-  for (int q = 0; q < MAXQ; ++q) {
-    const int blk = part_id + 32 * q;
-    const bool ok = c < C && blk < blocks;
-    va[q] = ok ? part[(size_t)blk * 2 * C + c] : 0.f;
-    vb[q] = ok ? part[(size_t)blk * 2 * C + C + c] : 0.f;
-  }
+                                                double (*sh)[2][32], double& s0, double& s1, int batched) {  // sh[32][2][32]
+  // the partials are loaded in groups of 4 INDEPENDENT loads (5 memory round trips instead of a chain of up to 19
+  // dependent ones -- the finalize kernels were pure latency, ~15 us each, 127 launches per training step) and summed in
+  // the same fixed order as before (bit-identical results).  A first version loaded all 19 at once: 64 registers x 1024
+  // threads = the whole register file of an SM, and the kernel showed sporadic 20-80 ms stalls -- keep the footprint low.
+  constexpr int MAXQ = (BN_MAX_BLOCKS + 31) / 32, GRP = 4;
   double a = 0.0, b = 0.0;
+  if (!batched) {  // round-1 form: a chain of dependent loads (CTL_BN_FINALIZE_BATCHED=0)
+    if (c < C)
+      for (int blk = part_id; blk < blocks; blk += 32) {
+        a += (double)part[(size_t)blk * 2 * C + c];
+        b += (double)part[(size_t)blk * 2 * C + C + c];
+      }
+  } else {
+#pragma unroll 1
+    for (int q0 = 0; q0 < MAXQ; q0 += GRP) {
+      float va[GRP], vb[GRP];
 #pragma unroll
-  for (int q = 0; q < MAXQ; ++q) {
-    if (part_id + 32 * q < blocks) {
-      a += (double)va[q];
-      b += (double)vb[q];
+      for (int j = 0; j < GRP; ++j) {
+        const int blk = part_id + 32 * (q0 + j);
+        const bool ok = c < C && blk < blocks;
+        va[j] = ok ? part[(size_t)blk * 2 * C + c] : 0.f;
+        vb[j] = ok ? part[(size_t)blk * 2 * C + C + c] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < GRP; ++j) {
+        if (c < C && part_id + 32 * (q0 + j) < blocks) {
+          a += (double)va[j];
+          b += (double)vb[j];
+        }
+      }
     }
   }
   sh[part_id][0][threadIdx.x & 31] = a;
@@ -698,13 +513,13 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
                                                           float eps, float momentum, float* __restrict__ running_mean,
                                                           float* __restrict__ running_var, float* __restrict__ mean,
                                                           float* __restrict__ invstd, float* __restrict__ scale,
-                                                          float* __restrict__ shift) {
+                                                          float* __restrict__ shift, int batched) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ double sh[32][2][32];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31), part_id = threadIdx.x >> 5;
   double s, ss;
-  bn_sum_partials(part, blocks, C, c, part_id, sh, s, ss);
+  bn_sum_partials(part, blocks, C, c, part_id, sh, s, ss, batched);
   if (part_id != 0 || c >= C) return;
   const double m = s / count;
   double var = ss / count - m * m;
@@ -821,13 +636,13 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __re
                                                               const float* __restrict__ gamma, const float* __restrict__ mean,
                                                               const float* __restrict__ invstd, float grad_unscale,
                                                               float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                              float* __restrict__ coef) {
+                                                              float* __restrict__ coef, int batched) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ double sh[32][2][32];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31), part_id = threadIdx.x >> 5;
   double sg, sgx;
-  bn_sum_partials(part, blocks, C, c, part_id, sh, sg, sgx);
+  bn_sum_partials(part, blocks, C, c, part_id, sh, sg, sgx, batched);
   if (part_id != 0 || c >= C) return;
   dbeta[c] = (float)sg * grad_unscale;
   dgamma[c] = (float)sgx * grad_unscale;
@@ -1331,15 +1146,11 @@ int ctl_conv2d_wgrad_nhwc_f16_ex(const void* x, int32_t n, int32_t h, int32_t w,
                                   (int)WgCfg<false>::SMEM));
     CTL_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)WgCfg<true>::SMEM));
-    CTL_CUDA(cudaFuncSetAttribute(conv_wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WGP_SMEM));
     attr_set = true;
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = std::min(p.n_items * p.splits, sm_count());
-  if (p.pair) {
-    const int clusters = std::min(p.n_items * p.splits, sm_count() / 2);
-    CTL_CUDA(launch_k(conv_wgrad_pair_kernel, dim3(2 * clusters), dim3(WG_THREADS), WGP_SMEM, st, p));
-  } else if (p.bnw == 256)
+  if (p.bnw == 256)
     CTL_CUDA(launch_k(conv_wgrad_kernel<true>, dim3(grid), dim3(WG_THREADS), WgCfg<true>::SMEM, st, p));
   else
     CTL_CUDA(launch_k(conv_wgrad_kernel<false>, dim3(grid), dim3(WG_THREADS), WgCfg<false>::SMEM, st, p));
@@ -1399,7 +1210,8 @@ int ctl_bn_train_forward_nhwc_f16(const void* y, int64_t rows, int32_t c, int32_
   CTL_CUDA(launch_k(bn_stats_kernel, dim3(g.blocks), dim3(BN_THREADS), sm, st, static_cast<const __half*>(y), (long long)rows,
                     (int)c, (int)pitch, g.rows_per_block, g.lanes, part));
   CTL_CUDA(launch_k(bn_finalize_kernel, dim3((c + 31) / 32), dim3(1024), 0, st, (const float*)part, g.blocks, (int)c,
-                    (double)rows, gamma, beta, eps, momentum, running_mean, running_var, save_mean, save_invstd, scale, shift));
+                    (double)rows, gamma, beta, eps, momentum, running_mean, running_var, save_mean, save_invstd, scale, shift,
+                    bn_batched()));
   CTL_CUDA(launch_k(bn_apply_kernel, dim3(row_grid(rows, g.lanes)), dim3(BN_THREADS), 0, st, static_cast<const __half*>(y),
                     (long long)rows, (int)c, (int)pitch, g.lanes, (const float*)scale, (const float*)shift, static_cast<const __half*>(residual),
                     (int)relu, static_cast<__half*>(out)));
@@ -1425,7 +1237,7 @@ int ctl_bn_train_backward_nhwc_f16(const void* dz, const void* z, const void* y,
                     static_cast<const __half*>(z), static_cast<const __half*>(y), (long long)rows, (int)c, (int)pitch, g.rows_per_block,
                     g.lanes, save_mean, save_invstd, static_cast<__half*>(g_out), part));
   CTL_CUDA(launch_k(bn_bwd_finalize_kernel, dim3((c + 31) / 32), dim3(1024), 0, st, (const float*)part, g.blocks, (int)c,
-                    (double)rows, gamma, save_mean, save_invstd, grad_unscale, dgamma, dbeta, coef));
+                    (double)rows, gamma, save_mean, save_invstd, grad_unscale, dgamma, dbeta, coef, bn_batched()));
   const __half* gsrc = z ? static_cast<const __half*>(g_out) : static_cast<const __half*>(dz);
   CTL_CUDA(launch_k(bn_bwd_apply_kernel, dim3(row_grid(rows, g.lanes)), dim3(BN_THREADS), 0, st, gsrc, static_cast<const __half*>(y),
                     (long long)rows, (int)c, (int)pitch, g.lanes, (const float*)coef, static_cast<__half*>(dy)));

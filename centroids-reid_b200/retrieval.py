@@ -107,13 +107,48 @@ def topk(qp: Planes, gp: Planes, k: int, g_index_offset: int = 0):
     return idx, dst, ovf
 
 
-def topk_similar(q: torch.Tensor, g: torch.Tensor, k: int = 100, dist: str = "euclidean", normalize: bool = False):
-    """inference/get_similar.py:104-128 without the distance matrix: (indices, distances)."""
-    qp, gp = build_planes(q, dist, normalize), build_planes(g, dist, normalize)
-    idx, dst, ovf = topk(qp, gp, k)
-    if int(ovf.item()) != 0:
-        raise OverflowError("top-k candidate capacity exceeded (too many exact ties at the k-th distance)")
+def topk_dense(q: torch.Tensor, g: torch.Tensor, k: int, dist: str = "euclidean", normalize: bool = False,
+               chunk_bytes: int = 1 << 30):
+    """The k smallest distances per query from MATERIALISED rows of the distance matrix (the reference's own
+    dist + argsort + `[:, :topk]`, inference/get_similar.py:104-128), chunked over queries so the matrix slice stays under
+    `chunk_bytes`: the general path for every (gallery size, k) the streamed kernel's plan does not cover and for
+    degenerate inputs (hundreds of exact ties at the k-th distance).  Same canonical ascending (distance, index) order:
+    rows of packed integer keys are sorted."""
+    nq, ng = q.shape[0], g.shape[0]
+    k = int(min(k, ng))
+    gp = build_planes(g, dist, normalize)
+    rows = max(1, int(chunk_bytes // (12 * ng)))
+    col = torch.arange(ng, device=q.device, dtype=torch.int64)[None, :]
+    idx = torch.empty(nq, k, dtype=torch.int64, device=q.device)
+    dst = torch.empty(nq, k, dtype=torch.float32, device=q.device)
+    flip = -(1 << 63)  # unsigned key order == signed order of key ^ 2^63
+    for lo in range(0, nq, rows):
+        qp = build_planes(q[lo:lo + rows], dist, normalize)
+        d = torch.empty(qp.n, ng, dtype=torch.float32, device=q.device)
+        with torch.cuda.device(q.device):
+            N.check(N.lib().ctl_dist_matrix(qp.ptr, qp.n, gp.ptr, ng, qp.d, qp.flags, d.data_ptr(), ng, N.stream_ptr()))
+        keys = (pack_keys(d, col.expand(qp.n, ng)) ^ flip).topk(k, dim=1, largest=False, sorted=True).values ^ flip
+        idx[lo:lo + rows] = keys & 0xFFFFFFFF
+        dst[lo:lo + rows] = torch.gather(d, 1, idx[lo:lo + rows])
     return idx, dst
+
+
+def topk_similar(q: torch.Tensor, g: torch.Tensor, k: int = 100, dist: str = "euclidean", normalize: bool = False):
+    """inference/get_similar.py:104-128 without the distance matrix: (indices, distances).  The reference's
+    `argsort[:, :topk]` works for every topk; so does this: the streamed two-pass kernel where its plan applies
+    (ctl_topk_plan: k <= ceil(ng / 16) merged column groups, candidate capacity <= 16384), otherwise -- and when more rows
+    than the candidate capacity tie at the threshold -- the materialised path `topk_dense`."""
+    import ctypes as C
+
+    k = int(min(k, g.shape[0]))
+    a, b, c, d_ = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+    rc = N.lib().ctl_topk_plan(g.shape[0], k, C.byref(a), C.byref(b), C.byref(c), C.byref(d_))
+    if rc == 0 and N.lib().ctl_topk_workspace_bytes(q.shape[0], g.shape[0], k) > 0:
+        qp, gp = build_planes(q, dist, normalize), build_planes(g, dist, normalize)
+        idx, dst, ovf = topk(qp, gp, k)
+        if int(ovf.item()) == 0:
+            return idx, dst
+    return topk_dense(q, g, k, dist, normalize)
 
 
 # ----------------------------------------------------------------------------------------

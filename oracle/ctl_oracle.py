@@ -9,7 +9,7 @@ restatement is pinned against outputs of the *reference itself*, executed in the
 container through ``oracle/ref_import.py`` by ``oracle/make_golden.py``; the resulting
 vectors are committed under ``tests/golden/`` and checked by ``tests/test_oracle_golden.py``
 (CPU, ``-m "not gpu"``), and -- when /root/reference is mounted -- directly against the
-live reference by ``tests/test_oracle_vs_reference.py``.
+live reference by ``tests/test_oracle_golden.py``.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl
 reference`` legs may import this module.  The product (``centroids-reid_b200``) never does.

@@ -200,3 +200,29 @@ def test_eval_many_positives_per_query(R):
     assert np.array_equal(res.cmc, cmc_o)
     np.testing.assert_allclose(res.mAP, map_o, rtol=1e-12)
     np.testing.assert_allclose(res.single_performance[:, 2].astype(np.float64), single_o[:, 2].astype(np.float64), rtol=1e-12)
+
+
+def test_topk_similar_has_no_capability_cliffs():
+    """the reference's `argsort[:, :topk]` works for every topk and every input; topk_similar / get_similar must
+    too.  (a) a 6000-row gallery with topk = 500 and topk = 1500 -- outside the streamed kernel's plan (k <= ceil(ng/16)
+    merged groups) -> the materialised path; (b) 3000 identical gallery rows -- thousands of exact ties at the k-th
+    distance overflow the candidate list -> the materialised path; both in the canonical (distance, index) order."""
+    from ctl_b200 import retrieval as R
+    from ctl_b200.inference.inference_utils import get_similar
+
+    g = torch.Generator().manual_seed(3)
+    q = torch.randn(40, 256, generator=g)
+    gal = torch.randn(6000, 256, generator=g)
+    d = O.get_euclidean(q.double(), gal.double()).numpy()
+    for k in (500, 1500):
+        idx, dst = R.topk_similar(q.cuda(), gal.cuda(), k)
+        dm = R.dist_matrix(q.cuda(), gal.cuda()).cpu().numpy()
+        want = np.argsort(dm, axis=1, kind="stable")[:, :k]
+        assert np.array_equal(idx.cpu().numpy(), want)
+        assert np.array_equal(dst.cpu().numpy(), np.take_along_axis(dm, want, 1))
+        assert float(np.abs(np.take_along_axis(d, want, 1) - dst.cpu().numpy()).max()) < 1e-3
+    same = torch.randn(1, 128, generator=g).expand(3000, 128).contiguous()
+    idx, dst = R.topk_similar(torch.randn(5, 128, generator=g).cuda(), same.cuda(), 100)
+    assert np.array_equal(idx.cpu().numpy(), np.tile(np.arange(100), (5, 1)))  # all tied: ascending gallery index
+    out = get_similar(q.numpy(), [f"q{i}" for i in range(40)], gal.numpy(), np.asarray([f"g{i}" for i in range(6000)]), topk=700)
+    assert out["q3"]["indices"].shape == (700,) and out["q3"]["paths"][0] == f"g{int(out['q3']['indices'][0])}"

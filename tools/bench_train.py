@@ -12,8 +12,9 @@ params = {k: v.clone().cuda() for k, v in sd.items() if v.is_floating_point()}
 tr = TrunkTrainer("cuda", graphs=os.environ.get("CTL_TRAIN_GRAPHS", "1") == "1")
 x = torch.randn(bs, 3, 256, 128, device="cuda")
 df = torch.randn(bs, 2048, device="cuda") * 1e-3
-for _ in range(3):
-    tr.forward(x, params); tr.backward(df)
+for w_ in range(3):
+    tr.forward(x, params); torch.cuda.synchronize(); print(f"warm {w_}: forward done", flush=True)
+    tr.backward(df); torch.cuda.synchronize(); print(f"warm {w_}: backward done", flush=True)
 torch.cuda.synchronize()
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
 t0 = time.perf_counter()
