@@ -15,11 +15,11 @@ WGRAD_SHAPES = [
     (2, 16, 16, 128, 128, 3, 2),
     (2, 12, 20, 64, 256, 1, 2),
     (5, 8, 4, 512, 192, 3, 1),
-    (4, 32, 16, 128, 512, 1, 1),      # CTA-pair kernel: cout % 256 == 0, cin = 128 (one x box per CTA)
-    (3, 16, 8, 256, 256, 3, 1),       # CTA-pair kernel, 3x3, cin chunk of 256 (two x boxes per CTA)
-    (6, 16, 8, 1024, 512, 1, 1),      # CTA-pair kernel: several cin chunks and cout tiles per cluster
-    (2, 32, 16, 256, 512, 1, 2),      # CTA-pair kernel on a strided shortcut (parity views)
-    (2, 20, 20, 512, 256, 3, 1),      # CTA-pair kernel, 320x320 geometry: partial pixel tiles
+    (4, 32, 16, 128, 512, 1, 1),      # wide layers (layer2 expand)
+    (3, 16, 8, 256, 256, 3, 1),       # layer3 3x3
+    (6, 16, 8, 1024, 512, 1, 1),      # several cin chunks and cout tiles per CTA
+    (2, 32, 16, 256, 512, 1, 2),      # strided shortcut (parity views)
+    (2, 20, 20, 512, 256, 3, 1),      # 320x320 geometry: partial pixel tiles
 ]
 
 
