@@ -1015,35 +1015,41 @@ __global__ void __launch_bounds__(256) upsample2_zero_kernel(const __half* __res
 }
 
 // im2col of the stem for its weight gradient: out[pixel][k], k = (c*7 + r)*8 + s (s = 7 and k >= 168 zero): the K
-// ordering of ctl_stem_conv7x7_tc's weight operand, fp16
+// ordering of ctl_stem_conv7x7_tc's weight operand, fp16.
+// One block per (image, output row): the 7 x 3 input rows that feed this output row are staged ONCE in shared memory
+// (coalesced loads, zero outside the image, 3 zero columns of left border), then every thread assembles 16-byte chunks
+// from 7 consecutive shared-memory words.  Round 1 read the 7 taps of every chunk straight from global memory (42
+// scattered 4-byte loads per thread: 0.84 ms at bs 256, an LSU-bound kernel that only writes 805 MB).
+static constexpr int IM2COL_MAXW = 512;  // widest input row staged: 21 x 521 floats stay under the 48 KB default
+
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, int N, int H, int W, int Ho, int Wo,
                                                           __half* __restrict__ out) {
   pdl_launch_dependents();
   pdl_wait();
-  const long long total = (long long)N * Ho * Wo * 24;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int chunk = (int)(i % 24);
-    long long t = i / 24;
-    const int ox = (int)(t % Wo);
-    t /= Wo;
-    const int oy = (int)(t % Ho);
-    const int n = (int)(t / Ho);
+  extern __shared__ float srow[];  // [21][pitch], pitch = (W + 8) | 1: srow[cr][3 + xx] = x[c][2 oy - 3 + r][xx]
+  const int pitch = (W + 8) | 1;  // odd pitch: the 24 chunks of one pixel hit distinct banks
+  const int n = blockIdx.x / Ho, oy = blockIdx.x - n * Ho;
+  for (int i = threadIdx.x; i < 21 * pitch; i += blockDim.x) {
+    const int cr = i / pitch, col = i - cr * pitch;
+    const int c = cr / 7, r = cr - c * 7;
+    const int yy = 2 * oy - 3 + r, xx = col - 3;
+    float v = 0.f;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = x[(((size_t)n * 3 + c) * H + yy) * W + xx];
+    srow[i] = v;
+  }
+  __syncthreads();
+  __half* orow = out + ((size_t)n * Ho + oy) * Wo * 192;
+  for (int i = threadIdx.x; i < Wo * 24; i += blockDim.x) {
+    const int ox = i / 24, chunk = i - ox * 24;
     float f[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = 0.f;
     if (chunk < 21) {
-      const int c = chunk / 7, r = chunk - c * 7;
-      const int yy = 2 * oy - 3 + r;
-      if (yy >= 0 && yy < H) {
-        const float* row = x + (((size_t)n * 3 + c) * H + yy) * W;
+      const float* src = srow + chunk * pitch + 2 * ox;  // column 2 ox - 3 + s  ->  index 3 + 2 ox - 3 + s
 #pragma unroll
-        for (int s = 0; s < 7; ++s) {
-          const int xx = 2 * ox - 3 + s;
-          if (xx >= 0 && xx < W) f[s] = row[xx];
-        }
-      }
+      for (int sft = 0; sft < 7; ++sft) f[sft] = src[sft];
     }
-    *reinterpret_cast<uint4*>(out + i * 8) = pack8(f);
+    *reinterpret_cast<uint4*>(orow + (size_t)i * 8) = pack8(f);
   }
 }
 
@@ -1332,9 +1338,11 @@ int ctl_stem_im2col_f16(const float* x_nchw, int32_t n, int32_t h, int32_t w, vo
   CTL_CHECK_ARG(x_nchw && out && n >= 1 && h >= 7 && w >= 7, "bad arguments");
   int rc = ctl_device_check();
   if (rc) return rc;
+  CTL_CHECK_ARG(w <= IM2COL_MAXW, "stem im2col stages whole input rows: W=%d exceeds %d", w, IM2COL_MAXW);
   const int Ho = (h + 6 - 7) / 2 + 1, Wo = (w + 6 - 7) / 2 + 1;
-  CTL_CUDA(launch_k(stem_im2col_kernel, dim3(ew_grid((long long)n * Ho * Wo * 24)), dim3(256), 0, (cudaStream_t)stream, x_nchw,
-                    (int)n, (int)h, (int)w, Ho, Wo, static_cast<__half*>(out)));
+  const size_t smem = (size_t)21 * ((w + 8) | 1) * sizeof(float);
+  CTL_CUDA(launch_k(stem_im2col_kernel, dim3((unsigned)(n * Ho)), dim3(256), smem, (cudaStream_t)stream, x_nchw, (int)n, (int)h,
+                    (int)w, Ho, Wo, static_cast<__half*>(out)));
   return 0;
 }
 
