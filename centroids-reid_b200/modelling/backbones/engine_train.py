@@ -365,3 +365,68 @@ class TrunkTrainer:
             dw = self._wgrad(col, (n, h, w), dy0, 64, 1, 1)  # [64][1][1][192]
             grads["conv1.weight"] = dw.reshape(64, 192)[:, :168].reshape(64, 3, 7, 8)[..., :7].mul(1.0 / self.grad_scale)
         return grads
+
+
+class NativeTrainer:
+    """The same train-mode trunk with the LAYER GRAPH behind the C ABI (ctl_trainer_create / ctl_trainer_bind /
+    ctl_train_forward / ctl_train_backward, csrc/trunk_train.cu): what a non-Python host binds.  `params` as in
+    TrunkTrainer; gradients land in fp32 tensors this object owns (`grads`, the parameters' own layouts).
+    Bit-identical to TrunkTrainer (tests/test_train_gpu.py::test_native_trainer_handle_matches_trunk_trainer)."""
+
+    def __init__(self, params: Dict[str, torch.Tensor], device, last_stride: int = 1, ibn: bool = False,
+                 grad_scale: float = 1024.0, momentum: float = 0.1):
+        import ctypes as C
+
+        self.device = torch.device(device)
+        self.grad_scale = float(grad_scale)
+        self._h = C.c_void_p()
+        N.check(N.lib().ctl_trainer_create(C.byref(self._h), int(ibn), int(last_stride), float(momentum)))
+        self._ws = None
+        self.bind(params)
+
+    def bind(self, params: Dict[str, torch.Tensor]):
+        for k, v in params.items():
+            if v.is_floating_point() and (v.dtype != torch.float32 or not v.is_contiguous() or v.device != self.device):
+                raise TypeError(f"{k} must be a contiguous fp32 tensor on {self.device}")
+        self.params = {k: v for k, v in params.items() if v.is_floating_point()}
+        self.grads = {k: torch.empty_like(v) for k, v in self.params.items() if "running" not in k}
+        pa = (N.NamedTensor * len(self.params))()
+        for i, (k, v) in enumerate(self.params.items()):
+            pa[i].name, pa[i].data, pa[i].numel = k.encode(), v.data_ptr(), v.numel()
+        ga = (N.NamedTensor * len(self.grads))()  # ctl_named_buffer has the same layout (writable data pointer)
+        for i, (k, v) in enumerate(self.grads.items()):
+            ga[i].name, ga[i].data, ga[i].numel = k.encode(), v.data_ptr(), v.numel()
+        with torch.cuda.device(self.device):
+            N.check(N.lib().ctl_trainer_bind(self._h, pa, len(self.params), ga, len(self.grads)))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        N.require_cuda(x)
+        self._x = x.float().contiguous()  # the backward's stem im2col reads it again
+        n, _, H, W = self._x.shape
+        L = N.lib()
+        need = L.ctl_train_workspace_bytes(self._h, n, H, W)
+        if need == 0:
+            raise ValueError(f"unsupported input shape {tuple(x.shape)}")
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        feat = torch.empty(n, 2048, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(L.ctl_train_forward(self._h, self._x.data_ptr(), n, H, W, feat.data_ptr(), self._ws.data_ptr(),
+                                        self._ws.numel(), N.stream_ptr()))
+        return feat
+
+    def backward(self, dfeat: torch.Tensor) -> Dict[str, torch.Tensor]:
+        dfeat = dfeat.float().contiguous()
+        with torch.cuda.device(self.device):
+            N.check(N.lib().ctl_train_backward(self._h, dfeat.data_ptr(), self.grad_scale, self._ws.data_ptr(),
+                                               self._ws.numel(), N.stream_ptr()))
+        return self.grads
+
+    def __del__(self):
+        try:
+            if self._h:
+                N.lib().ctl_trainer_destroy(self._h)
+                self._h = None
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass

@@ -358,6 +358,39 @@ int ctl_stem_im2col_f16(const float* x_nchw, int32_t n, int32_t h, int32_t w, vo
 
 /* ---- optimizer step (solver/build.py:9-47, train_ctl_model.py:155-159, modelling/bases.py:102-133) ---- */
 
+/* ---- train-mode trunk behind an opaque handle (the train forward / backward variants) ----
+ * replaces: torch autograd through ResNet.forward / ResNet_IBN.forward in train mode (modelling/backbones/resnet.py:67-87,
+ * 122-133, resnet_ibn_a.py:18-32,126-141) + Baseline.forward's pooling (modelling/baseline.py:91-96) inside
+ * CTLModel.training_step (train_ctl_model.py:38-179): x -> global_feat [n][2048], then d(loss)/d(global_feat) -> every
+ * parameter gradient.  Same launches, same order, same bits as modelling/backbones/engine_train.py.
+ *   ctl_trainer_create      : ResNet50 or ResNet50-IBN-a (`ibn` != 0), MODEL.LAST_STRIDE 1 or 2, BatchNorm momentum.
+ *   ctl_trainer_bind        : `params` = the `base.*`-stripped fp32 parameters AND BatchNorm running buffers as device
+ *                             pointers, by name (running_mean / running_var optional per layer, updated in place like
+ *                             torch); `grads` = one fp32 output per PARAMETER, same name, the parameter's own layout
+ *                             (conv [Cout][Cin][k][k]).  The handle keeps the pointers: re-bind when storage moves.
+ *   ctl_train_workspace_bytes: bytes of the caller's workspace for one (n, h, w) step: the saved activations of the
+ *                             forward + the scratch of the backward (≈ 60 MB per 256x128 image).
+ *   ctl_train_forward       : x NCHW fp32 -> out_feat [n][2048] fp32 (global_feat); saved tensors stay in `workspace`.
+ *   ctl_train_backward      : dfeat [n][2048] fp32 = dLoss/dglobal_feat.  Activation gradients are computed on
+ *                             grad_scale * dfeat in fp16 (loss scaling, the role of PL's GradScaler, utils/misc.py:111);
+ *                             the parameter gradients are written UN-scaled.  Same workspace as the forward, once per forward.
+ * Not thread-safe; all launches go to `stream`; 256-byte aligned workspace. */
+typedef struct ctl_trainer ctl_trainer;
+typedef struct ctl_named_buffer {
+  const char* name;
+  float* data; /* device pointer, written */
+  int64_t numel;
+} ctl_named_buffer;
+int ctl_trainer_create(ctl_trainer** out, int32_t ibn, int32_t last_stride, float momentum);
+void ctl_trainer_destroy(ctl_trainer* t);
+int ctl_trainer_bind(ctl_trainer* t, const ctl_named_tensor* params, int32_t n_params, const ctl_named_buffer* grads,
+                     int32_t n_grads);
+size_t ctl_train_workspace_bytes(const ctl_trainer* t, int32_t n, int32_t height, int32_t width);
+int ctl_train_forward(ctl_trainer* t, const float* x_nchw, int32_t n, int32_t height, int32_t width, float* out_feat,
+                      void* workspace, size_t workspace_bytes, ctl_stream_t stream);
+int ctl_train_backward(ctl_trainer* t, const float* dfeat, float grad_scale, void* workspace, size_t workspace_bytes,
+                       ctl_stream_t stream);
+
 /* One table entry per parameter tensor, resident on the device; chunk_begin = running sum of
  * ceil(numel / CTL_OPT_CHUNK) over the preceding entries. */
 #define CTL_OPT_CHUNK 8192

@@ -107,6 +107,8 @@ def test_c_abi_argument_errors_are_reported_without_a_gpu():
         lambda: L.ctl_loss_scale_update(one, one, one, one, 1024.0, 0.5, 0.5, 2000, None),                    # growth < 1
         lambda: L.ctl_conv1x1_dual_nhwc_f16(one, 64, one, 7, 8, 64, 2, 1, one, one, one, 256, 1, None),       # odd H2, stride 2
         lambda: L.ctl_augment_batch_u8(one, 1, 8, 8, -1, one, (C.c_float * 3)(0, 0, 0), (C.c_float * 3)(1, 1, 1), one, None),
+        lambda: L.ctl_trainer_create(C.byref(C.c_void_p()), 0, 3, 0.1),                                      # LAST_STRIDE 3
+        lambda: L.ctl_trainer_create(C.byref(C.c_void_p()), 0, 1, 0.0),                                      # momentum 0
     ]
     for i, call in enumerate(cases):
         rc = call()
@@ -115,3 +117,25 @@ def test_c_abi_argument_errors_are_reported_without_a_gpu():
         with pytest.raises(ValueError):
             N.check(rc)
     assert L.ctl_bn_workspace_bytes(10, 48) == 0 and L.ctl_conv2d_wgrad_workspace_bytes(1, 8, 8, 60, 64, 1, 1) == 0
+
+
+def test_trainer_handle_plans_its_workspace_without_a_gpu():
+    """ctl_train_workspace_bytes is a dry walk of the forward + backward launch sequence (no device work): it grows
+    linearly with the batch and covers at least the saved activations (y and z of every conv + BatchNorm)."""
+    import ctypes as C
+
+    from ctl_b200 import _native as N
+
+    L = N.lib()
+    for ibn in (0, 1):
+        h = C.c_void_p()
+        assert L.ctl_trainer_create(C.byref(h), ibn, 1, 0.1) == 0
+        b16, b32 = L.ctl_train_workspace_bytes(h, 16, 256, 128), L.ctl_train_workspace_bytes(h, 32, 256, 128)
+        assert b16 > 0 and 1.8 < b32 / b16 < 2.05
+        # saved y + z alone: ~29 MB per 256x128 image (fp16), the whole step stays below 3x that
+        assert 16 * 25e6 < b16 < 16 * 90e6
+        assert L.ctl_train_workspace_bytes(h, 0, 256, 128) == 0 and L.ctl_train_workspace_bytes(h, 4, 16, 16) == 0
+        df = C.c_void_p(256)
+        assert L.ctl_train_backward(h, df, C.c_float(1024.0), df, 1 << 30, None) == -1  # no forward yet
+        assert b"forward" in L.ctl_last_error()
+        L.ctl_trainer_destroy(h)

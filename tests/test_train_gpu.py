@@ -434,3 +434,69 @@ def test_trunk_train_matches_reference_under_autocast(tag, ibn):
             worst = (cos, k)
         assert cos >= 0.97 and abs(nr - 1) <= 5e-2, (k, cos, nr)
     print(f"{tag}: worst gradient cosine vs reference-under-autocast {worst[0]:.4f} ({worst[1]})")
+
+
+@pytest.mark.parametrize("ibn,shape,last_stride", [(False, (4, 64, 32), 1), (False, (3, 96, 64), 2), (True, (6, 160, 80), 1)])
+def test_native_trainer_handle_matches_trunk_trainer(ibn, shape, last_stride):
+    """ctl_trainer_* (csrc/trunk_train.cu, the train forward / backward behind the C ABI) issues the launches of
+    engine_train.TrunkTrainer in the same order: features, every parameter gradient and the running statistics are
+    bit-identical over two consecutive steps (the InstanceNorm affine gradients, which TrunkTrainer sums over the
+    images with torch.sum and the handle with its own fixed-order kernel: 1e-6 relative)."""
+    from oracle import ctl_oracle as O
+    from ctl_b200.modelling.backbones.engine_train import NativeTrainer, TrunkTrainer
+
+    sd = O.make_trunk_state(seed=21, ibn=ibn)
+    n, H, W = shape
+    g = torch.Generator().manual_seed(31)
+    xs = [torch.randn(n, 3, H, W, generator=g).cuda() for _ in range(2)]
+    dfs = [(torch.randn(n, 2048, generator=g) * 1e-3).cuda() for _ in range(2)]
+    outs = []
+    for native in (False, True):
+        params = {k: v.clone().cuda().contiguous() for k, v in sd.items() if v.is_floating_point()}
+        tr = (NativeTrainer(params, "cuda:0", last_stride=last_stride, ibn=ibn, grad_scale=2048.0) if native
+              else TrunkTrainer("cuda:0", last_stride=last_stride, ibn=ibn, grad_scale=2048.0))
+        res = []
+        for x, df in zip(xs, dfs):
+            feat = tr.forward(x) if native else tr.forward(x, params)
+            grads = tr.backward(df)
+            res.append((feat.clone(), {k: v.clone() for k, v in grads.items()}))
+        torch.cuda.synchronize()
+        outs.append((res, {k: v.clone() for k, v in params.items() if "running" in k}))
+    (py, run_p), (nat, run_n) = outs
+    for (fp, gp), (fn, gn) in zip(py, nat):
+        assert torch.equal(fp, fn)
+        assert set(gp) == set(gn)
+        for k in gp:
+            assert gp[k].shape == gn[k].shape, k
+            if ".IN." in k:
+                assert _rel(gn[k], gp[k]) < 1e-6, k
+            else:
+                assert torch.equal(gp[k], gn[k]), k
+    assert all(torch.equal(run_p[k], run_n[k]) for k in run_p)
+
+
+def test_native_trainer_argument_errors():
+    """missing tensors, a backward without its forward, and a foreign workspace are reported, not executed."""
+    import ctypes as C
+
+    from ctl_b200 import _native as N
+    from oracle import ctl_oracle as O
+    from ctl_b200.modelling.backbones.engine_train import NativeTrainer
+
+    sd = O.make_trunk_state(seed=2)
+    params = {k: v.clone().cuda().contiguous() for k, v in sd.items() if v.is_floating_point()}
+    broken = dict(params)
+    del broken["layer2.0.downsample.1.weight"]
+    with pytest.raises(ValueError, match="layer2.0.downsample.1.weight"):
+        NativeTrainer(broken, "cuda:0")
+    tr = NativeTrainer(params, "cuda:0")
+    df = torch.zeros(2, 2048, device="cuda")
+    tr._ws = torch.empty(1 << 20, dtype=torch.uint8, device="cuda")
+    with pytest.raises(ValueError, match="forward"):
+        tr.backward(df)
+    tr.forward(torch.randn(2, 3, 64, 32, device="cuda"))
+    other = torch.empty_like(tr._ws)
+    rc = N.lib().ctl_train_backward(tr._h, df.data_ptr(), C.c_float(1024.0), other.data_ptr(), other.numel(), N.stream_ptr())
+    assert rc != 0 and b"workspace of the forward" in N.lib().ctl_last_error()
+    tr.backward(df)  # the right workspace still works
+    torch.cuda.synchronize()
