@@ -388,7 +388,8 @@ class NativeTrainer:
         for k, v in params.items():
             if v.is_floating_point() and (v.dtype != torch.float32 or not v.is_contiguous() or v.device != self.device):
                 raise TypeError(f"{k} must be a contiguous fp32 tensor on {self.device}")
-        self.params = {k: v for k, v in params.items() if v.is_floating_point()}
+        # the trunk's own tensors only (resnet_ibn_a.py keeps an unused ImageNet `fc` in its state_dict)
+        self.params = {k: v for k, v in params.items() if v.is_floating_point() and not k.startswith("fc.")}
         self.grads = {k: torch.empty_like(v) for k, v in self.params.items() if "running" not in k}
         pa = (N.NamedTensor * len(self.params))()
         for i, (k, v) in enumerate(self.params.items()):
