@@ -18,6 +18,7 @@ CTL_DIST_EUCLIDEAN = 0
 CTL_DIST_COSINE = 1
 CTL_FLAG_NORMALIZE = 2
 CTL_DIST_SQRT = 4
+CTL_FLAG_EXACT_PASS = 8
 
 _ERRORS = {
     -1: ValueError,   # CTL_ERR_INVALID_ARGUMENT
@@ -52,7 +53,8 @@ class PassDesc(C.Structure):
     _fields_ = [("dist_out", _p), ("ld_out", _i64), ("gmin", _p), ("tau", _p), ("cand_keys", _p),
                 ("cand_count", _p), ("cand_cap", _i32), ("q_pid", _p), ("q_cam", _p), ("g_pid", _p),
                 ("g_cammask", _p), ("pos_keys", _p), ("pos_count", _p), ("max_pos", _i32), ("thr_keys", _p),
-                ("thr_count", _p), ("buckets", _p), ("overflow", _p), ("g_index_offset", _i64)]
+                ("thr_count", _p), ("buckets", _p), ("overflow", _p), ("g_index_offset", _i64),
+                ("approx", _i32), ("q_tile_range", _p), ("g_tile_range", _p), ("g_index_map", _p)]
 
 class NamedTensor(C.Structure):
     """struct ctl_named_tensor (include/ctl_b200.h)."""
@@ -79,6 +81,8 @@ SIGNATURES = {
     "ctl_debug_set_dist_profile": (None, [_p]),
     "ctl_topk_plan": (C.c_int, [_i64, _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     "ctl_select_tau": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p]),
+    "ctl_select_tau_approx": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _i32, _i32, _p, _p, _p]),
+    "ctl_dist_prep": (C.c_int, [_p, _i64, _p, _i64, _i32, _p, _p, _p, _p, _p, _p]),
     "ctl_fill_f32": (C.c_int, [_p, _i64, C.c_float, _p]),
     "ctl_topk_emit": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p, _p, _p]),
     "ctl_key_encode": (C.c_uint64, [C.c_float, C.c_uint32]),

@@ -14,6 +14,7 @@
 // One persistent CTA per SM, 6 warps: TMA producer / MMA issuer / 4 epilogue warps; 3-stage
 // smem ring of {q_hi, q_lo, g_hi, g_lo} 128x64 fp16 tiles (SWIZZLE_128B), double-buffered TMEM
 // accumulators (2 x (128 + 128) columns) so the epilogue of tile i overlaps the MMAs of i+1.
+#include <limits.h>
 #include <math_constants.h>
 #include <math.h>
 #include <string.h>
@@ -72,11 +73,16 @@ struct PlanesView {
   const __half* lo;
   const float* sq;
   const float* inv_scale;
+  const float* hn;  // |hi| / s         (un-scaled norm of the leading plane)
+  const float* ln;  // 2^-11 |lo| / s   (un-scaled norm of the correction plane): the hi-only product of a pair (q, g)
+                    // differs from the three-product value by at most hn_q ln_g + ln_q hn_g
 };
 static size_t planes_off_lo(int64_t n, int32_t d) { return ((size_t)n * d * 2 + 255) & ~size_t(255); }
 static size_t planes_off_sq(int64_t n, int32_t d) { return 2 * planes_off_lo(n, d); }
 static size_t planes_off_is(int64_t n, int32_t d) { return planes_off_sq(n, d) + (((size_t)n * 4 + 255) & ~size_t(255)); }
-static size_t planes_total(int64_t n, int32_t d) { return planes_off_is(n, d) + (((size_t)n * 4 + 255) & ~size_t(255)); }
+static size_t planes_off_hn(int64_t n, int32_t d) { return planes_off_is(n, d) + (((size_t)n * 4 + 255) & ~size_t(255)); }
+static size_t planes_off_ln(int64_t n, int32_t d) { return planes_off_hn(n, d) + (((size_t)n * 4 + 255) & ~size_t(255)); }
+static size_t planes_total(int64_t n, int32_t d) { return planes_off_ln(n, d) + (((size_t)n * 4 + 255) & ~size_t(255)); }
 static PlanesView planes_view(const void* p, int64_t n, int32_t d) {
   const char* c = static_cast<const char*>(p);
   PlanesView v;
@@ -84,6 +90,8 @@ static PlanesView planes_view(const void* p, int64_t n, int32_t d) {
   v.lo = reinterpret_cast<const __half*>(c + planes_off_lo(n, d));
   v.sq = reinterpret_cast<const float*>(c + planes_off_sq(n, d));
   v.inv_scale = reinterpret_cast<const float*>(c + planes_off_is(n, d));
+  v.hn = reinterpret_cast<const float*>(c + planes_off_hn(n, d));
+  v.ln = reinterpret_cast<const float*>(c + planes_off_ln(n, d));
   return v;
 }
 
@@ -103,7 +111,8 @@ __device__ __forceinline__ float warp_max(float v) {
 // exact hi/lo split and the fp32 squared norm of the (normalised) row.
 __global__ void __launch_bounds__(128) planes_build_kernel(const float* __restrict__ x, int64_t n, int d, int n_norm,
                                                            __half* __restrict__ hi, __half* __restrict__ lo,
-                                                           float* __restrict__ sq, float* __restrict__ inv_scale) {
+                                                           float* __restrict__ sq, float* __restrict__ inv_scale,
+                                                           float* __restrict__ hn, float* __restrict__ ln) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= n) return;
@@ -136,6 +145,7 @@ __global__ void __launch_bounds__(128) planes_build_kernel(const float* __restri
     sexp = min(14 - e, 120);   // mx * 2^sexp in [2^13, 2^14)
   }
   const float scale = scalbnf(1.f, sexp);
+  float shi = 0.f, slo = 0.f;
   for (int i = lane; i < d; i += 32) {
     float v = xr[i];
     if (n_norm > 0) v = __fdiv_rn(v, denom[0]);
@@ -143,12 +153,20 @@ __global__ void __launch_bounds__(128) planes_build_kernel(const float* __restri
     const float vs = v * scale;  // exact (power of two)
     const __half h = __float2half_rn(vs);
     const float r = vs - __half2float(h);  // exact remainder
+    const __half l = __float2half_rn(r * 2048.f);
     hi[row * d + i] = h;
-    lo[row * d + i] = __float2half_rn(r * 2048.f);
+    lo[row * d + i] = l;
+    shi = __fmaf_rn(__half2float(h), __half2float(h), shi);
+    slo = __fmaf_rn(__half2float(l), __half2float(l), slo);
   }
+  shi = warp_sum(shi);
+  slo = warp_sum(slo);
   if (lane == 0) {
     sq[row] = ss;
-    inv_scale[row] = scalbnf(1.f, -sexp);
+    const float is = scalbnf(1.f, -sexp);
+    inv_scale[row] = is;
+    hn[row] = __fsqrt_ru(shi) * is;                    // power-of-two scale: exact
+    ln[row] = __fsqrt_ru(slo) * is * 4.8828125e-4f;    // 2^-11
   }
 }
 
@@ -187,6 +205,13 @@ struct GemmPass {
   const int* thr_count;
   int* buckets;
   int* overflow;
+  // cheap tiles: a (query tile, gallery tile) pair whose identity ranges are disjoint holds no positive, so a pass that
+  // only needs exact distances for the positives may run it with the leading product only (approx == 1: group minima
+  // within a known bound of the exact ones) or skip it altogether (approx == 2: collect-only passes)
+  int approx;
+  const int2* q_range;  // [m_tiles] {min pid, max pid}; nullptr: no identities, every tile is cheap
+  const int2* g_range;  // [n_tiles]
+  const int* g_map;     // optional: gallery row -> index written into the keys (rows stored in another order)
   long long* prof;  // debug: [grid][8] epilogue cycle counters (tools/prof_retrieval.py)
 };
 
@@ -240,6 +265,17 @@ __device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, 
   nt = band * band_w + rem % w;
 }
 
+// 0: three products (exact), 1: leading product only, 2: tile skipped.  Every role of the CTA evaluates this on the same
+// two global words, so they agree on the tile sequence.
+__device__ __forceinline__ int tile_mode(const GemmPass& p, int mt, int nt) {
+  if (!p.approx) return 0;
+  if (p.q_range) {
+    const int2 a = p.q_range[mt], b = p.g_range[nt];
+    if (!(b.y < a.x || b.x > a.y)) return 0;
+  }
+  return p.approx;
+}
+
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     dist_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmPass p) {
   extern __shared__ uint8_t smem_raw[];
@@ -291,14 +327,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int mt, nt;
         tile_coords(tile, p.m_tiles, p.n_tiles, mt, nt);
+        const int mode = tile_mode(p, mt, nt);
+        if (mode == 2) continue;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t dst = smem_base + stage * STAGE_BYTES;
-          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+          mbar_arrive_expect_tx(full_bar(stage), mode ? 2 * TILE_BYTES : STAGE_BYTES);
           tma_load_2d(dst + 0 * TILE_BYTES, &maps.q_hi, full_bar(stage), kb * BK, mt * BM);
-          tma_load_2d(dst + 1 * TILE_BYTES, &maps.q_lo, full_bar(stage), kb * BK, mt * BM);
+          if (!mode) tma_load_2d(dst + 1 * TILE_BYTES, &maps.q_lo, full_bar(stage), kb * BK, mt * BM);
           tma_load_2d(dst + 2 * TILE_BYTES, &maps.g_hi, full_bar(stage), kb * BK, nt * BN);
-          tma_load_2d(dst + 3 * TILE_BYTES, &maps.g_lo, full_bar(stage), kb * BK, nt * BN);
+          if (!mode) tma_load_2d(dst + 3 * TILE_BYTES, &maps.g_lo, full_bar(stage), kb * BK, nt * BN);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -315,6 +353,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       int as = 0;
       uint32_t aphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int mt, nt;
+        tile_coords(tile, p.m_tiles, p.n_tiles, mt, nt);
+        const int mode = tile_mode(p, mt, nt);
+        if (mode == 2) continue;
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
         const uint32_t acc0 = tmem_base + as * 256;
@@ -331,8 +373,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           for (int k = 0; k < BK / 16; ++k) {
             const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
             umma_f16(acc0, desc_advance_k(d_qh, k), desc_advance_k(d_gh, k), idesc, acc);
-            umma_f16(acc1, desc_advance_k(d_qh, k), desc_advance_k(d_gl, k), idesc, acc);
-            umma_f16(acc1, desc_advance_k(d_ql, k), desc_advance_k(d_gh, k), idesc, 1u);
+            if (!mode) {
+              umma_f16(acc1, desc_advance_k(d_qh, k), desc_advance_k(d_gl, k), idesc, acc);
+              umma_f16(acc1, desc_advance_k(d_ql, k), desc_advance_k(d_gh, k), idesc, 1u);
+            }
           }
           umma_commit(empty_bar(stage));  // smem slot free once these MMAs have read it
           if (++stage == STAGES) {
@@ -373,9 +417,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     pc[i] += _t - tprev;            \
     tprev = _t;                     \
   }
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int mt, nt;
       tile_coords(tile, p.m_tiles, p.n_tiles, mt, nt);
+      const int mode = tile_mode(p, mt, nt);
+      if (mode == 2) continue;  // `it` (metadata slice parity) counts PROCESSED tiles only
       const int row = mt * BM + row_in_tile;
       const bool row_ok = row < p.nq;
       const int mb = (it & 1) * BN;  // double-buffered metadata slice
@@ -448,7 +494,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       for (int c = 0; c < 4; ++c) {
         uint32_t r0[16], r1[16];
         tmem_ld16(t0 + c * 16, r0);
-        tmem_ld16(t0 + 128 + c * 16, r1);
+        if (!mode) {
+          tmem_ld16(t0 + 128 + c * 16, r1);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r1[j] = 0u;  // the correction accumulator was not computed: fma(0, 2^-11, acc0) == acc0
+        }
         tmem_ld_wait();
         CTL_STAMP(3)
         const int cl0 = chalf * 64 + c * 16;  // column inside the tile
@@ -506,7 +557,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             const uint32_t bit = 1u << j;
             m_any &= ~bit;
             const float dj = select16(dist, j);
-            const unsigned int gidx = static_cast<unsigned int>(col0 + j + p.g_off);
+            const unsigned int gidx = p.g_map ? static_cast<unsigned int>(p.g_map[col0 + j]) : static_cast<unsigned int>(col0 + j + p.g_off);
             const unsigned long long key = make_key(dj, gidx);
             if (m_cand & bit) {
               const int slot = atomicAdd(p.cand_count + row, 1);
@@ -545,6 +596,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       if (lane == 0) mbar_arrive(tempty_bar(as));
       if (thr_in_smem) named_bar_sync(2, 256);  // nobody still reads this tile's thresholds
       CTL_STAMP(5)
+      ++it;
       if (++as == 2) {
         as = 0;
         aphase ^= 1u;
@@ -596,8 +648,11 @@ __device__ __forceinline__ void bitonic_sort_smem(T* s, int n_pow2) {
 // Radix select on the order-preserving uint32 keys (4 passes of 8 bits, shared-memory histogram + warp scan): the k-th
 // smallest needs no sort -- round 1 sorted all n_merged keys with a bitonic network (55 block-wide stages for 1024 keys,
 // 128 us for 3368 queries; this form: ~20 us).
+// With `q_hn` (approximate group minima, ctl_dist_pass approx == 1): tau += the bound of |approximate - exact| distance
+// of this query against ANY gallery row, so that {exact distance <= tau} still contains the k nearest rows.
 __global__ void __launch_bounds__(256) select_tau_kernel(const float* __restrict__ gmin, int n_groups, int merge, int k,
-                                                         int n_pow2, float* __restrict__ tau) {
+                                                         int n_pow2, float* __restrict__ tau, const float* __restrict__ q_hn,
+                                                         const float* __restrict__ q_ln, const float* __restrict__ g_err_max) {
   extern __shared__ uint32_t skeys[];
   __shared__ int hist[256];
   __shared__ int s_bucket, s_k;
@@ -655,7 +710,69 @@ __global__ void __launch_bounds__(256) select_tau_kernel(const float* __restrict
     kk = s_k;
     __syncthreads();
   }
-  if (threadIdx.x == 0) tau[blockIdx.x] = orderable_float(prefix);
+  if (threadIdx.x == 0) {
+    float t = orderable_float(prefix);
+    if (q_hn) {
+      // |dot(hi-only) - dot(3 products)| <= hn_q * max ln_g + ln_q * max hn_g (Cauchy-Schwarz on the two dropped products);
+      // a squared distance moves by twice that, a cosine distance by once (2x kept: conservative).  1 % + an absolute
+      // term cover the fp32 roundings of the norms, of the accumulators and of the final fma.
+      const float hq = q_hn[blockIdx.x], lq = q_ln[blockIdx.x], gl = g_err_max[0], gh = g_err_max[1];
+      const float e = __fmaf_ru(hq, gl, __fmul_ru(lq, gh));
+      t = __fadd_ru(t, __fmaf_ru(2.02f, e, 4e-6f * __fmaf_ru(hq, hq, __fmul_ru(gh, gh))));
+    }
+    tau[blockIdx.x] = t;
+  }
+}
+
+// per-tile identity ranges and the gallery-wide maxima of the two plane norms (inputs of the cheap-tile decision and of
+// the tau margin).  blocks [0, m_tiles): query tiles; blocks [m_tiles, m_tiles + n_tiles): gallery tiles.
+__global__ void __launch_bounds__(BM) dist_prep_kernel(const int* __restrict__ q_pid, int nq, int m_tiles, const int* __restrict__ g_pid,
+                                                        int ng, const float* __restrict__ g_hn, const float* __restrict__ g_ln,
+                                                        int2* __restrict__ q_range, int2* __restrict__ g_range,
+                                                        unsigned int* __restrict__ g_err_max) {
+  __shared__ int s_lo[BM / 32], s_hi[BM / 32];
+  __shared__ float s_h[BM / 32], s_l[BM / 32];
+  const bool is_q = (int)blockIdx.x < m_tiles;
+  const int t = is_q ? blockIdx.x : blockIdx.x - m_tiles;
+  const int row = t * BM + threadIdx.x;
+  const int n = is_q ? nq : ng;
+  const int* pid = is_q ? q_pid : g_pid;
+  int lo = INT_MAX, hi = INT_MIN;
+  float h = 0.f, l = 0.f;
+  if (row < n) {
+    if (pid) lo = hi = pid[row];
+    if (!is_q && g_err_max) {
+      h = g_hn[row];
+      l = g_ln[row];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    h = fmaxf(h, __shfl_xor_sync(0xffffffffu, h, o));
+    l = fmaxf(l, __shfl_xor_sync(0xffffffffu, l, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_lo[threadIdx.x >> 5] = lo;
+    s_hi[threadIdx.x >> 5] = hi;
+    s_h[threadIdx.x >> 5] = h;
+    s_l[threadIdx.x >> 5] = l;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < BM / 32; ++w) {
+      lo = min(lo, s_lo[w]);
+      hi = max(hi, s_hi[w]);
+      h = fmaxf(h, s_h[w]);
+      l = fmaxf(l, s_l[w]);
+    }
+    if (pid) (is_q ? q_range : g_range)[t] = make_int2(lo, hi);
+    if (!is_q && g_err_max) {  // non-negative floats order like their bit patterns
+      atomicMax(g_err_max + 0, __float_as_uint(l));
+      atomicMax(g_err_max + 1, __float_as_uint(h));
+    }
+  }
 }
 
 __global__ void sort_key_rows_kernel(unsigned long long* __restrict__ keys, const int* __restrict__ counts,
@@ -858,7 +975,8 @@ int ctl_planes_build(const float* x, int64_t n, int32_t d, int32_t flags, void* 
   const int n_norm = ((flags & CTL_FLAG_NORMALIZE) ? 1 : 0) + ((flags & CTL_DIST_COSINE) ? 1 : 0);
   planes_build_kernel<<<(unsigned)((n + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
       x, n, d, n_norm, reinterpret_cast<__half*>(c), reinterpret_cast<__half*>(c + planes_off_lo(n, d)),
-      reinterpret_cast<float*>(c + planes_off_sq(n, d)), reinterpret_cast<float*>(c + planes_off_is(n, d)));
+      reinterpret_cast<float*>(c + planes_off_sq(n, d)), reinterpret_cast<float*>(c + planes_off_is(n, d)),
+      reinterpret_cast<float*>(c + planes_off_hn(n, d)), reinterpret_cast<float*>(c + planes_off_ln(n, d)));
   CTL_LAUNCH_CHECK();
   return 0;
 }
@@ -880,6 +998,7 @@ size_t ctl_topk_workspace_bytes(int64_t nq, int64_t ng, int32_t k) {
   ws.take<float>((size_t)nq);
   ws.take<unsigned long long>((size_t)nq * pl.cap);
   ws.take<int>((size_t)nq);
+  ws.take<float>(2);
   return ws.off;
 }
 
@@ -898,7 +1017,8 @@ int ctl_l2_topk(const void* q_planes, int64_t nq, const void* g_planes, int64_t 
   float* tau = ws.take<float>((size_t)nq);
   unsigned long long* cand = ws.take<unsigned long long>((size_t)nq * pl.cap);
   int* cand_count = ws.take<int>((size_t)nq);
-  if (!gmin || !tau || !cand || !cand_count) {
+  float* g_err_max = ws.take<float>(2);
+  if (!gmin || !tau || !cand || !cand_count || !g_err_max) {
     set_error("workspace too small: need %zu bytes, have %zu", ws.off, workspace_bytes);
     return CTL_ERR_WORKSPACE;
   }
@@ -909,13 +1029,22 @@ int ctl_l2_topk(const void* q_planes, int64_t nq, const void* g_planes, int64_t 
     fill_f32_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, stream>>>(tau, nq, INFINITY);
     CTL_LAUNCH_CHECK();
   } else {
-    // pass A: minima of 16-column groups -> tau = k-th smallest group minimum
+    // pass A: minima of 16-column groups -> tau = k-th smallest group minimum.  No identities here, so pass A only feeds
+    // the threshold: it runs with the leading fp16 product alone (half the operand traffic, a third of the tensor work)
+    // and tau gets the rigorous bound of the difference added (ctl_select_tau_approx) -- pass B is exact either way.
+    const bool approx = !(flags & (CTL_DIST_SQRT | CTL_FLAG_EXACT_PASS));
     GemmPass a = {};
     a.gmin = gmin;
     a.n_groups = pl.n_groups;
+    a.approx = approx ? 1 : 0;
+    if (approx) {
+      CTL_CUDA(cudaMemsetAsync(g_err_max, 0, 2 * sizeof(float), stream));
+      if ((rc = ctl_dist_prep(q_planes, nq, g_planes, ng, d, nullptr, nullptr, nullptr, nullptr, g_err_max, stream))) return rc;
+    }
     if ((rc = launch_gemm_pass(q_planes, nq, g_planes, ng, d, flags, a, stream))) return rc;
-    select_tau_kernel<<<(unsigned)nq, 256, pl.n_merged_pow2 * sizeof(uint32_t), stream>>>(gmin, pl.n_groups, pl.merge, k,
-                                                                                         pl.n_merged_pow2, tau);
+    const PlanesView qv = planes_view(q_planes, nq, d);
+    select_tau_kernel<<<(unsigned)nq, 256, pl.n_merged_pow2 * sizeof(uint32_t), stream>>>(
+        gmin, pl.n_groups, pl.merge, k, pl.n_merged_pow2, tau, approx ? qv.hn : nullptr, approx ? qv.ln : nullptr, g_err_max);
     CTL_LAUNCH_CHECK();
   }
   // pass B: rows with distance <= tau become (distance, index) keys
@@ -1041,6 +1170,16 @@ int ctl_dist_pass(const void* q_planes, int64_t nq, const void* g_planes, int64_
   p.g_off = e.g_index_offset;
   p.prof = g_dist_prof;
   CTL_CHECK_ARG(e.g_index_offset >= 0 && e.g_index_offset + ng < (1ll << 32), "gallery index out of uint32 range");
+  CTL_CHECK_ARG(e.approx >= 0 && e.approx <= 2, "approx must be 0, 1 or 2");
+  CTL_CHECK_ARG((e.q_tile_range == nullptr) == (e.g_tile_range == nullptr), "q_tile_range and g_tile_range come together");
+  CTL_CHECK_ARG(!e.approx || !(e.dist_out || e.cand_keys || e.buckets),
+                "cheap tiles give approximate distances: not for the full matrix, the candidates or the bucket counts");
+  CTL_CHECK_ARG(e.approx != 2 || !e.gmin, "skipped tiles produce no group minima (approx == 2 is for collect-only passes)");
+  CTL_CHECK_ARG(!e.approx || !e.pos_keys || e.q_tile_range, "collecting positives with cheap tiles needs the tile identity ranges");
+  p.approx = e.approx;
+  p.q_range = e.approx ? reinterpret_cast<const int2*>(e.q_tile_range) : nullptr;
+  p.g_range = e.approx ? reinterpret_cast<const int2*>(e.g_tile_range) : nullptr;
+  p.g_map = e.g_index_map;
   if (!p.pos_keys && !p.buckets) p.q_pid = nullptr;  // identities unused
   return launch_gemm_pass(q_planes, nq, g_planes, ng, d, flags, p, (cudaStream_t)stream);
 }
@@ -1065,7 +1204,44 @@ int ctl_select_tau(const float* gmin, int64_t nq, int32_t n_groups, int32_t merg
   int rc = ctl_device_check();
   if (rc) return rc;
   const int np2 = next_pow2(n_merged);
-  select_tau_kernel<<<(unsigned)nq, 256, np2 * sizeof(uint32_t), (cudaStream_t)stream>>>(gmin, n_groups, merge, k, np2, tau);
+  select_tau_kernel<<<(unsigned)nq, 256, np2 * sizeof(uint32_t), (cudaStream_t)stream>>>(gmin, n_groups, merge, k, np2, tau, nullptr,
+                                                                                         nullptr, nullptr);
+  CTL_LAUNCH_CHECK();
+  return 0;
+}
+
+int ctl_select_tau_approx(const float* gmin, int64_t nq, int32_t n_groups, int32_t merge, int32_t k, const void* q_planes, int32_t d,
+                          int32_t flags, const float* g_err_max, float* tau, ctl_stream_t stream) {
+  CTL_CHECK_ARG(gmin && tau && q_planes && g_err_max && nq > 0 && n_groups > 0 && merge >= 1 && k >= 1 && d > 0, "bad arguments");
+  CTL_CHECK_ARG(!(flags & CTL_DIST_SQRT), "the approximate first pass has no error bound for CTL_DIST_SQRT distances");
+  const int n_merged = (n_groups + merge - 1) / merge;
+  CTL_CHECK_ARG(n_merged >= k && n_merged <= SELECT_MAX, "need k <= merged groups <= %d (have %d)", SELECT_MAX, n_merged);
+  int rc = ctl_device_check();
+  if (rc) return rc;
+  const PlanesView q = planes_view(q_planes, nq, d);
+  const int np2 = next_pow2(n_merged);
+  select_tau_kernel<<<(unsigned)nq, 256, np2 * sizeof(uint32_t), (cudaStream_t)stream>>>(gmin, n_groups, merge, k, np2, tau, q.hn, q.ln,
+                                                                                         g_err_max);
+  CTL_LAUNCH_CHECK();
+  return 0;
+}
+
+int ctl_dist_prep(const void* q_planes, int64_t nq, const void* g_planes, int64_t ng, int32_t d, const int32_t* q_pid,
+                  const int32_t* g_pid, int32_t* q_tile_range, int32_t* g_tile_range, float* g_err_max, ctl_stream_t stream) {
+  CTL_CHECK_ARG(q_planes && g_planes && nq > 0 && ng > 0 && nq < (1ll << 31) && ng < (1ll << 31) && d > 0, "bad arguments");
+  CTL_CHECK_ARG((q_pid == nullptr) == (g_pid == nullptr) && (q_pid == nullptr) == (q_tile_range == nullptr) &&
+                    (q_pid == nullptr) == (g_tile_range == nullptr),
+                "identities and tile ranges come together (or not at all)");
+  CTL_CHECK_ARG(q_pid || g_err_max, "nothing to do");
+  int rc = ctl_device_check();
+  if (rc) return rc;
+  const PlanesView g = planes_view(g_planes, ng, d);
+  const int m_tiles = (int)((nq + BM - 1) / BM), n_tiles = (int)((ng + BN - 1) / BN);
+  static_assert(BM == BN, "dist_prep_kernel uses one block size for both tile kinds");
+  dist_prep_kernel<<<m_tiles + n_tiles, BM, 0, (cudaStream_t)stream>>>(q_pid, (int)nq, m_tiles, g_pid, (int)ng, g.hn, g.ln,
+                                                                       reinterpret_cast<int2*>(q_tile_range),
+                                                                       reinterpret_cast<int2*>(g_tile_range),
+                                                                       reinterpret_cast<unsigned int*>(g_err_max));
   CTL_LAUNCH_CHECK();
   return 0;
 }

@@ -259,10 +259,11 @@ class CTLModel(_Base):
         nq = hp.num_query
         emb = torch.as_tensor(embeddings).float()
         emb = emb if emb.is_cuda else emb.cuda(non_blocking=True)
-        qp = _R.build_planes(emb[:nq], hp.SOLVER.DISTANCE_FUNC, hp.TEST.FEAT_NORM)
-        gp = _R.build_planes(emb[nq:], hp.SOLVER.DISTANCE_FUNC, hp.TEST.FEAT_NORM)
-        res = _R.evaluate_streamed(qp, gp, np.asarray(labels[:nq]), np.asarray(labels[nq:]), camids[:nq], camids[nq:],
-                                   50, respect)
+        q_lab, g_lab = np.asarray(labels[:nq]), np.asarray(labels[nq:])
+        go = _R.pid_order(g_lab) if len(g_lab) == emb.shape[0] - nq else None  # identity order: cheap collect pass
+        qp = _R.build_planes(emb[:nq], hp.SOLVER.DISTANCE_FUNC, hp.TEST.FEAT_NORM, order=_R.pid_order(q_lab))
+        gp = _R.build_planes(emb[nq:], hp.SOLVER.DISTANCE_FUNC, hp.TEST.FEAT_NORM, order=go)
+        res = _R.evaluate_streamed(qp, gp, q_lab, g_lab, camids[:nq], camids[nq:], 50, respect)
         for top_k, kk in zip(res.all_topk, [1, 5, 10, 20, 50]):
             print("top-k, Rank-{:<3}:{:.1%}".format(kk, top_k))
         print(f"mAP: {res.mAP}")

@@ -26,6 +26,10 @@ class Planes:
     n: int
     d: int
     flags: int
+    # rows stored in another order than the caller's (build_planes(order=)): stored row i == caller's row order[i].
+    # Results are always reported in the CALLER's indexing (gallery: ctl_pass_desc.g_index_map; queries: un-permuted).
+    order: Optional[torch.Tensor] = None        # int32 on the device
+    order_host: Optional[np.ndarray] = None
 
     @property
     def ptr(self):
@@ -43,18 +47,36 @@ def _flags(dist: str, normalize: bool) -> int:
     return f
 
 
-def build_planes(x: torch.Tensor, dist: str = "euclidean", normalize: bool = False) -> Planes:
+def pid_order(pids) -> np.ndarray:
+    """Stable order that sorts rows by identity.  With BOTH operands stored in this order almost every 128 x 128 tile
+    of the distance GEMM pairs rows of disjoint identity ranges: such a tile holds no positive, so the threshold pass
+    runs it with one fp16 product instead of three and the collect pass skips it (ctl_pass_desc.approx) -- the results
+    (indices, distances, ranks, AP) are bit-identical to the unsorted run."""
+    return np.argsort(np.asarray(pids), kind="stable")
+
+
+def build_planes(x: torch.Tensor, dist: str = "euclidean", normalize: bool = False, order=None) -> Planes:
+    """`order` (optional, a permutation of the rows, e.g. pid_order(pids)): the planes hold x[order]."""
     N.require_cuda(x)
     if x.dim() != 2:
         raise ValueError(f"expected [n, d] features, got {tuple(x.shape)}")
-    x = x.detach().float().contiguous()
+    x = x.detach().float()
+    order_dev = order_host = None
+    if order is not None:
+        order_host = np.ascontiguousarray(np.asarray(order, dtype=np.int64))
+        if order_host.shape != (x.shape[0],):
+            raise ValueError("order must be a permutation of the rows")
+        o64 = torch.from_numpy(order_host).to(x.device, non_blocking=True)
+        x = x.index_select(0, o64)
+        order_dev = o64.to(torch.int32)
+    x = x.contiguous()
     n, d = x.shape
     flags = _flags(dist, normalize)
     L = N.lib()
     buf = torch.empty(L.ctl_planes_bytes(n, d), dtype=torch.uint8, device=x.device)
     with torch.cuda.device(x.device):
         N.check(L.ctl_planes_build(x.data_ptr(), n, d, flags, buf.data_ptr(), N.stream_ptr()))
-    return Planes(buf, n, d, flags)
+    return Planes(buf, n, d, flags, order_dev, order_host)
 
 
 class PlaneCache:
@@ -67,13 +89,14 @@ class PlaneCache:
         self.capacity = capacity
         self._items = {}
 
-    def get(self, x: torch.Tensor, dist: str = "euclidean", normalize: bool = False) -> Planes:
-        key = (x.data_ptr(), tuple(x.shape), x._version, str(x.device), dist, normalize)
+    def get(self, x: torch.Tensor, dist: str = "euclidean", normalize: bool = False, order=None) -> Planes:
+        okey = None if order is None else hash(np.ascontiguousarray(np.asarray(order, dtype=np.int64)).tobytes())
+        key = (x.data_ptr(), tuple(x.shape), x._version, str(x.device), dist, normalize, okey)
         p = self._items.get(key)
         if p is None:
             if len(self._items) >= self.capacity:
                 self._items.pop(next(iter(self._items)))
-            p = self._items[key] = build_planes(x, dist, normalize)
+            p = self._items[key] = build_planes(x, dist, normalize, order)
         return p
 
 
@@ -88,9 +111,13 @@ def dist_matrix(x: torch.Tensor, y: torch.Tensor, dist: str = "euclidean", norma
     return out
 
 
-def topk(qp: Planes, gp: Planes, k: int, g_index_offset: int = 0):
+def topk(qp: Planes, gp: Planes, k: int, g_index_offset: int = 0, exact_threshold_pass: bool = False):
     """k nearest gallery rows per query in ascending (distance, index) order.
-    Returns (idx int64 [nq, k], dist float32 [nq, k]) on the device."""
+    Returns (idx int64 [nq, k], dist float32 [nq, k], overflow flag) on the device.  The threshold pass runs with the leading fp16
+    product + a rigorous error bound unless `exact_threshold_pass` (identical results; the flag only trades a slightly
+    larger candidate set for a third of that pass's tensor work)."""
+    if qp.order is not None or gp.order is not None:
+        raise ValueError("topk() takes planes in the caller's row order (use topk_and_eval for pid-sorted planes)")
     L = N.lib()
     k = int(min(k, gp.n))
     dev = qp.buf.device
@@ -102,7 +129,8 @@ def topk(qp: Planes, gp: Planes, k: int, g_index_offset: int = 0):
         N.check(-3)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        N.check(L.ctl_l2_topk(qp.ptr, qp.n, gp.ptr, gp.n, qp.d, qp.flags, k, g_index_offset, idx.data_ptr(),
+        flags = qp.flags | (N.CTL_FLAG_EXACT_PASS if exact_threshold_pass else 0)
+        N.check(L.ctl_l2_topk(qp.ptr, qp.n, gp.ptr, gp.n, qp.d, flags, k, g_index_offset, idx.data_ptr(),
                               dst.data_ptr(), ovf.data_ptr(), ws.data_ptr(), ws_bytes, N.stream_ptr()))
     return idx, dst, ovf
 
@@ -145,9 +173,10 @@ def topk_similar(q: torch.Tensor, g: torch.Tensor, k: int = 100, dist: str = "eu
     rc = N.lib().ctl_topk_plan(g.shape[0], k, C.byref(a), C.byref(b), C.byref(c), C.byref(d_))
     if rc == 0 and N.lib().ctl_topk_workspace_bytes(q.shape[0], g.shape[0], k) > 0:
         qp, gp = build_planes(q, dist, normalize), build_planes(g, dist, normalize)
-        idx, dst, ovf = topk(qp, gp, k)
-        if int(ovf.item()) == 0:
-            return idx, dst
+        for exact in (False, True):  # a candidate overflow of the bounded threshold pass: once more with the exact one
+            idx, dst, ovf = topk(qp, gp, k, exact_threshold_pass=exact)
+            if int(ovf.item()) == 0:
+                return idx, dst
     return topk_dense(q, g, k, dist, normalize)
 
 
@@ -205,11 +234,18 @@ class EncodedIds:
     max_pos: int
 
 
-def encode_ids(q_pids, g_pids, q_camids, g_camids, respect_camids: bool, device, global_labels: bool = False) -> EncodedIds:
+def encode_ids(q_pids, g_pids, q_camids, g_camids, respect_camids: bool, device, global_labels: bool = False,
+               q_order=None, g_order=None) -> EncodedIds:
+    """`q_order` / `g_order`: the row orders of the planes these identities go with (Planes.order_host); the inputs are in
+    the caller's order."""
     if global_labels:
         arrs = _encode_identities_global(q_pids, g_pids, q_camids, g_camids)
     else:
         arrs = encode_identities(q_pids, g_pids, q_camids, g_camids, respect_camids)
+    if q_order is not None:
+        arrs = (arrs[0][q_order], arrs[1][q_order]) + tuple(arrs[2:])
+    if g_order is not None:
+        arrs = tuple(arrs[:2]) + (arrs[2][g_order], arrs[3][g_order], arrs[4])
 
     def to_dev(a):
         return torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=True)
@@ -276,6 +312,48 @@ def _finalize_and_read_back(buckets, count, nq, max_pos, ovf):
     return ranks, h[:nq, 0], h[:nq, 1].astype(np.int64), h[:nq, 2].astype(np.int32), int(h[nq, 0])
 
 
+def _approx_enabled(qp: Planes) -> bool:
+    """Cheap tiles (ctl_pass_desc.approx) are on unless CTL_RETRIEVAL_APPROX=0 (bisect aid); CTL_DIST_SQRT distances have
+    no error bound for the one-product threshold pass."""
+    import os
+
+    return os.environ.get("CTL_RETRIEVAL_APPROX", "1") != "0" and not (qp.flags & N.CTL_DIST_SQRT)
+
+
+def _cheap_tiles(qp: Planes, gp: Planes, ids: "EncodedIds", with_bound: bool):
+    """ctl_dist_prep: per-tile identity ranges of both operands (+ the gallery-wide plane-norm maxima behind the tau
+    bound).  Returns (q_tile_range, g_tile_range, g_err_max | None) on the device."""
+    dev = qp.buf.device
+    mt, nt = (qp.n + 127) // 128, (gp.n + 127) // 128
+    ranges = torch.empty(mt + nt, 2, dtype=torch.int32, device=dev)
+    gerr = torch.zeros(2, dtype=torch.float32, device=dev) if with_bound else None
+    q_rng, g_rng = ranges[:mt], ranges[mt:]
+    N.check(N.lib().ctl_dist_prep(qp.ptr, qp.n, gp.ptr, gp.n, qp.d, ids.q_pid.data_ptr(), ids.g_pid.data_ptr(),
+                                  q_rng.data_ptr(), g_rng.data_ptr(), N.ptr(gerr), N.stream_ptr()))
+    return q_rng, g_rng, gerr
+
+
+def _g_index_map(gp: Planes, g_index_offset: int) -> Optional[torch.Tensor]:
+    """int32 map stored gallery row -> index reported in the results (None: row + g_index_offset)."""
+    if gp.order is None:
+        return None
+    if g_index_offset + gp.n >= (1 << 31):
+        raise NotImplementedError("re-ordered gallery planes report int32 indices")
+    return gp.order if g_index_offset == 0 else (gp.order + int(g_index_offset)).to(torch.int32)
+
+
+def _query_inverse(qp: Planes):
+    """(device int64, host) inverse of the query row order: results[inv] are in the caller's order."""
+    if qp.order is None:
+        return None, None
+    inv = getattr(qp, "_inv", None)
+    if inv is None:
+        inv_h = np.empty(qp.n, dtype=np.int64)
+        inv_h[qp.order_host] = np.arange(qp.n)
+        inv = qp._inv = (torch.from_numpy(inv_h).to(qp.buf.device), inv_h)
+    return inv
+
+
 def evaluate_streamed(
     qp: Planes,
     gp: Planes,
@@ -293,7 +371,11 @@ def evaluate_streamed(
     """eval_func semantics (utils/eval_reid.py:25-92) straight from the features: two tensor-
     core passes (collect the positives' distances; count kept rows before each positive),
     no distance matrix, no argsort.  With `group` (torch.distributed), `gp` is this rank's
-    gallery shard and g_* its identities; keys are all-gathered, buckets all-reduced."""
+    gallery shard and g_* its identities; keys are all-gathered, buckets all-reduced.
+    Identities are given in the caller's row order even when the planes were built with `order=`; a precomputed `ids`
+    must have been encoded with the planes' orders (encode_ids(q_order=, g_order=))."""
+    import ctypes as C
+
     import torch.distributed as dist
 
     L = N.lib()
@@ -304,7 +386,8 @@ def evaluate_streamed(
         if world > 1 and not np.issubdtype(np.asarray(q_pids).dtype, np.integer):
             raise ValueError("sharded evaluation needs integer pids")
         # sharded: dense re-labelling must agree across ranks -> identity map instead of np.unique
-        ids = encode_ids(q_pids, g_pids, q_camids, g_camids, respect_camids, dev, global_labels=world > 1)
+        ids = encode_ids(q_pids, g_pids, q_camids, g_camids, respect_camids, dev, global_labels=world > 1,
+                         q_order=qp.order_host, g_order=gp.order_host)
     d_qpid, d_qcam, d_gpid, d_gmask, max_pos_local = ids.q_pid, ids.q_cam, ids.g_pid, ids.g_mask, ids.max_pos
     max_pos = max_pos_local
     if world > 1:
@@ -315,22 +398,31 @@ def evaluate_streamed(
     pos_count = torch.zeros(nq, dtype=torch.int32, device=dev)
     ovf = torch.zeros(1, dtype=torch.int32, device=dev)
     s = N.stream_ptr
+    gmap = _g_index_map(gp, g_index_offset)
+    idp = dict(q_pid=d_qpid.data_ptr(), q_cam=d_qcam.data_ptr(), g_pid=d_gpid.data_ptr(), g_cammask=d_gmask.data_ptr(),
+               max_pos=max_pos, overflow=ovf.data_ptr(), g_index_offset=g_index_offset, g_index_map=N.ptr(gmap))
     with torch.cuda.device(dev):
-        N.check(L.ctl_eval_collect(qp.ptr, nq, gp.ptr, ng, qp.d, qp.flags, d_qpid.data_ptr(), d_qcam.data_ptr(),
-                                   d_gpid.data_ptr(), d_gmask.data_ptr(), g_index_offset, max_pos,
-                                   pos_keys.data_ptr(), pos_count.data_ptr(), ovf.data_ptr(), s()))
+        # pass 1 (collect) only wants the positives: tiles whose identity ranges are disjoint are skipped -- with both
+        # operands stored in pid order (build_planes(order=pid_order(..))) that is ~95 % of a Market-sized problem
+        p1 = N.PassDesc(pos_keys=pos_keys.data_ptr(), pos_count=pos_count.data_ptr(), **idp)
+        if _approx_enabled(qp):
+            q_rng, g_rng, _ = _cheap_tiles(qp, gp, ids, with_bound=False)
+            p1.approx, p1.q_tile_range, p1.g_tile_range = 2, q_rng.data_ptr(), g_rng.data_ptr()
+        N.check(L.ctl_dist_pass(qp.ptr, nq, gp.ptr, ng, qp.d, qp.flags, C.byref(p1), s()))
         if world > 1:
             pos_keys, pos_count = _allgather_keys(pos_keys, pos_count, max_pos, group)
         N.check(L.ctl_sort_key_rows(pos_keys.data_ptr(), pos_count.data_ptr(), nq, max_pos, s()))
         buckets = torch.zeros(nq, max_pos + 1, dtype=torch.int32, device=dev)
-        N.check(L.ctl_eval_count(qp.ptr, nq, gp.ptr, ng, qp.d, qp.flags, d_qpid.data_ptr(), d_qcam.data_ptr(),
-                                 d_gpid.data_ptr(), d_gmask.data_ptr(), g_index_offset, max_pos,
-                                 pos_keys.data_ptr(), pos_count.data_ptr(), buckets.data_ptr(), s()))
+        p2 = N.PassDesc(thr_keys=pos_keys.data_ptr(), thr_count=pos_count.data_ptr(), buckets=buckets.data_ptr(), **idp)
+        N.check(L.ctl_dist_pass(qp.ptr, nq, gp.ptr, ng, qp.d, qp.flags, C.byref(p2), s()))
         if world > 1:
             dist.all_reduce(buckets, op=dist.ReduceOp.SUM, group=group)
         ranks, ap_h, first_h, cnt_h, ovf_h = _finalize_and_read_back(buckets, pos_count, nq, max_pos, ovf)
     if ovf_h:
         raise OverflowError("positives list overflowed (max_pos too small)")
+    inv_d, inv_h = _query_inverse(qp)
+    if inv_h is not None:  # back to the caller's query order
+        ranks, ap_h, first_h, cnt_h = ranks.index_select(0, inv_d), ap_h[inv_h], first_h[inv_h], cnt_h[inv_h]
     num_g = total_gallery if total_gallery is not None else ng
     return _aggregate(ranks, ap_h, cnt_h, np.asarray(q_pids), num_g, max_rank, first=first_h)
 
@@ -433,12 +525,18 @@ def topk_sharded(q_local: torch.Tensor, g_local: torch.Tensor, k: int, g_index_o
 
 
 def topk_and_eval(qp: Planes, gp: Planes, k: int, q_pids, g_pids, q_camids, g_camids, max_rank: int = 50,
-                  respect_camids: bool = False, ids: "Optional[EncodedIds]" = None):
+                  respect_camids: bool = False, ids: "Optional[EncodedIds]" = None, approx: Optional[bool] = None):
     """BASELINE config 3 in TWO tensor-core passes: per-query top-k (ascending (distance, index))
     AND eval_func's CMC / mAP, neither materialising the distance matrix.
       pass 1: 16-column group minima (-> tau) + the positives' distances
       pass 2: candidates <= tau + kept rows before each positive
-    Returns (idx [nq,k] int64, dist [nq,k] float32 on the device, EvalResult)."""
+    Pass 1 only needs EXACT distances for the positives: every tile whose query / gallery identity ranges are disjoint
+    runs with the leading fp16 product alone and tau gets the rigorous bound of the difference added
+    (ctl_select_tau_approx); pass 2 is exact, so indices, distances, ranks and AP are bit-identical to the all-exact run
+    (`approx=False`).  It pays off when both operands are stored in pid order: build_planes(order=pid_order(pids)).
+    Identities are given in the caller's row order; a precomputed `ids` must carry the planes' orders
+    (encode_ids(q_order=qp.order_host, g_order=gp.order_host)).
+    Returns (idx [nq,k] int64, dist [nq,k] float32 on the device, EvalResult), all in the caller's indexing."""
     import ctypes as C
 
     L = N.lib()
@@ -448,7 +546,10 @@ def topk_and_eval(qp: Planes, gp: Planes, k: int, q_pids, g_pids, q_camids, g_ca
     emit_all, n_groups, merge, cap = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
     N.check(L.ctl_topk_plan(ng, k, C.byref(emit_all), C.byref(n_groups), C.byref(merge), C.byref(cap)))
     if ids is None:
-        ids = encode_ids(q_pids, g_pids, q_camids, g_camids, respect_camids, dev)
+        ids = encode_ids(q_pids, g_pids, q_camids, g_camids, respect_camids, dev, q_order=qp.order_host,
+                         g_order=gp.order_host)
+    if approx is None:
+        approx = _approx_enabled(qp)
     d_qpid, d_qcam, d_gpid, d_gmask, max_pos = ids.q_pid, ids.q_cam, ids.g_pid, ids.g_mask, ids.max_pos
     gmin = torch.empty(nq, n_groups.value, dtype=torch.float32, device=dev)
     tau = torch.empty(nq, dtype=torch.float32, device=dev)
@@ -460,15 +561,23 @@ def topk_and_eval(qp: Planes, gp: Planes, k: int, q_pids, g_pids, q_camids, g_ca
     idx = torch.empty(nq, k, dtype=torch.int64, device=dev)
     dst = torch.empty(nq, k, dtype=torch.float32, device=dev)
     s = N.stream_ptr
+    gmap = _g_index_map(gp, 0)
     idp = dict(q_pid=d_qpid.data_ptr(), q_cam=d_qcam.data_ptr(), g_pid=d_gpid.data_ptr(),
-               g_cammask=d_gmask.data_ptr(), max_pos=max_pos, overflow=ovf.data_ptr())
+               g_cammask=d_gmask.data_ptr(), max_pos=max_pos, overflow=ovf.data_ptr(), g_index_map=N.ptr(gmap))
     with torch.cuda.device(dev):
         p1 = N.PassDesc(pos_keys=pos_keys.data_ptr(), pos_count=pos_count.data_ptr(), **idp)
         if not emit_all.value:
             p1.gmin = gmin.data_ptr()
+        if approx:
+            q_rng, g_rng, gerr = _cheap_tiles(qp, gp, ids, with_bound=not emit_all.value)
+            # small gallery (tau = +inf): pass 1 only collects, cheap tiles are skipped
+            p1.approx, p1.q_tile_range, p1.g_tile_range = (2 if emit_all.value else 1), q_rng.data_ptr(), g_rng.data_ptr()
         N.check(L.ctl_dist_pass(qp.ptr, nq, gp.ptr, ng, qp.d, qp.flags, C.byref(p1), s()))
         if emit_all.value:
             N.check(L.ctl_fill_f32(tau.data_ptr(), nq, float("inf"), s()))
+        elif approx:
+            N.check(L.ctl_select_tau_approx(gmin.data_ptr(), nq, n_groups.value, merge.value, k, qp.ptr, qp.d, qp.flags,
+                                            gerr.data_ptr(), tau.data_ptr(), s()))
         else:
             N.check(L.ctl_select_tau(gmin.data_ptr(), nq, n_groups.value, merge.value, k, tau.data_ptr(), s()))
         N.check(L.ctl_sort_key_rows(pos_keys.data_ptr(), pos_count.data_ptr(), nq, max_pos, s()))
@@ -480,18 +589,27 @@ def topk_and_eval(qp: Planes, gp: Planes, k: int, q_pids, g_pids, q_camids, g_ca
         N.check(L.ctl_topk_emit(cand.data_ptr(), cand_count.data_ptr(), nq, cap.value, k, idx.data_ptr(),
                                 dst.data_ptr(), ovf.data_ptr(), s()))
         ranks, ap_h, first_h, cnt_h, ovf_h = _finalize_and_read_back(buckets, pos_count, nq, max_pos, ovf)
+        if ovf_h and approx and not emit_all.value:
+            # more rows inside the bound of the threshold than the candidate list holds: the exact threshold pass
+            return topk_and_eval(qp, gp, k, q_pids, g_pids, q_camids, g_camids, max_rank, respect_camids, ids, approx=False)
+        inv_d, inv_h = _query_inverse(qp)
+        if inv_h is not None:  # back to the caller's query order
+            idx, dst, ranks = idx.index_select(0, inv_d), dst.index_select(0, inv_d), ranks.index_select(0, inv_d)
+            ap_h, first_h, cnt_h = ap_h[inv_h], first_h[inv_h], cnt_h[inv_h]
     if ovf_h:
         raise OverflowError("a device-side list overflowed (exact ties at the k-th distance, or max_pos)")
     return idx, dst, _aggregate(ranks, ap_h, cnt_h, np.asarray(q_pids), ng, max_rank, first=first_h)
 
 
-def encode_ids_sharded(q_pids, g_pids_local, q_camids, g_camids_local, device, group) -> EncodedIds:
+def encode_ids_sharded(q_pids, g_pids_local, q_camids, g_camids_local, device, group, q_order=None,
+                       g_order=None) -> EncodedIds:
     """Identity arrays of (all queries, THIS rank's gallery shard) for topk_and_eval_sharded: raw integer pids (every
     rank must agree on the labelling, so no np.unique), camera ids in [0, 64); `max_pos` = the largest number of
     same-pid rows of any shard (one MAX all-reduce, done once per validation set)."""
     import torch.distributed as dist
 
-    ids = encode_ids(q_pids, g_pids_local, q_camids, g_camids_local, False, device, global_labels=True)
+    ids = encode_ids(q_pids, g_pids_local, q_camids, g_camids_local, False, device, global_labels=True, q_order=q_order,
+                     g_order=g_order)
     mp = torch.tensor([ids.max_pos], device=device, dtype=torch.int64)
     dist.all_reduce(mp, op=dist.ReduceOp.MAX, group=group)
     ids.max_pos = int(mp.item())
@@ -499,7 +617,7 @@ def encode_ids_sharded(q_pids, g_pids_local, q_camids, g_camids_local, device, g
 
 
 def topk_and_eval_sharded(qp: Planes, gp_local: Planes, k: int, ids: EncodedIds, q_pids, g_index_offset: int,
-                          total_gallery: int, group, max_rank: int = 50):
+                          total_gallery: int, group, max_rank: int = 50, approx: Optional[bool] = None):
     """BASELINE config 5: topk_and_eval with the GALLERY AXIS SHARDED over the ranks of `group` (queries replicated:
     all-gather them once before building `qp`).  Every rank runs the two tensor-core passes over its own shard; the
     exchange steps are (utils/reid_metric.py:112-136 + utils/eval_reid.py:25-92 semantics, bit-identical to one GPU):
@@ -528,15 +646,25 @@ def topk_and_eval_sharded(qp: Planes, gp_local: Planes, k: int, ids: EncodedIds,
     pos_keys = torch.empty(nq, mp_l, dtype=torch.int64, device=dev)
     buckets = torch.zeros(nq, mp + 1, dtype=torch.int32, device=dev)
     s = N.stream_ptr
+    if approx is None:
+        approx = _approx_enabled(qp)
+    gmap = _g_index_map(gp_local, g_index_offset)  # pid-sorted shard: keys carry the GLOBAL gallery row
     idp = dict(q_pid=ids.q_pid.data_ptr(), q_cam=ids.q_cam.data_ptr(), g_pid=ids.g_pid.data_ptr(),
-               g_cammask=ids.g_mask.data_ptr(), overflow=ovf.data_ptr(), g_index_offset=g_index_offset)
+               g_cammask=ids.g_mask.data_ptr(), overflow=ovf.data_ptr(), g_index_offset=g_index_offset,
+               g_index_map=N.ptr(gmap))
     with torch.cuda.device(dev):
         p1 = N.PassDesc(pos_keys=pos_keys.data_ptr(), pos_count=pos_count.data_ptr(), max_pos=mp_l, **idp)
         if not emit_all.value:
             p1.gmin = gmin.data_ptr()
+        if approx:  # cheap tiles in the threshold / collect pass, as in topk_and_eval
+            q_rng, g_rng, gerr = _cheap_tiles(qp, gp_local, ids, with_bound=not emit_all.value)
+            p1.approx, p1.q_tile_range, p1.g_tile_range = (2 if emit_all.value else 1), q_rng.data_ptr(), g_rng.data_ptr()
         N.check(L.ctl_dist_pass(qp.ptr, nq, gp_local.ptr, ng, qp.d, qp.flags, C.byref(p1), s()))
         if emit_all.value:
             N.check(L.ctl_fill_f32(tau.data_ptr(), nq, float("inf"), s()))
+        elif approx:
+            N.check(L.ctl_select_tau_approx(gmin.data_ptr(), nq, n_groups.value, merge.value, k_loc, qp.ptr, qp.d, qp.flags,
+                                            gerr.data_ptr(), tau.data_ptr(), s()))
         else:
             N.check(L.ctl_select_tau(gmin.data_ptr(), nq, n_groups.value, merge.value, k_loc, tau.data_ptr(), s()))
         # exchange 1: every rank's positives, unused slots = the largest key, so ONE row sort packs and orders them
@@ -563,6 +691,12 @@ def topk_and_eval_sharded(qp: Planes, gp_local: Planes, k: int, ids: EncodedIds,
         dist.all_reduce(ovf, op=dist.ReduceOp.MAX, group=group)
         idx, dst = merge_topk_keys(g_best.permute(1, 0, 2).reshape(nq, world * k_loc), int(min(k, world * k_loc)))
         ranks, ap_h, first_h, cnt_h, ovf_h = _finalize_and_read_back(buckets, thr_count, nq, mp, ovf)
+        if ovf_h and approx and not emit_all.value:  # (the flag is MAX-reduced: every rank takes this branch together)
+            return topk_and_eval_sharded(qp, gp_local, k, ids, q_pids, g_index_offset, total_gallery, group, max_rank, approx=False)
+        inv_d, inv_h = _query_inverse(qp)
+        if inv_h is not None:  # back to the caller's query order
+            idx, dst, ranks = idx.index_select(0, inv_d), dst.index_select(0, inv_d), ranks.index_select(0, inv_d)
+            ap_h, first_h, cnt_h = ap_h[inv_h], first_h[inv_h], cnt_h[inv_h]
     if ovf_h:
         raise OverflowError("a device-side list overflowed on some rank (exact ties at the k-th distance, or max_pos)")
     return idx, dst, _aggregate(ranks, ap_h, cnt_h, np.asarray(q_pids), total_gallery, max_rank, first=first_h)

@@ -77,7 +77,8 @@ def eval_streamed(q_feats, g_feats, q_pids, g_pids, q_camids, g_camids, max_rank
         q = q.cuda(non_blocking=True)
     if not g.is_cuda:
         g = g.cuda(non_blocking=True)
-    qp = _R.build_planes(q, dist_func, feat_norm)
-    gp = _R.build_planes(g, dist_func, feat_norm)
+    go = _R.pid_order(g_pids) if len(g_pids) == g.shape[0] else None  # identity order: cheap collect pass
+    qp = _R.build_planes(q, dist_func, feat_norm, order=_R.pid_order(q_pids))
+    gp = _R.build_planes(g, dist_func, feat_norm, order=go)
     res = _R.evaluate_streamed(qp, gp, q_pids, g_pids, q_camids, g_camids, max_rank, respect_camids)
     return res.cmc, res.mAP, res.all_topk, res.single_performance

@@ -76,8 +76,12 @@ class R1_mAP:
             raise NotImplementedError("ranked-result visualisation (utils/visrank.py) is outside the B200 hot path")
         # reid_metric.py:113-136: F.normalize -> dist -> argsort -> eval_func(.., 50, ..), fused.
         # (the reference hard-codes max_rank=50 in the eval_func call, :134-136)
-        qp = _R.build_planes(feats[:nq], self.dist_name, self.feat_norm)
-        gp = _R.build_planes(feats[nq:], self.dist_name, self.feat_norm)
+        # both operands are stored in identity order: the collect pass then skips every tile that cannot hold a positive
+        # (retrieval.pid_order); results come back in the caller's indexing, bit-identical to the unsorted run
+        qo = _R.pid_order(q_pids)
+        go = _R.pid_order(g_pids) if len(g_pids) == feats.shape[0] - nq else None
+        qp = _R.build_planes(feats[:nq], self.dist_name, self.feat_norm, order=qo)
+        gp = _R.build_planes(feats[nq:], self.dist_name, self.feat_norm, order=go)
         res = _R.evaluate_streamed(qp, gp, q_pids, g_pids, q_camids, g_camids, 50, respect_camids)
         self.last_result = res
         return res.cmc, res.mAP, res.all_topk
