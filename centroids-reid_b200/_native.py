@@ -54,7 +54,7 @@ class PassDesc(C.Structure):
                 ("cand_count", _p), ("cand_cap", _i32), ("q_pid", _p), ("q_cam", _p), ("g_pid", _p),
                 ("g_cammask", _p), ("pos_keys", _p), ("pos_count", _p), ("max_pos", _i32), ("thr_keys", _p),
                 ("thr_count", _p), ("buckets", _p), ("overflow", _p), ("g_index_offset", _i64),
-                ("approx", _i32), ("q_tile_range", _p), ("g_tile_range", _p), ("g_index_map", _p)]
+                ("tile_list", _p), ("g_index_map", _p)]
 
 class NamedTensor(C.Structure):
     """struct ctl_named_tensor (include/ctl_b200.h)."""
@@ -81,8 +81,9 @@ SIGNATURES = {
     "ctl_debug_set_dist_profile": (None, [_p]),
     "ctl_topk_plan": (C.c_int, [_i64, _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     "ctl_select_tau": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p]),
-    "ctl_select_tau_approx": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _i32, _i32, _p, _p, _p]),
-    "ctl_dist_prep": (C.c_int, [_p, _i64, _p, _i64, _i32, _p, _p, _p, _p, _p, _p]),
+    "ctl_dist_worklist_bytes": (_sz, [_i64, _i64]),
+    "ctl_dist_subset_stride": (C.c_int, [_i64, _i32]),
+    "ctl_dist_worklist": (C.c_int, [_p, _i64, _p, _i64, _i32, _p, _p]),
     "ctl_fill_f32": (C.c_int, [_p, _i64, C.c_float, _p]),
     "ctl_topk_emit": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p, _p, _p]),
     "ctl_key_encode": (C.c_uint64, [C.c_float, C.c_uint32]),

@@ -34,7 +34,7 @@ static constexpr int TILE_BYTES = BM * BK * 2;          // 16 KiB
 static constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // q_hi, q_lo, g_hi, g_lo
 static constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 static constexpr int GROUP_W = 16;                      // columns per group-min
-static constexpr int META_BYTES = 2 * BN * (4 + 4 + 4 + 8);  // double-buffered per-tile column metadata
+static constexpr int META_BYTES = 2 * BN * (4 + 4 + 4 + 8 + 4);  // double-buffered per-tile column metadata
 static constexpr int THR_MAX = 44, THR_STRIDE = 45;         // positives per query held in shared memory
 static constexpr int THR_BYTES = BM * THR_STRIDE * 4;
 static constexpr size_t GEMM_SMEM = STAGES * STAGE_BYTES + META_BYTES + THR_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -73,16 +73,11 @@ struct PlanesView {
   const __half* lo;
   const float* sq;
   const float* inv_scale;
-  const float* hn;  // |hi| / s         (un-scaled norm of the leading plane)
-  const float* ln;  // 2^-11 |lo| / s   (un-scaled norm of the correction plane): the hi-only product of a pair (q, g)
-                    // differs from the three-product value by at most hn_q ln_g + ln_q hn_g
 };
 static size_t planes_off_lo(int64_t n, int32_t d) { return ((size_t)n * d * 2 + 255) & ~size_t(255); }
 static size_t planes_off_sq(int64_t n, int32_t d) { return 2 * planes_off_lo(n, d); }
 static size_t planes_off_is(int64_t n, int32_t d) { return planes_off_sq(n, d) + (((size_t)n * 4 + 255) & ~size_t(255)); }
-static size_t planes_off_hn(int64_t n, int32_t d) { return planes_off_is(n, d) + (((size_t)n * 4 + 255) & ~size_t(255)); }
-static size_t planes_off_ln(int64_t n, int32_t d) { return planes_off_hn(n, d) + (((size_t)n * 4 + 255) & ~size_t(255)); }
-static size_t planes_total(int64_t n, int32_t d) { return planes_off_ln(n, d) + (((size_t)n * 4 + 255) & ~size_t(255)); }
+static size_t planes_total(int64_t n, int32_t d) { return planes_off_is(n, d) + (((size_t)n * 4 + 255) & ~size_t(255)); }
 static PlanesView planes_view(const void* p, int64_t n, int32_t d) {
   const char* c = static_cast<const char*>(p);
   PlanesView v;
@@ -90,8 +85,6 @@ static PlanesView planes_view(const void* p, int64_t n, int32_t d) {
   v.lo = reinterpret_cast<const __half*>(c + planes_off_lo(n, d));
   v.sq = reinterpret_cast<const float*>(c + planes_off_sq(n, d));
   v.inv_scale = reinterpret_cast<const float*>(c + planes_off_is(n, d));
-  v.hn = reinterpret_cast<const float*>(c + planes_off_hn(n, d));
-  v.ln = reinterpret_cast<const float*>(c + planes_off_ln(n, d));
   return v;
 }
 
@@ -111,8 +104,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // exact hi/lo split and the fp32 squared norm of the (normalised) row.
 __global__ void __launch_bounds__(128) planes_build_kernel(const float* __restrict__ x, int64_t n, int d, int n_norm,
                                                            __half* __restrict__ hi, __half* __restrict__ lo,
-                                                           float* __restrict__ sq, float* __restrict__ inv_scale,
-                                                           float* __restrict__ hn, float* __restrict__ ln) {
+                                                           float* __restrict__ sq, float* __restrict__ inv_scale) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= n) return;
@@ -145,7 +137,6 @@ __global__ void __launch_bounds__(128) planes_build_kernel(const float* __restri
     sexp = min(14 - e, 120);   // mx * 2^sexp in [2^13, 2^14)
   }
   const float scale = scalbnf(1.f, sexp);
-  float shi = 0.f, slo = 0.f;
   for (int i = lane; i < d; i += 32) {
     float v = xr[i];
     if (n_norm > 0) v = __fdiv_rn(v, denom[0]);
@@ -153,20 +144,12 @@ __global__ void __launch_bounds__(128) planes_build_kernel(const float* __restri
     const float vs = v * scale;  // exact (power of two)
     const __half h = __float2half_rn(vs);
     const float r = vs - __half2float(h);  // exact remainder
-    const __half l = __float2half_rn(r * 2048.f);
     hi[row * d + i] = h;
-    lo[row * d + i] = l;
-    shi = __fmaf_rn(__half2float(h), __half2float(h), shi);
-    slo = __fmaf_rn(__half2float(l), __half2float(l), slo);
+    lo[row * d + i] = __float2half_rn(r * 2048.f);
   }
-  shi = warp_sum(shi);
-  slo = warp_sum(slo);
   if (lane == 0) {
     sq[row] = ss;
-    const float is = scalbnf(1.f, -sexp);
-    inv_scale[row] = is;
-    hn[row] = __fsqrt_ru(shi) * is;                    // power-of-two scale: exact
-    ln[row] = __fsqrt_ru(slo) * is * 4.8828125e-4f;    // 2^-11
+    inv_scale[row] = scalbnf(1.f, -sexp);
   }
 }
 
@@ -205,12 +188,10 @@ struct GemmPass {
   const int* thr_count;
   int* buckets;
   int* overflow;
-  // cheap tiles: a (query tile, gallery tile) pair whose identity ranges are disjoint holds no positive, so a pass that
-  // only needs exact distances for the positives may run it with the leading product only (approx == 1: group minima
-  // within a known bound of the exact ones) or skip it altogether (approx == 2: collect-only passes)
-  int approx;
-  const int2* q_range;  // [m_tiles] {min pid, max pid}; nullptr: no identities, every tile is cheap
-  const int2* g_range;  // [n_tiles]
+  // optional tile list (ctl_dist_worklist): work[0] = number of tiles to run, work[1..] their ids in ascending order.
+  // A pass that only collects the positives and a threshold needs the tiles that can hold a positive plus a subset for
+  // the group minima -- with both operands stored in identity order that is a fraction of the matrix.
+  const int* work;
   const int* g_map;     // optional: gallery row -> index written into the keys (rows stored in another order)
   long long* prof;  // debug: [grid][8] epilogue cycle counters (tools/prof_retrieval.py)
 };
@@ -265,17 +246,6 @@ __device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, 
   nt = band * band_w + rem % w;
 }
 
-// 0: three products (exact), 1: leading product only, 2: tile skipped.  Every role of the CTA evaluates this on the same
-// two global words, so they agree on the tile sequence.
-__device__ __forceinline__ int tile_mode(const GemmPass& p, int mt, int nt) {
-  if (!p.approx) return 0;
-  if (p.q_range) {
-    const int2 a = p.q_range[mt], b = p.g_range[nt];
-    if (!(b.y < a.x || b.x > a.y)) return 0;
-  }
-  return p.approx;
-}
-
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     dist_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmPass p) {
   extern __shared__ uint8_t smem_raw[];
@@ -292,7 +262,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int num_work = p.work ? p.work[0] : p.m_tiles * p.n_tiles;  // every role walks the same tile sequence
   const int k_blocks = (p.d + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
@@ -324,19 +294,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int tile = p.work ? p.work[1 + w] : w;
         int mt, nt;
         tile_coords(tile, p.m_tiles, p.n_tiles, mt, nt);
-        const int mode = tile_mode(p, mt, nt);
-        if (mode == 2) continue;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t dst = smem_base + stage * STAGE_BYTES;
-          mbar_arrive_expect_tx(full_bar(stage), mode ? 2 * TILE_BYTES : STAGE_BYTES);
+          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
           tma_load_2d(dst + 0 * TILE_BYTES, &maps.q_hi, full_bar(stage), kb * BK, mt * BM);
-          if (!mode) tma_load_2d(dst + 1 * TILE_BYTES, &maps.q_lo, full_bar(stage), kb * BK, mt * BM);
+          tma_load_2d(dst + 1 * TILE_BYTES, &maps.q_lo, full_bar(stage), kb * BK, mt * BM);
           tma_load_2d(dst + 2 * TILE_BYTES, &maps.g_hi, full_bar(stage), kb * BK, nt * BN);
-          if (!mode) tma_load_2d(dst + 3 * TILE_BYTES, &maps.g_lo, full_bar(stage), kb * BK, nt * BN);
+          tma_load_2d(dst + 3 * TILE_BYTES, &maps.g_lo, full_bar(stage), kb * BK, nt * BN);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -352,11 +321,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        int mt, nt;
-        tile_coords(tile, p.m_tiles, p.n_tiles, mt, nt);
-        const int mode = tile_mode(p, mt, nt);
-        if (mode == 2) continue;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
         const uint32_t acc0 = tmem_base + as * 256;
@@ -373,10 +338,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           for (int k = 0; k < BK / 16; ++k) {
             const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
             umma_f16(acc0, desc_advance_k(d_qh, k), desc_advance_k(d_gh, k), idesc, acc);
-            if (!mode) {
-              umma_f16(acc1, desc_advance_k(d_qh, k), desc_advance_k(d_gl, k), idesc, acc);
-              umma_f16(acc1, desc_advance_k(d_ql, k), desc_advance_k(d_gh, k), idesc, 1u);
-            }
+            umma_f16(acc1, desc_advance_k(d_qh, k), desc_advance_k(d_gl, k), idesc, acc);
+            umma_f16(acc1, desc_advance_k(d_ql, k), desc_advance_k(d_gh, k), idesc, 1u);
           }
           umma_commit(empty_bar(stage));  // smem slot free once these MMAs have read it
           if (++stage == STAGES) {
@@ -405,6 +368,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     float* cm_is = cm_sq + 2 * BN;
     int* cm_pid = reinterpret_cast<int*>(cm_is + 2 * BN);
     unsigned long long* cm_mask = reinterpret_cast<unsigned long long*>(cm_pid + 2 * BN);
+    unsigned int* cm_idx = reinterpret_cast<unsigned int*>(cm_mask + 2 * BN);  // index written into the keys
     uint32_t* thr_s = reinterpret_cast<uint32_t*>(smem_raw + (thr_base - smem_u32(smem_raw)));
     int as = 0;
     uint32_t aphase = 0;
@@ -417,11 +381,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     pc[i] += _t - tprev;            \
     tprev = _t;                     \
   }
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+      const int tile = p.work ? p.work[1 + w] : w;
       int mt, nt;
       tile_coords(tile, p.m_tiles, p.n_tiles, mt, nt);
-      const int mode = tile_mode(p, mt, nt);
-      if (mode == 2) continue;  // `it` (metadata slice parity) counts PROCESSED tiles only
       const int row = mt * BM + row_in_tile;
       const bool row_ok = row < p.nq;
       const int mb = (it & 1) * BN;  // double-buffered metadata slice
@@ -430,6 +393,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         const bool ok = col < p.ng;
         cm_sq[mb + et] = ok ? p.g_sq[col] : 0.f;
         cm_is[mb + et] = ok ? p.g_is[col] : 0.f;
+        cm_idx[mb + et] = (ok && p.g_map) ? static_cast<unsigned int>(p.g_map[col]) : static_cast<unsigned int>(col + p.g_off);
         if (p.q_pid) {
           cm_pid[mb + et] = ok ? p.g_pid[col] : -2;
           cm_mask[mb + et] = ok ? p.g_mask[col] : 0ull;
@@ -494,12 +458,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       for (int c = 0; c < 4; ++c) {
         uint32_t r0[16], r1[16];
         tmem_ld16(t0 + c * 16, r0);
-        if (!mode) {
-          tmem_ld16(t0 + 128 + c * 16, r1);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) r1[j] = 0u;  // the correction accumulator was not computed: fma(0, 2^-11, acc0) == acc0
-        }
+        tmem_ld16(t0 + 128 + c * 16, r1);
         tmem_ld_wait();
         CTL_STAMP(3)
         const int cl0 = chalf * 64 + c * 16;  // column inside the tile
@@ -557,7 +516,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             const uint32_t bit = 1u << j;
             m_any &= ~bit;
             const float dj = select16(dist, j);
-            const unsigned int gidx = p.g_map ? static_cast<unsigned int>(p.g_map[col0 + j]) : static_cast<unsigned int>(col0 + j + p.g_off);
+            const unsigned int gidx = cm_idx[mb + cl0 + j];
             const unsigned long long key = make_key(dj, gidx);
             if (m_cand & bit) {
               const int slot = atomicAdd(p.cand_count + row, 1);
@@ -596,7 +555,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       if (lane == 0) mbar_arrive(tempty_bar(as));
       if (thr_in_smem) named_bar_sync(2, 256);  // nobody still reads this tile's thresholds
       CTL_STAMP(5)
-      ++it;
       if (++as == 2) {
         as = 0;
         aphase ^= 1u;
@@ -648,11 +606,8 @@ __device__ __forceinline__ void bitonic_sort_smem(T* s, int n_pow2) {
 // Radix select on the order-preserving uint32 keys (4 passes of 8 bits, shared-memory histogram + warp scan): the k-th
 // smallest needs no sort -- round 1 sorted all n_merged keys with a bitonic network (55 block-wide stages for 1024 keys,
 // 128 us for 3368 queries; this form: ~20 us).
-// With `q_hn` (approximate group minima, ctl_dist_pass approx == 1): tau += the bound of |approximate - exact| distance
-// of this query against ANY gallery row, so that {exact distance <= tau} still contains the k nearest rows.
 __global__ void __launch_bounds__(256) select_tau_kernel(const float* __restrict__ gmin, int n_groups, int merge, int k,
-                                                         int n_pow2, float* __restrict__ tau, const float* __restrict__ q_hn,
-                                                         const float* __restrict__ q_ln, const float* __restrict__ g_err_max) {
+                                                         int n_pow2, float* __restrict__ tau) {
   extern __shared__ uint32_t skeys[];
   __shared__ int hist[256];
   __shared__ int s_bucket, s_k;
@@ -710,69 +665,61 @@ __global__ void __launch_bounds__(256) select_tau_kernel(const float* __restrict
     kk = s_k;
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    float t = orderable_float(prefix);
-    if (q_hn) {
-      // |dot(hi-only) - dot(3 products)| <= hn_q * max ln_g + ln_q * max hn_g (Cauchy-Schwarz on the two dropped products);
-      // a squared distance moves by twice that, a cosine distance by once (2x kept: conservative).  1 % + an absolute
-      // term cover the fp32 roundings of the norms, of the accumulators and of the final fma.
-      const float hq = q_hn[blockIdx.x], lq = q_ln[blockIdx.x], gl = g_err_max[0], gh = g_err_max[1];
-      const float e = __fmaf_ru(hq, gl, __fmul_ru(lq, gh));
-      t = __fadd_ru(t, __fmaf_ru(2.02f, e, 4e-6f * __fmaf_ru(hq, hq, __fmul_ru(gh, gh))));
-    }
-    tau[blockIdx.x] = t;
-  }
+  if (threadIdx.x == 0) tau[blockIdx.x] = orderable_float(prefix);
 }
 
-// per-tile identity ranges and the gallery-wide maxima of the two plane norms (inputs of the cheap-tile decision and of
-// the tau margin).  blocks [0, m_tiles): query tiles; blocks [m_tiles, m_tiles + n_tiles): gallery tiles.
-__global__ void __launch_bounds__(BM) dist_prep_kernel(const int* __restrict__ q_pid, int nq, int m_tiles, const int* __restrict__ g_pid,
-                                                        int ng, const float* __restrict__ g_hn, const float* __restrict__ g_ln,
-                                                        int2* __restrict__ q_range, int2* __restrict__ g_range,
-                                                        unsigned int* __restrict__ g_err_max) {
-  __shared__ int s_lo[BM / 32], s_hi[BM / 32];
-  __shared__ float s_h[BM / 32], s_l[BM / 32];
-  const bool is_q = (int)blockIdx.x < m_tiles;
-  const int t = is_q ? blockIdx.x : blockIdx.x - m_tiles;
-  const int row = t * BM + threadIdx.x;
-  const int n = is_q ? nq : ng;
-  const int* pid = is_q ? q_pid : g_pid;
-  int lo = INT_MAX, hi = INT_MIN;
-  float h = 0.f, l = 0.f;
-  if (row < n) {
-    if (pid) lo = hi = pid[row];
-    if (!is_q && g_err_max) {
-      h = g_hn[row];
-      l = g_ln[row];
-    }
+// Tile list of a collect / threshold pass (ONE block): a tile is kept if the identity ranges of its 128 query rows and
+// its 128 gallery rows intersect (it may hold a positive) or if its gallery tile index is a multiple of `keep_stride`
+// (the subset of the matrix the group minima -- hence tau -- are taken from; 0: none).  Phase 1: {min, max} pid of every
+// row tile into shared memory; phase 2: the kept tile ids in ascending order (block-wide prefix sums), work[0] = count.
+static constexpr int WL_THREADS = 1024;
+static constexpr int WL_MAX_ROW_TILES = 5632;  // int2 each: 44 KiB of shared memory
+
+__global__ void __launch_bounds__(WL_THREADS) dist_worklist_kernel(const int* __restrict__ q_pid, int nq, int m_tiles,
+                                                                   const int* __restrict__ g_pid, int ng, int n_tiles,
+                                                                   int keep_stride, int* __restrict__ work) {
+  extern __shared__ int2 s_rng[];  // [m_tiles + n_tiles]
+  __shared__ int s_warp[WL_THREADS / 32];
+  __shared__ int s_base;
+  for (int t = threadIdx.x; t < m_tiles + n_tiles; t += blockDim.x) {
+    const bool is_q = t < m_tiles;
+    const int* pid = is_q ? q_pid : g_pid;
+    const int n = is_q ? nq : ng;
+    const int r0 = (is_q ? t : t - m_tiles) * BM, r1 = min(n, r0 + BM);
+    int lo = INT_MAX, hi = INT_MIN;
+    if (pid)
+      for (int r = r0; r < r1; ++r) {
+        const int v = pid[r];
+        lo = min(lo, v);
+        hi = max(hi, v);
+      }
+    s_rng[t] = make_int2(lo, hi);
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-    h = fmaxf(h, __shfl_xor_sync(0xffffffffu, h, o));
-    l = fmaxf(l, __shfl_xor_sync(0xffffffffu, l, o));
-  }
-  if ((threadIdx.x & 31) == 0) {
-    s_lo[threadIdx.x >> 5] = lo;
-    s_hi[threadIdx.x >> 5] = hi;
-    s_h[threadIdx.x >> 5] = h;
-    s_l[threadIdx.x >> 5] = l;
-  }
+  if (threadIdx.x == 0) s_base = 0;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < BM / 32; ++w) {
-      lo = min(lo, s_lo[w]);
-      hi = max(hi, s_hi[w]);
-      h = fmaxf(h, s_h[w]);
-      l = fmaxf(l, s_l[w]);
+  const int num_tiles = m_tiles * n_tiles;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int t0 = 0; t0 < num_tiles; t0 += blockDim.x) {
+    const int tile = t0 + threadIdx.x;
+    int keep = 0;
+    if (tile < num_tiles) {
+      int mt, nt;
+      tile_coords(tile, m_tiles, n_tiles, mt, nt);
+      const int2 a = s_rng[mt], b = s_rng[m_tiles + nt];
+      keep = (!(b.y < a.x || b.x > a.y)) || (keep_stride > 0 && nt % keep_stride == 0);
     }
-    if (pid) (is_q ? q_range : g_range)[t] = make_int2(lo, hi);
-    if (!is_q && g_err_max) {  // non-negative floats order like their bit patterns
-      atomicMax(g_err_max + 0, __float_as_uint(l));
-      atomicMax(g_err_max + 1, __float_as_uint(h));
-    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[warp] = __popc(ballot);
+    __syncthreads();
+    int before = 0;
+    for (int w2 = 0; w2 < warp; ++w2) before += s_warp[w2];
+    const int base = s_base;
+    if (keep) work[1 + base + before + __popc(ballot & ((1u << lane) - 1u))] = tile;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) s_base = base + before + __popc(ballot);
+    __syncthreads();
   }
+  if (threadIdx.x == 0) work[0] = s_base;
 }
 
 __global__ void sort_key_rows_kernel(unsigned long long* __restrict__ keys, const int* __restrict__ counts,
@@ -920,6 +867,36 @@ static int next_pow2(int v) {
   return p;
 }
 
+static constexpr long long WORK_MAX_TILES = 1 << 20;  // beyond this the single-block list builder is not worth it
+static size_t worklist_ints(int64_t nq, int64_t ng) {
+  const long long tiles = ((nq + BM - 1) / BM) * ((ng + BN - 1) / BN);
+  return (size_t)std::min<long long>(tiles, WORK_MAX_TILES) + 1;
+}
+// every `stride`-th gallery tile leaves >= ~2.5 k merged groups for the k-th smallest group minimum
+static int subset_stride(int n_tiles, int merge, int k) {
+  if (merge > 1) return 1;  // merged groups span tiles (galleries > 131 072 rows): keep every tile
+  const long long groups_per_tile = BN / GROUP_W;
+  const long long want = (5LL * k + 1) / 2;
+  const long long tiles_needed = (want + groups_per_tile - 1) / groups_per_tile;
+  return (int)std::max<long long>(1, n_tiles / std::max<long long>(1, tiles_needed));
+}
+static int launch_worklist(const int* q_pid, int64_t nq, const int* g_pid, int64_t ng, int keep_stride, int* work, cudaStream_t stream) {
+  const int m_tiles = (int)((nq + BM - 1) / BM), n_tiles = (int)((ng + BN - 1) / BN);
+  if ((long long)m_tiles * n_tiles > WORK_MAX_TILES || m_tiles + n_tiles > WL_MAX_ROW_TILES) {
+    set_error("tile list: %d x %d tiles exceed the list builder (run the pass without a list)", m_tiles, n_tiles);
+    return CTL_ERR_UNSUPPORTED;
+  }
+  const size_t smem = (size_t)(m_tiles + n_tiles) * sizeof(int2);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CTL_CUDA(cudaFuncSetAttribute(dist_worklist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WL_MAX_ROW_TILES * sizeof(int2))));
+    attr_set = true;
+  }
+  dist_worklist_kernel<<<1, WL_THREADS, smem, stream>>>(q_pid, (int)nq, m_tiles, g_pid, (int)ng, n_tiles, keep_stride, work);
+  CTL_LAUNCH_CHECK();
+  return 0;
+}
+
 struct TopkPlan {
   bool emit_all;
   int n_groups;   // GROUP_W-wide groups
@@ -975,8 +952,7 @@ int ctl_planes_build(const float* x, int64_t n, int32_t d, int32_t flags, void* 
   const int n_norm = ((flags & CTL_FLAG_NORMALIZE) ? 1 : 0) + ((flags & CTL_DIST_COSINE) ? 1 : 0);
   planes_build_kernel<<<(unsigned)((n + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
       x, n, d, n_norm, reinterpret_cast<__half*>(c), reinterpret_cast<__half*>(c + planes_off_lo(n, d)),
-      reinterpret_cast<float*>(c + planes_off_sq(n, d)), reinterpret_cast<float*>(c + planes_off_is(n, d)),
-      reinterpret_cast<float*>(c + planes_off_hn(n, d)), reinterpret_cast<float*>(c + planes_off_ln(n, d)));
+      reinterpret_cast<float*>(c + planes_off_sq(n, d)), reinterpret_cast<float*>(c + planes_off_is(n, d)));
   CTL_LAUNCH_CHECK();
   return 0;
 }
@@ -998,7 +974,7 @@ size_t ctl_topk_workspace_bytes(int64_t nq, int64_t ng, int32_t k) {
   ws.take<float>((size_t)nq);
   ws.take<unsigned long long>((size_t)nq * pl.cap);
   ws.take<int>((size_t)nq);
-  ws.take<float>(2);
+  ws.take<int>(worklist_ints(nq, ng));
   return ws.off;
 }
 
@@ -1017,8 +993,8 @@ int ctl_l2_topk(const void* q_planes, int64_t nq, const void* g_planes, int64_t 
   float* tau = ws.take<float>((size_t)nq);
   unsigned long long* cand = ws.take<unsigned long long>((size_t)nq * pl.cap);
   int* cand_count = ws.take<int>((size_t)nq);
-  float* g_err_max = ws.take<float>(2);
-  if (!gmin || !tau || !cand || !cand_count || !g_err_max) {
+  int* work = ws.take<int>(worklist_ints(nq, ng));
+  if (!gmin || !tau || !cand || !cand_count || !work) {
     set_error("workspace too small: need %zu bytes, have %zu", ws.off, workspace_bytes);
     return CTL_ERR_WORKSPACE;
   }
@@ -1029,22 +1005,24 @@ int ctl_l2_topk(const void* q_planes, int64_t nq, const void* g_planes, int64_t 
     fill_f32_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, stream>>>(tau, nq, INFINITY);
     CTL_LAUNCH_CHECK();
   } else {
-    // pass A: minima of 16-column groups -> tau = k-th smallest group minimum.  No identities here, so pass A only feeds
-    // the threshold: it runs with the leading fp16 product alone (half the operand traffic, a third of the tensor work)
-    // and tau gets the rigorous bound of the difference added (ctl_select_tau_approx) -- pass B is exact either way.
-    const bool approx = !(flags & (CTL_DIST_SQRT | CTL_FLAG_EXACT_PASS));
+    // pass A: minima of 16-column groups -> tau = k-th smallest group minimum, an upper bound of the k-th smallest
+    // distance.  ANY subset of the groups gives such a bound, so pass A only runs every `stride`-th gallery tile (about
+    // 2.5 k groups: the bound gets looser, the candidate lists longer -- still exact); the other groups read +inf.
+    const int n_tiles = (int)((ng + BN - 1) / BN), m_tiles = (int)((nq + BM - 1) / BM);
+    int stride = (flags & CTL_FLAG_EXACT_PASS) ? 1 : subset_stride(n_tiles, pl.merge, k);
+    if ((long long)m_tiles * n_tiles > WORK_MAX_TILES || m_tiles + n_tiles > WL_MAX_ROW_TILES) stride = 1;
     GemmPass a = {};
     a.gmin = gmin;
     a.n_groups = pl.n_groups;
-    a.approx = approx ? 1 : 0;
-    if (approx) {
-      CTL_CUDA(cudaMemsetAsync(g_err_max, 0, 2 * sizeof(float), stream));
-      if ((rc = ctl_dist_prep(q_planes, nq, g_planes, ng, d, nullptr, nullptr, nullptr, nullptr, g_err_max, stream))) return rc;
+    if (stride > 1) {
+      fill_f32_kernel<<<(unsigned)(((size_t)nq * pl.n_groups + 255) / 256), 256, 0, stream>>>(gmin, (int64_t)nq * pl.n_groups, INFINITY);
+      CTL_LAUNCH_CHECK();
+      if ((rc = launch_worklist(nullptr, nq, nullptr, ng, stride, work, stream))) return rc;
+      a.work = work;
     }
     if ((rc = launch_gemm_pass(q_planes, nq, g_planes, ng, d, flags, a, stream))) return rc;
-    const PlanesView qv = planes_view(q_planes, nq, d);
-    select_tau_kernel<<<(unsigned)nq, 256, pl.n_merged_pow2 * sizeof(uint32_t), stream>>>(
-        gmin, pl.n_groups, pl.merge, k, pl.n_merged_pow2, tau, approx ? qv.hn : nullptr, approx ? qv.ln : nullptr, g_err_max);
+    select_tau_kernel<<<(unsigned)nq, 256, pl.n_merged_pow2 * sizeof(uint32_t), stream>>>(gmin, pl.n_groups, pl.merge, k,
+                                                                                         pl.n_merged_pow2, tau);
     CTL_LAUNCH_CHECK();
   }
   // pass B: rows with distance <= tau become (distance, index) keys
@@ -1170,15 +1148,9 @@ int ctl_dist_pass(const void* q_planes, int64_t nq, const void* g_planes, int64_
   p.g_off = e.g_index_offset;
   p.prof = g_dist_prof;
   CTL_CHECK_ARG(e.g_index_offset >= 0 && e.g_index_offset + ng < (1ll << 32), "gallery index out of uint32 range");
-  CTL_CHECK_ARG(e.approx >= 0 && e.approx <= 2, "approx must be 0, 1 or 2");
-  CTL_CHECK_ARG((e.q_tile_range == nullptr) == (e.g_tile_range == nullptr), "q_tile_range and g_tile_range come together");
-  CTL_CHECK_ARG(!e.approx || !(e.dist_out || e.cand_keys || e.buckets),
-                "cheap tiles give approximate distances: not for the full matrix, the candidates or the bucket counts");
-  CTL_CHECK_ARG(e.approx != 2 || !e.gmin, "skipped tiles produce no group minima (approx == 2 is for collect-only passes)");
-  CTL_CHECK_ARG(!e.approx || !e.pos_keys || e.q_tile_range, "collecting positives with cheap tiles needs the tile identity ranges");
-  p.approx = e.approx;
-  p.q_range = e.approx ? reinterpret_cast<const int2*>(e.q_tile_range) : nullptr;
-  p.g_range = e.approx ? reinterpret_cast<const int2*>(e.g_tile_range) : nullptr;
+  CTL_CHECK_ARG(!e.tile_list || !(e.dist_out || e.cand_keys || e.buckets),
+                "a tile list drops tiles: not for the full matrix, the candidates or the bucket counts");
+  p.work = e.tile_list;
   p.g_map = e.g_index_map;
   if (!p.pos_keys && !p.buckets) p.q_pid = nullptr;  // identities unused
   return launch_gemm_pass(q_planes, nq, g_planes, ng, d, flags, p, (cudaStream_t)stream);
@@ -1204,46 +1176,30 @@ int ctl_select_tau(const float* gmin, int64_t nq, int32_t n_groups, int32_t merg
   int rc = ctl_device_check();
   if (rc) return rc;
   const int np2 = next_pow2(n_merged);
-  select_tau_kernel<<<(unsigned)nq, 256, np2 * sizeof(uint32_t), (cudaStream_t)stream>>>(gmin, n_groups, merge, k, np2, tau, nullptr,
-                                                                                         nullptr, nullptr);
+  select_tau_kernel<<<(unsigned)nq, 256, np2 * sizeof(uint32_t), (cudaStream_t)stream>>>(gmin, n_groups, merge, k, np2, tau);
   CTL_LAUNCH_CHECK();
   return 0;
 }
 
-int ctl_select_tau_approx(const float* gmin, int64_t nq, int32_t n_groups, int32_t merge, int32_t k, const void* q_planes, int32_t d,
-                          int32_t flags, const float* g_err_max, float* tau, ctl_stream_t stream) {
-  CTL_CHECK_ARG(gmin && tau && q_planes && g_err_max && nq > 0 && n_groups > 0 && merge >= 1 && k >= 1 && d > 0, "bad arguments");
-  CTL_CHECK_ARG(!(flags & CTL_DIST_SQRT), "the approximate first pass has no error bound for CTL_DIST_SQRT distances");
-  const int n_merged = (n_groups + merge - 1) / merge;
-  CTL_CHECK_ARG(n_merged >= k && n_merged <= SELECT_MAX, "need k <= merged groups <= %d (have %d)", SELECT_MAX, n_merged);
-  int rc = ctl_device_check();
-  if (rc) return rc;
-  const PlanesView q = planes_view(q_planes, nq, d);
-  const int np2 = next_pow2(n_merged);
-  select_tau_kernel<<<(unsigned)nq, 256, np2 * sizeof(uint32_t), (cudaStream_t)stream>>>(gmin, n_groups, merge, k, np2, tau, q.hn, q.ln,
-                                                                                         g_err_max);
-  CTL_LAUNCH_CHECK();
-  return 0;
+size_t ctl_dist_worklist_bytes(int64_t nq, int64_t ng) {
+  if (nq < 1 || ng < 1) return 0;
+  return worklist_ints(nq, ng) * sizeof(int);
 }
 
-int ctl_dist_prep(const void* q_planes, int64_t nq, const void* g_planes, int64_t ng, int32_t d, const int32_t* q_pid,
-                  const int32_t* g_pid, int32_t* q_tile_range, int32_t* g_tile_range, float* g_err_max, ctl_stream_t stream) {
-  CTL_CHECK_ARG(q_planes && g_planes && nq > 0 && ng > 0 && nq < (1ll << 31) && ng < (1ll << 31) && d > 0, "bad arguments");
-  CTL_CHECK_ARG((q_pid == nullptr) == (g_pid == nullptr) && (q_pid == nullptr) == (q_tile_range == nullptr) &&
-                    (q_pid == nullptr) == (g_tile_range == nullptr),
-                "identities and tile ranges come together (or not at all)");
-  CTL_CHECK_ARG(q_pid || g_err_max, "nothing to do");
+int ctl_dist_subset_stride(int64_t ng, int32_t k) {
+  TopkPlan pl;
+  if (ng < 1 || k < 1 || k > ng || plan_topk(ng, k, &pl) || pl.emit_all) return 1;
+  return subset_stride((int)((ng + BN - 1) / BN), pl.merge, k);
+}
+
+int ctl_dist_worklist(const int32_t* q_pid, int64_t nq, const int32_t* g_pid, int64_t ng, int32_t keep_stride, int32_t* tile_list,
+                      ctl_stream_t stream) {
+  CTL_CHECK_ARG(tile_list && nq > 0 && ng > 0 && nq < (1ll << 31) && ng < (1ll << 31) && keep_stride >= 0, "bad arguments");
+  CTL_CHECK_ARG((q_pid == nullptr) == (g_pid == nullptr), "q_pid and g_pid come together");
+  CTL_CHECK_ARG(q_pid || keep_stride > 0, "an empty selection: give identities and / or a stride");
   int rc = ctl_device_check();
   if (rc) return rc;
-  const PlanesView g = planes_view(g_planes, ng, d);
-  const int m_tiles = (int)((nq + BM - 1) / BM), n_tiles = (int)((ng + BN - 1) / BN);
-  static_assert(BM == BN, "dist_prep_kernel uses one block size for both tile kinds");
-  dist_prep_kernel<<<m_tiles + n_tiles, BM, 0, (cudaStream_t)stream>>>(q_pid, (int)nq, m_tiles, g_pid, (int)ng, g.hn, g.ln,
-                                                                       reinterpret_cast<int2*>(q_tile_range),
-                                                                       reinterpret_cast<int2*>(g_tile_range),
-                                                                       reinterpret_cast<unsigned int*>(g_err_max));
-  CTL_LAUNCH_CHECK();
-  return 0;
+  return launch_worklist(q_pid, nq, g_pid, ng, keep_stride, tile_list, (cudaStream_t)stream);
 }
 
 int ctl_fill_f32(float* p, int64_t n, float value, ctl_stream_t stream) {

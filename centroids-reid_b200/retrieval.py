@@ -49,9 +49,9 @@ def _flags(dist: str, normalize: bool) -> int:
 
 def pid_order(pids) -> np.ndarray:
     """Stable order that sorts rows by identity.  With BOTH operands stored in this order almost every 128 x 128 tile
-    of the distance GEMM pairs rows of disjoint identity ranges: such a tile holds no positive, so the threshold pass
-    runs it with one fp16 product instead of three and the collect pass skips it (ctl_pass_desc.approx) -- the results
-    (indices, distances, ranks, AP) are bit-identical to the unsorted run."""
+    of the distance GEMM pairs rows of disjoint identity ranges: such a tile holds no positive, so the pass that collects
+    the positives (and the top-k threshold, which any subset of the gallery bounds) does not run it
+    (ctl_pass_desc.tile_list) -- the results (indices, distances, ranks, AP) are bit-identical to the unsorted run."""
     return np.argsort(np.asarray(pids), kind="stable")
 
 
@@ -312,25 +312,24 @@ def _finalize_and_read_back(buckets, count, nq, max_pos, ovf):
     return ranks, h[:nq, 0], h[:nq, 1].astype(np.int64), h[:nq, 2].astype(np.int32), int(h[nq, 0])
 
 
-def _approx_enabled(qp: Planes) -> bool:
-    """Cheap tiles (ctl_pass_desc.approx) are on unless CTL_RETRIEVAL_APPROX=0 (bisect aid); CTL_DIST_SQRT distances have
-    no error bound for the one-product threshold pass."""
+def _tile_lists_enabled(qp: Planes, gp: Planes) -> bool:
+    """Tile lists (ctl_pass_desc.tile_list) pay off when BOTH operands are stored in identity order (then few tiles can
+    hold a positive); off with CTL_RETRIEVAL_TILE_LISTS=0 (bisect aid)."""
     import os
 
-    return os.environ.get("CTL_RETRIEVAL_APPROX", "1") != "0" and not (qp.flags & N.CTL_DIST_SQRT)
+    return os.environ.get("CTL_RETRIEVAL_TILE_LISTS", "1") != "0" and qp.order is not None and gp.order is not None
 
 
-def _cheap_tiles(qp: Planes, gp: Planes, ids: "EncodedIds", with_bound: bool):
-    """ctl_dist_prep: per-tile identity ranges of both operands (+ the gallery-wide plane-norm maxima behind the tau
-    bound).  Returns (q_tile_range, g_tile_range, g_err_max | None) on the device."""
-    dev = qp.buf.device
-    mt, nt = (qp.n + 127) // 128, (gp.n + 127) // 128
-    ranges = torch.empty(mt + nt, 2, dtype=torch.int32, device=dev)
-    gerr = torch.zeros(2, dtype=torch.float32, device=dev) if with_bound else None
-    q_rng, g_rng = ranges[:mt], ranges[mt:]
-    N.check(N.lib().ctl_dist_prep(qp.ptr, qp.n, gp.ptr, gp.n, qp.d, ids.q_pid.data_ptr(), ids.g_pid.data_ptr(),
-                                  q_rng.data_ptr(), g_rng.data_ptr(), N.ptr(gerr), N.stream_ptr()))
-    return q_rng, g_rng, gerr
+def _tile_list(qp: Planes, gp: Planes, ids: "EncodedIds", keep_stride: int) -> Optional[torch.Tensor]:
+    """ctl_dist_worklist: the tiles that can hold a positive (+ every keep_stride-th gallery tile for the threshold).
+    None when the problem is beyond the list builder (the pass then runs every tile)."""
+    L = N.lib()
+    if ((qp.n + 127) // 128) * ((gp.n + 127) // 128) > (1 << 20) or (qp.n + 127) // 128 + (gp.n + 127) // 128 > 5632:
+        return None
+    work = torch.empty(L.ctl_dist_worklist_bytes(qp.n, gp.n) // 4, dtype=torch.int32, device=qp.buf.device)
+    N.check(L.ctl_dist_worklist(ids.q_pid.data_ptr(), qp.n, ids.g_pid.data_ptr(), gp.n, int(keep_stride), work.data_ptr(),
+                                N.stream_ptr()))
+    return work
 
 
 def _g_index_map(gp: Planes, g_index_offset: int) -> Optional[torch.Tensor]:
@@ -402,12 +401,10 @@ def evaluate_streamed(
     idp = dict(q_pid=d_qpid.data_ptr(), q_cam=d_qcam.data_ptr(), g_pid=d_gpid.data_ptr(), g_cammask=d_gmask.data_ptr(),
                max_pos=max_pos, overflow=ovf.data_ptr(), g_index_offset=g_index_offset, g_index_map=N.ptr(gmap))
     with torch.cuda.device(dev):
-        # pass 1 (collect) only wants the positives: tiles whose identity ranges are disjoint are skipped -- with both
+        # pass 1 (collect) only wants the positives: tiles whose identity ranges are disjoint are not run -- with both
         # operands stored in pid order (build_planes(order=pid_order(..))) that is ~95 % of a Market-sized problem
-        p1 = N.PassDesc(pos_keys=pos_keys.data_ptr(), pos_count=pos_count.data_ptr(), **idp)
-        if _approx_enabled(qp):
-            q_rng, g_rng, _ = _cheap_tiles(qp, gp, ids, with_bound=False)
-            p1.approx, p1.q_tile_range, p1.g_tile_range = 2, q_rng.data_ptr(), g_rng.data_ptr()
+        work = _tile_list(qp, gp, ids, 0) if _tile_lists_enabled(qp, gp) else None
+        p1 = N.PassDesc(pos_keys=pos_keys.data_ptr(), pos_count=pos_count.data_ptr(), tile_list=N.ptr(work), **idp)
         N.check(L.ctl_dist_pass(qp.ptr, nq, gp.ptr, ng, qp.d, qp.flags, C.byref(p1), s()))
         if world > 1:
             pos_keys, pos_count = _allgather_keys(pos_keys, pos_count, max_pos, group)
@@ -525,15 +522,17 @@ def topk_sharded(q_local: torch.Tensor, g_local: torch.Tensor, k: int, g_index_o
 
 
 def topk_and_eval(qp: Planes, gp: Planes, k: int, q_pids, g_pids, q_camids, g_camids, max_rank: int = 50,
-                  respect_camids: bool = False, ids: "Optional[EncodedIds]" = None, approx: Optional[bool] = None):
+                  respect_camids: bool = False, ids: "Optional[EncodedIds]" = None, tile_lists: Optional[bool] = None):
     """BASELINE config 3 in TWO tensor-core passes: per-query top-k (ascending (distance, index))
     AND eval_func's CMC / mAP, neither materialising the distance matrix.
       pass 1: 16-column group minima (-> tau) + the positives' distances
       pass 2: candidates <= tau + kept rows before each positive
-    Pass 1 only needs EXACT distances for the positives: every tile whose query / gallery identity ranges are disjoint
-    runs with the leading fp16 product alone and tau gets the rigorous bound of the difference added
-    (ctl_select_tau_approx); pass 2 is exact, so indices, distances, ranks and AP are bit-identical to the all-exact run
-    (`approx=False`).  It pays off when both operands are stored in pid order: build_planes(order=pid_order(pids)).
+    Pass 1 does not need the whole matrix: the positives sit in the tiles whose query / gallery identity ranges
+    intersect, and the k-th smallest group minimum of ANY subset of the gallery bounds the k-th distance from above.
+    With both operands stored in pid order (build_planes(order=pid_order(pids))) pass 1 therefore runs a tile list
+    (ctl_dist_worklist: the few tiles that can hold a positive + every s-th gallery tile, ~30 % of the matrix); the
+    looser tau only lengthens the candidate lists of the exact pass 2, so indices, distances, ranks and AP are
+    bit-identical to the full run (`tile_lists=False`).
     Identities are given in the caller's row order; a precomputed `ids` must carry the planes' orders
     (encode_ids(q_order=qp.order_host, g_order=gp.order_host)).
     Returns (idx [nq,k] int64, dist [nq,k] float32 on the device, EvalResult), all in the caller's indexing."""
@@ -548,8 +547,8 @@ def topk_and_eval(qp: Planes, gp: Planes, k: int, q_pids, g_pids, q_camids, g_ca
     if ids is None:
         ids = encode_ids(q_pids, g_pids, q_camids, g_camids, respect_camids, dev, q_order=qp.order_host,
                          g_order=gp.order_host)
-    if approx is None:
-        approx = _approx_enabled(qp)
+    if tile_lists is None:
+        tile_lists = _tile_lists_enabled(qp, gp)
     d_qpid, d_qcam, d_gpid, d_gmask, max_pos = ids.q_pid, ids.q_cam, ids.g_pid, ids.g_mask, ids.max_pos
     gmin = torch.empty(nq, n_groups.value, dtype=torch.float32, device=dev)
     tau = torch.empty(nq, dtype=torch.float32, device=dev)
@@ -568,16 +567,19 @@ def topk_and_eval(qp: Planes, gp: Planes, k: int, q_pids, g_pids, q_camids, g_ca
         p1 = N.PassDesc(pos_keys=pos_keys.data_ptr(), pos_count=pos_count.data_ptr(), **idp)
         if not emit_all.value:
             p1.gmin = gmin.data_ptr()
-        if approx:
-            q_rng, g_rng, gerr = _cheap_tiles(qp, gp, ids, with_bound=not emit_all.value)
-            # small gallery (tau = +inf): pass 1 only collects, cheap tiles are skipped
-            p1.approx, p1.q_tile_range, p1.g_tile_range = (2 if emit_all.value else 1), q_rng.data_ptr(), g_rng.data_ptr()
+        work = None
+        if tile_lists:
+            # (small gallery, tau = +inf: pass 1 only collects -> stride 0, just the tiles that can hold a positive)
+            stride = 0 if emit_all.value else L.ctl_dist_subset_stride(ng, k)
+            if emit_all.value or stride > 1:
+                work = _tile_list(qp, gp, ids, stride)
+        if work is not None:
+            p1.tile_list = work.data_ptr()
+            if not emit_all.value:
+                N.check(L.ctl_fill_f32(gmin.data_ptr(), gmin.numel(), float("inf"), s()))  # groups of tiles not run
         N.check(L.ctl_dist_pass(qp.ptr, nq, gp.ptr, ng, qp.d, qp.flags, C.byref(p1), s()))
         if emit_all.value:
             N.check(L.ctl_fill_f32(tau.data_ptr(), nq, float("inf"), s()))
-        elif approx:
-            N.check(L.ctl_select_tau_approx(gmin.data_ptr(), nq, n_groups.value, merge.value, k, qp.ptr, qp.d, qp.flags,
-                                            gerr.data_ptr(), tau.data_ptr(), s()))
         else:
             N.check(L.ctl_select_tau(gmin.data_ptr(), nq, n_groups.value, merge.value, k, tau.data_ptr(), s()))
         N.check(L.ctl_sort_key_rows(pos_keys.data_ptr(), pos_count.data_ptr(), nq, max_pos, s()))
@@ -589,9 +591,9 @@ def topk_and_eval(qp: Planes, gp: Planes, k: int, q_pids, g_pids, q_camids, g_ca
         N.check(L.ctl_topk_emit(cand.data_ptr(), cand_count.data_ptr(), nq, cap.value, k, idx.data_ptr(),
                                 dst.data_ptr(), ovf.data_ptr(), s()))
         ranks, ap_h, first_h, cnt_h, ovf_h = _finalize_and_read_back(buckets, pos_count, nq, max_pos, ovf)
-        if ovf_h and approx and not emit_all.value:
-            # more rows inside the bound of the threshold than the candidate list holds: the exact threshold pass
-            return topk_and_eval(qp, gp, k, q_pids, g_pids, q_camids, g_camids, max_rank, respect_camids, ids, approx=False)
+        if ovf_h and work is not None and not emit_all.value:
+            # the looser threshold let more rows through than the candidate list holds: threshold from every tile
+            return topk_and_eval(qp, gp, k, q_pids, g_pids, q_camids, g_camids, max_rank, respect_camids, ids, tile_lists=False)
         inv_d, inv_h = _query_inverse(qp)
         if inv_h is not None:  # back to the caller's query order
             idx, dst, ranks = idx.index_select(0, inv_d), dst.index_select(0, inv_d), ranks.index_select(0, inv_d)
@@ -617,7 +619,7 @@ def encode_ids_sharded(q_pids, g_pids_local, q_camids, g_camids_local, device, g
 
 
 def topk_and_eval_sharded(qp: Planes, gp_local: Planes, k: int, ids: EncodedIds, q_pids, g_index_offset: int,
-                          total_gallery: int, group, max_rank: int = 50, approx: Optional[bool] = None):
+                          total_gallery: int, group, max_rank: int = 50, tile_lists: Optional[bool] = None):
     """BASELINE config 5: topk_and_eval with the GALLERY AXIS SHARDED over the ranks of `group` (queries replicated:
     all-gather them once before building `qp`).  Every rank runs the two tensor-core passes over its own shard; the
     exchange steps are (utils/reid_metric.py:112-136 + utils/eval_reid.py:25-92 semantics, bit-identical to one GPU):
@@ -646,8 +648,8 @@ def topk_and_eval_sharded(qp: Planes, gp_local: Planes, k: int, ids: EncodedIds,
     pos_keys = torch.empty(nq, mp_l, dtype=torch.int64, device=dev)
     buckets = torch.zeros(nq, mp + 1, dtype=torch.int32, device=dev)
     s = N.stream_ptr
-    if approx is None:
-        approx = _approx_enabled(qp)
+    if tile_lists is None:
+        tile_lists = _tile_lists_enabled(qp, gp)
     gmap = _g_index_map(gp_local, g_index_offset)  # pid-sorted shard: keys carry the GLOBAL gallery row
     idp = dict(q_pid=ids.q_pid.data_ptr(), q_cam=ids.q_cam.data_ptr(), g_pid=ids.g_pid.data_ptr(),
                g_cammask=ids.g_mask.data_ptr(), overflow=ovf.data_ptr(), g_index_offset=g_index_offset,
@@ -656,15 +658,18 @@ def topk_and_eval_sharded(qp: Planes, gp_local: Planes, k: int, ids: EncodedIds,
         p1 = N.PassDesc(pos_keys=pos_keys.data_ptr(), pos_count=pos_count.data_ptr(), max_pos=mp_l, **idp)
         if not emit_all.value:
             p1.gmin = gmin.data_ptr()
-        if approx:  # cheap tiles in the threshold / collect pass, as in topk_and_eval
-            q_rng, g_rng, gerr = _cheap_tiles(qp, gp_local, ids, with_bound=not emit_all.value)
-            p1.approx, p1.q_tile_range, p1.g_tile_range = (2 if emit_all.value else 1), q_rng.data_ptr(), g_rng.data_ptr()
+        work = None
+        if tile_lists:  # pid-sorted shard: pass 1 runs the tiles that can hold a positive + a subset for tau (topk_and_eval)
+            stride = 0 if emit_all.value else L.ctl_dist_subset_stride(ng, k_loc)
+            if emit_all.value or stride > 1:
+                work = _tile_list(qp, gp_local, ids, stride)
+        if work is not None:
+            p1.tile_list = work.data_ptr()
+            if not emit_all.value:
+                N.check(L.ctl_fill_f32(gmin.data_ptr(), gmin.numel(), float("inf"), s()))
         N.check(L.ctl_dist_pass(qp.ptr, nq, gp_local.ptr, ng, qp.d, qp.flags, C.byref(p1), s()))
         if emit_all.value:
             N.check(L.ctl_fill_f32(tau.data_ptr(), nq, float("inf"), s()))
-        elif approx:
-            N.check(L.ctl_select_tau_approx(gmin.data_ptr(), nq, n_groups.value, merge.value, k_loc, qp.ptr, qp.d, qp.flags,
-                                            gerr.data_ptr(), tau.data_ptr(), s()))
         else:
             N.check(L.ctl_select_tau(gmin.data_ptr(), nq, n_groups.value, merge.value, k_loc, tau.data_ptr(), s()))
         # exchange 1: every rank's positives, unused slots = the largest key, so ONE row sort packs and orders them
@@ -691,8 +696,9 @@ def topk_and_eval_sharded(qp: Planes, gp_local: Planes, k: int, ids: EncodedIds,
         dist.all_reduce(ovf, op=dist.ReduceOp.MAX, group=group)
         idx, dst = merge_topk_keys(g_best.permute(1, 0, 2).reshape(nq, world * k_loc), int(min(k, world * k_loc)))
         ranks, ap_h, first_h, cnt_h, ovf_h = _finalize_and_read_back(buckets, thr_count, nq, mp, ovf)
-        if ovf_h and approx and not emit_all.value:  # (the flag is MAX-reduced: every rank takes this branch together)
-            return topk_and_eval_sharded(qp, gp_local, k, ids, q_pids, g_index_offset, total_gallery, group, max_rank, approx=False)
+        if ovf_h and tile_lists and not emit_all.value:  # (the flag is MAX-reduced: every rank takes this branch together)
+            return topk_and_eval_sharded(qp, gp_local, k, ids, q_pids, g_index_offset, total_gallery, group, max_rank,
+                                         tile_lists=False)
         inv_d, inv_h = _query_inverse(qp)
         if inv_h is not None:  # back to the caller's query order
             idx, dst, ranks = idx.index_select(0, inv_d), dst.index_select(0, inv_d), ranks.index_select(0, inv_d)

@@ -52,8 +52,8 @@ int ctl_device_check(void);
 #define CTL_DIST_COSINE 1    /* clamp(|1 - cos|, 1e-12) */
 #define CTL_FLAG_NORMALIZE 2 /* torch.nn.functional.normalize(x, dim=1, p=2) first */
 #define CTL_DIST_SQRT 4      /* euclidean only: sqrt(clamp(d, 1e-12)) -- losses/triplet_loss.py:27-41 */
-#define CTL_FLAG_EXACT_PASS 8 /* ctl_l2_topk: threshold pass with the full three-product arithmetic (default: leading
-                                 product + error bound; same results, a looser candidate set) */
+#define CTL_FLAG_EXACT_PASS 8 /* ctl_l2_topk: threshold pass over EVERY gallery tile (default: a subset of the tiles --
+                                 same results from a looser threshold and longer candidate lists) */
 
 /* Row planes: the fp32 rows split into two fp16 planes (hi + 2^-11 lo, per-row power-of-two
  * scale) plus fp32 squared norms, the operand format of the tensor-core distance kernel.
@@ -131,16 +131,11 @@ typedef struct ctl_pass_desc {
   int32_t* buckets;           /* [nq, max_pos + 1], zeroed by the caller */
   int32_t* overflow;          /* device int, set non-zero when a list overflows */
   int64_t g_index_offset;
-  /* Cheap tiles (all optional, zero = off).  A 128 x 128 tile whose query rows and gallery rows share no identity
-   * (ranges from ctl_dist_prep; rows stored sorted by pid make almost every tile such a tile) holds no positive:
-   *   approx = 1: it is computed with the leading fp16 product only -- its group minima are within the bound that
-   *               ctl_select_tau_approx adds to tau (only gmin / pos_keys outputs allowed);
-   *   approx = 2: it is skipped (collect-only passes: pos_keys / pos_count).
-   * Without tile ranges every tile is cheap (top-k without identities).  Tiles that may hold a positive always run
-   * the full three-product arithmetic, so the collected keys are bit-identical to an exact pass. */
-  int32_t approx;
-  const int32_t* q_tile_range; /* [ceil(nq/128)][2] {min pid, max pid} */
-  const int32_t* g_tile_range; /* [ceil(ng/128)][2] */
+  /* Optional (NULL = off). */
+  const int32_t* tile_list;    /* ctl_dist_worklist: run only these 128 x 128 tiles.  For passes whose outputs do not need
+                                  every tile: pos_keys / pos_count (tiles that can hold a positive) and gmin (any subset of
+                                  the groups still bounds the k-th distance from above; the caller pre-fills gmin with
+                                  +inf).  Rejected with dist_out, cand_keys or buckets. */
   const int32_t* g_index_map;  /* [ng] index written into the keys for gallery row i (instead of i + g_index_offset):
                                   lets the rows be stored in another order (e.g. sorted by pid) with unchanged results */
 } ctl_pass_desc;
@@ -152,16 +147,16 @@ void ctl_debug_set_dist_profile(long long* device_buffer);
 int ctl_topk_plan(int64_t ng, int32_t k, int32_t* emit_all, int32_t* n_groups, int32_t* merge, int32_t* cand_cap);
 int ctl_select_tau(const float* gmin, int64_t nq, int32_t n_groups, int32_t merge, int32_t k, float* tau,
                    ctl_stream_t stream);
-/* Inputs of the cheap-tile passes: per-tile {min, max} identity ranges of both operands (q_pid / g_pid and the two range
- * outputs together, or all four NULL) and g_err_max[2] (zeroed by the caller; NULL = not wanted) = the gallery-wide
- * maxima of the two plane norms. */
-int ctl_dist_prep(const void* q_planes, int64_t nq, const void* g_planes, int64_t ng, int32_t d, const int32_t* q_pid,
-                  const int32_t* g_pid, int32_t* q_tile_range, int32_t* g_tile_range, float* g_err_max, ctl_stream_t stream);
-/* ctl_select_tau for group minima of an approx == 1 pass: tau[q] = k-th smallest merged minimum + a rigorous bound of
- * |approximate - exact| for this query (from the plane norms), so {exact distance <= tau} still holds the k nearest rows.
- * Euclidean / cosine distances only (CTL_DIST_SQRT is rejected). */
-int ctl_select_tau_approx(const float* gmin, int64_t nq, int32_t n_groups, int32_t merge, int32_t k, const void* q_planes,
-                          int32_t d, int32_t flags, const float* g_err_max, float* tau, ctl_stream_t stream);
+/* Tile list for ctl_pass_desc.tile_list: tile_list[0] = count, then the kept tile ids (ascending).  A tile is kept if
+ * the identity ranges of its 128 query rows and its 128 gallery rows intersect (q_pid / g_pid in the planes' row order;
+ * both NULL = no identities) or if its gallery-tile index is a multiple of keep_stride (0 = none).  With both operands
+ * stored in identity order the first set is a few per cent of the matrix.  ctl_dist_subset_stride(ng, k): the stride that
+ * leaves ~2.5 k column groups for ctl_select_tau (1 = use every tile).  Limits: <= 2^20 tiles, <= 5632 row tiles
+ * (CTL_ERR_UNSUPPORTED beyond: run the pass without a list). */
+size_t ctl_dist_worklist_bytes(int64_t nq, int64_t ng);
+int ctl_dist_subset_stride(int64_t ng, int32_t k);
+int ctl_dist_worklist(const int32_t* q_pid, int64_t nq, const int32_t* g_pid, int64_t ng, int32_t keep_stride,
+                      int32_t* tile_list, ctl_stream_t stream);
 int ctl_fill_f32(float* p, int64_t n, float value, ctl_stream_t stream);
 int ctl_topk_emit(const uint64_t* cand_keys_sorted, const int32_t* cand_count, int64_t nq, int32_t cand_cap, int32_t k,
                   int64_t* out_idx, float* out_dist, int32_t* overflow, ctl_stream_t stream);

@@ -252,26 +252,25 @@ def _same_eval(a, b):
 
 @pytest.mark.parametrize("nq,ng,nid,dim,dyadic", [(700, 9000, 150, 512, False), (300, 6000, 60, 256, True),
                                                    (200, 3000, 40, 2048, False)])
-def test_cheap_tiles_and_pid_sorted_planes_are_bit_identical(R, nq, ng, nid, dim, dyadic):
-    """Threshold / collect passes with cheap tiles (ctl_pass_desc.approx: one fp16 product or skipped where the identity
-    ranges of a tile are disjoint) and planes stored in identity order (build_planes(order=pid_order(..)), keys written
-    through g_index_map, queries un-permuted) give the SAME indices, distances, ranks, AP, CMC as the all-exact run on
-    the caller's order -- bit for bit.  (ng = 3000: the small-gallery plan, pass 1 collects only and skips tiles.)
-    Duplicated gallery rows put exact ties at positives and inside the top-k, where the index order decides."""
+def test_tile_lists_and_pid_sorted_planes_are_bit_identical(R, nq, ng, nid, dim, dyadic):
+    """Planes stored in identity order (build_planes(order=pid_order(..)), keys written through g_index_map, queries
+    un-permuted) with pass 1 restricted to a tile list (the tiles that can hold a positive + a subset of the gallery for the
+    threshold) give the SAME indices, distances, ranks, AP, CMC as the full run on the caller's order -- bit for bit.
+    (ng = 3000: the small-gallery plan, pass 1 collects only.)  Duplicated gallery rows put exact ties at positives and
+    inside the top-k, where the index order decides."""
     feats, pids, cams = O.synth_retrieval(nq, ng, nid, dim, 2.0, 29, num_cams=4, dyadic=dyadic)
     feats[nq + 50:nq + 90] = feats[nq + 500:nq + 540]
     pids[nq + 50:nq + 90] = pids[nq + 500:nq + 540]
     q, gal = feats[:nq].cuda(), feats[nq:].cuda()
     args = (pids[:nq], pids[nq:], cams[:nq], cams[nq:])
-    base = R.topk_and_eval(R.build_planes(q), R.build_planes(gal), 50, *args, approx=False)
+    base = R.topk_and_eval(R.build_planes(q), R.build_planes(gal), 50, *args)
     qo, go = R.pid_order(pids[:nq]), R.pid_order(pids[nq:])
     runs = {
-        "unsorted, cheap tiles": R.topk_and_eval(R.build_planes(q), R.build_planes(gal), 50, *args, approx=True),
-        "pid-sorted, cheap tiles": R.topk_and_eval(R.build_planes(q, order=qo), R.build_planes(gal, order=go), 50, *args,
-                                                   approx=True),
-        "pid-sorted, exact": R.topk_and_eval(R.build_planes(q, order=qo), R.build_planes(gal, order=go), 50, *args,
-                                             approx=False),
-        "gallery sorted only": R.topk_and_eval(R.build_planes(q), R.build_planes(gal, order=go), 50, *args, approx=True),
+        "pid-sorted, tile lists": R.topk_and_eval(R.build_planes(q, order=qo), R.build_planes(gal, order=go), 50, *args),
+        "pid-sorted, every tile": R.topk_and_eval(R.build_planes(q, order=qo), R.build_planes(gal, order=go), 50, *args,
+                                                  tile_lists=False),
+        "gallery sorted only": R.topk_and_eval(R.build_planes(q), R.build_planes(gal, order=go), 50, *args),
+        "queries sorted only": R.topk_and_eval(R.build_planes(q, order=qo), R.build_planes(gal), 50, *args),
     }
     for name, (idx, dst, res) in runs.items():
         assert torch.equal(idx, base[0]), name
@@ -281,64 +280,71 @@ def test_cheap_tiles_and_pid_sorted_planes_are_bit_identical(R, nq, ng, nid, dim
     ev1 = R.evaluate_streamed(R.build_planes(q, order=qo), R.build_planes(gal, order=go), *args)
     _same_eval(ev0, base[2])
     _same_eval(ev1, base[2])
-    idx_t, dst_t, ovf = R.topk(R.build_planes(q), R.build_planes(gal), 50)
+    idx_t, dst_t, ovf = R.topk(R.build_planes(q), R.build_planes(gal), 50)          # threshold from a subset of the tiles
     idx_e, dst_e, ovf_e = R.topk(R.build_planes(q), R.build_planes(gal), 50, exact_threshold_pass=True)
     assert int(ovf.item()) == 0 and int(ovf_e.item()) == 0
     assert torch.equal(idx_t, idx_e) and torch.equal(dst_t, dst_e) and torch.equal(idx_t, base[0])
 
 
-def test_cheap_tile_group_minima_stay_inside_the_tau_bound(R):
-    """Kernel-level check of the approximate threshold pass: on pid-sorted float data most tiles run with the leading
-    product only, so their 16-column group minima differ from the exact pass -- by less than the bound
-    ctl_select_tau_approx adds (tau_approx - margin <= tau_exact <= tau_approx), while every group of a tile that may
-    hold a positive is bit-identical.  The collected positive keys are identical too."""
+def test_tile_list_pass_against_the_full_pass(R):
+    """Kernel-level: ctl_dist_worklist keeps exactly the tiles whose identity ranges intersect plus every stride-th gallery
+    tile (checked against numpy, in the kernel's tile order); a pass over that list writes the SAME group minima on the kept
+    tiles (the rest stay +inf), collects the same positives, and its tau is an upper bound of the full pass's tau."""
     import ctypes as C
 
     from ctl_b200 import _native as N
 
-    nq, ng, nid, dim = 640, 8192, 64, 1024
+    nq, ng, nid, dim, k = 640, 8192, 64, 1024, 50
     feats, pids, cams = O.synth_retrieval(nq, ng, nid, dim, 2.0, 41, num_cams=4)
     qo, go = R.pid_order(pids[:nq]), R.pid_order(pids[nq:])
     qp = R.build_planes(feats[:nq].cuda(), order=qo)
     gp = R.build_planes(feats[nq:].cuda(), order=go)
     ids = R.encode_ids(pids[:nq], pids[nq:], cams[:nq], cams[nq:], False, "cuda", q_order=qo, g_order=go)
     L = N.lib()
-    n_groups = (ng + 15) // 16
+    n_groups, m_tiles, n_tiles = (ng + 15) // 16, (nq + 127) // 128, (ng + 127) // 128
+    stride = L.ctl_dist_subset_stride(ng, k)
+    assert 1 < stride <= n_tiles // 8
+    work = R._tile_list(qp, gp, ids, stride)
+    torch.cuda.synchronize()
+    w = work.cpu().numpy()
+    # expectation in numpy: ranges of the sorted identity arrays, tile order = bands of 16 gallery tiles, query tiles fastest
+    qpid, gpid = ids.q_pid.cpu().numpy(), ids.g_pid.cpu().numpy()
+    qr = np.array([[qpid[i * 128:(i + 1) * 128].min(), qpid[i * 128:(i + 1) * 128].max()] for i in range(m_tiles)])
+    gr = np.array([[gpid[i * 128:(i + 1) * 128].min(), gpid[i * 128:(i + 1) * 128].max()] for i in range(n_tiles)])
+    keep = ~((gr[None, :, 1] < qr[:, None, 0]) | (gr[None, :, 0] > qr[:, None, 1])) | (np.arange(n_tiles)[None, :] % stride == 0)
+    expect = []
+    for band in range((n_tiles + 15) // 16):
+        wdt = min(16, n_tiles - band * 16)
+        for mt in range(m_tiles):
+            for j in range(wdt):
+                if keep[mt, band * 16 + j]:
+                    expect.append(band * 16 * m_tiles + mt * wdt + j)
+    assert int(w[0]) == len(expect) and np.array_equal(w[1:1 + len(expect)], np.asarray(expect))
+    assert 0.1 < len(expect) / (m_tiles * n_tiles) < 0.6
     out = {}
-    q_rng, g_rng, gerr = R._cheap_tiles(qp, gp, ids, with_bound=True)
-    for approx in (0, 1):
-        gmin = torch.empty(nq, n_groups, device="cuda")
+    for use_list in (False, True):
+        gmin = torch.full((nq, n_groups), float("inf"), device="cuda")
         pos = torch.zeros(nq, ids.max_pos, dtype=torch.int64, device="cuda")
         cnt = torch.zeros(nq, dtype=torch.int32, device="cuda")
         ovf = torch.zeros(1, dtype=torch.int32, device="cuda")
         p = N.PassDesc(gmin=gmin.data_ptr(), pos_keys=pos.data_ptr(), pos_count=cnt.data_ptr(), q_pid=ids.q_pid.data_ptr(),
                        q_cam=ids.q_cam.data_ptr(), g_pid=ids.g_pid.data_ptr(), g_cammask=ids.g_mask.data_ptr(),
-                       max_pos=ids.max_pos, overflow=ovf.data_ptr(), approx=approx, q_tile_range=q_rng.data_ptr(),
-                       g_tile_range=g_rng.data_ptr(), g_index_map=gp.order.data_ptr())
+                       max_pos=ids.max_pos, overflow=ovf.data_ptr(), tile_list=work.data_ptr() if use_list else None,
+                       g_index_map=gp.order.data_ptr())
         N.check(L.ctl_dist_pass(qp.ptr, nq, gp.ptr, ng, dim, qp.flags, C.byref(p), N.stream_ptr()))
         N.check(L.ctl_sort_key_rows(pos.data_ptr(), cnt.data_ptr(), nq, ids.max_pos, N.stream_ptr()))
         tau = torch.empty(nq, device="cuda")
-        if approx:
-            N.check(L.ctl_select_tau_approx(gmin.data_ptr(), nq, n_groups, 1, 50, qp.ptr, dim, qp.flags, gerr.data_ptr(),
-                                            tau.data_ptr(), N.stream_ptr()))
-        else:
-            N.check(L.ctl_select_tau(gmin.data_ptr(), nq, n_groups, 1, 50, tau.data_ptr(), N.stream_ptr()))
+        N.check(L.ctl_select_tau(gmin.data_ptr(), nq, n_groups, 1, k, tau.data_ptr(), N.stream_ptr()))
         torch.cuda.synchronize()
         assert int(ovf.item()) == 0
-        out[approx] = (gmin.cpu().numpy(), pos.cpu().numpy(), cnt.cpu().numpy(), tau.cpu().numpy())
-    (g0, p0, c0, t0), (g1, p1, c1, t1) = out[0], out[1]
+        out[use_list] = (gmin.cpu().numpy(), pos.cpu().numpy(), cnt.cpu().numpy(), tau.cpu().numpy())
+    (g0, p0, c0, t0), (g1, p1, c1, t1) = out[False], out[True]
     assert np.array_equal(c0, c1)
     col = np.arange(p0.shape[1])[None, :]
     assert np.array_equal(np.where(col < c0[:, None], p0, 0), np.where(col < c1[:, None], p1, 0))
-    # which (query tile, gallery tile) pairs are exact?  identity ranges intersect
-    qr, gr = q_rng.cpu().numpy(), g_rng.cpu().numpy()
-    exact = ~((gr[None, :, 1] < qr[:, None, 0]) | (gr[None, :, 0] > qr[:, None, 1]))  # [m_tiles, n_tiles]
-    assert 0.02 < exact.mean() < 0.5, "pid-sorted operands: few tiles can hold a positive"
-    ex_elem = np.repeat(np.repeat(exact, 128, 0)[:nq], 8, 1)[:, :n_groups]              # 8 groups of 16 per tile
-    assert np.array_equal(g0[ex_elem], g1[ex_elem])
-    diff = np.abs(g0.astype(np.float64) - g1.astype(np.float64))
-    assert diff[~ex_elem].max() > 0, "the one-product path was not exercised"
-    margin = t1.astype(np.float64) - np.partition(g1, 49, axis=1)[:, 49]
-    assert (margin > 0).all() and diff.max() <= margin.min(), (diff.max(), margin.min())
-    assert (t1 >= t0).all(), "tau of the bounded pass must not cut below the exact threshold"
-    assert float(margin.max()) < 5e-3, "unit-norm features: the bound is ~2^-10, candidates barely grow"
+    kept = np.repeat(np.repeat(keep, 128, 0)[:nq], 8, 1)[:, :n_groups]   # 8 groups of 16 columns per gallery tile
+    assert np.array_equal(g1[kept], g0[kept]) and np.isinf(g1[~kept]).all() and np.isfinite(g0).all()
+    assert (t1 >= t0).all() and np.isfinite(t1).all()
+    # a tile list is refused where every tile is needed
+    bad = N.PassDesc(dist_out=gmin.data_ptr(), ld_out=ng, tile_list=work.data_ptr())
+    assert L.ctl_dist_pass(qp.ptr, nq, gp.ptr, ng, dim, qp.flags, C.byref(bad), N.stream_ptr()) == -1
