@@ -35,9 +35,14 @@ static constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // q_hi, q_lo, g_hi, g_l
 static constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 static constexpr int GROUP_W = 16;                      // columns per group-min
 static constexpr int META_BYTES = 2 * BN * (4 + 4 + 4 + 8 + 4);  // double-buffered per-tile column metadata
-static constexpr int THR_MAX = 44, THR_STRIDE = 45;         // positives per query held in shared memory
+static constexpr int THR_MAX = 32, THR_STRIDE = 33;         // positives per query held in shared memory
 static constexpr int THR_BYTES = BM * THR_STRIDE * 4;
-static constexpr size_t GEMM_SMEM = STAGES * STAGE_BYTES + META_BYTES + THR_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+static constexpr int CNT_STRIDE = THR_MAX / 2 + 1;          // bucket counters of one query row: 2 x 16 bit per word
+static constexpr int CNT_BYTES = BM * CNT_STRIDE * 4;
+static constexpr int UNIT_R = 4;  // count passes: gallery tiles a CTA runs back to back for ONE query tile
+static constexpr size_t GEMM_SMEM = STAGES * STAGE_BYTES + META_BYTES + THR_BYTES + CNT_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+static_assert(GEMM_SMEM <= 227 * 1024, "dist_gemm_kernel shared memory");
+static_assert(UNIT_R * BN < 65536, "16-bit bucket counters of a unit");
 
 // ---------------------------------------------------------------------------------------
 // (distance, index) keys: ascending uint64 order == ascending (distance, index)
@@ -192,6 +197,7 @@ struct GemmPass {
   // A pass that only collects the positives and a threshold needs the tiles that can hold a positive plus a subset for
   // the group minima -- with both operands stored in identity order that is a fraction of the matrix.
   const int* work;
+  int unit_r;           // gallery tiles per work item of a full pass (set by launch_gemm_pass)
   const int* g_map;     // optional: gallery row -> index written into the keys (rows stored in another order)
   long long* prof;  // debug: [grid][8] epilogue cycle counters (tools/prof_retrieval.py)
 };
@@ -235,15 +241,24 @@ __device__ __noinline__ int bucket_search_global(const unsigned long long* __res
   return lo;
 }
 
-__device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, int& mt, int& nt) {
-  // bands of 16 gallery tiles, query tiles fastest inside a band-row: the CTAs that run
-  // concurrently touch a compact (m x n) block, so each operand tile is fetched from HBM ~once
-  const int band_w = 16;
-  const int band = tile / (band_w * m_tiles);
-  const int rem = tile - band * band_w * m_tiles;
-  const int w = min(band_w, n_tiles - band * band_w);
-  mt = rem / w;
-  nt = band * band_w + rem % w;
+// Work item w of a pass -> query tile mt, first gallery tile nt0, number of gallery tiles run back to back.
+//   full pass: (query tile, `unit_r` consecutive gallery tiles), query tiles fastest -- the CTAs that run concurrently
+//              touch ~5 gallery-tile groups x all query tiles, so each operand tile is fetched from HBM about once.
+//              unit_r > 1 for the count pass: the per-row state of a query tile (sorted thresholds in shared memory,
+//              bucket counters) is set up and flushed once per unit instead of once per tile;
+//   tile list: one listed tile, id = nt * m_tiles + mt.
+__device__ __forceinline__ void unit_coords(const GemmPass& p, int w, int& mt, int& nt0, int& cnt) {
+  if (p.work) {
+    const int id = p.work[1 + w];
+    nt0 = id / p.m_tiles;
+    mt = id - nt0 * p.m_tiles;
+    cnt = 1;
+  } else {
+    const int g = w / p.m_tiles;
+    mt = w - g * p.m_tiles;
+    nt0 = g * p.unit_r;
+    cnt = min(p.unit_r, p.n_tiles - nt0);
+  }
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -252,7 +267,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t meta_base = smem_base + STAGES * STAGE_BYTES;
   const uint32_t thr_base = meta_base + META_BYTES;
-  const uint32_t bar_base = thr_base + THR_BYTES;
+  const uint32_t bar_base = thr_base + THR_BYTES + CNT_BYTES;
   // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -262,7 +277,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_work = p.work ? p.work[0] : p.m_tiles * p.n_tiles;  // every role walks the same tile sequence
+  // every role walks the same sequence of work items (unit_coords)
+  const int num_work = p.work ? p.work[0] : p.m_tiles * ((p.n_tiles + p.unit_r - 1) / p.unit_r);
   const int k_blocks = (p.d + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
@@ -295,22 +311,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       int stage = 0;
       uint32_t phase = 0;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-        const int tile = p.work ? p.work[1 + w] : w;
-        int mt, nt;
-        tile_coords(tile, p.m_tiles, p.n_tiles, mt, nt);
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t dst = smem_base + stage * STAGE_BYTES;
-          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
-          tma_load_2d(dst + 0 * TILE_BYTES, &maps.q_hi, full_bar(stage), kb * BK, mt * BM);
-          tma_load_2d(dst + 1 * TILE_BYTES, &maps.q_lo, full_bar(stage), kb * BK, mt * BM);
-          tma_load_2d(dst + 2 * TILE_BYTES, &maps.g_hi, full_bar(stage), kb * BK, nt * BN);
-          tma_load_2d(dst + 3 * TILE_BYTES, &maps.g_lo, full_bar(stage), kb * BK, nt * BN);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1u;
+        int mt, nt0, ncnt;
+        unit_coords(p, w, mt, nt0, ncnt);
+        for (int nt = nt0; nt < nt0 + ncnt; ++nt)
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t dst = smem_base + stage * STAGE_BYTES;
+            mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+            tma_load_2d(dst + 0 * TILE_BYTES, &maps.q_hi, full_bar(stage), kb * BK, mt * BM);
+            tma_load_2d(dst + 1 * TILE_BYTES, &maps.q_lo, full_bar(stage), kb * BK, mt * BM);
+            tma_load_2d(dst + 2 * TILE_BYTES, &maps.g_hi, full_bar(stage), kb * BK, nt * BN);
+            tma_load_2d(dst + 3 * TILE_BYTES, &maps.g_lo, full_bar(stage), kb * BK, nt * BN);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
           }
-        }
       }
     }
   } else if (warp == 1) {
@@ -322,6 +338,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       int as = 0;
       uint32_t aphase = 0;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        int mt, nt0, ncnt;
+        unit_coords(p, w, mt, nt0, ncnt);
+        for (int t = 0; t < ncnt; ++t) {
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
         const uint32_t acc0 = tmem_base + as * 256;
@@ -352,6 +371,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           as = 0;
           aphase ^= 1u;
         }
+        }
       }
     }
   } else {
@@ -381,24 +401,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     pc[i] += _t - tprev;            \
     tprev = _t;                     \
   }
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
-      const int tile = p.work ? p.work[1 + w] : w;
-      int mt, nt;
-      tile_coords(tile, p.m_tiles, p.n_tiles, mt, nt);
+    uint32_t* cnt_s = thr_s + BM * THR_STRIDE;  // [BM][CNT_STRIDE]: 2 x 16-bit bucket counters per word
+    const bool thr_in_smem = p.buckets != nullptr;
+    const int n_stage = min(p.max_pos, THR_MAX);
+    uint32_t* thr_row = thr_s + row_in_tile * THR_STRIDE;
+    uint32_t* cnt_row = cnt_s + row_in_tile * CNT_STRIDE;
+    if (thr_in_smem)  // the counters start at zero; every flush leaves them at zero again
+      for (int i = et; i < BM * CNT_STRIDE; i += 256) cnt_s[i] = 0u;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      int mt, nt0, ncnt;
+      unit_coords(p, w, mt, nt0, ncnt);
+      // ---- per work item: the state of this thread's query row ----
       const int row = mt * BM + row_in_tile;
       const bool row_ok = row < p.nq;
-      const int mb = (it & 1) * BN;  // double-buffered metadata slice
-      if (et < BN) {
-        const int col = nt * BN + et;
-        const bool ok = col < p.ng;
-        cm_sq[mb + et] = ok ? p.g_sq[col] : 0.f;
-        cm_is[mb + et] = ok ? p.g_is[col] : 0.f;
-        cm_idx[mb + et] = (ok && p.g_map) ? static_cast<unsigned int>(p.g_map[col]) : static_cast<unsigned int>(col + p.g_off);
-        if (p.q_pid) {
-          cm_pid[mb + et] = ok ? p.g_pid[col] : -2;
-          cm_mask[mb + et] = ok ? p.g_mask[col] : 0ull;
-        }
-      }
       float qq = 0.f, qis = 0.f, tau = -CUDART_INF_F;
       int qpid = -1, qcam = 0, npos = 0;
       unsigned long long maxkey = 0ull;
@@ -415,35 +430,38 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           if (npos > 0) maxkey = p.thr_keys[(size_t)row * p.max_pos + npos - 1];
         }
       }
-      // distance parts of this row's sorted positives staged in shared memory (row stride 45 words: conflict-
-      // free for 32 consecutive rows), so the bucket of a gallery row is a short LDS binary search instead of a
-      // dependent chain of L2 loads.  Both warps of a row quarter fill disjoint entries.
-      // The distance halves of each row's first THR_MAX sorted positives are staged in shared memory (row
-      // stride 45 words: conflict-free), so the bucket of a gallery row is a short LDS binary search instead of a
-      // dependent chain of L2 loads; deeper positives (rare) and exact distance ties use the 64-bit global search.
-      const bool thr_in_smem = p.buckets != nullptr;
-      const int n_stage = min(p.max_pos, THR_MAX);
-      uint32_t* thr_row = thr_s + row_in_tile * THR_STRIDE;
+      // The distance halves of each row's first THR_MAX sorted positives are staged in shared memory (row stride 33
+      // words: conflict-free), so the bucket of a gallery row is a short LDS binary search instead of a dependent chain
+      // of L2 loads; deeper positives (rare) and exact distance ties use the 64-bit global search.  Staged once per work
+      // item (UNIT_R gallery tiles of the same query tile); the first tile's metadata barrier publishes it.
       if (thr_in_smem) {
         const int rows_here = min(BM, p.nq - mt * BM);
         const unsigned long long* src = p.thr_keys + (size_t)mt * BM * p.max_pos;
-        // warp `ew` stages rows ew, ew+8, ...: coalesced along the sorted entries, and all 32 loads of a thread
-        // are issued before the first shared store (one memory latency per tile, not one per row)
+        // warp `ew` stages rows ew, ew+8, ...: coalesced along the sorted entries, and all loads of a thread are issued
+        // before the first shared store (one memory latency per work item, not one per row)
         const uint32_t* src_hi = reinterpret_cast<const uint32_t*>(src) + 1;  // distance half of a key
-        uint32_t v0[BM / 8], v1[BM / 8];
-        const bool in0 = lane < n_stage, in1 = lane + 32 < n_stage;
+        uint32_t v0[BM / 8];
+        const bool in0 = lane < n_stage;
 #pragma unroll
         for (int i = 0; i < BM / 8; ++i) {
           const int r = ew + 8 * i;
           const size_t o = 2 * ((size_t)r * p.max_pos + lane);
           v0[i] = (r < rows_here && in0) ? src_hi[o] : 0xFFFFFFFFu;
-          v1[i] = (r < rows_here && in1) ? src_hi[o + 64] : 0xFFFFFFFFu;
         }
 #pragma unroll
-        for (int i = 0; i < BM / 8; ++i) {
-          const int r = ew + 8 * i;
-          thr_s[r * THR_STRIDE + lane] = v0[i];
-          if (lane + 32 < THR_MAX) thr_s[r * THR_STRIDE + lane + 32] = v1[i];
+        for (int i = 0; i < BM / 8; ++i) thr_s[(ew + 8 * i) * THR_STRIDE + lane] = v0[i];
+      }
+      for (int nt = nt0; nt < nt0 + ncnt; ++nt, ++it) {
+      const int mb = (it & 1) * BN;  // double-buffered metadata slice
+      if (et < BN) {
+        const int col = nt * BN + et;
+        const bool ok = col < p.ng;
+        cm_sq[mb + et] = ok ? p.g_sq[col] : 0.f;
+        cm_is[mb + et] = ok ? p.g_is[col] : 0.f;
+        cm_idx[mb + et] = (ok && p.g_map) ? static_cast<unsigned int>(p.g_map[col]) : static_cast<unsigned int>(col + p.g_off);
+        if (p.q_pid) {
+          cm_pid[mb + et] = ok ? p.g_pid[col] : -2;
+          cm_mask[mb + et] = ok ? p.g_mask[col] : 0ull;
         }
       }
       const int nps = min(npos, THR_MAX);
@@ -543,7 +561,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 exact = (lo > 0 && thr_row[lo - 1] == kd) || thr_row[lo] == kd;
               }
               if (exact) lo_i = bucket_search_global(p.thr_keys + (size_t)row * p.max_pos, npos, key);
-              atomicAdd(p.buckets + (size_t)row * (p.max_pos + 1) + lo_i, 1);
+              // buckets below THR_MAX: 16-bit counters of this row in shared memory (flushed once per work item) --
+              // round 2 measured the count pass epilogue-bound on ~27 M global REDs per pass (wait_acc 30 k of 850 k clk)
+              if (lo_i < THR_MAX) atomicAdd(cnt_row + (lo_i >> 1), 1u << ((lo_i & 1) * 16));
+              else atomicAdd(p.buckets + (size_t)row * (p.max_pos + 1) + lo_i, 1);
             }
           }
         }
@@ -553,11 +574,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
-      if (thr_in_smem) named_bar_sync(2, 256);  // nobody still reads this tile's thresholds
       CTL_STAMP(5)
       if (++as == 2) {
         as = 0;
         aphase ^= 1u;
+      }
+      }  // gallery tiles of the work item
+      if (thr_in_smem) {
+        named_bar_sync(2, 256);  // every warp is done with this work item's thresholds and counters
+        // flush: the two warps of a row quarter take alternate counter words of the row and leave them zero.  The next
+        // work item's first metadata barrier orders these writes (and the new thresholds) before any use.
+        if (row_ok) {
+          int* dst = p.buckets + (size_t)row * (p.max_pos + 1);
+          for (int wd = chalf; wd < THR_MAX / 2; wd += 2) {
+            const uint32_t v = cnt_row[wd];
+            if (v) {
+              cnt_row[wd] = 0u;
+              if (v & 0xFFFFu) atomicAdd(dst + 2 * wd, (int)(v & 0xFFFFu));
+              if (v >> 16) atomicAdd(dst + 2 * wd + 1, (int)(v >> 16));
+            }
+          }
+        }
+        CTL_STAMP(6)
       }
     }
     if (p.prof && (threadIdx.x == 64 || threadIdx.x == 64 + 5 * 32 + 7)) {
@@ -703,8 +741,7 @@ __global__ void __launch_bounds__(WL_THREADS) dist_worklist_kernel(const int* __
     const int tile = t0 + threadIdx.x;
     int keep = 0;
     if (tile < num_tiles) {
-      int mt, nt;
-      tile_coords(tile, m_tiles, n_tiles, mt, nt);
+      const int nt = tile / m_tiles, mt = tile - nt * m_tiles;  // tile id = nt * m_tiles + mt (unit_coords)
       const int2 a = s_rng[mt], b = s_rng[m_tiles + nt];
       keep = (!(b.y < a.x || b.x > a.y)) || (keep_stride > 0 && nt % keep_stride == 0);
     }
@@ -827,8 +864,9 @@ static int launch_gemm_pass(const void* q_planes, int64_t nq, const void* g_plan
     CTL_CUDA(cudaFuncSetAttribute(dist_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
     attr_set = true;
   }
-  const long long tiles = (long long)p.m_tiles * p.n_tiles;
-  const int grid = (int)std::min<long long>(tiles, sm_count());
+  p.unit_r = p.buckets ? UNIT_R : 1;
+  const long long items = (long long)p.m_tiles * ((p.n_tiles + p.unit_r - 1) / p.unit_r);
+  const int grid = (int)std::min<long long>(items, sm_count());
   dist_gemm_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(maps, p);
   CTL_LAUNCH_CHECK();
   return 0;

@@ -147,7 +147,8 @@ void ctl_debug_set_dist_profile(long long* device_buffer);
 int ctl_topk_plan(int64_t ng, int32_t k, int32_t* emit_all, int32_t* n_groups, int32_t* merge, int32_t* cand_cap);
 int ctl_select_tau(const float* gmin, int64_t nq, int32_t n_groups, int32_t merge, int32_t k, float* tau,
                    ctl_stream_t stream);
-/* Tile list for ctl_pass_desc.tile_list: tile_list[0] = count, then the kept tile ids (ascending).  A tile is kept if
+/* Tile list for ctl_pass_desc.tile_list: tile_list[0] = count, then the kept tile ids (ascending; id = gallery tile *
+ * ceil(nq/128) + query tile).  A tile is kept if
  * the identity ranges of its 128 query rows and its 128 gallery rows intersect (q_pid / g_pid in the planes' row order;
  * both NULL = no identities) or if its gallery-tile index is a multiple of keep_stride (0 = none).  With both operands
  * stored in identity order the first set is a few per cent of the matrix.  ctl_dist_subset_stride(ng, k): the stride that

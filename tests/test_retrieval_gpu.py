@@ -288,7 +288,7 @@ def test_tile_lists_and_pid_sorted_planes_are_bit_identical(R, nq, ng, nid, dim,
 
 def test_tile_list_pass_against_the_full_pass(R):
     """Kernel-level: ctl_dist_worklist keeps exactly the tiles whose identity ranges intersect plus every stride-th gallery
-    tile (checked against numpy, in the kernel's tile order); a pass over that list writes the SAME group minima on the kept
+    tile (checked against numpy); a pass over that list writes the SAME group minima on the kept
     tiles (the rest stay +inf), collects the same positives, and its tau is an upper bound of the full pass's tau."""
     import ctypes as C
 
@@ -307,18 +307,12 @@ def test_tile_list_pass_against_the_full_pass(R):
     work = R._tile_list(qp, gp, ids, stride)
     torch.cuda.synchronize()
     w = work.cpu().numpy()
-    # expectation in numpy: ranges of the sorted identity arrays, tile order = bands of 16 gallery tiles, query tiles fastest
+    # expectation in numpy: ranges of the sorted identity arrays, ids ascending (gallery tile major, query tiles fastest)
     qpid, gpid = ids.q_pid.cpu().numpy(), ids.g_pid.cpu().numpy()
     qr = np.array([[qpid[i * 128:(i + 1) * 128].min(), qpid[i * 128:(i + 1) * 128].max()] for i in range(m_tiles)])
     gr = np.array([[gpid[i * 128:(i + 1) * 128].min(), gpid[i * 128:(i + 1) * 128].max()] for i in range(n_tiles)])
     keep = ~((gr[None, :, 1] < qr[:, None, 0]) | (gr[None, :, 0] > qr[:, None, 1])) | (np.arange(n_tiles)[None, :] % stride == 0)
-    expect = []
-    for band in range((n_tiles + 15) // 16):
-        wdt = min(16, n_tiles - band * 16)
-        for mt in range(m_tiles):
-            for j in range(wdt):
-                if keep[mt, band * 16 + j]:
-                    expect.append(band * 16 * m_tiles + mt * wdt + j)
+    expect = [nt * m_tiles + mt for nt in range(n_tiles) for mt in range(m_tiles) if keep[mt, nt]]  # id = nt * m_tiles + mt
     assert int(w[0]) == len(expect) and np.array_equal(w[1:1 + len(expect)], np.asarray(expect))
     assert 0.1 < len(expect) / (m_tiles * n_tiles) < 0.6
     out = {}
