@@ -468,10 +468,10 @@ def run_retrieval(args, world, rank, local, steps=None, warmup=None):
     qh, gh = feats[:RET_Q].contiguous().pin_memory(), feats[RET_Q:].contiguous().pin_memory()
     q, g = qh.to(dev), gh.to(dev)
     box = {}
-    # both operands are stored in identity order (known with the identities, once per validation set): pass 1 (positives +
-    # top-k threshold) then runs a tile list of ~30 % of the matrix (retrieval.pid_order / ctl_pass_desc.tile_list); results
-    # are reported in the caller's indexing and are bit-identical to the unsorted run (tests/test_retrieval_gpu.py)
-    qo, go = R.pid_order(pids[:RET_Q]), R.pid_order(pids[RET_Q:])
+    # Identity-ordered operands (retrieval.pid_order: pass 1 over a tile list) pay off from ~1.5e8 pairs on
+    # (retrieval.pid_order_pays, measured); config 3 is below that and runs in the caller's order, config 5 above.
+    sort = R.pid_order_pays(RET_Q, RET_G)
+    qo, go = (R.pid_order(pids[:RET_Q]), R.pid_order(pids[RET_Q:])) if sort else (None, None)
     ids = R.encode_ids(pids[:RET_Q], pids[RET_Q:], cams[:RET_Q], cams[RET_Q:], False, dev, q_order=qo, g_order=go)
 
     cache = R.PlaneCache()
@@ -495,9 +495,9 @@ def run_retrieval(args, world, rank, local, steps=None, warmup=None):
 
     def e2e_step(i):
         qd, gd = qh.to(dev, non_blocking=True), gh.to(dev, non_blocking=True)
-        # nothing cached: identity orders, planes and identity arrays are all rebuilt from the host inputs
-        qp = R.build_planes(qd, order=R.pid_order(pids[:RET_Q]))
-        gp = R.build_planes(gd, order=R.pid_order(pids[RET_Q:]))
+        # nothing cached: (identity orders,) planes and identity arrays are all rebuilt from the host inputs
+        qp = R.build_planes(qd, order=R.pid_order(pids[:RET_Q]) if sort else None)
+        gp = R.build_planes(gd, order=R.pid_order(pids[RET_Q:]) if sort else None)
         idx, dst, res = R.topk_and_eval(qp, gp, RET_K, pids[:RET_Q], pids[RET_Q:], cams[:RET_Q], cams[RET_Q:])
         return idx.cpu(), dst.cpu(), res
 
@@ -523,20 +523,33 @@ def run_retrieval(args, world, rank, local, steps=None, warmup=None):
     e1.record()
     torch.cuda.synchronize()
     pass_ms = e0.elapsed_time(e1) / 5
-    # pass 1 as the step runs it: pid-sorted operands, the tile list of the positives + the threshold subset
-    qps, gps = R.build_planes(q, order=qo), cache.get(g, order=go)
-    work = R._tile_list(qps, gps, ids, N.lib().ctl_dist_subset_stride(RET_G, RET_K))
-    desc1 = N.PassDesc(gmin=gmin.data_ptr(), tile_list=work.data_ptr())
-    for _ in range(2):
-        N.check(N.lib().ctl_dist_pass(qps.ptr, RET_Q, gps.ptr, RET_G, RET_D, qps.flags, C.byref(desc1), N.stream_ptr()))
-    torch.cuda.synchronize()
-    e0.record()
+    # pass 2 as the step runs it (candidates + bucket counts): the other half of the step's tensor work
+    ids_b = R.encode_ids(pids[:RET_Q], pids[RET_Q:], cams[:RET_Q], cams[RET_Q:], False, dev)
+    pcnt = torch.zeros(RET_Q, dtype=torch.int32, device=dev)
+    ovf = torch.zeros(1, dtype=torch.int32, device=dev)
+    pos = torch.zeros(RET_Q, ids_b.max_pos, dtype=torch.int64, device=dev)
+    idk = dict(q_pid=ids_b.q_pid.data_ptr(), q_cam=ids_b.q_cam.data_ptr(), g_pid=ids_b.g_pid.data_ptr(),
+               g_cammask=ids_b.g_mask.data_ptr(), max_pos=ids_b.max_pos, overflow=ovf.data_ptr())
+    L = N.lib()
+    N.check(L.ctl_dist_pass(qp.ptr, RET_Q, gp.ptr, RET_G, RET_D, qp.flags, C.byref(N.PassDesc(
+        gmin=gmin.data_ptr(), pos_keys=pos.data_ptr(), pos_count=pcnt.data_ptr(), **idk)), N.stream_ptr()))
+    tau = torch.empty(RET_Q, device=dev)
+    N.check(L.ctl_select_tau(gmin.data_ptr(), RET_Q, gmin.shape[1], 1, RET_K, tau.data_ptr(), N.stream_ptr()))
+    N.check(L.ctl_sort_key_rows(pos.data_ptr(), pcnt.data_ptr(), RET_Q, ids_b.max_pos, N.stream_ptr()))
+    cand = torch.empty(RET_Q, 4096, dtype=torch.int64, device=dev)
+    cc = torch.zeros(RET_Q, dtype=torch.int32, device=dev)
+    buckets = torch.zeros(RET_Q, ids_b.max_pos + 1, dtype=torch.int32, device=dev)
+    desc1 = N.PassDesc(tau=tau.data_ptr(), cand_keys=cand.data_ptr(), cand_count=cc.data_ptr(), cand_cap=4096,
+                       thr_keys=pos.data_ptr(), thr_count=pcnt.data_ptr(), buckets=buckets.data_ptr(), **idk)
+    times = []
     for _ in range(5):
-        N.check(N.lib().ctl_dist_pass(qps.ptr, RET_Q, gps.ptr, RET_G, RET_D, qps.flags, C.byref(desc1), N.stream_ptr()))
-    e1.record()
-    torch.cuda.synchronize()
-    tiles_run = int(work[0].item())
-    thr_pass_ms = e0.elapsed_time(e1) / 5
+        cc.zero_()
+        e0.record()
+        N.check(L.ctl_dist_pass(qp.ptr, RET_Q, gp.ptr, RET_G, RET_D, qp.flags, C.byref(desc1), N.stream_ptr()))
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    pass2_ms = sorted(times)[2]
     pk = peaks()
     flops = 2.0 * RET_Q * RET_G * RET_D  # algorithmic (2*D flop per pair); the kernel issues 3 fp16 products
     ach = flops / (pass_ms * 1e-3) / 1e12
@@ -551,7 +564,7 @@ def run_retrieval(args, world, rank, local, steps=None, warmup=None):
                 "d2h_bytes_per_step": RET_Q * RET_K * 12},
         "roofline": {"kernel": "dist_gemm_kernel (split-fp16 x3 tcgen05, one pass)", "bound": "tensor",
                      "achieved": ach, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"],
-                     "peak_source": pk["src"] + ", bf16 burst (a 0.5 ms kernel timed alone)", "pass_ms": pass_ms, "pass1_ms": thr_pass_ms, "pass1_tiles": f"{tiles_run} of {((RET_Q + 127) // 128) * ((RET_G + 127) // 128)}",
+                     "peak_source": pk["src"] + ", bf16 burst (a 0.5 ms kernel timed alone)", "pass_ms": pass_ms, "pass2_ms": pass2_ms,
                      "traffic": _json_metric("dist_traffic.json", "dram_bytes_per_pass"),
                      "tensor_pipe_tflops": 3 * ach,
                      "note": "achieved = algorithmic 2*Q*G*D flop per pass; the fp32-equivalent split issues 3 fp16 "

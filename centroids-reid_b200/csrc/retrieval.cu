@@ -17,6 +17,7 @@
 #include <limits.h>
 #include <math_constants.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -35,10 +36,12 @@ static constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // q_hi, q_lo, g_hi, g_l
 static constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 static constexpr int GROUP_W = 16;                      // columns per group-min
 static constexpr int META_BYTES = 2 * BN * (4 + 4 + 4 + 8 + 4);  // double-buffered per-tile column metadata
-static constexpr int THR_MAX = 32, THR_STRIDE = 33;         // positives per query held in shared memory
+static constexpr int THR_MAX = 32, THR_STRIDE = 36;         // positives per query held in shared memory (16-byte rows)
 static constexpr int THR_BYTES = BM * THR_STRIDE * 4;
 static constexpr int CNT_STRIDE = THR_MAX / 2 + 1;          // bucket counters of one query row: 2 x 16 bit per word
 static constexpr int CNT_BYTES = BM * CNT_STRIDE * 4;
+static constexpr int FAR_LEVELS = 1;  // buckets of the count pass resolved by plain compares against the farthest positives
+                                      // (measured on config 3: 1 level 0.514 ms, 3 levels 0.531 ms, none 0.568 ms per pass)
 static constexpr int UNIT_R = 4;  // count passes: gallery tiles a CTA runs back to back for ONE query tile
 static constexpr size_t GEMM_SMEM = STAGES * STAGE_BYTES + META_BYTES + THR_BYTES + CNT_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 static_assert(GEMM_SMEM <= 227 * 1024, "dist_gemm_kernel shared memory");
@@ -417,6 +420,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       float qq = 0.f, qis = 0.f, tau = -CUDART_INF_F;
       int qpid = -1, qcam = 0, npos = 0;
       unsigned long long maxkey = 0ull;
+      // distance parts of the FAR_LEVELS + 1 farthest positives of this row, farthest first (0 where there is none)
+      uint32_t tf[FAR_LEVELS + 1];
+#pragma unroll
+      for (int l = 0; l <= FAR_LEVELS; ++l) tf[l] = 0u;
       if (row_ok) {
         qq = p.q_sq[row];
         qis = p.q_is[row];
@@ -428,11 +435,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         if (p.buckets) {
           npos = p.thr_count[row];
           if (npos > 0) maxkey = p.thr_keys[(size_t)row * p.max_pos + npos - 1];
+#pragma unroll
+          for (int l = 0; l <= FAR_LEVELS; ++l)
+            if (npos > l) tf[l] = (uint32_t)(p.thr_keys[(size_t)row * p.max_pos + npos - 1 - l] >> 32);
         }
       }
-      // The distance halves of each row's first THR_MAX sorted positives are staged in shared memory (row stride 33
-      // words: conflict-free), so the bucket of a gallery row is a short LDS binary search instead of a dependent chain
-      // of L2 loads; deeper positives (rare) and exact distance ties use the 64-bit global search.  Staged once per work
+      // The distance halves of each row's first THR_MAX sorted positives are staged in shared memory (row stride 36
+      // words: 16-byte rows, conflict-free LDS.128), so the bucket of a gallery row comes from shared memory instead of a
+      // dependent chain of L2 loads; deeper positives (rare) and exact distance ties use the 64-bit global search.  Staged once per work
       // item (UNIT_R gallery tiles of the same query tile); the first tile's metadata barrier publishes it.
       if (thr_in_smem) {
         const int rows_here = min(BM, p.nq - mt * BM);
@@ -440,13 +450,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         // warp `ew` stages rows ew, ew+8, ...: coalesced along the sorted entries, and all loads of a thread are issued
         // before the first shared store (one memory latency per work item, not one per row)
         const uint32_t* src_hi = reinterpret_cast<const uint32_t*>(src) + 1;  // distance half of a key
+        // slots at and beyond a row's own count hold 0xFFFFFFFF (the key rows are only defined up to their count)
         uint32_t v0[BM / 8];
-        const bool in0 = lane < n_stage;
+        int cn[BM / 8];
+#pragma unroll
+        for (int i = 0; i < BM / 8; ++i) {
+          const int r = ew + 8 * i;
+          cn[i] = r < rows_here ? min(p.thr_count[mt * BM + r], n_stage) : 0;
+        }
 #pragma unroll
         for (int i = 0; i < BM / 8; ++i) {
           const int r = ew + 8 * i;
           const size_t o = 2 * ((size_t)r * p.max_pos + lane);
-          v0[i] = (r < rows_here && in0) ? src_hi[o] : 0xFFFFFFFFu;
+          v0[i] = lane < cn[i] ? src_hi[o] : 0xFFFFFFFFu;
         }
 #pragma unroll
         for (int i = 0; i < BM / 8; ++i) thr_s[(ew + 8 * i) * THR_STRIDE + lane] = v0[i];
@@ -484,6 +500,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         // ---- phase 1, branch-free: the 16 distances and the masks of the (rare) elements that need more ----
         float dist[16];
         uint32_t m_valid = 0, m_cand = 0, m_pos = 0, m_cnt = 0;
+        uint32_t m_far[FAR_LEVELS];
+#pragma unroll
+        for (int l = 0; l < FAR_LEVELS; ++l) m_far[l] = 0u;
         float gmin = CUDART_INF_F;
         {
           const float4* sqv = reinterpret_cast<const float4*>(cm_sq + mb + cl0);
@@ -510,14 +529,35 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               const bool junk = same && ((cm_mask[mb + cl0 + j] >> qcam) & 1ull);
               const bool ok = (m_valid >> j) & 1u;
               m_pos |= ((ok && same && !junk) ? 1u : 0u) << j;
-              // float compare first (cheap); exact 64-bit key order is re-checked in phase 2
-              m_cnt |= ((ok && !junk && npos > 0 && float_orderable(dist[j]) <= (uint32_t)(maxkey >> 32)) ? 1u : 0u) << j;
+              // kept rows at or before the farthest positive are counted.  A row strictly between two of the FAR_LEVELS + 1
+              // farthest positives (for a query with a few far positives: almost everything that is counted) has its
+              // bucket without a search -> m_far[l], one popc per chunk and level; the rest (nearer rows and distance
+              // ties) take the per-row path of phase 2.
+              const uint32_t kdj = float_orderable(dist[j]);
+              const bool cnt = ok && !junk && npos > 0 && kdj <= tf[0];
+              bool fast = false;
+#pragma unroll
+              for (int l = 0; l < FAR_LEVELS; ++l) {
+                const bool f = cnt && kdj > tf[l + 1] && kdj < tf[l];
+                m_far[l] |= (f ? 1u : 0u) << j;
+                fast = fast || f;
+              }
+              m_cnt |= ((cnt && !fast) ? 1u : 0u) << j;
             }
           }
         }
         if (!p.cand_keys) m_cand = 0;
         if (!p.pos_keys) m_pos = 0;
         if (!p.buckets) m_cnt = 0;
+        if (p.buckets) {
+#pragma unroll
+          for (int l = 0; l < FAR_LEVELS; ++l)
+            if (m_far[l]) {  // (tf[l + 1] < kd < tf[l] needs positive npos - 1 - l to exist: the bucket index is >= 0)
+              const int b = npos - 1 - l, c = __popc(m_far[l]);
+              if (b < THR_MAX) atomicAdd(cnt_row + (b >> 1), (uint32_t)c << ((b & 1) * 16));
+              else atomicAdd(p.buckets + (size_t)row * (p.max_pos + 1) + b, c);
+            }
+        }
         // ---- phase 2: full-matrix output (dense) and the rare per-element actions ----
         if (p.dist_out) {
 #pragma unroll
@@ -550,15 +590,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               bool exact = true;
               const uint32_t kd = (uint32_t)(key >> 32);
               if (nps == npos || kd < thr_row[nps - 1]) {
-                int lo = 0, hi = nps - 1;  // thr_row[hi] >= kd
-                while (lo < hi) {
-                  const int mid = (lo + hi) >> 1;
-                  if (thr_row[mid] > kd) hi = mid; else lo = mid + 1;
+                // lo = number of staged positives whose distance is <= kd = index of the first LARGER one.  Branch-free
+                // over all THR_MAX slots (unused ones hold 0xFFFFFFFF): 8 independent LDS.128 + 32 compares -- the
+                // binary search this replaces was a chain of 5 dependent shared-memory loads per counted row, and with
+                // ~half the gallery counted for a query with one far positive it made the count pass epilogue-bound.
+                int lo = 0;
+#pragma unroll
+                for (int t4 = 0; t4 < THR_MAX / 4; ++t4) {
+                  const uint4 v = *reinterpret_cast<const uint4*>(thr_row + 4 * t4);
+                  lo += (v.x <= kd ? 1 : 0) + (v.y <= kd ? 1 : 0) + (v.z <= kd ? 1 : 0) + (v.w <= kd ? 1 : 0);
                 }
                 lo_i = lo;
-                // `lo` = first entry with a LARGER distance; a positive with the SAME distance needs the
-                // 64-bit (distance, index) comparison
-                exact = (lo > 0 && thr_row[lo - 1] == kd) || thr_row[lo] == kd;
+                // a positive with the SAME distance needs the 64-bit (distance, index) comparison
+                exact = lo > 0 && thr_row[lo - 1] == kd;
               }
               if (exact) lo_i = bucket_search_global(p.thr_keys + (size_t)row * p.max_pos, npos, key);
               // buckets below THR_MAX: 16-bit counters of this row in shared memory (flushed once per work item) --
@@ -864,7 +908,12 @@ static int launch_gemm_pass(const void* q_planes, int64_t nq, const void* g_plan
     CTL_CUDA(cudaFuncSetAttribute(dist_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
     attr_set = true;
   }
-  p.unit_r = p.buckets ? UNIT_R : 1;
+  static const int unit_r_env = [] {
+    const char* e = getenv("CTL_DIST_UNIT_R");  // experiments: gallery tiles per work item of the count pass
+    const int v = e ? atoi(e) : 1;  // measured (round 2): no gain from longer items once the thresholds are staged cheaply
+    return v >= 1 && v <= UNIT_R ? v : UNIT_R;
+  }();
+  p.unit_r = p.buckets ? unit_r_env : 1;
   const long long items = (long long)p.m_tiles * ((p.n_tiles + p.unit_r - 1) / p.unit_r);
   const int grid = (int)std::min<long long>(items, sm_count());
   dist_gemm_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(maps, p);
