@@ -657,7 +657,7 @@ def topk_and_eval_sharded(qp: Planes, gp_local: Planes, k: int, ids: EncodedIds,
     buckets = torch.zeros(nq, mp + 1, dtype=torch.int32, device=dev)
     s = N.stream_ptr
     if tile_lists is None:
-        tile_lists = _tile_lists_enabled(qp, gp)
+        tile_lists = _tile_lists_enabled(qp, gp_local)
     gmap = _g_index_map(gp_local, g_index_offset)  # pid-sorted shard: keys carry the GLOBAL gallery row
     idp = dict(q_pid=ids.q_pid.data_ptr(), q_cam=ids.q_cam.data_ptr(), g_pid=ids.g_pid.data_ptr(),
                g_cammask=ids.g_mask.data_ptr(), overflow=ovf.data_ptr(), g_index_offset=g_index_offset,

@@ -162,3 +162,17 @@ def test_ctl_model_under_a_lightning_like_base(monkeypatch):
     finally:
         monkeypatch.undo()
         importlib.reload(M)
+
+
+def test_no_undefined_names_in_the_python_sources():
+    """GPU-only branches (sharded retrieval, NCCL paths) are not executed by the CPU suite: a static scan keeps a typo in them
+    from surviving until the GPU box (tools/undefined_names.py: names loaded in a function that are bound nowhere)."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[1]
+    files = [str(p) for p in list((root / "centroids-reid_b200").rglob("*.py")) + [root / "bench.py", root / "__graft_entry__.py"]
+             + list((root / "tools").glob("*.py"))]
+    r = subprocess.run([sys.executable, str(root / "tools" / "undefined_names.py")] + files, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout
