@@ -475,13 +475,19 @@ def run_retrieval(args, world, rank, local, steps=None, warmup=None):
     ids = R.encode_ids(pids[:RET_Q], pids[RET_Q:], cams[:RET_Q], cams[RET_Q:], False, dev, q_order=qo, g_order=go)
 
     cache = R.PlaneCache()
+    # one validation set evaluated again and again: the step's launch sequence is captured once (retrieval.TopkEvalSession)
+    # when the operands stay in the caller's order; identity-ordered operands (config 5 sizes) take the eager path
+    sess = None if sort else R.TopkEvalSession(g, RET_Q, RET_K, pids[:RET_Q], pids[RET_Q:], cams[:RET_Q], cams[RET_Q:])
 
     def step(i):
         # one retrieval pass against a RESIDENT gallery: query planes from the fp32 query features, the gallery's planes
-        # from the cache (built once per gallery tensor version -- a fixed `embeddings.npy` searched by successive query
-        # sets, inference/get_similar.py:104-128), two tensor-core passes, top-100 + CMC/mAP, one read-back
-        qp, gp = R.build_planes(q, order=qo), cache.get(g, order=go)
-        idx, dst, res = R.topk_and_eval(qp, gp, RET_K, pids[:RET_Q], pids[RET_Q:], cams[:RET_Q], cams[RET_Q:], ids=ids)
+        # built once per gallery tensor (a fixed `embeddings.npy` searched by successive query sets,
+        # inference/get_similar.py:104-128), two tensor-core passes, top-100 + CMC/mAP, one read-back
+        if sess is not None:
+            idx, dst, res = sess(q)
+        else:
+            qp, gp = R.build_planes(q, order=qo), cache.get(g, order=go)
+            idx, dst, res = R.topk_and_eval(qp, gp, RET_K, pids[:RET_Q], pids[RET_Q:], cams[:RET_Q], cams[RET_Q:], ids=ids)
         box["res"] = res
 
     for i in range(warmup):
@@ -558,8 +564,9 @@ def run_retrieval(args, world, rank, local, steps=None, warmup=None):
         "unit": "pairs/s", "ms_per_step": dt * 1e3, "steps": steps, "n_gpus": 1, "mAP": box["res"].mAP,
         "rank1": float(box["res"].cmc[0]),
         "config": {"workload": "BASELINE config 3: 3368 query x 15913 gallery x 2048-d, L2 top-100 + CMC/mAP",
-                   "planes": "`value`: gallery planes cached across steps (resident gallery, retrieval.PlaneCache), query planes "
-                             "built every step; `e2e`: both built every step from the freshly uploaded host features"},
+                   "planes": "`value`: gallery planes resident (built once), query features copied in and their planes built every "
+                             "step, the step's launches replayed from one CUDA graph (retrieval.TopkEvalSession); `e2e`: "
+                             "eager path, both operands' planes built every step from the freshly uploaded host features"},
         "e2e": {"value": RET_Q * RET_G / dte, "unit": "pairs/s", "h2d_bytes_per_step": (RET_Q + RET_G) * RET_D * 4,
                 "d2h_bytes_per_step": RET_Q * RET_K * 12},
         "roofline": {"kernel": "dist_gemm_kernel (split-fp16 x3 tcgen05, one pass)", "bound": "tensor",

@@ -306,18 +306,28 @@ def _aggregate(ranks, ap: np.ndarray, n_pos: np.ndarray, q_pids, num_g: int, max
     return EvalResult(cmc, float(np.mean(aps)), topk, np.nonzero(valid)[0], aps, q_pids, ranks)
 
 
-def _finalize_and_read_back(buckets, count, nq, max_pos, ovf):
-    """ctl_eval_finalize_packed + ONE device->host copy: per query (AP, first-hit rank, #positives) and the overflow flag
-    as float64 (exact for these integers).  Returns (ranks on the device, ap, first, count, overflow) -- the last four on
-    the host."""
+def _finalize(buckets, count, nq, max_pos, ovf):
+    """ctl_eval_finalize_packed (enqueue only): ranks [nq, max_pos] and the packed per-query results [nq + 1, 3] float64
+    (AP, first-hit rank, #positives; last row: overflow flag) on the device."""
     dev = buckets.device
     ranks = torch.empty(nq, max_pos, dtype=torch.int32, device=dev)
     ap = torch.empty(nq, dtype=torch.float64, device=dev)
     pack = torch.empty(nq + 1, 3, dtype=torch.float64, device=dev)
     N.check(N.lib().ctl_eval_finalize_packed(buckets.data_ptr(), count.data_ptr(), nq, max_pos, ranks.data_ptr(), ap.data_ptr(),
                                              pack.data_ptr(), ovf.data_ptr(), N.stream_ptr()))
-    h = pack.cpu().numpy()
-    return ranks, h[:nq, 0], h[:nq, 1].astype(np.int64), h[:nq, 2].astype(np.int32), int(h[nq, 0])
+    return ranks, pack
+
+
+def _unpack(h: np.ndarray, nq: int):
+    """host view of `pack`: (ap, first-hit rank, #positives, overflow flag) -- float64 is exact for these integers."""
+    return h[:nq, 0], h[:nq, 1].astype(np.int64), h[:nq, 2].astype(np.int32), int(h[nq, 0])
+
+
+def _finalize_and_read_back(buckets, count, nq, max_pos, ovf):
+    """_finalize + ONE device->host copy.  Returns (ranks on the device, ap, first, count, overflow) -- the last four on
+    the host."""
+    ranks, pack = _finalize(buckets, count, nq, max_pos, ovf)
+    return (ranks,) + _unpack(pack.cpu().numpy(), nq)
 
 
 def _tile_lists_enabled(qp: Planes, gp: Planes) -> bool:
@@ -544,6 +554,21 @@ def topk_and_eval(qp: Planes, gp: Planes, k: int, q_pids, g_pids, q_camids, g_ca
     Identities are given in the caller's row order; a precomputed `ids` must carry the planes' orders
     (encode_ids(q_order=qp.order_host, g_order=gp.order_host)).
     Returns (idx [nq,k] int64, dist [nq,k] float32 on the device, EvalResult), all in the caller's indexing."""
+    dev = qp.buf.device
+    if ids is None:
+        ids = encode_ids(q_pids, g_pids, q_camids, g_camids, respect_camids, dev, q_order=qp.order_host,
+                         g_order=gp.order_host)
+    if tile_lists is None:
+        tile_lists = _tile_lists_enabled(qp, gp)
+    with torch.cuda.device(dev):
+        out = _topk_and_eval_enqueue(qp, gp, k, ids, tile_lists)
+        h = out["pack"].cpu().numpy()
+    return _topk_and_eval_finish(out, h, qp, gp, k, q_pids, g_pids, q_camids, g_camids, max_rank, respect_camids, ids)
+
+
+def _topk_and_eval_enqueue(qp: Planes, gp: Planes, k: int, ids: "EncodedIds", tile_lists: bool):
+    """The launch sequence of topk_and_eval, no host synchronisation (capturable in a CUDA graph): returns the device
+    tensors {idx, dst, ranks, pack} in the planes' row order and whether pass 1 ran a threshold subset."""
     import ctypes as C
 
     L = N.lib()
@@ -552,11 +577,6 @@ def topk_and_eval(qp: Planes, gp: Planes, k: int, q_pids, g_pids, q_camids, g_ca
     k = int(min(k, ng))
     emit_all, n_groups, merge, cap = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
     N.check(L.ctl_topk_plan(ng, k, C.byref(emit_all), C.byref(n_groups), C.byref(merge), C.byref(cap)))
-    if ids is None:
-        ids = encode_ids(q_pids, g_pids, q_camids, g_camids, respect_camids, dev, q_order=qp.order_host,
-                         g_order=gp.order_host)
-    if tile_lists is None:
-        tile_lists = _tile_lists_enabled(qp, gp)
     d_qpid, d_qcam, d_gpid, d_gmask, max_pos = ids.q_pid, ids.q_cam, ids.g_pid, ids.g_mask, ids.max_pos
     gmin = torch.empty(nq, n_groups.value, dtype=torch.float32, device=dev)
     tau = torch.empty(nq, dtype=torch.float32, device=dev)
@@ -571,44 +591,107 @@ def topk_and_eval(qp: Planes, gp: Planes, k: int, q_pids, g_pids, q_camids, g_ca
     gmap = _g_index_map(gp, 0)
     idp = dict(q_pid=d_qpid.data_ptr(), q_cam=d_qcam.data_ptr(), g_pid=d_gpid.data_ptr(),
                g_cammask=d_gmask.data_ptr(), max_pos=max_pos, overflow=ovf.data_ptr(), g_index_map=N.ptr(gmap))
-    with torch.cuda.device(dev):
-        p1 = N.PassDesc(pos_keys=pos_keys.data_ptr(), pos_count=pos_count.data_ptr(), **idp)
+    p1 = N.PassDesc(pos_keys=pos_keys.data_ptr(), pos_count=pos_count.data_ptr(), **idp)
+    if not emit_all.value:
+        p1.gmin = gmin.data_ptr()
+    work = None
+    if tile_lists:
+        # (small gallery, tau = +inf: pass 1 only collects -> stride 0, just the tiles that can hold a positive)
+        stride = 0 if emit_all.value else L.ctl_dist_subset_stride(ng, k)
+        if emit_all.value or stride > 1:
+            work = _tile_list(qp, gp, ids, stride)
+    if work is not None:
+        p1.tile_list = work.data_ptr()
         if not emit_all.value:
-            p1.gmin = gmin.data_ptr()
-        work = None
-        if tile_lists:
-            # (small gallery, tau = +inf: pass 1 only collects -> stride 0, just the tiles that can hold a positive)
-            stride = 0 if emit_all.value else L.ctl_dist_subset_stride(ng, k)
-            if emit_all.value or stride > 1:
-                work = _tile_list(qp, gp, ids, stride)
-        if work is not None:
-            p1.tile_list = work.data_ptr()
-            if not emit_all.value:
-                N.check(L.ctl_fill_f32(gmin.data_ptr(), gmin.numel(), float("inf"), s()))  # groups of tiles not run
-        N.check(L.ctl_dist_pass(qp.ptr, nq, gp.ptr, ng, qp.d, qp.flags, C.byref(p1), s()))
-        if emit_all.value:
-            N.check(L.ctl_fill_f32(tau.data_ptr(), nq, float("inf"), s()))
-        else:
-            N.check(L.ctl_select_tau(gmin.data_ptr(), nq, n_groups.value, merge.value, k, tau.data_ptr(), s()))
-        N.check(L.ctl_sort_key_rows(pos_keys.data_ptr(), pos_count.data_ptr(), nq, max_pos, s()))
-        p2 = N.PassDesc(tau=tau.data_ptr(), cand_keys=cand.data_ptr(), cand_count=cand_count.data_ptr(),
-                        cand_cap=cap.value, thr_keys=pos_keys.data_ptr(), thr_count=pos_count.data_ptr(),
-                        buckets=buckets.data_ptr(), **idp)
-        N.check(L.ctl_dist_pass(qp.ptr, nq, gp.ptr, ng, qp.d, qp.flags, C.byref(p2), s()))
-        N.check(L.ctl_sort_key_rows(cand.data_ptr(), cand_count.data_ptr(), nq, cap.value, s()))
-        N.check(L.ctl_topk_emit(cand.data_ptr(), cand_count.data_ptr(), nq, cap.value, k, idx.data_ptr(),
-                                dst.data_ptr(), ovf.data_ptr(), s()))
-        ranks, ap_h, first_h, cnt_h, ovf_h = _finalize_and_read_back(buckets, pos_count, nq, max_pos, ovf)
-        if ovf_h and work is not None and not emit_all.value:
-            # the looser threshold let more rows through than the candidate list holds: threshold from every tile
-            return topk_and_eval(qp, gp, k, q_pids, g_pids, q_camids, g_camids, max_rank, respect_camids, ids, tile_lists=False)
-        inv_d, inv_h = _query_inverse(qp)
-        if inv_h is not None:  # back to the caller's query order
-            idx, dst, ranks = idx.index_select(0, inv_d), dst.index_select(0, inv_d), ranks.index_select(0, inv_d)
-            ap_h, first_h, cnt_h = ap_h[inv_h], first_h[inv_h], cnt_h[inv_h]
+            N.check(L.ctl_fill_f32(gmin.data_ptr(), gmin.numel(), float("inf"), s()))  # groups of tiles not run
+    N.check(L.ctl_dist_pass(qp.ptr, nq, gp.ptr, ng, qp.d, qp.flags, C.byref(p1), s()))
+    if emit_all.value:
+        N.check(L.ctl_fill_f32(tau.data_ptr(), nq, float("inf"), s()))
+    else:
+        N.check(L.ctl_select_tau(gmin.data_ptr(), nq, n_groups.value, merge.value, k, tau.data_ptr(), s()))
+    N.check(L.ctl_sort_key_rows(pos_keys.data_ptr(), pos_count.data_ptr(), nq, max_pos, s()))
+    p2 = N.PassDesc(tau=tau.data_ptr(), cand_keys=cand.data_ptr(), cand_count=cand_count.data_ptr(),
+                    cand_cap=cap.value, thr_keys=pos_keys.data_ptr(), thr_count=pos_count.data_ptr(),
+                    buckets=buckets.data_ptr(), **idp)
+    N.check(L.ctl_dist_pass(qp.ptr, nq, gp.ptr, ng, qp.d, qp.flags, C.byref(p2), s()))
+    N.check(L.ctl_sort_key_rows(cand.data_ptr(), cand_count.data_ptr(), nq, cap.value, s()))
+    N.check(L.ctl_topk_emit(cand.data_ptr(), cand_count.data_ptr(), nq, cap.value, k, idx.data_ptr(),
+                            dst.data_ptr(), ovf.data_ptr(), s()))
+    ranks, pack = _finalize(buckets, pos_count, nq, max_pos, ovf)
+    return {"idx": idx, "dst": dst, "ranks": ranks, "pack": pack, "subset": work is not None and not emit_all.value,
+            "keep": (gmin, tau, cand, zeros, pos_keys, buckets, work, gmap)}
+
+
+def _topk_and_eval_finish(out, h, qp, gp, k, q_pids, g_pids, q_camids, g_camids, max_rank, respect_camids, ids):
+    """host half of topk_and_eval: overflow handling, back to the caller's query order, eval_func's final reductions."""
+    nq, ng = qp.n, gp.n
+    idx, dst, ranks = out["idx"], out["dst"], out["ranks"]
+    ap_h, first_h, cnt_h, ovf_h = _unpack(h, nq)
+    if ovf_h and out["subset"]:
+        # the looser threshold let more rows through than the candidate list holds: threshold from every tile
+        return topk_and_eval(qp, gp, k, q_pids, g_pids, q_camids, g_camids, max_rank, respect_camids, ids, tile_lists=False)
     if ovf_h:
         raise OverflowError("a device-side list overflowed (exact ties at the k-th distance, or max_pos)")
+    inv_d, inv_h = _query_inverse(qp)
+    if inv_h is not None:  # back to the caller's query order
+        idx, dst, ranks = idx.index_select(0, inv_d), dst.index_select(0, inv_d), ranks.index_select(0, inv_d)
+        ap_h, first_h, cnt_h = ap_h[inv_h], first_h[inv_h], cnt_h[inv_h]
     return idx, dst, _aggregate(ranks, ap_h, cnt_h, np.asarray(q_pids), ng, max_rank, first=first_h)
+
+
+class TopkEvalSession:
+    """topk_and_eval for ONE validation set evaluated again and again (a resident gallery searched by successive query
+    batches, inference/get_similar.py:104-128; the per-epoch validation of train_ctl_model.py): the ~12 launches of the step
+    (query planes, both tensor-core passes, selection, sorts, emit, finalize, the packed device->host copy) are captured
+    ONCE in a CUDA graph over static buffers and replayed -- no per-step allocation, descriptor encoding or launch gaps.
+    Results are those of topk_and_eval, bit for bit (tests/test_retrieval_gpu.py)."""
+
+    def __init__(self, gallery: torch.Tensor, num_query: int, k: int, q_pids, g_pids, q_camids, g_camids, max_rank: int = 50,
+                 respect_camids: bool = False, dist: str = "euclidean", normalize: bool = False):
+        N.require_cuda(gallery)
+        dev = gallery.device
+        self.dev, self.k, self.max_rank, self.respect = dev, int(k), max_rank, respect_camids
+        self.args = (q_pids, g_pids, q_camids, g_camids)
+        self.dist, self.normalize = dist, normalize
+        self.gp = build_planes(gallery, dist, normalize)
+        self.ids = encode_ids(q_pids, g_pids, q_camids, g_camids, respect_camids, dev)
+        self.q = torch.empty(num_query, gallery.shape[1], dtype=torch.float32, device=dev)  # static input of the graph
+        self.host = torch.empty(num_query + 1, 3, dtype=torch.float64).pin_memory()
+        self.done = torch.cuda.Event()
+
+        def enqueue():
+            qp = build_planes(self.q, dist, normalize)
+            out = _topk_and_eval_enqueue(qp, self.gp, self.k, self.ids, False)
+            self.host.copy_(out["pack"], non_blocking=True)
+            out["qp"] = qp
+            return out
+
+        with torch.cuda.device(dev):
+            cur = torch.cuda.current_stream(dev)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):  # eager warm-up: function attributes, allocator pools
+                self.q.zero_()
+                for _ in range(2):
+                    enqueue()
+            cur.wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = enqueue()
+
+    def __call__(self, q: torch.Tensor):
+        """q: [num_query, d] features on the device -> (idx, dist, EvalResult) like topk_and_eval.  The returned device
+        tensors are the graph's static outputs: valid until the next call."""
+        N.require_cuda(q)
+        with torch.cuda.device(self.dev):
+            self.q.copy_(q, non_blocking=True)
+            self.graph.replay()
+            self.done.record()
+            self.done.synchronize()
+        out = self.out
+        return _topk_and_eval_finish(out, self.host.numpy(), out["qp"], self.gp, self.k, *self.args, self.max_rank,
+                                     self.respect, self.ids)
 
 
 def encode_ids_sharded(q_pids, g_pids_local, q_camids, g_camids_local, device, group, q_order=None,

@@ -342,3 +342,20 @@ def test_tile_list_pass_against_the_full_pass(R):
     # a tile list is refused where every tile is needed
     bad = N.PassDesc(dist_out=gmin.data_ptr(), ld_out=ng, tile_list=work.data_ptr())
     assert L.ctl_dist_pass(qp.ptr, nq, gp.ptr, ng, dim, qp.flags, C.byref(bad), N.stream_ptr()) == -1
+
+
+def test_topk_eval_session_replays_bit_identical(R):
+    """TopkEvalSession = the launch sequence of topk_and_eval captured once in a CUDA graph: successive query sets against
+    the resident gallery give exactly topk_and_eval's indices, distances, ranks, AP and CMC."""
+    nq, ng, nid, dim = 500, 7000, 120, 512
+    feats, pids, cams = O.synth_retrieval(nq, ng, nid, dim, 2.0, 53, num_cams=4)
+    gal = feats[nq:].cuda()
+    args = (pids[:nq], pids[nq:], cams[:nq], cams[nq:])
+    sess = R.TopkEvalSession(gal, nq, 50, *args)
+    g = torch.Generator().manual_seed(7)
+    for rep in range(3):
+        q = torch.nn.functional.normalize(feats[:nq] + 0.3 * rep * torch.randn(nq, dim, generator=g), dim=1).cuda()
+        idx, dst, res = sess(q)
+        idx0, dst0, res0 = R.topk_and_eval(R.build_planes(q), R.build_planes(gal), 50, *args)
+        assert torch.equal(idx, idx0) and torch.equal(dst, dst0)
+        _same_eval(res, res0)
