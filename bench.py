@@ -188,7 +188,6 @@ def build_engine(device):
 def run_embed(args, world, rank, local):
     import torch.distributed as dist
 
-    from ctl_b200.datasets.transforms import normalize_batch
     from ctl_b200.modelling.backbones.engine import GraphedCall, GraphedForward
 
     dev = torch.device("cuda", local)
@@ -241,9 +240,8 @@ def run_embed(args, world, rank, local):
         emb_ready = [torch.cuda.Event() for _ in range(2)]  # graph b's output tensor holds this step's embeddings
         d2h_done = [torch.cuda.Event() for _ in range(2)]   # ... and has been copied out (graph b may overwrite it)
 
-        def fwd(b):
-            x = normalize_batch(stage_in[b]) if kind == "u8" else stage_in[b]
-            return eng.forward(x, want_emb=True)
+        def fwd(b):  # uint8 crops: ToTensor + Normalize run inside the fused stem's packing kernel (forward_u8)
+            return eng.forward_u8(stage_in[b], want_emb=True) if kind == "u8" else eng.forward(stage_in[b], want_emb=True)
 
         stage_graphs = [GraphedCall(lambda b=b: fwd(b), dev) for b in range(2)]
 
@@ -295,8 +293,9 @@ def run_embed(args, world, rank, local):
     v32, b32 = e2e_run("f32")
     clk.__exit__(None, None, None)
     e2e = {"value": v8, "unit": "embeddings/s", "h2d_bytes_per_step": b8, "d2h_bytes_per_step": BATCH * 2048 * 4,
-           "input": "pinned uint8 HWC crops; ToTensor + Normalize on the device (datasets/transforms.normalize_batch), then "
-                    "TrunkEngine.forward; H2D of step i+1 overlaps the compute of step i",
+           "input": "pinned uint8 HWC crops; ToTensor + Normalize folded into the fused stem's input packing "
+                    "(TrunkEngine.forward_u8 == forward(normalize_batch(x)) bit for bit); H2D of step i+1 overlaps the compute "
+                    "of step i",
            "fp32_input": {"value": v32, "unit": "embeddings/s", "h2d_bytes_per_step": b32,
                           "input": "pinned fp32 NCHW crops already normalised on the host (the tensor the reference's "
                                    "forward takes)"}}

@@ -113,6 +113,7 @@ SIGNATURES = {
     "ctl_stem_conv7x7_tc": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _i32, _p, _p]),
     "ctl_stem_pad_bytes": (C.c_size_t, [_i32, _i32, _i32]),
     "ctl_stem_pool_fused": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _p, _i32, _p, _p]),
+    "ctl_stem_pool_fused_u8": (C.c_int, [_p, _i32, _i32, _i32, C.POINTER(C.c_float), C.POINTER(C.c_float), _p, _p, _p, _i32, _p, _p]),
     "ctl_maxpool3x3s2_nhwc_f16": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p]),
     "ctl_gap_bn_nhwc_f16": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
     "ctl_instnorm_relu_nhwc_f16": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p, _f, _p]),

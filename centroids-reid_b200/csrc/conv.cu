@@ -1232,6 +1232,30 @@ __global__ void __launch_bounds__(256) stem_pack_input_kernel(const float* __res
   dst[1] = make_uint2(*reinterpret_cast<const uint32_t*>(&a1), *reinterpret_cast<const uint32_t*>(&b1));
 }
 
+// The same packed layout straight from uint8 HWC crops: ToTensor + Normalize (datasets/transforms/build.py:29-33) folded
+// into the pack -- (u / 255 - mean) / std in IEEE fp32 (the arithmetic of augment_kernel, so the fp16 operand is
+// bit-identical to normalize_batch followed by stem_pack_input_kernel) without the fp32 NCHW tensor in between
+// (3 B read per pixel instead of 12 B written + 12 B read).
+__global__ void __launch_bounds__(256) stem_pack_input_u8_kernel(const uint8_t* __restrict__ x, int N, int H, int W, float m0,
+                                                                 float m1, float m2, float s0, float s1, float s2,
+                                                                 __half* __restrict__ xp) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 6);  // n * H + y
+  const int xw = 2 * (threadIdx.x & 63);
+  if (row >= N * H || xw >= W) return;
+  const int n = row / H, y = row - n * H;
+  const uint16_t* src = reinterpret_cast<const uint16_t*>(x + ((size_t)row * W + xw) * 3);  // 6 bytes, 2-byte aligned
+  const uint32_t w0 = src[0], w1 = src[1], w2 = src[2];  // r0 g0 | b0 r1 | g1 b1
+  const float r0 = (float)(w0 & 255u) / 255.f, g0 = (float)(w0 >> 8) / 255.f, b0 = (float)(w1 & 255u) / 255.f;
+  const float r1 = (float)(w1 >> 8) / 255.f, g1 = (float)(w2 & 255u) / 255.f, b1 = (float)(w2 >> 8) / 255.f;
+  const __half2 a0 = __floats2half2_rn((r0 - m0) / s0, (g0 - m1) / s1), c0 = __floats2half2_rn((b0 - m2) / s2, 0.f);
+  const __half2 a1 = __floats2half2_rn((r1 - m0) / s0, (g1 - m1) / s1), c1 = __floats2half2_rn((b1 - m2) / s2, 0.f);
+  uint2* dst = reinterpret_cast<uint2*>(xp + (((size_t)n * (H + 6) + y + 3) * S3_WP + xw + 3) * 4);
+  dst[0] = make_uint2(*reinterpret_cast<const uint32_t*>(&a0), *reinterpret_cast<const uint32_t*>(&c0));
+  dst[1] = make_uint2(*reinterpret_cast<const uint32_t*>(&a1), *reinterpret_cast<const uint32_t*>(&c1));
+}
+
 __global__ void __launch_bounds__(S3_THREADS, 1) stem_pool_kernel(const __grid_constant__ Stem3Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -1863,16 +1887,10 @@ size_t ctl_stem_pad_bytes(int32_t n, int32_t h, int32_t w) {
   return (size_t)n * (h + 6) * S3_WP * 4 * sizeof(__half) + 256;  // + slack: the last piece of a row is read 256 B wide
 }
 
-int ctl_stem_pool_fused(const float* x_nchw, int32_t n, int32_t h, int32_t w, void* xpad, const void* weight_packed_f16,
-                        const float* bias, int32_t relu, void* out_pooled_nhwc_f16, ctl_stream_t stream) {
-  CTL_CHECK_ARG(x_nchw && xpad && weight_packed_f16 && bias && out_pooled_nhwc_f16, "null pointer");
-  CTL_CHECK_ARG(n >= 1 && h >= 8 && w >= 8 && h % 4 == 0 && w % 2 == 0 && w <= 128,
-                "the fused stem needs h % 4 == 0, even w <= 128 (use ctl_stem_conv7x7_tc + ctl_maxpool3x3s2_nhwc_f16)");
-  int rc = ctl_device_check();
-  if (rc) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
-  CTL_CUDA(launch_k(stem_pack_input_kernel, dim3((unsigned)(((size_t)n * h + 3) / 4)), dim3(256), 0, st, x_nchw, (int)n, (int)h,
-                    (int)w, static_cast<__half*>(xpad)));
+// the conv + pool kernel on an already packed input (shared by the fp32 and the uint8 entry points)
+static int stem_pool_launch(int32_t n, int32_t h, int32_t w, void* xpad, const void* weight_packed_f16, const float* bias,
+                            int32_t relu, void* out_pooled_nhwc_f16, cudaStream_t st) {
+  int rc;
   Stem3Params p = {};
   p.w = static_cast<const __half*>(weight_packed_f16);
   p.bias = bias;
@@ -1899,6 +1917,38 @@ int ctl_stem_pool_fused(const float* x_nchw, int32_t n, int32_t h, int32_t w, vo
   const int grid = (int)std::min<long long>(tiles, (long long)sm_count());
   CTL_CUDA(launch_k(stem_pool_kernel, dim3(grid), dim3(S3_THREADS), S3_SMEM, st, p));
   return 0;
+}
+
+static int stem_fused_check(const void* x, int32_t n, int32_t h, int32_t w, const void* xpad, const void* wt, const float* bias,
+                            const void* out) {
+  CTL_CHECK_ARG(x && xpad && wt && bias && out, "null pointer");
+  CTL_CHECK_ARG(n >= 1 && h >= 8 && w >= 8 && h % 4 == 0 && w % 2 == 0 && w <= 128,
+                "the fused stem needs h % 4 == 0, even w <= 128 (use ctl_stem_conv7x7_tc + ctl_maxpool3x3s2_nhwc_f16)");
+  return ctl_device_check();
+}
+
+int ctl_stem_pool_fused(const float* x_nchw, int32_t n, int32_t h, int32_t w, void* xpad, const void* weight_packed_f16,
+                        const float* bias, int32_t relu, void* out_pooled_nhwc_f16, ctl_stream_t stream) {
+  int rc = stem_fused_check(x_nchw, n, h, w, xpad, weight_packed_f16, bias, out_pooled_nhwc_f16);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  CTL_CUDA(launch_k(stem_pack_input_kernel, dim3((unsigned)(((size_t)n * h + 3) / 4)), dim3(256), 0, st, x_nchw, (int)n, (int)h,
+                    (int)w, static_cast<__half*>(xpad)));
+  return stem_pool_launch(n, h, w, xpad, weight_packed_f16, bias, relu, out_pooled_nhwc_f16, st);
+}
+
+int ctl_stem_pool_fused_u8(const void* x_u8_nhwc, int32_t n, int32_t h, int32_t w, const float* mean3_host, const float* std3_host,
+                           void* xpad, const void* weight_packed_f16, const float* bias, int32_t relu, void* out_pooled_nhwc_f16,
+                           ctl_stream_t stream) {
+  CTL_CHECK_ARG(mean3_host && std3_host, "null pointer");
+  CTL_CHECK_ARG(std3_host[0] > 0 && std3_host[1] > 0 && std3_host[2] > 0, "std must be positive");
+  int rc = stem_fused_check(x_u8_nhwc, n, h, w, xpad, weight_packed_f16, bias, out_pooled_nhwc_f16);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  CTL_CUDA(launch_k(stem_pack_input_u8_kernel, dim3((unsigned)(((size_t)n * h + 3) / 4)), dim3(256), 0, st,
+                    static_cast<const uint8_t*>(x_u8_nhwc), (int)n, (int)h, (int)w, mean3_host[0], mean3_host[1], mean3_host[2],
+                    std3_host[0], std3_host[1], std3_host[2], static_cast<__half*>(xpad)));
+  return stem_pool_launch(n, h, w, xpad, weight_packed_f16, bias, relu, out_pooled_nhwc_f16, st);
 }
 
 int ctl_maxpool3x3s2_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, void* out,

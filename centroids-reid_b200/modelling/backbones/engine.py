@@ -156,11 +156,36 @@ class TrunkEngine:
             a, h, w = self.bottlenecks(a, n, h, w)
             return self.tail(a, n, h, w, want_base, want_emb)
 
+    def forward_u8(self, images_u8: torch.Tensor, want_base: bool = False, want_emb: bool = False,
+                   pixel_mean=(0.485, 0.456, 0.406), pixel_std=(0.229, 0.224, 0.225)):
+        """images_u8: [B, H, W, 3] uint8 crops on the device (what a validation loader ships after `T.Resize`) -> the same
+        dict as forward(normalize_batch(images_u8)), bit for bit: ToTensor + Normalize (datasets/transforms/build.py:29-33)
+        are folded into the fused stem's input packing, the fp32 NCHW tensor is never written.  Shapes the fused stem does
+        not take (W > 128, H % 4 != 0) go through normalize_batch."""
+        N.require_cuda(images_u8)
+        if images_u8.dim() != 4 or images_u8.shape[3] != 3 or images_u8.dtype != torch.uint8:
+            raise ValueError(f"expected uint8 [B, H, W, 3], got {images_u8.dtype} {tuple(images_u8.shape)}")
+        n, H, W, _ = images_u8.shape
+        if not (H % 4 == 0 and W % 2 == 0 and W <= 128 and os.environ.get("CTL_STEM_FUSED", "1") == "1"):
+            from ...datasets.transforms import normalize_batch
+
+            return self.forward(normalize_batch(images_u8, pixel_mean, pixel_std), want_base, want_emb)
+        images_u8 = images_u8.contiguous()
+        self.launches_per_forward = 0
+        with torch.cuda.device(self.device):
+            a, n, h, w = self.stem(images_u8, u8_norm=(pixel_mean, pixel_std))
+            a, h, w = self.bottlenecks(a, n, h, w)
+            return self.tail(a, n, h, w, want_base, want_emb)
+
     # The three segments of the forward (bench.py captures each as its own CUDA graph to attribute the graph-mode step
     # time to the convolution kernels without leaving graph / PDL mode).
-    def stem(self, x: torch.Tensor):
-        """conv1 7x7/2 + bn1 (+ReLU for IBN-a) + maxpool 3x3/2 -> NHWC fp16 [n, hp, wp, 64]."""
-        n, _, H, W = x.shape
+    def stem(self, x: torch.Tensor, u8_norm=None):
+        """conv1 7x7/2 + bn1 (+ReLU for IBN-a) + maxpool 3x3/2 -> NHWC fp16 [n, hp, wp, 64].  `u8_norm` = (mean, std):
+        x is a uint8 [n, H, W, 3] batch, normalised inside the fused stem's packing kernel (forward_u8)."""
+        if u8_norm is not None:
+            n, H, W, _ = x.shape
+        else:
+            n, _, H, W = x.shape
         L = N.lib()
         h, w = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
         hp, wp = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
@@ -172,8 +197,16 @@ class TrunkEngine:
                 pad = torch.zeros(L.ctl_stem_pad_bytes(n, H, W), dtype=torch.uint8, device=self.device)
                 self._stem_pad[(n, H, W)] = pad
             with self._timed("stem_pool", 2.0 * n * h * w * 64 * 147, n * (3.0 * H * W * 4 + hp * wp * 64 * 2)):
-                N.check(L.ctl_stem_pool_fused(x.data_ptr(), n, H, W, pad.data_ptr(), self.stem_w3.data_ptr(),
-                                              self.stem_b.data_ptr(), int(self.ibn), a.data_ptr(), N.stream_ptr()))
+                if u8_norm is not None:
+                    import ctypes as C
+
+                    mean = (C.c_float * 3)(*[float(v) for v in u8_norm[0]])
+                    std = (C.c_float * 3)(*[float(v) for v in u8_norm[1]])
+                    N.check(L.ctl_stem_pool_fused_u8(x.data_ptr(), n, H, W, mean, std, pad.data_ptr(), self.stem_w3.data_ptr(),
+                                                     self.stem_b.data_ptr(), int(self.ibn), a.data_ptr(), N.stream_ptr()))
+                else:
+                    N.check(L.ctl_stem_pool_fused(x.data_ptr(), n, H, W, pad.data_ptr(), self.stem_w3.data_ptr(),
+                                                  self.stem_b.data_ptr(), int(self.ibn), a.data_ptr(), N.stream_ptr()))
             self.launches_per_forward += 1  # pack + conv/pool kernels
         else:
             s = torch.empty(n, h, w, 64, dtype=torch.float16, device=self.device)

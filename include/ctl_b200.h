@@ -270,6 +270,13 @@ int ctl_stem_conv7x7_tc(const float* x_nchw, int32_t n, int32_t h, int32_t w, co
 size_t ctl_stem_pad_bytes(int32_t n, int32_t h, int32_t w);
 int ctl_stem_pool_fused(const float* x_nchw, int32_t n, int32_t h, int32_t w, void* xpad, const void* weight_packed_f16,
                         const float* bias, int32_t relu, void* out_pooled_nhwc_f16, ctl_stream_t stream);
+/* ctl_stem_pool_fused from uint8 HWC crops [n][h][w][3]: ToTensor + Normalize ((u / 255 - mean) / std, IEEE fp32 -- the
+ * arithmetic of ctl_augment_batch_u8 without flip / crop / erasing; datasets/transforms/build.py:29-33) folded into the
+ * stem's input packing, so a validation loader that ships uint8 crops never materialises the fp32 NCHW tensor.
+ * Bit-identical to ctl_augment_batch_u8 (neutral parameters) followed by ctl_stem_pool_fused. */
+int ctl_stem_pool_fused_u8(const void* x_u8_nhwc, int32_t n, int32_t h, int32_t w, const float* mean3_host,
+                           const float* std3_host, void* xpad, const void* weight_packed_f16, const float* bias, int32_t relu,
+                           void* out_pooled_nhwc_f16, ctl_stream_t stream);
 int ctl_maxpool3x3s2_nhwc_f16(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, void* out,
                               ctl_stream_t stream);
 int ctl_gap_bn_nhwc_f16(const void* x, int32_t n, int32_t hw, int32_t c, const float* bn_scale, const float* bn_shift,

@@ -320,3 +320,24 @@ def test_native_trunk_handle_matches_engine(ibn, hw, n):
     bad = {k: v for k, v in sd.items() if k != "layer2.1.bn2.running_var"}
     with pytest.raises(ValueError, match="layer2.1.bn2.running_var"):
         nat.pack(bad)
+
+
+@pytest.mark.parametrize("ibn,shape", [(False, (6, 256, 128)), (True, (3, 64, 32)), (False, (2, 96, 160))])
+def test_forward_u8_matches_normalize_then_forward(ibn, shape):
+    """TrunkEngine.forward_u8 (ToTensor + Normalize folded into the fused stem's input packing, ctl_stem_pool_fused_u8)
+    == forward(normalize_batch(images)) bit for bit: the same IEEE (u / 255 - mean) / std, rounded to fp16 once.
+    (96 x 160: wider than the fused stem takes -> the normalize_batch route.)"""
+    from ctl_b200.datasets.transforms import normalize_batch
+    from ctl_b200.modelling.backbones.engine import TrunkEngine
+
+    n, H, W = shape
+    sd = O.make_trunk_state(seed=9, ibn=ibn)
+    head = dict(weight=torch.rand(2048) + 0.5, bias=torch.randn(2048) * 0.1, running_mean=torch.randn(2048) * 0.1,
+                running_var=torch.rand(2048) + 0.5)
+    eng = TrunkEngine(sd, "cuda", ibn=ibn, bn_head=head)
+    img = torch.randint(0, 256, (n, H, W, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(4)).cuda()
+    a = eng.forward_u8(img, want_emb=True)
+    b = eng.forward(normalize_batch(img), want_emb=True)
+    assert torch.equal(a["global_feat"], b["global_feat"]) and torch.equal(a["emb"], b["emb"])
+    with pytest.raises(ValueError, match="uint8"):
+        eng.forward_u8(img.float())
