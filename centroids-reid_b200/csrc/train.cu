@@ -608,15 +608,16 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const __half*
   }
   if (lane_row < lanes) {
     const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
-    // two rows per iteration: 4-6 independent 16-byte loads in flight per thread (the one-row loop ran at 0.40 of the HBM
-    // roofline in profiles/r2g_train_launches_summary.txt); rows are accumulated in the same order as before
-    auto one = [&](const uint4& vg, const uint4& vy, const uint4& vz, size_t off) {
+    // (one row per iteration: a two-row version was measured in round 2 -- 78 registers, 3 instead of 4 blocks per SM,
+    // 2.85 -> 3.04 ms per step; capped at 64 registers it spilled.  The kernel is latency-bound on its small layers.)
+    for (long long r = r0 + lane_row; r < r1; r += lanes) {
+      const size_t off = (size_t)r * pitch + group * 8;
       float g[8], yv[8];
-      unpack8(vg, g);
-      unpack8(vy, yv);
+      unpack8(*reinterpret_cast<const uint4*>(dz + off), g);
+      unpack8(*reinterpret_cast<const uint4*>(y + off), yv);
       if (z) {
         float zv[8];
-        unpack8(vz, zv);
+        unpack8(*reinterpret_cast<const uint4*>(z + off), zv);
 #pragma unroll
         for (int i = 0; i < 8; ++i) g[i] = zv[i] > 0.f ? g[i] : 0.f;
         *reinterpret_cast<uint4*>(g_out + off) = pack8(g);
@@ -626,25 +627,6 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const __half*
         acc[0][i] += g[i];
         acc[1][i] = fmaf(g[i], (yv[i] - mu[i]) * is[i], acc[1][i]);
       }
-    };
-    long long r = r0 + lane_row;
-    for (; r + lanes < r1; r += 2LL * lanes) {
-      const size_t off0 = (size_t)r * pitch + group * 8, off1 = (size_t)(r + lanes) * pitch + group * 8;
-      const uint4 g0 = *reinterpret_cast<const uint4*>(dz + off0), g1 = *reinterpret_cast<const uint4*>(dz + off1);
-      const uint4 y0 = *reinterpret_cast<const uint4*>(y + off0), y1 = *reinterpret_cast<const uint4*>(y + off1);
-      uint4 z0 = make_uint4(0, 0, 0, 0), z1 = z0;
-      if (z) {
-        z0 = *reinterpret_cast<const uint4*>(z + off0);
-        z1 = *reinterpret_cast<const uint4*>(z + off1);
-      }
-      one(g0, y0, z0, off0);
-      one(g1, y1, z1, off1);
-    }
-    if (r < r1) {
-      const size_t off = (size_t)r * pitch + group * 8;
-      const uint4 g0 = *reinterpret_cast<const uint4*>(dz + off), y0 = *reinterpret_cast<const uint4*>(y + off);
-      const uint4 z0 = z ? *reinterpret_cast<const uint4*>(z + off) : make_uint4(0, 0, 0, 0);
-      one(g0, y0, z0, off);
     }
     bn_block_store<2>(acc, group, lane_row, lanes, C, part + (size_t)blockIdx.x * 2 * C, sred);
   }
