@@ -121,9 +121,9 @@ def dist_matrix(x: torch.Tensor, y: torch.Tensor, dist: str = "euclidean", norma
 
 def topk(qp: Planes, gp: Planes, k: int, g_index_offset: int = 0, exact_threshold_pass: bool = False):
     """k nearest gallery rows per query in ascending (distance, index) order.
-    Returns (idx int64 [nq, k], dist float32 [nq, k], overflow flag) on the device.  The threshold pass runs with the leading fp16
-    product + a rigorous error bound unless `exact_threshold_pass` (identical results; the flag only trades a slightly
-    larger candidate set for a third of that pass's tensor work)."""
+    Returns (idx int64 [nq, k], dist float32 [nq, k], overflow flag) on the device.  The threshold pass runs every s-th
+    gallery tile only (any subset of the gallery bounds the k-th distance from above; ctl_dist_subset_stride) unless
+    `exact_threshold_pass`: identical results, the subset only trades longer candidate lists for ~2/3 of that pass."""
     if qp.order is not None or gp.order is not None:
         raise ValueError("topk() takes planes in the caller's row order (use topk_and_eval for pid-sorted planes)")
     L = N.lib()
