@@ -139,3 +139,33 @@ def test_trainer_handle_plans_its_workspace_without_a_gpu():
         assert L.ctl_train_backward(h, df, C.c_float(1024.0), df, 1 << 30, None) == -1  # no forward yet
         assert b"forward" in L.ctl_last_error()
         L.ctl_trainer_destroy(h)
+
+
+def test_identity_orders_and_encoded_ids_on_the_host():
+    """retrieval.pid_order is a stable sort by identity; encode_ids(q_order=, g_order=) hands the kernels the identity
+    arrays in the planes' row order (dense labels keep the identity order, so sorted rows give monotone labels -- what the
+    tile-range test of ctl_dist_worklist relies on); pid_order_pays switches by problem size."""
+    import numpy as np
+
+    from ctl_b200 import retrieval as R
+
+    rng = np.random.default_rng(3)
+    q_pid, g_pid = rng.integers(100, 160, 300), rng.integers(100, 160, 2000)
+    q_cam, g_cam = rng.integers(0, 6, 300), rng.integers(0, 6, 2000)
+    qo, go = R.pid_order(q_pid), R.pid_order(g_pid)
+    assert np.array_equal(np.sort(qo), np.arange(300)) and (np.diff(q_pid[qo]) >= 0).all()
+    same = q_pid[qo][1:] == q_pid[qo][:-1]
+    assert (np.diff(qo)[same] > 0).all(), "stable: equal identities keep the caller's order"
+    plain = R.encode_ids(q_pid, g_pid, q_cam, g_cam, False, "cpu")
+    srt = R.encode_ids(q_pid, g_pid, q_cam, g_cam, False, "cpu", q_order=qo, g_order=go)
+    assert np.array_equal(srt.q_pid.numpy(), plain.q_pid.numpy()[qo]) and np.array_equal(srt.g_pid.numpy(), plain.g_pid.numpy()[go])
+    assert np.array_equal(srt.q_cam.numpy(), plain.q_cam.numpy()[qo]) and np.array_equal(srt.g_mask.numpy(), plain.g_mask.numpy()[go])
+    assert srt.max_pos == plain.max_pos
+    assert (np.diff(srt.q_pid.numpy()) >= 0).all() and (np.diff(srt.g_pid.numpy()) >= 0).all()
+    # sorted operands: few 128 x 128 tiles have intersecting identity ranges; unsorted: all of them
+    def hot_fraction(qp, gp):
+        qr = [(qp[i:i + 128].min(), qp[i:i + 128].max()) for i in range(0, len(qp), 128)]
+        gr = [(gp[i:i + 128].min(), gp[i:i + 128].max()) for i in range(0, len(gp), 128)]
+        return np.mean([not (b[1] < a[0] or b[0] > a[1]) for a in qr for b in gr])
+    assert hot_fraction(srt.q_pid.numpy(), srt.g_pid.numpy()) < 0.5 < hot_fraction(plain.q_pid.numpy(), plain.g_pid.numpy())
+    assert not R.pid_order_pays(3368, 15913) and R.pid_order_pays(50000, 25000)
